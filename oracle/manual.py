@@ -1,0 +1,311 @@
+"""Explicit-formula oracle (numpy) for the gradients of the path-space losses.
+
+TEST INFRASTRUCTURE -- not product code (see oracle/ref_port.py for the rules).  Where ref_port.py restates the
+reference *procedurally* (rollout + autograd), this file restates the closed-form gradient structure the CUDA
+kernels implement, in float64 by default, so that (i) the derivations in DESIGN.md are pinned against the
+reference fixtures and (ii) tests get condition-aware tolerances from a high-precision evaluation.
+
+  Mode A  detached forward (solver.py:468-469): X is theta-independent, per-(k,n) VJPs only.
+          cotangent on Z_n:  zeta = wY*(sqrt(dt)*xi_{n+1} + [not adaptive]*Z*dt) + wZ*Z*dt
+  Mode B  attached forward, relative entropy (solver.py:180, :486): discrete adjoint lambda_n.
+  Mode D  diffusion loss (solver.py:1076-1163), h == 0: value + x-tangent forward, reverse of both.
+
+Parity pin: tests/test_oracle_golden.py checks all three against tests/golden/*.npz (reference outputs).
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------ network spec
+class Net:
+    """kind 'densenet' (relu^2, dense concat; W (fan_in, out)) or 'mlp_tanh' (nn.Linear W (out, in))."""
+
+    def __init__(self, kind, dims, theta, dtype=np.float64):
+        self.kind, self.dims = kind, list(dims)
+        self.W, self.b = [], []
+        off = 0
+        theta = np.asarray(theta, dtype=dtype)
+        for i in range(len(dims) - 1):
+            fan_in = sum(dims[:i + 1]) if kind == "densenet" else dims[i]
+            n = fan_in * dims[i + 1]
+            if kind == "densenet":
+                self.W.append(theta[off:off + n].reshape(fan_in, dims[i + 1]))
+            else:
+                self.W.append(theta[off:off + n].reshape(dims[i + 1], fan_in).T)   # store as (in, out)
+            off += n
+            self.b.append(theta[off:off + dims[i + 1]])
+            off += dims[i + 1]
+        self.n_params = off
+        assert off == theta.size, (off, theta.size)
+
+    def act(self, pre):
+        return np.maximum(pre, 0) ** 2 if self.kind == "densenet" else np.tanh(pre)
+
+    def dact(self, pre, h):
+        return 2 * np.maximum(pre, 0) if self.kind == "densenet" else 1 - h ** 2
+
+    def d2act(self, pre, h):
+        return 2.0 * (pre > 0) if self.kind == "densenet" else -2 * h * (1 - h ** 2)
+
+    def forward(self, a0):
+        """returns output and the tape [(a_l, pre_l, h_l)]."""
+        a, tape = a0, []
+        L = len(self.W)
+        for l in range(L):
+            pre = a @ self.W[l] + self.b[l]
+            if l == L - 1:
+                tape.append((a, pre, None))
+                return pre, tape
+            h = self.act(pre)
+            tape.append((a, pre, h))
+            a = np.concatenate([a, h], 1) if self.kind == "densenet" else h
+
+    def vjp(self, tape, zeta, want_dx=False):
+        """theta-gradient (flat, parameter order) of sum(out*zeta); optionally d/d a0."""
+        L = len(self.W)
+        gW, gb = [None] * L, [None] * L
+        delta = zeta
+        abar = None                                  # cotangent on the (concat) activation row
+        for l in range(L - 1, -1, -1):
+            a, pre, h = tape[l]
+            if l < L - 1:
+                if self.kind == "densenet":
+                    hbar = abar[:, a.shape[1]:]
+                    abar = abar[:, :a.shape[1]]
+                else:
+                    hbar, abar = abar, None
+                delta = hbar * self.dact(pre, h)
+            gW[l] = a.T @ delta
+            gb[l] = delta.sum(0)
+            contrib = delta @ self.W[l].T
+            abar = contrib if abar is None else abar + contrib
+        flat = []
+        for l in range(L):
+            flat.append((gW[l] if self.kind == "densenet" else gW[l].T).reshape(-1))
+            flat.append(gb[l])
+        g = np.concatenate(flat)
+        return (g, abar) if want_dx else g
+
+    # ---- forward-mode tangent + its reverse (diffusion loss)
+    def forward_tangent(self, a0, da0):
+        a, da, tape = a0, da0, []
+        L = len(self.W)
+        for l in range(L):
+            pre = a @ self.W[l] + self.b[l]
+            dpre = da @ self.W[l]
+            if l == L - 1:
+                tape.append((a, da, pre, dpre, None))
+                return pre, dpre, tape
+            h = self.act(pre)
+            dh = self.dact(pre, h) * dpre
+            tape.append((a, da, pre, dpre, h))
+            if self.kind == "densenet":
+                a, da = np.concatenate([a, h], 1), np.concatenate([da, dh], 1)
+            else:
+                a, da = h, dh
+
+    def vjp_tangent(self, tape, ybar, dybar):
+        """theta-gradient of sum(y*ybar + y'*dybar) for the pair (value y, tangent y')."""
+        L = len(self.W)
+        gW, gb = [None] * L, [None] * L
+        pbar, dpbar = ybar, dybar
+        abar = dabar = None
+        for l in range(L - 1, -1, -1):
+            a, da, pre, dpre, h = tape[l]
+            if l < L - 1:
+                if self.kind == "densenet":
+                    hbar, dhbar = abar[:, a.shape[1]:], dabar[:, a.shape[1]:]
+                    abar, dabar = abar[:, :a.shape[1]], dabar[:, :a.shape[1]]
+                else:
+                    hbar, dhbar, abar, dabar = abar, dabar, None, None
+                d1 = self.dact(pre, h)
+                dpbar = dhbar * d1
+                pbar = hbar * d1 + dhbar * self.d2act(pre, h) * dpre
+            gW[l] = a.T @ pbar + da.T @ dpbar
+            gb[l] = pbar.sum(0)
+            c, dc = pbar @ self.W[l].T, dpbar @ self.W[l].T
+            abar = c if abar is None else abar + c
+            dabar = dc if dabar is None else dabar + dc
+        flat = []
+        for l in range(L):
+            flat.append((gW[l] if self.kind == "densenet" else gW[l].T).reshape(-1))
+            flat.append(gb[l])
+        return np.concatenate(flat)
+
+
+# ------------------------------------------------------------------ problems (numpy)
+class Problem:
+    def __init__(self, kind, d, dtype=np.float64, A=None, B=None, eta_=None, kappa_=None):
+        self.kind, self.d = kind, d
+        I = np.eye(d, dtype=dtype)
+        self.A = -I if A is None else np.asarray(A, dtype)
+        self.B = I if B is None else np.asarray(B, dtype)
+        if kind == "dwm":
+            self.B = I
+            self.eta_, self.kappa_ = np.asarray(eta_, dtype), np.asarray(kappa_, dtype)
+        if kind == "heat":
+            self.B = np.sqrt(dtype(2.0)) * I
+        self.P, self.R, self.alpha = 0.5 * I, I, np.ones(d, dtype)
+
+    def b(self, x):
+        if self.kind in ("llgc", "lqgc"):
+            return x @ self.A.T
+        if self.kind == "dwm":
+            return -4.0 * self.kappa_ * x * (x ** 2 - 1)
+        return np.zeros_like(x)
+
+    def Jb_T_vec(self, x, lam):          # J_b(x)^T lam, row convention
+        if self.kind in ("llgc", "lqgc"):
+            return lam @ self.A
+        return -4.0 * self.kappa_ * (3 * x ** 2 - 1) * lam
+
+    def f(self, x):
+        return ((x @ self.P.T) * x).sum(1) if self.kind == "lqgc" else np.zeros(x.shape[0], x.dtype)
+
+    def grad_f(self, x):
+        return x @ (self.P + self.P.T) if self.kind == "lqgc" else np.zeros_like(x)
+
+    def g(self, x):
+        if self.kind == "llgc":
+            return x @ self.alpha
+        if self.kind == "lqgc":
+            return ((x @ self.R.T) * x).sum(1)
+        return (self.eta_ * (x - 1) ** 2).sum(1)
+
+    def grad_g(self, x):
+        if self.kind == "llgc":
+            return np.tile(self.alpha, (x.shape[0], 1))
+        if self.kind == "lqgc":
+            return x @ (self.R + self.R.T)
+        return 2 * self.eta_ * (x - 1)
+
+
+def net_input(X, n, dt, time_mode):
+    t = np.full((X.shape[0], 1), np.float32(n) * np.float32(dt), dtype=X.dtype)
+    if time_mode == "first":
+        return np.concatenate([t, X], 1)
+    return X
+
+
+# ------------------------------------------------------------------ HJB rollout (solver.py:440-489)
+def rollout(problem, nets, xi, dt, N, X0, adaptive=True, y0=0.0, time_mode="first"):
+    """nets: one Net (inner) or a list of N Nets (outer). xi (K,d,N+1). Returns dict with the X path."""
+    K = xi.shape[0]
+    dtype = xi.dtype
+    s = np.sqrt(dtype.type(dt))
+    X = np.tile(np.asarray(X0, dtype), (K, 1))
+    Y = np.full(K, y0, dtype)
+    Zsum = np.zeros(K, dtype)
+    path, Zs = [X], []
+    for n in range(N):
+        net = nets[n] if isinstance(nets, list) else nets
+        Z, _ = net.forward(net_input(X, n, dt, time_mode))
+        c = -Z if adaptive else np.zeros_like(Z)
+        x = xi[:, :, n + 1]
+        X = X + (problem.b(X) + c @ problem.B.T) * dt + (x @ problem.B.T) * s
+        fX = problem.f(X)
+        zz = (Z ** 2).sum(1)
+        Y = Y + ((0.5 * zz + fX) + (Z * c).sum(1)) * dt + (Z * x).sum(1) * s
+        Zsum = Zsum + (0.5 * zz + fX) * dt
+        path.append(X)
+        Zs.append(Z)
+    return dict(X=X, Y=Y, Zsum=Zsum, gX=problem.g(X), path=path, Z=Zs)
+
+
+def loss_and_weights(loss_method, Y, gX, Zsum, adaptive=True):
+    """Loss value and per-path cotangents (wY on Y_N, wZ on Z_sum) -- solver.py:164-192 differentiated by hand."""
+    K = Y.shape[0]
+    D = Y - gX
+    zero = np.zeros_like(Y)
+    if loss_method == "moment":
+        return (D ** 2).mean(), 2 * D / K, zero
+    if loss_method == "log-variance":
+        return (D ** 2).mean() - D.mean() ** 2, 2 * (D - D.mean()) / K, zero
+    if loss_method == "variance":
+        E = np.exp(D)
+        return E.var(ddof=1), 2 * (E - E.mean()) * E / (K - 1), zero
+    if loss_method == "cross_entropy":
+        E = np.exp(D) if adaptive else np.exp(-gX)
+        return (Y * E).mean(), E / K, zero
+    if loss_method == "relative_entropy":
+        return (Zsum + gX).mean(), zero, np.full_like(Y, 1.0 / K)
+    raise ValueError(loss_method)
+
+
+def grad_mode_a(problem, nets, xi, dt, N, X0, wY, wZ, adaptive=True, time_mode="first", y0=0.0):
+    """SURVEY.md A.3 generalised: detached forward, one VJP per (k, n)."""
+    dtype = xi.dtype
+    s = np.sqrt(dtype.type(dt))
+    ro = rollout(problem, nets, xi, dt, N, X0, adaptive, y0, time_mode)
+    outer = isinstance(nets, list)
+    grads = [0.0] * (N if outer else 1)
+    for n in range(N):
+        net = nets[n] if outer else nets
+        Z, tape = net.forward(net_input(ro["path"][n], n, dt, time_mode))
+        zeta = wY[:, None] * (s * xi[:, :, n + 1] + (0.0 if adaptive else 1.0) * Z * dt) + wZ[:, None] * Z * dt
+        g = net.vjp(tape, zeta)
+        grads[n if outer else 0] = grads[n if outer else 0] + g
+    return np.concatenate([np.atleast_1d(g) for g in grads]), ro
+
+
+def grad_mode_b(problem, net, xi, dt, N, X0, time_mode="first"):
+    """relative entropy, attached adaptive forward, discrete adjoint (w = 1/K)."""
+    K = xi.shape[0]
+    ro = rollout(problem, net, xi, dt, N, X0, True, 0.0, time_mode)
+    lam = problem.grad_g(ro["X"]) / K
+    grad = 0.0
+    x_lo = 1 if time_mode == "first" else 0
+    for n in range(N - 1, -1, -1):
+        Xn = ro["path"][n]
+        lam = lam + problem.grad_f(ro["path"][n + 1]) * dt / K
+        Z, tape = net.forward(net_input(Xn, n, dt, time_mode))
+        zeta = Z * dt / K - dt * (lam @ problem.B)
+        g, dx = net.vjp(tape, zeta, want_dx=True)
+        grad = grad + g
+        lam = lam + dt * problem.Jb_T_vec(Xn, lam) + dx[:, x_lo:x_lo + problem.d]
+    return grad, ro
+
+
+# ------------------------------------------------------------------ diffusion loss (solver.py:1062-1163, h == 0)
+def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0):
+    """Value and theta-gradient of the diffusion loss, unbounded domain, non-adaptive; net input is [X, t]."""
+    dtype = X0.dtype
+    K, d = X0.shape
+    dt = dtype.type(np.float32(dt))
+    s = np.sqrt(dt)
+    Bt = problem.B.T
+    # terminal-condition term on the first K_boundary interior samples (:1063-1064)
+    aT = np.concatenate([X0[:K_boundary], np.full((K_boundary, 1), T, dtype)], 1)
+    vT, tapeT = net.forward(aT)
+    fT = (X0[:K_boundary] ** 2).sum(1)
+    rT = vT[:, 0] - fT
+    loss = alpha[1] * (rT ** 2).mean()
+    grad = net.vjp(tapeT, (alpha[1] * 2 * rT / K_boundary)[:, None])
+    # pass 1: values
+    X, t = X0.copy(), t0.reshape(-1).copy()
+    v0, tape0 = net.forward(np.concatenate([X, t[:, None]], 1))
+    Y = v0[:, 0].copy()
+    stopped = np.zeros(K, bool)
+    steps = []
+    K_count = 0
+    for n in range(N):
+        if not (~stopped).any():
+            break
+        act = (~stopped) & ((t.astype(np.float32) + np.float32(dt)) <= np.float32(T))
+        v = (xis[n] @ Bt) * s                                      # direction B xi sqrt(dt)
+        a0 = np.concatenate([X, t[:, None]], 1)
+        da0 = np.concatenate([v, np.zeros((K, 1), dtype)], 1)
+        _, dy, tape = net.forward_tangent(a0, da0)
+        Y = Y + dy[:, 0] * act
+        steps.append((tape, act.copy()))
+        X = X + (problem.b(X) * dt + v) * act[:, None]
+        t = t + dt * act
+        K_count += int(act.sum())
+        stopped |= ~act
+    vE, tapeE = net.forward(np.concatenate([X, t[:, None]], 1))
+    r = vE[:, 0] - Y
+    loss = loss + alpha[0] * (r ** 2).mean()
+    w = alpha[0] * 2 * r / K
+    grad = grad + net.vjp(tapeE, w[:, None]) - net.vjp(tape0, w[:, None])
+    for tape, act in steps:
+        grad = grad + net.vjp_tangent(tape, np.zeros((K, 1), dtype), (-w * act)[:, None])
+    return dict(loss=loss, grad=grad, K_count=K_count, X=X, t=t, Y=Y)

@@ -1,0 +1,366 @@
+"""CPU oracle for the path-space hot path (TEST INFRASTRUCTURE -- not product code).
+
+A from-scratch PyTorch-CPU restatement of the reference algorithm
+(lorenzrichter/path-space-PDE-solver) for the one hot path this repository
+accelerates.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this module; the product
+package (``path-space-pde-solver_b200/pspde``) never does.
+
+Parity pin: every function below is checked in ``tests/test_oracle_golden.py``
+against golden vectors produced by the UNMODIFIED reference run on CPU in the
+build container (``tests/golden/make_golden.py`` + ``tests/golden/refload.py``).
+The reference ships no tests or fixtures of its own.
+
+Reference lines restated here
+  * networks ............ function_space.py:116-140 (DenseNet), :177-195 (MySequential)
+  * problems ............ problems.py:14-65 (LLGC), :118-175 (LQGC),
+                          :285-334 (DoubleWell_multidim), :1733-1764 (HeatEquation)
+  * HJB rollout ......... solver.py:364-382 (init), :349-356 (Z_n_), :440-494 (loop)
+  * losses .............. solver.py:164-192
+  * backward ............ solver.py:202-223 (autograd of the loss)
+  * diffusion loss ...... solver.py:1040-1064, :1076-1163, :1187
+  * importance sampling . utilities.py:287-359
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch as pt
+
+
+# --------------------------------------------------------------------------- networks
+def densenet_init(d_in, d_out, arch=(30, 30), seed=42, dtype=pt.float32):
+    """Parameter list [W0, b0, W1, b1, ...] with the reference's init and draw order
+    (function_space.py:117-126): W_i ~ 0.1*N(0,1) of shape (sum(dims[:i+1]), dims[i+1]), b_i = 0."""
+    pt.manual_seed(seed)
+    dims = [d_in] + list(arch) + [d_out]
+    params = []
+    for i in range(len(dims) - 1):
+        params.append((pt.randn(sum(dims[:i + 1]), dims[i + 1]) * 0.1).to(dtype))
+        params.append(pt.zeros(dims[i + 1], dtype=dtype))
+    return params
+
+
+def densenet_forward(params, x):
+    """Dense-concat MLP, activation relu(.)**2 (function_space.py:133-140)."""
+    n_layers = len(params) // 2
+    for i in range(n_layers):
+        W, b = params[2 * i], params[2 * i + 1]
+        pre = x @ W + b
+        if i == n_layers - 1:
+            return pre
+        x = pt.cat([x, pt.relu(pre) ** 2], dim=1)
+    return x
+
+
+def mlp_init(d_in, d_out, seed=123, dtype=pt.float32):
+    """[W0, b0, W1, b1, W2, b2] in nn.Linear layout (out, in) for dims [d_in, 30, 30, d_out];
+    nn.Linear default init is drawn first, then overwritten by N(0, 0.01^2) weight-then-bias per layer
+    (function_space.py:178-188) -- the draw order matters for bit-equal initial weights."""
+    pt.manual_seed(seed)
+    dims = [d_in, 30, 30, d_out]
+    lins = [pt.nn.Linear(dims[i], dims[i + 1]) for i in range(3)]
+    for lin in lins:
+        pt.nn.init.normal_(lin.weight, 0, 0.01)
+        pt.nn.init.normal_(lin.bias, 0, 0.01)
+    out = []
+    for lin in lins:
+        out += [lin.weight.detach().clone().to(dtype), lin.bias.detach().clone().to(dtype)]
+    return out
+
+
+def mlp_forward(params, x):
+    """tanh MLP (function_space.py:190-195)."""
+    n_layers = len(params) // 2
+    for i in range(n_layers):
+        x = x @ params[2 * i].t() + params[2 * i + 1]
+        if i < n_layers - 1:
+            x = pt.tanh(x)
+    return x
+
+
+NET_FORWARD = {"densenet": densenet_forward, "mlp_tanh": mlp_forward}
+
+
+# --------------------------------------------------------------------------- problems
+def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
+    """Problem functors b, sigma(B), h, f, g as closures over plain tensors."""
+    p = SimpleNamespace(kind=kind, d=d)
+    one = pt.ones(d, dtype=dtype)
+    if kind in ("llgc", "lqgc"):
+        # problems.py:18-27 / :122-139
+        seed = kw.get("seed", 42)
+        off = kw.get("off_diag", 0)
+        pt.manual_seed(seed)
+        p.T = 5 if T is None else T
+        p.A = (-pt.eye(d) + off * pt.randn(d, d)).to(dtype)
+        p.B = (pt.eye(d) + off * pt.randn(d, d)).to(dtype)
+        p.X_0 = pt.zeros(d, dtype=dtype)
+        p.b = lambda x: (p.A @ x.t()).t()
+        if kind == "llgc":
+            p.alpha = pt.ones(d, 1, dtype=dtype)
+            p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype)
+            p.h = lambda t, x, y, z: -0.5 * (z ** 2).sum(1)            # problems.py:45-46
+            p.g = lambda x: (x @ p.alpha)[:, 0]                         # :48-49
+        else:
+            p.P = 0.5 * pt.eye(d, dtype=dtype)
+            p.Q = 0.5 * pt.eye(d, dtype=dtype)
+            p.R = pt.eye(d, dtype=dtype)
+            p.f = lambda x, t: (x.t() * (p.P @ x.t())).sum(0)           # :160-161
+            p.g = lambda x: (x.t() * (p.R @ x.t())).sum(0)              # :163-164
+            p.h = lambda t, x, y, z: -0.5 * (z ** 2).sum(1) - p.f(x, t)  # :166-167
+    elif kind == "dwm":
+        # problems.py:289-303, 311-334
+        d_1 = kw.get("d_1", d)
+        d_2 = kw.get("d_2", 0)
+        assert d_1 + d_2 == d
+        p.T = 1 if T is None else T
+        p.eta_ = pt.tensor([kw.get("eta", 1)] * d_1 + [1.0] * d_2, dtype=dtype)
+        p.kappa_ = pt.tensor([kw.get("kappa", 1)] * d_1 + [1.0] * d_2, dtype=dtype)
+        p.B = pt.eye(d, dtype=dtype)
+        p.X_0 = -pt.ones(d, dtype=dtype)
+        p.b = lambda x: -(4.0 * p.kappa_ * (x * (x ** 2 - one)))
+        p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype)
+        p.h = lambda t, x, y, z: -0.5 * (z ** 2).sum(1)
+        p.g = lambda x: (p.eta_ * (x - one) ** 2).sum(1)
+    elif kind == "heat":
+        # problems.py:1734-1758 (f is the *terminal* condition here)
+        p.T = 1 if T is None else T
+        p.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(dtype)
+        p.boundary_distance = 1.0
+        p.b = lambda x: pt.zeros_like(x)
+        p.h = lambda t, x, y, z: pt.zeros(x.shape[0], dtype=dtype)
+        p.f = lambda x: (x ** 2).sum(1)
+        p.v_true = lambda x, t: (x ** 2).sum(1) + 2 * (p.T - t) * d
+    else:
+        raise ValueError(kind)
+    return p
+
+
+# --------------------------------------------------------------------------- HJB rollout
+def control_eval(net, params, X, n, delta_t, time_approx, N):
+    """Z_n_ for approx_method='control' (solver.py:349-356)."""
+    if time_approx == "outer":
+        n = max(0, min(n, N - 1))
+        return NET_FORWARD[net](params[n], X)
+    t_col = pt.ones(X.shape[0], 1, dtype=X.dtype) * n * delta_t
+    return NET_FORWARD[net](params, pt.cat([t_col, X], 1))
+
+
+def hjb_rollout(problem, net, params, xi, delta_t, N, time_approx="inner", adaptive=True,
+                detach_forward=True, want_zsum=True, y0=None, X0=None, store_path=False):
+    """N Euler-Maruyama steps of (X, Y, Z_sum) (solver.py:440-489).
+
+    xi has the reference layout (K, d, N+1); slice n+1 drives step n (:472).
+    delta_t is a 0-dim tensor so that t_n, *dt and *sqrt(dt) round as in the reference (:39-40)."""
+    K = xi.shape[0]
+    dtype = xi.dtype
+    dt = pt.as_tensor(delta_t, dtype=dtype)
+    sq = pt.sqrt(dt)
+    X = (problem.X_0 if X0 is None else X0).repeat(K, 1) if (X0 is None or X0.dim() == 1) else X0
+    Y = pt.zeros(K, dtype=dtype) if y0 is None else y0.expand(K) + pt.zeros(K, dtype=dtype)
+    Zsum = pt.zeros(K, dtype=dtype)
+    path = [X] if store_path else None
+    B = problem.B
+    for n in range(N):
+        Z = control_eval(net, params, X, n, dt, time_approx, N)                     # :449
+        c = -Z.t() if adaptive else pt.zeros(problem.d, K, dtype=dtype)             # :451-456
+        if detach_forward:
+            c = c.detach()                                                          # :468-469
+        xin = xi[:, :, n + 1]
+        X = X + (problem.b(X) + (B @ c).t()) * dt + (B @ xin.t()).t() * sq          # :471-472
+        Y = (Y + (-problem.h(dt * n, X, Y, Z) + (Z * c.t()).sum(1)) * dt
+             + (Z * xin).sum(1) * sq)                                               # :477-478
+        if want_zsum:
+            Zsum = Zsum + (0.5 * (Z ** 2).sum(1) + problem.f(X, n * dt)) * dt       # :486
+        if store_path:
+            path.append(X)
+    return X, Y, Zsum, path
+
+
+def hjb_loss(loss_method, problem, X, Y, Zsum, adaptive=True):
+    """solver.py:164-192 (the variants that are live code)."""
+    gX = problem.g(X)
+    if loss_method == "moment":
+        return ((Y - gX) ** 2).mean()
+    if loss_method == "log-variance":
+        return ((Y - gX) ** 2).mean() - (Y - gX).mean() ** 2
+    if loss_method == "variance":
+        return pt.var(pt.exp(-gX + Y))
+    if loss_method == "relative_entropy":
+        return (Zsum + gX).mean()
+    if loss_method == "cross_entropy":
+        if adaptive:
+            return (Y * pt.exp(-gX + Y.detach())).mean()
+        return (Y * pt.exp(-gX)).mean()
+    raise ValueError(loss_method)
+
+
+def flat_params(params, time_approx="inner"):
+    if time_approx == "outer":
+        return [q for net in params for q in net]
+    return list(params)
+
+
+def hjb_iteration(problem, net, params, xi, delta_t, N, loss_method="log-variance", time_approx="inner",
+                  adaptive=True, detach_forward=True, y0=None):
+    """One training iteration's loss and dLoss/dtheta by autograd (solver.py:433-499, :220-221).
+
+    Returns dict(loss, grads (list, parameter order), X, Y, Zsum, grad_y0)."""
+    if loss_method == "relative_entropy":
+        adaptive = True                                                             # :61-62
+    leaves = flat_params(params, time_approx)
+    for q in leaves:
+        q.requires_grad_(True)
+        q.grad = None
+    if y0 is not None:
+        y0.requires_grad_(True)
+        y0.grad = None
+    X, Y, Zsum, _ = hjb_rollout(problem, net, params, xi, delta_t, N, time_approx, adaptive, detach_forward,
+                                want_zsum="relative_entropy" in loss_method, y0=y0)
+    loss = hjb_loss(loss_method, problem, X, Y, Zsum, adaptive)
+    loss.backward()
+    grads = [pt.zeros_like(q) if q.grad is None else q.grad.detach().clone() for q in leaves]
+    out = dict(loss=loss.detach(), grads=grads, X=X.detach(), Y=Y.detach(), Zsum=Zsum.detach(),
+               gX=problem.g(X).detach(), grad_y0=None if y0 is None else y0.grad.detach().clone())
+    for q in leaves:
+        q.requires_grad_(False)
+    return out
+
+
+# --------------------------------------------------------------------------- diffusion loss (GeneralSolver)
+def diffusion_iteration(problem, params, X0, t0, xis, delta_t, N, K_boundary=50, alpha=(1.0, 1.0, 1.0)):
+    """One iteration of GeneralSolver.train for loss_method='diffusion', boundary='unbounded',
+    non-adaptive, detach_forward=True (solver.py:1062-1064, :1076-1163).
+
+    X0 (K,d), t0 (K,1), xis (N,K,d) are the random draws (:1045-1046, :1078, :1106) supplied by the caller.
+    The network sees [X, t] with t as the LAST column (:1079)."""
+    dtype = X0.dtype
+    dt = pt.as_tensor(delta_t, dtype=dtype)
+    sq = pt.sqrt(dt)
+    K = X0.shape[0]
+    for q in params:
+        q.requires_grad_(True)
+        q.grad = None
+    V = lambda z: densenet_forward(params, z)
+    X_T = pt.cat([X0[:K_boundary], problem.T * pt.ones(K_boundary, 1, dtype=dtype)], 1)
+    loss = alpha[1] * ((V(X_T).squeeze() - problem.f(X0[:K_boundary])) ** 2).mean()  # :1063-1064
+    X = X0.clone().requires_grad_(True)
+    t_n = t0.clone()
+    X_t = pt.cat([X, t_n], 1)
+    Y = V(X_t).squeeze()                                                             # :1081
+    stopped = pt.zeros(K, dtype=pt.bool)
+    K_count = 0
+    for n in range(N):
+        if int((~stopped).sum()) == 0:
+            break
+        Y_ = V(X_t)
+        grad_V, = pt.autograd.grad(Y_.squeeze().sum(), X, create_graph=True)         # :1100-1103
+        Z = (problem.B.t() @ grad_V.t()).t()                                         # :1104
+        xin = xis[n]
+        sel = (~stopped).to(dtype).unsqueeze(1)
+        X_prop = X + (problem.b(X) * dt + (problem.B @ xin.t()).t() * sq) * sel      # :1116-1117 (c = 0)
+        new_sel = (t_n.squeeze(1) + dt) <= problem.T                                 # :1119, :1131
+        act = (new_sel & ~stopped)
+        actf = act.to(dtype)
+        Y = Y + (-problem.h(n * dt, X, Y_.squeeze(), Z) * dt + (Z * xin).sum(1) * sq) * actf   # :1141-1142
+        X = X * (1 - actf).unsqueeze(1) + X_prop * actf.unsqueeze(1)                 # :1145-1146
+        t_n = t_n + dt * actf.unsqueeze(1)                                           # :1148
+        X_t = pt.cat([X, t_n], 1)
+        K_count += int(act.sum())                                                    # :1151-1152
+        stopped = stopped | (~new_sel & ~stopped)                                    # :1154-1155
+    loss = loss + alpha[0] * ((V(X_t).squeeze() - Y) ** 2).mean()                    # :1163
+    loss.backward()
+    grads = [q.grad.detach().clone() for q in params]
+    for q in params:
+        q.requires_grad_(False)
+    return dict(loss=loss.detach(), grads=grads, K_count=K_count, X=X.detach(), t=t_n.detach(), Y=Y.detach())
+
+
+def sample_ball(K, d, radius, dtype=pt.float32):
+    """Uniform sample in the d-ball, draw order of solver.py:1045-1046."""
+    X = pt.randn(K, d).to(dtype)
+    return radius * X / pt.sqrt((X ** 2).sum(1)).unsqueeze(1) * (pt.rand(K).to(dtype).unsqueeze(1) ** (1 / d))
+
+
+# --------------------------------------------------------------------------- importance sampling (next row f1)
+def importance_sampling(problem, net, params, xis, delta_t, solver_delta_t, time_approx="inner", N_solver=None):
+    """utilities.py:287-359 with control='approx'; xis (N,K,d) supplied by the caller.
+
+    Returns (mean_IS, variance_IS, rel_error_IS).  The control net is addressed through Z_n(X, t)
+    (solver.py:360-362: n = ceil(t / solver_delta_t))."""
+    N, K, d = xis.shape
+    dtype = xis.dtype
+    sq = float(np.sqrt(delta_t))
+    sdt = pt.as_tensor(solver_delta_t, dtype=dtype)
+    X = problem.X_0.repeat(K, 1)
+    ito = pt.zeros(K, dtype=dtype)
+    rie = pt.zeros(K, dtype=dtype)
+    fint = pt.zeros(K, dtype=dtype)
+    with pt.no_grad():
+        for n in range(N):
+            xin = xis[n]
+            nn_ = int(pt.ceil(pt.as_tensor(n * delta_t) / sdt))
+            ut = -control_eval(net, params, X, nn_, sdt, time_approx, N_solver)
+            X = X + (problem.b(X) + (problem.B @ ut.t()).t()) * delta_t + (problem.B @ xin.t()).t() * sq
+            ito += (ut * xin).sum(1) * sq
+            rie += (ut ** 2).sum(1) * delta_t
+            fint += problem.f(X, n * delta_t) * delta_t
+        w = pt.exp(-fint - problem.g(X)) * pt.exp(-ito - 0.5 * rie)
+        mean = w.mean().item()
+        var = pt.var(w).item()
+    return mean, var, float(np.sqrt(var) / mean)
+
+
+# --------------------------------------------------------------------------- whole training loops (CPU baseline)
+def hjb_train_loop(problem, net, params, K, delta_t, L, lr, loss_method="log-variance", time_approx="inner",
+                   adaptive=True, detach_forward=True, seed=42, times=None):
+    """Solver.train (solver.py:420-531) without logging extras: per iteration draw xi = randn(K, d, N+1)
+    on the CPU generator (:381), roll out, loss, backward, one Adam step per network (:198-200)."""
+    import time
+    N = int(np.floor(problem.T / delta_t))                                          # :41
+    nets = params if time_approx == "outer" else [params]
+    for net_ in nets:
+        for q in net_:
+            q.requires_grad_(True)
+    optims = [pt.optim.Adam(net_, lr=lr) for net_ in nets]
+    pt.manual_seed(seed)                                                            # :422
+    loss_log = []
+    for _ in range(L):
+        t0 = time.time()
+        xi = pt.randn(K, problem.d, N + 1)
+        for o in optims:
+            o.zero_grad()
+        ad = True if loss_method == "relative_entropy" else adaptive
+        X, Y, Zsum, _ = hjb_rollout(problem, net, params, xi, delta_t, N, time_approx, ad, detach_forward,
+                                    want_zsum="relative_entropy" in loss_method)
+        loss = hjb_loss(loss_method, problem, X, Y, Zsum, ad)
+        loss.backward()
+        for o in optims:
+            o.step()
+        loss_log.append(loss.item())
+        if times is not None:
+            times.append(time.time() - t0)
+    return loss_log
+
+
+def diffusion_train_loop(problem, params, K, K_boundary, N, delta_t, L, lr, seed=42, times=None):
+    """GeneralSolver.train, loss 'diffusion', boundary 'unbounded' (solver.py:1001-1200)."""
+    import time
+    opt = pt.optim.Adam(params, lr=lr)
+    pt.manual_seed(seed)                                                            # :1003
+    loss_log, K_log = [], []
+    for _ in range(L):
+        t0 = time.time()
+        X0 = sample_ball(K, problem.d, problem.boundary_distance)                   # :1045-1046
+        t0_ = pt.rand(K, 1) * problem.T                                             # :1078
+        xis = pt.stack([pt.randn(K, problem.d) for _ in range(N)])                  # :1106 (no early break here)
+        opt.zero_grad()
+        out = diffusion_iteration(problem, params, X0, t0_, xis, delta_t, N, K_boundary)
+        for q, g in zip(params, out["grads"]):
+            q.grad = g
+        opt.step()
+        loss_log.append(float(out["loss"]))
+        K_log.append(out["K_count"])
+        if times is not None:
+            times.append(time.time() - t0)
+    return loss_log, K_log
