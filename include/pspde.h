@@ -1,0 +1,128 @@
+/* pspde.h -- C ABI of libpspde: the B200 (sm_100a) fused path-space rollout.
+ *
+ * The reference (lorenzrichter/path-space-PDE-solver) has no FFI; its de-facto boundary for the hot path is
+ * the body of Solver.train (solver.py:433-499: initialize_training_data -> N-step Euler-Maruyama loop ->
+ * loss_function -> loss.backward) and of GeneralSolver.train (solver.py:1040-1188).  Each entry point below
+ * replaces one slice of that body; the reference lines it stands for are cited at the declaration.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch types.  All buffer arguments of the device entry points
+ *     are DEVICE pointers owned by the caller; the library allocates nothing persistent.
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no host synchronisation,
+ *     re-entrant per device, one process per GPU.  The *_host entry point is the exception (documented there).
+ *   - return value 0 = ok; negative = error, message via pspde_last_error() (thread local).  Never throws.
+ *   - fp32 arithmetic throughout (dtype "f32"); loss statistics are accumulated in fp64.
+ */
+#ifndef PSPDE_H
+#define PSPDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSPDE_ABI_VERSION 1
+#define PSPDE_MAX_LAYERS 4          /* linear layers per network (<= 3 hidden) */
+
+/* problem functors (problems.py): drift b(x), diffusion sigma = B, running cost f, terminal cost g.
+ *   PSPDE_PROBLEM_OU   LLGC (problems.py:14-49) and LQGC (:118-167):
+ *                      b = A x, sigma = B, f = x'Px, g = alpha.x + x'Rx, h = -|z|^2/2 - f
+ *   PSPDE_PROBLEM_DW   DoubleWell(_multidim) (problems.py:178-214, :285-334):
+ *                      b_i = -4 kappa_i x_i (x_i^2 - 1), sigma = I, f = 0, g = sum eta_i (x_i - 1)^2
+ *   PSPDE_PROBLEM_HEAT HeatEquation (problems.py:1733-1764), diffusion loss only:
+ *                      b = 0, sigma = sqrt(2) I, h = 0, terminal f = |x|^2
+ * Parameter pack `prob` (fp32): 7 vectors of length d, in this order
+ *      a_diag | b_diag | p_diag | r_diag | alpha | kappa | eta
+ * followed, when PSPDE_FLAG_DENSE_AB is set, by the row-major d x d matrices A then B (the diagonal
+ * vectors are then ignored for drift/diffusion).  P and R are diagonal in every reference problem. */
+enum { PSPDE_PROBLEM_OU = 0, PSPDE_PROBLEM_DW = 1, PSPDE_PROBLEM_HEAT = 2 };
+enum { PSPDE_FLAG_DENSE_AB = 1 };
+
+/* networks (function_space.py).  theta is the flat concatenation of module.parameters():
+ *   PSPDE_NET_DENSENET  DenseNet (:116-140): W_i (sum(dims[:i+1]), dims[i+1]) row major, b_i; act relu(.)^2
+ *   PSPDE_NET_MLP_TANH  MySequential (:177-195): nn.Linear weight_i (dims[i+1], dims[i]), bias_i; act tanh */
+enum { PSPDE_NET_DENSENET = 0, PSPDE_NET_MLP_TANH = 1 };
+
+/* where time enters the network input (solver.py:349-356, :1079):
+ *   TIME_FIRST  'inner': input [t_n, X]            (Solver)
+ *   TIME_NONE   'outer': input X, one parameter set per step, theta = N stacked sets
+ *   TIME_LAST   input [X, t]                       (GeneralSolver) */
+enum { PSPDE_TIME_FIRST = 0, PSPDE_TIME_NONE = 1, PSPDE_TIME_LAST = 2 };
+
+/* Brownian increments: INJECT reads xi from memory (parity with solver.py:381), PHILOX generates them in
+ * the kernel: Philox4x32-10, counter (k_global, n, j/4, offset), key = seed, Box-Muller. */
+enum { PSPDE_NOISE_INJECT = 0, PSPDE_NOISE_PHILOX = 1 };
+
+typedef struct pspde_cfg {
+  int32_t K_local;      /* trajectories simulated by this call (this GPU's shard)                  */
+  int32_t k_offset;     /* global index of the first local trajectory (Philox counter)             */
+  int32_t d;            /* state dimension                                                         */
+  int32_t N;            /* Euler-Maruyama steps (computed on the host: solver.py:41)               */
+  float   dt;           /* step size as fp32 (solver.py:39); sqrt(dt) is taken in fp32 (:40)       */
+  int32_t problem_id;   /* PSPDE_PROBLEM_*                                                         */
+  int32_t problem_flags;
+  int32_t net_id;       /* PSPDE_NET_*                                                             */
+  int32_t n_layers;     /* number of linear layers L (dims has L+1 entries)                        */
+  int32_t dims[PSPDE_MAX_LAYERS + 1];  /* [d_in, h_1, ..., d_out]; d_in includes the time column   */
+  int32_t time_mode;    /* PSPDE_TIME_*                                                            */
+  int32_t adaptive;     /* adaptive_forward_process: c = -Z (solver.py:452-456) else c = 0         */
+  int32_t noise_mode;   /* PSPDE_NOISE_*                                                           */
+  int32_t x0_per_path;  /* 0: x0 is one row of d floats (X_0.repeat, :365); 1: K_local x d rows    */
+  uint64_t seed;        /* Philox key                                                              */
+  uint32_t offset;      /* Philox stream id: the training-iteration counter                       */
+  int32_t  reserved;
+  /* INJECT: element (k, j, step n) is read at xi[k*xi_stride_k + j*xi_stride_j + n*xi_stride_n], n = 0..N-1
+   * being the increment that drives step n.  Reference layout (K, d, N+1) with slice n+1 driving step n
+   * (solver.py:472): pass xi + 1 and strides (d*(N+1), N+1, 1). */
+  int64_t xi_stride_k, xi_stride_j, xi_stride_n;
+} pspde_cfg;
+
+int          pspde_abi_version(void);
+const char*  pspde_last_error(void);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+uint64_t     pspde_launch_count(void);
+/* number of parameters in theta for cfg (all N sets in TIME_NONE mode); <0 on invalid cfg */
+int64_t      pspde_theta_size(const pspde_cfg* cfg);
+/* scratch bytes the rollout entry points need for cfg (upper bound over all of them) */
+size_t       pspde_workspace_bytes(const pspde_cfg* cfg);
+
+/* Forward rollout -- replaces solver.py:433-494 (initialize_training_data + the N-step loop) and the
+ * reductions of loss_function (:164-192).  Per path: X_N (nullable, K x d), Y_N, gX = g(X_N),
+ * Zsum = sum_n (|Z|^2/2 + f(X_{n+1})) dt (:486).  y0 (nullable) is a device scalar added to Y (learn_Y_0, :372-373).
+ * stats (nullable) receives 4 doubles: sum D, sum D^2 (D = Y_N - gX), sum (Zsum + gX), #non-finite D. */
+int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                      const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
+                      double* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward for detach_forward=True (solver.py:468-469 + loss.backward at :221).  The trajectories do not
+ * depend on theta, so dLoss/dtheta = sum_{k,n} J_theta Z(t_n, X_{k,n})' zeta_{k,n} with
+ *   zeta = wY_k (sqrt(dt) xi_{n+1} + [adaptive == 0] Z dt) + wZ_k Z dt,
+ * wY = dLoss/dY_N, wZ = dLoss/dZsum (nullable = 0), both of length K_local.  The rollout is recomputed
+ * from (x0, xi | Philox); nothing of size K x N x d is kept in HBM.  grad_theta (pspde_theta_size floats)
+ * is overwritten. */
+int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                               const float* xi, const float* wY, const float* wZ, float* grad_theta,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward + backward for detach_forward=False with the relative-entropy loss mean(Zsum + g(X_N))
+ * (solver.py:180, :484-486, :221): per tile of paths the states X_n are checkpointed to the workspace and
+ * the discrete adjoint runs backwards in time in the same kernel.  w = 1 / K_global.  Outputs as in
+ * pspde_rollout_fwd plus grad_theta (overwritten). */
+int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                           const float* xi, float w, float* X_N, float* gX, float* Zsum, double* stats,
+                           float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook: writes the increments the kernels would generate for cfg (Philox mode) in the layout
+ * (N, K_local, d), i.e. strides (d, 1, K_local*d). */
+int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream);
+
+/* Deterministic fp32 FMA throughput probe (roofline denominator measured live by bench.py):
+ * runs `iters` dependent-chain FMA rounds on every SM; returns the FLOP count launched, or <0. */
+int64_t pspde_fma_probe(int iters, float* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSPDE_H */

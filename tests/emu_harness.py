@@ -1,0 +1,113 @@
+"""Drives the host-emulator build of the CUDA sources (tests/emu) through the same C ABI with numpy buffers.
+
+Test infrastructure only: lets `-m "not gpu"` tests execute the real kernel source (index logic, shared-memory
+layout, barrier placement, host-side planning) on the CPU.  The product never loads this library."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from pspde import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "path-space-pde-solver_b200", "csrc")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libpspde_emu.so")
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "simt_emul.h")]
+        if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < max(os.path.getmtime(s) for s in srcs):
+            os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPSPDE_EMULATE", "-x", "c++",
+                                   "-I", EMU_DIR, "-I", CSRC, os.path.join(CSRC, "pspde_api.cu"), "-o", EMU_SO])
+        _emu = L.bind(EMU_SO)
+    return _emu
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def problem_pack(kind, d, pkw, A=None, B=None):
+    """(problem_id, flags, fp32 pack) as laid out in include/pspde.h."""
+    z, one = np.zeros(d, np.float32), np.ones(d, np.float32)
+    flags = 0
+    if kind in ("llgc", "lqgc"):
+        A = -np.eye(d, dtype=np.float32) if A is None else A.astype(np.float32)
+        B = np.eye(d, dtype=np.float32) if B is None else B.astype(np.float32)
+        lq = kind == "lqgc"
+        vecs = [np.diag(A).copy(), np.diag(B).copy(), 0.5 * one if lq else z, one if lq else z, z if lq else one, z, z]
+        pack = np.concatenate(vecs)
+        if np.any(A != np.diag(np.diag(A))) or np.any(B != np.diag(np.diag(B))):
+            flags = L.FLAG_DENSE_AB
+            pack = np.concatenate([pack, A.reshape(-1), B.reshape(-1)])
+        return L.PROBLEM_OU, flags, pack.astype(np.float32)
+    if kind == "dwm":
+        d1, d2 = int(pkw["d_1"]), int(pkw["d_2"])
+        eta = np.array([pkw["eta"]] * d1 + [1.0] * d2, np.float32)
+        kap = np.array([pkw["kappa"]] * d1 + [1.0] * d2, np.float32)
+        return L.PROBLEM_DW, 0, np.concatenate([z, one, z, z, z, kap, eta]).astype(np.float32)
+    raise ValueError(kind)
+
+
+def cfg_from_golden(g, noise=L.NOISE_INJECT, K=None, k_offset=0, seed=0, offset=0):
+    d, N = g["d"], g["N"]
+    pid, flags, pack = problem_pack(g["kind"], d, g.get("pkw", {}), g.get("A"), g.get("B"))
+    outer = g["time_approx"] == "outer"
+    dims = [d if outer else d + 1, 30, 30, d]
+    cfg = L.make_cfg(K or g["K"], d, N, np.float32(g["delta_t"]), pid,
+                     L.NET_DENSENET if g["net"] == "densenet" else L.NET_MLP_TANH, dims,
+                     L.TIME_NONE if outer else L.TIME_FIRST, adaptive=g["adaptive"], k_offset=k_offset,
+                     problem_flags=flags, noise_mode=noise, seed=seed, offset=offset,
+                     xi_strides=(d * (N + 1), N + 1, 1))
+    x0 = (-np.ones(d) if g["kind"] == "dwm" else np.zeros(d)).astype(np.float32)
+    return cfg, pack, x0
+
+
+class Runner:
+    """numpy-buffer front end of the C ABI (works for the emulator; the GPU tests use torch tensors instead)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def fwd(self, cfg, theta, pack, x0, xi=None, y0=None):
+        K, d = cfg.K_local, cfg.d
+        ws = np.zeros(self.lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 1, np.float64)
+        out = dict(X=np.zeros((K, d), np.float32), Y=np.zeros(K, np.float32), gX=np.zeros(K, np.float32),
+                   Zsum=np.zeros(K, np.float32), stats=np.zeros(4, np.float64))
+        xi_p = None if xi is None else ctypes.c_void_p(xi.ctypes.data + 4)   # slice n+1 drives step n
+        y0a = None if y0 is None else np.array([y0], np.float32)
+        rc = self.lib.pspde_rollout_fwd(ctypes.byref(cfg), ptr(theta), ptr(pack), ptr(x0), ptr(y0a), xi_p,
+                                        ptr(out["X"]), ptr(out["Y"]), ptr(out["gX"]), ptr(out["Zsum"]),
+                                        ptr(out["stats"]), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return out
+
+    def bwd(self, cfg, theta, pack, x0, wY, wZ=None, xi=None):
+        ws = np.zeros(self.lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 1, np.float64)
+        grad = np.full(self.lib.pspde_theta_size(ctypes.byref(cfg)), np.nan, np.float32)
+        xi_p = None if xi is None else ctypes.c_void_p(xi.ctypes.data + 4)
+        wY = np.ascontiguousarray(wY, np.float32)
+        wZ = None if wZ is None else np.ascontiguousarray(wZ, np.float32)
+        rc = self.lib.pspde_rollout_bwd_detached(ctypes.byref(cfg), ptr(theta), ptr(pack), ptr(x0), xi_p, ptr(wY),
+                                                 ptr(wZ), ptr(grad), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return grad
+
+    def attached(self, cfg, theta, pack, x0, w, xi=None):
+        K, d = cfg.K_local, cfg.d
+        ws = np.zeros(self.lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 1, np.float64)
+        out = dict(X=np.zeros((K, d), np.float32), gX=np.zeros(K, np.float32), Zsum=np.zeros(K, np.float32),
+                   stats=np.zeros(4, np.float64),
+                   grad=np.full(self.lib.pspde_theta_size(ctypes.byref(cfg)), np.nan, np.float32))
+        xi_p = None if xi is None else ctypes.c_void_p(xi.ctypes.data + 4)
+        rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), ptr(theta), ptr(pack), ptr(x0), xi_p,
+                                             ctypes.c_float(w), ptr(out["X"]), ptr(out["gX"]), ptr(out["Zsum"]),
+                                             ptr(out["stats"]), ptr(out["grad"]), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return out

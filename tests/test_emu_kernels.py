@@ -1,0 +1,151 @@
+"""The CUDA kernel SOURCE (path-space-pde-solver_b200/csrc) executed on the CPU through the fiber emulator
+(tests/emu), compared with the reference's golden vectors and the oracle.  These tests check index logic,
+shared-memory layout, barrier placement and the host-side planning of the C ABI; the `-m gpu` tests repeat the
+same comparisons on the real sm_100a build."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import emu_harness as H
+from conftest import HJB_TAGS, load_golden, relerr
+from oracle import manual as man
+from oracle import philox as ph
+from pspde import _lib as L
+
+
+@pytest.fixture(scope="module")
+def run():
+    return H.Runner(H.emu_lib())
+
+
+def test_emulator_exports_the_whole_abi():
+    lib = H.emu_lib()
+    assert lib.pspde_abi_version() == L.ABI_VERSION
+
+
+@pytest.mark.parametrize("tag", HJB_TAGS)
+def test_golden_parity(run, tag):
+    g = load_golden(tag)
+    cfg, pack, x0 = H.cfg_from_golden(g)
+    theta, xi = g["theta"].astype(np.float32), np.ascontiguousarray(g["xi"], np.float32)
+    K = g["K"]
+    if g["detach_forward"]:
+        o = run.fwd(cfg, theta, pack, x0, xi, y0=g["y0"] if g["learn_Y_0"] else None)
+        assert relerr(o["X"], g["X_N"]) < 1e-5 and relerr(o["Y"], g["Y_N"]) < 1e-5 and relerr(o["gX"], g["gX"]) < 1e-5
+        D = o["Y"].astype(np.float64) - o["gX"]
+        np.testing.assert_allclose(o["stats"][:2], [D.sum(), (D ** 2).sum()], rtol=1e-12)
+        assert o["stats"][3] == 0
+        loss, wY, wZ = man.loss_and_weights(g["loss_method"], o["Y"].astype(np.float64), o["gX"].astype(np.float64),
+                                            o["Zsum"].astype(np.float64), g["adaptive"])
+        tol = 1e-5 * abs(g["loss"]) + (4 * 6e-8 * float((D ** 2).mean()) if "variance" in g["loss_method"] else 0)
+        assert abs(loss - g["loss"]) <= tol
+        grad = run.bwd(cfg, theta, pack, x0, wY, wZ, xi)
+        assert relerr(grad, g["grad"]) < 1e-5
+        if g["learn_Y_0"]:
+            assert abs(wY.sum() - g["grad_y0"]) < 1e-4 * abs(g["grad_y0"])
+    else:
+        o = run.attached(cfg, theta, pack, x0, 1.0 / K, xi)
+        assert relerr(o["X"], g["X_N"]) < 1e-5 and relerr(o["Zsum"], g["Zsum"]) < 1e-5
+        assert abs(o["stats"][2] / K - g["loss"]) < 1e-5 * abs(g["loss"])
+        assert relerr(o["grad"], g["grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_schedule_independence(order):
+    """A missing barrier shows up as a result that depends on the order threads run in between barriers."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import conftest, numpy as np, emu_harness as H;"
+            "from conftest import load_golden;"
+            "r = H.Runner(H.emu_lib());"
+            "g = load_golden('hjb_dwm_d50_mlp_re'); cfg, pack, x0 = H.cfg_from_golden(g);"
+            "o = r.attached(cfg, g['theta'], pack, x0, 1.0 / g['K'], np.ascontiguousarray(g['xi']));"
+            "g2 = load_golden('hjb_lqgc_d10_outer_lv'); cfg2, pack2, x02 = H.cfg_from_golden(g2);"
+            "w = np.linspace(-1, 1, g2['K']).astype(np.float32);"
+            "gr = r.bwd(cfg2, g2['theta'], pack2, x02, w, w, np.ascontiguousarray(g2['xi']));"
+            "sys.stdout.write('%%.17g %%.17g' %% (float(np.abs(o['grad']).sum()), float(np.abs(gr).sum())))"
+            % os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for o in ("forward", order):
+        env = dict(os.environ, PSPDE_EMU_ORDER=o)
+        outs.append(subprocess.check_output([sys.executable, "-c", code], env=env).decode())
+    assert outs[0] == outs[1]
+
+
+def _philox_case(run, K, k_offset=0, adaptive=True):
+    """multi-tile, multi-CTA, ragged last tile, in-kernel Philox; oracle fed with the restated Philox noise."""
+    g = load_golden("hjb_lqgc_d10_dense_lv")
+    d, N, dt = g["d"], 6, 0.05
+    g = dict(g, N=N, adaptive=adaptive)
+    cfg, pack, x0 = H.cfg_from_golden(g, noise=L.NOISE_PHILOX, K=K, k_offset=k_offset, seed=1234567, offset=3)
+    theta = g["theta"].astype(np.float32)
+    o = run.fwd(cfg, theta, pack, x0)
+    rng = np.random.default_rng(5)
+    wY, wZ = rng.standard_normal(K), rng.standard_normal(K)
+    grad = run.bwd(cfg, theta, pack, x0, wY, wZ)
+    return g, o, grad, (wY, wZ), theta
+
+
+def test_philox_multi_tile_vs_oracle(run):
+    K = 64 * 4 * 2 + 17           # 9 tiles over the emulator's 4 "SMs", last tile ragged
+    g, o, grad, (wY, wZ), theta = _philox_case(run, K)
+    d, N, dt = g["d"], g["N"], g["delta_t"]
+    xi = ph.xi_tensor(1234567, 3, 0, K, d, N).astype(np.float64)
+    net = man.Net("densenet", [d + 1, 30, 30, d], theta)
+    prob = man.Problem("lqgc", d)
+    gm, ro = man.grad_mode_a(prob, net, xi, dt, N, np.zeros(d), wY, wZ, True, "first")
+    assert relerr(o["X"], ro["X"]) < 1e-5 and relerr(o["Y"], ro["Y"]) < 1e-5 and relerr(o["Zsum"], ro["Zsum"]) < 1e-5
+    assert relerr(grad, gm) < 2e-5
+    D = o["Y"].astype(np.float64) - o["gX"]
+    np.testing.assert_allclose(o["stats"][:3], [D.sum(), (D ** 2).sum(), (o["Zsum"].astype(np.float64) + o["gX"]).sum()],
+                               rtol=1e-12)
+
+
+def test_philox_dump_matches_oracle_and_kernel(run):
+    lib = run.lib
+    K, d, N = 70, 10, 4
+    cfg = L.make_cfg(K, d, N, 0.05, L.PROBLEM_OU, L.NET_DENSENET, [d + 1, 30, 30, d], L.TIME_FIRST, k_offset=5,
+                     seed=99, offset=2)
+    out = np.zeros((N, K, d), np.float32)
+    L.check(lib, lib.pspde_philox_dump(ctypes.byref(cfg), H.ptr(out), None))
+    ref = ph.xi_tensor(99, 2, 5, K, d, N)[:, :, 1:].transpose(2, 0, 1)
+    assert np.abs(out - ref).max() < 1e-5
+
+
+def test_sharding_invariance(run):
+    """Per-path results do not depend on how K is split over ranks (global-index Philox counter)."""
+    K = 150
+    _, o, grad, (wY, wZ), theta = _philox_case(run, K)
+    g = load_golden("hjb_lqgc_d10_dense_lv")
+    g = dict(g, N=6)
+    parts, grads = [], []
+    for lo, hi in ((0, 80), (80, 150)):
+        cfg, pack, x0 = H.cfg_from_golden(g, noise=L.NOISE_PHILOX, K=hi - lo, k_offset=lo, seed=1234567, offset=3)
+        parts.append(run.fwd(cfg, theta, pack, x0))
+        grads.append(run.bwd(cfg, theta, pack, x0, wY[lo:hi], wZ[lo:hi]))
+    assert np.array_equal(np.concatenate([p["Y"] for p in parts]), o["Y"])
+    assert np.array_equal(np.concatenate([p["X"] for p in parts]), o["X"])
+    assert relerr(grads[0] + grads[1], grad) < 1e-6
+    assert abs(sum(p["stats"][0] for p in parts) - o["stats"][0]) < 1e-9 * abs(o["stats"][0]) + 1e-12
+
+
+def test_error_paths(run):
+    lib = run.lib
+    d = 10
+    bad = L.make_cfg(8, d, 4, 0.05, L.PROBLEM_OU, L.NET_DENSENET, [d + 2, 30, 30, d], L.TIME_FIRST)
+    assert lib.pspde_theta_size(ctypes.byref(bad)) < 0 and b"geometry" in lib.pspde_last_error()
+    heat = L.make_cfg(8, d, 4, 0.05, L.PROBLEM_HEAT, L.NET_DENSENET, [d + 1, 30, 30, d], L.TIME_FIRST)
+    assert lib.pspde_workspace_bytes(ctypes.byref(heat)) == 0
+    ok = L.make_cfg(8, d, 4, 0.05, L.PROBLEM_OU, L.NET_DENSENET, [d + 1, 30, 30, d], L.TIME_FIRST,
+                    noise_mode=L.NOISE_INJECT)
+    theta = np.zeros(lib.pspde_theta_size(ctypes.byref(ok)), np.float32)
+    pack, x0 = np.zeros(7 * d, np.float32), np.zeros(d, np.float32)
+    ws = np.zeros(1 << 16, np.float64)
+    rc = lib.pspde_rollout_fwd(ctypes.byref(ok), H.ptr(theta), H.ptr(pack), H.ptr(x0), None, None, None, None, None,
+                               None, None, H.ptr(ws), ws.nbytes, None)
+    assert rc < 0 and b"xi" in lib.pspde_last_error()          # INJECT without xi
+    rc = lib.pspde_rollout_fwd(ctypes.byref(ok), H.ptr(theta), H.ptr(pack), H.ptr(x0), None, H.ptr(ws), None, None,
+                               None, None, None, H.ptr(ws), 8, None)
+    assert rc < 0 and b"workspace" in lib.pspde_last_error()
