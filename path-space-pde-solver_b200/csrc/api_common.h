@@ -1,0 +1,158 @@
+// api_common.h -- shared by the api_*.cu translation units: error reporting, validation, launch planning.
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/pspde.h"
+#include "rollout_kernels.cuh"
+
+#if defined(PSPDE_EMULATE)
+#define PSPDE_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
+static inline int pspde_sm_count() { return emu::M().sm_count; }
+static inline int pspde_memset0(void* p, size_t n, void*) { memset(p, 0, n); return 0; }
+template <typename K> static inline int pspde_set_smem(K, size_t) { return 0; }
+static inline const char* pspde_peek_error() { return nullptr; }
+#else
+#define PSPDE_LAUNCH(kern, grid, block, smem, stream, ...) \
+  kern<<<dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+static inline int pspde_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { n = 0; return -1; }
+  }
+  return n;
+}
+static inline int pspde_memset0(void* p, size_t n, void* stream) {
+  return cudaMemsetAsync(p, 0, n, (cudaStream_t)stream) == cudaSuccess ? 0 : -1;
+}
+template <typename K> static inline int pspde_set_smem(K kern, size_t bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
+}
+static inline const char* pspde_peek_error() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+#endif
+
+using namespace pspde;
+
+static_assert(sizeof(pspde_cfg) == 112, "pspde_cfg layout is part of the ABI (mirrored by pspde/_lib.py)");
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+static inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+constexpr int kP = 64;                       // trajectories per tile
+constexpr size_t kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per CTA on sm_100
+
+struct Plan {
+  NetGeom g;
+  int T, NB, n_tiles, grid, n_sets, n_theta_total;
+  int r_fwd[PSPDE_MAXL];
+  size_t smem_bytes, stats_bytes, grad_bytes;
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static inline int validate(const pspde_cfg* c) {
+  if (!c) return fail(-1, "cfg is NULL");
+  if (c->K_local < 1 || c->d < 1 || c->N < 0) return fail(-2, "bad sizes K_local=%d d=%d N=%d", c->K_local, c->d, c->N);
+  if (!(c->dt > 0.f)) return fail(-2, "dt must be > 0");
+  if (c->n_layers < 1 || c->n_layers > PSPDE_MAX_LAYERS) return fail(-3, "n_layers=%d unsupported (1..%d)", c->n_layers, PSPDE_MAX_LAYERS);
+  if (c->net_id != PSPDE_NET_DENSENET && c->net_id != PSPDE_NET_MLP_TANH) return fail(-3, "unknown net_id %d", c->net_id);
+  if (c->time_mode < 0 || c->time_mode > 2) return fail(-3, "unknown time_mode %d", c->time_mode);
+  if (c->problem_id != PSPDE_PROBLEM_OU && c->problem_id != PSPDE_PROBLEM_DW)
+    return fail(-4, "problem_id %d is not supported by the HJB rollout", c->problem_id);
+  if ((c->problem_flags & PSPDE_FLAG_DENSE_AB) && c->d > 128) return fail(-4, "dense A/B needs d <= 128 (d=%d)", c->d);
+  if (c->dims[c->n_layers] != c->d) return fail(-3, "control network must map to d outputs (got %d)", c->dims[c->n_layers]);
+  if (c->noise_mode != PSPDE_NOISE_INJECT && c->noise_mode != PSPDE_NOISE_PHILOX) return fail(-5, "unknown noise_mode");
+  return 0;
+}
+
+// paths per thread tile in gemm_nn: minimise (waves over the CTA) x (issue slots per 4-wide k step)
+static inline int choose_r(int Np, int T, int rmax) {
+  int best = 1;
+  long best_cost = -1;
+  for (int R = 1; R <= rmax; R *= 2) {
+    const long tiles = (long)(kP / R) * (Np / 4);
+    const long waves = (tiles + T - 1) / T;
+    const long cost = waves * (R + 4 + 16 * R);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = R; }
+  }
+  return best;
+}
+
+static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& pl) {
+  int rc = validate(c);
+  if (rc) return rc;
+  rc = build_geom(pl.g, c->net_id, c->n_layers, c->dims, c->time_mode, c->d);
+  if (rc) return fail(-3, "network geometry rejected (code %d): dims[0] must be d%s", rc, c->time_mode == PSPDE_TIME_NONE ? "" : "+1");
+  pl.n_sets = (c->time_mode == PSPDE_TIME_NONE) ? c->N : 1;
+  pl.n_theta_total = pl.g.n_params * pl.n_sets;
+  pl.n_tiles = (c->K_local + kP - 1) / kP;
+  const int sms = pspde_sm_count();
+  if (sms <= 0) return fail(-10, "no CUDA device");
+  pl.grid = pl.n_tiles < sms ? pl.n_tiles : sms;
+  pl.T = 512; pl.NB = 1;
+  if (bwd) {
+    const int nb = pl.g.n_blocks;
+    if (nb <= 256) { pl.T = 256; pl.NB = 1; }
+    else if (nb <= 512) { pl.T = 256; pl.NB = 2; }
+    else if (nb <= 768) { pl.T = 256; pl.NB = 3; }
+    else if (nb <= 1024) { pl.T = 512; pl.NB = 2; }
+    else if (nb <= 1536) { pl.T = 512; pl.NB = 3; }
+    else if (nb <= 2048) { pl.T = 256; pl.NB = 8; }
+    else return fail(-6, "network too large for the register-resident gradient path (%d blocks > 2048)", nb);
+  }
+  for (int l = 0; l < pl.g.L; ++l) pl.r_fwd[l] = choose_r(pl.g.layer[l].Np, pl.T, bwd ? 4 : 8);
+  const SmemLayout sl = smem_layout(pl.g, kP, bwd, attached);
+  pl.smem_bytes = (size_t)sl.total * sizeof(float);
+  if (pl.smem_bytes > kMaxSmem)
+    return fail(-6, "network + tile need %zu B of shared memory (> %zu)", pl.smem_bytes, kMaxSmem);
+  pl.stats_bytes = align256((size_t)pl.grid * 4 * sizeof(double));
+  pl.grad_bytes = bwd ? align256((size_t)pl.grid * pl.n_theta_total * sizeof(float)) : 0;
+  return 0;
+}
+
+static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.g = pl.g;
+  p.K_local = c->K_local; p.k_offset = c->k_offset; p.d = c->d; p.N = c->N; p.dt = c->dt;
+  p.problem_id = c->problem_id; p.flags = c->problem_flags; p.adaptive = c->adaptive;
+  p.noise_mode = c->noise_mode; p.x0_per_path = c->x0_per_path;
+  p.seed = c->seed; p.offset = c->offset;
+  p.xs_k = c->xi_stride_k; p.xs_j = c->xi_stride_j; p.xs_n = c->xi_stride_n;
+  p.n_tiles = pl.n_tiles; p.n_theta_total = pl.n_theta_total;
+  for (int l = 0; l < PSPDE_MAXL; ++l) p.r_fwd[l] = pl.r_fwd[l];
+}
+
+template <int T, bool BWD, int NB>
+static inline int launch_rollout(const Plan& pl, const RolloutParams& p, void* stream) {
+  auto kern = rollout_kernel<kP, T, BWD, NB>;
+  if (pspde_set_smem(kern, pl.smem_bytes)) return fail(-11, "cudaFuncSetAttribute(%zu B smem) failed", pl.smem_bytes);
+  PSPDE_LAUNCH(kern, pl.grid, T, pl.smem_bytes, stream, p);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "rollout kernel launch failed: %s", e);
+  return 0;
+}
+
+
+
+// defined in api_bwd256.cu / api_bwd512.cu / api_att256.cu / api_att512.cu (one TU per thread count so that the
+// template instantiations compile in parallel)
+int pspde_launch_bwd_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
+int pspde_launch_bwd_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);
+int pspde_launch_att_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
+int pspde_launch_att_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);

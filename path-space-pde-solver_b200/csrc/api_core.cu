@@ -1,0 +1,136 @@
+// api_core.cu -- extern "C" entry points declared in include/pspde.h.
+#include "api_common.h"
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+extern "C" {
+
+int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
+const char* pspde_last_error(void) { return g_err; }
+uint64_t pspde_launch_count(void) { return g_launches.load(); }
+
+int64_t pspde_theta_size(const pspde_cfg* cfg) {
+  if (validate(cfg)) return -1;
+  NetGeom g;
+  if (build_geom(g, cfg->net_id, cfg->n_layers, cfg->dims, cfg->time_mode, cfg->d)) { fail(-3, "bad network geometry"); return -1; }
+  return (int64_t)g.n_params * (cfg->time_mode == PSPDE_TIME_NONE ? cfg->N : 1);
+}
+
+size_t pspde_workspace_bytes(const pspde_cfg* cfg) {
+  // upper bound over the entry points that are feasible for cfg (0 if none is)
+  Plan pl;
+  size_t need = 0;
+  if (make_plan(cfg, false, false, pl) == 0) need = pl.stats_bytes;
+  if (make_plan(cfg, true, false, pl) == 0) need = pl.stats_bytes + pl.grad_bytes;
+  if (make_plan(cfg, true, true, pl) == 0)
+    need = pl.stats_bytes + pl.grad_bytes + align256((size_t)pl.grid * cfg->N * kP * cfg->d * sizeof(float));
+  return need ? need + 256 : 0;
+}
+
+int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0, const float* y0,
+                      const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, false, false, pl);
+  if (rc) return rc;
+  if (!theta || !prob || !x0) return fail(-1, "theta/prob/x0 must not be NULL");
+  if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
+  if (!workspace || workspace_bytes < pl.stats_bytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes);
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi;
+  p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Zsum = Zsum;
+  p.stats_partial = reinterpret_cast<double*>(workspace);
+  rc = launch_rollout<512, false, 1>(pl, p, stream);
+  if (rc) return rc;
+  if (stats) {
+    PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);
+    g_launches++;
+    if (const char* e = pspde_peek_error()) return fail(-12, "reduce_stats launch failed: %s", e);
+  }
+  return 0;
+}
+
+int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                               const float* xi, const float* wY, const float* wZ, float* grad_theta,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, true, false, pl);
+  if (rc) return rc;
+  if (!theta || !prob || !x0 || !wY || !grad_theta) return fail(-1, "theta/prob/x0/wY/grad_theta must not be NULL");
+  if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
+  if (!workspace || workspace_bytes < pl.stats_bytes + pl.grad_bytes)
+    return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.grad_bytes);
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY; p.wZ = wZ;
+  p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
+  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
+    return fail(-12, "memset of the gradient partials failed");
+  if (pl.T == 256) rc = pspde_launch_bwd_256(pl, p, stream);
+  else if (pl.T == 512) rc = pspde_launch_bwd_512(pl, p, stream);
+  else rc = fail(-13, "internal: no kernel for T=%d NB=%d", pl.T, pl.NB);
+  if (rc) return rc;
+  const int n = pl.n_theta_total;
+  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, pl.grid, n, grad_theta);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
+  return 0;
+}
+
+int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                           const float* xi, float w, float* X_N, float* gX, float* Zsum, double* stats,
+                           float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, true, true, pl);
+  if (rc) return rc;
+  if (!cfg->adaptive) return fail(-4, "attached mode implies adaptive_forward_process (solver.py:61-62)");
+  if (!theta || !prob || !x0 || !grad_theta) return fail(-1, "theta/prob/x0/grad_theta must not be NULL");
+  if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
+  const size_t ckpt_bytes = align256((size_t)pl.grid * cfg->N * kP * cfg->d * sizeof(float));
+  if (!workspace || workspace_bytes < pl.stats_bytes + pl.grad_bytes + ckpt_bytes)
+    return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.grad_bytes + ckpt_bytes);
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.w_attached = w;
+  p.X_N = X_N; p.gX = gX; p.Zsum = Zsum;
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.stats_partial = reinterpret_cast<double*>(ws);
+  p.grad_partial = reinterpret_cast<float*>(ws + pl.stats_bytes);
+  p.x_ckpt = reinterpret_cast<float*>(ws + pl.stats_bytes + pl.grad_bytes);
+  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
+    return fail(-12, "memset of the gradient partials failed");
+  rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
+  if (rc) return rc;
+  if (stats) {
+    PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);
+    g_launches++;
+  }
+  const int n = pl.n_theta_total;
+  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, pl.grid, n, grad_theta);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "reduce launch failed: %s", e);
+  return 0;
+}
+
+int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream) {
+  if (!cfg || !xi_out) return fail(-1, "NULL argument");
+  if (cfg->K_local < 1 || cfg->d < 1 || cfg->N < 1) return fail(-2, "bad sizes");
+  PSPDE_LAUNCH(philox_dump_kernel, 64, 256, 0, stream, cfg->K_local, cfg->k_offset, cfg->d, cfg->N, cfg->seed,
+               cfg->offset, xi_out);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "philox_dump launch failed: %s", e);
+  return 0;
+}
+
+int64_t pspde_fma_probe(int iters, float* sink, void* stream) {
+  const int sms = pspde_sm_count();
+  if (sms <= 0 || iters < 1 || !sink) { fail(-1, "bad arguments"); return -1; }
+  PSPDE_LAUNCH(fma_probe_kernel, sms, 1024, 0, stream, iters, sink);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) { fail(-12, "fma_probe launch failed: %s", e); return -1; }
+  return (int64_t)sms * 1024 * (int64_t)iters * 16 * 8 * 2;
+}
+
+}  // extern "C"

@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // deterministic cross-CTA reductions (fixed order, fp64 accumulation)
-__global__ void reduce_stats_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
+static __global__ void reduce_stats_kernel(const double* __restrict__ partial, int nparts, double* __restrict__ out) {
   const int i = threadIdx.x;
   if (i < 4) {
     double s = 0.0;
@@ -759,7 +759,7 @@ __global__ void reduce_stats_kernel(const double* __restrict__ partial, int npar
   }
 }
 
-__global__ void reduce_grad_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
+static __global__ void reduce_grad_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     double s = 0.0;
@@ -769,7 +769,7 @@ __global__ void reduce_grad_kernel(const float* __restrict__ partial, int nparts
 }
 
 // increments the rollout kernels would draw, layout (N, K_local, d)
-__global__ void philox_dump_kernel(int K_local, int k_offset, int d, int N, unsigned long long seed, unsigned offset,
+static __global__ void philox_dump_kernel(int K_local, int k_offset, int d, int N, unsigned long long seed, unsigned offset,
                                    float* __restrict__ out) {
   const int nb4 = (d + 3) >> 2;
   const long long total = (long long)N * K_local * nb4;
@@ -787,7 +787,7 @@ __global__ void philox_dump_kernel(int K_local, int k_offset, int d, int N, unsi
 }
 
 // FP32 FMA throughput probe: 8 independent chains per thread, 2 FLOP per FMA
-__global__ void __launch_bounds__(1024, 1) fma_probe_kernel(int iters, float* __restrict__ sink) {
+static __global__ void __launch_bounds__(1024, 1) fma_probe_kernel(int iters, float* __restrict__ sink) {
   float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
         a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float m = 0.9999f, c = 1e-7f;

@@ -1,0 +1,170 @@
+"""torch.autograd bridge to the fused CUDA rollout (C ABI: include/pspde.h).
+
+``RolloutEngine`` owns what one Solver needs on the device (problem functor pack, x0, workspace, per-path output
+buffers) and exposes the library calls with torch tensors.  ``FusedRollout`` / ``FusedRolloutAttached`` are the
+autograd Functions that replace the body of the reference's training iteration (solver.py:433-499 forward,
+:221 backward):
+
+  detached forward (detach_forward=True)      Y_N, gX, Zsum = FusedRollout.apply(theta, y0, engine, call)
+      backward: one recompute rollout with per-path cotangents (dL/dY_N, dL/dZsum) -> dL/dtheta, dL/dy0
+  attached forward (relative entropy loss)     loss = FusedRolloutAttached.apply(theta, engine, call)
+      forward and adjoint run in one kernel; backward hands the stored gradient back.
+
+There is no CPU fallback: constructing an engine without the CUDA library raises.
+"""
+import ctypes
+
+import torch as pt
+
+from . import _lib as L
+
+
+class Call:
+    """What varies from one training iteration to the next."""
+
+    def __init__(self, offset=0, xi=None):
+        self.offset = int(offset)    # Philox stream id (iteration counter)
+        self.xi = xi                 # injected increments, reference layout (K_local, d, N+1) on the device, or None
+        self.X_N = None              # filled by the forward pass
+        self.stats = None
+
+
+class RolloutEngine:
+    def __init__(self, problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive=True, k_offset=0,
+                 K_global=None, seed=42, device=None, want_X_N=True):
+        self.lib = L.load()
+        self.device = pt.device("cuda", pt.cuda.current_device()) if device is None else pt.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("the fused rollout runs on CUDA devices only (got %s)" % self.device)
+        self.d, self.N, self.K_local, self.k_offset = int(problem.d), int(N), int(K_local), int(k_offset)
+        self.K_global = int(K_global if K_global is not None else K_local)
+        self.net_id, self.dims, self.time_mode = net_id, list(dims), time_mode
+        self.adaptive, self.seed = bool(adaptive), int(seed)
+        # delta_t enters the arithmetic as an fp32 scalar, like the reference's 0-dim tensor (solver.py:39)
+        self.dt = float(pt.tensor(delta_t, dtype=pt.float32))
+        pid, flags, pack = problem.functor_pack()
+        self.problem_id, self.flags = pid, flags
+        self.pack = pack.to(self.device)
+        self.x0 = problem.X_0.detach().to(self.device, pt.float32).contiguous()
+        self.x0_per_path = False
+        self.want_X_N = want_X_N
+        f32 = dict(dtype=pt.float32, device=self.device)
+        self.Y_N, self.gX, self.Zsum = (pt.empty(self.K_local, **f32) for _ in range(3))
+        self.X_N = pt.empty(self.K_local, self.d, **f32) if want_X_N else None
+        self.stats = pt.zeros(4, dtype=pt.float64, device=self.device)
+        cfg = self.cfg(Call())
+        self.n_theta = int(self.lib.pspde_theta_size(ctypes.byref(cfg)))
+        if self.n_theta < 0:
+            raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
+        nbytes = int(self.lib.pspde_workspace_bytes(ctypes.byref(cfg)))
+        if nbytes == 0:
+            raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
+        self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
+
+    def set_x0(self, x0):
+        """(d,) broadcast start or (K_local, d) per-path starts (random_X_0, solver.py:366-367)."""
+        x0 = x0.detach().to(self.device, pt.float32).contiguous()
+        self.x0, self.x0_per_path = x0, x0.dim() == 2
+
+    def cfg(self, call):
+        noise = L.NOISE_PHILOX if call.xi is None else L.NOISE_INJECT
+        strides = (0, 0, 0)
+        if call.xi is not None:
+            xi = call.xi
+            if xi.dtype != pt.float32 or xi.device != self.device or tuple(xi.shape) != (self.K_local, self.d, self.N + 1):
+                raise ValueError("xi must be a float32 (K_local, d, N+1) tensor on %s" % self.device)
+            strides = (xi.stride(0), xi.stride(1), xi.stride(2))
+        return L.make_cfg(self.K_local, self.d, self.N, self.dt, self.problem_id, self.net_id, self.dims,
+                          self.time_mode, adaptive=self.adaptive, k_offset=self.k_offset, problem_flags=self.flags,
+                          noise_mode=noise, seed=self.seed, offset=call.offset, x0_per_path=self.x0_per_path,
+                          xi_strides=strides)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _xi_ptr(self, call):
+        # slice n+1 of the reference layout drives step n (solver.py:472)
+        return None if call.xi is None else ctypes.c_void_p(call.xi.data_ptr() + 4 * call.xi.stride(2))
+
+    def _stream(self):
+        return ctypes.c_void_p(pt.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, theta, y0, call):
+        cfg = self.cfg(call)
+        rc = self.lib.pspde_rollout_fwd(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+                                        self._p(y0), self._xi_ptr(call), self._p(self.X_N), self._p(self.Y_N),
+                                        self._p(self.gX), self._p(self.Zsum), self._p(self.stats),
+                                        self._p(self.workspace), self.workspace.numel(), self._stream())
+        L.check(self.lib, rc)
+
+    def backward_detached(self, theta, wY, wZ, call, grad_out):
+        cfg = self.cfg(call)
+        rc = self.lib.pspde_rollout_bwd_detached(ctypes.byref(cfg), self._p(theta), self._p(self.pack),
+                                                 self._p(self.x0), self._xi_ptr(call), self._p(wY), self._p(wZ),
+                                                 self._p(grad_out), self._p(self.workspace), self.workspace.numel(),
+                                                 self._stream())
+        L.check(self.lib, rc)
+
+    def attached(self, theta, call, grad_out):
+        cfg = self.cfg(call)
+        rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+                                             self._xi_ptr(call), ctypes.c_float(1.0 / self.K_global),
+                                             self._p(self.X_N), self._p(self.gX), self._p(self.Zsum),
+                                             self._p(self.stats), self._p(grad_out), self._p(self.workspace),
+                                             self.workspace.numel(), self._stream())
+        L.check(self.lib, rc)
+
+    def philox_dump(self, offset=0):
+        """Increments the kernels generate for iteration `offset`, in the reference layout (K_local, d, N+1)."""
+        out = pt.empty(self.N, self.K_local, self.d, dtype=pt.float32, device=self.device)
+        cfg = self.cfg(Call(offset))
+        L.check(self.lib, self.lib.pspde_philox_dump(ctypes.byref(cfg), self._p(out), self._stream()))
+        xi = pt.zeros(self.K_local, self.d, self.N + 1, dtype=pt.float32, device=self.device)
+        xi[:, :, 1:] = out.permute(1, 2, 0)
+        return xi
+
+
+class FusedRollout(pt.autograd.Function):
+    """(theta, y0) -> per-path (Y_N, g(X_N), Z_sum) for a theta-independent (detached) forward process."""
+
+    @staticmethod
+    def forward(ctx, theta, y0, engine, call):
+        theta_c = theta.detach().contiguous()
+        y0_c = None if y0 is None else y0.detach().contiguous()
+        engine.forward(theta_c, y0_c, call)
+        call.X_N, call.stats = engine.X_N, engine.stats
+        ctx.engine, ctx.call, ctx.has_y0 = engine, call, y0 is not None
+        ctx.save_for_backward(theta_c)
+        Y, gX, Zsum = engine.Y_N.clone(), engine.gX.clone(), engine.Zsum.clone()
+        ctx.mark_non_differentiable(gX)
+        return Y, gX, Zsum
+
+    @staticmethod
+    def backward(ctx, gY, ggX, gZsum):
+        (theta_c,) = ctx.saved_tensors
+        engine = ctx.engine
+        wY = pt.zeros(engine.K_local, dtype=pt.float32, device=engine.device) if gY is None else gY.contiguous().float()
+        wZ = None if gZsum is None else gZsum.contiguous().float()
+        grad = pt.empty(engine.n_theta, dtype=pt.float32, device=engine.device)
+        engine.backward_detached(theta_c, wY, wZ, ctx.call, grad)
+        gy0 = wY.sum().reshape(1) if ctx.has_y0 else None
+        return grad, gy0, None, None
+
+
+class FusedRolloutAttached(pt.autograd.Function):
+    """theta -> sum_k (Z_sum + g(X_N))_k / K_global over the local shard, attached forward process."""
+
+    @staticmethod
+    def forward(ctx, theta, engine, call):
+        theta_c = theta.detach().contiguous()
+        grad = pt.empty(engine.n_theta, dtype=pt.float32, device=engine.device)
+        engine.attached(theta_c, call, grad)
+        call.X_N, call.stats = engine.X_N, engine.stats
+        ctx.save_for_backward(grad)
+        return (engine.stats[2] / engine.K_global).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None

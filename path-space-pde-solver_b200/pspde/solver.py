@@ -1,0 +1,305 @@
+"""Solver with the interface of the reference's ``Solver`` (solver.py:18-557), running the training hot path --
+noise, N-step Euler-Maruyama rollout, per-step network evaluation, path-space loss and its gradient
+(solver.py:433-499, :221) -- as fused sm_100a CUDA kernels (pspde.fused / libpspde.so).
+
+Kept from the reference: the constructor signature (solver.py:20-25), the mutable attributes ``z_n``, ``y_0``,
+``Phis`` with ``update_Phis()`` (:142-162), ``train()`` (:420), ``Z_n(X, t)`` (:360-362), the per-module Adam
+(:198-200) and the result lists ``loss_log, u_L2_loss, Y_0_log, IS_rel_log, times, particles_close_to_target``
+(:112-119).  Added keyword arguments:
+    noise='philox' | 'inject'   in-kernel counter-based noise (default) or the reference's CPU draw
+                                xi = randn(K, d, N+1) (:381) pushed to the device (parity mode: identical
+                                torch RNG stream, hence identical trajectories to the reference)
+    device                      CUDA device (default: current)
+    process_group               torch.distributed group; K is the GLOBAL batch, sharded over its ranks
+There is no CPU fallback; options of the reference that are off the fused path raise NotImplementedError.
+"""
+import time
+from datetime import date
+
+import numpy as np
+import torch as pt
+
+from . import _lib as L
+from . import dist, losses
+from .function_space import DenseNet, MySequential, SingleParam
+from .fused import Call, FusedRollout, FusedRolloutAttached, RolloutEngine
+
+
+class Solver:
+
+    def __init__(self, name, problem, lr=0.001, L=10000, K=50, delta_t=0.05,
+                 approx_method='control', loss_method='log-variance', time_approx='outer',
+                 learn_Y_0=False, adaptive_forward_process=True, detach_forward=False,
+                 early_stopping_time=10000, random_X_0=False, compute_gradient_variance=0,
+                 IS_variance_K=0, IS_variance_iter=1, metastability_logs=None, print_every=100,
+                 plot_trajectories=None, seed=42, save_results=False, u_l2_error_flag=True, log_gradient=False,
+                 burgers_drift=False, verbose=True, noise='philox', device=None, process_group=None):
+        self.problem, self.name = problem, name
+        self.date = date.today().strftime('%Y-%m-%d')
+        self.d, self.T, self.X_0 = problem.d, problem.T, problem.X_0
+        self.Y_0 = pt.tensor([0.0])
+
+        self.device = pt.device('cuda', pt.cuda.current_device()) if device is None else pt.device(device)
+        self.seed = seed
+        self.delta_t_np = delta_t
+        self.delta_t = pt.tensor(self.delta_t_np).to(self.device)
+        self.sq_delta_t = pt.sqrt(self.delta_t).to(self.device)
+        self.N = int(np.floor(self.T / self.delta_t_np))         # host float64, like solver.py:41
+        self.lr, self.L, self.K, self.random_X_0 = lr, L, K, random_X_0
+
+        self.loss_method, self.approx_method, self.learn_Y_0 = loss_method, approx_method, learn_Y_0
+        self.adaptive_forward_process, self.detach_forward = adaptive_forward_process, detach_forward
+        self.early_stopping_time, self.burgers_drift = early_stopping_time, burgers_drift
+        self.has_ref_solution = hasattr(problem, 'u_true')
+        self.u_l2_error_flag = u_l2_error_flag and self.has_ref_solution
+        if self.loss_method == 'relative_entropy':
+            self.adaptive_forward_process = True                  # solver.py:61-62
+        if self.loss_method == 'cross_entropy':
+            self.learn_Y_0 = False                                # solver.py:63-64
+
+        self.print_every, self.verbose, self.save_results = print_every, verbose, save_results
+        self.compute_gradient_variance, self.IS_variance_K, self.IS_variance_iter = (
+            compute_gradient_variance, IS_variance_K, IS_variance_iter)
+        self.metastability_logs, self.plot_trajectories, self.log_gradient = (
+            metastability_logs, plot_trajectories, log_gradient)
+        self.noise, self.process_group = noise, process_group
+        if noise not in ('philox', 'inject'):
+            raise ValueError("noise must be 'philox' or 'inject'")
+
+        self.Phis, self.time_approx = [], time_approx
+        pt.manual_seed(seed)                                      # solver.py:84
+        if self.approx_method == 'control':
+            self.y_0 = SingleParam(lr=self.lr).to(self.device)
+            if self.time_approx == 'outer':
+                self.z_n = [DenseNet(d_in=self.d, d_out=self.d, lr=self.lr, seed=seed) for _ in range(self.N)]
+            elif self.time_approx == 'inner':
+                self.z_n = MySequential(d_in=self.d + 1, d_out=self.d, lr=self.lr, seed=123)   # solver.py:91
+            else:
+                raise ValueError("time_approx must be 'outer' or 'inner'")
+        else:
+            raise NotImplementedError("approx_method=%r is off the fused hot path (only 'control')" % approx_method)
+        self.update_Phis()
+        for phi in self.Phis:
+            phi.train()
+
+        self.Y_0_log, self.loss_log, self.u_L2_loss, self.IS_rel_log = [], [], [], []
+        self.times, self.grads_rel_error_log, self.particles_close_to_target = [], [], []
+        self.path_steps_per_sec = []
+        self._iteration = 0
+
+    # ------------------------------------------------------------------ problem pass-throughs (solver.py:121-140)
+    def b(self, x):
+        return self.problem.b(x)
+
+    def sigma(self, x):
+        return self.problem.sigma(x)
+
+    def h(self, t, x, y, z):
+        return self.problem.h(t, x, y, z)
+
+    def f(self, x, t):
+        return self.problem.f(x, t)
+
+    def g(self, x):
+        return self.problem.g(x)
+
+    def u_true(self, x, t):
+        return self.problem.u_true(x, t)
+
+    def v_true(self, x, t):
+        return self.problem.v_true(x, t)
+
+    # ------------------------------------------------------------------ parameters
+    def _nets(self):
+        return list(self.z_n) if self.time_approx == 'outer' else [self.z_n]
+
+    def update_Phis(self):
+        """Collect the trainable modules (solver.py:142-162) and re-home their parameters in ONE flat device buffer
+        (theta layout of include/pspde.h: parameters() order, N stacked sets in 'outer' mode).  The nn.Parameters
+        become views of that buffer and their .grad views of the flat gradient, so the kernels read theta and
+        write dLoss/dtheta in place and every module's own Adam keeps working unchanged."""
+        nets = self._nets()
+        self.Phis = nets + [self.y_0] if self.learn_Y_0 else list(nets)
+        for phi in self.Phis:
+            phi.to(self.device)
+        self.p = sum(int(np.prod(q.size())) for q in self.Phis[0].parameters() if q.requires_grad)
+        spec = nets[0].net_spec() if hasattr(nets[0], 'net_spec') else None
+        if spec is None:
+            raise NotImplementedError("%s has no fused kernel (supported: DenseNet, MySequential)"
+                                      % type(nets[0]).__name__)
+        for m in nets[1:]:
+            if m.net_spec() != spec:
+                raise NotImplementedError("'outer' mode needs identically shaped networks")
+        self._net_id, self._dims = spec
+        params = [q for m in nets for q in m.parameters()]
+        n = sum(q.numel() for q in params)
+        flat = pt.empty(n, dtype=pt.float32, device=self.device)
+        gflat = pt.zeros(n, dtype=pt.float32, device=self.device)
+        off = 0
+        for q in params:
+            k = q.numel()
+            flat[off:off + k].copy_(q.data.reshape(-1))
+            q.data = flat[off:off + k].view(q.shape)
+            q.grad = gflat[off:off + k].view(q.shape)
+            off += k
+        self._theta = flat.requires_grad_(True)
+        self._theta.grad = gflat
+        self._params = params
+        self._engine = None
+        if self.log_gradient:
+            self.gradient_log = pt.zeros(self.L, self.p)
+
+    def zero_grad(self):
+        self._theta.grad.zero_()
+        if self.learn_Y_0 and self.y_0.Y_0.grad is not None:
+            self.y_0.Y_0.grad.zero_()
+
+    def optimization_step(self):
+        for phi in self.Phis:                                     # one Adam per module, solver.py:198-200
+            phi.optim.step()
+
+    def _ensure_grad_views(self):
+        # optimizers may have dropped .grad (zero_grad(set_to_none=True)); restore the views of the flat gradient
+        off = 0
+        g = self._theta.grad
+        for q in self._params:
+            k = q.numel()
+            if q.grad is None or q.grad.data_ptr() != g.data_ptr() + 4 * off:
+                q.grad = g[off:off + k].view(q.shape)
+            off += k
+
+    # ------------------------------------------------------------------ engine
+    def _get_engine(self):
+        if self._engine is None:
+            unsupported = []
+            if self.burgers_drift:
+                unsupported.append('burgers_drift')
+            if self.compute_gradient_variance:
+                unsupported.append('compute_gradient_variance')
+            if self.loss_method not in losses.SUPPORTED:
+                unsupported.append('loss_method=%r' % self.loss_method)
+            if not self.detach_forward and self.loss_method != 'relative_entropy':
+                unsupported.append('detach_forward=False with loss_method=%r' % self.loss_method)
+            if not self.detach_forward and self.learn_Y_0:
+                unsupported.append('learn_Y_0 with detach_forward=False')
+            if unsupported:
+                raise NotImplementedError("off the fused hot path: " + ", ".join(unsupported))
+            rank, W = dist.world(self.process_group)
+            lo, hi = dist.shard_range(self.K, rank, W)
+            self._k_lo, self._k_hi = lo, hi
+            tm = L.TIME_NONE if self.time_approx == 'outer' else L.TIME_FIRST
+            self._engine = RolloutEngine(self.problem, self._net_id, self._dims, tm, hi - lo, self.N, self.delta_t_np,
+                                         adaptive=self.adaptive_forward_process, k_offset=lo, K_global=self.K,
+                                         seed=self.seed, device=self.device)
+            if self._engine.n_theta != self._theta.numel():
+                raise RuntimeError("parameter count mismatch: modules %d vs kernel %d"
+                                   % (self._theta.numel(), self._engine.n_theta))
+        return self._engine
+
+    def initialize_training_data(self):
+        """Noise for one iteration.  'inject' reproduces solver.py:381 (CPU draw of the whole (K, d, N+1) tensor,
+        then H2D); 'philox' draws nothing here -- the kernels generate the increments from (seed, iteration)."""
+        eng = self._get_engine()
+        if self.random_X_0:
+            X0 = pt.randn(self.K, self.d)[self._k_lo:self._k_hi]  # solver.py:366-367
+            eng.set_x0(X0.to(self.device))
+        xi = None
+        if self.noise == 'inject':
+            xi = pt.randn(self.K, self.d, self.N + 1)[self._k_lo:self._k_hi].to(self.device)
+        return Call(offset=self._iteration, xi=xi)
+
+    # ------------------------------------------------------------------ one training iteration
+    def gradient_descent(self, call):
+        """zero_grad -> fused rollout -> loss -> fused backward -> Adam (solver.py:202-223)."""
+        eng = self._get_engine()
+        self.zero_grad()
+        self._ensure_grad_views()
+        if self.detach_forward:
+            y0 = self.y_0.Y_0 if self.learn_Y_0 else None
+            Y, gX, Zsum = FusedRollout.apply(self._theta, y0, eng, call)
+            loss, wY, wZ = losses.value_and_cotangents(self.loss_method, Y.detach(), gX, Zsum.detach(), self.K,
+                                                       self.adaptive_forward_process, self.process_group,
+                                                       stats=call.stats)
+            outs, cots = [], []
+            if wY is not None:
+                outs.append(Y); cots.append(wY)
+            if wZ is not None:
+                outs.append(Zsum); cots.append(wZ)
+            pt.autograd.backward(outs, cots)
+        else:
+            loss_local = FusedRolloutAttached.apply(self._theta, eng, call)
+            loss_local.backward()
+            loss = dist.all_reduce_sum_(loss_local.detach().double().reshape(1), self.process_group)[0]
+        self._ensure_grad_views()
+        dist.all_reduce_sum_(self._theta.grad, self.process_group)
+        if self.learn_Y_0 and self.y_0.Y_0.grad is not None:
+            dist.all_reduce_sum_(self.y_0.Y_0.grad, self.process_group)
+        self.optimization_step()
+        return loss
+
+    def train_step(self, l):
+        """One full training iteration (noise -> rollout -> loss -> backward -> Adam -> logs), solver.py:431-531."""
+        t_0 = time.time()
+        self._iteration = l
+        call = self.initialize_training_data()
+        if self.learn_Y_0:
+            self.Y_0_log.append(self.y_0.Y_0.item())
+        loss = self.gradient_descent(call)
+        if self.log_gradient:
+            self.gradient_log[l, :] = self._theta.grad[:self.p].detach().cpu()
+        self.loss_log.append(loss.item())                     # the only host sync of the iteration
+        self.u_L2_loss.append(float('nan'))                   # on-device u_true tables: SURVEY 8(f) row f2
+        if self.metastability_logs is not None:
+            target, epsilon = self.metastability_logs
+            X = call.X_N
+            close = (pt.sqrt(pt.sum((X - target) ** 2, 1)) < epsilon).float().sum().reshape(1).double()
+            self.particles_close_to_target.append(
+                (dist.all_reduce_sum_(close, self.process_group)[0] / self.K).item())
+        t_1 = time.time()
+        self.times.append(t_1 - t_0)
+        self.path_steps_per_sec.append(self.K * self.N / max(t_1 - t_0, 1e-12))
+        return self.loss_log[-1]
+
+    def train(self):
+        pt.manual_seed(self.seed)                                 # solver.py:422
+        if self.verbose:
+            print('d = %d, L = %d, K = %d, delta_t = %.2e, lr = %.2e, %s, %s, %s, %s'
+                  % (self.d, self.L, self.K, self.delta_t_np, self.lr, self.approx_method, self.time_approx,
+                     self.loss_method, 'adaptive' if self.adaptive_forward_process else ''))
+        if self.IS_variance_K > 0:
+            raise NotImplementedError("IS_variance_K > 0 (do_importance_sampling_me) is not on the fused path yet")
+        for l in range(self.L):
+            self.train_step(l)
+            if self.verbose and l % self.print_every == 0:
+                string = ('%d - loss: %.4e - u L2: %.4e - time/iter: %.2fs'
+                          % (l, self.loss_log[-1], self.u_L2_loss[-1], np.mean(self.times[-self.print_every:])))
+                if self.learn_Y_0:
+                    string += ' - Y_0: %.4e' % self.Y_0_log[-1]
+                print(string)
+            if self.early_stopping_time is not None and l > self.early_stopping_time:
+                if np.std(self.u_L2_loss[-self.early_stopping_time:]) / self.u_L2_loss[-1] < 0.02:
+                    break
+
+    # ------------------------------------------------------------------ host-side evaluation of the control
+    def Z_n_(self, X, n):
+        if self.time_approx == 'outer':
+            n = max(0, min(n, self.N - 1))
+            return self.z_n[n](X)
+        t_X = pt.cat([pt.ones([X.shape[0], 1], device=X.device) * n * self.delta_t, X], 1)
+        return self.z_n(t_X)
+
+    def Z_n(self, X, t):
+        n = int(pt.ceil(pt.as_tensor(t, dtype=pt.float32, device=self.device) / self.delta_t))
+        return self.Z_n_(X, n)
+
+    def save_networks(self):
+        path_name = 'output/%s_%s.pt' % (self.name, self.date)
+        pt.save({'nn%d' % i: z.state_dict() for i, z in enumerate(self.Phis)}, path_name)
+        print('\nnetworks data has been stored to file: %s' % path_name)
+
+    def load_networks(self, cp_name):
+        print('\nload network data from file: %s' % cp_name)
+        checkpoint = pt.load(cp_name)
+        for i, z in enumerate(self.Phis):
+            z.load_state_dict(checkpoint['nn%d' % i])             # copies into the flat-buffer views in place
+            z.eval()

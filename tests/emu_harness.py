@@ -20,11 +20,12 @@ _emu = None
 def emu_lib():
     global _emu
     if _emu is None:
-        srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "simt_emul.h")]
+        srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith("_")] + [os.path.join(EMU_DIR, "simt_emul.h")]
         if not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < max(os.path.getmtime(s) for s in srcs):
             os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+            cus = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DPSPDE_EMULATE", "-x", "c++",
-                                   "-I", EMU_DIR, "-I", CSRC, os.path.join(CSRC, "pspde_api.cu"), "-o", EMU_SO])
+                                   "-I", EMU_DIR, "-I", CSRC] + cus + ["-o", EMU_SO])
         _emu = L.bind(EMU_SO)
     return _emu
 

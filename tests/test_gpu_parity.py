@@ -1,0 +1,216 @@
+"""-m gpu: the sm_100a build (libpspde.so) driven through the C ABI by pspde.Solver / RolloutEngine, compared with
+the reference's golden vectors, the CPU oracle and size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+import torch as pt
+
+from conftest import HJB_TAGS, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # north_star: states, losses, gradients within 1e-5 relative (fp32) on identical Brownian increments
+
+
+def make_solver(g, K=None, noise="inject", **kw):
+    import pspde
+    d = g["d"]
+    pkw = dict(g["pkw"])
+    cls = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC, "dwm": pspde.DoubleWell_multidim}[g["kind"]]
+    prob = cls(d=d, device="cuda", **pkw)
+    S = pspde.Solver(g.get("tag", "t"), prob, lr=0.0, L=1, K=K or g["K"], delta_t=g["delta_t"],
+                     loss_method=g["loss_method"], time_approx=g["time_approx"], learn_Y_0=g["learn_Y_0"],
+                     adaptive_forward_process=g["adaptive"], detach_forward=g["detach_forward"],
+                     early_stopping_time=None, u_l2_error_flag=False, verbose=False, noise=noise, **kw)
+    if g["net"] == "densenet" and g["time_approx"] == "inner":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=0.0, seed=42)
+    if g["learn_Y_0"]:
+        S.y_0 = pspde.SingleParam(lr=0.0, initial=g["y0"]).to("cuda")
+    S.update_Phis()
+    assert S.N == g["N"]
+    return S
+
+
+@pytest.mark.parametrize("tag", HJB_TAGS)
+def test_golden_parity(tag):
+    """One training iteration on the reference's own inputs (theta, xi) -> X_N, Y_N, loss, dLoss/dtheta."""
+    from pspde.fused import Call
+    g = load_golden(tag)
+    S = make_solver(g)
+    with pt.no_grad():
+        S._theta.copy_(pt.tensor(g["theta"]))
+    call = Call(offset=0, xi=pt.tensor(g["xi"]).cuda())
+    loss = S.gradient_descent(call)
+    pt.cuda.synchronize()
+    eng = S._get_engine()
+    assert relerr(eng.X_N.cpu().numpy(), g["X_N"]) < TOL
+    assert relerr(eng.gX.cpu().numpy(), g["gX"]) < TOL
+    if g["detach_forward"]:
+        assert relerr(eng.Y_N.cpu().numpy(), g["Y_N"]) < TOL
+    if "relative_entropy" in g["loss_method"]:
+        assert relerr(eng.Zsum.cpu().numpy(), g["Zsum"]) < TOL
+    D = g["Y_N"].astype(np.float64) - g["gX"]
+    cond = 4 * 6e-8 * float((D ** 2).mean()) if "variance" in g["loss_method"] else 0.0   # SURVEY finding 9
+    assert abs(loss.item() - g["loss"]) <= TOL * abs(g["loss"]) + cond
+    assert relerr(S._theta.grad.cpu().numpy(), g["grad"]) < TOL
+    if g["learn_Y_0"]:
+        assert abs(S.y_0.Y_0.grad.item() - g["grad_y0"]) < 1e-4 * abs(g["grad_y0"])
+    assert eng.stats[3].item() == 0
+
+
+LOOPS = {
+    "loop_G1": dict(kind="lqgc", d=10, pkw={}, net="densenet", ta="outer", K=200, dt=0.05, L=3, lr=1e-3,
+                    loss="log-variance", detach=True),
+    "loop_G1b": dict(kind="lqgc", d=10, pkw={}, net="densenet", ta="inner", K=200, dt=0.05, L=3, lr=1e-3,
+                     loss="log-variance", detach=True),
+    "loop_G2": dict(kind="llgc", d=100, pkw=dict(off_diag=0, T=1, seed=42), net="densenet", ta="inner", K=256,
+                    dt=0.01, L=2, lr=1e-3, loss="log-variance", detach=True),
+    "loop_G3a": dict(kind="dwm", d=50, pkw=dict(d_1=15, d_2=35, T=1, eta=3, kappa=5), net="mlp", ta="inner", K=256,
+                     dt=0.005, L=2, lr=0.05, loss="log-variance", detach=True),
+    "loop_G3b": dict(kind="dwm", d=50, pkw=dict(d_1=15, d_2=35, T=1, eta=3, kappa=5), net="mlp", ta="inner", K=256,
+                     dt=0.005, L=2, lr=0.05, loss="relative_entropy", detach=False),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(LOOPS))
+def test_training_loop_reproduces_reference_loss_log(tag):
+    """Solver.train() with noise='inject' draws the reference's torch CPU noise stream, so the whole loop
+    (rollout, loss, gradient, Adam) must reproduce the reference's stored loss_log."""
+    import pspde
+    c, g = LOOPS[tag], load_golden(tag)
+    cls = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC, "dwm": pspde.DoubleWell_multidim}[c["kind"]]
+    prob = cls(d=c["d"], device="cuda", **c["pkw"])
+    S = pspde.Solver(tag, prob, lr=c["lr"], L=c["L"], K=c["K"], delta_t=c["dt"], loss_method=c["loss"],
+                     time_approx=c["ta"], detach_forward=c["detach"], early_stopping_time=None,
+                     u_l2_error_flag=False, verbose=False, noise="inject")
+    if c["net"] == "densenet" and c["ta"] == "inner":
+        S.z_n = pspde.DenseNet(d_in=c["d"] + 1, d_out=c["d"], lr=c["lr"], seed=42)
+        S.update_Phis()
+    S.train()
+    ref = g["loss_log"]
+    for a, b in zip(S.loss_log, ref):
+        # the reference evaluates mean(D^2) - mean(D)^2 in fp32 (finding 9): allow its own cancellation error
+        cond = 2e-4 * abs(b) if (c["loss"] == "log-variance" and c["kind"] == "dwm") else 0.0
+        assert abs(a - b) <= 2e-5 * abs(b) + cond, (S.loss_log, ref)
+    gn = float(S._theta.grad.norm())
+    assert abs(gn - g["grad_norm"]) < 1e-4 * g["grad_norm"]
+
+
+def test_philox_dump_and_rollout_vs_oracle():
+    """In-kernel Philox: the dumped increments match the numpy restatement, and the Philox rollout equals the
+    injected rollout fed with the dump (bit-exact, same kernel arithmetic)."""
+    from oracle import philox as ph
+    from pspde.fused import Call
+    g = load_golden("hjb_lqgc_d10_dense_lv")
+    K = 64 * 9 + 17
+    S = make_solver(dict(g, tag="ph"), K=K, noise="philox", seed=77)
+    eng = S._get_engine()
+    xi = eng.philox_dump(offset=5)
+    ref = ph.xi_tensor(77, 5, 0, K, g["d"], g["N"])
+    assert np.abs(xi.cpu().numpy() - ref).max() < 1e-5
+    theta = S._theta.detach()
+    eng.forward(theta, None, Call(offset=5))
+    Y1, X1 = eng.Y_N.clone(), eng.X_N.clone()
+    wY = pt.randn(K, device="cuda")
+    g1 = pt.empty(eng.n_theta, device="cuda")
+    eng.backward_detached(theta, wY, None, Call(offset=5), g1)
+    eng.forward(theta, None, Call(offset=5, xi=xi))
+    g2 = pt.empty(eng.n_theta, device="cuda")
+    eng.backward_detached(theta, wY, None, Call(offset=5, xi=xi), g2)
+    assert pt.equal(Y1, eng.Y_N) and pt.equal(X1, eng.X_N)
+    assert pt.equal(g1, g2)
+    z = xi[:, :, 1:]
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
+
+
+def test_sharding_invariance_single_gpu():
+    """Splitting K into two shards (k_offset) gives the same per-path results and the same summed gradient."""
+    import pspde
+    from pspde.fused import Call, RolloutEngine
+    from pspde import _lib as L
+    d, K, N = 10, 1000, 20
+    prob = pspde.LLGC(d=d, T=1.0, device="cuda")
+    net = pspde.DenseNet(d_in=d + 1, d_out=d, lr=0.0, seed=42).cuda()
+    theta = pt.cat([q.detach().reshape(-1) for q in net.parameters()])
+    mk = lambda lo, hi: RolloutEngine(prob, L.NET_DENSENET, net.nn_dims, L.TIME_FIRST, hi - lo, N, 0.05,
+                                      k_offset=lo, K_global=K, seed=3)
+    full, a, b = mk(0, K), mk(0, 600), mk(600, K)
+    w = pt.randn(K, device="cuda")
+    outs = []
+    for e, sl in ((full, slice(0, K)), (a, slice(0, 600)), (b, slice(600, K))):
+        e.forward(theta, None, Call(offset=2))
+        gr = pt.empty(e.n_theta, device="cuda")
+        e.backward_detached(theta, w[sl].contiguous(), None, Call(offset=2), gr)
+        outs.append((e.Y_N.clone(), e.X_N.clone(), gr, e.stats.clone()))
+    assert pt.equal(pt.cat([outs[1][0], outs[2][0]]), outs[0][0])
+    assert pt.equal(pt.cat([outs[1][1], outs[2][1]]), outs[0][1])
+    assert relerr((outs[1][2] + outs[2][2]).cpu().numpy(), outs[0][2].cpu().numpy()) < 1e-6
+    assert pt.allclose(outs[1][3] + outs[2][3], outs[0][3], rtol=1e-12)
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] size (K = 2^16, d = 100, N = 100): determinism, statistics consistency, linearity of
+    the backward pass in the cotangent, and the analytic structure E[D] -> -V(0,0)-like drift of the loss."""
+    import pspde
+    from pspde.fused import Call
+    d, K = 100, 1 << 16
+    prob = pspde.LLGC(d=d, off_diag=0, T=1, seed=42, device="cuda")
+    S = pspde.Solver("c2", prob, K=K, L=1, delta_t=0.01, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, early_stopping_time=None, verbose=False)
+    S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+    S.update_Phis()
+    eng = S._get_engine()
+    theta = S._theta.detach()
+    eng.forward(theta, None, Call(offset=0))
+    Y, gX, st = eng.Y_N.clone(), eng.gX.clone(), eng.stats.clone()
+    eng.forward(theta, None, Call(offset=0))
+    assert pt.equal(Y, eng.Y_N) and pt.equal(st, eng.stats)                 # deterministic
+    D = (Y - gX).double()
+    assert pt.allclose(st[:2], pt.stack([D.sum(), (D * D).sum()]), rtol=1e-10)
+    assert st[3].item() == 0 and bool(pt.isfinite(Y).all())
+    w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    gs = []
+    for w in (w1, w2, (w1 + 2 * w2).contiguous()):
+        gr = pt.empty(eng.n_theta, device="cuda")
+        eng.backward_detached(theta, w, None, Call(offset=0), gr)
+        gs.append(gr)
+    assert relerr((gs[0] + 2 * gs[1]).cpu().numpy(), gs[2].cpu().numpy()) < 2e-5   # linear in the cotangent
+    gr2 = pt.empty(eng.n_theta, device="cuda")
+    eng.backward_detached(theta, w1, None, Call(offset=0), gr2)
+    assert pt.equal(gr2, gs[0])                                                    # deterministic reduction
+    # a few training iterations reduce the log-variance loss
+    S.L = 6
+    S.train()
+    assert S.loss_log[-1] < S.loss_log[0] and all(np.isfinite(S.loss_log))
+
+
+def test_trained_value_matches_analytic_llgc():
+    """LLGC(A=-I, B=I, alpha=1): V(0,0) = -(d/4)(1 - exp(-2T)).  After training with the log-variance loss,
+    -mean(D) estimates V(0,0) (D = Y_N - g(X_N) becomes path-wise constant at the optimum)."""
+    import pspde
+    d, T = 10, 1.0
+    prob = pspde.LLGC(d=d, T=T, device="cuda")
+    S = pspde.Solver("ana", prob, K=4096, L=400, lr=5e-3, delta_t=0.01, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, early_stopping_time=None, verbose=False)
+    S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=5e-3, seed=42)
+    S.update_Phis()
+    S.train()
+    eng = S._get_engine()
+    V00 = -(d / 4) * (1 - np.exp(-2 * T))
+    est = -(eng.stats[0].item() / S.K)
+    assert S.loss_log[-1] < 0.05 * S.loss_log[0]
+    assert abs(est - V00) < 0.02 * abs(V00), (est, V00)
+    # control vs u*(x, t) = -exp(-(T - t)) at t = 0.5
+    X = pt.randn(256, d, device="cuda")
+    u = -S.Z_n_(X, 50)
+    assert (u + np.exp(-(T - 0.5))).abs().mean().item() < 0.05
+
+
+def test_no_cpu_fallback_and_error_reporting():
+    import pspde
+    from pspde import _lib
+    prob = pspde.LLGC(d=4, T=0.5, device="cuda")
+    S = pspde.Solver("e", prob, K=8, delta_t=0.05, time_approx="inner", verbose=False)     # attached log-variance
+    with pytest.raises(NotImplementedError):
+        S.train()
+    lib = _lib.load()
+    assert lib.pspde_abi_version() == _lib.ABI_VERSION

@@ -1,0 +1,178 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the Solver's flat
+parameter buffer, sharding, the loss/cotangent formulas, problem reference solutions, and a world-size-2 gloo run."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch as pt
+
+from conftest import ROOT, load_golden, relerr
+from oracle import manual as man
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    from pspde import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "pspde.h")).read()
+    declared = set(re.findall(r"\b(pspde_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    bound = _lib.bind(_lib.LIB_PATH)                     # no compute calls without a GPU
+    assert bound.pspde_abi_version() == _lib.ABI_VERSION
+    assert ctypes.sizeof(_lib.pspde_cfg) == 112      # static_assert-ed in csrc/api_common.h
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import pspde
+    if pt.cuda.is_available():
+        pytest.skip("CUDA present")
+    prob = pspde.LLGC(d=4, T=0.5, device="cpu")
+    with pytest.raises(Exception):
+        pspde.Solver("x", prob, K=8, delta_t=0.05, time_approx="inner", verbose=False)       # default device = cuda
+    S = pspde.Solver("x", prob, K=8, delta_t=0.05, time_approx="inner", detach_forward=True, verbose=False,
+                     device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA|no CPU fallback"):
+        S.train()
+
+
+def test_flat_parameter_buffer_and_module_adam():
+    import pspde
+    prob = pspde.LQGC(d=3, T=0.25, device="cpu")
+    S = pspde.Solver("x", prob, K=8, delta_t=0.05, lr=0.1, detach_forward=True, verbose=False, device="cpu")
+    assert S.N == 5 and len(S.z_n) == 5 and S._theta.numel() == 5 * S.p
+    off = 0
+    for net in S.z_n:
+        for q in net.parameters():
+            assert q.data_ptr() == S._theta.data_ptr() + 4 * off
+            assert q.grad.data_ptr() == S._theta.grad.data_ptr() + 4 * off
+            off += q.numel()
+    # same seeds -> bit-equal initial weights to the reference's constructors (oracle restates their draw order)
+    from oracle import ref_port as orc
+    ref = orc.densenet_init(3, 3, seed=42)
+    for a, b in zip(S.z_n[0].parameters(), ref):
+        assert pt.equal(a.detach(), b)
+    before = S._theta.detach().clone()
+    S._theta.grad.fill_(1.0)
+    S.optimization_step()                               # every module's own Adam steps through the views
+    assert pt.allclose(S._theta.detach(), before - 0.1, atol=1e-6)
+    S2 = pspde.Solver("x", prob, K=8, delta_t=0.05, time_approx="inner", verbose=False, device="cpu")
+    for a, b in zip(S2.z_n.parameters(), orc.mlp_init(4, 3, seed=123)):
+        assert pt.equal(a.detach(), b)
+
+
+def test_shard_range_covers_everything():
+    from pspde.dist import shard_range
+    for K in (1, 7, 200, 65536, 65537):
+        for W in (1, 2, 3, 8):
+            r = [shard_range(K, i, W) for i in range(W)]
+            assert r[0][0] == 0 and r[-1][1] == K
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+@pytest.mark.parametrize("method", ["log-variance", "moment", "variance", "cross_entropy", "relative_entropy"])
+def test_loss_cotangents_match_oracle(method):
+    from pspde import losses
+    rng = np.random.default_rng(1)
+    K = 257
+    Y, gX, Zs = rng.standard_normal(K), rng.standard_normal(K), rng.random(K)
+    lv, wY, wZ = man.loss_and_weights(method, Y, gX, Zs, True)
+    t = lambda a: pt.tensor(a, dtype=pt.float32)
+    loss, a, b = losses.value_and_cotangents(method, t(Y), t(gX), t(Zs), K, True)
+    assert abs(loss.item() - lv) < 1e-5 * max(1, abs(lv))
+    if a is not None:
+        assert relerr(a.numpy(), wY) < 1e-5
+    else:
+        assert np.all(wY == 0)
+    if b is not None:
+        assert relerr(b.numpy(), wZ) < 1e-6
+
+
+def test_problem_reference_solutions():
+    import pspde
+    p = pspde.LLGC(d=10, off_diag=0.1, T=1, device="cpu")
+    v = p.v_true(pt.zeros(1, 10), 0.0)
+    assert abs(float(v) - (-2.5651046)) < 1e-5           # SURVEY.md Appendix B known answer
+    p = pspde.LLGC(d=100, off_diag=0, T=1, device="cpu")
+    assert np.allclose(p.u_true(pt.zeros(3, 100), 0.25), -np.exp(-0.75))
+    dw = pspde.DoubleWell(eta=3, kappa=5, device="cpu")
+    dw.compute_reference_solution()
+    assert abs(float(dw.v_true(pt.tensor([[-1.0, 0.0]]), 0.0)[0, 0]) - 8.6673) < 1e-3
+    lq = pspde.LQGC(d=2, device="cpu")
+    assert lq.F.shape == (101, 2, 2) and pt.allclose(lq.F[100], pt.eye(2))
+    assert float(lq.v_true(pt.zeros(1, 2), 0.0)) == pytest.approx(float(lq.G[0]))
+    he = pspde.HeatEquation(d=5, T=1, device="cpu")
+    assert float(he.v_true(pt.ones(1, 5), 0.25)) == pytest.approx(5 + 2 * 0.75 * 5)
+    for prob in (p, dw, lq, he, pspde.DoubleWell_multidim(d=4, d_1=2, d_2=2, eta=3, kappa=5, device="cpu")):
+        pid, flags, pack = prob.functor_pack()
+        assert pack.dtype == pt.float32 and pack.numel() >= 7 * prob.d
+
+
+def test_problem_functors_match_oracle():
+    import pspde
+    from oracle import ref_port as orc
+    x = pt.randn(6, 5)
+    z = pt.randn(6, 5)
+    for kind, mine, kw in (("llgc", pspde.LLGC, dict(off_diag=0.2, T=1)), ("lqgc", pspde.LQGC, dict(off_diag=0.2, T=1)),
+                           ("dwm", pspde.DoubleWell_multidim, dict(d_1=2, d_2=3, eta=3, kappa=5))):
+        a, b = mine(d=5, device="cpu", **kw), orc.make_problem(kind, 5, **kw)
+        assert pt.allclose(a.b(x), b.b(x), atol=1e-6) and pt.allclose(a.g(x), b.g(x), atol=1e-5)
+        assert pt.allclose(a.h(0.1, x, None, z), b.h(0.1, x, None, z), atol=1e-5)
+        assert pt.allclose(a.f(x, 0.1), b.f(x, 0.1), atol=1e-5)
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "path-space-pde-solver_b200"))
+import numpy as np, torch as pt, torch.distributed as td
+from pspde import losses
+from pspde.dist import shard_range, world, all_reduce_sum_
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, W = world()
+K = 101
+rng = np.random.default_rng(0)
+Y, gX, Zs = (pt.tensor(rng.standard_normal(K), dtype=pt.float32) for _ in range(3))
+lo, hi = shard_range(K, rank, W)
+ok = True
+for m in ("log-variance", "moment", "variance", "cross_entropy", "relative_entropy"):
+    full = losses.value_and_cotangents.__wrapped__(m, Y, gX, Zs, K) if hasattr(losses.value_and_cotangents, "__wrapped__") else None
+    loss, wY, wZ = losses.value_and_cotangents(m, Y[lo:hi], gX[lo:hi], Zs[lo:hi], K)
+    # single-process reference computed without any process group semantics: emulate by gathering
+    parts = [None, None]
+    td.all_gather_object(parts, (None if wY is None else wY.numpy(), None if wZ is None else wZ.numpy(), loss.item()))
+    if rank == 0:
+        from oracle import manual as man
+        lv, oY, oZ = man.loss_and_weights(m, Y.double().numpy(), gX.double().numpy(), Zs.double().numpy(), True)
+        ok &= abs(parts[0][2] - lv) < 1e-5 * max(1, abs(lv)) and abs(parts[1][2] - lv) < 1e-5 * max(1, abs(lv))
+        if parts[0][0] is not None:
+            ok &= np.allclose(np.concatenate([parts[0][0], parts[1][0]]), oY, rtol=2e-5, atol=1e-7)
+        if parts[0][1] is not None:
+            ok &= np.allclose(np.concatenate([parts[0][1], parts[1][1]]), oZ, rtol=2e-5, atol=1e-9)
+g = pt.full((5,), float(rank + 1))
+all_reduce_sum_(g)
+ok &= bool((g == 3).all())
+td.destroy_process_group()
+if rank == 0:
+    print("GLOO_OK" if ok else "GLOO_FAIL")
+'''
+
+
+def test_world_size_2_gloo_sharded_statistics(tmp_path):
+    """N>1 host logic on CPU: contiguous sharding + all_reduce of the loss statistics / gradient over gloo give the
+    same loss value and per-path cotangents as one process."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GLOO_OK" in outs[0][0], outs
