@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/pspde.h"
@@ -105,6 +106,10 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
   const int sms = pspde_sm_count();
   if (sms <= 0) return fail(-10, "no CUDA device");
   pl.grid = pl.n_tiles < sms ? pl.n_tiles : sms;
+  if (const char* mg = getenv("PSPDE_MAX_GRID")) {   // debugging hook: fewer CTAs -> more tiles per CTA
+    const int v = atoi(mg);
+    if (v > 0 && v < pl.grid) pl.grid = v;
+  }
   pl.T = 512; pl.NB = 1;
   if (bwd) {
     const int nb = pl.g.n_blocks;

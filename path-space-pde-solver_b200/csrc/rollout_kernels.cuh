@@ -293,6 +293,10 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
     float* xr = smem + sl.act + p * g.lda + g.x_col;
     float* er = smem + sl.xi + p * g.ldz;
     const float wy = BWD ? swY[p] : 0.f, wz = BWD ? swZ[p] : 0.f;
+    // BWD: a row with zero cotangents (padding, or a trajectory whose D was non-finite and was therefore given
+    // zero weight by the host) is inert: its state stays at X_0 so that all its activations remain finite and
+    // every product it contributes to the weight gradient is exactly 0 (0 * NaN would poison the gradient).
+    const bool inert = BWD && wy == 0.f && wz == 0.f;
     float zz = 0.f, zxi = 0.f, ff = 0.f, gg = 0.f;
     if (!dense) {
       for (int j = lane; j < d; j += 32) {
@@ -304,7 +308,7 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
         const float xn = x + (drift + b_d[j] * c) * dt + (b_d[j] * e) * sq;
         ff = fmaf(p_d[j] * xn, xn, ff);
         if (last) gg += al[j] * xn + r_d[j] * xn * xn + eta[j] * (xn - 1.0f) * (xn - 1.0f);
-        if (BWD) { er[j] = wy * (sq * e + kA * dt * z) + wz * dt * z; zr[j] = xn; }
+        if (BWD) { er[j] = inert ? 0.f : wy * (sq * e + kA * dt * z) + wz * dt * z; zr[j] = inert ? x : xn; }
         else xr[j] = xn;
       }
     } else {
@@ -338,7 +342,7 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
       for (int q = 0; q < 4; ++q) {
         const int i = lane + 32 * q;
         if (i < d) {
-          if (BWD) { er[i] = ze_loc[q]; zr[i] = xn_loc[q]; }
+          if (BWD) { er[i] = inert ? 0.f : ze_loc[q]; zr[i] = inert ? xr[i] : xn_loc[q]; }
           else xr[i] = xn_loc[q];
         }
       }
@@ -479,6 +483,10 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       float x = 0.f;
       if (prm.x0_per_path) { if (k < prm.K_local) x = __ldg(prm.x0 + (size_t)k * d + j); }
       else x = __ldg(prm.x0 + j);
+      if (BWD) {   // inert rows (zero cotangents, see sde_step) sit at the origin: finite activations whatever X_0 is
+        const bool live = k < prm.K_local && ((prm.wY && __ldg(prm.wY + k) != 0.f) || (prm.wZ && __ldg(prm.wZ + k) != 0.f));
+        if (!live) x = 0.f;
+      }
       sAct[p * g.lda + g.x_col + j] = x;
     }
     for (int p = tid; p < P; p += T) {
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           if (prm.Zsum) prm.Zsum[k] = ZS;
           if (prm.Y_N) prm.Y_N[k] = sY[tid];
           const double v = (double)ZS + (double)G;
-          if (isfinite(v)) s2 = v; else s3 = 1.0;
+          if (isfinite(v)) s2 = v; else { s3 = 1.0; swY[tid] = 0.f; }   // dropped from the batch and counted
         }
       }
       if (warp < (P + 31) / 32) {
@@ -654,12 +662,13 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
         }
       }
     }
+    __syncthreads();   // weights of non-finite trajectories were zeroed above
     for (int p = warp; p < P; p += NW) {
       const float w = swY[p];
       const float* xr = sAct + p * g.lda + g.x_col;
       for (int j = lane; j < d; j += 32) {
         const float x = xr[j];
-        sLam[p * g.ldz + j] = w * (al[j] + 2.0f * r_d[j] * x + 2.0f * eta[j] * (x - 1.0f));
+        sLam[p * g.ldz + j] = (w != 0.f) ? w * (al[j] + 2.0f * r_d[j] * x + 2.0f * eta[j] * (x - 1.0f)) : 0.f;
       }
     }
     __syncthreads();   // X_N has been copied out by the flat loop above before any row is overwritten below
@@ -671,8 +680,10 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
         float* xr = sAct + p * g.lda + g.x_col;
         float* lr = sLam + p * g.ldz;
         for (int j = lane; j < d; j += 32) {
-          lr[j] += w * dt * 2.0f * p_d[j] * xr[j];                 // grad f at X_{n+1} (f = x'Px, P diagonal)
-          xr[j] = ck[(size_t)n * P * d + p * d + j];               // reload X_n
+          if (w != 0.f) {
+            lr[j] += w * dt * 2.0f * p_d[j] * xr[j];               // grad f at X_{n+1} (f = x'Px, P diagonal)
+            xr[j] = ck[(size_t)n * P * d + p * d + j];             // reload X_n
+          } else { lr[j] = 0.f; xr[j] = 0.f; }                     // inert row: finite state, zero adjoint
         }
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;

@@ -12,28 +12,38 @@ SUPPORTED = ("log-variance", "moment", "variance", "cross_entropy", "relative_en
 
 def value_and_cotangents(method, Y, gX, Zsum, K_global, adaptive=True, group=None, stats=None):
     """Y, gX, Zsum: (K_local,) fp32.  stats: optional fp64 [sum D, sum D^2, sum(Zsum+gX), #nonfinite] of the local
-    shard as produced by the forward kernel.  Returns (loss fp64 0-dim, wY fp32 or None, wZ fp32 or None)."""
-    K = float(K_global)
+    shard as produced by the forward kernel (non-finite trajectories already excluded from the sums).
+    Returns (loss fp64 0-dim, wY fp32 or None, wZ fp32 or None, n_bad fp64 0-dim).
+
+    Trajectories whose D = Y_N - g(X_N) is not finite (a rare blow-up of the untrained feedback control at large
+    K) are dropped from the batch: zero cotangent, statistics over the K_eff = K - n_bad remaining ones.  The
+    reference would return NaN for the whole batch in that case (NaNs propagate silently, SURVEY.md section 5);
+    with no such trajectory the formulas below are exactly solver.py:164-192."""
     D = (Y - gX).double()
+    ok = pt.isfinite(D) & pt.isfinite(Zsum)
+    n_bad = all_reduce_sum_((~ok).sum().double().reshape(1), group)[0]
+    K = float(K_global) - n_bad
+    D = pt.where(ok, D, pt.zeros_like(D))
+    zero = pt.zeros_like(D)
     if method in ("log-variance", "moment"):
         s = stats[:2].clone() if stats is not None else pt.stack([D.sum(), (D * D).sum()])
         all_reduce_sum_(s, group)
         mean = s[0] / K
         if method == "moment":                                       # :165-166
-            return s[1] / K, (D * (2.0 / K)).float(), None
-        return s[1] / K - mean * mean, ((D - mean) * (2.0 / K)).float(), None   # :167-168 (biased variance)
+            return s[1] / K, pt.where(ok, D * (2.0 / K), zero).float(), None, n_bad
+        return s[1] / K - mean * mean, pt.where(ok, (D - mean) * (2.0 / K), zero).float(), None, n_bad   # :167-168
     if method == "variance":                                         # :171-172  pt.var (unbiased) of exp(-g + Y)
-        E = pt.exp(D)
+        E = pt.where(ok, pt.exp(D), zero)
         s = all_reduce_sum_(pt.stack([E.sum(), (E * E).sum()]), group)
         mean = s[0] / K
-        return (s[1] - K * mean * mean) / (K - 1.0), (2.0 * (E - mean) * E / (K - 1.0)).float(), None
+        return (s[1] - K * mean * mean) / (K - 1.0), pt.where(ok, 2.0 * (E - mean) * E / (K - 1.0), zero).float(), None, n_bad
     if method == "cross_entropy":                                    # :183-186
-        E = pt.exp(D) if adaptive else pt.exp(-gX.double())
-        s = all_reduce_sum_((Y.double() * E).sum().reshape(1), group)
-        return s[0] / K, (E / K).float(), None
+        E = pt.where(ok, pt.exp(D) if adaptive else pt.exp(-gX.double()), zero)
+        s = all_reduce_sum_((pt.where(ok, Y.double(), zero) * E).sum().reshape(1), group)
+        return s[0] / K, (E / K).float(), None, n_bad
     if method == "relative_entropy":                                 # :179-180 with a detached forward process
-        s = stats[2:3].clone() if stats is not None else (Zsum.double() + gX.double()).sum().reshape(1)
+        s = stats[2:3].clone() if stats is not None else pt.where(ok, Zsum.double() + gX.double(), zero).sum().reshape(1)
         all_reduce_sum_(s, group)
-        return s[0] / K, None, pt.full_like(Zsum, 1.0 / K)
+        return s[0] / K, None, pt.where(ok, pt.ones_like(D) / K, zero).float(), n_bad
     raise NotImplementedError("loss_method %r is not implemented by the fused solver (supported: %s)"
                               % (method, ", ".join(SUPPORTED)))

@@ -84,7 +84,7 @@ class Solver:
 
         self.Y_0_log, self.loss_log, self.u_L2_loss, self.IS_rel_log = [], [], [], []
         self.times, self.grads_rel_error_log, self.particles_close_to_target = [], [], []
-        self.path_steps_per_sec = []
+        self.path_steps_per_sec, self.nonfinite_log = [], []
         self._iteration = 0
 
     # ------------------------------------------------------------------ problem pass-throughs (solver.py:121-140)
@@ -217,9 +217,9 @@ class Solver:
         if self.detach_forward:
             y0 = self.y_0.Y_0 if self.learn_Y_0 else None
             Y, gX, Zsum = FusedRollout.apply(self._theta, y0, eng, call)
-            loss, wY, wZ = losses.value_and_cotangents(self.loss_method, Y.detach(), gX, Zsum.detach(), self.K,
-                                                       self.adaptive_forward_process, self.process_group,
-                                                       stats=call.stats)
+            loss, wY, wZ, n_bad = losses.value_and_cotangents(self.loss_method, Y.detach(), gX, Zsum.detach(),
+                                                              self.K, self.adaptive_forward_process,
+                                                              self.process_group, stats=call.stats)
             outs, cots = [], []
             if wY is not None:
                 outs.append(Y); cots.append(wY)
@@ -230,12 +230,13 @@ class Solver:
             loss_local = FusedRolloutAttached.apply(self._theta, eng, call)
             loss_local.backward()
             loss = dist.all_reduce_sum_(loss_local.detach().double().reshape(1), self.process_group)[0]
+            n_bad = dist.all_reduce_sum_(call.stats[3:4].clone(), self.process_group)[0]
         self._ensure_grad_views()
         dist.all_reduce_sum_(self._theta.grad, self.process_group)
         if self.learn_Y_0 and self.y_0.Y_0.grad is not None:
             dist.all_reduce_sum_(self.y_0.Y_0.grad, self.process_group)
         self.optimization_step()
-        return loss
+        return pt.stack([loss.double(), n_bad.double()])
 
     def train_step(self, l):
         """One full training iteration (noise -> rollout -> loss -> backward -> Adam -> logs), solver.py:431-531."""
@@ -244,10 +245,12 @@ class Solver:
         call = self.initialize_training_data()
         if self.learn_Y_0:
             self.Y_0_log.append(self.y_0.Y_0.item())
-        loss = self.gradient_descent(call)
+        res = self.gradient_descent(call)
         if self.log_gradient:
             self.gradient_log[l, :] = self._theta.grad[:self.p].detach().cpu()
-        self.loss_log.append(loss.item())                     # the only host sync of the iteration
+        loss, n_bad = res.tolist()                            # the only host sync of the iteration (16 bytes D2H)
+        self.loss_log.append(loss)
+        self.nonfinite_log.append(int(n_bad))                 # trajectories dropped from the batch (blow-ups)
         self.u_L2_loss.append(float('nan'))                   # on-device u_true tables: SURVEY 8(f) row f2
         if self.metastability_logs is not None:
             target, epsilon = self.metastability_logs

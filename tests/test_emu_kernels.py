@@ -149,3 +149,39 @@ def test_error_paths(run):
     rc = lib.pspde_rollout_fwd(ctypes.byref(ok), H.ptr(theta), H.ptr(pack), H.ptr(x0), None, H.ptr(ws), None, None,
                                None, None, None, H.ptr(ws), 8, None)
     assert rc < 0 and b"workspace" in lib.pspde_last_error()
+
+
+def test_blown_up_trajectory_is_inert(run):
+    """One trajectory starts at 1e20 and overflows.  Forward: it is counted and excluded from the statistics.
+    Backward (weight 0 from the host) and attached adjoint: gradients stay finite and equal the batch without it."""
+    g = load_golden("hjb_lqgc_d10_dense_lv")
+    d, N, K = g["d"], 5, 70
+    g = dict(g, N=N)
+    theta = g["theta"].astype(np.float32)
+    bad = 37
+    x0 = np.zeros((K, d), np.float32)
+    x0[bad] = 1e20
+    cfg, pack, _ = H.cfg_from_golden(g, noise=L.NOISE_PHILOX, K=K, seed=11, offset=0)
+    cfg.x0_per_path = 1
+    o = run.fwd(cfg, theta, pack, x0)
+    assert o["stats"][3] == 1 and not np.isfinite(o["Y"][bad] - o["gX"][bad])
+    keep = np.arange(K) != bad
+    D = o["Y"].astype(np.float64)[keep] - o["gX"][keep]
+    np.testing.assert_allclose(o["stats"][:2], [D.sum(), (D ** 2).sum()], rtol=1e-12)
+    w = np.random.default_rng(0).standard_normal(K).astype(np.float32)
+    w[bad] = 0.0
+    grad = run.bwd(cfg, theta, pack, x0, w, w)
+    assert np.isfinite(grad).all()
+    x0b = x0.copy()
+    x0b[bad] = 0.0                      # same batch with a harmless trajectory of zero weight in that slot
+    grad_ref = run.bwd(cfg, theta, pack, x0b, w, w)
+    assert relerr(grad, grad_ref) < 1e-6
+    # attached adjoint
+    oa = run.attached(cfg, theta, pack, x0, 1.0 / K)
+    assert oa["stats"][3] == 1 and np.isfinite(oa["grad"]).all()
+    ob = run.attached(cfg, theta, pack, x0b, 1.0 / K)
+    # reference batch: the harmless trajectory contributes; remove its contribution by linearity (run it alone)
+    cfg1, _, _ = H.cfg_from_golden(g, noise=L.NOISE_PHILOX, K=1, k_offset=bad, seed=11, offset=0)
+    cfg1.x0_per_path = 1
+    o1 = run.attached(cfg1, theta, pack, x0b[bad:bad + 1].copy(), 1.0 / K)
+    assert relerr(oa["grad"], ob["grad"] - o1["grad"]) < 1e-5

@@ -86,7 +86,8 @@ def test_loss_cotangents_match_oracle(method):
     Y, gX, Zs = rng.standard_normal(K), rng.standard_normal(K), rng.random(K)
     lv, wY, wZ = man.loss_and_weights(method, Y, gX, Zs, True)
     t = lambda a: pt.tensor(a, dtype=pt.float32)
-    loss, a, b = losses.value_and_cotangents(method, t(Y), t(gX), t(Zs), K, True)
+    loss, a, b, n_bad = losses.value_and_cotangents(method, t(Y), t(gX), t(Zs), K, True)
+    assert n_bad.item() == 0
     assert abs(loss.item() - lv) < 1e-5 * max(1, abs(lv))
     if a is not None:
         assert relerr(a.numpy(), wY) < 1e-5
@@ -94,6 +95,24 @@ def test_loss_cotangents_match_oracle(method):
         assert np.all(wY == 0)
     if b is not None:
         assert relerr(b.numpy(), wZ) < 1e-6
+
+
+def test_nonfinite_trajectories_are_dropped_and_counted():
+    from pspde import losses
+    rng = np.random.default_rng(2)
+    K = 64
+    Y, gX, Zs = rng.standard_normal(K), rng.standard_normal(K), rng.random(K)
+    Yb = Y.copy(); Yb[[3, 17]] = [np.nan, np.inf]
+    keep = np.ones(K, bool); keep[[3, 17]] = False
+    t = lambda a: pt.tensor(a, dtype=pt.float32)
+    for m in ("log-variance", "moment", "variance", "cross_entropy", "relative_entropy"):
+        lv, wY, wZ = man.loss_and_weights(m, Y[keep], gX[keep], Zs[keep], True)
+        loss, a, b, n_bad = losses.value_and_cotangents(m, t(Yb), t(gX), t(Zs), K, True)
+        assert n_bad.item() == 2 and abs(loss.item() - lv) < 1e-5 * max(1, abs(lv))
+        for w, ref in ((a, wY), (b, wZ)):
+            if w is not None:
+                assert bool(pt.isfinite(w).all()) and float(w[3]) == 0 and float(w[17]) == 0
+                assert relerr(w.numpy()[keep], ref) < 1e-5
 
 
 def test_problem_reference_solutions():
@@ -144,7 +163,7 @@ lo, hi = shard_range(K, rank, W)
 ok = True
 for m in ("log-variance", "moment", "variance", "cross_entropy", "relative_entropy"):
     full = losses.value_and_cotangents.__wrapped__(m, Y, gX, Zs, K) if hasattr(losses.value_and_cotangents, "__wrapped__") else None
-    loss, wY, wZ = losses.value_and_cotangents(m, Y[lo:hi], gX[lo:hi], Zs[lo:hi], K)
+    loss, wY, wZ, n_bad = losses.value_and_cotangents(m, Y[lo:hi], gX[lo:hi], Zs[lo:hi], K)
     # single-process reference computed without any process group semantics: emulate by gathering
     parts = [None, None]
     td.all_gather_object(parts, (None if wY is None else wY.numpy(), None if wZ is None else wZ.numpy(), loss.item()))
