@@ -50,7 +50,8 @@ def test_golden_parity(tag):
         assert relerr(eng.Zsum.cpu().numpy(), g["Zsum"]) < TOL
     D = g["Y_N"].astype(np.float64) - g["gX"]
     cond = 4 * 6e-8 * float((D ** 2).mean()) if "variance" in g["loss_method"] else 0.0   # SURVEY finding 9
-    assert abs(loss.item() - g["loss"]) <= TOL * abs(g["loss"]) + cond
+    assert abs(loss[0].item() - g["loss"]) <= TOL * abs(g["loss"]) + cond
+    assert loss[1].item() == 0
     assert relerr(S._theta.grad.cpu().numpy(), g["grad"]) < TOL
     if g["learn_Y_0"]:
         assert abs(S.y_0.Y_0.grad.item() - g["grad_y0"]) < 1e-4 * abs(g["grad_y0"])
