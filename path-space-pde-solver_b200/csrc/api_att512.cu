@@ -1,17 +1,10 @@
-// api_att512.cu -- template instantiations for T = 512 threads per CTA.
+// api_att512.cu -- attached-mode kernel instantiation for 512 threads per CTA.
 #include "api_common.h"
 
 int pspde_launch_att_512(const Plan& pl, const pspde::RolloutParams& p, void* stream) {
-#define PSPDE_ATT(NBB)                                                                       \
-  {                                                                                         \
-    auto kern = rollout_attached_kernel<kP, 512, NBB>;                                      \
-    if (pspde_set_smem(kern, pl.smem_bytes)) return fail(-11, "cudaFuncSetAttribute failed"); \
-    PSPDE_LAUNCH(kern, pl.grid, 512, pl.smem_bytes, stream, p);                              \
-  }
-  if (pl.NB == 2) PSPDE_ATT(2)
-  else if (pl.NB == 3) PSPDE_ATT(3)
-  else return fail(-13, "internal: no attached kernel for T=%d NB=%d", pl.T, pl.NB);
-#undef PSPDE_ATT
+  auto kern = rollout_attached_kernel<kP, 512, 1>;
+  if (pspde_set_smem(kern, pl.smem_bytes)) return fail(-11, "cudaFuncSetAttribute failed");
+  PSPDE_LAUNCH(kern, pl.grid, 512, pl.smem_bytes, stream, p);
   g_launches++;
   if (const char* e = pspde_peek_error()) return fail(-12, "attached kernel launch failed: %s", e);
   return 0;

@@ -82,14 +82,21 @@ static inline int validate(const pspde_cfg* c) {
   return 0;
 }
 
-// paths per thread tile in gemm_nn: minimise (waves over the CTA) x (issue slots per 4-wide k step)
-static inline int choose_r(int Np, int T, int rmax) {
+// rows per thread tile in gemm_nn.  Per k4 step a warp tile of R rows x 4 cols issues 8R FFMA2 (16R FP32-pipe
+// cycles on its SMSP) and 2R + 8 shared-memory wavefronts (one per cycle, SM wide).  Pick the R that minimises
+// max(pipe time of the busiest SMSP, shared-memory time), with a penalty when an SMSP is left with a single warp
+// (nothing to hide the LDS latency behind).
+static inline int choose_r(int nng, int T, int rmax) {
+  const int nw = T / 32;
   int best = 1;
   long best_cost = -1;
   for (int R = 1; R <= rmax; R *= 2) {
-    const long tiles = (long)(kP / R) * (Np / 4);
-    const long waves = (tiles + T - 1) / T;
-    const long cost = waves * (R + 4 + 16 * R);
+    const long nwt = (long)(kP / R / 8) * ((nng + 3) / 4);
+    const long waves = (nwt + nw - 1) / nw;
+    const long per_wave = nwt < nw ? nwt : nw;
+    const long per_smsp = (per_wave + 3) / 4;
+    long cost = waves * (per_smsp * 16 * R > per_wave * (2 * R + 8) ? per_smsp * 16 * R : per_wave * (2 * R + 8));
+    if (per_smsp == 1) cost += 40 * waves;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = R; }
   }
   return best;
@@ -111,17 +118,14 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
     if (v > 0 && v < pl.grid) pl.grid = v;
   }
   pl.T = 512; pl.NB = 1;
-  if (bwd) {
+  if (bwd) {   // one 8x8 weight-gradient block (64 accumulators) per thread
     const int nb = pl.g.n_blocks;
-    if (nb <= 256) { pl.T = 256; pl.NB = 1; }
-    else if (nb <= 512) { pl.T = 256; pl.NB = 2; }
-    else if (nb <= 768) { pl.T = 256; pl.NB = 3; }
-    else if (nb <= 1024) { pl.T = 512; pl.NB = 2; }
-    else if (nb <= 1536) { pl.T = 512; pl.NB = 3; }
-    else if (nb <= 2048) { pl.T = 256; pl.NB = 8; }
-    else return fail(-6, "network too large for the register-resident gradient path (%d blocks > 2048)", nb);
+    if (nb <= 256) pl.T = 256;
+    else if (nb <= 448) pl.T = 448;
+    else if (nb <= 512) pl.T = 512;
+    else return fail(-6, "network too large for the register-resident gradient path (%d 8x8 blocks > 512)", nb);
   }
-  for (int l = 0; l < pl.g.L; ++l) pl.r_fwd[l] = choose_r(pl.g.layer[l].Np, pl.T, bwd ? 4 : 8);
+  for (int l = 0; l < pl.g.L; ++l) pl.r_fwd[l] = choose_r(pl.g.layer[l].nng, pl.T, bwd ? 4 : 8);
   const SmemLayout sl = smem_layout(pl.g, kP, bwd, attached);
   pl.smem_bytes = (size_t)sl.total * sizeof(float);
   if (pl.smem_bytes > kMaxSmem)
@@ -155,9 +159,11 @@ static inline int launch_rollout(const Plan& pl, const RolloutParams& p, void* s
 
 
 
-// defined in api_bwd256.cu / api_bwd512.cu / api_att256.cu / api_att512.cu (one TU per thread count so that the
-// template instantiations compile in parallel)
+// defined in api_bwd*.cu / api_att*.cu (one translation unit per thread count so that the template instantiations
+// compile in parallel)
 int pspde_launch_bwd_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
+int pspde_launch_bwd_448(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_bwd_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_att_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
+int pspde_launch_att_448(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_att_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);

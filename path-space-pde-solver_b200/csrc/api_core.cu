@@ -69,6 +69,7 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
   if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
   if (pl.T == 256) rc = pspde_launch_bwd_256(pl, p, stream);
+  else if (pl.T == 448) rc = pspde_launch_bwd_448(pl, p, stream);
   else if (pl.T == 512) rc = pspde_launch_bwd_512(pl, p, stream);
   else rc = fail(-13, "internal: no kernel for T=%d NB=%d", pl.T, pl.NB);
   if (rc) return rc;
@@ -101,7 +102,8 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
   p.x_ckpt = reinterpret_cast<float*>(ws + pl.stats_bytes + pl.grad_bytes);
   if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
-  rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
+  rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream)
+       : (pl.T == 448) ? pspde_launch_att_448(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
   if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);

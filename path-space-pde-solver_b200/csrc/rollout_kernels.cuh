@@ -41,7 +41,7 @@ struct RolloutParams {
   float* x_ckpt;          // attached mode: [gridDim.x][N][P][d] state checkpoints of the current tile
 };
 
-struct SmemLayout { int w, act, z, xi, delta, lam, scal, prob, red, total; };
+struct SmemLayout { int w, act, z, xi, delta, lam, scal, prob, red, zero, total; };
 
 PSPDE_HD inline SmemLayout smem_layout(const NetGeom& g, int P, bool bwd, bool attached) {
   SmemLayout s;
@@ -55,6 +55,7 @@ PSPDE_HD inline SmemLayout smem_layout(const NetGeom& g, int P, bool bwd, bool a
   s.scal = o;  o += 8 * P;
   s.prob = o;  o += 7 * ceil4(g.d);
   s.red = o;   o += 16;
+  s.zero = o;  o += 4;
   s.total = o;
   return s;
 }
@@ -73,63 +74,129 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------------ packed FP32 FMA
+// Blackwell's FFMA2 (PTX fma.rn.f32x2): two FP32 FMAs per lane in ONE issue slot.  The FP32 pipe rate is
+// unchanged, but the slot that is freed lets the LDS / address instructions of the register-tiled GEMMs issue
+// beside the math instead of in front of it.  ptxas encodes a {s, s} operand as a scalar-broadcast source
+// (`R.F32`), so the outer-product form acc[i][j..j+1] += a_i * (b_j, b_j+1) needs no extra moves.
+struct f32x2 {
+#if defined(PSPDE_EMULATE)
+  float lo, hi;
+#else
+  unsigned long long v;
+#endif
+};
+__device__ __forceinline__ f32x2 f2_zero() {
+#if defined(PSPDE_EMULATE)
+  return f32x2{0.f, 0.f};
+#else
+  return f32x2{0ull};
+#endif
+}
+// d += (s, s) * (b0, b1)
+__device__ __forceinline__ void ffma2_s(f32x2& d, float s, float b0, float b1) {
+#if defined(PSPDE_EMULATE)
+  d.lo = fmaf(s, b0, d.lo); d.hi = fmaf(s, b1, d.hi);
+#else
+  asm("{\n\t.reg .b64 ss, bb;\n\tmov.b64 ss, {%1, %1};\n\tmov.b64 bb, {%2, %3};\n\tfma.rn.f32x2 %0, ss, bb, %0;\n\t}"
+      : "+l"(d.v) : "f"(s), "f"(b0), "f"(b1));
+#endif
+}
+// d += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void ffma2_v(f32x2& d, float a0, float a1, float b0, float b1) {
+#if defined(PSPDE_EMULATE)
+  d.lo = fmaf(a0, b0, d.lo); d.hi = fmaf(a1, b1, d.hi);
+#else
+  asm("{\n\t.reg .b64 aa, bb;\n\tmov.b64 aa, {%1, %2};\n\tmov.b64 bb, {%3, %4};\n\tfma.rn.f32x2 %0, aa, bb, %0;\n\t}"
+      : "+l"(d.v) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+#endif
+}
+__device__ __forceinline__ void f2_unpack(const f32x2& d, float& lo, float& hi) {
+#if defined(PSPDE_EMULATE)
+  lo = d.lo; hi = d.hi;
+#else
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d.v));
+#endif
+}
+
+// Lane -> tile mapping shared by the GEMM routines: a warp covers a patch of 8 row groups x 4 column groups
+// (lane & 7, lane >> 3).  A half-warp then touches 8 distinct activation rows (8 x 16 B = one 128 B wavefront)
+// and 2 distinct weight float4s, so every LDS.128 costs the minimum of 2 shared-memory wavefronts; with the
+// lanes laid along a single dimension the same loads cost 4 and the GEMMs become shared-memory bound.
+
 // ------------------------------------------------------------------------------------------------ gemm_nn
-// out[p][n0..n0+3] = sum_k act[p][k] * W[k][n0..n0+3]; thread tile = R strided paths x 4 contiguous outputs.
+// out[p][4ni..4ni+3] = sum_k act[p][k] * W[k][4ni..4ni+3]; thread tile = R strided rows x 4 contiguous outputs,
+// W in the k4-blocked layout (pspde_geom.h).  Kp % 4 == 0.
 template <int P, int R, typename Epi>
 __device__ __forceinline__ void gemm_nn(const float* __restrict__ act, int lda, const float* __restrict__ W,
-                                        int ldw, int Kp, int Np, int tid, int nthr, Epi&& epi) {
-  constexpr int PG = P / R;
-  const int ntiles = PG * (Np >> 2);
-  for (int tile = tid; tile < ntiles; tile += nthr) {
-    const int pi = tile % PG, ni = tile / PG;
-    float acc[R][4];
+                                        int nng, int Kp, int warp, int lane, int nwarps, Epi&& epi) {
+  constexpr int PG = P / R;            // row groups (multiple of 8)
+  constexpr int NPP = PG / 8;          // row patches
+  const int ncp = (nng + 3) >> 2;      // column patches
+  const int nwt = NPP * ncp;
+  const int wstep = nng * 16;          // floats per k4 step in W
+  for (int wt = warp; wt < nwt; wt += nwarps) {
+    const int pp = wt % NPP, cp = wt / NPP;
+    const int pi = pp * 8 + (lane & 7);
+    const int ni = cp * 4 + (lane >> 3);
+    const bool valid = ni < nng;
+    f32x2 acc[R][2];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    for (int r = 0; r < R; ++r) { acc[r][0] = f2_zero(); acc[r][1] = f2_zero(); }
     const float* ap = act + pi * lda;
-    const float* wp = W + 4 * ni;
+    const float* wp = W + (valid ? ni : nng - 1) * 16;
 #pragma unroll 2
     for (int k = 0; k < Kp; k += 4) {
       float4 a[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) a[r] = ld4(ap + r * PG * lda + k);
-      const float4 w0 = ld4(wp + (k + 0) * ldw), w1 = ld4(wp + (k + 1) * ldw);
-      const float4 w2 = ld4(wp + (k + 2) * ldw), w3 = ld4(wp + (k + 3) * ldw);
+      const float4 w0 = ld4(wp), w1 = ld4(wp + 4), w2 = ld4(wp + 8), w3 = ld4(wp + 12);
+      wp += wstep;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        acc[r][0] = fmaf(a[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(a[r].x, w0.y, acc[r][1]);
-        acc[r][2] = fmaf(a[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(a[r].x, w0.w, acc[r][3]);
-        acc[r][0] = fmaf(a[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(a[r].y, w1.y, acc[r][1]);
-        acc[r][2] = fmaf(a[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(a[r].y, w1.w, acc[r][3]);
-        acc[r][0] = fmaf(a[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(a[r].z, w2.y, acc[r][1]);
-        acc[r][2] = fmaf(a[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(a[r].z, w2.w, acc[r][3]);
-        acc[r][0] = fmaf(a[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(a[r].w, w3.y, acc[r][1]);
-        acc[r][2] = fmaf(a[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(a[r].w, w3.w, acc[r][3]);
+        ffma2_s(acc[r][0], a[r].x, w0.x, w0.y); ffma2_s(acc[r][1], a[r].x, w0.z, w0.w);
+        ffma2_s(acc[r][0], a[r].y, w1.x, w1.y); ffma2_s(acc[r][1], a[r].y, w1.z, w1.w);
+        ffma2_s(acc[r][0], a[r].z, w2.x, w2.y); ffma2_s(acc[r][1], a[r].z, w2.z, w2.w);
+        ffma2_s(acc[r][0], a[r].w, w3.x, w3.y); ffma2_s(acc[r][1], a[r].w, w3.z, w3.w);
       }
     }
+    if (valid) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) epi(pi + r * PG, 4 * ni, acc[r]);
+      for (int r = 0; r < R; ++r) {
+        float o[4];
+        f2_unpack(acc[r][0], o[0], o[1]);
+        f2_unpack(acc[r][1], o[2], o[3]);
+        epi(pi + r * PG, 4 * ni, o);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ gemm_nt
-// out[p][c] = sum_n dl[p][n] * Wrows[c][n]; both operands contiguous along the reduction.
-// thread tile = R strided paths x C strided rows.
+// out[p][c] = sum_n dl[p][n] * W[row0 + c][n], c < ncols; both operands contiguous along the reduction (W rows in
+// the k4-blocked layout are float4-contiguous).  thread tile = R strided rows x C strided W-rows.  Nred % 4 == 0.
 template <int P, int R, int C, typename Epi>
-__device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, const float* __restrict__ Wrows,
-                                        int ldw, int Nred, int ncols, int tid, int nthr, Epi&& epi) {
+__device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, const float* __restrict__ W, int nng,
+                                        int row0, int Nred, int ncols, int warp, int lane, int nwarps, Epi&& epi) {
   constexpr int PG = P / R;
+  constexpr int NPP = PG / 8;
   const int CG = (ncols + C - 1) / C;
-  const int ntiles = PG * CG;
-  for (int tile = tid; tile < ntiles; tile += nthr) {
-    const int pi = tile % PG, ci = tile / PG;
-    float acc[R][C];
+  const int ncp = (CG + 3) >> 2;
+  const int nwt = NPP * ncp;
+  for (int wt = warp; wt < nwt; wt += nwarps) {
+    const int pp = wt % NPP, cp = wt / NPP;
+    const int pi = pp * 8 + (lane & 7);
+    const int ci = cp * 4 + (lane >> 3);
+    f32x2 acc[R][C];
     const float* wr[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-      const int c = ci + CG * j;
-      wr[j] = Wrows + (c < ncols ? c : ncols - 1) * ldw;
+      int c = ci + CG * j;
+      if (c >= ncols) c = ncols - 1;
+      const int rr = row0 + c;
+      wr[j] = W + (rr >> 2) * nng * 16 + (rr & 3) * 4;
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r][j] = 0.f;
+      for (int r = 0; r < R; ++r) acc[r][j] = f2_zero();
     }
     const float* dp = dl + pi * ldl;
 #pragma unroll 2
@@ -138,60 +205,66 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, c
 #pragma unroll
       for (int r = 0; r < R; ++r) dv[r] = ld4(dp + r * PG * ldl + n);
 #pragma unroll
-      for (int j = 0; j < C; ++j) wv[j] = ld4(wr[j] + n);
+      for (int j = 0; j < C; ++j) wv[j] = ld4(wr[j] + n * 4);      // 4 columns further = next 16-float block
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-          acc[r][j] = fmaf(dv[r].x, wv[j].x, acc[r][j]); acc[r][j] = fmaf(dv[r].y, wv[j].y, acc[r][j]);
-          acc[r][j] = fmaf(dv[r].z, wv[j].z, acc[r][j]); acc[r][j] = fmaf(dv[r].w, wv[j].w, acc[r][j]);
+          ffma2_v(acc[r][j], dv[r].x, dv[r].y, wv[j].x, wv[j].y);
+          ffma2_v(acc[r][j], dv[r].z, dv[r].w, wv[j].z, wv[j].w);
         }
     }
+    if (ci < CG) {
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      const int c = ci + CG * j;
-      if (c < ncols) {
+      for (int j = 0; j < C; ++j) {
+        const int c = ci + CG * j;
+        if (c < ncols) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) epi(pi + r * PG, c, acc[r][j]);
+          for (int r = 0; r < R; ++r) {
+            float lo, hi;
+            f2_unpack(acc[r][j], lo, hi);
+            epi(pi + r * PG, c, lo + hi);
+          }
+        }
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-// Block b of the global list -> (layer, row group, col group); returns shared-memory offsets of the operands.
-__device__ __forceinline__ void bw_decode(const NetGeom& g, const SmemLayout& sl, int b, int& a_off, int& d_off,
-                                          int& d_ld) {
-  int l = 0;
-  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
-  const LayerGeom& y = g.layer[l];
-  const int r = b - y.blk_begin, kg = r / y.nng, ng = r % y.nng;
-  a_off = sl.act + y.in_start + 4 * kg;
-  if (l == g.L - 1) { d_off = sl.xi + 4 * ng; d_ld = g.ldz; }
-  else { d_off = sl.delta + (y.out_col - g.hid_off) + 4 * ng; d_ld = g.ldd; }
-}
-
+// dW_l += act^T . delta_l, accumulated in registers across the whole step loop.  Block b of the global list ->
+// (layer, kg, ng) owning the 4-row groups {kg, kg + kgh} x the 4-col groups {ng, ng + ngh} (64 accumulators).
 template <int P, int NB>
-__device__ __forceinline__ void bw_accum(float (&acc)[NB][16], const int (&a_off)[NB], const int (&d_off)[NB],
-                                         const int (&d_ld)[NB], const float* smem, int lda) {
+__device__ __forceinline__ void bw_accum(f32x2 (&acc)[NB][32], const NetGeom& g, const SmemLayout& sl,
+                                         const float* smem, int tid, int nthr) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (a_off[j] >= 0) {
-      const float* ap = smem + a_off[j];
-      const float* dp = smem + d_off[j];
-      const int ld = d_ld[j];
-#pragma unroll 4
+    const int b = tid + nthr * j;
+    if (b < g.n_blocks) {
+      int l = 0;
+      while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
+      const LayerGeom& y = g.layer[l];
+      const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+      const bool last = (l == g.L - 1);
+      const int ldd = last ? g.ldz : g.ldd;
+      const float* a0p = smem + sl.act + y.in_start + 4 * kg;
+      const float* d0p = smem + (last ? sl.xi : sl.delta + (y.out_col - g.hid_off)) + 4 * ng;
+      // a missing half (edge block) reads the always-zero pad with stride 0
+      const bool ha = kg + y.kgh < y.nkg, hd = ng + y.ngh < y.nng;
+      const float* a1p = ha ? a0p + 4 * y.kgh : smem + sl.zero;
+      const float* d1p = hd ? d0p + 4 * y.ngh : smem + sl.zero;
+      const int sa1 = ha ? g.lda : 0, sd1 = hd ? ldd : 0;
+      const int lda = g.lda;
+#pragma unroll 2
       for (int p = 0; p < P; ++p) {
-        const float4 a = ld4(ap + p * lda);
-        const float4 v = ld4(dp + p * ld);
-        acc[j][0] = fmaf(a.x, v.x, acc[j][0]);   acc[j][1] = fmaf(a.x, v.y, acc[j][1]);
-        acc[j][2] = fmaf(a.x, v.z, acc[j][2]);   acc[j][3] = fmaf(a.x, v.w, acc[j][3]);
-        acc[j][4] = fmaf(a.y, v.x, acc[j][4]);   acc[j][5] = fmaf(a.y, v.y, acc[j][5]);
-        acc[j][6] = fmaf(a.y, v.z, acc[j][6]);   acc[j][7] = fmaf(a.y, v.w, acc[j][7]);
-        acc[j][8] = fmaf(a.z, v.x, acc[j][8]);   acc[j][9] = fmaf(a.z, v.y, acc[j][9]);
-        acc[j][10] = fmaf(a.z, v.z, acc[j][10]); acc[j][11] = fmaf(a.z, v.w, acc[j][11]);
-        acc[j][12] = fmaf(a.w, v.x, acc[j][12]); acc[j][13] = fmaf(a.w, v.y, acc[j][13]);
-        acc[j][14] = fmaf(a.w, v.z, acc[j][14]); acc[j][15] = fmaf(a.w, v.w, acc[j][15]);
+        const float4 a0 = ld4(a0p), v0 = ld4(d0p), a1 = ld4(a1p), v1 = ld4(d1p);
+        a0p += lda; a1p += sa1; d0p += ldd; d1p += sd1;
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ffma2_s(acc[j][4 * i + 0], ar[i], v0.x, v0.y); ffma2_s(acc[j][4 * i + 1], ar[i], v0.z, v0.w);
+          ffma2_s(acc[j][4 * i + 2], ar[i], v1.x, v1.y); ffma2_s(acc[j][4 * i + 3], ar[i], v1.z, v1.w);
+        }
       }
     }
   }
@@ -199,7 +272,7 @@ __device__ __forceinline__ void bw_accum(float (&acc)[NB][16], const int (&a_off
 
 // acc -> grad_partial (this CTA's private slice; plain read-modify-write, no other writer), then clear.
 template <int NB>
-__device__ __forceinline__ void bw_flush(float (&acc)[NB][16], const NetGeom& g, int tid, int nthr,
+__device__ __forceinline__ void bw_flush(f32x2 (&acc)[NB][32], const NetGeom& g, int tid, int nthr,
                                          float* __restrict__ gp) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
@@ -208,74 +281,72 @@ __device__ __forceinline__ void bw_flush(float (&acc)[NB][16], const NetGeom& g,
       int l = 0;
       while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
       const LayerGeom& y = g.layer[l];
-      const int r = b - y.blk_begin, kg = r / y.nng, ng = r % y.nng;
+      const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * (i < 4 ? kg : kg + y.kgh) + (i & 3);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int idx = theta_index(g, l, 4 * kg + i, 4 * ng + q);
-          if (idx >= 0) gp[idx] += acc[j][4 * i + q];
-          acc[j][4 * i + q] = 0.f;
+          float v[2];
+          f2_unpack(acc[j][4 * i + q], v[0], v[1]);
+          acc[j][4 * i + q] = f2_zero();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = 4 * (q < 2 ? ng : ng + y.ngh) + 2 * (q & 1) + h;
+            const bool ok = (i < 4 || kg + y.kgh < y.nkg) && (q < 2 || ng + y.ngh < y.nng);
+            const int idx = ok ? theta_index(g, l, row, col) : -1;
+            if (idx >= 0) gp[idx] += v[h];
+          }
         }
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ staging
-// theta (one parameter set, reference layout) -> shared W_l[row][ldw] with zero pads.
+// theta (one parameter set, reference layout) -> shared k4-blocked W_l with zero pads.
 __device__ __forceinline__ void stage_weights(const NetGeom& g, const float* __restrict__ th, float* sW, int tid,
                                               int nthr) {
   for (int l = 0; l < g.L; ++l) {
     const LayerGeom& y = g.layer[l];
-    const int tot = y.Kp * y.ldw;
-    for (int q = tid; q < tot; q += nthr) {
-      const int r = q / y.ldw, n = q - r * y.ldw;
-      const int idx = (n < y.Np) ? theta_index(g, l, r, n) : -1;
+    const int tot = y.Kp * y.Np;
+    for (int q = tid; q < tot; q += nthr) {        // q = shared offset; decode (row, col) of the blocked layout
+      const int blk = q >> 4, in = q & 15;
+      const int r = 4 * (blk / y.nng) + (in >> 2), n = 4 * (blk % y.nng) + (in & 3);
+      const int idx = theta_index(g, l, r, n);
       sW[y.w_off + q] = idx >= 0 ? __ldg(th + idx) : 0.f;
     }
   }
 }
 
-// Brownian increment of step n for the tile -> sXi (pads stay zero)
+// INJECT mode: Brownian increment of step n for the tile -> sXi (pads stay zero).  In PHILOX mode the increments
+// are generated in registers inside sde_step and never staged.
 template <int P>
 __device__ __forceinline__ void stage_noise(const RolloutParams& prm, int tile, int n, float* sXi, int tid,
                                             int nthr) {
   const int d = prm.d, ldz = prm.g.ldz;
-  if (prm.noise_mode == NOISE_PHILOX) {
-    const int nb4 = (d + 3) >> 2;
-    for (int q = tid; q < P * nb4; q += nthr) {
-      const int p = q / nb4, jb = q - p * nb4;
-      const int k = tile * P + p;
-      float4 z = philox_normal4((unsigned)(prm.k_offset + k), (unsigned)n, (unsigned)jb, prm.offset, prm.seed);
-      const int j = 4 * jb;
-      if (j + 1 >= d) z.y = 0.f;
-      if (j + 2 >= d) z.z = 0.f;
-      if (j + 3 >= d) z.w = 0.f;
-      st4(sXi + p * ldz + j, z);
-    }
-  } else {
-    for (int q = tid; q < P * d; q += nthr) {
-      const int p = q / d, j = q - p * d;
-      const int k = tile * P + p;
-      sXi[p * ldz + j] = (k < prm.K_local)
-                             ? __ldg(prm.xi + (long long)k * prm.xs_k + (long long)j * prm.xs_j + (long long)n * prm.xs_n)
-                             : 0.f;
-    }
+  for (int q = tid; q < P * d; q += nthr) {
+    const int p = q / d, j = q - p * d;
+    const int k = tile * P + p;
+    sXi[p * ldz + j] = (k < prm.K_local)
+                           ? __ldg(prm.xi + (long long)k * prm.xs_k + (long long)j * prm.xs_j + (long long)n * prm.xs_n)
+                           : 0.f;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ SDE step
-// Euler-Maruyama update of X, Y, Z_sum for the tile (solver.py:471-486), one warp per trajectory.
+// Euler-Maruyama update of X, Y, Z_sum for the tile (solver.py:471-486), one warp per trajectory, one float4
+// (4 state components, one Philox call) per lane.
 //   X+ = X + (b(X) + B c) dt + (B xi) sqrt(dt),  c = -Z (adaptive) or 0
 //   Y+ = Y + ((|Z|^2/2 + f(X+)) + Z.c) dt + (Z.xi) sqrt(dt)          [-h = |Z|^2/2 + f for every problem here]
 //   Zsum += (|Z|^2/2 + f(X+)) dt
-// BWD: the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt, replaces xi in sXi and X+ is
-// parked in sZ (the activation tile must keep X_n until the weight gradient has been accumulated).
+// BWD: the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt, goes to sXi and X+ is parked in sZ
+// (the activation tile must keep X_n until the weight gradient has been accumulated).
 template <int P, bool BWD>
-__device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLayout& sl, float* smem, bool last,
-                                         int warp, int lane, int nwarps) {
+__device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLayout& sl, float* smem, int tile,
+                                         int n, bool last, int warp, int lane, int nwarps) {
   const NetGeom& g = prm.g;
-  const int d = prm.d, d4 = ceil4(d);
+  const int d = prm.d, d4 = ceil4(d), ngrp = d4 >> 2;
   const float dt = prm.dt, sq = sqrtf(prm.dt);
   const float* pa = smem + sl.prob;
   const float *a_d = pa, *b_d = pa + d4, *p_d = pa + 2 * d4, *r_d = pa + 3 * d4, *al = pa + 4 * d4,
@@ -287,33 +358,76 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
   const float* swZ = sY + 4 * P;
   const bool adaptive = prm.adaptive != 0;
   const bool dense = (prm.flags & FLAG_DENSE_AB) != 0;
+  const bool philox = prm.noise_mode == NOISE_PHILOX;
+  const bool dw = prm.problem_id == PROBLEM_DW;
   const float kA = adaptive ? 0.f : 1.f;
   for (int p = warp; p < P; p += nwarps) {
     float* zr = smem + sl.z + p * g.ldz;
-    float* xr = smem + sl.act + p * g.lda + g.x_col;
+    float* xr = smem + sl.act + p * g.lda;          // X starts at column 0
     float* er = smem + sl.xi + p * g.ldz;
     const float wy = BWD ? swY[p] : 0.f, wz = BWD ? swZ[p] : 0.f;
     // BWD: a row with zero cotangents (padding, or a trajectory whose D was non-finite and was therefore given
-    // zero weight by the host) is inert: its state stays at X_0 so that all its activations remain finite and
-    // every product it contributes to the weight gradient is exactly 0 (0 * NaN would poison the gradient).
+    // zero weight by the host) is inert: its state stays where tile init put it (the origin) so that all its
+    // activations remain finite and every product it adds to the weight gradient is exactly 0.
     const bool inert = BWD && wy == 0.f && wz == 0.f;
+    const unsigned kglob = (unsigned)(prm.k_offset + tile * P + p);
     float zz = 0.f, zxi = 0.f, ff = 0.f, gg = 0.f;
     if (!dense) {
-      for (int j = lane; j < d; j += 32) {
-        const float z = zr[j], x = xr[j], e = er[j];
-        zz = fmaf(z, z, zz);
-        zxi = fmaf(z, e, zxi);
-        const float c = adaptive ? -z : 0.f;
-        const float drift = (prm.problem_id == PROBLEM_DW) ? -(4.0f * kap[j] * (x * (x * x - 1.0f))) : a_d[j] * x;
-        const float xn = x + (drift + b_d[j] * c) * dt + (b_d[j] * e) * sq;
-        ff = fmaf(p_d[j] * xn, xn, ff);
-        if (last) gg += al[j] * xn + r_d[j] * xn * xn + eta[j] * (xn - 1.0f) * (xn - 1.0f);
-        if (BWD) { er[j] = inert ? 0.f : wy * (sq * e + kA * dt * z) + wz * dt * z; zr[j] = inert ? x : xn; }
-        else xr[j] = xn;
+      for (int jb = lane; jb < ngrp; jb += 32) {
+        const int j0 = 4 * jb;
+        const float4 z4 = ld4(zr + j0), x4 = ld4(xr + j0);
+        float4 e4 = philox ? philox_normal4(kglob, (unsigned)n, (unsigned)jb, prm.offset, prm.seed) : ld4(er + j0);
+        const float4 A4 = ld4(a_d + j0), B4 = ld4(b_d + j0), P4 = ld4(p_d + j0);
+        const float4 K4 = ld4(kap + j0);
+        const float zv[4] = {z4.x, z4.y, z4.z, z4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
+        const float pv[4] = {P4.x, P4.y, P4.z, P4.w}, kv[4] = {K4.x, K4.y, K4.z, K4.w};
+        float xn[4], ze[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // components >= d of the last group are the t / 1 / pad columns of the row: no noise, no control; all
+          // their problem coefficients are zero, so x_new == x there and the group can be stored back whole
+          const bool padc = j0 + i >= d;
+          if (padc) ev[i] = 0.f;
+          const float z = padc ? 0.f : zv[i], x = xv[i], e = ev[i];
+          zz = fmaf(z, z, zz);
+          zxi = fmaf(z, e, zxi);
+          const float c = adaptive ? -z : 0.f;
+          const float drift = dw ? -(4.0f * kv[i] * (x * (x * x - 1.0f))) : av[i] * x;
+          xn[i] = x + (drift + bv[i] * c) * dt + (bv[i] * e) * sq;
+          ff = fmaf(pv[i] * xn[i], xn[i], ff);
+          ze[i] = wy * (sq * e + kA * dt * z) + wz * dt * z;
+        }
+        if (last) {
+          const float4 L4 = ld4(al + j0), R4 = ld4(r_d + j0), E4 = ld4(eta + j0);
+          const float lv[4] = {L4.x, L4.y, L4.z, L4.w}, rv[4] = {R4.x, R4.y, R4.z, R4.w};
+          const float tv[4] = {E4.x, E4.y, E4.z, E4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            gg += lv[i] * xn[i] + rv[i] * xn[i] * xn[i] + tv[i] * (xn[i] - 1.0f) * (xn[i] - 1.0f);
+        }
+        if (BWD) {
+          st4(er + j0, inert ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(ze[0], ze[1], ze[2], ze[3]));
+          st4(zr + j0, inert ? x4 : make_float4(xn[0], xn[1], xn[2], xn[3]));
+        } else {
+          st4(xr + j0, make_float4(xn[0], xn[1], xn[2], xn[3]));
+        }
       }
     } else {
+      // dense A, B (off_diag != 0): matrices read through the read-only path; d <= 128
       const float* Am = prm.prob + 7 * d;
       const float* Bm = Am + d * d;
+      if (philox) {   // the matvecs need the whole increment of the row: stage it first
+        for (int jb = lane; jb < ngrp; jb += 32) {
+          float4 e4 = philox_normal4(kglob, (unsigned)n, (unsigned)jb, prm.offset, prm.seed);
+          if (4 * jb + 1 >= d) e4.y = 0.f;
+          if (4 * jb + 2 >= d) e4.z = 0.f;
+          if (4 * jb + 3 >= d) e4.w = 0.f;
+          st4(er + 4 * jb, e4);
+        }
+        __syncwarp();
+      }
       float xn_loc[4], ze_loc[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -346,6 +460,8 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
           else xr[i] = xn_loc[q];
         }
       }
+      // the float4 copy-back of the parked state covers whole groups: carry the t / 1 / pad columns along
+      if (BWD) for (int i = d + lane; i < d4; i += 32) { zr[i] = xr[i]; er[i] = 0.f; }
     }
     zz = warp_sum(zz); zxi = warp_sum(zxi); ff = warp_sum(ff);
     if (last) gg = warp_sum(gg);
@@ -361,8 +477,8 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
 // ------------------------------------------------------------------------------------------------ network
 // forward through all layers for the tile; hidden activations -> sAct, output Z -> sZ.  Ends with a barrier.
 template <int P, int RMAX>
-__device__ __forceinline__ void net_forward(const RolloutParams& prm, const SmemLayout& sl, float* smem, int tid,
-                                            int nthr) {
+__device__ __forceinline__ void net_forward(const RolloutParams& prm, const SmemLayout& sl, float* smem, int warp,
+                                            int lane, int nwarps) {
   const NetGeom& g = prm.g;
   float* sAct = smem + sl.act;
   for (int l = 0; l < g.L; ++l) {
@@ -374,25 +490,28 @@ __device__ __forceinline__ void net_forward(const RolloutParams& prm, const Smem
     const int N = y.N;
     auto epi = [&](int p, int n0, const float (&acc)[4]) {
       float* o = out + p * ldo + n0;
+      float v[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (n0 + q < N) {
-          float v = acc[q];
-          if (!lastl) {
-            if (kind == NET_DENSENET) { v = fmaxf(v, 0.f); v = v * v; }
-            else v = tanhf(v);
-          }
-          o[q] = v;
+        v[q] = acc[q];
+        if (!lastl) {
+          if (kind == NET_DENSENET) { v[q] = fmaxf(v[q], 0.f); v[q] = v[q] * v[q]; }
+          else v[q] = tanhf(v[q]);
         }
+      }
+      if (n0 + 3 < N) st4(o, make_float4(v[0], v[1], v[2], v[3]));
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (n0 + q < N) o[q] = v[q];     // never touch the 1-column / pads
       }
     };
     const float* A = sAct + y.in_start;
     const float* W = smem + sl.w + y.w_off;
     const int R = prm.r_fwd[l];
-    if (RMAX >= 8 && R == 8) gemm_nn<P, (RMAX >= 8 ? 8 : 1)>(A, g.lda, W, y.ldw, y.Kp, y.Np, tid, nthr, epi);
-    else if (RMAX >= 4 && R == 4) gemm_nn<P, (RMAX >= 4 ? 4 : 1)>(A, g.lda, W, y.ldw, y.Kp, y.Np, tid, nthr, epi);
-    else if (R == 2) gemm_nn<P, 2>(A, g.lda, W, y.ldw, y.Kp, y.Np, tid, nthr, epi);
-    else gemm_nn<P, 1>(A, g.lda, W, y.ldw, y.Kp, y.Np, tid, nthr, epi);
+    if (RMAX >= 8 && R == 8) gemm_nn<P, (RMAX >= 8 ? 8 : 1)>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
+    else if (RMAX >= 4 && R == 4) gemm_nn<P, (RMAX >= 4 ? 4 : 1)>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
+    else if (R == 2) gemm_nn<P, 2>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
+    else gemm_nn<P, 1>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
     __syncthreads();
   }
 }
@@ -402,7 +521,7 @@ __device__ __forceinline__ void net_forward(const RolloutParams& prm, const Smem
 // every layer.  (Cotangent on the network INPUT is not needed in detached mode.)
 template <int P>
 __device__ __forceinline__ void net_backward_hidden(const RolloutParams& prm, const SmemLayout& sl, float* smem,
-                                                    int tid, int nthr) {
+                                                    int warp, int lane, int nwarps) {
   const NetGeom& g = prm.g;
   float* sDl = smem + sl.delta;
   const float* sAct = smem + sl.act;
@@ -413,7 +532,6 @@ __device__ __forceinline__ void net_backward_hidden(const RolloutParams& prm, co
     const bool accumulate = (g.kind == NET_DENSENET) && (l < g.L - 1);
     const float* dl = (l == g.L - 1) ? smem + sl.xi : sDl + (y.out_col - g.hid_off);
     const int ldl = (l == g.L - 1) ? g.ldz : g.ldd;
-    const float* Wrows = smem + sl.w + y.w_off + (c_lo - y.in_start) * y.ldw;
     const int seg_lo = g.seg_off[l], seg_n = g.dims[l];
     const int kind = g.kind, lda = g.lda, ldd = g.ldd, hid_off = g.hid_off;
     auto epi = [&](int p, int c, float v) {
@@ -429,9 +547,29 @@ __device__ __forceinline__ void net_backward_hidden(const RolloutParams& prm, co
       }
       *o = v;
     };
-    gemm_nt<P, 2, 4>(dl, ldl, Wrows, y.ldw, y.Np, c_hi - c_lo, tid, nthr, epi);
+    gemm_nt<P, 2, 4>(dl, ldl, smem + sl.w + y.w_off, y.nng, c_lo - y.in_start, y.Np, c_hi - c_lo, warp, lane,
+                     nwarps, epi);
     __syncthreads();
   }
+}
+
+__device__ __forceinline__ void tile_init_state(const RolloutParams& prm, float* sAct, int tile, int P, bool bwd,
+                                                int tid, int nthr) {
+  const NetGeom& g = prm.g;
+  const int d = prm.d;
+  for (int q = tid; q < P * d; q += nthr) {
+    const int p = q / d, j = q - p * d, k = tile * P + p;
+    float x = 0.f;
+    if (prm.x0_per_path) { if (k < prm.K_local) x = __ldg(prm.x0 + (size_t)k * d + j); }
+    else x = __ldg(prm.x0 + j);
+    if (bwd) {   // inert rows (zero cotangents, see sde_step) sit at the origin: finite activations whatever X_0 is
+      const bool live = k < prm.K_local && ((prm.wY && __ldg(prm.wY + k) != 0.f) || (prm.wZ && __ldg(prm.wZ + k) != 0.f));
+      if (!live) x = 0.f;
+    }
+    sAct[p * g.lda + j] = x;
+  }
+  for (int p = tid; p < P; p += nthr)
+    for (int s = 0; s < g.L; ++s) if (g.seg_one[s] >= 0) sAct[p * g.lda + g.seg_one[s]] = 1.0f;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -454,6 +592,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
   float* swZ = sY + 4 * P;
   double* sRed = reinterpret_cast<double*>(smem + sl.red);
   const bool outer = (g.time_mode == TIME_NONE);
+  const bool inject = prm.noise_mode != NOISE_PHILOX;
 
   // ---- one-time: clear every tile (pads must be zero), stage problem vectors and (inner) weights
   for (int q = sl.act + tid; q < sl.total; q += T) smem[q] = 0.f;
@@ -461,37 +600,21 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
   for (int q = tid; q < 7 * d; q += T) { const int v = q / d, j = q - v * d; smem[sl.prob + v * d4 + j] = __ldg(prm.prob + q); }
   if (!outer) stage_weights(g, prm.theta, smem + sl.w, tid, T);
 
-  float acc[NB][16];
-  int a_off[NB], d_off[NB], d_ld[NB];
+  f32x2 acc[NB][32];
   if (BWD) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+    for (int j = 0; j < NB; ++j)
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[j][q] = 0.f;
-      const int b = tid + T * j;
-      a_off[j] = -1; d_off[j] = 0; d_ld[j] = 0;
-      if (b < g.n_blocks) bw_decode(g, sl, b, a_off[j], d_off[j], d_ld[j]);
-    }
+      for (int q = 0; q < 32; ++q) acc[j][q] = f2_zero();
   }
   float* gp = BWD ? prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total : nullptr;
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     // ---- tile init (solver.py:365-376): X = X_0, Y = y0, Z_sum = 0
-    for (int q = tid; q < P * d; q += T) {
-      const int p = q / d, j = q - p * d, k = tile * P + p;
-      float x = 0.f;
-      if (prm.x0_per_path) { if (k < prm.K_local) x = __ldg(prm.x0 + (size_t)k * d + j); }
-      else x = __ldg(prm.x0 + j);
-      if (BWD) {   // inert rows (zero cotangents, see sde_step) sit at the origin: finite activations whatever X_0 is
-        const bool live = k < prm.K_local && ((prm.wY && __ldg(prm.wY + k) != 0.f) || (prm.wZ && __ldg(prm.wZ + k) != 0.f));
-        if (!live) x = 0.f;
-      }
-      sAct[p * g.lda + g.x_col + j] = x;
-    }
+    tile_init_state(prm, sAct, tile, P, BWD, tid, T);
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
-      for (int s = 0; s < g.L; ++s) if (g.seg_one[s] >= 0) sAct[p * g.lda + g.seg_one[s]] = 1.0f;
       sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f;
       sZs[p] = 0.f; sG[p] = 0.f;
       const bool ok = BWD && k < prm.K_local;
@@ -501,21 +624,25 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
     // (no barrier needed here: the step prologue below ends with one)
 
     for (int n = 0; n < N; ++n) {
-      if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * prm.dt;
-      stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
+      // time column: in BWD the float4 copy-back of X_{n+1} at the end of the previous step also covers the t column
+      // when d % 4 != 0; it then writes t_{n+1} itself (same thread, no race with this loop)
+      if (g.t_col >= 0 && (!BWD || n == 0 || g.t_col >= d4))
+        for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * prm.dt;
+      if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
       __syncthreads();
-      net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, tid, T);
-      sde_step<P, BWD>(prm, sl, smem, n == N - 1, warp, lane, NW);
+      net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, warp, lane, NW);
+      sde_step<P, BWD>(prm, sl, smem, tile, n, n == N - 1, warp, lane, NW);
       __syncthreads();
       if (BWD) {
-        net_backward_hidden<P>(prm, sl, smem, tid, T);
-        bw_accum<P, NB>(acc, a_off, d_off, d_ld, smem, g.lda);
+        net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);
+        bw_accum<P, NB>(acc, g, sl, smem, tid, T);
         if (outer) bw_flush<NB>(acc, g, tid, T, gp + (size_t)n * g.n_params);
         __syncthreads();
-        for (int q = tid; q < P * d; q += T) {  // X_{n+1}: parked in sZ -> activation tile
-          const int p = q / d, j = q - p * d;
-          sAct[p * g.lda + g.x_col + j] = smem[sl.z + p * g.ldz + j];
+        for (int q = tid; q < P * (d4 >> 2); q += T) {  // X_{n+1}: parked in sZ -> activation tile
+          const int p = q / (d4 >> 2), jb = q - p * (d4 >> 2);
+          st4(sAct + p * g.lda + 4 * jb, ld4(smem + sl.z + p * g.ldz + 4 * jb));
+          if (g.t_col >= 0 && (g.t_col >> 2) == jb) sAct[p * g.lda + g.t_col] = (float)(n + 1) * prm.dt;
         }
         // the next step's prologue barrier (or the one below) orders this copy
       }
@@ -533,7 +660,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
           const double D = (double)Y - (double)G;
-          if (isfinite(D)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)G; }
+          if (isfinite(D) && isfinite((double)ZS)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)G; }
           else s3 = 1.0;
         }
       }
@@ -544,7 +671,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       if (prm.X_N) {
         for (int q = tid; q < P * d; q += T) {
           const int p = q / d, j = q - p * d, k = tile * P + p;
-          if (k < prm.K_local) prm.X_N[(size_t)k * d + j] = sAct[p * g.lda + g.x_col + j];
+          if (k < prm.K_local) prm.X_N[(size_t)k * d + j] = sAct[p * g.lda + j];
         }
       }
     } else if (!outer) {
@@ -579,10 +706,11 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
   float* sY = smem + sl.scal;
   float* sZs = sY + P;
   float* sG = sY + 2 * P;
-  float* swY = sY + 3 * P;   // per-path weight w (0 for padding rows)
+  float* swY = sY + 3 * P;   // per-path weight w (0 for padding rows and dropped trajectories)
   double* sRed = reinterpret_cast<double*>(smem + sl.red);
   const bool outer = (g.time_mode == TIME_NONE);
   const bool dense = (prm.flags & FLAG_DENSE_AB) != 0;
+  const bool inject = prm.noise_mode != NOISE_PHILOX;
   const float* pa = smem + sl.prob;
   const float *a_d = pa, *b_d = pa + d4, *p_d = pa + 2 * d4, *r_d = pa + 3 * d4, *al = pa + 4 * d4,
               *kap = pa + 5 * d4, *eta = pa + 6 * d4;
@@ -594,31 +722,19 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
   for (int q = tid; q < 7 * d; q += T) { const int v = q / d, j = q - v * d; smem[sl.prob + v * d4 + j] = __ldg(prm.prob + q); }
   if (!outer) stage_weights(g, prm.theta, smem + sl.w, tid, T);
 
-  float acc[NB][16];
-  int a_off[NB], d_off[NB], d_ld[NB];
+  f32x2 acc[NB][32];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
+  for (int j = 0; j < NB; ++j)
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc[j][q] = 0.f;
-    const int b = tid + T * j;
-    a_off[j] = -1; d_off[j] = 0; d_ld[j] = 0;
-    if (b < g.n_blocks) bw_decode(g, sl, b, a_off[j], d_off[j], d_ld[j]);
-  }
+    for (int q = 0; q < 32; ++q) acc[j][q] = f2_zero();
   float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
   float* ck = prm.x_ckpt + (size_t)blockIdx.x * N * P * d;
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-    for (int q = tid; q < P * d; q += T) {
-      const int p = q / d, j = q - p * d, k = tile * P + p;
-      float x = 0.f;
-      if (prm.x0_per_path) { if (k < prm.K_local) x = __ldg(prm.x0 + (size_t)k * d + j); }
-      else x = __ldg(prm.x0 + j);
-      sAct[p * g.lda + g.x_col + j] = x;
-    }
+    tile_init_state(prm, sAct, tile, P, false, tid, T);
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
-      for (int s = 0; s < g.L; ++s) if (g.seg_one[s] >= 0) sAct[p * g.lda + g.seg_one[s]] = 1.0f;
       sY[p] = 0.f; sZs[p] = 0.f; sG[p] = 0.f;
       swY[p] = (k < prm.K_local) ? prm.w_attached : 0.f;
     }
@@ -627,14 +743,14 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     for (int n = 0; n < N; ++n) {
       for (int q = tid; q < P * d; q += T) {  // checkpoint X_n
         const int p = q / d, j = q - p * d;
-        ck[(size_t)n * P * d + q] = sAct[p * g.lda + g.x_col + j];
+        ck[(size_t)n * P * d + q] = sAct[p * g.lda + j];
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
-      stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
+      if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
       __syncthreads();
-      net_forward<P, 4>(prm, sl, smem, tid, T);
-      sde_step<P, false>(prm, sl, smem, n == N - 1, warp, lane, NW);
+      net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
+      sde_step<P, false>(prm, sl, smem, tile, n, n == N - 1, warp, lane, NW);
       __syncthreads();
     }
     // ---------------- outputs + lambda_N = w grad g(X_N)
@@ -658,14 +774,14 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
       if (prm.X_N) {
         for (int q = tid; q < P * d; q += T) {
           const int p = q / d, j = q - p * d, k = tile * P + p;
-          if (k < prm.K_local) prm.X_N[(size_t)k * d + j] = sAct[p * g.lda + g.x_col + j];
+          if (k < prm.K_local) prm.X_N[(size_t)k * d + j] = sAct[p * g.lda + j];
         }
       }
     }
     __syncthreads();   // weights of non-finite trajectories were zeroed above
     for (int p = warp; p < P; p += NW) {
       const float w = swY[p];
-      const float* xr = sAct + p * g.lda + g.x_col;
+      const float* xr = sAct + p * g.lda;
       for (int j = lane; j < d; j += 32) {
         const float x = xr[j];
         sLam[p * g.ldz + j] = (w != 0.f) ? w * (al[j] + 2.0f * r_d[j] * x + 2.0f * eta[j] * (x - 1.0f)) : 0.f;
@@ -677,7 +793,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     for (int n = N - 1; n >= 0; --n) {
       for (int p = warp; p < P; p += NW) {
         const float w = swY[p];
-        float* xr = sAct + p * g.lda + g.x_col;
+        float* xr = sAct + p * g.lda;
         float* lr = sLam + p * g.ldz;
         for (int j = lane; j < d; j += 32) {
           if (w != 0.f) {
@@ -689,7 +805,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
       __syncthreads();
-      net_forward<P, 4>(prm, sl, smem, tid, T);
+      net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
       for (int p = warp; p < P; p += NW) {                          // zeta -> sXi
         const float w = swY[p];
         const float* zr = smem + sl.z + p * g.ldz;
@@ -703,7 +819,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
         }
       }
       __syncthreads();
-      net_backward_hidden<P>(prm, sl, smem, tid, T);
+      net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);
       // cotangent on X through the network input: dx = sum_l delta_l . W_l[x rows]'  -> sZ
       {
         float* sDx = smem + sl.z;
@@ -713,20 +829,19 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           const LayerGeom& y = g.layer[l];
           const float* dl = (l == g.L - 1) ? smem + sl.xi : smem + sl.delta + (y.out_col - g.hid_off);
           const int ldl = (l == g.L - 1) ? g.ldz : g.ldd;
-          const float* Wrows = smem + sl.w + y.w_off + g.x_col * y.ldw;
           const bool first = (l == 0);
           auto epi = [&](int p, int c, float v) {
             float* o = sDx + p * ldz + c;
             *o = first ? v : *o + v;
           };
-          gemm_nt<P, 2, 4>(dl, ldl, Wrows, y.ldw, y.Np, d, tid, T, epi);
+          gemm_nt<P, 2, 4>(dl, ldl, smem + sl.w + y.w_off, y.nng, 0, y.Np, d, warp, lane, NW, epi);   // X rows = 0..d-1
         }
       }
-      bw_accum<P, NB>(acc, a_off, d_off, d_ld, smem, g.lda);
+      bw_accum<P, NB>(acc, g, sl, smem, tid, T);
       if (outer) bw_flush<NB>(acc, g, tid, T, gp + (size_t)n * g.n_params);
       __syncthreads();
       for (int p = warp; p < P; p += NW) {                          // lambda_n
-        const float* xr = sAct + p * g.lda + g.x_col;
+        const float* xr = sAct + p * g.lda;
         const float* dx = smem + sl.z + p * g.ldz;
         float* lr = sLam + p * g.ldz;
         if (!dense) {
