@@ -121,6 +121,8 @@ int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream);
 /* Deterministic fp32 FMA throughput probe (roofline denominator measured live by bench.py):
  * runs `iters` dependent-chain FMA rounds on every SM; returns the FLOP count launched, or <0. */
 int64_t pspde_fma_probe(int iters, float* sink, void* stream);
+/* mode 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2), 2 = FFMA2 and FFMA interleaved */
+int64_t pspde_fma_probe_ex(int mode, int iters, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -120,8 +120,7 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
   pl.T = 512; pl.NB = 1;
   if (bwd) {   // one 8x8 weight-gradient block (64 accumulators) per thread
     const int nb = pl.g.n_blocks;
-    if (nb <= 256) pl.T = 256;
-    else if (nb <= 448) pl.T = 448;
+    if (nb <= 224) pl.T = 256;           // leaves a spare warp for the row-split leftover blocks
     else if (nb <= 512) pl.T = 512;
     else return fail(-6, "network too large for the register-resident gradient path (%d 8x8 blocks > 512)", nb);
   }
@@ -162,8 +161,6 @@ static inline int launch_rollout(const Plan& pl, const RolloutParams& p, void* s
 // defined in api_bwd*.cu / api_att*.cu (one translation unit per thread count so that the template instantiations
 // compile in parallel)
 int pspde_launch_bwd_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
-int pspde_launch_bwd_448(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_bwd_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_att_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);
-int pspde_launch_att_448(const Plan& pl, const pspde::RolloutParams& p, void* stream);
 int pspde_launch_att_512(const Plan& pl, const pspde::RolloutParams& p, void* stream);

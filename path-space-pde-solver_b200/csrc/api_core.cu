@@ -69,7 +69,6 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
   if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
   if (pl.T == 256) rc = pspde_launch_bwd_256(pl, p, stream);
-  else if (pl.T == 448) rc = pspde_launch_bwd_448(pl, p, stream);
   else if (pl.T == 512) rc = pspde_launch_bwd_512(pl, p, stream);
   else rc = fail(-13, "internal: no kernel for T=%d NB=%d", pl.T, pl.NB);
   if (rc) return rc;
@@ -102,8 +101,7 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
   p.x_ckpt = reinterpret_cast<float*>(ws + pl.stats_bytes + pl.grad_bytes);
   if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
-  rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream)
-       : (pl.T == 448) ? pspde_launch_att_448(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
+  rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
   if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);
@@ -126,13 +124,19 @@ int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream) {
   return 0;
 }
 
-int64_t pspde_fma_probe(int iters, float* sink, void* stream) {
+int64_t pspde_fma_probe(int iters, float* sink, void* stream) { return pspde_fma_probe_ex(0, iters, sink, stream); }
+
+int64_t pspde_fma_probe_ex(int mode, int iters, float* sink, void* stream) {
   const int sms = pspde_sm_count();
-  if (sms <= 0 || iters < 1 || !sink) { fail(-1, "bad arguments"); return -1; }
-  PSPDE_LAUNCH(fma_probe_kernel, sms, 1024, 0, stream, iters, sink);
+  if (sms <= 0 || iters < 1 || !sink || mode < 0 || mode > 2) { fail(-1, "bad arguments"); return -1; }
+  if (mode == 0) PSPDE_LAUNCH(fma_probe_kernel<0>, sms, 1024, 0, stream, iters, sink);
+  else if (mode == 1) PSPDE_LAUNCH(fma_probe_kernel<1>, sms, 1024, 0, stream, iters, sink);
+  else PSPDE_LAUNCH(fma_probe_kernel<2>, sms, 1024, 0, stream, iters, sink);
   g_launches++;
   if (const char* e = pspde_peek_error()) { fail(-12, "fma_probe launch failed: %s", e); return -1; }
-  return (int64_t)sms * 1024 * (int64_t)iters * 16 * 8 * 2;
+  // FLOPs: 16 x 8 FMA-slots per iteration; a packed slot is 2 FMAs, the mixed mode has 4 packed + 8 scalar per 8 slots
+  const int64_t fma_per_iter = mode == 0 ? 16 * 8 : mode == 1 ? 16 * 16 : 16 * (4 * 2 + 4 * 2);
+  return (int64_t)sms * 1024 * (int64_t)iters * fma_per_iter * 2;
 }
 
 }  // extern "C"

@@ -234,70 +234,93 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, c
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW_l += act^T . delta_l, accumulated in registers across the whole step loop.  Block b of the global list ->
 // (layer, kg, ng) owning the 4-row groups {kg, kg + kgh} x the 4-col groups {ng, ng + ngh} (64 accumulators).
-template <int P, int NB>
-__device__ __forceinline__ void bw_accum(f32x2 (&acc)[NB][32], const NetGeom& g, const SmemLayout& sl,
-                                         const float* smem, int tid, int nthr) {
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const int b = tid + nthr * j;
-    if (b < g.n_blocks) {
-      int l = 0;
-      while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
-      const LayerGeom& y = g.layer[l];
-      const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
-      const bool last = (l == g.L - 1);
-      const int ldd = last ? g.ldz : g.ldd;
-      const float* a0p = smem + sl.act + y.in_start + 4 * kg;
-      const float* d0p = smem + (last ? sl.xi : sl.delta + (y.out_col - g.hid_off)) + 4 * ng;
-      // a missing half (edge block) reads the always-zero pad with stride 0
-      const bool ha = kg + y.kgh < y.nkg, hd = ng + y.ngh < y.nng;
-      const float* a1p = ha ? a0p + 4 * y.kgh : smem + sl.zero;
-      const float* d1p = hd ? d0p + 4 * y.ngh : smem + sl.zero;
-      const int sa1 = ha ? g.lda : 0, sd1 = hd ? ldd : 0;
-      const int lda = g.lda;
+// Block -> thread assignment.  Whole warps take one block per lane over all P rows; the nb % 32 leftover blocks are
+// split along the row (trajectory) dimension over the lanes of the otherwise idle warps, so that no SMSP carries
+// an extra full-length warp for a handful of blocks (SMSP loads 3/3/3/3 + a sliver instead of 4/3/3/3 at C2).
+// A leftover block is split into cpb = 2^k row chunks held by cpb ADJACENT lanes of one warp; the flush combines
+// them with a fixed xor-shuffle butterfly, so the result stays bitwise deterministic.
+struct BwSlot { int b, p_lo, p_hi, cpb; };   // cpb > 1: this WARP holds row-split blocks (uniform per warp)
+
+__device__ __forceinline__ BwSlot bw_slot(const NetGeom& g, int P, int tid, int nthr) {
+  BwSlot s; s.b = -1; s.p_lo = 0; s.p_hi = P; s.cpb = 1;
+  const int nb = g.n_blocks, full = nb & ~31, rem = nb - full, lrem = nthr - full;
+  if (tid < full) { s.b = tid; return s; }
+  if (rem == 0 || lrem <= 0) return s;
+  int cpb = 1;
+  while (cpb * 2 <= 32 && cpb * 2 <= P && cpb * 2 * rem <= lrem) cpb *= 2;
+  const int l = tid - full, chunk = P / cpb;     // P and cpb are powers of two
+  s.cpb = cpb;
+  if (l < rem * cpb) {
+    s.b = full + l / cpb;
+    s.p_lo = (l % cpb) * chunk;
+    s.p_hi = s.p_lo + chunk;
+  }
+  return s;
+}
+
+template <int P>
+__device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, const SmemLayout& sl,
+                                         const float* smem, const BwSlot& slot) {
+  if (slot.b < 0) return;
+  const int b = slot.b;
+  int l = 0;
+  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
+  const LayerGeom& y = g.layer[l];
+  const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+  const bool last = (l == g.L - 1);
+  const int ldd = last ? g.ldz : g.ldd;
+  const int lda = g.lda;
+  const float* a0p = smem + sl.act + y.in_start + 4 * kg + slot.p_lo * lda;
+  const float* d0p = smem + (last ? sl.xi : sl.delta + (y.out_col - g.hid_off)) + 4 * ng + slot.p_lo * ldd;
+  // a missing half (edge block) reads the always-zero pad with stride 0
+  const bool ha = kg + y.kgh < y.nkg, hd = ng + y.ngh < y.nng;
+  const float* a1p = ha ? a0p + 4 * y.kgh : smem + sl.zero;
+  const float* d1p = hd ? d0p + 4 * y.ngh : smem + sl.zero;
+  const int sa1 = ha ? lda : 0, sd1 = hd ? ldd : 0;
 #pragma unroll 2
-      for (int p = 0; p < P; ++p) {
-        const float4 a0 = ld4(a0p), v0 = ld4(d0p), a1 = ld4(a1p), v1 = ld4(d1p);
-        a0p += lda; a1p += sa1; d0p += ldd; d1p += sd1;
-        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  for (int p = slot.p_lo; p < slot.p_hi; ++p) {
+    const float4 a0 = ld4(a0p), v0 = ld4(d0p), a1 = ld4(a1p), v1 = ld4(d1p);
+    a0p += lda; a1p += sa1; d0p += ldd; d1p += sd1;
+    const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ffma2_s(acc[j][4 * i + 0], ar[i], v0.x, v0.y); ffma2_s(acc[j][4 * i + 1], ar[i], v0.z, v0.w);
-          ffma2_s(acc[j][4 * i + 2], ar[i], v1.x, v1.y); ffma2_s(acc[j][4 * i + 3], ar[i], v1.z, v1.w);
-        }
-      }
+    for (int i = 0; i < 8; ++i) {
+      ffma2_s(acc[4 * i + 0], ar[i], v0.x, v0.y); ffma2_s(acc[4 * i + 1], ar[i], v0.z, v0.w);
+      ffma2_s(acc[4 * i + 2], ar[i], v1.x, v1.y); ffma2_s(acc[4 * i + 3], ar[i], v1.z, v1.w);
     }
   }
 }
 
-// acc -> grad_partial (this CTA's private slice; plain read-modify-write, no other writer), then clear.
-template <int NB>
-__device__ __forceinline__ void bw_flush(f32x2 (&acc)[NB][32], const NetGeom& g, int tid, int nthr,
-                                         float* __restrict__ gp) {
+// acc -> grad_partial (this CTA's private slice; plain read-modify-write, one writer per element), then clear.
+// Must be called by all lanes of a warp (row-split warps combine their chunks with shuffles first).
+__device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, const BwSlot& slot,
+                                         float* __restrict__ gp, int lane) {
+  if (slot.cpb == 1 && slot.b < 0) return;      // whole warp idle or plain lane without a block
+  const int b = slot.b < 0 ? 0 : slot.b;
+  int l = 0;
+  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
+  const LayerGeom& y = g.layer[l];
+  const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+  const bool writer = slot.b >= 0 && (slot.cpb == 1 || (lane & (slot.cpb - 1)) == 0);
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const int b = tid + nthr * j;
-    if (b < g.n_blocks) {
-      int l = 0;
-      while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
-      const LayerGeom& y = g.layer[l];
-      const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * (i < 4 ? kg : kg + y.kgh) + (i & 3);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * (i < 4 ? kg : kg + y.kgh) + (i & 3);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[2];
-          f2_unpack(acc[j][4 * i + q], v[0], v[1]);
-          acc[j][4 * i + q] = f2_zero();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = 4 * (q < 2 ? ng : ng + y.ngh) + 2 * (q & 1) + h;
-            const bool ok = (i < 4 || kg + y.kgh < y.nkg) && (q < 2 || ng + y.ngh < y.nng);
-            const int idx = ok ? theta_index(g, l, row, col) : -1;
-            if (idx >= 0) gp[idx] += v[h];
-          }
+    for (int q = 0; q < 4; ++q) {
+      float v[2];
+      f2_unpack(acc[4 * i + q], v[0], v[1]);
+      acc[4 * i + q] = f2_zero();
+      if (slot.cpb > 1) {                        // warp-uniform: sum the row chunks of each block, fixed order
+        for (int o = 1; o < slot.cpb; o <<= 1) {
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+          v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
         }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = 4 * (q < 2 ? ng : ng + y.ngh) + 2 * (q & 1) + h;
+        const bool ok = writer && (i < 4 || kg + y.kgh < y.nkg) && (q < 2 || ng + y.ngh < y.nng);
+        const int idx = ok ? theta_index(g, l, row, col) : -1;
+        if (idx >= 0) gp[idx] += v[h];
       }
     }
   }
@@ -600,12 +623,12 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
   for (int q = tid; q < 7 * d; q += T) { const int v = q / d, j = q - v * d; smem[sl.prob + v * d4 + j] = __ldg(prm.prob + q); }
   if (!outer) stage_weights(g, prm.theta, smem + sl.w, tid, T);
 
-  f32x2 acc[NB][32];
+  static_assert(NB == 1, "one 8x8 weight-gradient block per thread");
+  f32x2 acc[32];
+  BwSlot slot = bw_slot(g, P, tid, T);
   if (BWD) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
-#pragma unroll
-      for (int q = 0; q < 32; ++q) acc[j][q] = f2_zero();
+    for (int q = 0; q < 32; ++q) acc[q] = f2_zero();
   }
   float* gp = BWD ? prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total : nullptr;
   __syncthreads();
@@ -636,8 +659,8 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       __syncthreads();
       if (BWD) {
         net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);
-        bw_accum<P, NB>(acc, g, sl, smem, tid, T);
-        if (outer) bw_flush<NB>(acc, g, tid, T, gp + (size_t)n * g.n_params);
+        bw_accum<P>(acc, g, sl, smem, slot);
+        if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.n_params, lane);
         __syncthreads();
         for (int q = tid; q < P * (d4 >> 2); q += T) {  // X_{n+1}: parked in sZ -> activation tile
           const int p = q / (d4 >> 2), jb = q - p * (d4 >> 2);
@@ -675,7 +698,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
         }
       }
     } else if (!outer) {
-      bw_flush<NB>(acc, g, tid, T, gp);   // one flush per tile bounds the fp32 accumulation length to P*N terms
+      bw_flush(acc, g, slot, gp, lane);   // one flush per tile bounds the fp32 accumulation length to P*N terms
     }
     __syncthreads();
   }
@@ -722,11 +745,11 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
   for (int q = tid; q < 7 * d; q += T) { const int v = q / d, j = q - v * d; smem[sl.prob + v * d4 + j] = __ldg(prm.prob + q); }
   if (!outer) stage_weights(g, prm.theta, smem + sl.w, tid, T);
 
-  f32x2 acc[NB][32];
+  static_assert(NB == 1, "one 8x8 weight-gradient block per thread");
+  f32x2 acc[32];
+  const BwSlot slot = bw_slot(g, P, tid, T);
 #pragma unroll
-  for (int j = 0; j < NB; ++j)
-#pragma unroll
-    for (int q = 0; q < 32; ++q) acc[j][q] = f2_zero();
+  for (int q = 0; q < 32; ++q) acc[q] = f2_zero();
   float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
   float* ck = prm.x_ckpt + (size_t)blockIdx.x * N * P * d;
   __syncthreads();
@@ -837,8 +860,8 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           gemm_nt<P, 2, 4>(dl, ldl, smem + sl.w + y.w_off, y.nng, 0, y.Np, d, warp, lane, NW, epi);   // X rows = 0..d-1
         }
       }
-      bw_accum<P, NB>(acc, g, sl, smem, tid, T);
-      if (outer) bw_flush<NB>(acc, g, tid, T, gp + (size_t)n * g.n_params);
+      bw_accum<P>(acc, g, sl, smem, slot);
+      if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.n_params, lane);
       __syncthreads();
       for (int p = warp; p < P; p += NW) {                          // lambda_n
         const float* xr = sAct + p * g.lda;
@@ -868,7 +891,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
         }
       }
     }
-    if (!outer) bw_flush<NB>(acc, g, tid, T, gp);
+    if (!outer) bw_flush(acc, g, slot, gp, lane);
     __syncthreads();
   }
   if (tid < 4 && prm.stats_partial) prm.stats_partial[blockIdx.x * 4 + tid] = sRed[tid];
@@ -912,19 +935,29 @@ static __global__ void philox_dump_kernel(int K_local, int k_offset, int d, int 
   }
 }
 
-// FP32 FMA throughput probe: 8 independent chains per thread, 2 FLOP per FMA
+// FP32 FMA throughput probe: 8 independent chains per thread.
+//   mode 0: scalar FFMA (2 FLOP each)   mode 1: packed FFMA2 (4 FLOP each)   mode 2: one FFMA2 + two FFMA interleaved
+template <int MODE>
 static __global__ void __launch_bounds__(1024, 1) fma_probe_kernel(int iters, float* __restrict__ sink) {
-  float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
-        a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float m = 0.9999f, c = 1e-7f;
-  for (int i = 0; i < iters; ++i) {
+  float a[8];
+  f32x2 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = threadIdx.x * 1e-9f + i; b[i] = f2_zero(); }
+  for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
-      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE == 0) a[i] = fmaf(a[i], m, c);
+        else if (MODE == 1) ffma2_s(b[i], m, a[i], c);
+        else { if (i & 1) ffma2_s(b[i], m, a[i], c); else { a[i] = fmaf(a[i], m, c); a[i] = fmaf(a[i], m, c); } }
+      }
     }
   }
-  const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { float lo, hi; f2_unpack(b[i], lo, hi); s += a[i] + lo + hi; }
   if (s == 123.456f) sink[0] = s;
 }
 

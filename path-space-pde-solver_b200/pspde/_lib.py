@@ -48,6 +48,7 @@ PROTOTYPES = {
                                               ctypes.c_size_t, _P]),
     "pspde_philox_dump": (ctypes.c_int, [_CFG, _P, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
+    "pspde_fma_probe_ex": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, _P, _P]),
 }
 
 
