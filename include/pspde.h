@@ -83,6 +83,10 @@ int          pspde_abi_version(void);
 const char*  pspde_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 uint64_t     pspde_launch_count(void);
+/* Debug hook: when set to a device buffer of 16 uint64 (zeroed by the caller), CTA 0 of the detached rollout
+ * kernels adds clock64() cycles per phase: [0] step prologue, [1] network forward, [2] SDE step, [3] hidden
+ * cotangents, [4] weight gradient.  NULL (default) disables it. */
+void         pspde_set_profile_buffer(unsigned long long* dev_buf16);
 /* number of parameters in theta for cfg (all N sets in TIME_NONE mode); <0 on invalid cfg */
 int64_t      pspde_theta_size(const pspde_cfg* cfg);
 /* scratch bytes the rollout entry points need for cfg (upper bound over all of them) */

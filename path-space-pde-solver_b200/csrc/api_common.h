@@ -46,6 +46,7 @@ static_assert(sizeof(pspde_cfg) == 112, "pspde_cfg layout is part of the ABI (mi
 
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
+extern unsigned long long* g_prof;   // device buffer for the opt-in phase profiler (pspde_set_profile_buffer)
 
 static inline int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -83,9 +84,11 @@ static inline int validate(const pspde_cfg* c) {
 }
 
 // rows per thread tile in gemm_nn.  Per k4 step a warp tile of R rows x 4 cols issues 8R FFMA2 (16R FP32-pipe
-// cycles on its SMSP) and 2R + 8 shared-memory wavefronts (one per cycle, SM wide).  Pick the R that minimises
-// max(pipe time of the busiest SMSP, shared-memory time), with a penalty when an SMSP is left with a single warp
-// (nothing to hide the LDS latency behind).
+// cycles on its SMSP) and, as measured with ncu on B200 (profiles/), 4 shared-memory wavefronts per activation
+// LDS.128 (8 distinct rows per quarter-warp; quarter-warps do not merge) and 2 per weight LDS.128 (quarter-uniform
+// address): 4R + 8 wavefronts at one wavefront per cycle SM wide.  Pick the R that minimises max(pipe time of the
+// busiest SMSP, shared-memory time), with a penalty when an SMSP is left with a single warp (nothing to hide the
+// LDS latency behind).
 static inline int choose_r(int nng, int T, int rmax) {
   const int nw = T / 32;
   int best = 1;
@@ -95,7 +98,8 @@ static inline int choose_r(int nng, int T, int rmax) {
     const long waves = (nwt + nw - 1) / nw;
     const long per_wave = nwt < nw ? nwt : nw;
     const long per_smsp = (per_wave + 3) / 4;
-    long cost = waves * (per_smsp * 16 * R > per_wave * (2 * R + 8) ? per_smsp * 16 * R : per_wave * (2 * R + 8));
+    const long pipe = per_smsp * 16 * R, smem = per_wave * (4 * R + 8);
+    long cost = waves * (pipe > smem ? pipe : smem);
     if (per_smsp == 1) cost += 40 * waves;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = R; }
   }
@@ -144,6 +148,7 @@ static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams
   p.xs_k = c->xi_stride_k; p.xs_j = c->xi_stride_j; p.xs_n = c->xi_stride_n;
   p.n_tiles = pl.n_tiles; p.n_theta_total = pl.n_theta_total;
   for (int l = 0; l < PSPDE_MAXL; ++l) p.r_fwd[l] = pl.r_fwd[l];
+  p.prof = g_prof;
 }
 
 template <int T, bool BWD, int NB>

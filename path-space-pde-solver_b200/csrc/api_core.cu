@@ -3,12 +3,14 @@
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+unsigned long long* g_prof = nullptr;
 
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
 const char* pspde_last_error(void) { return g_err; }
 uint64_t pspde_launch_count(void) { return g_launches.load(); }
+void pspde_set_profile_buffer(unsigned long long* dev_buf16) { g_prof = dev_buf16; }
 
 int64_t pspde_theta_size(const pspde_cfg* cfg) {
   if (validate(cfg)) return -1;

@@ -137,4 +137,14 @@ PSPDE_HD inline int theta_index(const NetGeom& g, int l, int r, int n) {
   return y.th_w + n * y.fan_in + fi;
 }
 
+// Weight-gradient block r (0 <= r < kgh * ngh) of a layer -> (kg, ng).  Blocks are ordered in column chunks of 8:
+// the 8 lanes of a quarter-warp then read ONE 4-row group of the activations (a broadcast) and 8 consecutive
+// float4s of the cotangent (one 128 B wavefront); with a plain row-major order a quarter-warp wraps around the
+// end of a cotangent row and hits 2-way bank conflicts.
+PSPDE_HD inline void bw_block_coords(const LayerGeom& y, int r, int& kg, int& ng) {
+  const int full = (y.ngh >> 3) * 8 * y.kgh;     // blocks in the full-width chunks
+  if (r < full) { const int c = r / (8 * y.kgh), q = r - c * 8 * y.kgh; kg = q >> 3; ng = 8 * c + (q & 7); }
+  else { const int w = y.ngh & 7, q = r - full; kg = q / w; ng = (y.ngh & ~7) + q % w; }
+}
+
 }  // namespace pspde

@@ -39,6 +39,7 @@ struct RolloutParams {
   double* stats_partial;  // [gridDim.x][4]
   float* grad_partial;    // [gridDim.x][n_theta_total]
   float* x_ckpt;          // attached mode: [gridDim.x][N][P][d] state checkpoints of the current tile
+  unsigned long long* prof;  // debug: per-phase clock64() totals of CTA 0 (16 slots) or nullptr
 };
 
 struct SmemLayout { int w, act, z, xi, delta, lam, scal, prob, red, zero, total; };
@@ -266,7 +267,8 @@ __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, con
   int l = 0;
   while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
   const LayerGeom& y = g.layer[l];
-  const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+  int kg, ng;
+  bw_block_coords(y, b - y.blk_begin, kg, ng);
   const bool last = (l == g.L - 1);
   const int ldd = last ? g.ldz : g.ldd;
   const int lda = g.lda;
@@ -299,7 +301,8 @@ __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, con
   int l = 0;
   while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
   const LayerGeom& y = g.layer[l];
-  const int r = b - y.blk_begin, kg = r / y.ngh, ng = r % y.ngh;
+  int kg, ng;
+  bw_block_coords(y, b - y.blk_begin, kg, ng);
   const bool writer = slot.b >= 0 && (slot.cpb == 1 || (lane & (slot.cpb - 1)) == 0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -595,6 +598,25 @@ __device__ __forceinline__ void tile_init_state(const RolloutParams& prm, float*
     for (int s = 0; s < g.L; ++s) if (g.seg_one[s] >= 0) sAct[p * g.lda + g.seg_one[s]] = 1.0f;
 }
 
+// opt-in phase profiler (pspde_set_profile_buffer): thread 0 of CTA 0 adds the cycles since the last mark to slot `ph`
+struct PhaseTimer {
+  unsigned long long* buf; long long t;
+  __device__ __forceinline__ void start(unsigned long long* b, int tid) {
+#if defined(PSPDE_EMULATE)
+    buf = nullptr; t = 0; (void)b; (void)tid;
+#else
+    buf = (b && tid == 0 && blockIdx.x == 0) ? b : nullptr; t = buf ? clock64() : 0;
+#endif
+  }
+  __device__ __forceinline__ void mark(int ph) {
+#if !defined(PSPDE_EMULATE)
+    if (buf) { const long long n = clock64(); buf[ph] += (unsigned long long)(n - t); t = n; }
+#else
+    (void)ph;
+#endif
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ the kernel
 // BWD = false: forward rollout, writes per-path outputs and the loss statistics.
 // BWD = true : recompute rollout + accumulate dLoss/dtheta (detached mode).  NB = weight-gradient blocks/thread.
@@ -646,6 +668,8 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
     }
     // (no barrier needed here: the step prologue below ends with one)
 
+    PhaseTimer pt_;
+    pt_.start(prm.prof, tid);
     for (int n = 0; n < N; ++n) {
       // time column: in BWD the float4 copy-back of X_{n+1} at the end of the previous step also covers the t column
       // when d % 4 != 0; it then writes t_{n+1} itself (same thread, no race with this loop)
@@ -654,14 +678,19 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
       __syncthreads();
+      pt_.mark(0);
       net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, warp, lane, NW);
+      pt_.mark(1);
       sde_step<P, BWD>(prm, sl, smem, tile, n, n == N - 1, warp, lane, NW);
       __syncthreads();
+      pt_.mark(2);
       if (BWD) {
         net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);
+        pt_.mark(3);
         bw_accum<P>(acc, g, sl, smem, slot);
         if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.n_params, lane);
         __syncthreads();
+        pt_.mark(4);
         for (int q = tid; q < P * (d4 >> 2); q += T) {  // X_{n+1}: parked in sZ -> activation tile
           const int p = q / (d4 >> 2), jb = q - p * (d4 >> 2);
           st4(sAct + p * g.lda + 4 * jb, ld4(smem + sl.z + p * g.ldz + 4 * jb));

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "pspde_abi_version": (ctypes.c_int, []),
     "pspde_last_error": (ctypes.c_char_p, []),
     "pspde_launch_count": (ctypes.c_uint64, []),
+    "pspde_set_profile_buffer": (None, [_P]),
     "pspde_theta_size": (ctypes.c_int64, [_CFG]),
     "pspde_workspace_bytes": (ctypes.c_size_t, [_CFG]),
     "pspde_rollout_fwd": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -173,6 +173,8 @@ def test_full_size_properties_c2():
     # they are counted, dropped from the statistics and must not poison the gradient
     assert st[3].item() == (~ok).sum().item() <= 8
     w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    w1[~ok] = 0.0                                     # the host gives dropped trajectories zero weight
+    w2[~ok] = 0.0
     gs = []
     for w in (w1, w2, (w1 + 2 * w2).contiguous()):
         gr = pt.empty(eng.n_theta, device="cuda")
