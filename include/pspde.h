@@ -110,12 +110,16 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
                                const float* xi, const float* wY, const float* wZ, float* grad_theta,
                                void* workspace, size_t workspace_bytes, void* stream);
 
-/* Forward + backward for detach_forward=False with the relative-entropy loss mean(Zsum + g(X_N))
- * (solver.py:180, :484-486, :221): per tile of paths the states X_n are checkpointed to the workspace and
- * the discrete adjoint runs backwards in time in the same kernel.  w = 1 / K_global.  Outputs as in
- * pspde_rollout_fwd plus grad_theta (overwritten). */
+/* Forward + backward for detach_forward=False (solver.py:451-469 without the detach, :221): per tile of paths the
+ * states X_n are checkpointed to the workspace and the discrete adjoint runs backwards in time in the same kernel.
+ *   - relative entropy, loss = mean(Zsum + g(X_N)) (solver.py:180): pass wY = wZ = wG = NULL and w = 1 / K_global;
+ *     one launch gives outputs, statistics and the gradient.
+ *   - any other loss: run pspde_rollout_fwd first, form the per-path cotangents wY = dL/dY_N, wZ = dL/dZsum,
+ *     wG = dL/dg(X_N) (length K_local, any of them nullable = 0), then call this with them (w is ignored).
+ * Outputs as in pspde_rollout_fwd (all nullable) plus grad_theta (overwritten). */
 int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
-                           const float* xi, float w, float* X_N, float* gX, float* Zsum, double* stats,
+                           const float* y0, const float* xi, float w, const float* wY, const float* wZ,
+                           const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                            float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Test hook: writes the increments the kernels would generate for cfg (Philox mode) in the layout

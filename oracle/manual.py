@@ -265,6 +265,47 @@ def grad_mode_b(problem, net, xi, dt, N, X0, time_mode="first"):
     return grad, ro
 
 
+def loss_cotangents_full(loss_method, Y, gX, Zsum, adaptive=True):
+    """(loss, wY, wZ, wG): cotangents on Y_N, Z_sum and g(X_N) -- needed when X depends on theta (attached mode)."""
+    K = Y.shape[0]
+    loss, wY, wZ = loss_and_weights(loss_method, Y, gX, Zsum, adaptive)
+    if loss_method == "relative_entropy":
+        wG = np.full_like(Y, 1.0 / K)
+    elif loss_method == "cross_entropy":
+        E = np.exp(Y - gX) if adaptive else np.exp(-gX)
+        wG = -Y * E / K
+    else:                       # log-variance, moment, variance depend on D = Y - g only
+        wG = -wY
+    return loss, wY, wZ, wG
+
+
+def grad_attached(problem, nets, xi, dt, N, X0, wY, wZ, wG, time_mode="first", y0=0.0):
+    """Discrete adjoint for the attached adaptive forward process (c = -Z, not detached) and ANY loss given as
+    per-path cotangents (wY on Y_N, wZ on Z_sum, wG on g(X_N)):
+        lambda_N = wG grad g(X_N)
+        n = N-1..0:  lambda += (wY + wZ) dt grad f(X_{n+1})
+                     zeta = wY (-Z dt + sqrt(dt) xi) + wZ Z dt - dt (lambda B)
+                     dtheta += J_theta' zeta ;  lambda += dt J_b' lambda + J_x' zeta
+    (Y+ = Y + (f(X+) - |Z|^2/2) dt + Z.xi sqrt(dt), Zsum+ = Zsum + (|Z|^2/2 + f(X+)) dt, X+ = X + (b - BZ) dt + B xi sqrt(dt))."""
+    dtype = xi.dtype
+    s = np.sqrt(dtype.type(dt))
+    ro = rollout(problem, nets, xi, dt, N, X0, True, y0, time_mode)
+    outer = isinstance(nets, list)
+    grads = [0.0] * (N if outer else 1)
+    lam = wG[:, None] * problem.grad_g(ro["X"])
+    for n in range(N - 1, -1, -1):
+        net = nets[n] if outer else nets
+        Xn = ro["path"][n]
+        lam = lam + (wY + wZ)[:, None] * problem.grad_f(ro["path"][n + 1]) * dt
+        Z, tape = net.forward(net_input(Xn, n, dt, time_mode))
+        zeta = wY[:, None] * (-Z * dt + s * xi[:, :, n + 1]) + wZ[:, None] * Z * dt - dt * (lam @ problem.B)
+        g, dx = net.vjp(tape, zeta, want_dx=True)
+        grads[n if outer else 0] = grads[n if outer else 0] + g
+        x_lo = 1 if time_mode == "first" else 0
+        lam = lam + dt * problem.Jb_T_vec(Xn, lam) + dx[:, x_lo:x_lo + problem.d]
+    return np.concatenate([np.atleast_1d(g) for g in grads]), ro
+
+
 # ------------------------------------------------------------------ diffusion loss (solver.py:1062-1163, h == 0)
 def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0):
     """Value and theta-gradient of the diffusion loss, unbounded domain, non-adaptive; net input is [X, t]."""

@@ -82,7 +82,8 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
 }
 
 int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
-                           const float* xi, float w, float* X_N, float* gX, float* Zsum, double* stats,
+                           const float* y0, const float* xi, float w, const float* wY, const float* wZ,
+                           const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                            float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
   Plan pl;
   int rc = make_plan(cfg, true, true, pl);
@@ -95,8 +96,9 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
     return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.grad_bytes + ckpt_bytes);
   RolloutParams p;
   fill_params(cfg, pl, p);
-  p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.w_attached = w;
-  p.X_N = X_N; p.gX = gX; p.Zsum = Zsum;
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi; p.w_attached = w;
+  p.wY = wY; p.wZ = wZ; p.wG = wG;
+  p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Zsum = Zsum;
   char* ws = reinterpret_cast<char*>(workspace);
   p.stats_partial = reinterpret_cast<double*>(ws);
   p.grad_partial = reinterpret_cast<float*>(ws + pl.stats_bytes);

@@ -33,8 +33,8 @@ struct RolloutParams {
   int n_tiles;         // ceil(K_local / P)
   int n_theta_total;   // n_params * (TIME_NONE ? N : 1)
   int r_fwd[PSPDE_MAXL];  // paths per thread tile in gemm_nn, per layer (1, 2, 4 or 8)
-  float w_attached;    // 1 / K_global (attached mode)
-  const float *theta, *prob, *x0, *y0, *xi, *wY, *wZ;
+  float w_attached;    // attached mode without per-path cotangents: wZ = wG = w_attached, wY = 0 (relative entropy)
+  const float *theta, *prob, *x0, *y0, *xi, *wY, *wZ, *wG;
   float *X_N, *Y_N, *gX, *Zsum;
   double* stats_partial;  // [gridDim.x][4]
   float* grad_partial;    // [gridDim.x][n_theta_total]
@@ -735,14 +735,18 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
 }
 
 // ------------------------------------------------------------------------------------------------ attached mode
-// detach_forward=False with loss = mean(Zsum + g(X_N)) (solver.py:180, :484-486).  The control feeds back into X,
-// so the gradient is a discrete adjoint lambda_n running backwards in time:
-//   lambda_N = w grad g(X_N)
-//   for n = N-1 .. 0:  lambda += w dt grad f(X_{n+1});  zeta = w dt Z_n - dt (lambda B)
+// detach_forward=False (solver.py:451-469 without the detach): the control feeds back into X, so the gradient is a
+// discrete adjoint lambda_n running backwards in time (generalised to any loss given by per-path
+// cotangents wY = dL/dY_N, wZ = dL/dZsum, wG = dL/dg(X_N); oracle/manual.py::grad_attached):
+//   lambda_N = wG grad g(X_N)
+//   for n = N-1 .. 0:  lambda += (wY + wZ) dt grad f(X_{n+1})
+//                      zeta = wY (-Z dt + sqrt(dt) xi_{n+1}) + wZ Z dt - dt (lambda B)
 //                      dtheta += J_theta Z(t_n, X_n)' zeta;  lambda += dt J_b(X_n)' lambda + J_x Z(t_n, X_n)' zeta
-// Per tile: forward sweep checkpoints X_n (P x d floats per step) to a per-CTA scratch slice, backward sweep
-// reloads them in reverse and recomputes the network; forward and backward of a tile run in the same kernel, so
-// the scratch is bounded by gridDim.x * N * P * d floats whatever K is.
+// Relative entropy (loss = mean(Zsum + g), solver.py:180) has constant cotangents wZ = wG = 1/K, wY = 0 and needs
+// a single launch; the other losses need the batch statistics first (forward launch, then this kernel).
+// Per tile: the forward sweep checkpoints X_n (P x d floats per step) to a per-CTA scratch slice, the backward
+// sweep reloads them in reverse and recomputes the network; forward and backward of a tile run in the same
+// kernel, so the scratch is bounded by gridDim.x * N * P * d floats whatever K is.
 template <int P, int T, int NB>
 __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutParams prm) {
   PSPDE_DYN_SMEM(smem4);
@@ -758,11 +762,15 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
   float* sY = smem + sl.scal;
   float* sZs = sY + P;
   float* sG = sY + 2 * P;
-  float* swY = sY + 3 * P;   // per-path weight w (0 for padding rows and dropped trajectories)
+  float* swY = sY + 3 * P;   // per-path cotangents (all 0 for padding rows and dropped trajectories)
+  float* swZ = sY + 4 * P;
+  float* swG = sY + 5 * P;
   double* sRed = reinterpret_cast<double*>(smem + sl.red);
   const bool outer = (g.time_mode == TIME_NONE);
   const bool dense = (prm.flags & FLAG_DENSE_AB) != 0;
   const bool inject = prm.noise_mode != NOISE_PHILOX;
+  const bool per_path = prm.wY != nullptr || prm.wZ != nullptr || prm.wG != nullptr;
+  const float sq = sqrtf(dt);
   const float* pa = smem + sl.prob;
   const float *a_d = pa, *b_d = pa + d4, *p_d = pa + 2 * d4, *r_d = pa + 3 * d4, *al = pa + 4 * d4,
               *kap = pa + 5 * d4, *eta = pa + 6 * d4;
@@ -787,8 +795,13 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     tile_init_state(prm, sAct, tile, P, false, tid, T);
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
-      sY[p] = 0.f; sZs[p] = 0.f; sG[p] = 0.f;
-      swY[p] = (k < prm.K_local) ? prm.w_attached : 0.f;
+      sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f; sZs[p] = 0.f; sG[p] = 0.f;
+      const bool in = k < prm.K_local;
+      if (per_path) {
+        swY[p] = (in && prm.wY) ? __ldg(prm.wY + k) : 0.f;
+        swZ[p] = (in && prm.wZ) ? __ldg(prm.wZ + k) : 0.f;
+        swG[p] = (in && prm.wG) ? __ldg(prm.wG + k) : 0.f;
+      } else { swY[p] = 0.f; swZ[p] = in ? prm.w_attached : 0.f; swG[p] = swZ[p]; }
     }
     __syncthreads();
     // ---------------- forward sweep
@@ -815,8 +828,9 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
           if (prm.Y_N) prm.Y_N[k] = sY[tid];
-          const double v = (double)ZS + (double)G;
-          if (isfinite(v)) s2 = v; else { s3 = 1.0; swY[tid] = 0.f; }   // dropped from the batch and counted
+          const double v = (double)ZS + (double)G, D = (double)sY[tid] - (double)G;
+          if (isfinite(v) && isfinite(D)) s2 = v;
+          else { s3 = 1.0; swY[tid] = 0.f; swZ[tid] = 0.f; swG[tid] = 0.f; }   // dropped from the batch and counted
         }
       }
       if (warp < (P + 31) / 32) {
@@ -832,11 +846,12 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     }
     __syncthreads();   // weights of non-finite trajectories were zeroed above
     for (int p = warp; p < P; p += NW) {
-      const float w = swY[p];
+      const float w = swG[p];
+      const bool live = swY[p] != 0.f || swZ[p] != 0.f || w != 0.f;
       const float* xr = sAct + p * g.lda;
       for (int j = lane; j < d; j += 32) {
         const float x = xr[j];
-        sLam[p * g.ldz + j] = (w != 0.f) ? w * (al[j] + 2.0f * r_d[j] * x + 2.0f * eta[j] * (x - 1.0f)) : 0.f;
+        sLam[p * g.ldz + j] = live ? w * (al[j] + 2.0f * r_d[j] * x + 2.0f * eta[j] * (x - 1.0f)) : 0.f;
       }
     }
     __syncthreads();   // X_N has been copied out by the flat loop above before any row is overwritten below
@@ -844,30 +859,49 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     //                  between the end of one iteration and the start of the next)
     for (int n = N - 1; n >= 0; --n) {
       for (int p = warp; p < P; p += NW) {
-        const float w = swY[p];
+        const float wf = swY[p] + swZ[p];
+        const bool live = swY[p] != 0.f || swZ[p] != 0.f || swG[p] != 0.f;
         float* xr = sAct + p * g.lda;
         float* lr = sLam + p * g.ldz;
         for (int j = lane; j < d; j += 32) {
-          if (w != 0.f) {
-            lr[j] += w * dt * 2.0f * p_d[j] * xr[j];               // grad f at X_{n+1} (f = x'Px, P diagonal)
+          if (live) {
+            lr[j] += wf * dt * 2.0f * p_d[j] * xr[j];              // grad f at X_{n+1} (f = x'Px, P diagonal)
             xr[j] = ck[(size_t)n * P * d + p * d + j];             // reload X_n
           } else { lr[j] = 0.f; xr[j] = 0.f; }                     // inert row: finite state, zero adjoint
         }
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
+      if (inject && per_path) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);   // xi_{n+1} enters zeta through wY
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
       __syncthreads();
       net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
       for (int p = warp; p < P; p += NW) {                          // zeta -> sXi
-        const float w = swY[p];
+        const float wy = swY[p], wz = swZ[p];
         const float* zr = smem + sl.z + p * g.ldz;
         const float* lr = sLam + p * g.ldz;
         float* er = smem + sl.xi + p * g.ldz;
-        for (int j = lane; j < d; j += 32) {
-          float lb;
-          if (!dense) lb = lr[j] * b_d[j];
-          else { lb = 0.f; for (int i = 0; i < d; ++i) lb = fmaf(lr[i], __ldg(Bm + i * d + j), lb); }
-          er[j] = w * dt * zr[j] - dt * lb;
+        const unsigned kglob = (unsigned)(prm.k_offset + tile * P + p);
+        for (int jb = lane; 4 * jb < d; jb += 32) {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (wy != 0.f) {
+            if (inject) { const float4 t4 = ld4(er + 4 * jb); e4[0] = t4.x; e4[1] = t4.y; e4[2] = t4.z; e4[3] = t4.w; }
+            else { const float4 t4 = philox_normal4(kglob, (unsigned)n, (unsigned)jb, prm.offset, prm.seed);
+                   e4[0] = t4.x; e4[1] = t4.y; e4[2] = t4.z; e4[3] = t4.w; }
+          }
+          float o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 4 * jb + i;
+            o4[i] = 0.f;
+            if (j < d) {
+              float lb;
+              if (!dense) lb = lr[j] * b_d[j];
+              else { lb = 0.f; for (int q = 0; q < d; ++q) lb = fmaf(lr[q], __ldg(Bm + q * d + j), lb); }
+              const float z = zr[j];
+              o4[i] = wy * (sq * e4[i] - dt * z) + wz * dt * z - dt * lb;
+            }
+          }
+          st4(er + 4 * jb, make_float4(o4[0], o4[1], o4[2], o4[3]));
         }
       }
       __syncthreads();

@@ -45,8 +45,8 @@ PROTOTYPES = {
     "pspde_workspace_bytes": (ctypes.c_size_t, [_CFG]),
     "pspde_rollout_fwd": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_rollout_bwd_detached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
-    "pspde_rollout_attached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P,
-                                              ctypes.c_size_t, _P]),
+    "pspde_rollout_attached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P,
+                                              _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_philox_dump": (ctypes.c_int, [_CFG, _P, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
     "pspde_fma_probe_ex": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, _P, _P]),

@@ -106,11 +106,13 @@ class RolloutEngine:
                                                  self._stream())
         L.check(self.lib, rc)
 
-    def attached(self, theta, call, grad_out):
+    def attached(self, theta, call, grad_out, y0=None, wY=None, wZ=None, wG=None):
+        """wY = wZ = wG = None: relative entropy in one launch (constant cotangents 1 / K_global)."""
         cfg = self.cfg(call)
         rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
-                                             self._xi_ptr(call), ctypes.c_float(1.0 / self.K_global),
-                                             self._p(self.X_N), self._p(self.gX), self._p(self.Zsum),
+                                             self._p(y0), self._xi_ptr(call), ctypes.c_float(1.0 / self.K_global),
+                                             self._p(wY), self._p(wZ), self._p(wG), self._p(self.X_N),
+                                             self._p(self.Y_N), self._p(self.gX), self._p(self.Zsum),
                                              self._p(self.stats), self._p(grad_out), self._p(self.workspace),
                                              self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
@@ -168,3 +170,32 @@ class FusedRolloutAttached(pt.autograd.Function):
     def backward(ctx, gout):
         (grad,) = ctx.saved_tensors
         return grad * gout, None, None
+
+
+class FusedRolloutAttachedGeneral(pt.autograd.Function):
+    """(theta, y0) -> per-path (Y_N, g(X_N), Z_sum) for the ATTACHED adaptive forward process (detach_forward=False).
+    Two-phase: forward = forward rollout kernel; backward = checkpointed adjoint kernel driven by the per-path
+    cotangents (dL/dY_N, dL/dg(X_N), dL/dZsum) -- any loss of solver.py:164-192."""
+
+    @staticmethod
+    def forward(ctx, theta, y0, engine, call):
+        theta_c = theta.detach().contiguous()
+        y0_c = None if y0 is None else y0.detach().contiguous()
+        engine.forward(theta_c, y0_c, call)
+        call.X_N, call.stats = engine.X_N, engine.stats
+        ctx.engine, ctx.call, ctx.has_y0, ctx.y0 = engine, call, y0 is not None, y0_c
+        ctx.save_for_backward(theta_c)
+        return engine.Y_N.clone(), engine.gX.clone(), engine.Zsum.clone()
+
+    @staticmethod
+    def backward(ctx, gY, ggX, gZsum):
+        (theta_c,) = ctx.saved_tensors
+        engine = ctx.engine
+        c = lambda t: None if t is None else t.contiguous().float()
+        wY, wG, wZ = c(gY), c(ggX), c(gZsum)
+        if wY is None and wG is None and wZ is None:
+            wY = pt.zeros(engine.K_local, dtype=pt.float32, device=engine.device)
+        grad = pt.empty(engine.n_theta, dtype=pt.float32, device=engine.device)
+        engine.attached(theta_c, ctx.call, grad, y0=ctx.y0, wY=wY, wZ=wZ, wG=wG)
+        gy0 = (wY.sum().reshape(1) if wY is not None else pt.zeros(1, device=engine.device)) if ctx.has_y0 else None
+        return grad, gy0, None, None

@@ -22,7 +22,7 @@ import torch as pt
 from . import _lib as L
 from . import dist, losses
 from .function_space import DenseNet, MySequential, SingleParam
-from .fused import Call, FusedRollout, FusedRolloutAttached, RolloutEngine
+from .fused import Call, FusedRollout, FusedRolloutAttached, FusedRolloutAttachedGeneral, RolloutEngine
 
 
 class Solver:
@@ -178,10 +178,6 @@ class Solver:
                 unsupported.append('compute_gradient_variance')
             if self.loss_method not in losses.SUPPORTED:
                 unsupported.append('loss_method=%r' % self.loss_method)
-            if not self.detach_forward and self.loss_method != 'relative_entropy':
-                unsupported.append('detach_forward=False with loss_method=%r' % self.loss_method)
-            if not self.detach_forward and self.learn_Y_0:
-                unsupported.append('learn_Y_0 with detach_forward=False')
             if unsupported:
                 raise NotImplementedError("off the fused hot path: " + ", ".join(unsupported))
             rank, W = dist.world(self.process_group)
@@ -214,23 +210,25 @@ class Solver:
         eng = self._get_engine()
         self.zero_grad()
         self._ensure_grad_views()
-        if self.detach_forward:
-            y0 = self.y_0.Y_0 if self.learn_Y_0 else None
-            Y, gX, Zsum = FusedRollout.apply(self._theta, y0, eng, call)
-            loss, wY, wZ, n_bad = losses.value_and_cotangents(self.loss_method, Y.detach(), gX, Zsum.detach(),
-                                                              self.K, self.adaptive_forward_process,
-                                                              self.process_group, stats=call.stats)
-            outs, cots = [], []
-            if wY is not None:
-                outs.append(Y); cots.append(wY)
-            if wZ is not None:
-                outs.append(Zsum); cots.append(wZ)
-            pt.autograd.backward(outs, cots)
-        else:
-            loss_local = FusedRolloutAttached.apply(self._theta, eng, call)
+        # X depends on theta only through an attached adaptive control (solver.py:451-469)
+        attached = (not self.detach_forward) and self.adaptive_forward_process
+        y0 = self.y_0.Y_0 if self.learn_Y_0 else None
+        if attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0:
+            loss_local = FusedRolloutAttached.apply(self._theta, eng, call)       # constant cotangents: one launch
             loss_local.backward()
             loss = dist.all_reduce_sum_(loss_local.detach().double().reshape(1), self.process_group)[0]
             n_bad = dist.all_reduce_sum_(call.stats[3:4].clone(), self.process_group)[0]
+        else:
+            fn = FusedRolloutAttachedGeneral if attached else FusedRollout
+            Y, gX, Zsum = fn.apply(self._theta, y0, eng, call)
+            loss, wY, wZ, wG, n_bad = losses.value_and_cotangents(self.loss_method, Y.detach(), gX.detach(),
+                                                                  Zsum.detach(), self.K, self.adaptive_forward_process,
+                                                                  self.process_group, stats=call.stats)
+            outs, cots = [], []
+            for o, w in ((Y, wY), (Zsum, wZ)) + (((gX, wG),) if attached else ()):
+                if w is not None:
+                    outs.append(o); cots.append(w)
+            pt.autograd.backward(outs, cots)
         self._ensure_grad_views()
         dist.all_reduce_sum_(self._theta.grad, self.process_group)
         if self.learn_Y_0 and self.y_0.Y_0.grad is not None:

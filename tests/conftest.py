@@ -37,7 +37,8 @@ def relerr(a, b):
 HJB_TAGS = ["hjb_llgc_d100_dense_lv", "hjb_lqgc_d10_dense_lv", "hjb_lqgc_d10_outer_lv", "hjb_dwm_d50_mlp_lv",
             "hjb_dwm_d50_mlp_re", "hjb_llgc_d10_dense_re", "hjb_lqgc_d10_dense_re", "hjb_llgc_d10_moment_y0",
             "hjb_llgc_d10_nonadaptive_lv", "hjb_llgc_d10_offdiag_lv", "hjb_llgc_d10_crossent",
-            "hjb_llgc_d10_variance", "hjb_llgc_d1_mlp_lv"]
+            "hjb_llgc_d10_variance", "hjb_llgc_d1_mlp_lv", "hjb_lqgc_d10_dense_lv_att", "hjb_dwm_d50_mlp_lv_att",
+            "hjb_llgc_d10_offdiag_moment_att", "hjb_lqgc_d10_outer_ce_att"]
 
 
 @pytest.fixture

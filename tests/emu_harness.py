@@ -100,15 +100,19 @@ class Runner:
         L.check(self.lib, rc)
         return grad
 
-    def attached(self, cfg, theta, pack, x0, w, xi=None):
+    def attached(self, cfg, theta, pack, x0, w, xi=None, y0=None, wY=None, wZ=None, wG=None):
         K, d = cfg.K_local, cfg.d
         ws = np.zeros(self.lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 1, np.float64)
-        out = dict(X=np.zeros((K, d), np.float32), gX=np.zeros(K, np.float32), Zsum=np.zeros(K, np.float32),
-                   stats=np.zeros(4, np.float64),
+        out = dict(X=np.zeros((K, d), np.float32), Y=np.zeros(K, np.float32), gX=np.zeros(K, np.float32),
+                   Zsum=np.zeros(K, np.float32), stats=np.zeros(4, np.float64),
                    grad=np.full(self.lib.pspde_theta_size(ctypes.byref(cfg)), np.nan, np.float32))
         xi_p = None if xi is None else ctypes.c_void_p(xi.ctypes.data + 4)
-        rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), ptr(theta), ptr(pack), ptr(x0), xi_p,
-                                             ctypes.c_float(w), ptr(out["X"]), ptr(out["gX"]), ptr(out["Zsum"]),
-                                             ptr(out["stats"]), ptr(out["grad"]), ptr(ws), ws.nbytes, None)
+        y0a = None if y0 is None else np.array([y0], np.float32)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        wY, wZ, wG = f(wY), f(wZ), f(wG)
+        rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), ptr(theta), ptr(pack), ptr(x0), ptr(y0a), xi_p,
+                                             ctypes.c_float(w), ptr(wY), ptr(wZ), ptr(wG), ptr(out["X"]),
+                                             ptr(out["Y"]), ptr(out["gX"]), ptr(out["Zsum"]), ptr(out["stats"]),
+                                             ptr(out["grad"]), ptr(ws), ws.nbytes, None)
         L.check(self.lib, rc)
         return out

@@ -195,6 +195,12 @@ def run_loss_log_case(tag, build, L):
 
 
 def main():
+    only = sys.argv[1:]
+    global run_hjb_case
+    if only:
+        _orig = run_hjb_case
+        def run_hjb_case(tag, *a, **k):
+            if tag in only: _orig(tag, *a, **k)
     # --- single-iteration, injected-noise fixtures (xi stored in the file)
     run_hjb_case("hjb_llgc_d100_dense_lv", "llgc", 100, dict(T=0.2), 16, 0.01, "densenet", "inner",
                  "log-variance", True)                                   # C2/C5 shape (N=20)
@@ -222,6 +228,17 @@ def main():
                  "variance", True)
     run_hjb_case("hjb_llgc_d1_mlp_lv", "llgc", 1, dict(T=0.5), 40, 0.05, "mlp_tanh", "inner",
                  "log-variance", True)                                   # edge: d=1, ragged K
+    # attached forward process (the reference's constructor defaults: detach_forward=False, log-variance)
+    run_hjb_case("hjb_lqgc_d10_dense_lv_att", "lqgc", 10, dict(T=0.5), 32, 0.05, "densenet", "inner",
+                 "log-variance", False)
+    run_hjb_case("hjb_dwm_d50_mlp_lv_att", "dwm", 50, dict(d_1=15, d_2=35, T=0.1, eta=3, kappa=5), 16, 0.005,
+                 "mlp_tanh", "inner", "log-variance", False, lr=0.05)
+    run_hjb_case("hjb_llgc_d10_offdiag_moment_att", "llgc", 10, dict(T=0.5, off_diag=0.1), 32, 0.05, "densenet",
+                 "inner", "moment", False)
+    run_hjb_case("hjb_lqgc_d10_outer_ce_att", "lqgc", 10, dict(T=0.5), 32, 0.05, "densenet", "outer",
+                 "cross_entropy", False)
+    if only:
+        return
     run_diffusion_case("diff_heat_d10_small", 10, 64, 50, 25, 1e-3, (24, 24), full=True)
     run_diffusion_case("diff_heat_d50_w256", 50, 256, 50, 25, 1e-3, (256, 256), full=False)   # C4 / G4
     run_is_case("is_llgc_d10_dense", "llgc", 10, dict(T=0.5), 64, 0.05, 0.01, "densenet")

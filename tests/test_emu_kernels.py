@@ -45,11 +45,20 @@ def test_golden_parity(run, tag):
         assert relerr(grad, g["grad"]) < 1e-5
         if g["learn_Y_0"]:
             assert abs(wY.sum() - g["grad_y0"]) < 1e-4 * abs(g["grad_y0"])
-    else:
+    elif g["loss_method"] == "relative_entropy":
         o = run.attached(cfg, theta, pack, x0, 1.0 / K, xi)
         assert relerr(o["X"], g["X_N"]) < 1e-5 and relerr(o["Zsum"], g["Zsum"]) < 1e-5
         assert abs(o["stats"][2] / K - g["loss"]) < 1e-5 * abs(g["loss"])
         assert relerr(o["grad"], g["grad"]) < 1e-5
+    else:   # attached forward process, general loss: forward launch -> cotangents -> adjoint launch
+        f = run.fwd(cfg, theta, pack, x0, xi)
+        assert relerr(f["X"], g["X_N"]) < 1e-5 and relerr(f["Y"], g["Y_N"]) < 1e-5
+        loss, wY, wZ, wG = man.loss_cotangents_full(g["loss_method"], f["Y"].astype(np.float64),
+                                                    f["gX"].astype(np.float64), f["Zsum"].astype(np.float64), True)
+        assert abs(loss - g["loss"]) <= 1e-5 * abs(g["loss"]) + 4 * 6e-8 * float(((f["Y"] - f["gX"]).astype(np.float64) ** 2).mean())
+        o = run.attached(cfg, theta, pack, x0, 0.0, xi, wY=wY, wZ=wZ, wG=wG)
+        assert relerr(o["Y"], f["Y"]) < 1e-6 and relerr(o["X"], f["X"]) < 1e-6
+        assert relerr(o["grad"], g["grad"]) < 2e-5
 
 
 @pytest.mark.parametrize("order", ["reverse", "random"])

@@ -217,8 +217,11 @@ def test_no_cpu_fallback_and_error_reporting():
     import pspde
     from pspde import _lib
     prob = pspde.LLGC(d=4, T=0.5, device="cuda")
-    S = pspde.Solver("e", prob, K=8, delta_t=0.05, time_approx="inner", verbose=False)     # attached log-variance
+    S = pspde.Solver("e", prob, K=8, delta_t=0.05, time_approx="inner", verbose=False, burgers_drift=True)
     with pytest.raises(NotImplementedError):
         S.train()
+    S = pspde.Solver("e", prob, K=8, L=2, delta_t=0.05, time_approx="inner", verbose=False)   # reference defaults:
+    S.train()                                                                                # attached log-variance
+    assert len(S.loss_log) == 2 and all(np.isfinite(S.loss_log))
     lib = _lib.load()
     assert lib.pspde_abi_version() == _lib.ABI_VERSION

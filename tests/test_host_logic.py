@@ -86,8 +86,10 @@ def test_loss_cotangents_match_oracle(method):
     Y, gX, Zs = rng.standard_normal(K), rng.standard_normal(K), rng.random(K)
     lv, wY, wZ = man.loss_and_weights(method, Y, gX, Zs, True)
     t = lambda a: pt.tensor(a, dtype=pt.float32)
-    loss, a, b, n_bad = losses.value_and_cotangents(method, t(Y), t(gX), t(Zs), K, True)
+    loss, a, b, c, n_bad = losses.value_and_cotangents(method, t(Y), t(gX), t(Zs), K, True)
     assert n_bad.item() == 0
+    _, _, _, wG = man.loss_cotangents_full(method, Y, gX, Zs, True)
+    assert relerr(c.numpy(), wG) < 1e-5
     assert abs(loss.item() - lv) < 1e-5 * max(1, abs(lv))
     if a is not None:
         assert relerr(a.numpy(), wY) < 1e-5
@@ -107,7 +109,7 @@ def test_nonfinite_trajectories_are_dropped_and_counted():
     t = lambda a: pt.tensor(a, dtype=pt.float32)
     for m in ("log-variance", "moment", "variance", "cross_entropy", "relative_entropy"):
         lv, wY, wZ = man.loss_and_weights(m, Y[keep], gX[keep], Zs[keep], True)
-        loss, a, b, n_bad = losses.value_and_cotangents(m, t(Yb), t(gX), t(Zs), K, True)
+        loss, a, b, c, n_bad = losses.value_and_cotangents(m, t(Yb), t(gX), t(Zs), K, True)
         assert n_bad.item() == 2 and abs(loss.item() - lv) < 1e-5 * max(1, abs(lv))
         for w, ref in ((a, wY), (b, wZ)):
             if w is not None:
@@ -163,7 +165,7 @@ lo, hi = shard_range(K, rank, W)
 ok = True
 for m in ("log-variance", "moment", "variance", "cross_entropy", "relative_entropy"):
     full = losses.value_and_cotangents.__wrapped__(m, Y, gX, Zs, K) if hasattr(losses.value_and_cotangents, "__wrapped__") else None
-    loss, wY, wZ, n_bad = losses.value_and_cotangents(m, Y[lo:hi], gX[lo:hi], Zs[lo:hi], K)
+    loss, wY, wZ, wG, n_bad = losses.value_and_cotangents(m, Y[lo:hi], gX[lo:hi], Zs[lo:hi], K)
     # single-process reference computed without any process group semantics: emulate by gathering
     parts = [None, None]
     td.all_gather_object(parts, (None if wY is None else wY.numpy(), None if wZ is None else wZ.numpy(), loss.item()))
