@@ -72,7 +72,7 @@ typedef struct pspde_cfg {
   int32_t x0_per_path;  /* 0: x0 is one row of d floats (X_0.repeat, :365); 1: K_local x d rows    */
   uint64_t seed;        /* Philox key                                                              */
   uint32_t offset;      /* Philox stream id: the training-iteration counter                       */
-  int32_t  reserved;
+  int32_t  n_sets;      /* TIME_NONE: number of stacked parameter sets in theta (0 = N)            */
   /* INJECT: element (k, j, step n) is read at xi[k*xi_stride_k + j*xi_stride_j + n*xi_stride_n], n = 0..N-1
    * being the increment that drives step n.  Reference layout (K, d, N+1) with slice n+1 driving step n
    * (solver.py:472): pass xi + 1 and strides (d*(N+1), N+1, 1). */
@@ -100,6 +100,25 @@ int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* pro
                       const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
                       double* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* u_L2 diagnostic of solver.py:491-494, u_L2 += sum_j (-Z_j - u*_j(X_{n+1}, n*delta_t))^2 dt, evaluated in the
+ * forward kernel from per-step device tables instead of the reference's per-step D2H / scipy / H2D round trip:
+ *   mode 1  u*_j = U0[n][j] + U1[n][j] * x_j          table fp32 [N][2][d]   (LLGC problems.py:51-53: U1 = 0;
+ *                                                      LQGC :169-171 with diagonal Q^-1 B' F_n: U0 = 0)
+ *   mode 2  u*_j = tab[n][j < d1 ? 0 : 1][cell(x_j)]  table fp32 [N][2][nx1], cell = floor((clip(x, -xb, xb - 2dx) + xb) / dx)
+ *                                                      (DoubleWell(_multidim) finite-difference tables, :398-404, :463-476) */
+typedef struct pspde_udiag {
+  int32_t mode;          /* 0 off */
+  int32_t nx1, d1;       /* mode 2 */
+  float   xb, dx;        /* mode 2 */
+  const float* table;    /* device */
+  float*  uL2;           /* device, K_local per-path results */
+} pspde_udiag;
+
+int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                           const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
+                           double* stats, const pspde_udiag* diag, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* Backward for detach_forward=True (solver.py:468-469 + loss.backward at :221).  The trajectories do not
  * depend on theta, so dLoss/dtheta = sum_{k,n} J_theta Z(t_n, X_{k,n})' zeta_{k,n} with
  *   zeta = wY_k (sqrt(dt) xi_{n+1} + [adaptive == 0] Z dt) + wZ_k Z dt,
@@ -121,6 +140,17 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
                            const float* y0, const float* xi, float w, const float* wY, const float* wZ,
                            const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                            float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Importance-sampling evaluation -- replaces the rollout of do_importance_sampling_me (utilities.py:287-359,
+ * called from solver.py:521-528): forward-only simulation of the controlled process u = -Z on a time grid that
+ * may differ from the training grid.  t_index[n] (device, length N, nullable) is the network's time index for
+ * step n, n_net = ceil(n*dt / dt_net) as in Solver.Z_n (solver.py:360-362); the network sees t = n_net * dt_net
+ * ('inner') or parameter set clamp(n_net) ('outer').  Per path: Y_N (the adaptive Y of pspde_rollout_fwd),
+ * gX = g(X_N), Fint = sum_n f(X_{n+1}) dt; the log of the Girsanov-weighted integrand of utilities.py:329-335 is
+ *   log w = -Fint - g(X_N) - ito - riemann/2 = Y_N - 2 Fint - g(X_N). */
+int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                              const float* xi, const int32_t* t_index, float dt_net, float* X_N, float* Y_N,
+                              float* gX, float* Fint, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Test hook: writes the increments the kernels would generate for cfg (Philox mode) in the layout
  * (N, K_local, d), i.e. strides (d, 1, K_local*d). */

@@ -111,7 +111,7 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
   if (rc) return rc;
   rc = build_geom(pl.g, c->net_id, c->n_layers, c->dims, c->time_mode, c->d);
   if (rc) return fail(-3, "network geometry rejected (code %d): dims[0] must be d%s", rc, c->time_mode == PSPDE_TIME_NONE ? "" : "+1");
-  pl.n_sets = (c->time_mode == PSPDE_TIME_NONE) ? c->N : 1;
+  pl.n_sets = (c->time_mode == PSPDE_TIME_NONE) ? (c->n_sets > 0 ? c->n_sets : c->N) : 1;
   pl.n_theta_total = pl.g.n_params * pl.n_sets;
   pl.n_tiles = (c->K_local + kP - 1) / kP;
   const int sms = pspde_sm_count();
@@ -149,6 +149,7 @@ static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams
   p.n_tiles = pl.n_tiles; p.n_theta_total = pl.n_theta_total;
   for (int l = 0; l < PSPDE_MAXL; ++l) p.r_fwd[l] = pl.r_fwd[l];
   p.prof = g_prof;
+  p.n_sets = pl.n_sets;
 }
 
 template <int T, bool BWD, int NB>

@@ -16,7 +16,7 @@ int64_t pspde_theta_size(const pspde_cfg* cfg) {
   if (validate(cfg)) return -1;
   NetGeom g;
   if (build_geom(g, cfg->net_id, cfg->n_layers, cfg->dims, cfg->time_mode, cfg->d)) { fail(-3, "bad network geometry"); return -1; }
-  return (int64_t)g.n_params * (cfg->time_mode == PSPDE_TIME_NONE ? cfg->N : 1);
+  return (int64_t)g.n_params * (cfg->time_mode == PSPDE_TIME_NONE ? (cfg->n_sets > 0 ? cfg->n_sets : cfg->N) : 1);
 }
 
 size_t pspde_workspace_bytes(const pspde_cfg* cfg) {
@@ -33,6 +33,14 @@ size_t pspde_workspace_bytes(const pspde_cfg* cfg) {
 int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0, const float* y0,
                       const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                       void* workspace, size_t workspace_bytes, void* stream) {
+  return pspde_rollout_fwd_diag(cfg, theta, prob, x0, y0, xi, X_N, Y_N, gX, Zsum, stats, nullptr, workspace,
+                                workspace_bytes, stream);
+}
+
+int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                           const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
+                           double* stats, const pspde_udiag* diag, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   Plan pl;
   int rc = make_plan(cfg, false, false, pl);
   if (rc) return rc;
@@ -43,6 +51,13 @@ int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* pro
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi;
   p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Zsum = Zsum;
+  if (diag && diag->mode != 0) {
+    if (diag->mode < 0 || diag->mode > 2 || !diag->table || !diag->uL2) return fail(-8, "bad u_L2 diagnostic descriptor");
+    if (diag->mode == 2 && (diag->nx1 < 1 || !(diag->dx > 0.f))) return fail(-8, "bad lookup-table geometry");
+    if (diag->mode == 2 && (cfg->problem_flags & PSPDE_FLAG_DENSE_AB)) return fail(-8, "lookup diagnostic needs a diagonal problem");
+    p.u_mode = diag->mode; p.u_tab = diag->table; p.u_nx1 = diag->nx1; p.u_d1 = diag->d1;
+    p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
+  }
   p.stats_partial = reinterpret_cast<double*>(workspace);
   rc = launch_rollout<512, false, 1>(pl, p, stream);
   if (rc) return rc;
@@ -116,6 +131,26 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
   g_launches++;
   if (const char* e = pspde_peek_error()) return fail(-12, "reduce launch failed: %s", e);
   return 0;
+}
+
+int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                              const float* xi, const int32_t* t_index, float dt_net, float* X_N, float* Y_N,
+                              float* gX, float* Fint, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, false, false, pl);
+  if (rc) return rc;
+  if (!cfg->adaptive) return fail(-4, "importance sampling simulates the CONTROLLED process (adaptive = 1)");
+  if (!theta || !prob || !x0 || !Y_N || !gX || !Fint) return fail(-1, "theta/prob/x0/Y_N/gX/Fint must not be NULL");
+  if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
+  if (t_index && !(dt_net > 0.f)) return fail(-2, "dt_net must be > 0 when t_index is given");
+  if (!workspace || workspace_bytes < pl.stats_bytes) return fail(-7, "workspace too small");
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi;
+  p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Fint = Fint;
+  p.t_index = t_index; p.dt_net = dt_net;
+  p.stats_partial = reinterpret_cast<double*>(workspace);
+  return launch_rollout<512, false, 1>(pl, p, stream);
 }
 
 int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream) {

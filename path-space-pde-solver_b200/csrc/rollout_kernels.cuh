@@ -35,7 +35,16 @@ struct RolloutParams {
   int r_fwd[PSPDE_MAXL];  // paths per thread tile in gemm_nn, per layer (1, 2, 4 or 8)
   float w_attached;    // attached mode without per-path cotangents: wZ = wG = w_attached, wY = 0 (relative entropy)
   const float *theta, *prob, *x0, *y0, *xi, *wY, *wZ, *wG;
-  float *X_N, *Y_N, *gX, *Zsum;
+  float *X_N, *Y_N, *gX, *Zsum, *Fint;   // Fint (nullable): per-path sum_n f(X_{n+1}) dt
+  const int* t_index;  // nullable: network time index of step n (importance sampling on a different grid)
+  float dt_net;        // time-grid spacing of the network when t_index is given
+  int n_sets;          // TIME_NONE: number of stacked parameter sets
+  // u_L2 diagnostic (solver.py:491-494): u*(x, t_n) from per-step device tables, see include/pspde.h
+  int u_mode;          // 0 off, 1 affine u* = U0[n][j] + U1[n][j] x_j, 2 lookup u* = tab[n][class(j)][cell(x_j)]
+  const float* u_tab;
+  int u_nx1, u_d1;
+  float u_xb, u_dx;
+  float* uL2;          // per-path output
   double* stats_partial;  // [gridDim.x][4]
   float* grad_partial;    // [gridDim.x][n_theta_total]
   float* x_ckpt;          // attached mode: [gridDim.x][N][P][d] state checkpoints of the current tile
@@ -397,7 +406,7 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
     // activations remain finite and every product it adds to the weight gradient is exactly 0.
     const bool inert = BWD && wy == 0.f && wz == 0.f;
     const unsigned kglob = (unsigned)(prm.k_offset + tile * P + p);
-    float zz = 0.f, zxi = 0.f, ff = 0.f, gg = 0.f;
+    float zz = 0.f, zxi = 0.f, ff = 0.f, gg = 0.f, ul = 0.f;
     if (!dense) {
       for (int jb = lane; jb < ngrp; jb += 32) {
         const int j0 = 4 * jb;
@@ -424,6 +433,19 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
           xn[i] = x + (drift + bv[i] * c) * dt + (bv[i] * e) * sq;
           ff = fmaf(pv[i] * xn[i], xn[i], ff);
           ze[i] = wy * (sq * e + kA * dt * z) + wz * dt * z;
+          if (!BWD && prm.u_mode != 0 && !padc) {           // (-Z - u*(X_{n+1}, t_n))^2, solver.py:492-493
+            const int j = j0 + i;
+            float us;
+            if (prm.u_mode == 1) us = __ldg(prm.u_tab + (size_t)(2 * n) * d + j) + __ldg(prm.u_tab + (size_t)(2 * n + 1) * d + j) * xn[i];
+            else {
+              const float xc = fminf(fmaxf(xn[i], -prm.u_xb), prm.u_xb - 2.0f * prm.u_dx);
+              int cell = (int)floorf((xc + prm.u_xb) / prm.u_dx);
+              cell = cell < 0 ? 0 : (cell >= prm.u_nx1 ? prm.u_nx1 - 1 : cell);
+              us = __ldg(prm.u_tab + ((size_t)(2 * n) + (j < prm.u_d1 ? 0 : 1)) * prm.u_nx1 + cell);
+            }
+            const float du = -z - us;
+            ul = fmaf(du, du, ul);
+          }
         }
         if (last) {
           const float4 L4 = ld4(al + j0), R4 = ld4(r_d + j0), E4 = ld4(eta + j0);
@@ -475,6 +497,10 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
           ze_loc[q] = wy * (sq * e + kA * dt * z) + wz * dt * z;
           ff = fmaf(p_d[i] * xn, xn, ff);
           if (last) gg += al[i] * xn + r_d[i] * xn * xn + eta[i] * (xn - 1.0f) * (xn - 1.0f);
+          if (!BWD && prm.u_mode == 1) {
+            const float du = -z - (__ldg(prm.u_tab + (size_t)(2 * n) * d + i) + __ldg(prm.u_tab + (size_t)(2 * n + 1) * d + i) * xn);
+            ul = fmaf(du, du, ul);
+          }
         }
       }
       __syncwarp();
@@ -491,10 +517,12 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
     }
     zz = warp_sum(zz); zxi = warp_sum(zxi); ff = warp_sum(ff);
     if (last) gg = warp_sum(gg);
+    if (!BWD && prm.u_mode != 0) { ul = warp_sum(ul); if (lane == 0) sY[7 * P + p] += ul * dt; }
     if (lane == 0) {
       const float run = 0.5f * zz + ff;
       sY[p] += (run + (adaptive ? -zz : 0.f)) * dt + zxi * sq;
       sZs[p] += run * dt;
+      sY[6 * P + p] += ff * dt;              // running cost alone (importance-sampling weights)
       if (last) sG[p] = gg;
     }
   }
@@ -661,7 +689,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
       sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f;
-      sZs[p] = 0.f; sG[p] = 0.f;
+      sZs[p] = 0.f; sG[p] = 0.f; sY[6 * P + p] = 0.f; sY[7 * P + p] = 0.f;
       const bool ok = BWD && k < prm.K_local;
       swY[p] = (ok && prm.wY) ? __ldg(prm.wY + k) : 0.f;
       swZ[p] = (ok && prm.wZ) ? __ldg(prm.wZ + k) : 0.f;
@@ -673,10 +701,15 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
     for (int n = 0; n < N; ++n) {
       // time column: in BWD the float4 copy-back of X_{n+1} at the end of the previous step also covers the t column
       // when d % 4 != 0; it then writes t_{n+1} itself (same thread, no race with this loop)
+      const int n_net = prm.t_index ? __ldg(prm.t_index + n) : n;          // Z_n(X, t): n = ceil(t / delta_t), :360-362
+      const float t_net = prm.t_index ? (float)n_net * prm.dt_net : (float)n * prm.dt;
       if (g.t_col >= 0 && (!BWD || n == 0 || g.t_col >= d4))
-        for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * prm.dt;
+        for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = t_net;
       if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
-      if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
+      if (outer) {
+        const int set = n_net < 0 ? 0 : (n_net >= prm.n_sets ? prm.n_sets - 1 : n_net);   // clamp like :352
+        stage_weights(g, prm.theta + (size_t)set * g.n_params, smem + sl.w, tid, T);
+      }
       __syncthreads();
       pt_.mark(0);
       net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, warp, lane, NW);
@@ -711,6 +744,8 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
           if (prm.Y_N) prm.Y_N[k] = Y;
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
+          if (prm.Fint) prm.Fint[k] = sY[6 * P + tid];
+          if (prm.uL2) prm.uL2[k] = sY[7 * P + tid];
           const double D = (double)Y - (double)G;
           if (isfinite(D) && isfinite((double)ZS)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)G; }
           else s3 = 1.0;
@@ -795,7 +830,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     tile_init_state(prm, sAct, tile, P, false, tid, T);
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
-      sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f; sZs[p] = 0.f; sG[p] = 0.f;
+      sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f; sZs[p] = 0.f; sG[p] = 0.f; sY[6 * P + p] = 0.f;
       const bool in = k < prm.K_local;
       if (per_path) {
         swY[p] = (in && prm.wY) ? __ldg(prm.wY + k) : 0.f;

@@ -28,9 +28,14 @@ class pspde_cfg(ctypes.Structure):
         ("dims", ctypes.c_int32 * (PSPDE_MAX_LAYERS + 1)),
         ("time_mode", ctypes.c_int32), ("adaptive", ctypes.c_int32), ("noise_mode", ctypes.c_int32),
         ("x0_per_path", ctypes.c_int32),
-        ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint32), ("reserved", ctypes.c_int32),
+        ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint32), ("n_sets", ctypes.c_int32),
         ("xi_stride_k", ctypes.c_int64), ("xi_stride_j", ctypes.c_int64), ("xi_stride_n", ctypes.c_int64),
     ]
+
+
+class pspde_udiag(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("nx1", ctypes.c_int32), ("d1", ctypes.c_int32), ("xb", ctypes.c_float),
+                ("dx", ctypes.c_float), ("table", ctypes.c_void_p), ("uL2", ctypes.c_void_p)]
 
 
 _P = ctypes.c_void_p
@@ -44,9 +49,13 @@ PROTOTYPES = {
     "pspde_theta_size": (ctypes.c_int64, [_CFG]),
     "pspde_workspace_bytes": (ctypes.c_size_t, [_CFG]),
     "pspde_rollout_fwd": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "pspde_rollout_fwd_diag": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(pspde_udiag),
+                                              _P, ctypes.c_size_t, _P]),
     "pspde_rollout_bwd_detached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_rollout_attached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, ctypes.c_size_t, _P]),
+    "pspde_importance_sampling": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P,
+                                                 ctypes.c_size_t, _P]),
     "pspde_philox_dump": (ctypes.c_int, [_CFG, _P, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
     "pspde_fma_probe_ex": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, _P, _P]),
@@ -87,7 +96,7 @@ def check(lib, rc):
 
 
 def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=True, k_offset=0, problem_flags=0,
-             noise_mode=NOISE_PHILOX, seed=0, offset=0, x0_per_path=False, xi_strides=(0, 0, 0)):
+             noise_mode=NOISE_PHILOX, seed=0, offset=0, x0_per_path=False, xi_strides=(0, 0, 0), n_sets=0):
     c = pspde_cfg()
     c.K_local, c.k_offset, c.d, c.N = int(K_local), int(k_offset), int(d), int(N)
     c.dt = float(dt)
@@ -100,5 +109,6 @@ def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=Tr
     c.time_mode, c.adaptive, c.noise_mode = int(time_mode), int(bool(adaptive)), int(noise_mode)
     c.x0_per_path = int(bool(x0_per_path))
     c.seed, c.offset = int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 32 - 1)
+    c.n_sets = int(n_sets)
     c.xi_stride_k, c.xi_stride_j, c.xi_stride_n = (int(s) for s in xi_strides)
     return c

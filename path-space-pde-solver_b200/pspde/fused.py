@@ -60,6 +60,7 @@ class RolloutEngine:
         if nbytes == 0:
             raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
         self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
+        self.udiag, self.uL2 = None, None
 
     def set_x0(self, x0):
         """(d,) broadcast start or (K_local, d) per-path starts (random_X_0, solver.py:366-367)."""
@@ -90,12 +91,23 @@ class RolloutEngine:
     def _stream(self):
         return ctypes.c_void_p(pt.cuda.current_stream(self.device).cuda_stream)
 
+    def enable_u_l2(self, desc):
+        """desc = problem.u_true_table(N, delta_t): switches on the u_L2 diagnostic of solver.py:491-494."""
+        self._utab = desc["table"].to(self.device, pt.float32).contiguous()
+        self.uL2 = pt.zeros(self.K_local, dtype=pt.float32, device=self.device)
+        u = L.pspde_udiag()
+        u.mode, u.nx1, u.d1 = int(desc["mode"]), int(desc.get("nx1", 0)), int(desc.get("d1", 0))
+        u.xb, u.dx = float(desc.get("xb", 0.0)), float(desc.get("dx", 0.0))
+        u.table, u.uL2 = self._utab.data_ptr(), self.uL2.data_ptr()
+        self.udiag = u
+
     def forward(self, theta, y0, call):
         cfg = self.cfg(call)
-        rc = self.lib.pspde_rollout_fwd(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
-                                        self._p(y0), self._xi_ptr(call), self._p(self.X_N), self._p(self.Y_N),
-                                        self._p(self.gX), self._p(self.Zsum), self._p(self.stats),
-                                        self._p(self.workspace), self.workspace.numel(), self._stream())
+        diag = None if self.udiag is None else ctypes.byref(self.udiag)
+        rc = self.lib.pspde_rollout_fwd_diag(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+                                             self._p(y0), self._xi_ptr(call), self._p(self.X_N), self._p(self.Y_N),
+                                             self._p(self.gX), self._p(self.Zsum), self._p(self.stats), diag,
+                                             self._p(self.workspace), self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
     def backward_detached(self, theta, wY, wZ, call, grad_out):

@@ -96,6 +96,16 @@ class LLGC(_OrnsteinUhlenbeck):
         z = pt.zeros(self.d)
         return self._pack(z, z, self.alpha.cpu().reshape(-1))
 
+    def u_true_table(self, N, delta_t):
+        """Device-table form of u_true on the solver grid t_n = n * delta_t (include/pspde.h, pspde_udiag mode 1):
+        u*(x, t_n) = U0[n] (independent of x).  Returns dict(mode, table (N, 2, d))."""
+        A, B = self.A.cpu().numpy().astype(np.float64), self.B.cpu().numpy().astype(np.float64)
+        al = self.alpha.cpu().numpy().astype(np.float64)
+        tab = np.zeros((N, 2, self.d), np.float32)
+        for n in range(N):
+            tab[n, 0] = (-B.T @ (expm(A.T * (self.T - n * delta_t)) @ al))[:, 0]
+        return dict(mode=1, table=pt.from_numpy(tab))
+
 
 class LQGC(_OrnsteinUhlenbeck):
     """Linear-quadratic Gaussian control: running cost x'Px, terminal cost x'Rx (P = Q = I/2, R = I)."""
@@ -142,6 +152,18 @@ class LQGC(_OrnsteinUhlenbeck):
             if not _is_diagonal(M):
                 raise NotImplementedError("LQGC with non-diagonal %s is not supported by the fused kernels" % nm)
         return self._pack(pt.diag(self.P).cpu(), pt.diag(self.R).cpu(), pt.zeros(self.d))
+
+    def u_true_table(self, N, delta_t):
+        """u*(x, t_n) = -Q^-1 B' F[ceil(t_n / self.delta_t)] x; table form needs a diagonal gain (else None)."""
+        tab = np.zeros((N, 2, self.d), np.float32)
+        Qi_Bt = pt.linalg.solve(self.Q, self.B.t()).cpu()
+        for n in range(N):
+            k = int(np.ceil(n * delta_t / self.delta_t))
+            gain = Qi_Bt @ self.F[min(k, self.N)].cpu()
+            if not pt.equal(gain, pt.diag(pt.diag(gain))):
+                return None
+            tab[n, 1] = -pt.diag(gain).numpy()
+        return dict(mode=1, table=pt.from_numpy(tab))
 
 
 # ----------------------------------------------------------------------------------------------- double well
@@ -238,6 +260,15 @@ class DoubleWell:
         z, one = pt.zeros(d), pt.ones(d)
         return L.PROBLEM_DW, 0, pt.cat([z, one, z, z, z, self.kappa * one, self.eta * one]).float().contiguous()
 
+    def u_true_table(self, N, delta_t):
+        """pspde_udiag mode 2 from the finite-difference reference (compute_reference_solution must have run).
+        The reference's `i[-1] -= 2` quirk on the last batch element (:279) is not reproduced."""
+        if not hasattr(self, "u"):
+            return None
+        rows = [min(int(np.ceil(n * delta_t / self.delta_t)), self.u.shape[0] - 1) for n in range(N)]
+        tab = np.stack([np.stack([self.u[r], self.u[r]]) for r in rows]).astype(np.float32)
+        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d, xb=self.xb, dx=self.dx)
+
 
 class DoubleWell_multidim:
     """d independent double wells; the first d_1 coordinates use (kappa, eta), the remaining d_2 use (1, 1)."""
@@ -318,6 +349,15 @@ class DoubleWell_multidim:
         d = self.d
         z, one = pt.zeros(d), pt.ones(d)
         return L.PROBLEM_DW, 0, pt.cat([z, one, z, z, z, self.kappa_.cpu(), self.eta_.cpu()]).float().contiguous()
+
+    def u_true_table(self, N, delta_t):
+        """pspde_udiag mode 2: class 0 = the first d_1 coordinates (u), class 1 = the rest (u_2)."""
+        if not hasattr(self, "u") or (self.d_2 > 0 and not hasattr(self, "u_2")):
+            return None
+        u2 = self.u_2 if self.d_2 > 0 else self.u
+        rows = [min(int(np.ceil(n * delta_t / self.delta_t)), self.u.shape[0] - 1) for n in range(N)]
+        tab = np.stack([np.stack([self.u[r], u2[r]]) for r in rows]).astype(np.float32)
+        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d_1, xb=self.xb, dx=self.dx)
 
 
 class HeatEquation:

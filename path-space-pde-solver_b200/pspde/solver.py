@@ -187,6 +187,12 @@ class Solver:
             self._engine = RolloutEngine(self.problem, self._net_id, self._dims, tm, hi - lo, self.N, self.delta_t_np,
                                          adaptive=self.adaptive_forward_process, k_offset=lo, K_global=self.K,
                                          seed=self.seed, device=self.device)
+            self._u_l2_on = False
+            if self.u_l2_error_flag and hasattr(self.problem, 'u_true_table'):
+                desc = self.problem.u_true_table(self.N, self.delta_t_np)
+                if desc is not None:
+                    self._engine.enable_u_l2(desc)
+                    self._u_l2_on = True
             if self._engine.n_theta != self._theta.numel():
                 raise RuntimeError("parameter count mismatch: modules %d vs kernel %d"
                                    % (self._theta.numel(), self._engine.n_theta))
@@ -234,7 +240,12 @@ class Solver:
         if self.learn_Y_0 and self.y_0.Y_0.grad is not None:
             dist.all_reduce_sum_(self.y_0.Y_0.grad, self.process_group)
         self.optimization_step()
-        return pt.stack([loss.double(), n_bad.double()])
+        u_l2 = pt.full((), float('nan'), dtype=pt.float64, device=self.device)
+        if self._u_l2_on and not (attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0):
+            u = eng.uL2.double()                               # filled by the forward launch of this iteration
+            u_l2 = dist.all_reduce_sum_(pt.where(pt.isfinite(u), u, pt.zeros_like(u)).sum().reshape(1),
+                                        self.process_group)[0] / self.K
+        return pt.stack([loss.double(), n_bad.double(), u_l2])
 
     def train_step(self, l):
         """One full training iteration (noise -> rollout -> loss -> backward -> Adam -> logs), solver.py:431-531."""
@@ -246,16 +257,21 @@ class Solver:
         res = self.gradient_descent(call)
         if self.log_gradient:
             self.gradient_log[l, :] = self._theta.grad[:self.p].detach().cpu()
-        loss, n_bad = res.tolist()                            # the only host sync of the iteration (16 bytes D2H)
+        loss, n_bad, u_l2 = res.tolist()                      # the only host sync of the iteration (24 bytes D2H)
         self.loss_log.append(loss)
         self.nonfinite_log.append(int(n_bad))                 # trajectories dropped from the batch (blow-ups)
-        self.u_L2_loss.append(float('nan'))                   # on-device u_true tables: SURVEY 8(f) row f2
+        self.u_L2_loss.append(u_l2)                           # mean_k sum_n |u - u*|^2 dt (solver.py:491-494, :515); NaN
+                                                              # when the problem has no device table for u_true
         if self.metastability_logs is not None:
             target, epsilon = self.metastability_logs
             X = call.X_N
             close = (pt.sqrt(pt.sum((X - target) ** 2, 1)) < epsilon).float().sum().reshape(1).double()
             self.particles_close_to_target.append(
                 (dist.all_reduce_sum_(close, self.process_group)[0] / self.K).item())
+        if self.IS_variance_K > 0 and l % self.IS_variance_iter == 0:     # solver.py:521-528
+            from .utilities import do_importance_sampling_me
+            _, _, rel_IS = do_importance_sampling_me(self.problem, self, self.IS_variance_K)
+            self.IS_rel_log.append(rel_IS)
         t_1 = time.time()
         self.times.append(t_1 - t_0)
         self.path_steps_per_sec.append(self.K * self.N / max(t_1 - t_0, 1e-12))
@@ -267,8 +283,6 @@ class Solver:
             print('d = %d, L = %d, K = %d, delta_t = %.2e, lr = %.2e, %s, %s, %s, %s'
                   % (self.d, self.L, self.K, self.delta_t_np, self.lr, self.approx_method, self.time_approx,
                      self.loss_method, 'adaptive' if self.adaptive_forward_process else ''))
-        if self.IS_variance_K > 0:
-            raise NotImplementedError("IS_variance_K > 0 (do_importance_sampling_me) is not on the fused path yet")
         for l in range(self.L):
             self.train_step(l)
             if self.verbose and l % self.print_every == 0:
@@ -276,6 +290,8 @@ class Solver:
                           % (l, self.loss_log[-1], self.u_L2_loss[-1], np.mean(self.times[-self.print_every:])))
                 if self.learn_Y_0:
                     string += ' - Y_0: %.4e' % self.Y_0_log[-1]
+                if self.IS_variance_K > 0:
+                    string += ' - rel IS: %.3e' % self.IS_rel_log[-1]
                 print(string)
             if self.early_stopping_time is not None and l > self.early_stopping_time:
                 if np.std(self.u_L2_loss[-self.early_stopping_time:]) / self.u_L2_loss[-1] < 0.02:

@@ -194,3 +194,84 @@ def test_blown_up_trajectory_is_inert(run):
     cfg1.x0_per_path = 1
     o1 = run.attached(cfg1, theta, pack, x0b[bad:bad + 1].copy(), 1.0 / K)
     assert relerr(oa["grad"], ob["grad"] - o1["grad"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["is_llgc_d10_dense", "is_dwm_d4_mlp"])
+def test_importance_sampling_rollout(run, tag):
+    """pspde_importance_sampling vs the reference's do_importance_sampling_me (utilities.py:287-359) on its own noise."""
+    import torch as pt
+    g = load_golden(tag)
+    d, K, N = g["d"], g["K"], g["N"]
+    net = L.NET_DENSENET if g["net"] == "densenet" else L.NET_MLP_TANH
+    pid, flags, pack = H.problem_pack(g["kind"], d, g["pkw"])
+    xis = np.ascontiguousarray(g["xis"], np.float32)                       # (N, K, d)
+    cfg = L.make_cfg(K, d, N, np.float32(g["is_dt"]), pid, net, [d + 1, 30, 30, d], L.TIME_FIRST, adaptive=True,
+                     problem_flags=flags, noise_mode=L.NOISE_INJECT, xi_strides=(d, 1, K * d))
+    sdt = pt.tensor(g["solver_dt"], dtype=pt.float32)
+    t_index = np.array([int(pt.ceil((n * g["is_dt"]) / sdt)) for n in range(N)], np.int32)
+    x0 = (-np.ones(d) if g["kind"] == "dwm" else np.zeros(d)).astype(np.float32)
+    Y, gX, F = (np.zeros(K, np.float32) for _ in range(3))
+    X = np.zeros((K, d), np.float32)
+    ws = np.zeros(1 << 14, np.float64)
+    lib = run.lib
+    rc = lib.pspde_importance_sampling(ctypes.byref(cfg), H.ptr(g["theta"].astype(np.float32)), H.ptr(pack), H.ptr(x0),
+                                       H.ptr(xis), H.ptr(t_index), ctypes.c_float(float(sdt)), H.ptr(X), H.ptr(Y),
+                                       H.ptr(gX), H.ptr(F), H.ptr(ws), ws.nbytes, None)
+    L.check(lib, rc)
+    w = np.exp(Y.astype(np.float64) - 2 * F - gX)
+    mean, var = w.mean(), w.var(ddof=1)
+    assert abs(mean - g["mean"]) < 2e-5 * abs(g["mean"])
+    assert abs(var - g["var"]) < 1e-4 * abs(g["var"])
+    assert abs(np.sqrt(var) / mean - g["rel"]) < 1e-4 * g["rel"]
+
+
+@pytest.mark.parametrize("kind", ["llgc", "lqgc", "dwm"])
+def test_u_l2_diagnostic(run, kind):
+    """u_L2 += sum_j (-Z_j - u*_j(X_{n+1}, n dt))^2 dt (solver.py:491-494) from device tables vs problem.u_true."""
+    import torch as pt
+    import pspde
+    d, K, N, dt = 4, 40, 6, 0.05
+    if kind == "llgc":
+        prob = pspde.LLGC(d=d, off_diag=0.1, T=N * dt, device="cpu")
+    elif kind == "lqgc":
+        prob = pspde.LQGC(d=d, T=N * dt, delta_t=0.025, device="cpu")
+    else:
+        prob = pspde.DoubleWell_multidim(d=d, d_1=2, d_2=2, T=N * dt, eta=3, kappa=5, device="cpu")
+        prob.compute_reference_solution(delta_t=0.025, nx=200)
+        prob.compute_reference_solution_2(delta_t=0.025, nx=200)
+    net = pspde.DenseNet(d_in=d + 1, d_out=d, lr=0.0, seed=3)
+    theta = np.concatenate([q.detach().reshape(-1).numpy() for q in net.parameters()]).astype(np.float32)
+    pid, flags, pack = prob.functor_pack()
+    desc = prob.u_true_table(N, dt)
+    tab = np.ascontiguousarray(desc["table"].numpy(), np.float32)
+    xi = np.random.default_rng(0).standard_normal((K, d, N + 1)).astype(np.float32)
+    cfg = L.make_cfg(K, d, N, np.float32(dt), pid, L.NET_DENSENET, [d + 1, 30, 30, d], L.TIME_FIRST, adaptive=True,
+                     problem_flags=flags, noise_mode=L.NOISE_INJECT, xi_strides=(d * (N + 1), N + 1, 1))
+    uL2 = np.zeros(K, np.float32)
+    u = L.pspde_udiag()
+    u.mode, u.nx1, u.d1 = desc["mode"], desc.get("nx1", 0), desc.get("d1", 0)
+    u.xb, u.dx = desc.get("xb", 0.0), desc.get("dx", 0.0)
+    u.table, u.uL2 = tab.ctypes.data, uL2.ctypes.data
+    Y = np.zeros(K, np.float32)
+    ws = np.zeros(1 << 14, np.float64)
+    x0 = prob.X_0.numpy().astype(np.float32)
+    lib = run.lib
+    rc = lib.pspde_rollout_fwd_diag(ctypes.byref(cfg), H.ptr(theta), H.ptr(np.ascontiguousarray(pack.numpy())),
+                                    H.ptr(x0), None, ctypes.c_void_p(xi.ctypes.data + 4), None, H.ptr(Y), None, None,
+                                    None, ctypes.byref(u), H.ptr(ws), ws.nbytes, None)
+    L.check(lib, rc)
+    # direct evaluation with the problem's own torch functors and u_true (the reference's procedure)
+    X = prob.X_0.repeat(K, 1)
+    ref = pt.zeros(K)
+    xit = pt.tensor(xi)
+    with pt.no_grad():
+        for n in range(N):
+            Z = net(pt.cat([pt.ones(K, 1) * n * pt.tensor(dt), X], 1))
+            X = X + (prob.b(X) + (prob.B @ (-Z).t()).t()) * dt + (prob.B @ xit[:, :, n + 1].t()).t() * float(np.sqrt(np.float32(dt)))
+            ut = pt.tensor(np.asarray(prob.u_true(X, n * dt))).t().float()
+            ref += ((-Z - ut) ** 2).sum(1) * dt
+    r = ref.numpy()
+    if kind == "dwm":      # the reference's `i[-1] -= 2` quirk moves the LAST batch element's cell; compare the others
+        assert relerr(uL2[:-1], r[:-1]) < 2e-3
+    else:
+        assert relerr(uL2, r) < 1e-4

@@ -225,3 +225,41 @@ def test_no_cpu_fallback_and_error_reporting():
     assert len(S.loss_log) == 2 and all(np.isfinite(S.loss_log))
     lib = _lib.load()
     assert lib.pspde_abi_version() == _lib.ABI_VERSION
+
+
+@pytest.mark.parametrize("tag", ["is_llgc_d10_dense", "is_dwm_d4_mlp"])
+def test_importance_sampling_matches_reference(tag):
+    """pspde.do_importance_sampling_me (reference signature, utilities.py:287-359) on the reference's own noise."""
+    import pspde
+    g = load_golden(tag)
+    d = g["d"]
+    cls = {"llgc": pspde.LLGC, "dwm": pspde.DoubleWell_multidim}[g["kind"]]
+    prob = cls(d=d, device="cuda", **g["pkw"])
+    S = pspde.Solver("is", prob, K=8, delta_t=g["solver_dt"], time_approx="inner", u_l2_error_flag=False, verbose=False)
+    if g["net"] == "densenet":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+        S.update_Phis()
+    with pt.no_grad():
+        S._theta.copy_(pt.tensor(g["theta"]))
+    mean, var, rel = pspde.do_importance_sampling_me(prob, S, g["K"], delta_t=g["is_dt"], xis=pt.tensor(g["xis"]))
+    assert abs(mean - g["mean"]) < 2e-5 * abs(g["mean"])
+    assert abs(var - g["var"]) < 1e-4 * abs(g["var"])
+    assert abs(rel - g["rel"]) < 1e-4 * g["rel"]
+    # Philox path at a size the reference cannot hold in memory: -log(mean) is finite and reproducible
+    m1 = pspde.do_importance_sampling_me(prob, S, 200000, delta_t=g["is_dt"])
+    m2 = pspde.do_importance_sampling_me(prob, S, 200000, delta_t=g["is_dt"])
+    assert np.isfinite(m1[0]) and m1 == m2
+
+
+def test_u_l2_diagnostic_and_is_log_during_training():
+    """u_l2_error_flag=True (the reference default) and IS_variance_K > 0 run on the device; u_L2 falls in training."""
+    import pspde
+    d = 10
+    prob = pspde.LLGC(d=d, T=1.0, device="cuda")
+    S = pspde.Solver("u", prob, K=2048, L=150, lr=5e-3, delta_t=0.02, time_approx="inner", detach_forward=True,
+                     early_stopping_time=None, verbose=False, IS_variance_K=20000, IS_variance_iter=50)
+    S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=5e-3, seed=42)
+    S.update_Phis()
+    S.train()
+    assert all(np.isfinite(S.u_L2_loss)) and S.u_L2_loss[-1] < 0.2 * S.u_L2_loss[0]
+    assert len(S.IS_rel_log) == 3 and S.IS_rel_log[-1] < S.IS_rel_log[0]
