@@ -152,6 +152,44 @@ int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const fl
                               const float* xi, const int32_t* t_index, float dt_net, float* X_N, float* Y_N,
                               float* gX, float* Fint, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Diffusion loss of GeneralSolver (solver.py:1001-1200, loss_method='diffusion', approx_method='Y',
+ * boundary='unbounded', adaptive_forward_process=False, detach_forward=True).
+ *
+ * cfg: net_id = PSPDE_NET_DENSENET with one output (the value function V, function_space.py:116-140),
+ * time_mode = PSPDE_TIME_LAST (input [X, t], solver.py:1079), dims[0] = d + 1, problem_id = PSPDE_PROBLEM_HEAT
+ * (b = a_diag x = 0, sigma = diag(b_diag) = sqrt(2) I, h = 0).  T_end = problem.T.  Per path k:
+ *     Y = V(X_0, t_0);  for n < N:  act = !stopped & (t + dt <= T_end)                       (:1119, :1131)
+ *         Y += (grad_x V(X, t) . (sigma xi_n sqrt(dt))) act      [= sum(Z * xi) sqrt(dt), :1100-1104, :1141-1142]
+ *         X += (b(X) dt + sigma xi_n sqrt(dt)) act;  t += dt act;  stopped |= !act           (:1116-1117, :1145-1155)
+ * Only the directional derivative of V enters, so the kernels carry a (value, tangent) row pair per path
+ * instead of forming grad_x V by a reverse sweep as the reference does.
+ * INJECT noise: element (step n, path k, component j) at xi[n*xi_stride_n + k*xi_stride_k + j*xi_stride_j]
+ * (reference draw (K, d) per step, :1106: strides n: K*d, k: d, j: 1).  X0 is K_local x d, t0 has K_local entries.
+ *
+ * pspde_diffusion_fwd -- per path: V0 = V(X_0, t_0), VE = V(X_end, t_end), Y_end, X_end (K_local x d), t_end
+ * (all nullable).  stats (nullable): 4 doubles: sum r^2 over finite r = VE - Y_end (:1163), number of active
+ * (path, step) pairs (K_log, :1151-1152), sum r, number of non-finite r.
+ * With N = 0 it evaluates V at (X0, t0): the terminal-condition term of :1063-1064 is this call on the first
+ * K_boundary samples with t0 = T. */
+size_t pspde_diffusion_workspace_bytes(const pspde_cfg* cfg, float T_end);
+int pspde_diffusion_fwd(const pspde_cfg* cfg, float T_end, const float* theta, const float* prob, const float* X0,
+                        const float* t0, const float* xi, float* V0, float* VE, float* Y_end, float* X_end,
+                        float* t_end, double* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of the diffusion loss -- replaces loss.backward() at solver.py:1187.  The trajectories are regenerated
+ * (they do not depend on theta) and every step runs the reverse of the (value, tangent) pair.  Per-path
+ * cotangents (length K_local, nullable = 0): c0 = dL/dV(X_0, t_0), cD = dL/d(each active directional derivative),
+ * cE = dL/dV(X_end, t_end).  For loss = alpha_0 mean(r^2): w = 2 alpha_0 r / K, c0 = cD = -w, cE = w.
+ * grad_theta (pspde_theta_size floats) is overwritten. */
+int pspde_diffusion_bwd(const pspde_cfg* cfg, float T_end, const float* theta, const float* prob, const float* X0,
+                        const float* t0, const float* xi, const float* c0, const float* cE, const float* cD,
+                        float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Initial points of one iteration from Philox (key = cfg.seed, stream id = cfg.offset, global path index):
+ * X_0 uniform in the ball of radius `radius` (solver.py:1045-1046), t_0 uniform in [0, T_end) (:1078). */
+int pspde_diffusion_sample(const pspde_cfg* cfg, float radius, float T_end, float* X0, float* t0, void* stream);
+
 /* Test hook: writes the increments the kernels would generate for cfg (Philox mode) in the layout
  * (N, K_local, d), i.e. strides (d, 1, K_local*d). */
 int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream);

@@ -13,7 +13,10 @@ uint64_t pspde_launch_count(void) { return g_launches.load(); }
 void pspde_set_profile_buffer(unsigned long long* dev_buf16) { g_prof = dev_buf16; }
 
 int64_t pspde_theta_size(const pspde_cfg* cfg) {
-  if (validate(cfg)) return -1;
+  // only the network fields matter here (shared by the HJB and the diffusion entry points)
+  if (!cfg) { fail(-1, "cfg is NULL"); return -1; }
+  if (cfg->n_layers < 1 || cfg->n_layers > PSPDE_MAX_LAYERS || cfg->d < 1 || cfg->time_mode < 0 || cfg->time_mode > 2 ||
+      (cfg->net_id != PSPDE_NET_DENSENET && cfg->net_id != PSPDE_NET_MLP_TANH)) { fail(-3, "bad network description"); return -1; }
   NetGeom g;
   if (build_geom(g, cfg->net_id, cfg->n_layers, cfg->dims, cfg->time_mode, cfg->d)) { fail(-3, "bad network geometry"); return -1; }
   return (int64_t)g.n_params * (cfg->time_mode == PSPDE_TIME_NONE ? (cfg->n_sets > 0 ? cfg->n_sets : cfg->N) : 1);

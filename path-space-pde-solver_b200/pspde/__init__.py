@@ -3,4 +3,5 @@ lorenzrichter/path-space-PDE-solver's training hot path.  See DESIGN.md / INTEGR
 from .function_space import DenseNet, MySequential, SingleParam  # noqa: F401
 from .problems import LLGC, LQGC, DoubleWell, DoubleWell_multidim, HeatEquation  # noqa: F401
 from .solver import Solver  # noqa: F401
+from .general_solver import GeneralSolver  # noqa: F401
 from .utilities import do_importance_sampling_me  # noqa: F401

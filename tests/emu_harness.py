@@ -116,3 +116,70 @@ class Runner:
                                              ptr(out["grad"]), ptr(ws), ws.nbytes, None)
         L.check(self.lib, rc)
         return out
+
+
+def diffusion_cfg(K, d, N, dt, arch, noise=L.NOISE_INJECT, k_offset=0, seed=0, offset=0):
+    dims = [d + 1] + [int(a) for a in arch] + [1]
+    return L.make_cfg(K, d, N, np.float32(dt), L.PROBLEM_HEAT, L.NET_DENSENET, dims, L.TIME_LAST, adaptive=False,
+                      k_offset=k_offset, noise_mode=noise, seed=seed, offset=offset, xi_strides=(d, 1, K * d))
+
+
+def heat_pack(d):
+    z = np.zeros(d, np.float32)
+    return np.concatenate([z, np.full(d, np.sqrt(np.float32(2.0)), np.float32), z, z, z, z, z]).astype(np.float32)
+
+
+class DiffusionRunner:
+    """numpy front end of pspde_diffusion_* (emulator build)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def _ws(self, cfg, T):
+        n = self.lib.pspde_diffusion_workspace_bytes(ctypes.byref(cfg), ctypes.c_float(T))
+        assert n > 0, self.lib.pspde_last_error()
+        return np.zeros(n // 8 + 1, np.float64)
+
+    def fwd(self, cfg, T, theta, pack, X0, t0, xis=None):
+        K, d = cfg.K_local, cfg.d
+        ws = self._ws(cfg, T)
+        o = dict(V0=np.zeros(K, np.float32), VE=np.zeros(K, np.float32), Y=np.zeros(K, np.float32),
+                 X=np.zeros((K, d), np.float32), t=np.zeros(K, np.float32), stats=np.zeros(4, np.float64))
+        rc = self.lib.pspde_diffusion_fwd(ctypes.byref(cfg), ctypes.c_float(T), ptr(theta), ptr(pack), ptr(X0), ptr(t0),
+                                          ptr(xis), ptr(o["V0"]), ptr(o["VE"]), ptr(o["Y"]), ptr(o["X"]), ptr(o["t"]),
+                                          ptr(o["stats"]), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return o
+
+    def bwd(self, cfg, T, theta, pack, X0, t0, xis, c0, cE, cD):
+        ws = self._ws(cfg, T)
+        grad = np.full(self.lib.pspde_theta_size(ctypes.byref(cfg)), np.nan, np.float32)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        c0, cE, cD = f(c0), f(cE), f(cD)
+        rc = self.lib.pspde_diffusion_bwd(ctypes.byref(cfg), ctypes.c_float(T), ptr(theta), ptr(pack), ptr(X0), ptr(t0),
+                                          ptr(xis), ptr(c0), ptr(cE), ptr(cD), ptr(grad), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return grad
+
+    def iteration(self, g, theta, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0):
+        """loss, grad, K_count, per-path outputs of one GeneralSolver iteration (solver.py:1062-1064, :1076-1163)."""
+        K, d, N = g["K"], g["d"], g["N"]
+        X0 = np.ascontiguousarray(g["X0"], np.float32)
+        t0 = np.ascontiguousarray(g["t0"], np.float32).reshape(-1)
+        xis = np.ascontiguousarray(g["xis"], np.float32)
+        pack = heat_pack(d)
+        cfg = diffusion_cfg(K, d, N, g["delta_t"], g["arch"])
+        f = self.fwd(cfg, T, theta, pack, X0, t0, xis)
+        r = f["VE"].astype(np.float64) - f["Y"]
+        loss = alpha[0] * np.mean(r ** 2)
+        w = alpha[0] * 2 * r / K
+        grad = self.bwd(cfg, T, theta, pack, X0, t0, xis, -w, w, -w).astype(np.float64)
+        # terminal condition on the first K_boundary samples (N = 0 call at t = T)
+        Kb = K_boundary
+        cfgb = diffusion_cfg(Kb, d, 0, g["delta_t"], g["arch"])
+        Xb, tb = np.ascontiguousarray(X0[:Kb]), np.full(Kb, T, np.float32)
+        fb = self.fwd(cfgb, T, theta, pack, Xb, tb)
+        rT = fb["V0"].astype(np.float64) - (Xb.astype(np.float64) ** 2).sum(1)
+        loss += alpha[1] * np.mean(rT ** 2)
+        grad += self.bwd(cfgb, T, theta, pack, Xb, tb, None, alpha[1] * 2 * rT / Kb, None, None)
+        return dict(loss=loss, grad=grad, K_count=int(f["stats"][1]), **f)

@@ -275,3 +275,41 @@ def test_u_l2_diagnostic(run, kind):
         assert relerr(uL2[:-1], r[:-1]) < 2e-3
     else:
         assert relerr(uL2, r) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- diffusion loss (a12)
+def test_diffusion_golden_parity_small():
+    """GeneralSolver iteration (solver.py:1062-1064, :1076-1163) on the reference's own draws: loss, K_count,
+    end states, Y and the full gradient against the golden vectors generated from the reference."""
+    g = load_golden("diff_heat_d10_small")
+    run = H.DiffusionRunner(H.emu_lib())
+    o = run.iteration(g, g["theta"].astype(np.float32), g["K_boundary"])
+    assert o["K_count"] == g["K_count"]
+    assert relerr(o["X"], g["X_end"]) < 1e-6 and relerr(o["t"], g["t_end"].reshape(-1)) < 1e-6
+    assert relerr(o["Y"], g["Y_end"]) < 1e-5
+    assert abs(o["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    assert relerr(o["grad"], g["grad"]) < 1e-5
+    assert abs(np.linalg.norm(o["grad"]) - g["grad_norm"]) < 1e-5 * g["grad_norm"]
+
+
+def test_diffusion_ragged_and_stopping():
+    """K not a multiple of the tile, paths that start close to T (stopped early) and a 3-hidden-layer net, against
+    the fp64 restatement (oracle/manual.py::diffusion)."""
+    rng = np.random.default_rng(5)
+    K, d, N, dt, arch, T = 37, 6, 7, 0.01, (9, 5, 12), 1.0
+    dims = [d + 1] + list(arch) + [1]
+    n_theta = sum((sum(dims[:i + 1]) + 1) * dims[i + 1] for i in range(len(dims) - 1))
+    theta = (rng.standard_normal(n_theta) * 0.3).astype(np.float32)
+    X0 = rng.standard_normal((K, d)).astype(np.float32) * 0.5
+    t0 = rng.uniform(0.9, 1.0, K).astype(np.float32)          # about half of the paths hit T within N steps
+    xis = rng.standard_normal((N, K, d)).astype(np.float32)
+    g = dict(K=K, d=d, N=N, delta_t=dt, arch=arch, X0=X0, t0=t0, xis=xis)
+    run = H.DiffusionRunner(H.emu_lib())
+    o = run.iteration(g, theta, K_boundary=11)
+    net = man.Net("densenet", dims, theta.astype(np.float64))
+    m = man.diffusion(man.Problem("heat", d), net, X0.astype(np.float64), t0.astype(np.float64),
+                      xis.astype(np.float64), dt, N, 11, T=T)
+    assert 0 < o["K_count"] < K * N and o["K_count"] == m["K_count"]
+    assert relerr(o["X"], m["X"]) < 1e-6 and relerr(o["Y"], m["Y"]) < 1e-5
+    assert abs(o["loss"] - m["loss"]) < 1e-5 * abs(m["loss"])
+    assert relerr(o["grad"], m["grad"]) < 2e-5

@@ -263,3 +263,103 @@ def test_u_l2_diagnostic_and_is_log_during_training():
     S.train()
     assert all(np.isfinite(S.u_L2_loss)) and S.u_L2_loss[-1] < 0.2 * S.u_L2_loss[0]
     assert len(S.IS_rel_log) == 3 and S.IS_rel_log[-1] < S.IS_rel_log[0]
+
+
+# ---------------------------------------------------------------------------------------------- diffusion loss (a12)
+def make_general_solver(g, lr=0.0, L=1, noise="inject", K=None):
+    import pspde
+    d = g["d"]
+    prob = pspde.HeatEquation(d=d, T=1, device="cuda")
+    G = pspde.GeneralSolver(prob, "t", seed=g["seed"], delta_t=g["delta_t"], N=g["N"], lr=lr, L=L, K=K or g["K"],
+                            K_boundary=g["K_boundary"], alpha=[1.0, 1.0, 1.0], loss_method="diffusion",
+                            verbose=False, noise=noise)
+    G.V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=lr, arch=list(g["arch"]), seed=g["seed"])
+    return G
+
+
+def test_diffusion_golden_parity_small():
+    """One GeneralSolver iteration on the reference's own draws (solver.py:1045-1046, :1078, :1106): loss, K_log,
+    end states, Y and the full gradient against the golden vectors generated from the reference."""
+    g = load_golden("diff_heat_d10_small")
+    G = make_general_solver(g)
+    G.train()            # noise='inject' replays the reference's CPU draw order after manual_seed(seed)
+    eng = G._get_engine()
+    assert relerr(G._theta.detach().cpu().numpy(), g["theta"]) == 0      # same initialisation as the reference
+    assert G.K_log[0] == g["K_count"]
+    assert relerr(eng.X_end.cpu().numpy(), g["X_end"]) < 1e-6
+    assert relerr(eng.t_end.cpu().numpy(), g["t_end"].reshape(-1)) < 1e-6
+    assert relerr(eng.Y.cpu().numpy(), g["Y_end"]) < TOL
+    assert abs(G.loss_log[0] - g["loss"]) < TOL * abs(g["loss"])
+    assert relerr(G._theta.grad.cpu().numpy(), g["grad"]) < TOL
+
+
+def test_diffusion_golden_parity_c4_shape():
+    """C4 / G4 shape: d = 50, DenseNet[256, 256] (92 724 parameters), K = 256, N = 25."""
+    g = load_golden("diff_heat_d50_w256")
+    G = make_general_solver(g)
+    G.train()
+    eng = G._get_engine()
+    assert G.K_log[0] == g["K_count"]
+    assert relerr(eng.X_end.cpu().numpy(), g["X_end"]) < 1e-6
+    assert relerr(eng.Y.cpu().numpy(), g["Y_end"]) < TOL
+    assert abs(G.loss_log[0] - g["loss"]) < TOL * abs(g["loss"])
+    grad = G._theta.grad.cpu().numpy()
+    assert relerr(grad[g["grad_sample_idx"]], g["grad_sample"]) < TOL
+    assert abs(np.linalg.norm(grad) - g["grad_norm"]) < TOL * g["grad_norm"]
+
+
+def test_diffusion_loss_log_G4():
+    """two Adam iterations of GeneralSolver reproduce the reference's loss_log and K_log."""
+    g = load_golden("loop_G4")
+    g4 = dict(d=50, seed=42, delta_t=1e-3, N=25, K=256, K_boundary=50, arch=[256, 256])
+    G = make_general_solver(g4, lr=1e-3, L=2)
+    G.train()
+    assert G.K_log == [int(v) for v in g["K_log"]]
+    assert relerr(G.loss_log, g["loss_log"]) < 2e-5
+    assert abs(float(G._theta.grad.norm()) - g["grad_norm"]) < 1e-4 * g["grad_norm"]
+
+
+def test_diffusion_full_size_properties():
+    """C4 size per GPU (K = 2^16 here, bounded for test time): Philox path is deterministic, independent of the
+    sharding (k_offset) and linear in the cotangents; training reduces the loss and the error of V(., 0)."""
+    import pspde
+    from pspde.general_solver import DiffusionEngine
+    d, N, K = 50, 25, 4096
+    prob = pspde.HeatEquation(d=d, T=1, device="cuda")
+    V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=1e-3, arch=[256, 256], seed=42).cuda()
+    theta = pt.cat([q.detach().reshape(-1) for q in V.parameters()]).contiguous()
+    eng = DiffusionEngine(prob, V.net_spec()[1], K, N, 1e-3, k_offset=0, seed=7)
+    X0, t0 = eng.sample(1.0, 3)
+    assert float((X0 ** 2).sum(1).max()) <= 1.0 + 1e-5 and 0 <= float(t0.min()) and float(t0.max()) < 1.0
+    eng.forward(theta, X0, t0, None, 3)
+    Y, VE, st = eng.Y.clone(), eng.VE.clone(), eng.stats.clone()
+    eng.forward(theta, X0, t0, None, 3)
+    assert pt.equal(Y, eng.Y) and pt.equal(st, eng.stats)
+    r = (VE - Y).double()
+    assert abs(float((r * r).sum()) - st[0].item()) < 1e-9 * st[0].item()
+    # second half as its own shard: same per-path results
+    half = DiffusionEngine(prob, V.net_spec()[1], K // 2, N, 1e-3, k_offset=K // 2, seed=7)
+    X0h, t0h = half.sample(1.0, 3)
+    assert pt.equal(X0h, X0[K // 2:]) and pt.equal(t0h, t0[K // 2:])
+    half.forward(theta, X0h, t0h, None, 3)
+    assert pt.equal(half.Y, Y[K // 2:])
+    # linearity of the backward pass in the cotangents, and determinism
+    w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    gs = []
+    for (a, b, c) in ((w1, w2, w1), (w2, w1, -w2), (w1 + 2 * w2, w2 + 2 * w1, w1 - 2 * w2)):
+        gr = pt.empty(eng.n_theta, device="cuda")
+        eng.backward(theta, X0, t0, None, 3, a, b, c, gr)
+        gs.append(gr)
+    assert relerr((gs[0] + 2 * gs[1]).cpu().numpy(), gs[2].cpu().numpy()) < 2e-5
+    gr2 = pt.empty(eng.n_theta, device="cuda")
+    eng.backward(theta, X0, t0, None, 3, w1, w2, w1, gr2)
+    assert pt.equal(gr2, gs[0])
+    # training
+    G = pspde.GeneralSolver(prob, "c4", seed=42, delta_t=1e-3, N=25, lr=1e-3, L=60, K=K, K_boundary=50,
+                            verbose=False)
+    G.V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=1e-3, arch=[256, 256], seed=42)
+    e0 = None
+    G.L = 1; G.train(); e0 = G.V_L2_error()
+    G.L = 60; G.train()
+    assert all(np.isfinite(G.loss_log)) and G.loss_log[-1] < 0.5 * G.loss_log[0]
+    assert G.V_L2_error() < e0
