@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- path-steps/sec per training iteration of the fused path-space rollout (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c3re|c4|c5]
 
 Workload (N=1 default): BASELINE.json configs[1] -- Ornstein-Uhlenbeck HJB with linear costs, LLGC(d=100,
 off_diag=0, T=1), DenseNet(101 -> 30 -> 30 -> 100) 'inner', K = 2^16 trajectories per GPU, delta_t = 0.01
@@ -52,6 +52,9 @@ WORKLOADS = {
     "c3re": dict(kind="dwm", pkw=dict(d=50, d_1=15, d_2=35, T=1, eta=3, kappa=5), net="mlp", ta="inner", K=1 << 18,
                  dt=0.005, loss="relative_entropy", detach=False, lr=0.05,
                  desc="C3: DoubleWell_multidim d=50, MySequential, K=2^18/GPU, N=200, relative entropy (attached)"),
+    "c4": dict(kind="heat", pkw=dict(d=50, T=1), net="densenet", arch=[256, 256], K=1 << 18, K_boundary=50, N=25,
+               dt=1e-3, loss="diffusion", lr=1e-3,
+               desc="C4: HeatEquation d=50, GeneralSolver diffusion loss, DenseNet[51,256,256,1], K=2^18/GPU, N=25"),
 }
 
 
@@ -80,6 +83,13 @@ def run_reference(args, wl):
     kind = wl["kind"]
     pkw = {k: v for k, v in wl["pkw"].items() if k != "d"}
     prob = orc.make_problem(kind, d, **pkw)
+    if kind == "heat":
+        N, K_cpu = wl["N"], min(wl["K"], 2048)
+        params = orc.densenet_init(d + 1, 1, wl["arch"], seed=42)
+        times = []
+        orc.diffusion_train_loop(prob, params, K_cpu, wl["K_boundary"], N, wl["dt"], args.warmup + args.steps, wl["lr"],
+                                 seed=42, times=times)
+        return _print_reference(args, wl, times, K_cpu, N, cores)
     N = int(np.floor(prob.T / wl["dt"]))
     K_cpu = min(wl["K"], 4096)      # the reference pre-draws xi = randn(K, d, N+1) on the host: ~0.5 MB per path
     if wl["net"] == "mlp":
@@ -91,6 +101,10 @@ def run_reference(args, wl):
     times = []
     orc.hjb_train_loop(prob, net, params, K_cpu, wl["dt"], args.warmup + args.steps, wl["lr"], wl["loss"], wl["ta"],
                        True, wl["detach"], seed=42, times=times)
+    _print_reference(args, wl, times, K_cpu, N, cores)
+
+
+def _print_reference(args, wl, times, K_cpu, N, cores):
     t = times[args.warmup:]
     ms = 1e3 * sum(t) / len(t)
     value = K_cpu * N / (ms * 1e-3)
@@ -353,6 +367,136 @@ def run_ours(args, wl):
         td.destroy_process_group()
 
 
+def run_ours_c4(args, wl):
+    """BASELINE config 4: one GeneralSolver iteration (device-side sampling, forward rollout with the directional
+    derivative of V, loss, backward rollout, terminal-condition term, Adam) per step."""
+    import torch.distributed as td
+    import pspde
+    from pspde import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not pt.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    pt.cuda.set_device(local)
+    dev = pt.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    d, N = wl["pkw"]["d"], wl["N"]
+    K_global = wl["K"] * world
+    prob = pspde.HeatEquation(device=dev, **wl["pkw"])
+    G = pspde.GeneralSolver(prob, "bench", seed=42, delta_t=wl["dt"], N=N, lr=wl["lr"], L=1, K=K_global,
+                            K_boundary=wl["K_boundary"], verbose=False, device=dev)
+    G.V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=wl["lr"], arch=wl["arch"], seed=42)
+    eng = G._get_engine()
+    flush = pt.empty(256 << 20, dtype=pt.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        pt.cuda.synchronize(dev)
+
+    for l in range(args.warmup):
+        G.train_step(l)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.pspde_launch_count()
+    step_ms = []
+    for l in range(args.steps):
+        flush.fill_(l & 1)
+        barrier()
+        e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
+        e0.record()
+        G.train_step(args.warmup + l)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    launches = lib.pspde_launch_count() - launches0
+    t = pt.tensor([sum(step_ms)], dtype=pt.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = K_global * N * args.steps / (total_ms * 1e-3)
+    pack_h = eng.pack.detach().cpu().pin_memory()
+    barrier()
+    w0 = time.perf_counter()
+    for l in range(args.steps):
+        eng.pack.copy_(pack_h, non_blocking=True)
+        G.train_step(args.warmup + args.steps + l)
+    barrier()
+    w1 = time.perf_counter()
+    t = pt.tensor([w1 - w0], dtype=pt.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    e2e_value = K_global * N * args.steps / float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    # kernel-level timing + roofline (FP32 FMA bound; value and tangent rows: 2 network rows per path-step)
+    M, Md = net_macs(eng.dims, True)
+    theta = G._theta.detach()
+    X0, t0 = eng.sample(1.0, 12345)
+    w = pt.randn(eng.K_local, device=dev) / K_global
+    grad = pt.empty(eng.n_theta, device=dev)
+    tf, tb = [], []
+    for i in range(4):
+        flush.fill_(i & 1)
+        e = [pt.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(); eng.forward(theta, X0, t0, None, 12345); e[1].record()
+        flush.fill_(1 - (i & 1))
+        e[2].record(); eng.backward(theta, X0, t0, None, 12345, -w, w, -w, grad); e[3].record()
+        pt.cuda.synchronize(dev)
+        if i:
+            tf.append(e[0].elapsed_time(e[1])); tb.append(e[2].elapsed_time(e[3]))
+    tf, tb = statistics.median(tf), statistics.median(tb)
+    peak = fma_peak_tflops(lib, dev)
+    ps = eng.K_local * N
+    flops_fwd, flops_bwd = 4.0 * M * ps, 4.0 * (M + Md) * ps
+    ach = flops_bwd / (tb * 1e-3) / 1e12
+    roof = {"bound": "fp32_fma", "kernel": "diffusion_kernel<BWD> (reverse of the value/tangent pair + weight gradient, recompute)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": "fp32 FMA probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure)",
+            "traffic": None, "kernel_ms": {"fwd": tf, "bwd": tb},
+            "fwd": {"achieved": flops_fwd / (tf * 1e-3) / 1e12, "frac": flops_fwd / (tf * 1e-3) / 1e12 / peak},
+            "step": {"algorithmic_flops_per_path_step": 4.0 * (2 * M + Md),
+                     "achieved": (flops_fwd + flops_bwd) / ((tf + tb) * 1e-3) / 1e12,
+                     "frac": (flops_fwd + flops_bwd) / ((tf + tb) * 1e-3) / 1e12 / peak},
+            "hbm_peak_gbs_measured": measured_peaks().get("hbm_gbs")}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_port as orc
+        cores = os.cpu_count() or 1
+        pt.set_num_threads(cores)
+        K_cpu = 1024
+        params = orc.densenet_init(d + 1, 1, wl["arch"], seed=42)
+        times = []
+        orc.diffusion_train_loop(orc.make_problem("heat", d, T=1), params, K_cpu, wl["K_boundary"], N, wl["dt"], 3,
+                                 wl["lr"], seed=42, times=times)
+        tt = times[1:]
+        cpu = {"value": K_cpu * N / (sum(tt) / len(tt)), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "K=%d of %d points, N=%d, 2 timed iterations after 1 warm-up (torch CPU eager, autograd with "
+                         "create_graph per step: the reference's procedure)" % (K_cpu, wl["K"], N)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "K_global": K_global, "K_per_gpu": wl["K"], "N": N, "d": d,
+                       "noise": "device-side Philox4x32-10 (initial points and increments)",
+                       "parallelism": "trajectory-sharded dp%d" % world,
+                       "l2": "256 MiB buffer written between timed steps; weights (371 KB) are re-read from L2 every tile-step by design"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pack_h.numel() * 4), "d2h_bytes_per_step": 32,
+                    "how": "pspde.GeneralSolver.train_step through the C ABI, wall clock, problem functor pack copied from "
+                           "pinned host memory and (loss, K_count) read back every step"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "final_loss": G.loss_log[-1]}
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +510,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl["kind"] == "heat":
+        run_ours_c4(args, wl)
     else:
         run_ours(args, wl)
 

@@ -194,6 +194,11 @@ int pspde_diffusion_sample(const pspde_cfg* cfg, float radius, float T_end, floa
  * (N, K_local, d), i.e. strides (d, 1, K_local*d). */
 int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream);
 
+/* Self test of the tensor-core building block (csrc/tc_sm100.cuh): D[128 x N] = A[128 x K] . B[K x N] (row-major
+ * device buffers) through tcgen05.mma kind::tf32 with the 3-pass hi/lo split that the tensor-core rollout uses.
+ * K % 8 == 0, N % 16 == 0, N <= 256, 2K + N <= 512.  variant 0 is the production descriptor encoding. */
+int pspde_tc_selftest(int K, int N, int variant, const float* A, const float* B, float* D, void* stream);
+
 /* Deterministic fp32 FMA throughput probe (roofline denominator measured live by bench.py):
  * runs `iters` dependent-chain FMA rounds on every SM; returns the FLOP count launched, or <0. */
 int64_t pspde_fma_probe(int iters, float* sink, void* stream);

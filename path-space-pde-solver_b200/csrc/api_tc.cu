@@ -1,0 +1,92 @@
+// api_tc.cu -- tensor-core (tcgen05 / tensor memory) building block and its self test.
+#include "api_common.h"
+#include "tc_sm100.cuh"
+
+#if !defined(PSPDE_EMULATE)
+namespace pspde {
+
+// D[128 x N] = A[128 x K] . B[K x N] through the 3xTF32 path of tc_sm100.cuh.  One CTA, 160 threads: warps 0-3 own
+// one row each (A -> tensor memory, D -> global), warp 4 lane 0 issues the MMAs.  K % 8 == 0, N % 16 == 0,
+// 2K + N <= 512.
+__global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int variant, const float* __restrict__ A,
+                                                             const float* __restrict__ B, float* __restrict__ D) {
+  extern __shared__ float4 smem4[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tile_bytes = tc::b_tile_bytes(K, N);
+  uint8_t* b_hi = smem;
+  uint8_t* b_lo = smem + tile_bytes;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+  // B tile: hi / lo copies in the K-major core-matrix layout
+  for (int q = tid; q < K * N; q += blockDim.x) {
+    const int k = q / N, n = q - k * N;
+    float hi, lo;
+    tc::tf32_split(B[q], hi, lo);
+    *reinterpret_cast<float*>(b_hi + tc::b_tile_offset(n, k, N)) = hi;
+    *reinterpret_cast<float*>(b_lo + tc::b_tile_offset(n, k, N)) = lo;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t a_hi = tbase, a_lo = tbase + (uint32_t)K, d_col = tbase + 2u * (uint32_t)K;
+  if (warp < 4) {
+    const int row = tid;
+    const uint32_t lane_addr = ((uint32_t)(32 * warp)) << 16;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc::tf32_split(A[row * K + k0 + i], hi[i], lo[i]);
+      tc::tmem_st8(a_hi + lane_addr + (uint32_t)k0, hi);
+      tc::tmem_st8(a_lo + lane_addr + (uint32_t)k0, lo);
+    }
+    tc::wait_st();
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4 && lane == 0) {
+    tc::fence_after_sync();
+    const uint32_t lbo = (variant & 1) ? 128u : (uint32_t)N * 16u;
+    const uint32_t sbo = (variant & 1) ? (uint32_t)N * 16u : 128u;
+    tc::mma_3xtf32(d_col, a_hi, a_lo, tc::smem_u32(b_hi), tc::smem_u32(b_lo), N, K / 8, tc::idesc_tf32(128, N), false, lbo, sbo);
+    tc::mma_commit(&bar);
+  }
+  if (warp < 4) {
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    const uint32_t lane_addr = ((uint32_t)(32 * warp)) << 16;
+    for (int n0 = 0; n0 < N; n0 += 8) {
+      float v[8];
+      tc::tmem_ld8(d_col + lane_addr + (uint32_t)n0, v);
+      tc::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) D[tid * N + n0 + i] = v[i];
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace pspde
+#endif
+
+extern "C" int pspde_tc_selftest(int K, int N, int variant, const float* A, const float* B, float* D, void* stream) {
+#if defined(PSPDE_EMULATE)
+  (void)K; (void)N; (void)variant; (void)A; (void)B; (void)D; (void)stream;
+  return fail(-20, "the tensor-core path does not exist in the host emulator");
+#else
+  if (K < 8 || (K & 7) || N < 16 || (N & 15) || N > 256 || 2 * K + N > 512 || !A || !B || !D) return fail(-2, "bad selftest shape");
+  const size_t smem = 2 * (size_t)tc::b_tile_bytes(K, N);
+  if (smem > kMaxSmem) return fail(-6, "selftest tile too large");
+  if (pspde_set_smem(tc_selftest_kernel, smem)) return fail(-11, "cudaFuncSetAttribute failed");
+  PSPDE_LAUNCH(tc_selftest_kernel, 1, 160, smem, stream, K, N, variant, A, B, D);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "tc_selftest launch failed: %s", e);
+  return 0;
+#endif
+}
