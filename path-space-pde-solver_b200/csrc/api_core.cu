@@ -1,5 +1,6 @@
 // api_core.cu -- extern "C" entry points declared in include/pspde.h.
 #include "api_common.h"
+#include "rollout_tc_kernels.cuh"
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
@@ -62,10 +63,30 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
     p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
   }
   p.stats_partial = reinterpret_cast<double*>(workspace);
-  rc = launch_rollout<512, false, 1>(pl, p, stream);
-  if (rc) return rc;
+  int grid = pl.grid;
+#if !defined(PSPDE_EMULATE)
+  // tensor-core forward (rollout_tc_kernels.cuh) for the shape class it covers; PSPDE_FWD_PATH=simt forces the
+  // FP32-FMA kernel (A/B tests), PSPDE_FWD_PATH=tc makes an ineligible configuration an error
+  TcGeom tg;
+  const char* path = getenv("PSPDE_FWD_PATH");
+  const bool eligible = !(diag && diag->mode != 0) && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
+  if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core forward kernel's shape class");
+  if (eligible && !(path && !strcmp(path, "simt"))) {
+    const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
+    const int sms = pspde_sm_count();
+    grid = n_tiles < sms ? n_tiles : sms;
+    p.n_tiles = n_tiles;
+    const cudaError_t ce = tc_launch(p, tg, grid, (cudaStream_t)stream);
+    g_launches++;
+    if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
+  } else
+#endif
+  {
+    rc = launch_rollout<512, false, 1>(pl, p, stream);
+    if (rc) return rc;
+  }
   if (stats) {
-    PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);
+    PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, grid, stats);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "reduce_stats launch failed: %s", e);
   }

@@ -1,0 +1,398 @@
+// rollout_tc_kernels.cuh -- forward rollout on the 5th-generation tensor cores (tcgen05 + tensor memory).
+//
+// Same computation as rollout_kernel<BWD = false> (reference hot loop solver.py:440-494) for the shape class
+//   DenseNet (function_space.py:116-140) with two hidden layers of at most 32 units, 'inner' time input,
+//   diagonal problem functors (LLGC / LQGC with off_diag = 0, DoubleWell_multidim),
+// which covers the BASELINE configs C1-inner, C2 and C5.  A tile is 128 trajectories = the 128 lanes of tensor
+// memory; every trajectory is owned by four threads (one per quarter of the state columns) for the whole rollout:
+//
+//   tensor memory (512 columns x 128 lanes, all allocated):
+//     A operands, hi and lo TF32 halves: a0 = [X | t | 1 | 0] (s0 columns), h1 (32), h2 (32)       2 (s0 + 64) columns
+//     accumulator D = [pre1 (32) | pre2 (32) | Z (np3)]                                              64 + np3 columns
+//   shared memory: the weights as six K-major B tiles (hi and lo of B0, B1, B2), staged once per CTA
+//     B0 = [W0 | W1[a0 rows] | W2[a0 rows]]   (s0 x (64 + np3))    the dense-concat layers all read a0: ONE MMA group
+//     B1 = [W1[h1 rows] | W2[h1 rows]]        (32 x (32 + np3))
+//     B2 =  W2[h2 rows]                       (32 x np3)
+//   registers: the state X (own columns), the per-path partial sums of Y, Z_sum, g.
+//
+// Per step: G0 = a0.B0 -> h1 = relu(pre1)^2 -> G1 += h1.B1 -> h2 = relu(pre2)^2 -> G2 += h2.B2 -> Z; the
+// Euler-Maruyama update then runs on the registers of the thread that owns the column and writes the next a0
+// straight back to tensor memory (tcgen05.st): activations never take a shared-memory layout.  Each product is
+// FP32-equivalent through the 3-pass hi/lo split of tc_sm100.cuh.  Thread 0 issues the MMAs; the hand-offs are
+// mbarriers (operands ready: every thread arrives; group done: tcgen05.commit).
+#pragma once
+#if !defined(PSPDE_EMULATE)
+#include "rollout_kernels.cuh"
+#include "tc_sm100.cuh"
+
+namespace pspde {
+
+constexpr int kTcP = 128;        // trajectories per tile = tensor-memory lanes
+constexpr int kTcTPP = 4;        // threads per trajectory (column parts); 16 warps per CTA
+constexpr int kTcThreads = kTcP * kTcTPP;
+constexpr int kTcMaxG = 8;       // float4 column groups per thread; the kernel is instantiated for NG <= this
+
+struct TcGeom {
+  int s0, hp, np3, n0, n1, n2, ng;   // ng = column groups per thread (max over the parts)
+  int c_a0h, c_a0l, c_h1h, c_h1l, c_h2h, c_h2l, c_d;                  // tensor-memory columns
+  uint32_t o_b0h, o_b0l, o_b1h, o_b1l, o_b2h, o_b2l, o_prob, o_exch, o_red, total;   // shared-memory byte offsets
+};
+
+// false if the network / problem is outside the shape class of this kernel
+inline bool tc_geom(const NetGeom& g, int d, TcGeom& t) {
+  if (g.kind != NET_DENSENET || g.L != 3 || g.time_mode != TIME_FIRST) return false;
+  if (g.dims[1] > 32 || g.dims[2] > 32 || g.dims[3] != d) return false;
+  t.s0 = (g.seg_len[0] + 7) & ~7;
+  t.hp = 32;
+  t.np3 = (t.s0 + 15) & ~15;        // >= s0: the SDE step may read Z for every own column group
+  t.n0 = 2 * t.hp + t.np3; t.n1 = t.hp + t.np3; t.n2 = t.np3;
+  if (t.n0 > 256) return false;
+  t.ng = (t.s0 / 4 + kTcTPP - 1) / kTcTPP;
+  if (t.ng > kTcMaxG) return false;
+  t.c_a0h = 0; t.c_a0l = t.s0; t.c_h1h = 2 * t.s0; t.c_h1l = t.c_h1h + t.hp; t.c_h2h = t.c_h1l + t.hp;
+  t.c_h2l = t.c_h2h + t.hp; t.c_d = t.c_h2l + t.hp;
+  if (t.c_d + t.n0 > 512) return false;
+  uint32_t o = 0;
+  t.o_b0h = o; o += tc::b_tile_bytes(t.s0, t.n0);
+  t.o_b0l = o; o += tc::b_tile_bytes(t.s0, t.n0);
+  t.o_b1h = o; o += tc::b_tile_bytes(t.hp, t.n1);
+  t.o_b1l = o; o += tc::b_tile_bytes(t.hp, t.n1);
+  t.o_b2h = o; o += tc::b_tile_bytes(t.hp, t.n2);
+  t.o_b2l = o; o += tc::b_tile_bytes(t.hp, t.n2);
+  t.o_prob = o; o += 7u * (uint32_t)t.s0 * 4u;
+  t.o_exch = o; o += (uint32_t)kTcP * (uint32_t)kTcTPP * 4u * 4u;
+  t.o_red = o;  o += 4u * 8u;
+  t.total = o;
+  return t.total <= 227u * 1024u;
+}
+
+// weights of one B tile: row k <-> activation column row0 + k (NetGeom numbering), column n <-> (layer, column) by range
+__device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __restrict__ th, uint8_t* hi, uint8_t* lo,
+                                              int Kp, int Np, int row0, int seg_len, int l_first, int hp, int tid, int nthr) {
+  for (int q = tid; q < Kp * Np; q += nthr) {
+    const int k = q / Np, n = q - k * Np;
+    // columns [0, hp) belong to layer l_first unless it is the output layer; then hp more for the next hidden layer ...
+    int l = l_first, nn = n;
+    while (l < g.L - 1 && nn >= hp) { nn -= hp; ++l; }
+    float w = 0.f;
+    if (k < seg_len) {
+      const int idx = theta_index(g, l, row0 + k, nn);
+      if (idx >= 0) w = __ldg(th + idx);
+    }
+    float h, r;
+    tc::tf32_split(w, h, r);
+    *reinterpret_cast<float*>(hi + tc::b_tile_offset(n, k, Np)) = h;
+    *reinterpret_cast<float*>(lo + tc::b_tile_offset(n, k, Np)) = r;
+  }
+}
+
+// One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread 0
+// additionally issues the MMAs: after the last arrival on an "operands ready" barrier it launches the group and
+// commits it to the matching "group done" barrier; everybody (thread 0 included) then waits for that one.
+template <int NG>
+__global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const RolloutParams prm, const TcGeom tg) {
+  extern __shared__ float4 smem4[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
+  __shared__ uint64_t bars[6];          // [0..2] operands of group g ready (all threads arrive), [3..5] group g done (commit)
+  __shared__ uint32_t tmem_base_s;
+  const NetGeom& g = prm.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = prm.d, N = prm.N;
+  const float dt = prm.dt, sq = sqrtf(prm.dt);
+  double* sRed = reinterpret_cast<double*>(smem + tg.o_red);
+  float* sProb = reinterpret_cast<float*>(smem + tg.o_prob);
+  float* sExch = reinterpret_cast<float*>(smem + tg.o_exch);
+
+  // ---- one-time setup: tensor memory, barriers, weights (hi / lo B tiles), problem vectors
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars[i], kTcThreads); tc::mbar_init(&bars[3 + i], 1); }
+    tc::mbar_fence_init();
+  }
+  if (tid < 4) sRed[tid] = 0.0;
+  tc_stage_tile(g, prm.theta, smem + tg.o_b0h, smem + tg.o_b0l, tg.s0, tg.n0, 0, g.seg_len[0], 0, tg.hp, tid, kTcThreads);
+  tc_stage_tile(g, prm.theta, smem + tg.o_b1h, smem + tg.o_b1l, tg.hp, tg.n1, g.seg_off[1], g.seg_len[1], 1, tg.hp, tid, kTcThreads);
+  tc_stage_tile(g, prm.theta, smem + tg.o_b2h, smem + tg.o_b2l, tg.hp, tg.n2, g.seg_off[2], g.seg_len[2], 2, tg.hp, tid, kTcThreads);
+  for (int q = tid; q < 7 * tg.s0; q += kTcThreads) {
+    const int v = q / tg.s0, j = q - v * tg.s0;
+    sProb[q] = j < d ? __ldg(prm.prob + v * d + j) : 0.f;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+
+  // ---- MMA groups (thread 0)
+  const uint32_t sb = tc::smem_u32(smem);
+  const uint32_t dcol = tbase + (uint32_t)tg.c_d;
+  auto issue = [&](int grp, uint32_t parity) {
+    tc::mbar_wait(&bars[grp], parity);
+    tc::fence_after_sync();
+    if (grp == 0)
+      tc::mma_3xtf32(dcol, tbase + tg.c_a0h, tbase + tg.c_a0l, sb + tg.o_b0h, sb + tg.o_b0l, tg.n0, tg.s0 / 8,
+                     tc::idesc_tf32(128, tg.n0), false, (uint32_t)tg.n0 * 16u, 128u);
+    else if (grp == 1)
+      tc::mma_3xtf32(dcol + tg.hp, tbase + tg.c_h1h, tbase + tg.c_h1l, sb + tg.o_b1h, sb + tg.o_b1l, tg.n1, tg.hp / 8,
+                     tc::idesc_tf32(128, tg.n1), true, (uint32_t)tg.n1 * 16u, 128u);
+    else
+      tc::mma_3xtf32(dcol + 2 * tg.hp, tbase + tg.c_h2h, tbase + tg.c_h2l, sb + tg.o_b2h, sb + tg.o_b2l, tg.n2, tg.hp / 8,
+                     tc::idesc_tf32(128, tg.n2), true, (uint32_t)tg.n2 * 16u, 128u);
+    tc::mma_commit(&bars[3 + grp]);
+  };
+
+  // ---- thread = (trajectory, column part)
+  const int qtr = warp & 3, part = warp >> 2;
+  const int p = 32 * qtr + lane;
+  const uint32_t lane_addr = ((uint32_t)(32 * qtr)) << 16;
+  const uint32_t tA0h = tbase + lane_addr + tg.c_a0h, tA0l = tbase + lane_addr + tg.c_a0l;
+  const uint32_t tD = tbase + lane_addr + tg.c_d;
+  const int G = tg.s0 / 4, gbase = G / kTcTPP, grem = G % kTcTPP;
+  const int g_lo = part * gbase + (part < grem ? part : grem);
+  const int ng = gbase + (part < grem ? 1 : 0);
+  constexpr int HC = 32 / kTcTPP;          // hidden columns per thread in the activation epilogues
+  const float *a_d = sProb, *b_d = sProb + tg.s0, *p_d = sProb + 2 * tg.s0, *r_d = sProb + 3 * tg.s0,
+              *al = sProb + 4 * tg.s0, *kap = sProb + 5 * tg.s0, *eta = sProb + 6 * tg.s0;
+  const bool adaptive = prm.adaptive != 0, philox = prm.noise_mode == NOISE_PHILOX, dw = prm.problem_id == PROBLEM_DW;
+  uint32_t ph = 0;
+  float X[NG][4];
+
+  for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+    const int k = tile * kTcP + p;
+    const bool in = k < prm.K_local;
+    const unsigned kglob = (unsigned)(prm.k_offset + k);
+    // ---- tile init (solver.py:365-376) and the first a0
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      if (gi < ng) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * (g_lo + gi) + i;
+          float x = 0.f;
+          if (j < d) { if (in) x = prm.x0_per_path ? __ldg(prm.x0 + (size_t)k * d + j) : __ldg(prm.x0 + j); }
+          else if (j == d + 1) x = 1.0f;                      // j == d: t_0 = 0
+          X[gi][i] = x;
+          tc::tf32_split(x, hi[i], lo[i]);
+        }
+        tc::tmem_st4(tA0h + 4 * (g_lo + gi), hi);
+        tc::tmem_st4(tA0l + 4 * (g_lo + gi), lo);
+      }
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    tc::mbar_arrive(&bars[0]);
+    if (tid == 0) issue(0, ph);
+    float yp = (part == 0 && prm.y0) ? __ldg(prm.y0) : 0.f, zsp = 0.f, gp = 0.f, fip = 0.f;
+    PhaseTimer pt_;          // debug: [0,2,4] wait for MMA group 0/1/2, [1,3] hidden epilogues, [5] SDE step, [6] noise
+    pt_.start(prm.prof, tid == 32 ? 0 : 1);      // an ordinary thread (thread 0 also issues the MMAs)
+
+    for (int n = 0; n < N; ++n) {
+      const bool last = (n == N - 1);
+      // ---- Brownian increments of this step for the own columns.  They do not depend on the network, so they are
+      //      generated (branch-free, NG independent Philox chains) while the tensor core works on G0.
+      // The draw is split in three parts placed in front of the three waits for the tensor core (G0 is the longest).
+      float E[NG][4];
+      constexpr int NA = (NG + 1) / 2, NB = NA + (NG - NA + 1) / 2;
+      auto draw = [&](int g0, int g1) {
+        if (philox) {
+#pragma unroll
+          for (int gi = 0; gi < NG; ++gi) {
+            if (gi >= g0 && gi < g1) {
+              const float4 e4 = philox_normal4(kglob, (unsigned)n, (unsigned)(g_lo + gi), prm.offset, prm.seed);
+              E[gi][0] = e4.x; E[gi][1] = e4.y; E[gi][2] = e4.z; E[gi][3] = e4.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int gi = 0; gi < NG; ++gi)
+            if (gi >= g0 && gi < g1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int j = 4 * (g_lo + gi) + i;
+                E[gi][i] = (in && gi < ng && j < d) ? __ldg(prm.xi + (long long)k * prm.xs_k + (long long)j * prm.xs_j + (long long)n * prm.xs_n) : 0.f;
+              }
+            }
+        }
+      };
+      draw(0, NA);
+      pt_.mark(6);
+      // ---- hidden layers: pre -> h = relu(.)^2 -> A operand (hi, lo)
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) {
+        tc::mbar_wait(&bars[3 + hl], ph);
+        tc::fence_after_sync();
+        pt_.mark(2 * hl);
+        float v[HC], hi[HC], lo[HC];
+        tc::tmem_ld8(tD + hl * tg.hp + HC * part, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < HC; ++i) { const float s = fmaxf(v[i], 0.f); tc::tf32_split(s * s, hi[i], lo[i]); }
+        const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + HC * part;
+        tc::tmem_st8(th, hi);
+        tc::tmem_st8(th + tg.hp, lo);
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&bars[1 + hl]);
+        if (tid == 0) issue(1 + hl, ph);
+        if (hl == 0) draw(NA, NB); else draw(NB, NG);
+        pt_.mark(2 * hl + 1);
+      }
+      // ---- Z is complete: Euler-Maruyama step on the own columns (solver.py:471-486)
+      tc::mbar_wait(&bars[5], ph);
+      tc::fence_after_sync();
+      pt_.mark(4);
+      // Branch-free per element: the problem vectors are zero on the [t | 1 | pad] columns (so x stays put there) and Z
+      // is exactly zero on them (zero weight columns); only the time column is patched afterwards.
+      float zz = 0.f, zxi = 0.f, ff = 0.f;
+      const float t_next = (float)(n + 1) * dt;
+      const float cm = adaptive ? -1.0f : 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < NG; c0 += 2) {          // 2 column groups (8 columns) per tensor-memory access
+        const bool full = (c0 + 1 < NG) && (c0 + 1 < ng);     // warp-uniform
+        float Z[8], H[8], Lo[8];
+        if (full) tc::tmem_ld8(tD + 2 * tg.hp + 4 * (g_lo + c0), Z);
+        else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float z4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c0 + u < NG && c0 + u < ng) tc::tmem_ld4(tD + 2 * tg.hp + 4 * (g_lo + c0 + u), z4);
+            Z[4 * u] = z4[0]; Z[4 * u + 1] = z4[1]; Z[4 * u + 2] = z4[2]; Z[4 * u + 3] = z4[3];
+          }
+        }
+        tc::wait_ld();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (c0 + u < NG) {
+            const int gi = c0 + u;
+            const int j0 = 4 * (g_lo + gi);
+            if (gi < ng) {
+              const float4 A4 = ld4(a_d + j0), B4 = ld4(b_d + j0), P4 = ld4(p_d + j0), K4 = ld4(kap + j0);
+              const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
+              const float pv[4] = {P4.x, P4.y, P4.z, P4.w}, kv[4] = {K4.x, K4.y, K4.z, K4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float z = Z[4 * u + i], x = X[gi][i], ee = E[gi][i];
+                zz = fmaf(z, z, zz);
+                zxi = fmaf(z, ee, zxi);
+                const float drift = fmaf(av[i], x, -(4.0f * kv[i] * (x * (x * x - 1.0f))));   // OU: kappa = 0; double well: a = 0
+                float xn = x + (drift + bv[i] * (cm * z)) * dt + (bv[i] * ee) * sq;
+                ff = fmaf(pv[i] * xn, xn, ff);
+                xn = (j0 + i == d) ? t_next : xn;                                          // the time column
+                X[gi][i] = xn;
+                tc::tf32_split(xn, H[4 * u + i], Lo[4 * u + i]);
+              }
+            }
+          }
+        }
+        if (!last) {
+          if (full) {
+            tc::tmem_st8(tA0h + 4 * (g_lo + c0), H);
+            tc::tmem_st8(tA0l + 4 * (g_lo + c0), Lo);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (c0 + u < NG && c0 + u < ng) {
+                const float h4[4] = {H[4 * u], H[4 * u + 1], H[4 * u + 2], H[4 * u + 3]};
+                const float l4[4] = {Lo[4 * u], Lo[4 * u + 1], Lo[4 * u + 2], Lo[4 * u + 3]};
+                tc::tmem_st4(tA0h + 4 * (g_lo + c0 + u), h4);
+                tc::tmem_st4(tA0l + 4 * (g_lo + c0 + u), l4);
+              }
+            }
+          }
+        }
+      }
+      float gg = 0.f;
+      if (last) {                                   // terminal cost g(X_N) on the own columns
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+          if (gi < ng) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * (g_lo + gi) + i;
+              const float xn = X[gi][i];
+              if (j < d) gg += al[j] * xn + r_d[j] * xn * xn + eta[j] * (xn - 1.0f) * (xn - 1.0f);
+            }
+          }
+        }
+      }
+      const float run = 0.5f * zz + ff;
+      yp += (run + (adaptive ? -zz : 0.f)) * dt + zxi * sq;
+      zsp += run * dt;
+      fip += ff * dt;
+      if (last) gp = gg;
+      else {
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::mbar_arrive(&bars[0]);
+      }
+      ph ^= 1u;
+      if (!last && tid == 0) issue(0, ph);
+      pt_.mark(5);
+    }
+
+    // ---- tile epilogue: combine the column parts of every trajectory, outputs, statistics
+    if (part != 0) {
+      float* e = sExch + 4 * (kTcP * (part - 1) + p);
+      e[0] = yp; e[1] = zsp; e[2] = gp; e[3] = fip;
+    }
+    __syncthreads();
+    if (part == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      if (in) {
+        float Y = yp, ZS = zsp, Gv = gp, FI = fip;
+#pragma unroll
+        for (int r = 1; r < kTcTPP; ++r) {
+          const float* e = sExch + 4 * (kTcP * (r - 1) + p);
+          Y += e[0]; ZS += e[1]; Gv += e[2]; FI += e[3];
+        }
+        if (prm.Y_N) prm.Y_N[k] = Y;
+        if (prm.gX) prm.gX[k] = Gv;
+        if (prm.Zsum) prm.Zsum[k] = ZS;
+        if (prm.Fint) prm.Fint[k] = FI;
+        const double D = (double)Y - (double)Gv;
+        if (isfinite(D) && isfinite((double)ZS)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)Gv; }
+        else s3 = 1.0;
+      }
+      s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); s3 = warp_sum_d(s3);
+      if (lane == 0) { atomicAdd(sRed + 0, s0); atomicAdd(sRed + 1, s1); atomicAdd(sRed + 2, s2); atomicAdd(sRed + 3, s3); }
+    }
+    if (prm.X_N && in) {
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) {
+        if (gi < ng) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 4 * (g_lo + gi) + i;
+            if (j < d) prm.X_N[(size_t)k * d + j] = X[gi][i];
+          }
+        }
+      }
+    }
+    __syncthreads();      // sExch is rewritten by the next tile
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid < 4 && prm.stats_partial) prm.stats_partial[blockIdx.x * 4 + tid] = sRed[tid];
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// NG instantiations: the smallest one that holds tg.ng column groups per thread
+template <int NG>
+inline cudaError_t tc_launch_one(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
+  if (e != cudaSuccess) return e;
+  rollout_tc_fwd_kernel<NG><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
+  return cudaGetLastError();
+}
+inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  if (tg.ng <= 1) return tc_launch_one<1>(p, tg, grid, stream);
+  if (tg.ng <= 2) return tc_launch_one<2>(p, tg, grid, stream);
+  if (tg.ng <= 4) return tc_launch_one<4>(p, tg, grid, stream);
+  if (tg.ng <= 7) return tc_launch_one<7>(p, tg, grid, stream);
+  return tc_launch_one<kTcMaxG>(p, tg, grid, stream);
+}
+
+}  // namespace pspde
+#endif  // !PSPDE_EMULATE
