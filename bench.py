@@ -188,6 +188,26 @@ def fma_peak_tflops(lib, dev):
     return best
 
 
+def fwd_roofline(flops_fwd, tf_ms, fma_peak, eng):
+    """Forward kernel: on the tensor cores (tcgen05 kind::tf32, 3 passes per product for FP32 equivalence) when the
+    network is in the tensor-core kernel's shape class, else FP32 FMA.  The tensor bound is the measured bf16 GEMM
+    peak / 2 (TF32 runs at half the bf16 rate) / 3 (passes): FP32-equivalent TFLOP/s."""
+    ach = flops_fwd / (tf_ms * 1e-3) / 1e12
+    tc_path = os.environ.get("PSPDE_FWD_PATH", "") != "simt" and eng.net_id == 0 and len(eng.dims) == 4 \
+        and max(eng.dims[1:3]) <= 32 and eng.time_mode == 0 and not (eng.flags & 1)
+    out = {"achieved": ach, "frac_of_fp32_fma_peak": ach / fma_peak}
+    if tc_path:
+        bf16 = measured_peaks().get("bf16_tflops")
+        src = "MEASURED_PEAKS.json bf16_tflops (burst) / 2 / 3"
+        if not bf16:
+            bf16, src = 1590.0, "fallback 1.59 PFLOP/s bf16 / 2 / 3"
+        out.update(kernel="rollout_tc_fwd_kernel (tcgen05.mma kind::tf32, 3xTF32, A from tensor memory)", bound="tensor",
+                   peak=bf16 / 6.0, frac=ach / (bf16 / 6.0), peak_source=src)
+    else:
+        out.update(kernel="rollout_kernel<FWD>", bound="fp32_fma", peak=fma_peak, frac=ach / fma_peak)
+    return out
+
+
 def build_solver(wl, K_global, dev):
     import pspde
     pkw = dict(wl["pkw"])
@@ -320,7 +340,7 @@ def run_ours(args, wl):
                                "nominal 148 SM x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s" % (nominal or 0),
                 "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
-                "fwd": {"achieved": flops_fwd / (tf * 1e-3) / 1e12, "frac": flops_fwd / (tf * 1e-3) / 1e12 / peak},
+                "fwd": fwd_roofline(flops_fwd, tf, peak, eng),
                 "step": {"algorithmic_flops_per_path_step": 2.0 * (2 * M + Md),
                          "achieved": (flops_fwd + flops_bwd) / ((tf + tb) * 1e-3) / 1e12,
                          "frac": (flops_fwd + flops_bwd) / ((tf + tb) * 1e-3) / 1e12 / peak},
