@@ -193,8 +193,9 @@ def fwd_roofline(flops_fwd, tf_ms, fma_peak, eng):
     network is in the tensor-core kernel's shape class, else FP32 FMA.  The tensor bound is the measured bf16 GEMM
     peak / 2 (TF32 runs at half the bf16 rate) / 3 (passes): FP32-equivalent TFLOP/s."""
     ach = flops_fwd / (tf_ms * 1e-3) / 1e12
-    tc_path = os.environ.get("PSPDE_FWD_PATH", "") != "simt" and eng.net_id == 0 and len(eng.dims) == 4 \
-        and max(eng.dims[1:3]) <= 32 and eng.time_mode == 0 and not (eng.flags & 1)
+    hid_max = 32 if eng.net_id == 0 else 31          # MySequential keeps a bias column per hidden segment
+    tc_path = os.environ.get("PSPDE_FWD_PATH", "") != "simt" and len(eng.dims) == 4 \
+        and max(eng.dims[1:3]) <= hid_max and eng.time_mode == 0 and not (eng.flags & 1)
     out = {"achieved": ach, "frac_of_fp32_fma_peak": ach / fma_peak}
     if tc_path:
         bf16 = measured_peaks().get("bf16_tflops")

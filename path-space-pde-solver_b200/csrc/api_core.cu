@@ -6,6 +6,33 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 unsigned long long* g_prof = nullptr;
 
+// Forward rollout launch: the tensor-core kernel (rollout_tc_kernels.cuh) for the shape class it covers, else the
+// FP32-FMA kernel.  PSPDE_FWD_PATH=simt forces the FMA kernel (A/B tests); PSPDE_FWD_PATH=tc makes an ineligible
+// configuration an error.  *grid_out = number of CTAs launched (rows of stats_partial that were written).
+static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, bool tc_allowed, void* stream, int* grid_out) {
+#if !defined(PSPDE_EMULATE)
+  TcGeom tg;
+  const char* path = getenv("PSPDE_FWD_PATH");
+  const bool eligible = tc_allowed && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
+  if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core forward kernel's shape class");
+  if (eligible && !(path && !strcmp(path, "simt"))) {
+    const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
+    const int sms = pspde_sm_count();
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    p.n_tiles = n_tiles;
+    const cudaError_t ce = tc_launch(p, tg, grid, (cudaStream_t)stream);
+    g_launches++;
+    if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
+    *grid_out = grid;
+    return 0;
+  }
+#else
+  (void)cfg; (void)tc_allowed;
+#endif
+  *grid_out = pl.grid;
+  return launch_rollout<512, false, 1>(pl, p, stream);
+}
+
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
@@ -64,27 +91,8 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
   }
   p.stats_partial = reinterpret_cast<double*>(workspace);
   int grid = pl.grid;
-#if !defined(PSPDE_EMULATE)
-  // tensor-core forward (rollout_tc_kernels.cuh) for the shape class it covers; PSPDE_FWD_PATH=simt forces the
-  // FP32-FMA kernel (A/B tests), PSPDE_FWD_PATH=tc makes an ineligible configuration an error
-  TcGeom tg;
-  const char* path = getenv("PSPDE_FWD_PATH");
-  const bool eligible = !(diag && diag->mode != 0) && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
-  if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core forward kernel's shape class");
-  if (eligible && !(path && !strcmp(path, "simt"))) {
-    const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
-    const int sms = pspde_sm_count();
-    grid = n_tiles < sms ? n_tiles : sms;
-    p.n_tiles = n_tiles;
-    const cudaError_t ce = tc_launch(p, tg, grid, (cudaStream_t)stream);
-    g_launches++;
-    if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
-  } else
-#endif
-  {
-    rc = launch_rollout<512, false, 1>(pl, p, stream);
-    if (rc) return rc;
-  }
+  rc = launch_forward(cfg, pl, p, !(diag && diag->mode != 0), stream, &grid);
+  if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, grid, stats);
     g_launches++;
@@ -174,7 +182,8 @@ int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const fl
   p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Fint = Fint;
   p.t_index = t_index; p.dt_net = dt_net;
   p.stats_partial = reinterpret_cast<double*>(workspace);
-  return launch_rollout<512, false, 1>(pl, p, stream);
+  int grid = pl.grid;
+  return launch_forward(cfg, pl, p, true, stream, &grid);
 }
 
 int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream) {

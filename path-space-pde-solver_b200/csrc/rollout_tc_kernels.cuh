@@ -1,9 +1,9 @@
 // rollout_tc_kernels.cuh -- forward rollout on the 5th-generation tensor cores (tcgen05 + tensor memory).
 //
 // Same computation as rollout_kernel<BWD = false> (reference hot loop solver.py:440-494) for the shape class
-//   DenseNet (function_space.py:116-140) with two hidden layers of at most 32 units, 'inner' time input,
-//   diagonal problem functors (LLGC / LQGC with off_diag = 0, DoubleWell_multidim),
-// which covers the BASELINE configs C1-inner, C2 and C5.  A tile is 128 trajectories = the 128 lanes of tensor
+//   DenseNet (function_space.py:116-140) or MySequential (:177-195) with two hidden layers of at most 32 (31) units,
+//   'inner' time input, diagonal problem functors (LLGC / LQGC with off_diag = 0, DoubleWell_multidim),
+// which covers the BASELINE configs C1-inner, C2, C3 (detached) and C5.  A tile is 128 trajectories = the 128 lanes of tensor
 // memory; every trajectory is owned by four threads (one per quarter of the state columns) for the whole rollout:
 //
 //   tensor memory (512 columns x 128 lanes, all allocated):
@@ -33,25 +33,29 @@ constexpr int kTcThreads = kTcP * kTcTPP;
 constexpr int kTcMaxG = 8;       // float4 column groups per thread; the kernel is instantiated for NG <= this
 
 struct TcGeom {
-  int s0, hp, np3, n0, n1, n2, ng;   // ng = column groups per thread (max over the parts)
+  int s0, hp, np3, n0, n1, n2, ng, dense;   // ng = column groups per thread (max over the parts)
   int c_a0h, c_a0l, c_h1h, c_h1l, c_h2h, c_h2l, c_d;                  // tensor-memory columns
   uint32_t o_b0h, o_b0l, o_b1h, o_b1l, o_b2h, o_b2l, o_prob, o_exch, o_red, total;   // shared-memory byte offsets
 };
 
 // false if the network / problem is outside the shape class of this kernel
 inline bool tc_geom(const NetGeom& g, int d, TcGeom& t) {
-  if (g.kind != NET_DENSENET || g.L != 3 || g.time_mode != TIME_FIRST) return false;
-  if (g.dims[1] > 32 || g.dims[2] > 32 || g.dims[3] != d) return false;
+  if (g.L != 3 || g.time_mode != TIME_FIRST || g.dims[3] != d) return false;
+  const bool dense = g.kind == NET_DENSENET;
+  if (g.seg_len[1] > 32 || g.seg_len[2] > 32) return false;     // MySequential: hidden width + its bias column <= 32
   t.s0 = (g.seg_len[0] + 7) & ~7;
   t.hp = 32;
   t.np3 = (t.s0 + 15) & ~15;        // >= s0: the SDE step may read Z for every own column group
-  t.n0 = 2 * t.hp + t.np3; t.n1 = t.hp + t.np3; t.n2 = t.np3;
+  // DenseNet: every layer reads a0, so group g also produces the a0 / h1 part of the later layers (accumulated on);
+  // MySequential: one layer per group
+  t.n0 = dense ? 2 * t.hp + t.np3 : t.hp; t.n1 = dense ? t.hp + t.np3 : t.hp; t.n2 = t.np3;
+  t.dense = dense ? 1 : 0;
   if (t.n0 > 256) return false;
   t.ng = (t.s0 / 4 + kTcTPP - 1) / kTcTPP;
   if (t.ng > kTcMaxG) return false;
   t.c_a0h = 0; t.c_a0l = t.s0; t.c_h1h = 2 * t.s0; t.c_h1l = t.c_h1h + t.hp; t.c_h2h = t.c_h1l + t.hp;
   t.c_h2l = t.c_h2h + t.hp; t.c_d = t.c_h2l + t.hp;
-  if (t.c_d + t.n0 > 512) return false;
+  if (t.c_d + 2 * t.hp + t.np3 > 512) return false;
   uint32_t o = 0;
   t.o_b0h = o; o += tc::b_tile_bytes(t.s0, t.n0);
   t.o_b0l = o; o += tc::b_tile_bytes(t.s0, t.n0);
@@ -76,7 +80,7 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
     while (l < g.L - 1 && nn >= hp) { nn -= hp; ++l; }
     float w = 0.f;
     if (k < seg_len) {
-      const int idx = theta_index(g, l, row0 + k, nn);
+      const int idx = theta_index(g, l, (g.kind == NET_DENSENET ? row0 : 0) + k, nn);   // row relative to the layer's first input column
       if (idx >= 0) w = __ldg(th + idx);
     }
     float h, r;
@@ -134,10 +138,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                      tc::idesc_tf32(128, tg.n0), false, (uint32_t)tg.n0 * 16u, 128u);
     else if (grp == 1)
       tc::mma_3xtf32(dcol + tg.hp, tbase + tg.c_h1h, tbase + tg.c_h1l, sb + tg.o_b1h, sb + tg.o_b1l, tg.n1, tg.hp / 8,
-                     tc::idesc_tf32(128, tg.n1), true, (uint32_t)tg.n1 * 16u, 128u);
+                     tc::idesc_tf32(128, tg.n1), tg.dense != 0, (uint32_t)tg.n1 * 16u, 128u);
     else
       tc::mma_3xtf32(dcol + 2 * tg.hp, tbase + tg.c_h2h, tbase + tg.c_h2l, sb + tg.o_b2h, sb + tg.o_b2l, tg.n2, tg.hp / 8,
-                     tc::idesc_tf32(128, tg.n2), true, (uint32_t)tg.n2 * 16u, 128u);
+                     tc::idesc_tf32(128, tg.n2), tg.dense != 0, (uint32_t)tg.n2 * 16u, 128u);
     tc::mma_commit(&bars[3 + grp]);
   };
 
@@ -171,7 +175,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
           const int j = 4 * (g_lo + gi) + i;
           float x = 0.f;
           if (j < d) { if (in) x = prm.x0_per_path ? __ldg(prm.x0 + (size_t)k * d + j) : __ldg(prm.x0 + j); }
-          else if (j == d + 1) x = 1.0f;                      // j == d: t_0 = 0
+          else if (j == d) x = prm.t_index ? (float)__ldg(prm.t_index) * prm.dt_net : 0.f;    // network time of step 0
+          else if (j == d + 1) x = 1.0f;
           X[gi][i] = x;
           tc::tf32_split(x, hi[i], lo[i]);
         }
@@ -226,8 +231,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         float v[HC], hi[HC], lo[HC];
         tc::tmem_ld8(tD + hl * tg.hp + HC * part, v);
         tc::wait_ld();
+        if (tg.dense) {
 #pragma unroll
-        for (int i = 0; i < HC; ++i) { const float s = fmaxf(v[i], 0.f); tc::tf32_split(s * s, hi[i], lo[i]); }
+          for (int i = 0; i < HC; ++i) { const float s = fmaxf(v[i], 0.f); tc::tf32_split(s * s, hi[i], lo[i]); }
+        } else {                           // MySequential: tanh, and the constant-1 column that carries the next bias
+          const int one_col = g.dims[1 + hl];
+#pragma unroll
+          for (int i = 0; i < HC; ++i) {
+            const float h = (HC * part + i == one_col) ? 1.0f : tanhf(v[i]);
+            tc::tf32_split(h, hi[i], lo[i]);
+          }
+        }
         const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + HC * part;
         tc::tmem_st8(th, hi);
         tc::tmem_st8(th + tg.hp, lo);
@@ -245,7 +259,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       // Branch-free per element: the problem vectors are zero on the [t | 1 | pad] columns (so x stays put there) and Z
       // is exactly zero on them (zero weight columns); only the time column is patched afterwards.
       float zz = 0.f, zxi = 0.f, ff = 0.f;
-      const float t_next = (float)(n + 1) * dt;
+      // network time of the next step: (n + 1) dt, or the caller's grid (importance sampling, Solver.Z_n :360-362)
+      const float t_next = (prm.t_index && !last) ? (float)__ldg(prm.t_index + n + 1) * prm.dt_net : (float)(n + 1) * dt;
       const float cm = adaptive ? -1.0f : 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < NG; c0 += 2) {          // 2 column groups (8 columns) per tensor-memory access

@@ -384,18 +384,22 @@ def test_tc_building_block_matches_fp64():
         assert float((D.double() - ref).norm() / ref.norm()) < 1e-6
 
 
-@pytest.mark.parametrize("kind,d,K", [("llgc", 100, 1000), ("lqgc", 10, 200), ("llgc", 3, 129)])
+@pytest.mark.parametrize("kind,d,K", [("llgc", 100, 1000), ("lqgc", 10, 200), ("llgc", 3, 129), ("dwm", 50, 300),
+                                      ("dwm", 7, 65)])
 def test_tc_forward_matches_fma_forward(monkeypatch, kind, d, K):
     """The tensor-core forward kernel against the FP32-FMA forward kernel on identical Philox noise: per-path
-    outputs within 1e-5 (ragged K, d % 4 != 0, C2 shape)."""
+    outputs within 1e-5 (ragged K, d % 4 != 0, C2 shape; 'dwm' = C3: double well + the default MySequential)."""
     import pspde
     from pspde.fused import Call
-    cls = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC}[kind]
-    prob = cls(d=d, T=1.0, device="cuda")
+    if kind == "dwm":
+        prob = pspde.DoubleWell_multidim(d=d, d_1=d // 3, d_2=d - d // 3, T=1.0, eta=3, kappa=5, device="cuda")
+    else:
+        prob = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC}[kind](d=d, T=1.0, device="cuda")
     S = pspde.Solver("tc", prob, K=K, L=1, delta_t=0.02, time_approx="inner", detach_forward=True,
                      u_l2_error_flag=False, early_stopping_time=None, verbose=False)
-    S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
-    S.update_Phis()
+    if kind != "dwm":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+        S.update_Phis()
     eng = S._get_engine()
     theta = S._theta.detach()
     outs = {}
