@@ -13,7 +13,7 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
 #if !defined(PSPDE_EMULATE)
   TcGeom tg;
   const char* path = getenv("PSPDE_FWD_PATH");
-  const bool eligible = tc_allowed && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
+  const bool eligible = tc_allowed && cfg->N >= 1 && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
   if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core forward kernel's shape class");
   if (eligible && !(path && !strcmp(path, "simt"))) {
     const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;

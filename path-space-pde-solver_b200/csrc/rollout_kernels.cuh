@@ -528,11 +528,30 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
   }
 }
 
+// opt-in phase profiler (pspde_set_profile_buffer): thread 0 of CTA 0 adds the cycles since the last mark to slot `ph`
+struct PhaseTimer {
+  unsigned long long* buf; long long t;
+  __device__ __forceinline__ void start(unsigned long long* b, int tid) {
+#if defined(PSPDE_EMULATE)
+    buf = nullptr; t = 0; (void)b; (void)tid;
+#else
+    buf = (b && tid == 0 && blockIdx.x == 0) ? b : nullptr; t = buf ? clock64() : 0;
+#endif
+  }
+  __device__ __forceinline__ void mark(int ph) {
+#if !defined(PSPDE_EMULATE)
+    if (buf) { const long long n = clock64(); buf[ph] += (unsigned long long)(n - t); t = n; }
+#else
+    (void)ph;
+#endif
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ network
 // forward through all layers for the tile; hidden activations -> sAct, output Z -> sZ.  Ends with a barrier.
 template <int P, int RMAX>
 __device__ __forceinline__ void net_forward(const RolloutParams& prm, const SmemLayout& sl, float* smem, int warp,
-                                            int lane, int nwarps) {
+                                            int lane, int nwarps, PhaseTimer* pt = nullptr) {
   const NetGeom& g = prm.g;
   float* sAct = smem + sl.act;
   for (int l = 0; l < g.L; ++l) {
@@ -566,7 +585,9 @@ __device__ __forceinline__ void net_forward(const RolloutParams& prm, const Smem
     else if (RMAX >= 4 && R == 4) gemm_nn<P, (RMAX >= 4 ? 4 : 1)>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
     else if (R == 2) gemm_nn<P, 2>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
     else gemm_nn<P, 1>(A, g.lda, W, y.nng, y.Kp, warp, lane, nwarps, epi);
+    if (pt) pt->mark(5 + l);         // own work of layer l (before the barrier) ...
     __syncthreads();
+    if (pt) pt->mark(8 + l);         // ... and the wait for the slowest warp
   }
 }
 
@@ -625,25 +646,6 @@ __device__ __forceinline__ void tile_init_state(const RolloutParams& prm, float*
   for (int p = tid; p < P; p += nthr)
     for (int s = 0; s < g.L; ++s) if (g.seg_one[s] >= 0) sAct[p * g.lda + g.seg_one[s]] = 1.0f;
 }
-
-// opt-in phase profiler (pspde_set_profile_buffer): thread 0 of CTA 0 adds the cycles since the last mark to slot `ph`
-struct PhaseTimer {
-  unsigned long long* buf; long long t;
-  __device__ __forceinline__ void start(unsigned long long* b, int tid) {
-#if defined(PSPDE_EMULATE)
-    buf = nullptr; t = 0; (void)b; (void)tid;
-#else
-    buf = (b && tid == 0 && blockIdx.x == 0) ? b : nullptr; t = buf ? clock64() : 0;
-#endif
-  }
-  __device__ __forceinline__ void mark(int ph) {
-#if !defined(PSPDE_EMULATE)
-    if (buf) { const long long n = clock64(); buf[ph] += (unsigned long long)(n - t); t = n; }
-#else
-    (void)ph;
-#endif
-  }
-};
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // BWD = false: forward rollout, writes per-path outputs and the loss statistics.
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       }
       __syncthreads();
       pt_.mark(0);
-      net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, warp, lane, NW);
+      net_forward<P, (BWD ? 4 : 8)>(prm, sl, smem, warp, lane, NW, &pt_);
       pt_.mark(1);
       sde_step<P, BWD>(prm, sl, smem, tile, n, n == N - 1, warp, lane, NW);
       __syncthreads();

@@ -413,3 +413,72 @@ def test_tc_forward_matches_fma_forward(monkeypatch, kind, d, K):
     sa, sb = outs["simt"][4].cpu().numpy(), outs["tc"][4].cpu().numpy()
     assert abs(sa[0] - sb[0]) < 1e-5 * (abs(sa[0]) + np.sqrt(K * sa[1]) * 1e-2) and abs(sa[1] - sb[1]) < 1e-5 * sa[1]
     assert sb[3] == 0
+
+
+@pytest.mark.parametrize("opts", [dict(K=1), dict(K=5, adaptive=False), dict(K=130, x0_per_path=True, y0=0.7),
+                                  dict(K=300, inject=True)])
+def test_tc_forward_options(monkeypatch, opts):
+    """Tensor-core forward against the FP32-FMA forward at the engine level: tiny K, non-adaptive forward process,
+    per-path X_0 (random_X_0), a learned Y_0 and injected noise."""
+    import pspde
+    from pspde import _lib
+    from pspde.fused import Call, RolloutEngine
+    d, N, K = 12, 30, opts["K"]
+    prob = pspde.LQGC(d=d, T=1.0, device="cuda")
+    net = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=3).cuda()
+    theta = pt.cat([q.detach().reshape(-1) for q in net.parameters()]).contiguous()
+    eng = RolloutEngine(prob, _lib.NET_DENSENET, net.net_spec()[1], _lib.TIME_FIRST, K, N, 1.0 / N,
+                        adaptive=opts.get("adaptive", True), seed=11)
+    if opts.get("x0_per_path"):
+        eng.set_x0(pt.randn(K, d, device="cuda") * 0.3)
+    y0 = pt.tensor([opts["y0"]], device="cuda") if "y0" in opts else None
+    xi = pt.randn(K, d, N + 1, device="cuda") if opts.get("inject") else None
+    outs = {}
+    for path in ("simt", "tc"):
+        monkeypatch.setenv("PSPDE_FWD_PATH", path)
+        eng.forward(theta, y0, Call(offset=2, xi=xi))
+        pt.cuda.synchronize()
+        outs[path] = [t.clone() for t in (eng.X_N, eng.Y_N, eng.gX, eng.Zsum)]
+    for a, b in zip(outs["simt"], outs["tc"]):
+        assert relerr(b.cpu().numpy(), a.cpu().numpy()) < TOL
+
+
+def test_tc_path_rejects_ineligible_configuration(monkeypatch):
+    """PSPDE_FWD_PATH=tc on a network outside the tensor-core kernel's shape class is an error, not a silent switch."""
+    import pspde
+    from pspde.fused import Call
+    prob = pspde.LLGC(d=10, off_diag=0.1, T=1.0, device="cuda")      # dense A, B
+    S = pspde.Solver("e", prob, K=64, L=1, delta_t=0.05, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, verbose=False)
+    S.z_n = pspde.DenseNet(d_in=11, d_out=10, lr=1e-3, seed=42)
+    S.update_Phis()
+    monkeypatch.setenv("PSPDE_FWD_PATH", "tc")
+    with pytest.raises(RuntimeError, match="shape class"):
+        S._get_engine().forward(S._theta.detach(), None, Call(offset=0))
+
+
+@pytest.mark.parametrize("K,N,Kb", [(7, 3, 50), (33, 1, 5), (96, 25, 50)])
+def test_diffusion_small_and_ragged_against_manual(K, N, Kb):
+    """GeneralSolver's kernels at ragged sizes (K below one tile, K_boundary > K, a single step) against the fp64
+    restatement (oracle/manual.py::diffusion) on injected draws, 3-hidden-layer value network."""
+    import pspde
+    from oracle import manual as man
+    from pspde.general_solver import DiffusionCall
+    d, dt, arch = 5, 0.02, [12, 7, 9]
+    rng = np.random.default_rng(K)
+    prob = pspde.HeatEquation(d=d, T=1, device="cuda")
+    G = pspde.GeneralSolver(prob, "t", seed=1, delta_t=dt, N=N, lr=0.0, L=1, K=K, K_boundary=Kb, verbose=False)
+    G.V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=0.0, arch=arch, seed=5)
+    G._get_engine()
+    X0 = (rng.standard_normal((K, d)) * 0.4).astype(np.float32)
+    t0 = rng.uniform(0.93, 1.0, K).astype(np.float32)              # many paths reach T within N steps
+    xis = rng.standard_normal((N, K, d)).astype(np.float32)
+    call = DiffusionCall(pt.tensor(X0).cuda(), pt.tensor(t0).cuda(), pt.tensor(xis).cuda(), 0)
+    loss, _, k_count, n_bad = G.gradient_descent(call).tolist()
+    theta = G._theta.detach().cpu().numpy().astype(np.float64)
+    net = man.Net("densenet", [d + 1] + arch + [1], theta)
+    m = man.diffusion(man.Problem("heat", d), net, X0.astype(np.float64), t0.astype(np.float64),
+                      xis.astype(np.float64), dt, N, min(Kb, K), T=1.0)
+    assert int(k_count) == m["K_count"] and n_bad == 0
+    assert abs(loss - m["loss"]) < TOL * abs(m["loss"])
+    assert relerr(G._theta.grad.cpu().numpy(), m["grad"]) < 2e-5

@@ -41,6 +41,15 @@ def test_product_path_fails_loudly_without_cuda():
                      device="cpu")
     with pytest.raises(RuntimeError, match="CUDA|no CPU fallback"):
         S.train()
+    # same for the diffusion-loss solver; options off the fused path are refused up front
+    heat = pspde.HeatEquation(d=4, T=1, device="cpu")
+    G = pspde.GeneralSolver(heat, "x", K=8, N=2, delta_t=1e-3, L=1, verbose=False, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA|no CPU fallback"):
+        G.train()
+    with pytest.raises(NotImplementedError):
+        pspde.GeneralSolver(heat, "x", loss_method="BSDE", device="cpu")
+    with pytest.raises(NotImplementedError):
+        pspde.GeneralSolver(heat, "x", adaptive_forward_process=True, device="cpu")
 
 
 def test_flat_parameter_buffer_and_module_adam():

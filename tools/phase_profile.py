@@ -11,7 +11,7 @@ dev = pt.device("cuda", 0); pt.cuda.set_device(0)
 lib = _lib.load()
 S = bench.build_solver(wl, wl["K"], dev); eng = S._get_engine(); theta = S._theta.detach()
 buf = pt.zeros(16, dtype=pt.int64, device=dev)
-names = ["prologue", "net_forward", "sde_step", "backward_hidden", "weight_grad(+copy wait)"]
+names = ["prologue", "net_forward(rest)", "sde_step", "backward_hidden", "weight_grad(+copy wait)", "L0 work", "L1 work", "L2 work", "L0 barrier wait", "L1 barrier wait", "L2 barrier wait"]
 tiles_cta0 = (eng.K_local + 63) // 64 // 148 + (1 if ((eng.K_local + 63) // 64) % 148 > 0 else 0)
 for which in ("fwd", "bwd"):
     eng.forward(theta, None, Call(offset=0)); pt.cuda.synchronize()
