@@ -186,6 +186,52 @@ int pspde_diffusion_bwd(const pspde_cfg* cfg, float T_end, const float* theta, c
                         const float* t0, const float* xi, const float* c0, const float* cE, const float* cD,
                         float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Elliptic sibling: diffusion loss of EllipticSolver (solver.py:628-790, loss_method='diffusion',
+ * approx_method='Y', adaptive_forward_process=False, detach_forward=True).
+ *
+ * cfg: net_id = PSPDE_NET_DENSENET with one output, time_mode = PSPDE_TIME_NONE (the value function sees X only,
+ * solver.py:606), dims[0] = d; the problem pack supplies the drift a_diag x (0 in every reference problem) and
+ * sigma = diag(b_diag).  Per path k:
+ *     Y = V(X_0);  for n < N:  act = !stopped & inside                                           (:750-760)
+ *         Y += (-h(X_n, V(X_n)) dt + grad V(X_n) . (sigma xi_n sqrt(dt))) act                    (:768-769, c = 0)
+ *         X += (b(X) dt + sigma xi_n sqrt(dt)) act;   stopped |= !inside                         (:741-742, :772-779)
+ *   PSPDE_DOMAIN_SPHERE  inside = |X_n| < radius, tested on the point BEFORE the step (:750-751)
+ *   PSPDE_DOMAIN_BOX     inside = all_j (x_l <= proposal_j <= x_r); one_boundary: only proposal_j <= x_r (:755-758)
+ * h functors (h_param[0..2]; r2 = |x|^2):
+ *   PSPDE_H_ZERO                  h = 0
+ *   PSPDE_H_EXP_LINEAR            ExponentialOnSphere (problems.py:985-986): -a y (4 a r2 + 2 d),                a = h_param[0]
+ *   PSPDE_H_EXP_NONLINEAR         ExponentialOnBallNonlinear (:1021-1022): -2 a y (2 a r2 + d) + exp(2 a r2) - y^2
+ *   PSPDE_H_EXP_NONLINEAR_SIN     ExponentialOnBallNonlinearSin (:1057-1058): ... + sin(exp(2 a r2) - y^2)
+ *   PSPDE_H_HELMHOLTZ             Helmholtz (:1645-1648), d = 2: k^2 y + ((a_1 pi)^2 + (a_2 pi)^2 - k^2) sin(a_1 pi x_0) sin(a_2 pi x_1),
+ *                                 (k, a_1, a_2) = h_param
+ * The exact solution used by the V_L2 diagnostic (:733) is exp(a r2) (sin sin for Helmholtz).
+ *
+ * pspde_elliptic_fwd -- per path: V0 = V(X_0), VE = V(X_end), Y_end, X_end (K_local x d), VL2 = sum over the steps
+ * a path entered un-stopped of (V(X_n) - v_true(X_n))^2 dt (all nullable).  stats as in pspde_diffusion_fwd.
+ * With N = 0 it evaluates V at X0 (the Dirichlet boundary term of :669-670 is this call on the boundary samples).
+ * pspde_elliptic_bwd -- cotangents as in pspde_diffusion_bwd; the value row of step n additionally receives
+ * cD act (-dh/dy(X_n, V(X_n)) dt).  INJECT strides as in pspde_diffusion_fwd. */
+enum { PSPDE_DOMAIN_SPHERE = 1, PSPDE_DOMAIN_BOX = 2 };
+enum { PSPDE_H_ZERO = 0, PSPDE_H_EXP_LINEAR = 1, PSPDE_H_EXP_NONLINEAR = 2, PSPDE_H_EXP_NONLINEAR_SIN = 3,
+       PSPDE_H_HELMHOLTZ = 4 };
+typedef struct pspde_elliptic {
+  int32_t domain;        /* PSPDE_DOMAIN_*                                   */
+  float   radius;        /* sphere: problem.boundary_distance                */
+  float   x_l, x_r;      /* box: problem.X_l, problem.X_r                    */
+  int32_t one_boundary;  /* box: problem.one_boundary                        */
+  int32_t h_id;          /* PSPDE_H_*                                        */
+  float   h_param[3];
+} pspde_elliptic;
+
+size_t pspde_elliptic_workspace_bytes(const pspde_cfg* cfg, const pspde_elliptic* ell);
+int pspde_elliptic_fwd(const pspde_cfg* cfg, const pspde_elliptic* ell, const float* theta, const float* prob,
+                       const float* X0, const float* xi, float* V0, float* VE, float* Y_end, float* X_end,
+                       float* VL2, double* stats, void* workspace, size_t workspace_bytes, void* stream);
+int pspde_elliptic_bwd(const pspde_cfg* cfg, const pspde_elliptic* ell, const float* theta, const float* prob,
+                       const float* X0, const float* xi, const float* c0, const float* cE, const float* cD,
+                       float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Initial points of one iteration from Philox (key = cfg.seed, stream id = cfg.offset, global path index):
  * X_0 uniform in the ball of radius `radius` (solver.py:1045-1046), t_0 uniform in [0, T_end) (:1078). */
 int pspde_diffusion_sample(const pspde_cfg* cfg, float radius, float T_end, float* X0, float* t0, void* stream);

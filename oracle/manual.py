@@ -350,3 +350,98 @@ def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0
     for tape, act in steps:
         grad = grad + net.vjp_tangent(tape, np.zeros((K, 1), dtype), (-w * act)[:, None])
     return dict(loss=loss, grad=grad, K_count=K_count, X=X, t=t, Y=Y)
+
+
+# ------------------------------------------------------------------ elliptic diffusion loss (solver.py:628-790)
+class EllipticProblem:
+    """numpy functors of the elliptic problems (problems.py:962-1064, :1614-1654): b = 0, sigma = sqrt(2) I,
+    h(x, y) with its y-derivative, Dirichlet data g, exact solution v_true."""
+
+    def __init__(self, kind, d, alpha=1.0, dtype=np.float64):
+        self.kind, self.d, self.alpha, self.dtype = kind, d, float(alpha), dtype
+        self.B = np.sqrt(dtype(2.0)) * np.eye(d, dtype=dtype)
+        if kind == "helmholtz":
+            self.boundary, self.one_boundary, self.X_l, self.X_r = "square", False, -1.0, 1.0
+            self.a_1, self.a_2, self.k = 1.0, 4.0, 1.0
+        else:
+            self.boundary, self.boundary_distance = "sphere", 1.0
+
+    def _ss(self, x):
+        return np.sin(self.a_1 * np.pi * x[:, 0]) * np.sin(self.a_2 * np.pi * x[:, 1])
+
+    def g(self, x):
+        return self._ss(x) if self.kind == "helmholtz" else np.exp(self.alpha * (x ** 2).sum(1))
+
+    v_true = g
+
+    def h(self, x, y):
+        a, d, r2 = self.alpha, self.d, (x ** 2).sum(1)
+        if self.kind == "expsphere":
+            return -a * y * (4 * a * r2 + 2 * d)
+        if self.kind == "expball":
+            return -2 * a * y * (2 * a * r2 + d) + np.exp(2 * a * r2) - y ** 2
+        if self.kind == "expball_sin":
+            return -2 * a * y * (2 * a * r2 + d) + np.sin(np.exp(2 * a * r2) - y ** 2)
+        c = (self.a_1 * np.pi) ** 2 + (self.a_2 * np.pi) ** 2 - self.k ** 2
+        return self.k ** 2 * y + c * self._ss(x)
+
+    def h_y(self, x, y):
+        a, d, r2 = self.alpha, self.d, (x ** 2).sum(1)
+        if self.kind == "expsphere":
+            return -a * (4 * a * r2 + 2 * d)
+        if self.kind == "expball":
+            return -2 * a * (2 * a * r2 + d) - 2 * y
+        if self.kind == "expball_sin":
+            return -2 * a * (2 * a * r2 + d) - 2 * y * np.cos(np.exp(2 * a * r2) - y ** 2)
+        return np.full(x.shape[0], self.k ** 2, dtype=x.dtype)
+
+    def inside(self, X, X_prop):
+        if self.boundary == "sphere":
+            return np.sqrt((X ** 2).sum(1)) < self.boundary_distance          # solver.py:750-751: X, not the proposal
+        if self.one_boundary:
+            return (X_prop <= self.X_r).all(1)
+        return ((X_prop >= self.X_l) & (X_prop <= self.X_r)).all(1)
+
+
+def elliptic(problem, net, Xb, X0, xis, dt, N, alpha=(1.0, 1.0)):
+    """Value and theta-gradient of the elliptic diffusion loss (non-adaptive, Dirichlet term); net input is X.
+        Y = V(X_0) + sum_n act_n (-h(X_n, V(X_n)) dt + grad V(X_n) . B xi_n sqrt(dt)),  r = V(X_end) - Y
+        dL = sum_k w_k [dV(X_end) - dV(X_0) + sum_n act_n (h_y dt dV(X_n) - d(grad V(X_n) . v_n))],  w = 2 alpha_0 r / K
+    i.e. per step the (value, tangent) pair gets the cotangents (w act h_y dt, -w act)."""
+    dtype = X0.dtype
+    K, d = X0.shape
+    dt = dtype.type(np.float32(dt))
+    s = np.sqrt(dt)
+    Bt = problem.B.T
+    vb, tapeb = net.forward(Xb)
+    rb = vb[:, 0] - problem.g(Xb)
+    loss_b = alpha[1] * (rb ** 2).mean()
+    grad = net.vjp(tapeb, (alpha[1] * 2 * rb / Xb.shape[0])[:, None])
+    X = X0.copy()
+    v0, tape0 = net.forward(X)
+    Y = v0[:, 0].copy()
+    stopped = np.zeros(K, bool)
+    V_L2 = np.zeros(K, dtype)
+    steps, K_count = [], 0
+    for n in range(N):
+        if not (~stopped).any():
+            break
+        v = (xis[n] @ Bt) * s
+        y, dy, tape = net.forward_tangent(X, v)
+        sel = ~stopped
+        V_L2 += (y[:, 0] - problem.v_true(X)) ** 2 * dt * sel
+        X_prop = X + v * sel[:, None]
+        act = problem.inside(X, X_prop) & ~stopped
+        Y = Y + (-problem.h(X, y[:, 0]) * dt + dy[:, 0]) * act
+        steps.append((tape, act.copy(), problem.h_y(X, y[:, 0])))
+        X = np.where(act[:, None], X_prop, X)
+        K_count += int(act.sum())
+        stopped |= ~act
+    vE, tapeE = net.forward(X)
+    r = vE[:, 0] - Y
+    loss = loss_b + alpha[0] * (r ** 2).mean()
+    w = alpha[0] * 2 * r / K
+    grad = grad + net.vjp(tapeE, w[:, None]) - net.vjp(tape0, w[:, None])
+    for tape, act, hy in steps:
+        grad = grad + net.vjp_tangent(tape, (w * act * hy * dt)[:, None], (-w * act)[:, None])
+    return dict(loss=loss, loss_boundary=loss_b, grad=grad, K_count=K_count, X=X, Y=Y, V_L2=V_L2, r=r)

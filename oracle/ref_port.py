@@ -19,6 +19,9 @@ Reference lines restated here
   * losses .............. solver.py:164-192
   * backward ............ solver.py:202-223 (autograd of the loss)
   * diffusion loss ...... solver.py:1040-1064, :1076-1163, :1187
+  * elliptic diffusion .. solver.py:628-826 (EllipticSolver.train, loss 'diffusion', sphere / square domains);
+                          problems.py:962-1064 (ExponentialOnSphere / ...OnBallNonlinear / ...NonlinearSin),
+                          :1614-1654 (Helmholtz)
   * importance sampling . utilities.py:287-359
 """
 from types import SimpleNamespace
@@ -131,6 +134,33 @@ def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
         p.h = lambda t, x, y, z: pt.zeros(x.shape[0], dtype=dtype)
         p.f = lambda x: (x ** 2).sum(1)
         p.v_true = lambda x, t: (x ** 2).sum(1) + 2 * (p.T - t) * d
+    elif kind in ("expsphere", "expball", "expball_sin"):
+        # problems.py:962-992, :995-1028, :1031-1064 (elliptic, unit ball, Dirichlet data g = exp(alpha |x|^2))
+        a = float(kw.get("alpha", 1.0))
+        p.alpha = a
+        p.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(dtype)
+        p.boundary, p.boundary_distance = "sphere", 1.0
+        p.b = lambda x: pt.zeros_like(x)
+        p.g = lambda x: pt.exp(a * (x ** 2).sum(1))
+        p.v_true = p.g
+        if kind == "expsphere":
+            p.h = lambda x, y, z: -a * y * (a * 4 * (x ** 2).sum(1) + 2 * d)
+        elif kind == "expball":
+            p.h = lambda x, y, z: -2 * a * y * (a * 2 * (x ** 2).sum(1) + d) + pt.exp(2 * a * (x ** 2).sum(1)) - y ** 2
+        else:
+            p.h = lambda x, y, z: -2 * a * y * (a * 2 * (x ** 2).sum(1) + d) + pt.sin(pt.exp(2 * a * (x ** 2).sum(1)) - y ** 2)
+    elif kind == "helmholtz":
+        # problems.py:1614-1654 (d = 2, square [-1, 1]^2, both sides absorbing)
+        assert d == 2
+        p.a_1, p.a_2, p.k = 1.0, 4.0, 1.0
+        pi = pt.tensor(np.pi)
+        p.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(dtype)
+        p.boundary, p.one_boundary, p.X_l, p.X_r = "square", False, -1.0, 1.0
+        p.b = lambda x: pt.zeros_like(x)
+        ss = lambda x: pt.sin(p.a_1 * pi * x[:, 0]) * pt.sin(p.a_2 * pi * x[:, 1])
+        p.g = ss
+        p.v_true = ss
+        p.h = lambda x, y, z: (p.k ** 2 * y + (p.a_1 * pi) ** 2 * ss(x) + (p.a_2 * pi) ** 2 * ss(x) - p.k ** 2 * ss(x))
     else:
         raise ValueError(kind)
     return p
@@ -274,6 +304,122 @@ def diffusion_iteration(problem, params, X0, t0, xis, delta_t, N, K_boundary=50,
     for q in params:
         q.requires_grad_(False)
     return dict(loss=loss.detach(), grads=grads, K_count=K_count, X=X.detach(), t=t_n.detach(), Y=Y.detach())
+
+
+# --------------------------------------------------------------------------- elliptic diffusion loss (EllipticSolver)
+def elliptic_exit_mask(problem, X, X_prop):
+    """new_selection of solver.py:750-760: the sphere test looks at X (before the step), the square test at the
+    proposal."""
+    if problem.boundary == "sphere":
+        return pt.sqrt((X ** 2).sum(1)) < problem.boundary_distance                  # :750-751
+    if problem.boundary == "square":
+        if problem.one_boundary:
+            return (X_prop <= problem.X_r).all(1)                                    # :755-756
+        return ((X_prop >= problem.X_l) & (X_prop <= problem.X_r)).all(1)            # :757-758
+    raise ValueError(problem.boundary)
+
+
+def elliptic_iteration(problem, params, Xb, X0, xis, delta_t, N, alpha=(1.0, 1.0)):
+    """One iteration of EllipticSolver.train for loss_method='diffusion', approx_method='Y', Dirichlet boundary
+    term, non-adaptive, detach_forward=True (solver.py:628-790).  Xb (K_boundary, d) are the boundary samples
+    (:646-648 / :655-665), X0 (K, d) the interior start points (:687-708), xis (N, K, d) the increments (:726);
+    with xis=None they are drawn here, one pt.randn(K, d) per step BEFORE the all-stopped check as the reference
+    does (:726-730), so the RNG stream of a whole training loop is reproduced (the draws are returned).
+    The value network sees X only.  Also returns the V_L2 diagnostic of :733 (per path)."""
+    dtype = X0.dtype
+    dt = pt.as_tensor(delta_t, dtype=dtype)
+    sq = pt.sqrt(dt)
+    K = X0.shape[0]
+    for q in params:
+        q.requires_grad_(True)
+        q.grad = None
+    V = lambda z: densenet_forward(params, z)
+    loss = alpha[1] * ((V(Xb).squeeze() - problem.g(Xb)) ** 2).mean()                # :669-670
+    loss_boundary = loss.detach().clone()
+    X = X0.clone().requires_grad_(True)
+    Y = V(X).squeeze()                                                               # :713
+    stopped = pt.zeros(K, dtype=pt.bool)
+    V_L2 = pt.zeros(K, dtype=dtype)
+    K_count = 0
+    drawn = []
+    for n in range(N):
+        Y_ = V(X)
+        grad_V, = pt.autograd.grad(Y_.squeeze().sum(), X, create_graph=True)         # :724
+        Z = (problem.B.t() @ grad_V.t()).t()                                         # :725
+        xin = xis[n] if xis is not None else pt.randn(K, problem.d).to(dtype)        # :726
+        drawn.append(xin)
+        sel = ~stopped
+        if int(sel.sum()) == 0:
+            break
+        V_L2 = V_L2 + ((Y_.squeeze() - problem.v_true(X)) ** 2).detach() * dt * sel.to(dtype)   # :733
+        X_prop = X + (problem.b(X) * dt + (problem.B @ xin.t()).t() * sq) * sel.to(dtype).unsqueeze(1)   # :741-742
+        new_sel = elliptic_exit_mask(problem, X, X_prop)
+        actf = (new_sel & ~stopped).to(dtype)
+        Y = Y + (-problem.h(X, Y_.squeeze(), Z) * dt + (Z * xin).sum(1) * sq) * actf  # :768-769 (c = 0)
+        X = X * (1 - actf).unsqueeze(1) + X_prop * actf.unsqueeze(1)                 # :772-773
+        K_count += int(actf.sum())                                                   # :775-776
+        stopped = stopped | (~new_sel & ~stopped)                                    # :778-779
+    loss = loss + alpha[0] * ((V(X).squeeze() - Y) ** 2).mean()                      # :790
+    loss.backward()
+    grads = [q.grad.detach().clone() for q in params]
+    for q in params:
+        q.requires_grad_(False)
+    return dict(loss=loss.detach(), loss_boundary=loss_boundary, grads=grads, K_count=K_count, X=X.detach(),
+                Y=Y.detach(), V_L2=V_L2, stopped=stopped, xis=drawn)
+
+
+def sample_sphere(K, d, radius, dtype=pt.float32):
+    """Uniform sample on the sphere, solver.py:646-648."""
+    X = pt.randn(K, d).to(dtype)
+    return radius * X / pt.sqrt((X ** 2).sum(1)).unsqueeze(1)
+
+
+def sample_square_boundary(K_boundary, d, X_l, X_r, one_boundary=False, dtype=pt.float32):
+    """Boundary samples of the square, solver.py:655-665 (numpy shuffles first, then one pt.rand draw)."""
+    h = int(K_boundary / 2)
+    s = np.concatenate([np.ones(h)[:, np.newaxis], np.zeros([h, d - 1])], 1)
+    np.apply_along_axis(np.random.shuffle, 1, s)
+    a = np.concatenate([s, np.zeros([h, d])]).astype(bool)
+    b = np.concatenate([np.zeros([h, d]), s]).astype(bool)
+    Xb = ((X_r - X_l) * pt.rand(K_boundary, d) + X_l).to(dtype)
+    Xb[pt.tensor(a)] = X_r if one_boundary else X_l
+    Xb[pt.tensor(b)] = X_r
+    return Xb
+
+
+def elliptic_draws(problem, K, K_boundary, N):
+    """The random draws of one EllipticSolver iteration in the reference's order (:646-665, :687-708, :726).
+    N = 0 leaves the increments to elliptic_iteration (drawn step by step until every path has stopped)."""
+    d = problem.d
+    if problem.boundary == "sphere":
+        Xb = sample_sphere(K_boundary, d, problem.boundary_distance)
+        X0 = sample_ball(K, d, problem.boundary_distance)
+    else:
+        Xb = sample_square_boundary(K_boundary, d, problem.X_l, problem.X_r, problem.one_boundary)
+        X0 = (problem.X_r - problem.X_l) * pt.rand(K, d) + problem.X_l
+    xis = pt.stack([pt.randn(K, d) for _ in range(N)]) if N > 0 else None
+    return Xb, X0, xis
+
+
+def elliptic_train_loop(problem, params, K, K_boundary, N, delta_t, L, lr, alpha=(1.0, 1.0), seed=42, times=None):
+    """EllipticSolver.train (solver.py:628-809) with the reference's RNG use and per-module Adam."""
+    import time
+    pt.manual_seed(seed)
+    np.random.seed(seed)
+    opt = pt.optim.Adam(params, lr=lr)
+    losses, kcounts = [], []
+    for _ in range(L):
+        t0 = time.time()
+        Xb, X0, _ = elliptic_draws(problem, K, K_boundary, 0)
+        o = elliptic_iteration(problem, params, Xb, X0, None, delta_t, N, alpha)
+        for q, g in zip(params, o["grads"]):
+            q.grad = g
+        opt.step()
+        losses.append(float(o["loss"]))
+        kcounts.append(o["K_count"])
+        if times is not None:
+            times.append(time.time() - t0)
+    return losses, kcounts
 
 
 def sample_ball(K, d, radius, dtype=pt.float32):

@@ -20,10 +20,51 @@
 // call into a padded k4-blocked buffer in global memory (L2 resident) and streamed through the read-only path;
 // the weight gradient of one tile-step is accumulated in registers (8x8 blocks over the 2P rows) and added to
 // the CTA's private partial buffer, which a final kernel reduces in fixed order.
+//
+// Elliptic variant (EllipticSolver.train, solver.py:628-790): the value network sees X only
+// (TIME_NONE), the path stops when it leaves the domain instead of at t = T, and h(x, y) need not vanish:
+//        act = !stopped & inside;   Y += (-h(X_n, V(X_n)) dt + grad V(X_n) . (B xi_n sqrt(dt))) act;   X += (...) act
+//   sphere: inside = |X_n| < R, tested on the point BEFORE the step (:750-751);  square: X_l <= proposal <= X_r (:755-758)
+// V(X_n) is the value row of the pair the kernel carries anyway; in the reverse pass it receives the cotangent
+// cD act (-dh/dy(X_n, V(X_n)) dt).  The V_L2 diagnostic of :733 is accumulated from the same value row.
 #pragma once
 #include "rollout_kernels.cuh"
 
 namespace pspde {
+
+enum { DOMAIN_TIME = 0, DOMAIN_SPHERE = 1, DOMAIN_BOX = 2 };
+enum { HFUN_ZERO = 0, HFUN_EXP_LINEAR = 1, HFUN_EXP_NONLINEAR = 2, HFUN_EXP_NONLINEAR_SIN = 3, HFUN_HELMHOLTZ = 4 };
+
+// h(x, y), dh/dy and the exact solution of the elliptic problems (problems.py:962-1064, :1614-1654).
+//   r2 = |x|^2;  sx = sin(a_1 pi x_0) sin(a_2 pi x_1) (Helmholtz only);  hp = {alpha} or {k, a_1, a_2}
+struct HFun {
+  int id, d;
+  float p0, p1, p2;
+  __host__ __device__ float h(float r2, float sx, float y) const {
+    const float a = p0;
+    switch (id) {
+      case HFUN_EXP_LINEAR:        return -a * y * (a * 4.0f * r2 + 2.0f * (float)d);
+      case HFUN_EXP_NONLINEAR:     return -2.0f * a * y * (a * 2.0f * r2 + (float)d) + expf(2.0f * a * r2) - y * y;
+      case HFUN_EXP_NONLINEAR_SIN: return -2.0f * a * y * (a * 2.0f * r2 + (float)d) + sinf(expf(2.0f * a * r2) - y * y);
+      case HFUN_HELMHOLTZ: {
+        const float pi = 3.14159265358979323846f, k2 = p0 * p0;
+        return k2 * y + (p1 * pi) * (p1 * pi) * sx + (p2 * pi) * (p2 * pi) * sx - k2 * sx;
+      }
+      default: return 0.f;
+    }
+  }
+  __host__ __device__ float h_y(float r2, float sx, float y) const {
+    const float a = p0;
+    switch (id) {
+      case HFUN_EXP_LINEAR:        return -a * (a * 4.0f * r2 + 2.0f * (float)d);
+      case HFUN_EXP_NONLINEAR:     return -2.0f * a * (a * 2.0f * r2 + (float)d) - 2.0f * y;
+      case HFUN_EXP_NONLINEAR_SIN: return -2.0f * a * (a * 2.0f * r2 + (float)d) - 2.0f * y * cosf(expf(2.0f * a * r2) - y * y);
+      case HFUN_HELMHOLTZ:         return p0 * p0;
+      default: return 0.f;
+    }
+  }
+  __host__ __device__ float v_true(float r2, float sx) const { return id == HFUN_HELMHOLTZ ? sx : expf(p0 * r2); }
+};
 
 struct DiffusionParams {
   NetGeom g;
@@ -41,6 +82,12 @@ struct DiffusionParams {
   const float *c0, *cE, *cD;       // backward: per-path cotangents (nullable = 0)
   float* grad_partial;             // [gridDim.x][dw_partial_floats(g)]
   double* stats_partial;           // [gridDim.x][4]: sum r^2, #active steps, sum r, #non-finite r
+  // elliptic variant
+  int domain;                      // DOMAIN_*
+  float radius, x_l, x_r;          // sphere radius / box bounds
+  int one_boundary;                // box: only the upper bound absorbs (solver.py:755-756)
+  HFun hf;
+  float* VL2;                      // forward output (per path, nullable): sum_n (V(X_n) - v_true(X_n))^2 dt over non-stopped steps
 };
 
 struct DiffSmem { int act, out, scal, prob, red, zero, total; };
@@ -50,7 +97,7 @@ PSPDE_HD inline DiffSmem diff_smem_layout(const NetGeom& g, int P) {
   int o = 0;
   s.act = o;  o += 2 * P * g.lda;
   s.out = o;  o += 2 * P * 4;
-  s.scal = o; o += 8 * P;
+  s.scal = o; o += 12 * P;
   s.prob = o; o += 2 * ceil4(g.d);
   s.red = o;  o += 16;
   s.zero = o; o += 4;
@@ -257,6 +304,12 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
   float* sCE = sY + 5 * P;
   float* sCD = sY + 6 * P;
   float* sNA = sY + 7 * P;
+  float* sR2 = sY + 8 * P;           // [8] |X_n|^2  [9] sin sin (Helmholtz)  [10] V_L2  [11] V(X_n) (backward)
+  float* sSX = sY + 9 * P;
+  float* sVL = sY + 10 * P;
+  float* sVn = sY + 11 * P;
+  const int domain = prm.domain;
+  const HFun hf = prm.hf;
   const float* a_d = smem + sl.prob;
   const float* b_d = a_d + d4;
   double* sRed = reinterpret_cast<double*>(smem + sl.red);
@@ -285,8 +338,8 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
       const bool in = k < prm.K_local;
-      sY[p] = 0.f; sA[p] = 0.f; sNA[p] = 0.f;
-      sT[p] = in ? __ldg(prm.t0 + k) : 0.f;
+      sY[p] = 0.f; sA[p] = 0.f; sNA[p] = 0.f; sVL[p] = 0.f;
+      sT[p] = (in && prm.t0) ? __ldg(prm.t0 + k) : 0.f;
       sS[p] = in ? 0.f : 1.f;
       sC0[p] = (BWD && in && prm.c0) ? __ldg(prm.c0 + k) : 0.f;
       sCE[p] = (BWD && in && prm.cE) ? __ldg(prm.cE + k) : 0.f;
@@ -297,18 +350,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
     // steps 0..N-1 plus the evaluation of V at the end point (n == N, zero direction)
     for (int n = 0; n <= N; ++n) {
       const bool step = n < N;
-      // ---- (a) who moves in this step (solver.py:1119, :1131, :1154-1155); time column of the value rows
-      for (int p = tid; p < P; p += T) {
-        const float t = sT[p];
-        const bool stopped = sS[p] != 0.f;
-        const bool sel = (t + dt) <= prm.T_end;
-        const bool act = step && !stopped && sel;
-        sA[p] = act ? 1.f : 0.f;
-        if (step && !sel) sS[p] = 1.f;
-        if (act) sNA[p] += 1.f;
-        sAct[p * lda + g.t_col] = t;
-      }
-      // ---- (b) direction v = (B xi) sqrt(dt) into segment 0 of the tangent rows (solver.py:1106, :1116-1117)
+      // ---- (a) direction v = (B xi) sqrt(dt) into segment 0 of the tangent rows (solver.py:1106, :1116-1117; :726, :741-742)
       for (int q = tid; q < P * ngrp0; q += T) {
         const int p = q / ngrp0, jb = q - p * ngrp0, j0 = 4 * jb, k = tile * P + p;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -326,6 +368,40 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           for (int i = 0; i < 4; ++i) if (j0 + i < d) v[i] = (b_d[j0 + i] * e[i]) * sq;
         }
         st4(sAct + (P + p) * lda + j0, make_float4(v[0], v[1], v[2], v[3]));
+      }
+      if (domain == DOMAIN_BOX) __syncthreads();       // the square test looks at the proposal X + b dt + v
+      // ---- (b) who moves in this step (solver.py:1119, :1131, :1154-1155; elliptic :750-779); time column
+      for (int p = tid; p < P; p += T) {
+        const bool stopped = sS[p] != 0.f;
+        bool sel;
+        if (domain == DOMAIN_TIME) {
+          const float t = sT[p];
+          sel = (t + dt) <= prm.T_end;
+          sAct[p * lda + g.t_col] = t;
+        } else {
+          const float* xr = sAct + p * lda;
+          float r2 = 0.f;
+          for (int j = 0; j < d; ++j) r2 += xr[j] * xr[j];
+          sR2[p] = r2;
+          if (hf.id == HFUN_HELMHOLTZ) {
+            const float pi = 3.14159265358979323846f;
+            sSX[p] = sinf(hf.p1 * pi * xr[0]) * sinf(hf.p2 * pi * xr[1]);
+          }
+          if (domain == DOMAIN_SPHERE) sel = sqrtf(r2) < prm.radius;
+          else {
+            const float* vr = sAct + (P + p) * lda;
+            sel = true;
+            for (int j = 0; j < d; ++j) {
+              const float xp = xr[j] + ((a_d[j] * xr[j]) * dt + vr[j]);
+              sel = sel && (xp <= prm.x_r) && (prm.one_boundary || xp >= prm.x_l);
+            }
+          }
+        }
+        const bool act = step && !stopped && sel;
+        sA[p] = act ? 1.f : 0.f;
+        if (step && !sel) sS[p] = 1.f;
+        if (act) sNA[p] += 1.f;
+        sVn[p] = stopped ? 0.f : 1.f;        // "selection" at the start of the step (V_L2, solver.py:733); reused below
       }
       __syncthreads();
 
@@ -363,14 +439,32 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           const int k = tile * P + p;
           const float V = sOut[p * 4], dV = sOut[(P + p) * 4];
           if (n == 0) { sY[p] = V; if (k < prm.K_local && prm.V0) prm.V0[k] = V; }
-          if (step) sY[p] += dV * sA[p];                       // solver.py:1141-1142 with h == 0
-          else if (k < prm.K_local && prm.VE) prm.VE[k] = V;
+          if (step) {
+            if (domain == DOMAIN_TIME) sY[p] += dV * sA[p];    // solver.py:1141-1142 with h == 0
+            else {                                             // solver.py:768-769 (c = 0) and the V_L2 diagnostic (:733)
+              const float r2 = sR2[p], sx = sSX[p];
+              if (sA[p] != 0.f) sY[p] += -hf.h(r2, sx, V) * dt + dV;
+              if (sVn[p] != 0.f) { const float e = V - hf.v_true(r2, sx); sVL[p] += (e * e) * dt; }
+            }
+          } else if (k < prm.K_local && prm.VE) prm.VE[k] = V;
         }
       } else {
         // ---- (e) reverse of the (value, tangent) pair; delta_l overwrites hidden segment l+1 in place
+        if (hf.id != HFUN_ZERO && step) {        // V(X_n) for dh/dy (value rows only)
+          for (int r = warp; r < P; r += NW) {
+            const float* ar = sAct + r * lda + ylast.in_start;
+            const float* w = prm.wpack + ylast.w_off;
+            float s = 0.f;
+            for (int kk = lane; kk < ylast.Kp; kk += 32) s = fmaf(ar[kk], __ldg(w + (kk >> 2) * ylast.nng * 16 + (kk & 3) * 4), s);
+            s = warp_sum(s);
+            if (lane == 0) sVn[r] = s;
+          }
+          __syncthreads();
+        }
         for (int p = tid; p < P; p += T) {
-          const float cv = (n == 0 ? sC0[p] : 0.f) + (step ? 0.f : sCE[p]);
+          float cv = (n == 0 ? sC0[p] : 0.f) + (step ? 0.f : sCE[p]);
           const float cd = step ? sCD[p] * sA[p] : 0.f;
+          if (hf.id != HFUN_ZERO && step) cv += cd * (-hf.h_y(sR2[p], sSX[p], sVn[p]) * dt);   // Y += -h(X_n, V(X_n)) dt
           sOut[p * 4] = cv;
           sOut[(P + p) * 4] = cd;
         }
@@ -408,7 +502,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           }
         }
         __syncthreads();    // sA / sT are read above and rewritten below
-        for (int p = tid; p < P; p += T) if (sA[p] != 0.f) sT[p] += dt;
+        for (int p = tid; p < P; p += T) if (sA[p] != 0.f) sT[p] += dt;      // (stays 0 in the elliptic variant's outputs: unused)
       }
       __syncthreads();
     }
@@ -422,6 +516,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           const float Y = sY[tid];
           if (prm.Y_end) prm.Y_end[k] = Y;
           if (prm.t_end) prm.t_end[k] = sT[tid];
+          if (prm.VL2) prm.VL2[k] = sVL[tid];
           const double r = (double)sOut[tid * 4] - (double)Y;    // V(X_end, t_end) - Y, solver.py:1163
           if (isfinite(r)) { s0 = r * r; s2 = r; } else s3 = 1.0;
           s1 = (double)sNA[tid];

@@ -13,6 +13,8 @@ FLAG_DENSE_AB = 1
 NET_DENSENET, NET_MLP_TANH = 0, 1
 TIME_FIRST, TIME_NONE, TIME_LAST = 0, 1, 2
 NOISE_INJECT, NOISE_PHILOX = 0, 1
+DOMAIN_SPHERE, DOMAIN_BOX = 1, 2
+H_ZERO, H_EXP_LINEAR, H_EXP_NONLINEAR, H_EXP_NONLINEAR_SIN, H_HELMHOLTZ = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -38,8 +40,15 @@ class pspde_udiag(ctypes.Structure):
                 ("dx", ctypes.c_float), ("table", ctypes.c_void_p), ("uL2", ctypes.c_void_p)]
 
 
+class pspde_elliptic(ctypes.Structure):
+    _fields_ = [("domain", ctypes.c_int32), ("radius", ctypes.c_float), ("x_l", ctypes.c_float),
+                ("x_r", ctypes.c_float), ("one_boundary", ctypes.c_int32), ("h_id", ctypes.c_int32),
+                ("h_param", ctypes.c_float * 3)]
+
+
 _P = ctypes.c_void_p
 _CFG = ctypes.POINTER(pspde_cfg)
+_ELL = ctypes.POINTER(pspde_elliptic)
 
 PROTOTYPES = {
     "pspde_abi_version": (ctypes.c_int, []),
@@ -62,6 +71,9 @@ PROTOTYPES = {
                                            ctypes.c_size_t, _P]),
     "pspde_diffusion_bwd": (ctypes.c_int, [_CFG, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                            ctypes.c_size_t, _P]),
+    "pspde_elliptic_workspace_bytes": (ctypes.c_size_t, [_CFG, _ELL]),
+    "pspde_elliptic_fwd": (ctypes.c_int, [_CFG, _ELL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "pspde_elliptic_bwd": (ctypes.c_int, [_CFG, _ELL, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_diffusion_sample": (ctypes.c_int, [_CFG, ctypes.c_float, ctypes.c_float, _P, _P, _P]),
     "pspde_tc_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
@@ -119,3 +131,12 @@ def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=Tr
     c.n_sets = int(n_sets)
     c.xi_stride_k, c.xi_stride_j, c.xi_stride_n = (int(s) for s in xi_strides)
     return c
+
+
+def make_elliptic(domain, radius=1.0, x_l=-1.0, x_r=1.0, one_boundary=False, h_id=H_ZERO, h_param=(0.0, 0.0, 0.0)):
+    e = pspde_elliptic()
+    e.domain, e.radius, e.x_l, e.x_r = int(domain), float(radius), float(x_l), float(x_r)
+    e.one_boundary, e.h_id = int(bool(one_boundary)), int(h_id)
+    for i in range(3):
+        e.h_param[i] = float(h_param[i]) if i < len(h_param) else 0.0
+    return e

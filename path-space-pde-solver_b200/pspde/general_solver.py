@@ -41,7 +41,7 @@ class DiffusionEngine:
         if self.device.type != "cuda":
             raise RuntimeError("the fused rollout runs on CUDA devices only (got %s)" % self.device)
         self.d, self.N, self.K_local, self.k_offset = int(problem.d), int(N), int(K_local), int(k_offset)
-        self.dims, self.seed, self.T = list(dims), int(seed), float(problem.T)
+        self.dims, self.seed, self.T = list(dims), int(seed), float(getattr(problem, 'T', 1.0))
         self.dt = float(pt.tensor(delta_t, dtype=pt.float32))
         pid, flags, pack = problem.functor_pack()
         self.problem_id, self.flags = pid, flags
@@ -53,10 +53,13 @@ class DiffusionEngine:
         self.stats = pt.zeros(4, dtype=pt.float64, device=self.device)
         cfg = self.cfg(self.K_local, self.N, None, 0)
         self.n_theta = int(self.lib.pspde_theta_size(ctypes.byref(cfg)))
-        nbytes = int(self.lib.pspde_diffusion_workspace_bytes(ctypes.byref(cfg), ctypes.c_float(self.T)))
+        nbytes = self.workspace_bytes(cfg)
         if self.n_theta < 0 or nbytes == 0:
             raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
         self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
+
+    def workspace_bytes(self, cfg):
+        return int(self.lib.pspde_diffusion_workspace_bytes(ctypes.byref(cfg), ctypes.c_float(self.T)))
 
     def cfg(self, K, N, xis, offset):
         noise, strides = L.NOISE_PHILOX, (0, 0, 0)

@@ -395,3 +395,128 @@ class HeatEquation:
         d = self.d
         z = pt.zeros(d)
         return L.PROBLEM_HEAT, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- elliptic problems
+class _ExponentialOnBall:
+    """Common part of the elliptic toy problems on the unit ball (problems.py:962-1064): b = 0, sigma = sqrt(2) I,
+    Dirichlet data and exact solution exp(alpha |x|^2).  Subclasses supply h(x, y, z) and its kernel functor id."""
+    H_ID = L.H_ZERO
+
+    def __init__(self, name, d=2, alpha=1.0, boundary_type="Dirichlet", device=None):
+        self.device = default_device() if device is None else pt.device(device)
+        self.name, self.d, self.alpha = name, d, alpha
+        self.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(self.device)
+        self.X_0 = pt.zeros(d, device=self.device)
+        self.Y_0 = pt.zeros(1, device=self.device)
+        self.boundary, self.boundary_distance, self.boundary_type = "sphere", 1.0, boundary_type
+
+    def b(self, x):
+        return pt.zeros_like(x)
+
+    def sigma(self, x):
+        return self.B
+
+    def f(self, x, t=None):
+        return pt.zeros(x.shape[0], device=x.device)
+
+    def g(self, x):
+        if self.boundary_type == "Neumann":
+            return 2 * self.alpha * x * pt.exp(self.alpha * (x ** 2).sum(1)).unsqueeze(1)
+        return pt.exp(self.alpha * (x ** 2).sum(1))
+
+    def u_true(self, x):
+        return -2 * np.sqrt(2.0) * self.alpha * x * pt.exp(self.alpha * (x ** 2).sum(1).unsqueeze(1))
+
+    def v_true(self, x):
+        return pt.exp(self.alpha * (x ** 2).sum(1))
+
+    def functor_pack(self):
+        z = pt.zeros(self.d)
+        return L.PROBLEM_HEAT, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
+
+    def elliptic_spec(self):
+        """Domain + h functor for the kernels (include/pspde.h: pspde_elliptic)."""
+        return L.make_elliptic(L.DOMAIN_SPHERE, radius=self.boundary_distance, h_id=self.H_ID,
+                               h_param=(self.alpha, 0.0, 0.0))
+
+
+class ExponentialOnSphere(_ExponentialOnBall):
+    """problems.py:962-992: linear h = -alpha y (4 alpha |x|^2 + 2 d)."""
+    H_ID = L.H_EXP_LINEAR
+
+    def __init__(self, name="Exponential on sphere", d=2, alpha=1.0, device=None):
+        super().__init__(name, d, alpha, "Dirichlet", device)
+
+    def h(self, x, y, z):
+        return -self.alpha * y * (self.alpha * 4 * (x ** 2).sum(1) + 2 * self.d)
+
+
+class ExponentialOnBallNonlinear(_ExponentialOnBall):
+    """problems.py:995-1028: h = -2 alpha y (2 alpha |x|^2 + d) + exp(2 alpha |x|^2) - y^2."""
+    H_ID = L.H_EXP_NONLINEAR
+
+    def __init__(self, name="Exponential on ball nonlinear", d=2, alpha=1.0, boundary_type="Dirichlet", device=None):
+        super().__init__(name, d, alpha, boundary_type, device)
+
+    def h(self, x, y, z):
+        r2 = (x ** 2).sum(1)
+        return -2 * self.alpha * y * (self.alpha * 2 * r2 + self.d) + pt.exp(2 * self.alpha * r2) - y ** 2
+
+
+class ExponentialOnBallNonlinearSin(_ExponentialOnBall):
+    """problems.py:1031-1064: h = -2 alpha y (2 alpha |x|^2 + d) + sin(exp(2 alpha |x|^2) - y^2)."""
+    H_ID = L.H_EXP_NONLINEAR_SIN
+
+    def __init__(self, name="Exponential on ball nonlinear", d=2, alpha=1.0, boundary_type="Dirichlet", device=None):
+        super().__init__(name, d, alpha, boundary_type, device)
+
+    def h(self, x, y, z):
+        r2 = (x ** 2).sum(1)
+        return -2 * self.alpha * y * (self.alpha * 2 * r2 + self.d) + pt.sin(pt.exp(2 * self.alpha * r2) - y ** 2)
+
+
+class Helmholtz:
+    """problems.py:1614-1654: Helmholtz equation on the square [-1, 1]^2 with exact solution
+    sin(a_1 pi x_0) sin(a_2 pi x_1)."""
+
+    def __init__(self, name="Helmholtz", d=2, r=1.0, device=None):
+        self.device = default_device() if device is None else pt.device(device)
+        self.name, self.d = name, d
+        self.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(self.device)
+        self.X_0 = -pt.ones(d, device=self.device)
+        self.a_1, self.a_2, self.k = 1.0, 4.0, 1.0
+        self.pi = pt.tensor(np.pi)
+        self.boundary, self.one_boundary, self.X_l, self.X_r = "square", False, -1.0, 1.0
+        if d != 2:
+            print("Only implemented for d = 2.")
+
+    def _ss(self, x):
+        return pt.sin(self.a_1 * self.pi * x[:, 0]) * pt.sin(self.a_2 * self.pi * x[:, 1])
+
+    def b(self, x):
+        return pt.zeros_like(x)
+
+    def sigma(self, x):
+        return self.B
+
+    def f(self, x):
+        return pt.zeros(x.shape[0], device=x.device)
+
+    def g(self, x):
+        return self._ss(x)
+
+    def h(self, x, y, z):
+        s = self._ss(x)
+        return self.k ** 2 * y + (self.a_1 * self.pi) ** 2 * s + (self.a_2 * self.pi) ** 2 * s - self.k ** 2 * s
+
+    def v_true(self, x):
+        return self._ss(x)
+
+    def functor_pack(self):
+        z = pt.zeros(self.d)
+        return L.PROBLEM_HEAT, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
+
+    def elliptic_spec(self):
+        return L.make_elliptic(L.DOMAIN_BOX, x_l=self.X_l, x_r=self.X_r, one_boundary=self.one_boundary,
+                               h_id=L.H_HELMHOLTZ, h_param=(self.k, self.a_1, self.a_2))

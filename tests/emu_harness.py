@@ -121,7 +121,7 @@ class Runner:
 def diffusion_cfg(K, d, N, dt, arch, noise=L.NOISE_INJECT, k_offset=0, seed=0, offset=0):
     dims = [d + 1] + [int(a) for a in arch] + [1]
     return L.make_cfg(K, d, N, np.float32(dt), L.PROBLEM_HEAT, L.NET_DENSENET, dims, L.TIME_LAST, adaptive=False,
-                      k_offset=k_offset, noise_mode=noise, seed=seed, offset=offset, xi_strides=(d, 1, K * d))
+                      k_offset=k_offset, noise_mode=noise, seed=seed, offset=offset, xi_strides=(d, 1, K * d), n_sets=0)
 
 
 def heat_pack(d):
@@ -182,4 +182,78 @@ class DiffusionRunner:
         rT = fb["V0"].astype(np.float64) - (Xb.astype(np.float64) ** 2).sum(1)
         loss += alpha[1] * np.mean(rT ** 2)
         grad += self.bwd(cfgb, T, theta, pack, Xb, tb, None, alpha[1] * 2 * rT / Kb, None, None)
+        return dict(loss=loss, grad=grad, K_count=int(f["stats"][1]), **f)
+
+
+# ---------------------------------------------------------------------------------------------- elliptic (row f4)
+ELLIPTIC_H = {"expsphere": L.H_EXP_LINEAR, "expball": L.H_EXP_NONLINEAR, "expball_sin": L.H_EXP_NONLINEAR_SIN,
+              "helmholtz": L.H_HELMHOLTZ}
+
+
+def elliptic_spec(kind, alpha=1.0):
+    """pspde_elliptic of the reference problems (problems.py:962-1064 unit ball; :1614-1654 square [-1, 1]^2)."""
+    if kind == "helmholtz":
+        return L.make_elliptic(L.DOMAIN_BOX, x_l=-1.0, x_r=1.0, one_boundary=False, h_id=L.H_HELMHOLTZ,
+                               h_param=(1.0, 1.0, 4.0))
+    return L.make_elliptic(L.DOMAIN_SPHERE, radius=1.0, h_id=ELLIPTIC_H[kind], h_param=(alpha, 0.0, 0.0))
+
+
+def elliptic_cfg(K, d, N, dt, arch, noise=L.NOISE_INJECT, k_offset=0, seed=0, offset=0):
+    dims = [d] + [int(a) for a in arch] + [1]
+    return L.make_cfg(K, d, N, np.float32(dt), L.PROBLEM_HEAT, L.NET_DENSENET, dims, L.TIME_NONE, adaptive=False,
+                      k_offset=k_offset, noise_mode=noise, seed=seed, offset=offset, xi_strides=(d, 1, K * d), n_sets=1)
+
+
+class EllipticRunner:
+    """numpy front end of pspde_elliptic_* (emulator build)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def _ws(self, cfg, ell):
+        n = self.lib.pspde_elliptic_workspace_bytes(ctypes.byref(cfg), ctypes.byref(ell))
+        assert n > 0, self.lib.pspde_last_error()
+        return np.zeros(n // 8 + 1, np.float64)
+
+    def fwd(self, cfg, ell, theta, pack, X0, xis=None):
+        K, d = cfg.K_local, cfg.d
+        ws = self._ws(cfg, ell)
+        o = dict(V0=np.zeros(K, np.float32), VE=np.zeros(K, np.float32), Y=np.zeros(K, np.float32),
+                 X=np.zeros((K, d), np.float32), VL2=np.zeros(K, np.float32), stats=np.zeros(4, np.float64))
+        rc = self.lib.pspde_elliptic_fwd(ctypes.byref(cfg), ctypes.byref(ell), ptr(theta), ptr(pack), ptr(X0), ptr(xis),
+                                         ptr(o["V0"]), ptr(o["VE"]), ptr(o["Y"]), ptr(o["X"]), ptr(o["VL2"]),
+                                         ptr(o["stats"]), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return o
+
+    def bwd(self, cfg, ell, theta, pack, X0, xis, c0, cE, cD):
+        ws = self._ws(cfg, ell)
+        grad = np.full(self.lib.pspde_theta_size(ctypes.byref(cfg)), np.nan, np.float32)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        c0, cE, cD = f(c0), f(cE), f(cD)
+        rc = self.lib.pspde_elliptic_bwd(ctypes.byref(cfg), ctypes.byref(ell), ptr(theta), ptr(pack), ptr(X0), ptr(xis),
+                                         ptr(c0), ptr(cE), ptr(cD), ptr(grad), ptr(ws), ws.nbytes, None)
+        L.check(self.lib, rc)
+        return grad
+
+    def iteration(self, g, theta, g_fun, alpha=(1.0, 1.0)):
+        """loss, grad, K_count, per-path outputs of one EllipticSolver iteration (solver.py:646-670, :687-790)."""
+        K, d, N = int(g["K"]), int(g["d"]), int(g["N"])
+        X0 = np.ascontiguousarray(g["X0"], np.float32)
+        Xb = np.ascontiguousarray(g["Xb"], np.float32)
+        xis = np.ascontiguousarray(g["xis"], np.float32)
+        pack = heat_pack(d)
+        ell = elliptic_spec(str(g["kind"]))
+        cfg = elliptic_cfg(K, d, N, g["delta_t"], g["arch"])
+        f = self.fwd(cfg, ell, theta, pack, X0, xis)
+        r = f["VE"].astype(np.float64) - f["Y"]
+        loss = alpha[0] * np.mean(r ** 2)
+        w = alpha[0] * 2 * r / K
+        grad = self.bwd(cfg, ell, theta, pack, X0, xis, -w, w, -w).astype(np.float64)
+        Kb = Xb.shape[0]                                   # Dirichlet term: N = 0 call on the boundary samples
+        cfgb = elliptic_cfg(Kb, d, 0, g["delta_t"], g["arch"])
+        fb = self.fwd(cfgb, ell, theta, pack, Xb)
+        rb = fb["V0"].astype(np.float64) - g_fun(Xb.astype(np.float64))
+        loss += alpha[1] * np.mean(rb ** 2)
+        grad += self.bwd(cfgb, ell, theta, pack, Xb, None, None, alpha[1] * 2 * rb / Kb, None)
         return dict(loss=loss, grad=grad, K_count=int(f["stats"][1]), **f)

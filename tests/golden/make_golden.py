@@ -159,6 +159,63 @@ def run_diffusion_case(tag, d, K, K_boundary, N, delta_t, arch, seed=42, full=Tr
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
 
 
+REF_ELLIPTIC = {"expsphere": "ExponentialOnSphere", "expball": "ExponentialOnBallNonlinear",
+                "expball_sin": "ExponentialOnBallNonlinearSin", "helmholtz": "Helmholtz"}
+
+
+def run_elliptic_case(tag, kind, d, K, K_boundary, N, delta_t, arch, alpha, seed=42):
+    """EllipticSolver, loss 'diffusion', Dirichlet boundary term (solver.py:628-809), L=1, lr frozen to 0."""
+    problem = getattr(RP, REF_ELLIPTIC[kind])(d=d)
+    E = RS.EllipticSolver(problem, tag, seed=seed, delta_t=delta_t, N=N, lr=0.0, L=1, K=K, K_boundary=K_boundary,
+                          alpha=list(alpha), loss_method="diffusion", verbose=False)
+    E.V = RF.DenseNet(d_in=d, d_out=1, lr=0.0, arch=list(arch), seed=seed)
+    with pt.no_grad():                       # non-zero biases (the reference initialises them to 0)
+        pt.manual_seed(seed + 1)
+        for q in E.V.parameters():
+            if q.dim() == 1:
+                q.add_(0.05 * pt.randn_like(q))
+    theta0 = [q.detach().clone() for q in E.V.parameters()]
+    E.train()
+    grads = [q.grad.detach().clone() for q in E.V.parameters()]
+    loss = E.loss_log[0]
+    # replicate the reference's draw order (solver.py:630-631, :646-665, :687-708, :726)
+    pt.manual_seed(seed)
+    np.random.seed(seed)
+    op = orc.make_problem(kind, d)
+    Xb, X0, _ = orc.elliptic_draws(op, K, K_boundary, 0)
+    o = orc.elliptic_iteration(op, [q.clone() for q in theta0], Xb, X0, None, delta_t, N, alpha)
+    xis = pt.stack(o["xis"] + [pt.zeros(K, d)] * (N - len(o["xis"])))      # the reference stops drawing once all paths stopped
+    errs = dict(loss=abs(float(o["loss"]) - loss) / abs(loss), grad=rel(flat(o["grads"]), flat(grads)),
+                kcount=abs(o["K_count"] - E.K_log[0]), vl2=abs(float(o["V_L2"].mean()) - E.V_L2_log[0]) / abs(E.V_L2_log[0]))
+    print("%-28s loss=%.7e |grad|=%.6e K_count=%d/%d V_L2=%.6e oracle-vs-ref: %s" % (
+        tag, loss, np.linalg.norm(flat(grads)), E.K_log[0], K * N, E.V_L2_log[0],
+        " ".join("%s=%.1e" % kv for kv in errs.items())))
+    assert errs["loss"] < 1e-6 and errs["grad"] < 1e-5 and errs["kcount"] == 0 and errs["vl2"] < 1e-5, errs
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), kind=kind, d=d, K=K, K_boundary=K_boundary, N=N,
+                        delta_t=delta_t, arch=np.array(arch), alpha=np.array(alpha, dtype=np.float64), seed=seed,
+                        loss=np.float64(loss), K_count=E.K_log[0], V_L2=np.float64(E.V_L2_log[0]),
+                        theta=flat(theta0), grad=flat(grads), Xb=Xb.numpy(), X0=X0.numpy(), xis=xis.numpy(),
+                        X_end=o["X"].numpy(), Y_end=o["Y"].numpy(), stopped=o["stopped"].numpy())
+
+
+def elliptic_cases():
+    run_elliptic_case("ell_expsin_d10", "expball_sin", 10, 64, 20, 20, 1e-3, (30, 30), (0.1, 1.0))   # 'trajectory length' nb
+    run_elliptic_case("ell_expball_d5", "expball", 5, 48, 10, 25, 4e-3, (16, 12), (1.0, 1.0))
+    run_elliptic_case("ell_expsphere_d4", "expsphere", 4, 40, 10, 30, 1e-2, (12, 8, 8), (0.5, 2.0))  # all paths exit
+    run_elliptic_case("ell_helmholtz_d2", "helmholtz", 2, 64, 20, 30, 5e-3, (20, 20), (1.0, 1.0))    # square domain
+
+    def g5():       # 'Nonlinear toy problem - elliptic with Dirichlet' notebook: d=50, K=200, N=20, dt=1e-3
+        return RS.EllipticSolver(RP.ExponentialOnBallNonlinearSin(d=50), "G5", seed=42, delta_t=1e-3, N=20, lr=1e-3,
+                                 L=3, K=200, K_boundary=50, alpha=[1.0, 1.0], loss_method="diffusion", verbose=False)
+
+    def g5b():
+        return RS.EllipticSolver(RP.Helmholtz(d=2), "G5b", seed=42, delta_t=1e-3, N=20, lr=1e-3, L=3, K=200,
+                                 K_boundary=50, alpha=[1.0, 1.0], loss_method="diffusion", verbose=False)
+
+    run_loss_log_case("loop_G5", g5, 3)
+    run_loss_log_case("loop_G5b", g5b, 3)
+
+
 def run_is_case(tag, kind, d, pkw, K, solver_dt, is_dt, net):
     """do_importance_sampling_me (utilities.py:287-359) on an untrained control."""
     problem = make_ref_problem(kind, d, **pkw)
@@ -191,12 +248,16 @@ def run_loss_log_case(tag, build, L):
         if hasattr(S, "Phis") else np.sqrt(sum(float((q.grad ** 2).sum()) for q in S.V.parameters()))
     print("%-28s loss_log=%s |grad|=%.7e" % (tag, ["%.7e" % v for v in S.loss_log], g))
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), loss_log=np.array(S.loss_log, dtype=np.float64),
-                        grad_norm=np.float64(g), K_log=np.array(getattr(S, "K_log", []), dtype=np.int64))
+                        grad_norm=np.float64(g), K_log=np.array(getattr(S, "K_log", []), dtype=np.int64),
+                        V_L2_log=np.array(getattr(S, "V_L2_log", []), dtype=np.float64))
 
 
 def main():
     only = sys.argv[1:]
     global run_hjb_case
+    if only == ["elliptic"]:
+        elliptic_cases()
+        return
     if only:
         _orig = run_hjb_case
         def run_hjb_case(tag, *a, **k):
@@ -281,6 +342,7 @@ def main():
     run_loss_log_case("loop_G3a", g3("log-variance", True), 2)
     run_loss_log_case("loop_G3b", g3("relative_entropy", False), 2)
     run_loss_log_case("loop_G4", g4, 2)
+    elliptic_cases()
 
 
 if __name__ == "__main__":

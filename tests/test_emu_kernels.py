@@ -313,3 +313,71 @@ def test_diffusion_ragged_and_stopping():
     assert relerr(o["X"], m["X"]) < 1e-6 and relerr(o["Y"], m["Y"]) < 1e-5
     assert abs(o["loss"] - m["loss"]) < 1e-5 * abs(m["loss"])
     assert relerr(o["grad"], m["grad"]) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- elliptic (row f4)
+@pytest.mark.parametrize("tag", ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2"])
+def test_elliptic_golden_parity(tag):
+    """EllipticSolver iteration (solver.py:646-670, :687-790) on the reference's own draws: loss, K_count, V_L2,
+    end states, Y and the full gradient against golden vectors generated from the reference."""
+    g = load_golden(tag)
+    run = H.EllipticRunner(H.emu_lib())
+    mp = man.EllipticProblem(str(g["kind"]), int(g["d"]))
+    o = run.iteration(g, g["theta"].astype(np.float32), mp.g, alpha=tuple(g["alpha"]))
+    assert o["K_count"] == g["K_count"]
+    assert relerr(o["X"], g["X_end"]) < 1e-6
+    assert relerr(o["Y"], g["Y_end"]) < 1e-5
+    assert abs(o["VL2"].astype(np.float64).mean() - g["V_L2"]) < 1e-5 * g["V_L2"]
+    assert abs(o["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    assert relerr(o["grad"], g["grad"]) < 1e-5
+
+
+def test_elliptic_ragged_one_boundary_and_philox():
+    """K not a multiple of the tile, a one-sided box (solver.py:755-756), h == 0, a 3-hidden-layer net, against the
+    fp64 restatement; then the same with in-kernel Philox increments read back through pspde_philox_dump."""
+    rng = np.random.default_rng(11)
+    K, d, N, dt, arch = 45, 3, 9, 0.02, (7, 10, 6)
+    dims = [d] + list(arch) + [1]
+    n_theta = sum((sum(dims[:i + 1]) + 1) * dims[i + 1] for i in range(len(dims) - 1))
+    theta = (rng.standard_normal(n_theta) * 0.3).astype(np.float32)
+    X0 = rng.uniform(-1, 1, (K, d)).astype(np.float32)
+    xis = rng.standard_normal((N, K, d)).astype(np.float32)
+    lib = H.emu_lib()
+    run = H.EllipticRunner(lib)
+    pack = H.heat_pack(d)
+    for one_boundary, h_id in ((True, L.H_ZERO), (False, L.H_EXP_NONLINEAR)):
+        ell = L.make_elliptic(L.DOMAIN_BOX, x_l=-1.0, x_r=1.0, one_boundary=one_boundary, h_id=h_id, h_param=(0.5, 0, 0))
+        mp = man.EllipticProblem("expball", d, alpha=0.5)
+        mp.boundary, mp.one_boundary, mp.X_l, mp.X_r = "square", one_boundary, -1.0, 1.0
+        if h_id == L.H_ZERO:
+            mp.h = lambda x, y: np.zeros(x.shape[0])
+            mp.h_y = lambda x, y: np.zeros(x.shape[0])
+        for noise in (L.NOISE_INJECT, L.NOISE_PHILOX):
+            cfg = H.elliptic_cfg(K, d, N, dt, arch, noise=noise, seed=7, offset=3, k_offset=5)
+            xs = xis
+            if noise == L.NOISE_PHILOX:
+                xs = np.zeros((N, K, d), np.float32)
+                L.check(lib, lib.pspde_philox_dump(ctypes.byref(cfg), H.ptr(xs), None))
+            f = run.fwd(cfg, ell, theta, pack, X0, xs if noise == L.NOISE_INJECT else None)
+            r = f["VE"].astype(np.float64) - f["Y"]
+            w = 2 * r / K
+            grad = run.bwd(cfg, ell, theta, pack, X0, xs if noise == L.NOISE_INJECT else None, -w, w, -w)
+            net = man.Net("densenet", dims, theta.astype(np.float64))
+            m = man.elliptic(mp, net, X0[:1].astype(np.float64), X0.astype(np.float64), xs.astype(np.float64), dt, N,
+                             alpha=(1.0, 0.0))
+            assert 0 < int(f["stats"][1]) < K * N and int(f["stats"][1]) == m["K_count"]
+            assert relerr(f["X"], m["X"]) < 1e-6 and relerr(f["Y"], m["Y"]) < 1e-5
+            assert relerr(f["VL2"], m["V_L2"]) < 1e-5
+            assert relerr(grad, m["grad"]) < 2e-5
+
+
+def test_elliptic_error_paths():
+    lib = H.emu_lib()
+    cfg = H.elliptic_cfg(8, 3, 2, 0.01, (4, 4))
+    ell = L.make_elliptic(7)
+    assert lib.pspde_elliptic_workspace_bytes(ctypes.byref(cfg), ctypes.byref(ell)) == 0
+    assert b"domain" in lib.pspde_last_error()
+    bad = H.diffusion_cfg(8, 3, 2, 0.01, (4, 4))              # TIME_LAST network on the elliptic entry point
+    ell = L.make_elliptic(L.DOMAIN_SPHERE)
+    assert lib.pspde_elliptic_workspace_bytes(ctypes.byref(bad), ctypes.byref(ell)) == 0
+    assert b"TIME_NONE" in lib.pspde_last_error()

@@ -482,3 +482,104 @@ def test_diffusion_small_and_ragged_against_manual(K, N, Kb):
     assert int(k_count) == m["K_count"] and n_bad == 0
     assert abs(loss - m["loss"]) < TOL * abs(m["loss"])
     assert relerr(G._theta.grad.cpu().numpy(), m["grad"]) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- elliptic (row f4)
+ELL_PROBLEMS = {"expsphere": "ExponentialOnSphere", "expball": "ExponentialOnBallNonlinear",
+                "expball_sin": "ExponentialOnBallNonlinearSin", "helmholtz": "Helmholtz"}
+
+
+def make_elliptic_solver(kind, d, K, Kb, N, dt, arch, alpha, lr=0.0, L=1, noise="inject", seed=42):
+    import pspde
+    prob = getattr(pspde, ELL_PROBLEMS[kind])(d=d, device="cuda")
+    E = pspde.EllipticSolver(prob, "t", seed=seed, delta_t=dt, N=N, lr=lr, L=L, K=K, K_boundary=Kb,
+                             alpha=list(alpha), loss_method="diffusion", verbose=False, noise=noise)
+    if arch is not None:
+        E.V = pspde.DenseNet(d_in=d, d_out=1, lr=lr, arch=list(arch), seed=seed)
+    return E
+
+
+@pytest.mark.parametrize("tag", ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2"])
+def test_elliptic_golden_parity(tag):
+    """One EllipticSolver iteration on the reference's own draws (solver.py:646-665, :687-708, :726): loss, K_log,
+    V_L2, end states, Y and the full gradient against the golden vectors generated from the reference."""
+    from pspde.general_solver import DiffusionCall
+    g = load_golden(tag)
+    d, K, N = int(g["d"]), int(g["K"]), int(g["N"])
+    E = make_elliptic_solver(str(g["kind"]), d, K, int(g["K_boundary"]), N, float(g["delta_t"]), g["arch"],
+                             g["alpha"])
+    eng = E._get_engine()
+    with pt.no_grad():
+        E._theta.copy_(pt.tensor(g["theta"]).cuda())          # the fixture has non-zero biases
+    call = DiffusionCall(pt.tensor(g["X0"]).cuda(), None, pt.tensor(g["xis"]).cuda(), 0)
+    call.Xb = pt.tensor(g["Xb"]).cuda()
+    loss, _, k_count, n_bad, vl2, lb = E.gradient_descent(call).tolist()
+    assert int(k_count) == g["K_count"] and n_bad == 0
+    assert relerr(eng.X_end.cpu().numpy(), g["X_end"]) < 1e-6
+    assert relerr(eng.Y.cpu().numpy(), g["Y_end"]) < TOL
+    assert abs(vl2 / K - g["V_L2"]) < TOL * g["V_L2"]
+    assert abs(loss - g["loss"]) < TOL * abs(g["loss"])
+    assert relerr(E._theta.grad.cpu().numpy(), g["grad"]) < TOL
+
+
+@pytest.mark.parametrize("tag,kind,d", [("loop_G5", "expball_sin", 50), ("loop_G5b", "helmholtz", 2)])
+def test_elliptic_loss_log(tag, kind, d):
+    """Three Adam iterations of EllipticSolver (notebook configuration d = 50, K = 200, N = 20; square domain with
+    the numpy-shuffled boundary samples) reproduce the reference's loss_log, K_log and V_L2_log."""
+    g = load_golden(tag)
+    E = make_elliptic_solver(kind, d, 200, 50, 20, 1e-3, None, [1.0, 1.0], lr=1e-3, L=3)
+    E.train()
+    assert E.K_log == [int(v) for v in g["K_log"]]
+    assert relerr(E.loss_log, g["loss_log"]) < 2e-5
+    assert relerr(E.V_L2_log, g["V_L2_log"]) < 2e-5
+    assert abs(float(E._theta.grad.norm()) - g["grad_norm"]) < 1e-4 * g["grad_norm"]
+
+
+def test_elliptic_full_size_properties_and_training():
+    """K = 2^14 per GPU, d = 50, the notebook's problem: the Philox path is deterministic, independent of the
+    sharding and linear in the cotangents; training reduces the loss and the error of V against exp(|x|^2)."""
+    import pspde
+    from pspde.elliptic_solver import EllipticEngine
+    d, N, K = 50, 20, 16384
+    prob = pspde.ExponentialOnBallNonlinearSin(d=d, device="cuda")
+    V = pspde.DenseNet(d_in=d, d_out=1, lr=1e-3, seed=42).cuda()
+    theta = pt.cat([q.detach().reshape(-1) for q in V.parameters()]).contiguous()
+    eng = EllipticEngine(prob, V.net_spec()[1], K, N, 1e-3, k_offset=0, seed=7)
+    X0, _ = eng.sample(1.0, 3)
+    eng.forward(theta, X0, None, None, 3)
+    Y, VE, st, vl2 = eng.Y.clone(), eng.VE.clone(), eng.stats.clone(), eng.VL2.clone()
+    eng.forward(theta, X0, None, None, 3)
+    assert pt.equal(Y, eng.Y) and pt.equal(st, eng.stats) and pt.equal(vl2, eng.VL2)
+    r = (VE - Y).double()
+    assert abs(float((r * r).sum()) - st[0].item()) < 1e-9 * st[0].item()
+    assert 0 < st[1].item() < K * N                               # some paths leave the ball
+    assert float((eng.X_end ** 2).sum(1).sqrt().max()) < 1.0 + 6 * np.sqrt(2 * 1e-3 * d)   # one step past the sphere at most
+    half = EllipticEngine(prob, V.net_spec()[1], K // 2, N, 1e-3, k_offset=K // 2, seed=7)
+    X0h, _ = half.sample(1.0, 3)
+    assert pt.equal(X0h, X0[K // 2:])
+    half.forward(theta, X0h, None, None, 3)
+    assert pt.equal(half.Y, Y[K // 2:]) and pt.equal(half.VL2, vl2[K // 2:])
+    w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    gs = []
+    for (a, b, c) in ((w1, w2, w1), (w2, w1, -w2), (w1 + 2 * w2, w2 + 2 * w1, w1 - 2 * w2)):
+        gr = pt.empty(eng.n_theta, device="cuda")
+        eng.backward(theta, X0, None, None, 3, a, b, c, gr)
+        gs.append(gr)
+    assert relerr((gs[0] + 2 * gs[1]).cpu().numpy(), gs[2].cpu().numpy()) < 2e-5
+    E = pspde.EllipticSolver(prob, "ell", seed=42, delta_t=1e-3, N=N, lr=1e-3, L=1, K=K, K_boundary=50,
+                             alpha=[1.0, 1.0], verbose=False, K_test_log=2000)
+    E.train()
+    e0 = E.V_L2_error()
+    E.L = 150
+    E.train()
+    assert all(np.isfinite(E.loss_log)) and E.loss_log[-1] < 0.5 * E.loss_log[0]
+    assert E.V_L2_error() < e0 and len(E.V_test_L2) == len(E.loss_log)
+
+
+def test_elliptic_off_path_options_raise():
+    import pspde
+    prob = pspde.ExponentialOnBallNonlinearSin(d=4, device="cuda")
+    for kw in (dict(loss_method="PINN"), dict(approx_method="Z"), dict(boundary_type="Neumann"),
+               dict(adaptive_forward_process=True), dict(loss_with_stopped=True)):
+        with pytest.raises(NotImplementedError):
+            pspde.EllipticSolver(prob, "x", K=8, N=2, verbose=False, **kw)

@@ -202,3 +202,54 @@ def test_analytic_llgc_value():
     V00 = -(d / 4) * (1 - np.exp(-2 * T))
     assert abs(D.mean() - (-V00)) < 5e-3 * abs(V00)
     assert D.std() < 2e-2 * abs(V00)
+
+
+# ---------------------------------------------------------------------------------------------- elliptic (row f4)
+ELL_TAGS = ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2"]
+
+
+def ell_params(g):
+    d, arch = int(g["d"]), [int(a) for a in g["arch"]]
+    dims = [d] + arch + [1]
+    params, off = [], 0
+    for i in range(len(dims) - 1):
+        for s in ((sum(dims[:i + 1]), dims[i + 1]), (dims[i + 1],)):
+            n = int(np.prod(s))
+            params.append(pt.tensor(g["theta"][off:off + n].reshape(s)))
+            off += n
+    return dims, params
+
+
+@pytest.mark.parametrize("tag", ELL_TAGS)
+def test_elliptic_port_and_manual(tag):
+    """EllipticSolver iteration (solver.py:646-670, :687-790): the PyTorch-CPU restatement and the explicit fp64
+    gradient formulas against the golden vectors generated from the reference."""
+    g = load_golden(tag)
+    d, kind = int(g["d"]), str(g["kind"])
+    dims, params = ell_params(g)
+    alpha = tuple(float(a) for a in g["alpha"])
+    o = orc.elliptic_iteration(orc.make_problem(kind, d), params, pt.tensor(g["Xb"]), pt.tensor(g["X0"]),
+                               pt.tensor(g["xis"]), g["delta_t"], int(g["N"]), alpha)
+    assert abs(float(o["loss"]) - g["loss"]) < 1e-6 * g["loss"]
+    assert o["K_count"] == g["K_count"]
+    assert abs(float(o["V_L2"].mean()) - g["V_L2"]) < 1e-6 * g["V_L2"]
+    assert relerr(np.concatenate([q.reshape(-1).numpy() for q in o["grads"]]), g["grad"]) < 2e-6
+    assert 0 < int(o["stopped"].sum())                       # the exit logic is exercised
+    net = man.Net("densenet", dims, g["theta"])
+    m = man.elliptic(man.EllipticProblem(kind, d), net, g["Xb"].astype(np.float64), g["X0"].astype(np.float64),
+                     g["xis"].astype(np.float64), g["delta_t"], int(g["N"]), alpha)
+    assert m["K_count"] == g["K_count"]
+    assert abs(m["loss"] - g["loss"]) < 1e-5 * g["loss"]
+    assert abs(m["V_L2"].mean() - g["V_L2"]) < 1e-5 * g["V_L2"]
+    assert relerr(m["grad"], g["grad"]) < 2e-5
+    assert relerr(m["X"], g["X_end"]) < 1e-6 and relerr(m["Y"], g["Y_end"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,kind,d", [("loop_G5", "expball_sin", 50), ("loop_G5b", "helmholtz", 2)])
+def test_elliptic_training_loop_pins(tag, kind, d):
+    """Whole-loop pins: torch + numpy RNG order, rollout and Adam reproduce the reference's loss_log and K_log."""
+    g = load_golden(tag)
+    params = orc.densenet_init(d, 1, seed=42)
+    ll, kc = orc.elliptic_train_loop(orc.make_problem(kind, d), params, 200, 50, 20, 1e-3, 3, 1e-3, seed=42)
+    np.testing.assert_allclose(ll, g["loss_log"], rtol=2e-6)
+    assert kc == [int(v) for v in g["K_log"]]
