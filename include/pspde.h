@@ -124,10 +124,25 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
  *   zeta = wY_k (sqrt(dt) xi_{n+1} + [adaptive == 0] Z dt) + wZ_k Z dt,
  * wY = dLoss/dY_N, wZ = dLoss/dZsum (nullable = 0), both of length K_local.  The rollout is recomputed
  * from (x0, xi | Philox); nothing of size K x N x d is kept in HBM.  grad_theta (pspde_theta_size floats)
- * is overwritten. */
+ * is overwritten.
+ * Two kernel families implement it: for the tensor-core shape class the trajectories of one wave of
+ * tiles (<= one 128-path tile per SM) are regenerated by the tensor-core forward kernel, which checkpoints the
+ * per-step operand rows in the workspace, and a gradient kernel streams them back (pspde_grad_from_ckpt); any other
+ * configuration, or a workspace smaller than pspde_workspace_bytes(), runs the FP32-FMA recompute kernel. */
 int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
                                const float* xi, const float* wY, const float* wZ, float* grad_theta,
                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Second half of the checkpointed detached backward, exposed for tests: accumulates dLoss/dtheta from the operand
+ * rows [a0 | h1 | h2 | zeta] of n_slots tiles of 128 paths x cfg->N steps.  Layout of ckpt (device, fp32): float4
+ * column groups with the 128 paths of a tile contiguous,
+ *     ckpt[(((slot * N + n) * C4 + c4) * 128 + path) * 4 + i],   C4 = 2 * (s0 / 4) + 16,
+ * groups [0, s0/4) = a0 = [X_n | t_n | 1 | 0..], then 8 groups h1, 8 groups h2 (hidden widths padded to 32, with the
+ * constant-1 column of MySequential), then s0/4 groups zeta (d used); s0 = the input segment padded to a multiple
+ * of 8.  pspde_rollout_bwd_detached fills this buffer with the tensor-core forward kernel, one wave of tiles (at
+ * most one per SM) at a time, so its size is independent of K.  Networks: 2 hidden layers of width <= 32 (31). */
+int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* ckpt, int n_slots, int s0,
+                         float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Forward + backward for detach_forward=False (solver.py:451-469 without the detach, :221): per tile of paths the
  * states X_n are checkpointed to the workspace and the discrete adjoint runs backwards in time in the same kernel.

@@ -164,6 +164,10 @@ static inline int launch_rollout(const Plan& pl, const RolloutParams& p, void* s
 
 
 
+// gradient accumulation from the checkpoint buffer (grad_kernels.cuh); grid CTAs, n_items work items
+int pspde_launch_grad_256(const Plan& pl, const pspde::RolloutParams& p, int grid, int n_items, void* stream);
+int pspde_launch_grad_512(const Plan& pl, const pspde::RolloutParams& p, int grid, int n_items, void* stream);
+
 // defined in api_bwd*.cu / api_att*.cu (one translation unit per thread count so that the template instantiations
 // compile in parallel)
 int pspde_launch_bwd_256(const Plan& pl, const pspde::RolloutParams& p, void* stream);

@@ -1,6 +1,7 @@
 // api_core.cu -- extern "C" entry points declared in include/pspde.h.
 #include "api_common.h"
 #include "rollout_tc_kernels.cuh"
+#include "grad_kernels.cuh"
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
@@ -33,6 +34,35 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
   return launch_rollout<512, false, 1>(pl, p, stream);
 }
 
+// ---- checkpointed detached backward: tensor-core forward (CKPT) + gradient accumulation, one wave of tiles at a time
+struct CkptPlan {
+  int n_tiles128, wave, c4, s0, grid_b;
+  size_t ckpt_bytes, grad_bytes;
+};
+
+static int launch_grad(const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream) {
+  if (pl.T == 256) return pspde_launch_grad_256(pl, p, grid, n_items, stream);
+  if (pl.T == 512) return pspde_launch_grad_512(pl, p, grid, n_items, stream);
+  return fail(-13, "internal: no gradient kernel for T=%d", pl.T);
+}
+
+#if !defined(PSPDE_EMULATE)
+// true if the detached backward of cfg can take the checkpointed path (same shape class as the tensor-core forward)
+static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan& cp) {
+  if (cfg->N < 1 || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return false;
+  const int sms = pspde_sm_count();
+  cp.n_tiles128 = (cfg->K_local + kTcP - 1) / kTcP;
+  cp.wave = cp.n_tiles128 < sms ? cp.n_tiles128 : sms;
+  cp.c4 = tc_ckpt_c4(tg);
+  cp.s0 = tg.s0;
+  const long long items = (long long)cp.wave * cfg->N * (kTcP / kP);
+  cp.grid_b = items < sms ? (int)items : sms;
+  cp.ckpt_bytes = align256((size_t)cp.wave * cfg->N * cp.c4 * kTcP * 16);
+  cp.grad_bytes = align256((size_t)cp.grid_b * pl.n_theta_total * sizeof(float));
+  return true;
+}
+#endif
+
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
@@ -55,9 +85,21 @@ size_t pspde_workspace_bytes(const pspde_cfg* cfg) {
   Plan pl;
   size_t need = 0;
   if (make_plan(cfg, false, false, pl) == 0) need = pl.stats_bytes;
-  if (make_plan(cfg, true, false, pl) == 0) need = pl.stats_bytes + pl.grad_bytes;
-  if (make_plan(cfg, true, true, pl) == 0)
-    need = pl.stats_bytes + pl.grad_bytes + align256((size_t)pl.grid * cfg->N * kP * cfg->d * sizeof(float));
+  if (make_plan(cfg, true, false, pl) == 0) {
+    need = pl.stats_bytes + pl.grad_bytes;
+#if !defined(PSPDE_EMULATE)
+    TcGeom tg;
+    CkptPlan cp;
+    if (ckpt_plan(cfg, pl, tg, cp)) {
+      const size_t n2 = pl.stats_bytes + cp.grad_bytes + cp.ckpt_bytes;
+      if (n2 > need) need = n2;
+    }
+#endif
+  }
+  if (make_plan(cfg, true, true, pl) == 0) {
+    const size_t n3 = pl.stats_bytes + pl.grad_bytes + align256((size_t)pl.grid * cfg->N * kP * cfg->d * sizeof(float));
+    if (n3 > need) need = n3;
+  }
   return need ? need + 256 : 0;
 }
 
@@ -115,6 +157,46 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY; p.wZ = wZ;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
+#if !defined(PSPDE_EMULATE)
+  {
+    // Kernel choice (both are this library's CUDA kernels): the checkpointed path -- tensor-core forward that leaves
+    // the operand rows of one wave of tiles in the workspace + gradient accumulation kernel -- for the tensor-core
+    // shape class when the workspace holds the wave, else the FP32-FMA recompute kernel.  PSPDE_BWD_PATH=simt forces
+    // the recompute kernel (A/B tests); PSPDE_BWD_PATH=ckpt makes an ineligible configuration an error.
+    TcGeom tg;
+    CkptPlan cp;
+    const char* path = getenv("PSPDE_BWD_PATH");
+    const bool force = path && !strcmp(path, "ckpt");
+    bool eligible = ckpt_plan(cfg, pl, tg, cp);
+    if (force && !eligible) return fail(-6, "configuration is outside the checkpointed backward's shape class");
+    if (eligible && workspace_bytes < pl.stats_bytes + cp.grad_bytes + cp.ckpt_bytes) {
+      if (force) return fail(-7, "workspace too small for the checkpointed backward (%zu < %zu)", workspace_bytes,
+                             pl.stats_bytes + cp.grad_bytes + cp.ckpt_bytes);
+      eligible = false;
+    }
+    if (eligible && !(path && !strcmp(path, "simt"))) {
+      if (pspde_memset0(p.grad_partial, (size_t)cp.grid_b * pl.n_theta_total * sizeof(float), stream))
+        return fail(-12, "memset of the gradient partials failed");
+      p.ckpt = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes + cp.grad_bytes);
+      p.ckpt_c4 = cp.c4; p.ckpt_s0 = cp.s0;
+      for (int t0 = 0; t0 < cp.n_tiles128; t0 += cp.wave) {
+        const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
+        p.tile0 = t0; p.n_tiles = nt;
+        const cudaError_t ce = tc_launch_t<true>(p, tg, nt, (cudaStream_t)stream);
+        g_launches++;
+        if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
+        const long long items = (long long)nt * cfg->N * (kTcP / kP);
+        rc = launch_grad(pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream);
+        if (rc) return rc;
+      }
+      const int n = pl.n_theta_total;
+      PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, cp.grid_b, n, grad_theta);
+      g_launches++;
+      if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
+      return 0;
+    }
+  }
+#endif
   if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
   if (pl.T == 256) rc = pspde_launch_bwd_256(pl, p, stream);
@@ -123,6 +205,35 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
   if (rc) return rc;
   const int n = pl.n_theta_total;
   PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, pl.grid, n, grad_theta);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
+  return 0;
+}
+
+int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* ckpt, int n_slots, int s0,
+                         float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, true, false, pl);
+  if (rc) return rc;
+  if (!theta || !ckpt || !grad_theta || n_slots < 1 || s0 < pl.g.seg_len[0] || (s0 & 7)) return fail(-1, "bad arguments");
+  if (pl.g.L != 3 || pl.g.time_mode == TIME_NONE || pl.g.seg_len[1] > 32 || pl.g.seg_len[2] > 32)
+    return fail(-6, "configuration is outside the checkpointed backward's shape class");
+  const int sms = pspde_sm_count();
+  const long long items = (long long)n_slots * cfg->N * (kCkP / kP);
+  const int grid = items < sms ? (int)items : sms;
+  const size_t gbytes = align256((size_t)grid * pl.n_theta_total * sizeof(float));
+  if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta;
+  p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
+  p.ckpt = const_cast<float*>(ckpt); p.ckpt_c4 = 2 * (s0 >> 2) + 16; p.ckpt_s0 = s0;
+  if (pspde_memset0(p.grad_partial, (size_t)grid * pl.n_theta_total * sizeof(float), stream))
+    return fail(-12, "memset of the gradient partials failed");
+  rc = launch_grad(pl, p, grid, (int)items, stream);
+  if (rc) return rc;
+  const int n = pl.n_theta_total;
+  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, grid, n, grad_theta);
   g_launches++;
   if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
   return 0;

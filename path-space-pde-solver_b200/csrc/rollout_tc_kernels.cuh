@@ -93,7 +93,12 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
 // One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread 0
 // additionally issues the MMAs: after the last arrival on an "operands ready" barrier it launches the group and
 // commits it to the matching "group done" barrier; everybody (thread 0 included) then waits for that one.
-template <int NG>
+// CKPT = true (detached backward, first half): the same rollout, but instead of the per-path outputs it writes the
+// operand rows of the gradient accumulation for every step -- the network input a0 = [X_n | t_n | 1], the hidden
+// activations h1, h2 and the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt -- to the
+// per-wave checkpoint buffer (RolloutParams::ckpt) that grad_kernel consumes.  Rows with zero cotangents (padding,
+// trajectories dropped by the host because their D was non-finite) are written as zeros: inert in the gradient.
+template <int NG, bool CKPT>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const RolloutParams prm, const TcGeom tg) {
   extern __shared__ float4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
@@ -162,8 +167,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   float X[NG][4];
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
-    const int k = tile * kTcP + p;
+    const int k = (prm.tile0 + tile) * kTcP + p;
     const bool in = k < prm.K_local;
+    float wy = 0.f, wz = 0.f;
+    if (CKPT && in) { wy = prm.wY ? __ldg(prm.wY + k) : 0.f; wz = prm.wZ ? __ldg(prm.wZ + k) : 0.f; }
+    const bool live = CKPT && (wy != 0.f || wz != 0.f);
+    float4* ck = CKPT ? reinterpret_cast<float4*>(prm.ckpt) + (size_t)tile * N * prm.ckpt_c4 * kTcP + p : nullptr;
     const unsigned kglob = (unsigned)(prm.k_offset + k);
     // ---- tile init (solver.py:365-376) and the first a0
 #pragma unroll
@@ -245,6 +254,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + HC * part;
         tc::tmem_st8(th, hi);
         tc::tmem_st8(th + tg.hp, lo);
+        if (CKPT) {                          // h = hi + lo exactly
+          float4* o = ck + (size_t)(n * prm.ckpt_c4 + (tg.s0 >> 2) + (tg.hp >> 2) * hl + (HC >> 2) * part) * kTcP;
+#pragma unroll
+          for (int u = 0; u < HC / 4; ++u)
+            o[u * kTcP] = live ? make_float4(hi[4 * u] + lo[4 * u], hi[4 * u + 1] + lo[4 * u + 1], hi[4 * u + 2] + lo[4 * u + 2],
+                                             hi[4 * u + 3] + lo[4 * u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&bars[1 + hl]);
@@ -285,6 +301,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
               const float4 A4 = ld4(a_d + j0), B4 = ld4(b_d + j0), P4 = ld4(p_d + j0), K4 = ld4(kap + j0);
               const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
               const float pv[4] = {P4.x, P4.y, P4.z, P4.w}, kv[4] = {K4.x, K4.y, K4.z, K4.w};
+              if (CKPT) {                    // operand rows of this step: a0 = X_n (own columns) and zeta
+                const float kA = adaptive ? 0.f : dt;
+                float ze[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float z = Z[4 * u + i], ee = E[gi][i];
+                  ze[i] = (j0 + i < d) ? wy * (sq * ee + kA * z) + wz * (dt * z) : 0.f;
+                }
+                float4* o = ck + (size_t)(n * prm.ckpt_c4 + (g_lo + gi)) * kTcP;
+                o[0] = live ? make_float4(X[gi][0], X[gi][1], X[gi][2], X[gi][3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[(size_t)((tg.s0 >> 2) + 2 * (tg.hp >> 2)) * kTcP] =
+                    live ? make_float4(ze[0], ze[1], ze[2], ze[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float z = Z[4 * u + i], x = X[gi][i], ee = E[gi][i];
@@ -394,20 +423,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
 }
 
 // NG instantiations: the smallest one that holds tg.ng column groups per thread
-template <int NG>
+template <int NG, bool CKPT>
 inline cudaError_t tc_launch_one(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
+  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
   if (e != cudaSuccess) return e;
-  rollout_tc_fwd_kernel<NG><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
+  rollout_tc_fwd_kernel<NG, CKPT><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
   return cudaGetLastError();
 }
-inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  if (tg.ng <= 1) return tc_launch_one<1>(p, tg, grid, stream);
-  if (tg.ng <= 2) return tc_launch_one<2>(p, tg, grid, stream);
-  if (tg.ng <= 4) return tc_launch_one<4>(p, tg, grid, stream);
-  if (tg.ng <= 7) return tc_launch_one<7>(p, tg, grid, stream);
-  return tc_launch_one<kTcMaxG>(p, tg, grid, stream);
+template <bool CKPT>
+inline cudaError_t tc_launch_t(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  if (tg.ng <= 1) return tc_launch_one<1, CKPT>(p, tg, grid, stream);
+  if (tg.ng <= 2) return tc_launch_one<2, CKPT>(p, tg, grid, stream);
+  if (tg.ng <= 4) return tc_launch_one<4, CKPT>(p, tg, grid, stream);
+  if (tg.ng <= 7) return tc_launch_one<7, CKPT>(p, tg, grid, stream);
+  return tc_launch_one<kTcMaxG, CKPT>(p, tg, grid, stream);
 }
+inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  return tc_launch_t<false>(p, tg, grid, stream);
+}
+// column groups (float4) per (tile slot, step) of the checkpoint buffer: a0 (s0) | h1 (hp) | h2 (hp) | zeta (s0)
+inline int tc_ckpt_c4(const TcGeom& tg) { return 2 * (tg.s0 >> 2) + 2 * (tg.hp >> 2); }
 
 }  // namespace pspde
 #endif  // !PSPDE_EMULATE

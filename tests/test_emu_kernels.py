@@ -381,3 +381,47 @@ def test_elliptic_error_paths():
     ell = L.make_elliptic(L.DOMAIN_SPHERE)
     assert lib.pspde_elliptic_workspace_bytes(ctypes.byref(bad), ctypes.byref(ell)) == 0
     assert b"TIME_NONE" in lib.pspde_last_error()
+
+
+# ---------------------------------------------------------------------------------------------- checkpointed backward
+@pytest.mark.parametrize("kind,d,hid", [("densenet", 10, (30, 30)), ("densenet", 7, (12, 20)), ("mlp_tanh", 6, (30, 30))])
+def test_grad_from_checkpoint_rows(kind, d, hid):
+    """grad_kernel (second half of the checkpointed detached backward) is a pure function of the operand rows
+    [a0 | h1 | h2 | zeta] and theta: dtheta = sum_rows J_theta Z(a0)' zeta.  Rows for 2 tile slots x N steps are built
+    with the fp64 network (oracle/manual.py) and random cotangents; padding rows are zero."""
+    rng = np.random.default_rng(d)
+    lib = H.emu_lib()
+    N, n_slots, K = 3, 2, 200                       # 200 of the 256 rows are live
+    dims = [d + 1, hid[0], hid[1], d]
+    net_id = L.NET_DENSENET if kind == "densenet" else L.NET_MLP_TANH
+    cfg = L.make_cfg(K, d, N, 0.01, L.PROBLEM_OU, net_id, dims, L.TIME_FIRST)
+    n_theta = lib.pspde_theta_size(ctypes.byref(cfg))
+    theta = (rng.standard_normal(n_theta) * 0.3).astype(np.float32)
+    net = man.Net(kind, dims, theta.astype(np.float64))
+    s0 = (d + 2 + 7) // 8 * 8
+    C4 = 2 * (s0 // 4) + 16
+    ck = np.zeros((n_slots, N, C4, 128, 4), np.float32)
+    grad = np.zeros(n_theta)
+    for slot in range(n_slots):
+        live = min(128, K - 128 * slot)
+        for n in range(N):
+            X = rng.standard_normal((live, d)).astype(np.float32)
+            t = np.full((live, 1), 0.01 * n, np.float32)
+            zeta = (rng.standard_normal((live, d)) * 0.1).astype(np.float32)
+            _, tape = net.forward(np.concatenate([t, X], 1).astype(np.float64))
+            grad += net.vjp(tape, zeta.astype(np.float64))
+            row = np.zeros((live, 4 * C4), np.float32)
+            row[:, :d], row[:, d:d + 1], row[:, d + 1] = X, t, 1.0
+            for l in (0, 1):
+                h = tape[l][2].astype(np.float32)
+                row[:, s0 + 32 * l:s0 + 32 * l + hid[l]] = h
+                if kind == "mlp_tanh":
+                    row[:, s0 + 32 * l + hid[l]] = 1.0           # the constant-1 column that carries the next bias
+            row[:, s0 + 64:s0 + 64 + d] = zeta
+            ck[slot, n, :, :live, :] = row.reshape(live, C4, 4).transpose(1, 0, 2)
+    out = np.full(n_theta, np.nan, np.float32)
+    ws = np.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 8 * n_theta * 64, np.float64)
+    rc = lib.pspde_grad_from_ckpt(ctypes.byref(cfg), H.ptr(theta), H.ptr(ck), n_slots, s0, H.ptr(out), H.ptr(ws),
+                                  ws.nbytes, None)
+    L.check(lib, rc)
+    assert relerr(out, grad) < 1e-5

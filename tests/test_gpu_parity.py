@@ -583,3 +583,68 @@ def test_elliptic_off_path_options_raise():
                dict(adaptive_forward_process=True), dict(loss_with_stopped=True)):
         with pytest.raises(NotImplementedError):
             pspde.EllipticSolver(prob, "x", K=8, N=2, verbose=False, **kw)
+
+
+# ---------------------------------------------------------------------------------------------- checkpointed backward
+@pytest.mark.parametrize("kind,d,K,opts", [("llgc", 100, 20000, {}), ("lqgc", 10, 333, {}), ("llgc", 3, 129, {}),
+                                           ("dwm", 50, 300, {}), ("dwm", 7, 65, {}),
+                                           ("lqgc", 12, 500, dict(adaptive=False, wZ=True)),
+                                           ("llgc", 20, 260, dict(inject=True, dead=True))])
+def test_checkpointed_backward_matches_recompute_backward(monkeypatch, kind, d, K, opts):
+    """The checkpointed detached backward (tensor-core forward that leaves the operand rows of one wave of tiles in
+    the workspace + gradient kernel) against the FP32-FMA recompute kernel on identical noise and cotangents:
+    C2 shape over more than one wave (K > 148 * 128) with a ragged last tile, d % 4 != 0, MySequential, the
+    non-adaptive zeta with a Z_sum cotangent, injected noise and rows with zero weight (dropped trajectories)."""
+    import pspde
+    from pspde import _lib
+    from pspde.fused import Call, RolloutEngine
+    N = 50 if kind == "dwm" else 12              # the double-well drift (kappa = 5) is stiff: dt = 0.02
+    if kind == "dwm":
+        prob = pspde.DoubleWell_multidim(d=d, d_1=d // 3, d_2=d - d // 3, T=1.0, eta=3, kappa=5, device="cuda")
+        net, net_id = pspde.MySequential(d_in=d + 1, d_out=d, lr=1e-3, seed=123).cuda(), _lib.NET_MLP_TANH
+    else:
+        prob = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC}[kind](d=d, T=1.0, device="cuda")
+        net, net_id = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42).cuda(), _lib.NET_DENSENET
+    theta = pt.cat([q.detach().reshape(-1) for q in net.parameters()]).contiguous()
+    eng = RolloutEngine(prob, net_id, net.net_spec()[1], _lib.TIME_FIRST, K, N, 1.0 / N,
+                        adaptive=opts.get("adaptive", True), seed=5)
+    gen = pt.Generator(device="cuda").manual_seed(K)
+    wY = pt.randn(K, device="cuda", generator=gen) / K
+    wZ = pt.randn(K, device="cuda", generator=gen) / K if opts.get("wZ") else None
+    if opts.get("dead"):
+        wY[::7] = 0.0
+    xi = pt.randn(K, d, N + 1, device="cuda", generator=gen) if opts.get("inject") else None
+    eng.forward(theta, None, Call(offset=9, xi=xi))               # as the host does: non-finite trajectories get zero weight
+    ok = pt.isfinite(eng.Y_N) & pt.isfinite(eng.gX)
+    wY = pt.where(ok, wY, pt.zeros_like(wY))
+    if wZ is not None:
+        wZ = pt.where(ok, wZ, pt.zeros_like(wZ))
+    assert int(ok.sum()) > 0.9 * K
+    grads = {}
+    for path in ("simt", "ckpt"):
+        monkeypatch.setenv("PSPDE_BWD_PATH", path)
+        g = pt.full((eng.n_theta,), float("nan"), device="cuda")
+        eng.backward_detached(theta, wY, wZ, Call(offset=9, xi=xi), g)
+        pt.cuda.synchronize()
+        grads[path] = g.cpu().numpy()
+    assert np.all(np.isfinite(grads["ckpt"]))
+    assert relerr(grads["ckpt"], grads["simt"]) < TOL
+    monkeypatch.setenv("PSPDE_BWD_PATH", "ckpt")                  # deterministic
+    g2 = pt.empty(eng.n_theta, device="cuda")
+    eng.backward_detached(theta, wY, wZ, Call(offset=9, xi=xi), g2)
+    assert np.array_equal(g2.cpu().numpy(), grads["ckpt"])
+
+
+def test_checkpointed_backward_rejects_ineligible_configuration(monkeypatch):
+    import pspde
+    from pspde.fused import Call
+    prob = pspde.LLGC(d=10, off_diag=0.1, T=1.0, device="cuda")      # dense A, B: outside the tensor-core shape class
+    S = pspde.Solver("e", prob, K=64, L=1, delta_t=0.05, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, verbose=False)
+    S.z_n = pspde.DenseNet(d_in=11, d_out=10, lr=1e-3, seed=42)
+    S.update_Phis()
+    eng = S._get_engine()
+    monkeypatch.setenv("PSPDE_BWD_PATH", "ckpt")
+    with pytest.raises(RuntimeError, match="shape class"):
+        eng.backward_detached(S._theta.detach(), pt.ones(64, device="cuda"), None, Call(offset=0),
+                              pt.empty(eng.n_theta, device="cuda"))
