@@ -2,6 +2,7 @@
 #include "api_common.h"
 #include "rollout_tc_kernels.cuh"
 #include "grad_kernels.cuh"
+#include "grad_tc_kernels.cuh"
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
@@ -40,7 +41,26 @@ struct CkptPlan {
   size_t ckpt_bytes, grad_bytes;
 };
 
-static int launch_grad(const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream) {
+// Gradient accumulation from the checkpoint rows: the tensor-core kernel (grad_tc_kernels.cuh) for the shape class it
+// covers, else the FP32-FMA kernel (grad_kernels.cuh).  PSPDE_GRAD_PATH=simt forces the FMA kernel (A/B tests),
+// PSPDE_GRAD_PATH=tc makes an ineligible configuration an error.
+static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream) {
+#if !defined(PSPDE_EMULATE)
+  GradTcGeom gt;
+  const char* path = getenv("PSPDE_GRAD_PATH");
+  const bool eligible = grad_tc_geom(pl.g, cfg->d, p.ckpt_s0, gt);
+  if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core gradient kernel's shape class");
+  if (eligible && !(path && !strcmp(path, "simt"))) {
+    if (cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt.total) != cudaSuccess)
+      return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", gt.total);
+    grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(p, gt, n_items);
+    g_launches++;
+    if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
+    return 0;
+  }
+#else
+  (void)cfg;
+#endif
   if (pl.T == 256) return pspde_launch_grad_256(pl, p, grid, n_items, stream);
   if (pl.T == 512) return pspde_launch_grad_512(pl, p, grid, n_items, stream);
   return fail(-13, "internal: no gradient kernel for T=%d", pl.T);
@@ -186,7 +206,7 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
         g_launches++;
         if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
         const long long items = (long long)nt * cfg->N * (kTcP / kP);
-        rc = launch_grad(pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream);
+        rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream);
         if (rc) return rc;
       }
       const int n = pl.n_theta_total;
@@ -230,7 +250,7 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   p.ckpt = const_cast<float*>(ckpt); p.ckpt_c4 = 2 * (s0 >> 2) + 16; p.ckpt_s0 = s0;
   if (pspde_memset0(p.grad_partial, (size_t)grid * pl.n_theta_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
-  rc = launch_grad(pl, p, grid, (int)items, stream);
+  rc = launch_grad(cfg, pl, p, grid, (int)items, stream);
   if (rc) return rc;
   const int n = pl.n_theta_total;
   PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, grid, n, grad_theta);

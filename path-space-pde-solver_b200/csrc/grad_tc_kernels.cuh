@@ -1,0 +1,282 @@
+// grad_tc_kernels.cuh -- gradient accumulation from the checkpoint rows with the WEIGHT GRADIENT on the 5th-generation
+// tensor cores (tcgen05 + tensor memory).  Same contract as grad_kernel (grad_kernels.cuh): a pure streaming kernel
+// over (trajectory, step) samples, dtheta = sum_samples J_theta Z(a0)' zeta.
+//
+// The reduction dimension K of the weight gradient
+//     D[act col][cot col] += sum_samples act[sample][act col] * cot[sample][cot col]
+// is the SAMPLE index, M = activation column, N = cotangent column.  A half tile (64 samples) of checkpoint rows is
+// copied into shared memory with a 4 x 4 register transpose so that four consecutive samples of one column form a
+// float4: element (row r, sample 4 j + i) at j * LBO + r * 16 + i * 4 bytes, the canonical no-swizzle K-major operand
+// layout of tcgen05.mma (8-row x 16-byte core matrices, SBO = 128 B).  All columns -- [a0 | h1 | h2] and
+// [zeta | delta_2 | delta_1] -- are rows of ONE such matrix, so the A operand (two M tiles: rows 0..127, 128..255) and
+// the B operand (rows from zeta on, N = 176 at the C2 shape) are windows of the same tile.  (MN-major descriptors,
+// which would accept the checkpoint layout without the transpose, returned zeros for kind::tf32 without swizzle.)
+// FP32 equivalence as in tc_sm100.cuh: the tile holds the raw FP32 values, which the tensor core truncates to TF32
+// (hi = trunc(x)), a second tile holds lo = x - trunc(x); three passes lo*hi + hi*lo + hi*hi into the FP32
+// accumulators in tensor memory (2 M tiles x N columns), which stay resident for the whole launch and are added to
+// the CTA's gradient partial once at the end.
+//
+// The hidden cotangents delta_2, delta_1 (6 900 of the 29 960 MACs per sample at the C2 shape) are formed by FP32
+// FMA code on 4 samples x 4 hidden columns per thread that reads zeta / h straight from the operand tile (one
+// LDS.128 = one column of a sample quad) and appends the result to it.
+#pragma once
+#if !defined(PSPDE_EMULATE)
+#include "grad_kernels.cuh"
+#include "tc_sm100.cuh"
+
+namespace pspde {
+
+constexpr int kGtS = 64;                 // samples per work item (half a checkpoint tile) = K of one MMA group
+constexpr int kGtThreads = 512;
+constexpr int kGtQ = kGtS / 4;           // sample quads per item
+
+struct GradTcGeom {
+  int s04;             // column groups of a0 in the checkpoint (s0 / 4)
+  int act_groups;      // s04 + 16: [a0 | h1 | h2]
+  int ze_groups;       // s04: zeta (d used, the rest zero)
+  int g_ze, g_d2, g_d1, n_groups;        // first group of zeta / delta_2 / delta_1 in the tile; total incl. zero pad
+  int nB;              // N of the MMA (multiple of 16): zeta | delta_2 | delta_1 | pad
+  int dense;
+  uint32_t lbo;        // bytes between sample quads of the operand tile: (4 n_groups + 1) * 16
+  // compact weights for the hidden cotangents, k4-blocked: W2c rows = [h1 (32) | h2 (32)] columns (zero rows where
+  // the layer does not read the column), W1c rows = h1 (32) columns
+  int w2_nng, w1_nng, o_w2, o_w1;
+  uint32_t o_hi, o_lo, o_w, total;       // shared-memory byte offsets
+};
+
+inline bool grad_tc_geom(const NetGeom& g, int d, int s0, GradTcGeom& t) {
+  if (g.L != 3 || g.time_mode == TIME_NONE || g.seg_len[1] > 32 || g.seg_len[2] > 32 || (s0 & 7) || s0 < g.seg_len[0]) return false;
+  t.dense = g.kind == NET_DENSENET ? 1 : 0;
+  t.s04 = s0 >> 2;
+  t.act_groups = t.s04 + 16;
+  t.ze_groups = t.s04;
+  t.g_ze = t.act_groups; t.g_d2 = t.g_ze + t.ze_groups; t.g_d1 = t.g_d2 + 8;
+  const int nb_groups = t.ze_groups + 16;
+  t.nB = ((nb_groups * 4 + 15) / 16) * 16;
+  t.n_groups = t.g_ze + t.nB / 4;
+  if (t.n_groups < 64) t.n_groups = 64;            // the second M tile reads rows [128, 256)
+  if (t.act_groups > 64 || t.nB > 256 || 2 * t.nB > 512) return false;
+  (void)d;
+  t.lbo = (uint32_t)(4 * t.n_groups + 1) * 16u;    // odd number of 16-byte rows: 8 consecutive quads hit 8 distinct bank groups
+  t.w2_nng = g.layer[2].nng; t.w1_nng = g.layer[1].nng;
+  uint32_t o = 0;
+  t.o_hi = o; o += (uint32_t)kGtQ * t.lbo;
+  t.o_lo = o; o += (uint32_t)kGtQ * t.lbo;
+  t.o_w = o;
+  t.o_w2 = 0; t.o_w1 = 64 * t.w2_nng * 4;
+  o += (uint32_t)(64 * t.w2_nng * 4 + 32 * t.w1_nng * 4) * 4u;
+  t.total = o;
+  return t.total <= 227u * 1024u;
+}
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// lo = x - trunc(x), rounded to TF32 so that the tensor core's own truncation of it is exact
+__device__ __forceinline__ float lo1(float x) { return tc::tf32_hi(x - trunc_tf32(x)); }
+__device__ __forceinline__ float4 lo4(const float4& v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+
+__global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutParams prm, const GradTcGeom tg, const int n_items) {
+  extern __shared__ float4 smem4[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const NetGeom& g = prm.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* tH = smem + tg.o_hi;
+  uint8_t* tL = smem + tg.o_lo;
+  float* sW = reinterpret_cast<float*>(smem + tg.o_w);
+  const uint32_t lbo = tg.lbo;
+  // element (row r = column of [a0 | h1 | h2 | zeta | delta_2 | delta_1], sample 4 j + i) sits at j * lbo + r * 16 + i * 4:
+  // the canonical no-swizzle K-major operand layout with K = sample (8 rows x 16 B core matrices, SBO = 128 B, LBO = lbo)
+  auto quad = [&](uint8_t* t, int r, int j) -> float4& { return *reinterpret_cast<float4*>(t + (uint32_t)j * lbo + (uint32_t)r * 16u); };
+
+  // ---- one-time setup
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { tc::mbar_init(&bar_mma, 1); tc::mbar_fence_init(); }
+  for (uint32_t q = tid; q < 2u * kGtQ * lbo / 16u; q += kGtThreads) reinterpret_cast<float4*>(tH)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 1; l <= 2; ++l) {            // compact k4-blocked weights: row = hidden column slot (32 per segment)
+    const LayerGeom& y = g.layer[l];
+    const int rows = l == 2 ? 64 : 32;
+    float* dst = sW + (l == 2 ? tg.o_w2 : tg.o_w1);
+    for (int q = tid; q < rows * y.Np; q += kGtThreads) {
+      const int blk = q >> 4, in = q & 15;
+      const int r = 4 * (blk / y.nng) + (in >> 2), n = 4 * (blk % y.nng) + (in & 3);
+      const int sg = 1 + (r >> 5), c = r & 31;                 // segment and column inside it
+      int idx = -1;
+      if (c < g.seg_len[sg]) {
+        const int lr = g.seg_off[sg] + c - y.in_start;         // row of W_l (relative to the first column it reads)
+        if (lr >= 0 && lr < y.Kp) idx = theta_index(g, l, lr, n);
+      }
+      dst[q] = idx >= 0 ? __ldg(prm.theta + idx) : 0.f;
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL);
+  const uint32_t idesc = tc::idesc_tf32(128, tg.nB);
+
+  const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
+  const int src_groups = tg.act_groups + tg.ze_groups;       // the checkpoint row: [a0 | h1 | h2 | zeta]
+  // hidden-cotangent mapping: warp = 4 hidden columns hc0 .. hc0 + 3 of [h1 (32) | h2 (32)], lane = (sample quad, half of
+  // the reduction range); the two halves are combined with one xor-shuffle
+  const int hc0 = 4 * warp, hj = lane & 15, hk = lane >> 4;
+  const bool is_h2 = hc0 >= 32;
+  const int seg_n = g.dims[is_h2 ? 2 : 1];
+  const int h_row = 4 * tg.s04 + hc0;                         // tile row of the hidden activation h[hc0]
+  uint32_t ph = 0;
+  bool first = true, pending = false;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int ts = item / 2, half = item - ts * 2;
+    const float4* src = ck + (size_t)ts * prm.ckpt_c4 * kCkP + half * kGtS;
+    // the tensor core must be done with the tile of the previous item before it is overwritten
+    if (pending) { tc::mbar_wait(&bar_mma, ph); ph ^= 1u; pending = false; tc::fence_after_sync(); }
+    // ---- (1) copy [a0 | h1 | h2 | zeta] with a 4 x 4 register transpose (sample-major float4 -> sample quads per column)
+    for (int q = tid; q < src_groups * kGtQ; q += kGtThreads) {
+      const int gi = q >> 4, j = q & (kGtQ - 1);
+      const float4* sp = src + (size_t)gi * kCkP + 4 * j;
+      const float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
+      const float4 c0 = make_float4(v0.x, v1.x, v2.x, v3.x), c1 = make_float4(v0.y, v1.y, v2.y, v3.y);
+      const float4 c2 = make_float4(v0.z, v1.z, v2.z, v3.z), c3 = make_float4(v0.w, v1.w, v2.w, v3.w);
+      quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
+      quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
+    }
+    __syncthreads();
+    // ---- (2) hidden cotangents for 4 samples x 4 hidden columns per thread:
+    //      dh[s][c] = sum_n zeta[s][n] W2[c][n]   (+ sum_n delta_2[s][n] W1[c][n] for the h1 columns)
+    float acc[4][4];                      // [hidden column][sample]
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+    auto accumulate = [&](const float* w, int nng, int row0, int nk4) {     // cotangent rows row0 + 4 k4 + e, weights W[hc0 + c][4 k4 + e]
+      for (int k4 = hk; k4 < nk4; k4 += 2) {
+        float4 z[4], wv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) z[e] = quad(tH, row0 + 4 * k4 + e, hj);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[c][0] = fmaf(z[e].x, we[e], acc[c][0]); acc[c][1] = fmaf(z[e].y, we[e], acc[c][1]);
+            acc[c][2] = fmaf(z[e].z, we[e], acc[c][2]); acc[c][3] = fmaf(z[e].w, we[e], acc[c][3]);
+          }
+        }
+      }
+    };
+    auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 16);
+        const float4 h = quad(tH, h_row + c, hj);
+        const float hv[4] = {h.x, h.y, h.z, h.w};
+        const bool live = (hc0 & 31) + c < seg_n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = live ? v[i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+        if (hk == (c & 1)) {               // the two halves share the stores
+          const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          quad(tH, row_dst + (hc0 & 31) + c, hj) = o;
+          quad(tL, row_dst + (hc0 & 31) + c, hj) = lo4(o);
+        }
+      }
+    };
+    if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, 4 * tg.g_ze, g.layer[2].nng);
+    if (is_h2) finish(4 * tg.g_d2);
+    __syncthreads();
+    if (!is_h2) {
+      accumulate(sW + tg.o_w1, tg.w1_nng, 4 * tg.g_d2, g.layer[1].nng);
+      finish(4 * tg.g_d1);
+    }
+    // ---- (3) weight gradient: D[m tile][act col][cot col] += sum_samples, three passes, one thread issues
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 0) ? sL : sH;
+        const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)(4 * tg.g_ze) * 16u;
+        for (int mt = 0; mt < 2; ++mt) {
+          for (int ks = 0; ks < kGtS / 8; ++ks) {
+            const uint64_t ad = tc::smem_desc(a + (uint32_t)mt * 2048u + (uint32_t)ks * 2u * lbo, lbo, 128u);
+            const uint64_t bd = tc::smem_desc(b + (uint32_t)ks * 2u * lbo, lbo, 128u);
+            mma_tf32_ss(tbase + (uint32_t)(mt * tg.nB), ad, bd, idesc, !first || pass > 0 || ks > 0);
+          }
+        }
+      }
+      tc::mma_commit(&bar_mma);
+    }
+    first = false;
+    pending = true;
+  }
+  if (pending) { tc::mbar_wait(&bar_mma, ph); tc::fence_after_sync(); }
+
+  if (prm.prof && blockIdx.x == 0) {         // debug hook (pspde_set_profile_buffer): raw accumulators of CTA 0, [2][128][nB]
+    float* dump = reinterpret_cast<float*>(prm.prof);
+    const int qtr = warp & 3, cpart = warp >> 2;
+    for (int mt = 0; mt < 2; ++mt)
+      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
+        float v[8];
+        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dump[(size_t)(mt * 128 + 32 * qtr + lane) * tg.nB + c0 + i] = v[i];
+      }
+  }
+  // ---- flush: accumulators -> this CTA's gradient partial.  Lane m of M tile mt is checkpoint column 128 mt + m,
+  // column c is cotangent column c of [zeta | delta_2 | delta_1].  A warp reads the lane quarter 32 (warp % 4).
+  if (!first) {
+    float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
+    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
+    for (int mt = 0; mt < 2; ++mt) {
+      const int m = 128 * mt + 32 * qtr + lane;           // checkpoint column of this lane
+      // checkpoint column -> activation column of NetGeom (segments are padded to s0 / 32 / 32 in the checkpoint)
+      int col = -1;
+      if (m < 4 * tg.s04) { if (m < g.seg_len[0]) col = m; }
+      else if (m < 4 * tg.s04 + 32) { if (m - 4 * tg.s04 < g.seg_len[1]) col = g.seg_off[1] + (m - 4 * tg.s04); }
+      else if (m < 4 * tg.s04 + 64) { if (m - 4 * tg.s04 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - 4 * tg.s04 - 32); }
+      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
+        float v[8];
+        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
+        tc::wait_ld();
+        if (col < 0) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          int l, n;
+          if (c < 4 * tg.ze_groups) { l = 2; n = c; }
+          else if (c < 4 * tg.ze_groups + 32) { l = 1; n = c - 4 * tg.ze_groups; }
+          else if (c < 4 * tg.ze_groups + 64) { l = 0; n = c - 4 * tg.ze_groups - 32; }
+          else continue;
+          const LayerGeom& y = g.layer[l];
+          const int r = col - y.in_start;
+          if (r < 0 || r >= y.Kp || n >= y.N) continue;
+          const int idx = theta_index(g, l, r, n);
+          if (idx >= 0) gp[idx] += v[i];
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace pspde
+#endif  // !PSPDE_EMULATE
