@@ -44,7 +44,8 @@ struct CkptPlan {
 // Gradient accumulation from the checkpoint rows: the tensor-core kernel (grad_tc_kernels.cuh) for the shape class it
 // covers, else the FP32-FMA kernel (grad_kernels.cuh).  PSPDE_GRAD_PATH=simt forces the FMA kernel (A/B tests),
 // PSPDE_GRAD_PATH=tc makes an ineligible configuration an error.
-static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream) {
+static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream, bool* used_tc) {
+  *used_tc = false;
 #if !defined(PSPDE_EMULATE)
   GradTcGeom gt;
   const char* path = getenv("PSPDE_GRAD_PATH");
@@ -56,6 +57,7 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
     grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(p, gt, n_items);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
+    *used_tc = true;
     return 0;
   }
 #else
@@ -64,6 +66,40 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
   if (pl.T == 256) return pspde_launch_grad_256(pl, p, grid, n_items, stream);
   if (pl.T == 512) return pspde_launch_grad_512(pl, p, grid, n_items, stream);
   return fail(-13, "internal: no gradient kernel for T=%d", pl.T);
+}
+
+// floats of one CTA's gradient partial: theta layout (FMA kernel) or raw accumulator layout (tensor-core kernel)
+static size_t grad_part_floats(const pspde_cfg* cfg, const Plan& pl, int s0) {
+  size_t n = (size_t)pl.n_theta_total;
+#if !defined(PSPDE_EMULATE)
+  GradTcGeom gt;
+  if (grad_tc_geom(pl.g, cfg->d, s0, gt) && (size_t)(2 * 128 * gt.nB) > n) n = (size_t)(2 * 128 * gt.nB);
+#else
+  (void)cfg; (void)s0;
+#endif
+  return n;
+}
+
+static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int nparts, bool used_tc, float* grad_theta, void* stream) {
+  const int n = pl.n_theta_total;
+#if !defined(PSPDE_EMULATE)
+  if (used_tc) {
+    GradTcGeom gt;
+    grad_tc_geom(pl.g, cfg->d, p.ckpt_s0, gt);
+    if (pspde_memset0(grad_theta, (size_t)n * sizeof(float), stream)) return fail(-12, "memset of grad_theta failed");
+    const int per = 2 * 128 * gt.nB;
+    reduce_grad_tc_kernel<<<(per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pl.g, gt, p.grad_partial, nparts, grad_theta);
+    g_launches++;
+    if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad_tc launch failed: %s", e);
+    return 0;
+  }
+#else
+  (void)cfg; (void)used_tc;
+#endif
+  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, nparts, n, grad_theta);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
+  return 0;
 }
 
 #if !defined(PSPDE_EMULATE)
@@ -78,7 +114,7 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
   const long long items = (long long)cp.wave * cfg->N * (kTcP / kP);
   cp.grid_b = items < sms ? (int)items : sms;
   cp.ckpt_bytes = align256((size_t)cp.wave * cfg->N * cp.c4 * kTcP * 16);
-  cp.grad_bytes = align256((size_t)cp.grid_b * pl.n_theta_total * sizeof(float));
+  cp.grad_bytes = align256((size_t)cp.grid_b * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
   return true;
 }
 #endif
@@ -195,10 +231,10 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
       eligible = false;
     }
     if (eligible && !(path && !strcmp(path, "simt"))) {
-      if (pspde_memset0(p.grad_partial, (size_t)cp.grid_b * pl.n_theta_total * sizeof(float), stream))
-        return fail(-12, "memset of the gradient partials failed");
+      if (pspde_memset0(p.grad_partial, cp.grad_bytes, stream)) return fail(-12, "memset of the gradient partials failed");
       p.ckpt = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes + cp.grad_bytes);
       p.ckpt_c4 = cp.c4; p.ckpt_s0 = cp.s0;
+      bool used_tc = false;
       for (int t0 = 0; t0 < cp.n_tiles128; t0 += cp.wave) {
         const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
         p.tile0 = t0; p.n_tiles = nt;
@@ -206,14 +242,10 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
         g_launches++;
         if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
         const long long items = (long long)nt * cfg->N * (kTcP / kP);
-        rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream);
+        rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream, &used_tc);
         if (rc) return rc;
       }
-      const int n = pl.n_theta_total;
-      PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, cp.grid_b, n, grad_theta);
-      g_launches++;
-      if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
-      return 0;
+      return reduce_grad(cfg, pl, p, cp.grid_b, used_tc, grad_theta, stream);
     }
   }
 #endif
@@ -241,22 +273,18 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   const int sms = pspde_sm_count();
   const long long items = (long long)n_slots * cfg->N * (kCkP / kP);
   const int grid = items < sms ? (int)items : sms;
-  const size_t gbytes = align256((size_t)grid * pl.n_theta_total * sizeof(float));
+  const size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, s0) * sizeof(float));
   if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
   p.ckpt = const_cast<float*>(ckpt); p.ckpt_c4 = 2 * (s0 >> 2) + 16; p.ckpt_s0 = s0;
-  if (pspde_memset0(p.grad_partial, (size_t)grid * pl.n_theta_total * sizeof(float), stream))
-    return fail(-12, "memset of the gradient partials failed");
-  rc = launch_grad(cfg, pl, p, grid, (int)items, stream);
+  if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
+  bool used_tc = false;
+  rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
   if (rc) return rc;
-  const int n = pl.n_theta_total;
-  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, grid, n, grad_theta);
-  g_launches++;
-  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
-  return 0;
+  return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
 }
 
 int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,

@@ -36,6 +36,7 @@ struct GradTcGeom {
   int ze_groups;       // s04: zeta (d used, the rest zero)
   int g_ze, g_d2, g_d1, n_groups;        // first group of zeta / delta_2 / delta_1 in the tile; total incl. zero pad
   int nB;              // N of the MMA (multiple of 16): zeta | delta_2 | delta_1 | pad
+  int nE;              // leading zeta columns (multiple of 16) whose MMAs are issued before the hidden cotangents exist
   int dense;
   uint32_t lbo;        // bytes between sample quads of the operand tile: (4 n_groups + 1) * 16
   // compact weights for the hidden cotangents, k4-blocked: W2c rows = [h1 (32) | h2 (32)] columns (zero rows where
@@ -53,6 +54,7 @@ inline bool grad_tc_geom(const NetGeom& g, int d, int s0, GradTcGeom& t) {
   t.g_ze = t.act_groups; t.g_d2 = t.g_ze + t.ze_groups; t.g_d1 = t.g_d2 + 8;
   const int nb_groups = t.ze_groups + 16;
   t.nB = ((nb_groups * 4 + 15) / 16) * 16;
+  t.nE = (4 * t.ze_groups / 16) * 16;
   t.n_groups = t.g_ze + t.nB / 4;
   if (t.n_groups < 64) t.n_groups = 64;            // the second M tile reads rows [128, 256)
   if (t.act_groups > 64 || t.nB > 256 || 2 * t.nB > 512) return false;
@@ -124,52 +126,105 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL);
-  const uint32_t idesc = tc::idesc_tf32(128, tg.nB);
 
   const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
   const int src_groups = tg.act_groups + tg.ze_groups;       // the checkpoint row: [a0 | h1 | h2 | zeta]
-  // hidden-cotangent mapping: warp = 4 hidden columns hc0 .. hc0 + 3 of [h1 (32) | h2 (32)], lane = (sample quad, half of
-  // the reduction range); the two halves are combined with one xor-shuffle
-  const int hc0 = 4 * warp, hj = lane & 15, hk = lane >> 4;
+  // hidden-cotangent mapping: warp = (8 hidden columns hc0 .. hc0 + 7 of [h1 (32) | h2 (32)], half of the sample quads),
+  // lane = (sample quad, quarter of the reduction range); the quarters are combined with two xor-shuffles
+  const int hc0 = 8 * (warp & 7), hj = 8 * (warp >> 3) + (lane & 7), hk = lane >> 3;
   const bool is_h2 = hc0 >= 32;
   const int seg_n = g.dims[is_h2 ? 2 : 1];
   const int h_row = 4 * tg.s04 + hc0;                         // tile row of the hidden activation h[hc0]
+  // D[m tile][:, n0 .. n0 + n) += act' . cot[:, n0 .. n0 + n) over the 64 samples of the tile, three passes (thread 0)
+  auto issue = [&](int n0, int n, bool overwrite) {
+    const uint32_t id = tc::idesc_tf32(128, n);
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a = (pass == 0) ? sL : sH;
+      const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)(4 * tg.g_ze + n0) * 16u;
+      for (int mt = 0; mt < 2; ++mt)
+        for (int ks = 0; ks < kGtS / 8; ++ks) {
+          const uint64_t ad = tc::smem_desc(a + (uint32_t)mt * 2048u + (uint32_t)ks * 2u * lbo, lbo, 128u);
+          const uint64_t bd = tc::smem_desc(b + (uint32_t)ks * 2u * lbo, lbo, 128u);
+          mma_tf32_ss(tbase + (uint32_t)(mt * tg.nB + n0), ad, bd, id, !overwrite || pass > 0 || ks > 0);
+        }
+    }
+  };
   uint32_t ph = 0;
   bool first = true, pending = false;
+  PhaseTimer pt_;          // debug: [0] wait for the tensor core, [1] copy + transpose, [2] hidden cotangents, [3] MMA issue, [4] zeta . W2', [5] delta_2 + barrier, [6] delta_2 . W1' + delta_1, [2] fences + barrier
+  pt_.start(prm.prof, tid == 32 ? 0 : 1);
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int ts = item / 2, half = item - ts * 2;
     const float4* src = ck + (size_t)ts * prm.ckpt_c4 * kCkP + half * kGtS;
-    // the tensor core must be done with the tile of the previous item before it is overwritten
-    if (pending) { tc::mbar_wait(&bar_mma, ph); ph ^= 1u; pending = false; tc::fence_after_sync(); }
-    // ---- (1) copy [a0 | h1 | h2 | zeta] with a 4 x 4 register transpose (sample-major float4 -> sample quads per column)
-    for (int q = tid; q < src_groups * kGtQ; q += kGtThreads) {
-      const int gi = q >> 4, j = q & (kGtQ - 1);
-      const float4* sp = src + (size_t)gi * kCkP + 4 * j;
-      const float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
-      const float4 c0 = make_float4(v0.x, v1.x, v2.x, v3.x), c1 = make_float4(v0.y, v1.y, v2.y, v3.y);
-      const float4 c2 = make_float4(v0.z, v1.z, v2.z, v3.z), c3 = make_float4(v0.w, v1.w, v2.w, v3.w);
-      quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
-      quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
-    }
-    __syncthreads();
-    // ---- (2) hidden cotangents for 4 samples x 4 hidden columns per thread:
-    //      dh[s][c] = sum_n zeta[s][n] W2[c][n]   (+ sum_n delta_2[s][n] W1[c][n] for the h1 columns)
-    float acc[4][4];                      // [hidden column][sample]
+    // ---- (1) copy [a0 | h1 | h2 | zeta] with a 4 x 4 register transpose (sample-major float4 -> sample quads per column);
+    //      all global loads of the thread are in flight before the first one is used
+    {
+      constexpr int MAXI = 3;
+      float4 v[MAXI][4];
+      const int nq = src_groups * kGtQ;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+      for (int it = 0; it < MAXI; ++it) {
+        const int q = tid + it * kGtThreads;
+        if (q < nq) {
+          const float4* sp = src + (size_t)(q >> 4) * kCkP + 4 * (q & (kGtQ - 1));
+          v[it][0] = __ldg(sp); v[it][1] = __ldg(sp + 1); v[it][2] = __ldg(sp + 2); v[it][3] = __ldg(sp + 3);
+        }
+      }
+      // the tensor core must be done with the tile of the previous item before it is overwritten (the loads above are
+      // in flight meanwhile)
+      if (pending) { tc::mbar_wait(&bar_mma, ph); ph ^= 1u; pending = false; tc::fence_after_sync(); }
+      pt_.mark(0);
+#pragma unroll
+      for (int it = 0; it < MAXI; ++it) {
+        const int q = tid + it * kGtThreads;
+        if (q < nq) {
+          const int gi = q >> 4, j = q & (kGtQ - 1);
+          const float4 c0 = make_float4(v[it][0].x, v[it][1].x, v[it][2].x, v[it][3].x), c1 = make_float4(v[it][0].y, v[it][1].y, v[it][2].y, v[it][3].y);
+          const float4 c2 = make_float4(v[it][0].z, v[it][1].z, v[it][2].z, v[it][3].z), c3 = make_float4(v[it][0].w, v[it][1].w, v[it][2].w, v[it][3].w);
+          quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
+          quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
+        }
+      }
+      for (int q = tid + MAXI * kGtThreads; q < nq; q += kGtThreads) {                  // (wider inputs than the C2 shape)
+        const int gi = q >> 4, j = q & (kGtQ - 1);
+        const float4* sp = src + (size_t)gi * kCkP + 4 * j;
+        const float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
+        const float4 c0 = make_float4(v0.x, v1.x, v2.x, v3.x), c1 = make_float4(v0.y, v1.y, v2.y, v3.y);
+        const float4 c2 = make_float4(v0.z, v1.z, v2.z, v3.z), c3 = make_float4(v0.w, v1.w, v2.w, v3.w);
+        quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
+        quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
+      }
+    }
+    // the zeta part of the weight gradient does not need the hidden cotangents: its MMAs run beside them
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0 && tg.nE > 0) { tc::fence_after_sync(); issue(0, tg.nE, first); }
+    if (item + (int)gridDim.x < n_items) {                    // next item -> L2 while the hidden cotangents are formed
+      const int nitem = item + gridDim.x, nts = nitem / 2, nhalf = nitem - nts * 2;
+      for (int q = tid; q < src_groups * 8; q += kGtThreads) {                           // 8 lines of 128 B per column group
+        const char* np_ = reinterpret_cast<const char*>(ck + (size_t)nts * prm.ckpt_c4 * kCkP + nhalf * kGtS + (size_t)(q >> 3) * kCkP) + (q & 7) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
+      }
+    }
+    pt_.mark(1);
+    // ---- (2) hidden cotangents for 4 samples x 8 hidden columns per thread:
+    //      dh[s][c] = sum_n zeta[s][n] W2[c][n]   (+ sum_n delta_2[s][n] W1[c][n] for the h1 columns)
+    float acc[8][4];                      // [hidden column][sample]
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
     auto accumulate = [&](const float* w, int nng, int row0, int nk4) {     // cotangent rows row0 + 4 k4 + e, weights W[hc0 + c][4 k4 + e]
-      for (int k4 = hk; k4 < nk4; k4 += 2) {
-        float4 z[4], wv[4];
+      for (int k4 = hk; k4 < nk4; k4 += 4) {
+        float4 z[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) z[e] = quad(tH, row0 + 4 * k4 + e, hj);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
+        for (int c = 0; c < 8; ++c) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + (((hc0 >> 2) + (c >> 2)) * nng + k4) * 16 + (c & 3) * 4);
+          const float we[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             acc[c][0] = fmaf(z[e].x, we[e], acc[c][0]); acc[c][1] = fmaf(z[e].y, we[e], acc[c][1]);
@@ -178,104 +233,104 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
         }
       }
     };
-    auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
+    auto finish = [&](int row_dst) {       // combine the quarters, act', zero the pads, raw -> tH, lo -> tL
+      float sel[2][4];                     // quarter hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float v[4];
+      for (int c = 0; c < 8; ++c) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 16);
+        for (int i = 0; i < 4; ++i) {
+          float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if ((c >> 1) == hk) sel[c & 1][i] = v;
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * hk + cc;
         const float4 h = quad(tH, h_row + c, hj);
         const float hv[4] = {h.x, h.y, h.z, h.w};
         const bool live = (hc0 & 31) + c < seg_n;
+        float v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = live ? v[i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
-        if (hk == (c & 1)) {               // the two halves share the stores
-          const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          quad(tH, row_dst + (hc0 & 31) + c, hj) = o;
-          quad(tL, row_dst + (hc0 & 31) + c, hj) = lo4(o);
-        }
+        for (int i = 0; i < 4; ++i) v[i] = live ? sel[cc][i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        quad(tH, row_dst + (hc0 & 31) + c, hj) = o;
+        quad(tL, row_dst + (hc0 & 31) + c, hj) = lo4(o);
       }
     };
     if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, 4 * tg.g_ze, g.layer[2].nng);
+    pt_.mark(4);
     if (is_h2) finish(4 * tg.g_d2);
     __syncthreads();
+    pt_.mark(5);
     if (!is_h2) {
       accumulate(sW + tg.o_w1, tg.w1_nng, 4 * tg.g_d2, g.layer[1].nng);
       finish(4 * tg.g_d1);
     }
+    pt_.mark(6);
     // ---- (3) weight gradient: D[m tile][act col][cot col] += sum_samples, three passes, one thread issues
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
+    pt_.mark(2);
     if (tid == 0) {
       tc::fence_after_sync();
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 0) ? sL : sH;
-        const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)(4 * tg.g_ze) * 16u;
-        for (int mt = 0; mt < 2; ++mt) {
-          for (int ks = 0; ks < kGtS / 8; ++ks) {
-            const uint64_t ad = tc::smem_desc(a + (uint32_t)mt * 2048u + (uint32_t)ks * 2u * lbo, lbo, 128u);
-            const uint64_t bd = tc::smem_desc(b + (uint32_t)ks * 2u * lbo, lbo, 128u);
-            mma_tf32_ss(tbase + (uint32_t)(mt * tg.nB), ad, bd, idesc, !first || pass > 0 || ks > 0);
-          }
-        }
-      }
+      issue(tg.nE, tg.nB - tg.nE, first);
       tc::mma_commit(&bar_mma);
     }
     first = false;
     pending = true;
+    pt_.mark(3);
   }
   if (pending) { tc::mbar_wait(&bar_mma, ph); tc::fence_after_sync(); }
 
-  if (prm.prof && blockIdx.x == 0) {         // debug hook (pspde_set_profile_buffer): raw accumulators of CTA 0, [2][128][nB]
-    float* dump = reinterpret_cast<float*>(prm.prof);
-    const int qtr = warp & 3, cpart = warp >> 2;
+  // ---- flush: raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
+  // reduce_grad_tc_kernel sums the partials and scatters them to theta.  A warp reads the lane quarter 32 (warp % 4).
+  if (!first) {
+    float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
+    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
     for (int mt = 0; mt < 2; ++mt)
       for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
         float v[8];
         tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
         tc::wait_ld();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dump[(size_t)(mt * 128 + 32 * qtr + lane) * tg.nB + c0 + i] = v[i];
+        for (int i = 0; i < 8; ++i) gp[(size_t)(mt * tg.nB + c0 + i) * 128 + 32 * qtr + lane] += v[i];
       }
-  }
-  // ---- flush: accumulators -> this CTA's gradient partial.  Lane m of M tile mt is checkpoint column 128 mt + m,
-  // column c is cotangent column c of [zeta | delta_2 | delta_1].  A warp reads the lane quarter 32 (warp % 4).
-  if (!first) {
-    float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
-    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
-    for (int mt = 0; mt < 2; ++mt) {
-      const int m = 128 * mt + 32 * qtr + lane;           // checkpoint column of this lane
-      // checkpoint column -> activation column of NetGeom (segments are padded to s0 / 32 / 32 in the checkpoint)
-      int col = -1;
-      if (m < 4 * tg.s04) { if (m < g.seg_len[0]) col = m; }
-      else if (m < 4 * tg.s04 + 32) { if (m - 4 * tg.s04 < g.seg_len[1]) col = g.seg_off[1] + (m - 4 * tg.s04); }
-      else if (m < 4 * tg.s04 + 64) { if (m - 4 * tg.s04 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - 4 * tg.s04 - 32); }
-      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
-        float v[8];
-        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
-        tc::wait_ld();
-        if (col < 0) continue;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = c0 + i;
-          int l, n;
-          if (c < 4 * tg.ze_groups) { l = 2; n = c; }
-          else if (c < 4 * tg.ze_groups + 32) { l = 1; n = c - 4 * tg.ze_groups; }
-          else if (c < 4 * tg.ze_groups + 64) { l = 0; n = c - 4 * tg.ze_groups - 32; }
-          else continue;
-          const LayerGeom& y = g.layer[l];
-          const int r = col - y.in_start;
-          if (r < 0 || r >= y.Kp || n >= y.N) continue;
-          const int idx = theta_index(g, l, r, n);
-          if (idx >= 0) gp[idx] += v[i];
-        }
-      }
-    }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// partial[cta][m tile][cotangent column c][lane m] -> grad_theta.  Lane m of M tile mt is checkpoint column 128 mt + m
+// (segments padded to s0 / 32 / 32), column c is cotangent column c of [zeta | delta_2 | delta_1]; every parameter is
+// produced by exactly one (column, row) pair.  Fixed summation order, fp64.
+static __global__ void reduce_grad_tc_kernel(const NetGeom g, const GradTcGeom tg, const float* __restrict__ partial, int nparts,
+                                             float* __restrict__ out) {
+  const int per = 2 * 128 * tg.nB;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+    const int lane = q & 127, mc = q >> 7, mt = mc / tg.nB, c = mc - mt * tg.nB;
+    const int m = 128 * mt + lane;
+    int col = -1;
+    if (m < 4 * tg.s04) { if (m < g.seg_len[0]) col = m; }
+    else if (m < 4 * tg.s04 + 32) { if (m - 4 * tg.s04 < g.seg_len[1]) col = g.seg_off[1] + (m - 4 * tg.s04); }
+    else if (m < 4 * tg.s04 + 64) { if (m - 4 * tg.s04 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - 4 * tg.s04 - 32); }
+    if (col < 0) continue;
+    int l, n;
+    if (c < 4 * tg.ze_groups) { l = 2; n = c; }
+    else if (c < 4 * tg.ze_groups + 32) { l = 1; n = c - 4 * tg.ze_groups; }
+    else if (c < 4 * tg.ze_groups + 64) { l = 0; n = c - 4 * tg.ze_groups - 32; }
+    else continue;
+    const LayerGeom& y = g.layer[l];
+    const int r = col - y.in_start;
+    if (r < 0 || r >= y.Kp || n >= y.N) continue;
+    const int idx = theta_index(g, l, r, n);
+    if (idx < 0) continue;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * per + q];
+    out[idx] = (float)s;
+  }
 }
 
 }  // namespace pspde
