@@ -335,12 +335,26 @@ def run_ours(args, wl):
                 prof = json.load(fh)
         except OSError:
             pass
-        roof = {"bound": "fp32_fma", "kernel": "rollout_kernel<BWD> (detached backward, recompute)",
+        hid_max = 32 if eng.net_id == 0 else 31
+        ckpt_path = os.environ.get("PSPDE_BWD_PATH", "") != "simt" and len(eng.dims) == 4 \
+            and max(eng.dims[1:3]) <= hid_max and eng.time_mode == 0 and not (eng.flags & 1)
+        if ckpt_path:
+            s0 = (d + 2 + 7) // 8 * 8
+            ckpt_bytes = 2.0 * eng.K_local * N * (2 * (s0 // 4) + 16) * 16          # operand rows written once, read once
+            kernel = ("checkpointed detached backward = rollout_tc_fwd_kernel<CKPT> (tensor-core rollout that leaves the "
+                      "operand rows [a0|h1|h2|zeta] of one wave of tiles in the workspace) + grad_tc_kernel (hidden "
+                      "cotangents in FP32 FMA, weight gradient on tcgen05 kind::tf32 3xTF32 with K = samples, accumulators "
+                      "resident in tensor memory); timed together")
+        else:
+            ckpt_bytes, kernel = 0.0, "rollout_kernel<BWD> (detached backward, FP32-FMA recompute)"
+        roof = {"bound": "fp32_fma", "kernel": kernel,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "fp32 FMA probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure); "
                                "nominal 148 SM x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s" % (nominal or 0),
                 "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
+                "bwd_checkpoint": {"bytes_per_step": ckpt_bytes, "gbs_over_bwd": ckpt_bytes / (tb * 1e-3) / 1e9,
+                                   "hbm_peak_gbs_measured": measured_peaks().get("hbm_gbs")} if ckpt_path else None,
                 "fwd": fwd_roofline(flops_fwd, tf, peak, eng),
                 "step": {"algorithmic_flops_per_path_step": 2.0 * (2 * M + Md),
                          "achieved": (flops_fwd + flops_bwd) / ((tf + tb) * 1e-3) / 1e12,

@@ -38,6 +38,7 @@ struct GradTcGeom {
   int nB;              // N of the MMA (multiple of 16): zeta | delta_2 | delta_1 | pad
   int nE;              // leading zeta columns (multiple of 16) whose MMAs are issued before the hidden cotangents exist
   int dense;
+  int n_mt;            // M tiles of 128 activation columns (1 when [a0 | h1 | h2] has at most 128 columns)
   uint32_t lbo;        // bytes between sample quads of the operand tile: (4 n_groups + 1) * 16
   // compact weights for the hidden cotangents, k4-blocked: W2c rows = [h1 (32) | h2 (32)] columns (zero rows where
   // the layer does not read the column), W1c rows = h1 (32) columns
@@ -56,7 +57,8 @@ inline bool grad_tc_geom(const NetGeom& g, int d, int s0, GradTcGeom& t) {
   t.nB = ((nb_groups * 4 + 15) / 16) * 16;
   t.nE = (4 * t.ze_groups / 16) * 16;
   t.n_groups = t.g_ze + t.nB / 4;
-  if (t.n_groups < 64) t.n_groups = 64;            // the second M tile reads rows [128, 256)
+  t.n_mt = t.act_groups > 32 ? 2 : 1;
+  if (t.n_groups < 32 * t.n_mt) t.n_groups = 32 * t.n_mt;     // M tile mt reads rows [128 mt, 128 mt + 128)
   if (t.act_groups > 64 || t.nB > 256 || 2 * t.nB > 512) return false;
   (void)d;
   t.lbo = (uint32_t)(4 * t.n_groups + 1) * 16u;    // odd number of 16-byte rows: 8 consecutive quads hit 8 distinct bank groups
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
     for (int pass = 0; pass < 3; ++pass) {
       const uint32_t a = (pass == 0) ? sL : sH;
       const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)(4 * tg.g_ze + n0) * 16u;
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < tg.n_mt; ++mt)
         for (int ks = 0; ks < kGtS / 8; ++ks) {
           const uint64_t ad = tc::smem_desc(a + (uint32_t)mt * 2048u + (uint32_t)ks * 2u * lbo, lbo, 128u);
           const uint64_t bd = tc::smem_desc(b + (uint32_t)ks * 2u * lbo, lbo, 128u);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
   if (!first) {
     float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
     const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < tg.n_mt; ++mt)
       for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
         float v[8];
         tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
@@ -311,6 +313,7 @@ static __global__ void reduce_grad_tc_kernel(const NetGeom g, const GradTcGeom t
   const int per = 2 * 128 * tg.nB;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
     const int lane = q & 127, mc = q >> 7, mt = mc / tg.nB, c = mc - mt * tg.nB;
+    if (mt >= tg.n_mt) continue;
     const int m = 128 * mt + lane;
     int col = -1;
     if (m < 4 * tg.s04) { if (m < g.seg_len[0]) col = m; }
