@@ -1,4 +1,4 @@
-"""Debug: tensor-core gradient kernel vs the FP32-FMA gradient kernel vs fp64 numpy on synthetic checkpoint rows."""
+"""Both gradient kernels (tensor-core, FP32-FMA) against fp64 numpy on synthetic checkpoint rows, several network shapes."""
 import os, sys, ctypes
 import numpy as np, torch as pt
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

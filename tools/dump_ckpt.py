@@ -1,4 +1,4 @@
-"""Debug: dump the checkpoint rows the tensor-core forward leaves in the workspace and look for non-finite values."""
+"""Dump the checkpoint rows the tensor-core forward leaves in the workspace and look for non-finite values."""
 import os, sys, ctypes
 import numpy as np, torch as pt
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
