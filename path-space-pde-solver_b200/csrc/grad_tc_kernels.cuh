@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
 
   const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
   const int src_groups = tg.act_groups + tg.ze_groups;       // the checkpoint row: [a0 | h1 | h2 | zeta]
-  // hidden-cotangent mapping: warp = (8 hidden columns hc0 .. hc0 + 7 of [h1 (32) | h2 (32)], half of the sample quads),
-  // lane = (sample quad, quarter of the reduction range); the quarters are combined with two xor-shuffles
-  const int hc0 = 8 * (warp & 7), hj = 8 * (warp >> 3) + (lane & 7), hk = lane >> 3;
+  // hidden-cotangent mapping: warp = 4 hidden columns hc0 .. hc0 + 3 of [h1 (32) | h2 (32)], lane = (sample quad, half of
+  // the reduction range); the two halves are combined with one xor-shuffle
+  const int hc0 = 4 * warp, hj = lane & 15, hk = lane >> 4;
   const bool is_h2 = hc0 >= 32;
   const int seg_n = g.dims[is_h2 ? 2 : 1];
   const int h_row = 4 * tg.s04 + hc0;                         // tile row of the hidden activation h[hc0]
@@ -211,22 +211,23 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
       }
     }
     pt_.mark(1);
-    // ---- (2) hidden cotangents for 4 samples x 8 hidden columns per thread:
+    // ---- (2) hidden cotangents for 4 samples x 4 hidden columns per thread:
     //      dh[s][c] = sum_n zeta[s][n] W2[c][n]   (+ sum_n delta_2[s][n] W1[c][n] for the h1 columns)
-    float acc[8][4];                      // [hidden column][sample]
+    float acc[4][4];                      // [hidden column][sample]
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
     auto accumulate = [&](const float* w, int nng, int row0, int nk4) {     // cotangent rows row0 + 4 k4 + e, weights W[hc0 + c][4 k4 + e]
-      for (int k4 = hk; k4 < nk4; k4 += 4) {
-        float4 z[4];
+      for (int k4 = hk; k4 < nk4; k4 += 2) {
+        float4 z[4], wv[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) z[e] = quad(tH, row0 + 4 * k4 + e, hj);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 wv = *reinterpret_cast<const float4*>(w + (((hc0 >> 2) + (c >> 2)) * nng + k4) * 16 + (c & 3) * 4);
-          const float we[4] = {wv.x, wv.y, wv.z, wv.w};
+        for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             acc[c][0] = fmaf(z[e].x, we[e], acc[c][0]); acc[c][1] = fmaf(z[e].y, we[e], acc[c][1]);
@@ -235,17 +236,15 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
         }
       }
     };
-    auto finish = [&](int row_dst) {       // combine the quarters, act', zero the pads, raw -> tH, lo -> tL
-      float sel[2][4];                     // quarter hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free)
+    auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
+      float sel[2][4];                     // half hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free selects)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 16);
           if ((c >> 1) == hk) sel[c & 1][i] = v;
         }
-      }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * hk + cc;
