@@ -54,7 +54,9 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
   if (eligible && !(path && !strcmp(path, "simt"))) {
     if (cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt.total) != cudaSuccess)
       return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", gt.total);
-    grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(p, gt, n_items);
+    int flush_items = kGtFlushItems;
+    if (const char* e = getenv("PSPDE_GRAD_FLUSH_ITEMS")) { const int v = atoi(e); if (v >= 1) flush_items = v; }
+    grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(p, gt, n_items, flush_items);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
     *used_tc = true;
@@ -108,7 +110,11 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
   if (cfg->N < 1 || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return false;
   const int sms = pspde_sm_count();
   cp.n_tiles128 = (cfg->K_local + kTcP - 1) / kTcP;
-  cp.wave = cp.n_tiles128 < sms ? cp.n_tiles128 : sms;
+  // tiles per wave: two per SM (fewer launches and accumulator flushes, finer quantisation of the last wave);
+  // PSPDE_WAVE_TILES_PER_SM overrides (1 halves the checkpoint buffer)
+  int per_sm = 2;
+  if (const char* e = getenv("PSPDE_WAVE_TILES_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
+  cp.wave = cp.n_tiles128 < per_sm * sms ? cp.n_tiles128 : per_sm * sms;
   cp.c4 = tc_ckpt_c4(tg);
   cp.s0 = tg.s0;
   const long long items = (long long)cp.wave * cfg->N * (kTcP / kP);
@@ -238,7 +244,8 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
       for (int t0 = 0; t0 < cp.n_tiles128; t0 += cp.wave) {
         const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
         p.tile0 = t0; p.n_tiles = nt;
-        const cudaError_t ce = tc_launch_t<true>(p, tg, nt, (cudaStream_t)stream);
+        const int sms = pspde_sm_count();
+        const cudaError_t ce = tc_launch_t<true>(p, tg, nt < sms ? nt : sms, (cudaStream_t)stream);
         g_launches++;
         if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
         const long long items = (long long)nt * cfg->N * (kTcP / kP);

@@ -9,7 +9,9 @@
 // float4: element (row r, sample 4 j + i) at j * LBO + r * 16 + i * 4 bytes, the canonical no-swizzle K-major operand
 // layout of tcgen05.mma (8-row x 16-byte core matrices, SBO = 128 B).  All columns -- [a0 | h1 | h2] and
 // [zeta | delta_2 | delta_1] -- are rows of ONE such matrix, so the A operand (two M tiles: rows 0..127, 128..255) and
-// the B operand (rows from zeta on, N = 176 at the C2 shape) are windows of the same tile.  (MN-major descriptors,
+// the B operand (rows from zeta on: zeta padded to a multiple of 16 | delta_2 | delta_1, N = 176 at the C2 shape) are
+// windows of the same tile; the zeta columns are issued right after the copy (beside the hidden-cotangent FMA code),
+// the delta columns when they exist.  (MN-major descriptors,
 // which would accept the checkpoint layout without the transpose, returned zeros for kind::tf32 without swizzle.)
 // FP32 equivalence as in tc_sm100.cuh: the tile holds the raw FP32 values, which the tensor core truncates to TF32
 // (hi = trunc(x)), a second tile holds lo = x - trunc(x); three passes lo*hi + hi*lo + hi*hi into the FP32
@@ -29,14 +31,15 @@ namespace pspde {
 constexpr int kGtS = 64;                 // samples per work item (half a checkpoint tile) = K of one MMA group
 constexpr int kGtThreads = 512;
 constexpr int kGtQ = kGtS / 4;           // sample quads per item
+constexpr int kGtFlushItems = 4;         // accumulator flush period (items of 64 samples = 48 MMAs per accumulator)
 
 struct GradTcGeom {
   int s04;             // column groups of a0 in the checkpoint (s0 / 4)
   int act_groups;      // s04 + 16: [a0 | h1 | h2]
   int ze_groups;       // s04: zeta (d used, the rest zero)
   int g_ze, g_d2, g_d1, n_groups;        // first group of zeta / delta_2 / delta_1 in the tile; total incl. zero pad
-  int nB;              // N of the MMA (multiple of 16): zeta | delta_2 | delta_1 | pad
-  int nE;              // leading zeta columns (multiple of 16) whose MMAs are issued before the hidden cotangents exist
+  int nB;              // N of the weight-gradient product: zeta (padded to nE) | delta_2 (32) | delta_1 (32)
+  int nE;              // zeta columns padded to a multiple of 16: their MMAs are issued before the hidden cotangents exist
   int dense;
   int n_mt;            // M tiles of 128 activation columns (1 when [a0 | h1 | h2] has at most 128 columns)
   uint32_t lbo;        // bytes between sample quads of the operand tile: (4 n_groups + 1) * 16
@@ -52,10 +55,9 @@ inline bool grad_tc_geom(const NetGeom& g, int d, int s0, GradTcGeom& t) {
   t.s04 = s0 >> 2;
   t.act_groups = t.s04 + 16;
   t.ze_groups = t.s04;
-  t.g_ze = t.act_groups; t.g_d2 = t.g_ze + t.ze_groups; t.g_d1 = t.g_d2 + 8;
-  const int nb_groups = t.ze_groups + 16;
-  t.nB = ((nb_groups * 4 + 15) / 16) * 16;
-  t.nE = (4 * t.ze_groups / 16) * 16;
+  t.nE = ((4 * t.ze_groups + 15) / 16) * 16;
+  t.nB = t.nE + 64;
+  t.g_ze = t.act_groups; t.g_d2 = t.g_ze + t.nE / 4; t.g_d1 = t.g_d2 + 8;
   t.n_groups = t.g_ze + t.nB / 4;
   t.n_mt = t.act_groups > 32 ? 2 : 1;
   if (t.n_groups < 32 * t.n_mt) t.n_groups = 32 * t.n_mt;     // M tile mt reads rows [128 mt, 128 mt + 128)
@@ -87,7 +89,8 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 __device__ __forceinline__ float lo1(float x) { return tc::tf32_hi(x - trunc_tf32(x)); }
 __device__ __forceinline__ float4 lo4(const float4& v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
 
-__global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutParams prm, const GradTcGeom tg, const int n_items) {
+__global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutParams prm, const GradTcGeom tg, const int n_items,
+                                                                const int flush_items) {
   extern __shared__ float4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
   __shared__ uint64_t bar_mma;
@@ -151,8 +154,26 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
         }
     }
   };
+  // raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
+  // reduce_grad_tc_kernel sums the partials in fp64 and scatters them to theta.  A warp reads the lane quarter 32 (warp % 4).
+  // Called every flush_items items (see the note at the call site).
+  auto flush = [&]() {
+    float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
+    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
+    for (int mt = 0; mt < tg.n_mt; ++mt) {
+      if (128 * mt + 32 * qtr >= 4 * tg.act_groups) continue;      // lanes past the last activation column hold garbage rows
+      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
+        float v[8];
+        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
+        tc::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(gp + (size_t)(mt * tg.nB + c0 + i) * 128 + 32 * qtr + lane, v[i]);   // RED: no round trip; one writer per address
+      }
+    }
+  };
   uint32_t ph = 0;
   bool first = true, pending = false;
+  int since_flush = 0;
   PhaseTimer pt_;          // debug: [0] wait for the tensor core, [1] copy + transpose, [2] hidden cotangents, [3] MMA issue, [4] zeta . W2', [5] delta_2 + barrier, [6] delta_2 . W1' + delta_1, [2] fences + barrier
   pt_.start(prm.prof, tid == 32 ? 0 : 1);
 
@@ -176,6 +197,11 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
       // the tensor core must be done with the tile of the previous item before it is overwritten (the loads above are
       // in flight meanwhile)
       if (pending) { tc::mbar_wait(&bar_mma, ph); ph ^= 1u; pending = false; tc::fence_after_sync(); }
+      // The tensor core does not round its FP32 accumulation to nearest: the error of a sum kept in tensor memory grows
+      // linearly with the number of MMAs that went into it (measured: 1.1e-5 relative after 25 items against 1.3e-6
+      // after one).  Every flush_items items the accumulators are therefore added to the CTA's partial (round-to-nearest
+      // FP32 adds, L2 resident) and started over -- here, where the pipeline has to wait for the tensor core anyway.
+      if (since_flush >= flush_items) { flush(); first = true; since_flush = 0; }
       pt_.mark(0);
 #pragma unroll
       for (int it = 0; it < MAXI; ++it) {
@@ -202,7 +228,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0 && tg.nE > 0) { tc::fence_after_sync(); issue(0, tg.nE, first); }
+    if (tid == 0) { tc::fence_after_sync(); issue(0, tg.nE, first); }
     if (item + (int)gridDim.x < n_items) {                    // next item -> L2 while the hidden cotangents are formed
       const int nitem = item + gridDim.x, nts = nitem / 2, nhalf = nitem - nts * 2;
       for (int q = tid; q < src_groups * 8; q += kGtThreads) {                           // 8 lines of 128 B per column group
@@ -276,29 +302,17 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
     pt_.mark(2);
     if (tid == 0) {
       tc::fence_after_sync();
-      issue(tg.nE, tg.nB - tg.nE, first);
+      issue(tg.nE, 64, first);
       tc::mma_commit(&bar_mma);
     }
     first = false;
     pending = true;
     pt_.mark(3);
+    ++since_flush;
   }
   if (pending) { tc::mbar_wait(&bar_mma, ph); tc::fence_after_sync(); }
 
-  // ---- flush: raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
-  // reduce_grad_tc_kernel sums the partials and scatters them to theta.  A warp reads the lane quarter 32 (warp % 4).
-  if (!first) {
-    float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
-    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
-    for (int mt = 0; mt < tg.n_mt; ++mt)
-      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
-        float v[8];
-        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
-        tc::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gp[(size_t)(mt * tg.nB + c0 + i) * 128 + 32 * qtr + lane] += v[i];
-      }
-  }
+  if (!first) flush();
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
@@ -321,9 +335,9 @@ static __global__ void reduce_grad_tc_kernel(const NetGeom g, const GradTcGeom t
     if (col < 0) continue;
     int l, n;
     if (c < 4 * tg.ze_groups) { l = 2; n = c; }
-    else if (c < 4 * tg.ze_groups + 32) { l = 1; n = c - 4 * tg.ze_groups; }
-    else if (c < 4 * tg.ze_groups + 64) { l = 0; n = c - 4 * tg.ze_groups - 32; }
-    else continue;
+    else if (c < tg.nE) continue;
+    else if (c < tg.nE + 32) { l = 1; n = c - tg.nE; }
+    else { l = 0; n = c - tg.nE - 32; }
     const LayerGeom& y = g.layer[l];
     const int r = col - y.in_start;
     if (r < 0 || r >= y.Kp || n >= y.N) continue;

@@ -17,8 +17,9 @@ theta = pt.randn(n_theta, device="cuda", generator=gen) * 0.1
 ws = pt.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) + 4 * n_theta * 160, dtype=pt.uint8, device="cuda")
 out = pt.empty(n_theta, device="cuda")
 names = ["wait tensor core", "copy + transpose", "fences + barrier", "MMA issue", "zeta . W2'", "delta_2 + barrier", "delta_2 . W1' + delta_1"]
-for path in ("tc", "simt"):
-    os.environ["PSPDE_GRAD_PATH"] = path
+for path in ("tc", "tc64", "simt"):
+    os.environ["PSPDE_GRAD_PATH"] = path[:2] if path != "simt" else path
+    os.environ["PSPDE_GRAD_FLUSH_ITEMS"] = path[2:] if path[:2] == "tc" and path[2:] else "4"
     call = lambda: lib.pspde_grad_from_ckpt(ctypes.byref(cfg), theta.data_ptr(), ck.data_ptr(), slots, s0, out.data_ptr(), ws.data_ptr(), ws.numel(), None)
     assert call() == 0, lib.pspde_last_error()
     pt.cuda.synchronize()
@@ -28,8 +29,8 @@ for path in ("tc", "simt"):
         e0.record(); call(); e1.record(); pt.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[2]
     items = slots * N * 2 / 148
-    print("%s: %.3f ms for %d samples -> %.0f cycles per 64-sample item per SM, %.1f TFLOP/s algorithmic (29 960 MAC/sample)"
-          % (path, ms, slots * 128 * N, ms * 1e-3 * 1.965e9 / items, 2 * 29960 * slots * 128 * N / ms / 1e9))
+    print("%s (flush every %s items): %.3f ms for %d samples -> %.0f cycles per 64-sample item per SM, %.1f TFLOP/s algorithmic (29 960 MAC/sample)"
+          % (path, os.environ["PSPDE_GRAD_FLUSH_ITEMS"], ms, slots * 128 * N, ms * 1e-3 * 1.965e9 / items, 2 * 29960 * slots * 128 * N / ms / 1e9))
     if path == "tc":
         buf = pt.zeros(16, dtype=pt.int64, device="cuda")
         lib.pspde_set_profile_buffer(ctypes.c_void_p(buf.data_ptr())); call(); pt.cuda.synchronize(); lib.pspde_set_profile_buffer(None)
