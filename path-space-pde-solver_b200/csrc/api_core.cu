@@ -195,7 +195,7 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
   }
   p.stats_partial = reinterpret_cast<double*>(workspace);
   int grid = pl.grid;
-  rc = launch_forward(cfg, pl, p, !(diag && diag->mode != 0), stream, &grid);
+  rc = launch_forward(cfg, pl, p, true, stream, &grid);
   if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, grid, stats);

@@ -98,7 +98,8 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
 // activations h1, h2 and the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt -- to the
 // per-wave checkpoint buffer (RolloutParams::ckpt) that grad_kernel consumes.  Rows with zero cotangents (padding,
 // trajectories dropped by the host because their D was non-finite) are written as zeros: inert in the gradient.
-template <int NG, bool CKPT>
+// DIAG = true: additionally the u_L2 diagnostic of solver.py:491-494 from the per-step device tables (include/pspde.h).
+template <int NG, bool CKPT, bool DIAG>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const RolloutParams prm, const TcGeom tg) {
   extern __shared__ float4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
     tc::fence_before_sync();
     tc::mbar_arrive(&bars[0]);
     if (tid == 0) issue(0, ph);
-    float yp = (part == 0 && prm.y0) ? __ldg(prm.y0) : 0.f, zsp = 0.f, gp = 0.f, fip = 0.f;
+    float yp = (part == 0 && prm.y0) ? __ldg(prm.y0) : 0.f, zsp = 0.f, gp = 0.f, fip = 0.f, ulp = 0.f;
     PhaseTimer pt_;          // debug: [0,2,4] wait for MMA group 0/1/2, [1,3] hidden epilogues, [5] SDE step, [6] noise
     pt_.start(prm.prof, tid == 32 ? 0 : 1);      // an ordinary thread (thread 0 also issues the MMAs)
 
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       pt_.mark(4);
       // Branch-free per element: the problem vectors are zero on the [t | 1 | pad] columns (so x stays put there) and Z
       // is exactly zero on them (zero weight columns); only the time column is patched afterwards.
-      float zz = 0.f, zxi = 0.f, ff = 0.f;
+      float zz = 0.f, zxi = 0.f, ff = 0.f, ul = 0.f;
       // network time of the next step: (n + 1) dt, or the caller's grid (importance sampling, Solver.Z_n :360-362)
       const float t_next = (prm.t_index && !last) ? (float)__ldg(prm.t_index + n + 1) * prm.dt_net : (float)(n + 1) * dt;
       const float cm = adaptive ? -1.0f : 0.f;
@@ -322,6 +323,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                 const float drift = fmaf(av[i], x, -(4.0f * kv[i] * (x * (x * x - 1.0f))));   // OU: kappa = 0; double well: a = 0
                 float xn = x + (drift + bv[i] * (cm * z)) * dt + (bv[i] * ee) * sq;
                 ff = fmaf(pv[i] * xn, xn, ff);
+                if (DIAG && j0 + i < d) {                                                  // (-Z - u*(X_{n+1}, t_n))^2, solver.py:492-493
+                  const int j = j0 + i;
+                  float us;
+                  if (prm.u_mode == 1) us = __ldg(prm.u_tab + (size_t)(2 * n) * d + j) + __ldg(prm.u_tab + (size_t)(2 * n + 1) * d + j) * xn;
+                  else {
+                    const float xc = fminf(fmaxf(xn, -prm.u_xb), prm.u_xb - 2.0f * prm.u_dx);
+                    int cell = (int)floorf((xc + prm.u_xb) / prm.u_dx);
+                    cell = cell < 0 ? 0 : (cell >= prm.u_nx1 ? prm.u_nx1 - 1 : cell);
+                    us = __ldg(prm.u_tab + ((size_t)(2 * n) + (j < prm.u_d1 ? 0 : 1)) * prm.u_nx1 + cell);
+                  }
+                  const float du = -z - us;
+                  ul = fmaf(du, du, ul);
+                }
                 xn = (j0 + i == d) ? t_next : xn;                                          // the time column
                 X[gi][i] = xn;
                 tc::tf32_split(xn, H[4 * u + i], Lo[4 * u + i]);
@@ -364,6 +378,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       yp += (run + (adaptive ? -zz : 0.f)) * dt + zxi * sq;
       zsp += run * dt;
       fip += ff * dt;
+      if (DIAG) ulp += ul * dt;
       if (last) gp = gg;
       else {
         tc::wait_st();
@@ -379,17 +394,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
     if (part != 0) {
       float* e = sExch + 4 * (kTcP * (part - 1) + p);
       e[0] = yp; e[1] = zsp; e[2] = gp; e[3] = fip;
+      if (DIAG) sExch[4 * kTcP * (kTcTPP - 1) + kTcP * (part - 1) + p] = ulp;
     }
     __syncthreads();
     if (part == 0) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       if (in) {
-        float Y = yp, ZS = zsp, Gv = gp, FI = fip;
+        float Y = yp, ZS = zsp, Gv = gp, FI = fip, UL = ulp;
 #pragma unroll
         for (int r = 1; r < kTcTPP; ++r) {
           const float* e = sExch + 4 * (kTcP * (r - 1) + p);
           Y += e[0]; ZS += e[1]; Gv += e[2]; FI += e[3];
+          if (DIAG) UL += sExch[4 * kTcP * (kTcTPP - 1) + kTcP * (r - 1) + p];
         }
+        if (DIAG && prm.uL2) prm.uL2[k] = UL;
         if (prm.Y_N) prm.Y_N[k] = Y;
         if (prm.gX) prm.gX[k] = Gv;
         if (prm.Zsum) prm.Zsum[k] = ZS;
@@ -423,23 +441,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
 }
 
 // NG instantiations: the smallest one that holds tg.ng column groups per thread
-template <int NG, bool CKPT>
+template <int NG, bool CKPT, bool DIAG>
 inline cudaError_t tc_launch_one(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
+  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
   if (e != cudaSuccess) return e;
-  rollout_tc_fwd_kernel<NG, CKPT><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
+  rollout_tc_fwd_kernel<NG, CKPT, DIAG><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
   return cudaGetLastError();
 }
-template <bool CKPT>
+template <bool CKPT, bool DIAG = false>
 inline cudaError_t tc_launch_t(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  if (tg.ng <= 1) return tc_launch_one<1, CKPT>(p, tg, grid, stream);
-  if (tg.ng <= 2) return tc_launch_one<2, CKPT>(p, tg, grid, stream);
-  if (tg.ng <= 4) return tc_launch_one<4, CKPT>(p, tg, grid, stream);
-  if (tg.ng <= 7) return tc_launch_one<7, CKPT>(p, tg, grid, stream);
-  return tc_launch_one<kTcMaxG, CKPT>(p, tg, grid, stream);
+  if (tg.ng <= 1) return tc_launch_one<1, CKPT, DIAG>(p, tg, grid, stream);
+  if (tg.ng <= 2) return tc_launch_one<2, CKPT, DIAG>(p, tg, grid, stream);
+  if (tg.ng <= 4) return tc_launch_one<4, CKPT, DIAG>(p, tg, grid, stream);
+  if (tg.ng <= 7) return tc_launch_one<7, CKPT, DIAG>(p, tg, grid, stream);
+  return tc_launch_one<kTcMaxG, CKPT, DIAG>(p, tg, grid, stream);
 }
 inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  return tc_launch_t<false>(p, tg, grid, stream);
+  return p.u_mode != 0 ? tc_launch_t<false, true>(p, tg, grid, stream) : tc_launch_t<false, false>(p, tg, grid, stream);
 }
 // column groups (float4) per (tile slot, step) of the checkpoint buffer: a0 (s0) | h1 (hp) | h2 (hp) | zeta (s0)
 inline int tc_ckpt_c4(const TcGeom& tg) { return 2 * (tg.s0 >> 2) + 2 * (tg.hp >> 2); }

@@ -663,3 +663,37 @@ def test_checkpointed_backward_rejects_ineligible_configuration(monkeypatch):
     with pytest.raises(RuntimeError, match="shape class"):
         eng.backward_detached(S._theta.detach(), pt.ones(64, device="cuda"), None, Call(offset=0),
                               pt.empty(eng.n_theta, device="cuda"))
+
+
+@pytest.mark.parametrize("kind,d,K", [("llgc", 100, 700), ("lqgc", 10, 333), ("dwm", 6, 200)])
+def test_tc_forward_u_l2_diagnostic_matches_fma_forward(monkeypatch, kind, d, K):
+    """u_l2_error_flag=True (the reference default, solver.py:491-494): the diagnostic of the tensor-core forward kernel
+    against the FP32-FMA forward kernel on identical Philox noise, affine tables (LLGC, LQGC) and lookup tables (DW)."""
+    import pspde
+    from pspde.fused import Call
+    if kind == "dwm":
+        prob = pspde.DoubleWell_multidim(d=d, d_1=2, d_2=d - 2, T=0.5, eta=3, kappa=5, device="cuda")
+        prob.compute_reference_solution(delta_t=0.005, nx=200)
+        prob.compute_reference_solution_2(delta_t=0.005, nx=200)
+    elif kind == "lqgc":
+        prob = pspde.LQGC(d=d, T=0.5, delta_t=0.005, device="cuda")
+    else:
+        prob = pspde.LLGC(d=d, T=0.5, device="cuda")
+    S = pspde.Solver("u", prob, K=K, L=1, delta_t=0.01, time_approx="inner", detach_forward=True, u_l2_error_flag=True,
+                     early_stopping_time=None, verbose=False)
+    if kind != "dwm":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+        S.update_Phis()
+    eng = S._get_engine()
+    assert eng.udiag is not None
+    theta = S._theta.detach()
+    outs = {}
+    for path in ("simt", "tc"):
+        monkeypatch.setenv("PSPDE_FWD_PATH", path)
+        eng.uL2.zero_()
+        eng.forward(theta, None, Call(offset=4))
+        pt.cuda.synchronize()
+        outs[path] = (eng.uL2.clone(), eng.Y_N.clone())
+    assert float(outs["simt"][0].min()) > 0
+    assert relerr(outs["tc"][0].cpu().numpy(), outs["simt"][0].cpu().numpy()) < TOL
+    assert relerr(outs["tc"][1].cpu().numpy(), outs["simt"][1].cpu().numpy()) < TOL
