@@ -89,8 +89,11 @@ uint64_t     pspde_launch_count(void);
 void         pspde_set_profile_buffer(unsigned long long* dev_buf16);
 /* number of parameters in theta for cfg (all N sets in TIME_NONE mode); <0 on invalid cfg */
 int64_t      pspde_theta_size(const pspde_cfg* cfg);
-/* scratch bytes the rollout entry points need for cfg (upper bound over all of them) */
+/* scratch bytes the rollout entry points need for cfg (upper bound over all of them; for the tensor-core shape
+ * class this includes the per-wave checkpoint buffer of pspde_rollout_bwd_detached, <= 24 GB) */
 size_t       pspde_workspace_bytes(const pspde_cfg* cfg);
+/* scratch bytes of the forward-only entry points (pspde_rollout_fwd / _fwd_diag, pspde_importance_sampling) */
+size_t       pspde_workspace_bytes_fwd(const pspde_cfg* cfg);
 
 /* Forward rollout -- replaces solver.py:433-494 (initialize_training_data + the N-step loop) and the
  * reductions of loss_function (:164-192).  Per path: X_N (nullable, K x d), Y_N, gX = g(X_N),

@@ -110,11 +110,16 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
   if (cfg->N < 1 || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return false;
   const int sms = pspde_sm_count();
   cp.n_tiles128 = (cfg->K_local + kTcP - 1) / kTcP;
-  // tiles per wave: two per SM (fewer launches and accumulator flushes, finer quantisation of the last wave);
-  // PSPDE_WAVE_TILES_PER_SM overrides (1 halves the checkpoint buffer)
+  // tiles per wave: two per SM (fewer launches, finer quantisation of the last wave) while the checkpoint buffer stays
+  // below 12 GB, else one per SM up to 24 GB, else the configuration (very long horizons) takes the recompute kernel.
+  // PSPDE_WAVE_TILES_PER_SM overrides the first choice.
   int per_sm = 2;
   if (const char* e = getenv("PSPDE_WAVE_TILES_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
-  cp.wave = cp.n_tiles128 < per_sm * sms ? cp.n_tiles128 : per_sm * sms;
+  const size_t tile_bytes = (size_t)cfg->N * tc_ckpt_c4(tg) * kTcP * 16;
+  auto wave_of = [&](int ps) { return cp.n_tiles128 < ps * sms ? cp.n_tiles128 : ps * sms; };
+  if ((size_t)wave_of(per_sm) * tile_bytes > ((size_t)12 << 30)) per_sm = 1;
+  if ((size_t)wave_of(per_sm) * tile_bytes > ((size_t)24 << 30)) return false;
+  cp.wave = wave_of(per_sm);
   cp.c4 = tc_ckpt_c4(tg);
   cp.s0 = tg.s0;
   const long long items = (long long)cp.wave * cfg->N * (kTcP / kP);
@@ -140,6 +145,12 @@ int64_t pspde_theta_size(const pspde_cfg* cfg) {
   NetGeom g;
   if (build_geom(g, cfg->net_id, cfg->n_layers, cfg->dims, cfg->time_mode, cfg->d)) { fail(-3, "bad network geometry"); return -1; }
   return (int64_t)g.n_params * (cfg->time_mode == PSPDE_TIME_NONE ? (cfg->n_sets > 0 ? cfg->n_sets : cfg->N) : 1);
+}
+
+size_t pspde_workspace_bytes_fwd(const pspde_cfg* cfg) {
+  Plan pl;
+  if (make_plan(cfg, false, false, pl)) return 0;
+  return pl.stats_bytes + 256;
 }
 
 size_t pspde_workspace_bytes(const pspde_cfg* cfg) {

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "pspde_set_profile_buffer": (None, [_P]),
     "pspde_theta_size": (ctypes.c_int64, [_CFG]),
     "pspde_workspace_bytes": (ctypes.c_size_t, [_CFG]),
+    "pspde_workspace_bytes_fwd": (ctypes.c_size_t, [_CFG]),
     "pspde_rollout_fwd": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_rollout_fwd_diag": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(pspde_udiag),
                                               _P, ctypes.c_size_t, _P]),

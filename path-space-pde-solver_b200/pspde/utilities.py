@@ -42,7 +42,7 @@ def do_importance_sampling_me(problem, model, K, control='approx', simulate_naiv
                      xi_strides=strides, n_sets=(model.N if eng.time_mode == L.TIME_NONE else 0))
     f32 = dict(dtype=pt.float32, device=dev)
     Y, gX, F, X = pt.empty(Kl, **f32), pt.empty(Kl, **f32), pt.empty(Kl, **f32), pt.empty(Kl, d, **f32)
-    ws = pt.empty(max(int(lib.pspde_workspace_bytes(ctypes.byref(cfg))), 4096), dtype=pt.uint8, device=dev)
+    ws = pt.empty(max(int(lib.pspde_workspace_bytes_fwd(ctypes.byref(cfg))), 4096), dtype=pt.uint8, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = lib.pspde_importance_sampling(ctypes.byref(cfg), p(model._theta.detach()), p(eng.pack), p(eng.x0), xi_ptr,
                                        p(t_index), ctypes.c_float(float(model.delta_t)), p(X), p(Y), p(gX), p(F), p(ws),
