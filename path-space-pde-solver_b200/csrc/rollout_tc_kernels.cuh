@@ -18,7 +18,7 @@
 // Per step: G0 = a0.B0 -> h1 = relu(pre1)^2 -> G1 += h1.B1 -> h2 = relu(pre2)^2 -> G2 += h2.B2 -> Z; the
 // Euler-Maruyama update then runs on the registers of the thread that owns the column and writes the next a0
 // straight back to tensor memory (tcgen05.st): activations never take a shared-memory layout.  Each product is
-// FP32-equivalent through the 3-pass hi/lo split of tc_sm100.cuh.  Thread 0 issues the MMAs; the hand-offs are
+// FP32-equivalent through the 3-pass hi/lo split of tc_sm100.cuh.  One thread (kTcIssuer) issues the MMAs; the hand-offs are
 // mbarriers (operands ready: every thread arrives; group done: tcgen05.commit).
 #pragma once
 #if !defined(PSPDE_EMULATE)
@@ -30,6 +30,8 @@ namespace pspde {
 constexpr int kTcP = 128;        // trajectories per tile = tensor-memory lanes
 constexpr int kTcTPP = 4;        // threads per trajectory (column parts); 16 warps per CTA
 constexpr int kTcThreads = kTcP * kTcTPP;
+constexpr int kTcIssuer = 15 * 32; // the thread that issues the MMAs: a lane of the last warp, whose column part is one of the
+                                   // short ones (the state columns do not divide evenly), so the issue work does not delay the slowest warp
 constexpr int kTcMaxG = 8;       // float4 column groups per thread; the kernel is instantiated for NG <= this
 
 struct TcGeom {
@@ -92,7 +94,7 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
 
 // One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread 0
 // additionally issues the MMAs: after the last arrival on an "operands ready" barrier it launches the group and
-// commits it to the matching "group done" barrier; everybody (thread 0 included) then waits for that one.
+// commits it to the matching "group done" barrier; everybody (the issuer included) then waits for that one.
 // CKPT = true (detached backward, first half): the same rollout, but instead of the per-path outputs it writes the
 // operand rows of the gradient accumulation for every step -- the network input a0 = [X_n | t_n | 1], the hidden
 // activations h1, h2 and the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt -- to the
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
 
-  // ---- MMA groups (thread 0)
+  // ---- MMA groups (thread kTcIssuer)
   const uint32_t sb = tc::smem_u32(smem);
   const uint32_t dcol = tbase + (uint32_t)tg.c_d;
   auto issue = [&](int grp, uint32_t parity) {
@@ -197,10 +199,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
     tc::wait_st();
     tc::fence_before_sync();
     tc::mbar_arrive(&bars[0]);
-    if (tid == 0) issue(0, ph);
+    if (tid == kTcIssuer) issue(0, ph);
     float yp = (part == 0 && prm.y0) ? __ldg(prm.y0) : 0.f, zsp = 0.f, gp = 0.f, fip = 0.f, ulp = 0.f;
     PhaseTimer pt_;          // debug: [0,2,4] wait for MMA group 0/1/2, [1,3] hidden epilogues, [5] SDE step, [6] noise
-    pt_.start(prm.prof, tid == 32 ? 0 : 1);      // an ordinary thread (thread 0 also issues the MMAs)
+    pt_.start(prm.prof, tid == 32 ? 0 : 1);      // an ordinary thread (kTcIssuer also issues the MMAs)
 
     for (int n = 0; n < N; ++n) {
       const bool last = (n == N - 1);
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         tc::wait_st();
         tc::fence_before_sync();
         tc::mbar_arrive(&bars[1 + hl]);
-        if (tid == 0) issue(1 + hl, ph);
+        if (tid == kTcIssuer) issue(1 + hl, ph);
         if (hl == 0) draw(NA, NB); else draw(NB, NG);
         pt_.mark(2 * hl + 1);
       }
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         tc::mbar_arrive(&bars[0]);
       }
       ph ^= 1u;
-      if (!last && tid == 0) issue(0, ph);
+      if (!last && tid == kTcIssuer) issue(0, ph);
       pt_.mark(5);
     }
 
