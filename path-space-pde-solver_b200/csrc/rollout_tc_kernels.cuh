@@ -92,7 +92,7 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
   }
 }
 
-// One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread 0
+// One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread kTcIssuer
 // additionally issues the MMAs: after the last arrival on an "operands ready" barrier it launches the group and
 // commits it to the matching "group done" barrier; everybody (the issuer included) then waits for that one.
 // CKPT = true (detached backward, first half): the same rollout, but instead of the per-path outputs it writes the
