@@ -33,11 +33,13 @@ extern "C" {
  *                      b_i = -4 kappa_i x_i (x_i^2 - 1), sigma = I, f = 0, g = sum eta_i (x_i - 1)^2
  *   PSPDE_PROBLEM_HEAT HeatEquation (problems.py:1733-1764), diffusion loss only:
  *                      b = 0, sigma = sqrt(2) I, h = 0, terminal f = |x|^2
+ *   PSPDE_PROBLEM_ALLEN_CAHN AllenCahn (problems.py:1175-1218), diffusion loss only:
+ *                      b = 0, sigma = sqrt(2) I, h = y - y^3, terminal f = 1 / (2 + 2/5 |x|^2)
  * Parameter pack `prob` (fp32): 7 vectors of length d, in this order
  *      a_diag | b_diag | p_diag | r_diag | alpha | kappa | eta
  * followed, when PSPDE_FLAG_DENSE_AB is set, by the row-major d x d matrices A then B (the diagonal
  * vectors are then ignored for drift/diffusion).  P and R are diagonal in every reference problem. */
-enum { PSPDE_PROBLEM_OU = 0, PSPDE_PROBLEM_DW = 1, PSPDE_PROBLEM_HEAT = 2 };
+enum { PSPDE_PROBLEM_OU = 0, PSPDE_PROBLEM_DW = 1, PSPDE_PROBLEM_HEAT = 2, PSPDE_PROBLEM_ALLEN_CAHN = 3 };
 enum { PSPDE_FLAG_DENSE_AB = 1 };
 
 /* networks (function_space.py).  theta is the flat concatenation of module.parameters():
@@ -176,7 +178,9 @@ int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const fl
  *
  * cfg: net_id = PSPDE_NET_DENSENET with one output (the value function V, function_space.py:116-140),
  * time_mode = PSPDE_TIME_LAST (input [X, t], solver.py:1079), dims[0] = d + 1, problem_id = PSPDE_PROBLEM_HEAT
- * (b = a_diag x = 0, sigma = diag(b_diag) = sqrt(2) I, h = 0).  T_end = problem.T.  Per path k:
+ * (b = a_diag x = 0, sigma = diag(b_diag) = sqrt(2) I, h = 0) or PSPDE_PROBLEM_ALLEN_CAHN (same with h = y - y^3: Y then
+ * also collects -h(V(X_n, t_n)) dt on every active step, :1141, and the value row of step n gets the cotangent
+ * cD act (-dh/dy dt) in the backward).  T_end = problem.T.  Per path k:
  *     Y = V(X_0, t_0);  for n < N:  act = !stopped & (t + dt <= T_end)                       (:1119, :1131)
  *         Y += (grad_x V(X, t) . (sigma xi_n sqrt(dt))) act      [= sum(Z * xi) sqrt(dt), :1100-1104, :1141-1142]
  *         X += (b(X) dt + sigma xi_n sqrt(dt)) act;  t += dt act;  stopped |= !act           (:1116-1117, :1145-1155)

@@ -307,8 +307,13 @@ def grad_attached(problem, nets, xi, dt, N, X0, wY, wZ, wG, time_mode="first", y
 
 
 # ------------------------------------------------------------------ diffusion loss (solver.py:1062-1163, h == 0)
-def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0):
-    """Value and theta-gradient of the diffusion loss, unbounded domain, non-adaptive; net input is [X, t]."""
+ALLEN_CAHN = dict(h=lambda y: y - y ** 3, h_y=lambda y: 1 - 3 * y ** 2, f=lambda x: 1 / (2 + 2 / 5 * (x ** 2).sum(1)))
+
+
+def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0, pde=None):
+    """Value and theta-gradient of the diffusion loss, unbounded domain, non-adaptive; net input is [X, t].
+    pde = None: heat equation (h == 0, terminal |x|^2); pde = ALLEN_CAHN: h(y) = y - y^3, the value row of every
+    active step then carries the cotangent w act h_y dt (as in `elliptic` below)."""
     dtype = X0.dtype
     K, d = X0.shape
     dt = dtype.type(np.float32(dt))
@@ -317,7 +322,7 @@ def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0
     # terminal-condition term on the first K_boundary interior samples (:1063-1064)
     aT = np.concatenate([X0[:K_boundary], np.full((K_boundary, 1), T, dtype)], 1)
     vT, tapeT = net.forward(aT)
-    fT = (X0[:K_boundary] ** 2).sum(1)
+    fT = (X0[:K_boundary] ** 2).sum(1) if pde is None else pde["f"](X0[:K_boundary])
     rT = vT[:, 0] - fT
     loss = alpha[1] * (rT ** 2).mean()
     grad = net.vjp(tapeT, (alpha[1] * 2 * rT / K_boundary)[:, None])
@@ -335,9 +340,13 @@ def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0
         v = (xis[n] @ Bt) * s                                      # direction B xi sqrt(dt)
         a0 = np.concatenate([X, t[:, None]], 1)
         da0 = np.concatenate([v, np.zeros((K, 1), dtype)], 1)
-        _, dy, tape = net.forward_tangent(a0, da0)
+        y, dy, tape = net.forward_tangent(a0, da0)
+        hy = np.zeros(K, dtype)
+        if pde is not None:
+            Y = Y - pde["h"](y[:, 0]) * dt * act
+            hy = pde["h_y"](y[:, 0])
         Y = Y + dy[:, 0] * act
-        steps.append((tape, act.copy()))
+        steps.append((tape, act.copy(), hy))
         X = X + (problem.b(X) * dt + v) * act[:, None]
         t = t + dt * act
         K_count += int(act.sum())
@@ -347,8 +356,8 @@ def diffusion(problem, net, X0, t0, xis, dt, N, K_boundary, alpha=(1.0, 1.0, 1.0
     loss = loss + alpha[0] * (r ** 2).mean()
     w = alpha[0] * 2 * r / K
     grad = grad + net.vjp(tapeE, w[:, None]) - net.vjp(tape0, w[:, None])
-    for tape, act in steps:
-        grad = grad + net.vjp_tangent(tape, np.zeros((K, 1), dtype), (-w * act)[:, None])
+    for tape, act, hy in steps:
+        grad = grad + net.vjp_tangent(tape, (w * act * hy * dt)[:, None], (-w * act)[:, None])
     return dict(loss=loss, grad=grad, K_count=K_count, X=X, t=t, Y=Y)
 
 

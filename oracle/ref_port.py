@@ -134,6 +134,14 @@ def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
         p.h = lambda t, x, y, z: pt.zeros(x.shape[0], dtype=dtype)
         p.f = lambda x: (x ** 2).sum(1)
         p.v_true = lambda x, t: (x ** 2).sum(1) + 2 * (p.T - t) * d
+    elif kind == "allencahn":
+        # problems.py:1175-1218 (modus 'pt'); the notebook sets boundary_distance = 7.0 after construction
+        p.T = 0.3 if T is None else T
+        p.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(dtype)
+        p.boundary_distance = kw.get("boundary_distance", 2.0)
+        p.b = lambda x: pt.zeros_like(x)
+        p.h = lambda t, x, y, z: y - y ** 3
+        p.f = lambda x: 1 / (2 + 2 / 5 * (x ** 2).sum(1))
     elif kind in ("expsphere", "expball", "expball_sin"):
         # problems.py:962-992, :995-1028, :1031-1064 (elliptic, unit ball, Dirichlet data g = exp(alpha |x|^2))
         a = float(kw.get("alpha", 1.0))
@@ -420,6 +428,12 @@ def elliptic_train_loop(problem, params, K, K_boundary, N, delta_t, L, lr, alpha
         if times is not None:
             times.append(time.time() - t0)
     return losses, kcounts
+
+
+def sample_ball_uniform_square(K, d, radius, dtype=pt.float32):
+    """GeneralSolver(uniform_square=True), solver.py:1041-1043: direction from the cube, radius U."""
+    X = (pt.rand(K, d) * 2 - 1).to(dtype)
+    return radius * X / pt.sqrt((X ** 2).sum(1)).unsqueeze(1) * pt.rand(K).to(dtype).unsqueeze(1)
 
 
 def sample_ball(K, d, radius, dtype=pt.float32):

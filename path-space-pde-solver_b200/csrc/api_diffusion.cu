@@ -38,8 +38,8 @@ int validate_diffusion(const pspde_cfg* c, float T_end, const pspde_elliptic* el
   if (c->net_id != PSPDE_NET_DENSENET) return fail(-3, "the diffusion loss needs a DenseNet value function (function_space.py:116-140)");
   if (c->time_mode != PSPDE_TIME_LAST) return fail(-3, "the value network sees [X, t] (solver.py:1079): time_mode must be TIME_LAST");
   if (c->dims[c->n_layers] != 1) return fail(-3, "the value network has one output (got %d)", c->dims[c->n_layers]);
-  if (c->problem_id != PSPDE_PROBLEM_HEAT && c->problem_id != PSPDE_PROBLEM_OU)
-    return fail(-4, "problem_id %d is not supported by the diffusion rollout (h must vanish)", c->problem_id);
+  if (c->problem_id != PSPDE_PROBLEM_HEAT && c->problem_id != PSPDE_PROBLEM_OU && c->problem_id != PSPDE_PROBLEM_ALLEN_CAHN)
+    return fail(-4, "problem_id %d is not supported by the diffusion rollout (h = 0 or Allen-Cahn)", c->problem_id);
   if (c->problem_flags & PSPDE_FLAG_DENSE_AB) return fail(-4, "the diffusion rollout needs diagonal drift / diffusion");
   if (c->noise_mode != PSPDE_NOISE_INJECT && c->noise_mode != PSPDE_NOISE_PHILOX) return fail(-5, "unknown noise_mode");
   return 0;
@@ -69,6 +69,7 @@ void fill_diff_params(const pspde_cfg* c, float T_end, const DiffPlan& pl, Diffu
   p.noise_mode = c->noise_mode; p.seed = c->seed; p.offset = c->offset;
   p.xs_n = c->xi_stride_n; p.xs_k = c->xi_stride_k; p.xs_j = c->xi_stride_j;
   p.n_tiles = pl.n_tiles;
+  if (c->problem_id == PSPDE_PROBLEM_ALLEN_CAHN) { p.hf.id = HFUN_ALLEN_CAHN; p.hf.d = c->d; }     // h = y - y^3 (problems.py:1203)
 }
 
 void fill_elliptic(const pspde_cfg* c, const pspde_elliptic* ell, DiffusionParams& p) {

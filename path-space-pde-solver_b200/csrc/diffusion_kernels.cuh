@@ -33,9 +33,11 @@
 namespace pspde {
 
 enum { DOMAIN_TIME = 0, DOMAIN_SPHERE = 1, DOMAIN_BOX = 2 };
-enum { HFUN_ZERO = 0, HFUN_EXP_LINEAR = 1, HFUN_EXP_NONLINEAR = 2, HFUN_EXP_NONLINEAR_SIN = 3, HFUN_HELMHOLTZ = 4 };
+enum { HFUN_ZERO = 0, HFUN_EXP_LINEAR = 1, HFUN_EXP_NONLINEAR = 2, HFUN_EXP_NONLINEAR_SIN = 3, HFUN_HELMHOLTZ = 4,
+       HFUN_ALLEN_CAHN = 5 };
 
-// h(x, y), dh/dy and the exact solution of the elliptic problems (problems.py:962-1064, :1614-1654).
+// h(x, y), dh/dy and the exact solution of the elliptic problems (problems.py:962-1064, :1614-1654); Allen-Cahn
+// (parabolic, problems.py:1203-1204): h = y - y^3.
 //   r2 = |x|^2;  sx = sin(a_1 pi x_0) sin(a_2 pi x_1) (Helmholtz only);  hp = {alpha} or {k, a_1, a_2}
 struct HFun {
   int id, d;
@@ -50,6 +52,7 @@ struct HFun {
         const float pi = 3.14159265358979323846f, k2 = p0 * p0;
         return k2 * y + (p1 * pi) * (p1 * pi) * sx + (p2 * pi) * (p2 * pi) * sx - k2 * sx;
       }
+      case HFUN_ALLEN_CAHN: return y - y * y * y;
       default: return 0.f;
     }
   }
@@ -60,6 +63,7 @@ struct HFun {
       case HFUN_EXP_NONLINEAR:     return -2.0f * a * (a * 2.0f * r2 + (float)d) - 2.0f * y;
       case HFUN_EXP_NONLINEAR_SIN: return -2.0f * a * (a * 2.0f * r2 + (float)d) - 2.0f * y * cosf(expf(2.0f * a * r2) - y * y);
       case HFUN_HELMHOLTZ:         return p0 * p0;
+      case HFUN_ALLEN_CAHN:        return 1.0f - 3.0f * y * y;
       default: return 0.f;
     }
   }
@@ -440,7 +444,9 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           const float V = sOut[p * 4], dV = sOut[(P + p) * 4];
           if (n == 0) { sY[p] = V; if (k < prm.K_local && prm.V0) prm.V0[k] = V; }
           if (step) {
-            if (domain == DOMAIN_TIME) sY[p] += dV * sA[p];    // solver.py:1141-1142 with h == 0
+            if (domain == DOMAIN_TIME) {                       // solver.py:1141-1142
+              if (sA[p] != 0.f) sY[p] += (hf.id != HFUN_ZERO ? -hf.h(0.f, 0.f, V) * dt : 0.f) + dV;
+            }
             else {                                             // solver.py:768-769 (c = 0) and the V_L2 diagnostic (:733)
               const float r2 = sR2[p], sx = sSX[p];
               if (sA[p] != 0.f) sY[p] += -hf.h(r2, sx, V) * dt + dV;

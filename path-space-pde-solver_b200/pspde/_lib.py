@@ -8,7 +8,7 @@ import ctypes
 import os
 
 PSPDE_MAX_LAYERS = 4
-PROBLEM_OU, PROBLEM_DW, PROBLEM_HEAT = 0, 1, 2
+PROBLEM_OU, PROBLEM_DW, PROBLEM_HEAT, PROBLEM_ALLEN_CAHN = 0, 1, 2, 3
 FLAG_DENSE_AB = 1
 NET_DENSENET, NET_MLP_TANH = 0, 1
 TIME_FIRST, TIME_NONE, TIME_LAST = 0, 1, 2

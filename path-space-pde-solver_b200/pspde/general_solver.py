@@ -169,6 +169,7 @@ class GeneralSolver:
         self.loss_with_stopped, self.boundary_loss = loss_with_stopped, boundary_loss
         self.print_every, self.verbose = print_every, verbose
         self.noise, self.process_group = noise, process_group
+        self.uniform_square = uniform_square
         off = []
         if loss_method != 'diffusion':
             off.append('loss_method=%r' % loss_method)
@@ -178,9 +179,9 @@ class GeneralSolver:
             off.append('adaptive / attached forward process')
         if getattr(problem, 'boundary', 'unbounded') != 'unbounded':
             off.append('boundary=%r' % problem.boundary)
-        if sample_center or loss_with_stopped or uniform_square or solve_linear_L2_projection or full_hessian \
+        if sample_center or loss_with_stopped or solve_linear_L2_projection or full_hessian \
                 or PINN_log_variance or K_test_log is not None:
-            off.append('sample_center / loss_with_stopped / uniform_square / L2 projection / K_test_log')
+            off.append('sample_center / loss_with_stopped / L2 projection / K_test_log')
         if off:
             raise NotImplementedError("off the fused hot path: " + ", ".join(off))
         if noise not in ('philox', 'inject'):
@@ -247,13 +248,23 @@ class GeneralSolver:
         lo, hi = self._k_lo, self._k_hi
         if self.noise == 'inject':
             R = self.problem.boundary_distance
-            X = pt.randn(self.K, self.d)
-            X = R * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * (pt.rand(self.K).unsqueeze(1) ** (1 / self.d))
+            if self.uniform_square:                                                         # solver.py:1041-1043
+                X = pt.rand(self.K, self.d) * 2 - 1
+                X = R * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * (pt.rand(self.K).unsqueeze(1))
+            else:
+                X = pt.randn(self.K, self.d)
+                X = R * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * (pt.rand(self.K).unsqueeze(1) ** (1 / self.d))
             t0 = pt.rand(self.K, 1) * self.problem.T
             xis = pt.stack([pt.randn(self.K, self.d) for _ in range(self.N)])
             return DiffusionCall(X[lo:hi].contiguous().to(self.device), t0[lo:hi, 0].contiguous().to(self.device),
                                  xis[:, lo:hi].contiguous().to(self.device), self._iteration)
         X0, t0 = eng.sample(float(self.problem.boundary_distance), self._iteration)
+        if self.uniform_square:      # direction from the cube, radius U (not U^(1/d)): a per-iteration device generator
+            gen = pt.Generator(device=self.device).manual_seed((self.seed * 1000003 + self._iteration) % (2 ** 63))
+            X = pt.rand(self.K, self.d, device=self.device, generator=gen) * 2 - 1
+            X = float(self.problem.boundary_distance) * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * \
+                pt.rand(self.K, 1, device=self.device, generator=gen)
+            X0 = X[lo:hi].contiguous()
         return DiffusionCall(X0, t0, None, self._iteration)
 
     def gradient_descent(self, call):

@@ -397,6 +397,37 @@ class HeatEquation:
         return L.PROBLEM_HEAT, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
 
 
+class AllenCahn:
+    """Allen-Cahn equation d_t V + Laplace V + V - V^3 = 0, V(x, T) = 1 / (2 + 2/5 |x|^2) (problems.py:1175-1218; the
+    d = 100 benchmark of the 'Allen-Cahn' notebook).  The reference's numpy / torch switch ``modus`` is kept as an
+    attribute for notebook compatibility; everything here is torch on the device."""
+
+    def __init__(self, name="Allen-Cahn", d=1, T=0.3, seed=42, modus="pt", device=None):
+        self.device = default_device() if device is None else pt.device(device)
+        np.random.seed(seed)
+        self.modus, self.name, self.d, self.T = modus, name, d, T
+        self.B = (pt.sqrt(pt.tensor(2.0)) * pt.eye(d)).to(self.device)
+        self.B_pt = self.B
+        self.X_0 = np.zeros(d)
+        self.sigma_modus, self.boundary, self.boundary_distance = "constant", "unbounded", 2.0
+
+    def b(self, x):
+        return pt.zeros_like(x)
+
+    def sigma(self, x):
+        return self.B
+
+    def h(self, t, x, y, z):
+        return y - y ** 3
+
+    def f(self, x):
+        return 1 / (2 + 2 / 5 * (x ** 2).sum(1))
+
+    def functor_pack(self):
+        z = pt.zeros(self.d)
+        return L.PROBLEM_ALLEN_CAHN, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
+
+
 # ---------------------------------------------------------------------------------------------- elliptic problems
 class _ExponentialOnBall:
     """Common part of the elliptic toy problems on the unit ball (problems.py:962-1064): b = 0, sigma = sqrt(2) I,

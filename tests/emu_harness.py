@@ -118,9 +118,9 @@ class Runner:
         return out
 
 
-def diffusion_cfg(K, d, N, dt, arch, noise=L.NOISE_INJECT, k_offset=0, seed=0, offset=0):
+def diffusion_cfg(K, d, N, dt, arch, noise=L.NOISE_INJECT, k_offset=0, seed=0, offset=0, problem_id=L.PROBLEM_HEAT):
     dims = [d + 1] + [int(a) for a in arch] + [1]
-    return L.make_cfg(K, d, N, np.float32(dt), L.PROBLEM_HEAT, L.NET_DENSENET, dims, L.TIME_LAST, adaptive=False,
+    return L.make_cfg(K, d, N, np.float32(dt), problem_id, L.NET_DENSENET, dims, L.TIME_LAST, adaptive=False,
                       k_offset=k_offset, noise_mode=noise, seed=seed, offset=offset, xi_strides=(d, 1, K * d), n_sets=0)
 
 
@@ -161,14 +161,17 @@ class DiffusionRunner:
         L.check(self.lib, rc)
         return grad
 
-    def iteration(self, g, theta, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0):
-        """loss, grad, K_count, per-path outputs of one GeneralSolver iteration (solver.py:1062-1064, :1076-1163)."""
-        K, d, N = g["K"], g["d"], g["N"]
+    def iteration(self, g, theta, K_boundary, alpha=(1.0, 1.0, 1.0), T=1.0, kind="heat"):
+        """loss, grad, K_count, per-path outputs of one GeneralSolver iteration (solver.py:1062-1064, :1076-1163);
+        kind 'heat' (h == 0, terminal |x|^2) or 'allencahn' (h = y - y^3, terminal 1 / (2 + 2/5 |x|^2))."""
+        pid = L.PROBLEM_HEAT if kind == "heat" else L.PROBLEM_ALLEN_CAHN
+        f_term = (lambda x: (x ** 2).sum(1)) if kind == "heat" else (lambda x: 1 / (2 + 2 / 5 * (x ** 2).sum(1)))
+        K, d, N = int(g["K"]), int(g["d"]), int(g["N"])
         X0 = np.ascontiguousarray(g["X0"], np.float32)
         t0 = np.ascontiguousarray(g["t0"], np.float32).reshape(-1)
         xis = np.ascontiguousarray(g["xis"], np.float32)
         pack = heat_pack(d)
-        cfg = diffusion_cfg(K, d, N, g["delta_t"], g["arch"])
+        cfg = diffusion_cfg(K, d, N, g["delta_t"], g["arch"], problem_id=pid)
         f = self.fwd(cfg, T, theta, pack, X0, t0, xis)
         r = f["VE"].astype(np.float64) - f["Y"]
         loss = alpha[0] * np.mean(r ** 2)
@@ -176,10 +179,10 @@ class DiffusionRunner:
         grad = self.bwd(cfg, T, theta, pack, X0, t0, xis, -w, w, -w).astype(np.float64)
         # terminal condition on the first K_boundary samples (N = 0 call at t = T)
         Kb = K_boundary
-        cfgb = diffusion_cfg(Kb, d, 0, g["delta_t"], g["arch"])
+        cfgb = diffusion_cfg(Kb, d, 0, g["delta_t"], g["arch"], problem_id=pid)
         Xb, tb = np.ascontiguousarray(X0[:Kb]), np.full(Kb, T, np.float32)
         fb = self.fwd(cfgb, T, theta, pack, Xb, tb)
-        rT = fb["V0"].astype(np.float64) - (Xb.astype(np.float64) ** 2).sum(1)
+        rT = fb["V0"].astype(np.float64) - f_term(Xb.astype(np.float64))
         loss += alpha[1] * np.mean(rT ** 2)
         grad += self.bwd(cfgb, T, theta, pack, Xb, tb, None, alpha[1] * 2 * rT / Kb, None, None)
         return dict(loss=loss, grad=grad, K_count=int(f["stats"][1]), **f)

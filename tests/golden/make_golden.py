@@ -126,11 +126,17 @@ def run_hjb_case(tag, kind, d, pkw, K, delta_t, net, time_approx, loss_method, d
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
 
 
-def run_diffusion_case(tag, d, K, K_boundary, N, delta_t, arch, seed=42, full=True):
-    """GeneralSolver, HeatEquation, loss 'diffusion' (solver.py:1001-1206), L=1, lr frozen to 0."""
-    problem = RP.HeatEquation(d=d, T=1)
+def run_diffusion_case(tag, d, K, K_boundary, N, delta_t, arch, seed=42, full=True, kind="heat", alpha=(1.0, 1.0, 1.0)):
+    """GeneralSolver, HeatEquation (or AllenCahn as in its notebook: T = 0.3, boundary_distance = 7, uniform_square),
+    loss 'diffusion' (solver.py:1001-1206), L=1, lr frozen to 0."""
+    if kind == "heat":
+        problem = RP.HeatEquation(d=d, T=1)
+    else:
+        problem = RP.AllenCahn(d=d, T=0.3)
+        problem.modus = "pt"
+        problem.boundary_distance = 7.0
     G = RS.GeneralSolver(problem, tag, seed=seed, delta_t=delta_t, N=N, lr=0.0, L=1, K=K, K_boundary=K_boundary,
-                         alpha=[1.0, 1.0, 1.0], loss_method="diffusion", verbose=False)
+                         alpha=list(alpha), loss_method="diffusion", verbose=False, uniform_square=(kind != "heat"))
     G.V = RF.DenseNet(d_in=d + 1, d_out=1, lr=0.0, arch=list(arch), seed=seed)
     theta0 = [q.detach().clone() for q in G.V.parameters()]
     G.train()
@@ -138,17 +144,18 @@ def run_diffusion_case(tag, d, K, K_boundary, N, delta_t, arch, seed=42, full=Tr
     loss = G.loss_log[0]
     # replicate the reference's draw order (solver.py:1003, :1045-1046, :1078, :1106)
     pt.manual_seed(seed)
-    X0 = orc.sample_ball(K, d, problem.boundary_distance)
+    X0 = orc.sample_ball(K, d, problem.boundary_distance) if kind == "heat" else \
+        orc.sample_ball_uniform_square(K, d, problem.boundary_distance)
     t0 = pt.rand(K, 1) * problem.T
     xis = pt.stack([pt.randn(K, d) for _ in range(N)])
-    op = orc.make_problem("heat", d, T=1)
-    o = orc.diffusion_iteration(op, [q.clone() for q in theta0], X0, t0, xis, delta_t, N, K_boundary)
+    op = orc.make_problem("heat", d, T=1) if kind == "heat" else orc.make_problem("allencahn", d, boundary_distance=7.0)
+    o = orc.diffusion_iteration(op, [q.clone() for q in theta0], X0, t0, xis, delta_t, N, K_boundary, alpha)
     errs = dict(loss=abs(float(o["loss"]) - loss) / abs(loss), grad=rel(flat(o["grads"]), flat(grads)),
                 kcount=abs(o["K_count"] - G.K_log[0]))
     print("%-28s loss=%.7e |grad|=%.6e K_count=%d  oracle-vs-ref: %s" % (
         tag, loss, np.linalg.norm(flat(grads)), G.K_log[0], " ".join("%s=%.1e" % kv for kv in errs.items())))
     assert errs["loss"] < 1e-6 and errs["grad"] < 1e-5 and errs["kcount"] == 0, errs
-    out = dict(kind="heat", d=d, K=K, K_boundary=K_boundary, N=N, delta_t=delta_t, arch=np.array(arch), seed=seed,
+    out = dict(kind=kind, alpha=np.array(alpha, dtype=np.float64), T=float(problem.T), d=d, K=K, K_boundary=K_boundary, N=N, delta_t=delta_t, arch=np.array(arch), seed=seed,
                loss=np.float64(loss), K_count=G.K_log[0], grad_norm=np.float64(np.linalg.norm(flat(grads))),
                X_end=o["X"].numpy(), t_end=o["t"].numpy(), Y_end=o["Y"].numpy())
     if full:
@@ -196,6 +203,19 @@ def run_elliptic_case(tag, kind, d, K, K_boundary, N, delta_t, arch, alpha, seed
                         loss=np.float64(loss), K_count=E.K_log[0], V_L2=np.float64(E.V_L2_log[0]),
                         theta=flat(theta0), grad=flat(grads), Xb=Xb.numpy(), X0=X0.numpy(), xis=xis.numpy(),
                         X_end=o["X"].numpy(), Y_end=o["Y"].numpy(), stopped=o["stopped"].numpy())
+
+
+def allen_cahn_cases():
+    run_diffusion_case("diff_allencahn_d20", 20, 64, 50, 25, 1e-3, (30, 30), kind="allencahn", alpha=(10.0, 1.0, 1.0))
+
+    def g6():       # the 'Allen-Cahn' notebook: d = 100, K = 200, N = 25, dt = 1e-3, alpha = [10, 1, 1], uniform_square
+        prob = RP.AllenCahn(d=100, T=0.3)
+        prob.modus = "pt"
+        prob.boundary_distance = 7.0
+        return RS.GeneralSolver(prob, "G6", seed=42, delta_t=1e-3, N=25, lr=1e-3, L=3, K=200, K_boundary=50,
+                                alpha=[10.0, 1.0, 1.0], loss_method="diffusion", verbose=False, uniform_square=True)
+
+    run_loss_log_case("loop_G6", g6, 3)
 
 
 def elliptic_cases():
@@ -257,6 +277,9 @@ def main():
     global run_hjb_case
     if only == ["elliptic"]:
         elliptic_cases()
+        return
+    if only == ["allencahn"]:
+        allen_cahn_cases()
         return
     if only:
         _orig = run_hjb_case
@@ -343,6 +366,7 @@ def main():
     run_loss_log_case("loop_G3b", g3("relative_entropy", False), 2)
     run_loss_log_case("loop_G4", g4, 2)
     elliptic_cases()
+    allen_cahn_cases()
 
 
 if __name__ == "__main__":

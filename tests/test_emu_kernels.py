@@ -292,6 +292,19 @@ def test_diffusion_golden_parity_small():
     assert abs(np.linalg.norm(o["grad"]) - g["grad_norm"]) < 1e-5 * g["grad_norm"]
 
 
+def test_diffusion_allen_cahn_golden_parity():
+    """GeneralSolver on the Allen-Cahn problem (h = y - y^3, uniform_square start points, alpha = [10, 1, 1]) on the
+    reference's own draws: loss, K_count, end states, Y and the full gradient against the golden vectors."""
+    g = load_golden("diff_allencahn_d20")
+    run = H.DiffusionRunner(H.emu_lib())
+    o = run.iteration(g, g["theta"].astype(np.float32), int(g["K_boundary"]), alpha=tuple(g["alpha"]), T=float(g["T"]),
+                      kind="allencahn")
+    assert o["K_count"] == g["K_count"]
+    assert relerr(o["X"], g["X_end"]) < 1e-6 and relerr(o["Y"], g["Y_end"]) < 1e-5
+    assert abs(o["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    assert relerr(o["grad"], g["grad"]) < 1e-5
+
+
 def test_diffusion_ragged_and_stopping():
     """K not a multiple of the tile, paths that start close to T (stopped early) and a 3-hidden-layer net, against
     the fp64 restatement (oracle/manual.py::diffusion)."""

@@ -319,6 +319,40 @@ def test_diffusion_loss_log_G4():
     assert abs(float(G._theta.grad.norm()) - g["grad_norm"]) < 1e-4 * g["grad_norm"]
 
 
+def test_allen_cahn_golden_parity_and_loss_log():
+    """GeneralSolver on the Allen-Cahn notebook problem (h = y - y^3, uniform_square start points): one iteration on
+    the reference's draws against the golden vectors, then the notebook configuration (d = 100, K = 200, N = 25,
+    alpha = [10, 1, 1]) over three Adam iterations against the reference's loss_log."""
+    import pspde
+    g = load_golden("diff_allencahn_d20")
+    d = int(g["d"])
+
+    def make(d, K, lr, L, arch):
+        prob = pspde.AllenCahn(d=d, T=0.3, device="cuda")
+        prob.boundary_distance = 7.0
+        G = pspde.GeneralSolver(prob, "ac", seed=42, delta_t=1e-3, N=25, lr=lr, L=L, K=K, K_boundary=50,
+                                alpha=[10.0, 1.0, 1.0], loss_method="diffusion", verbose=False, noise="inject",
+                                uniform_square=True)
+        if arch is not None:
+            G.V = pspde.DenseNet(d_in=d + 1, d_out=1, lr=lr, arch=arch, seed=42)
+        return G
+
+    G = make(d, int(g["K"]), 0.0, 1, [int(a) for a in g["arch"]])
+    G.train()
+    eng = G._get_engine()
+    assert relerr(G._theta.detach().cpu().numpy(), g["theta"]) == 0
+    assert G.K_log[0] == g["K_count"]
+    assert relerr(eng.X_end.cpu().numpy(), g["X_end"]) < 1e-6
+    assert relerr(eng.Y.cpu().numpy(), g["Y_end"]) < TOL
+    assert abs(G.loss_log[0] - g["loss"]) < TOL * abs(g["loss"])
+    assert relerr(G._theta.grad.cpu().numpy(), g["grad"]) < TOL
+    g6 = load_golden("loop_G6")
+    G = make(100, 200, 1e-3, 3, None)
+    G.train()
+    assert G.K_log == [int(v) for v in g6["K_log"]]
+    assert relerr(G.loss_log, g6["loss_log"]) < 2e-5
+
+
 def test_diffusion_full_size_properties():
     """C4 size per GPU (K = 2^16 here, bounded for test time): Philox path is deterministic, independent of the
     sharding (k_offset) and linear in the cotangents; training reduces the loss and the error of V(., 0)."""

@@ -124,6 +124,32 @@ def test_diffusion_small_port_and_manual():
     assert relerr(m["grad"], g["grad"]) < 2e-5
 
 
+def test_diffusion_allen_cahn_port_and_manual():
+    g = load_golden("diff_allencahn_d20")
+    d, arch = int(g["d"]), [int(a) for a in g["arch"]]
+    dims = [d + 1] + arch + [1]
+    params, off = [], 0
+    for i in range(len(dims) - 1):
+        for s in ((sum(dims[:i + 1]), dims[i + 1]), (dims[i + 1],)):
+            n = int(np.prod(s))
+            params.append(pt.tensor(g["theta"][off:off + n].reshape(s)))
+            off += n
+    alpha, T = tuple(float(a) for a in g["alpha"]), float(g["T"])
+    prob = orc.make_problem("allencahn", d, boundary_distance=7.0)
+    o = orc.diffusion_iteration(prob, params, pt.tensor(g["X0"]), pt.tensor(g["t0"]), pt.tensor(g["xis"]),
+                                g["delta_t"], int(g["N"]), int(g["K_boundary"]), alpha)
+    assert abs(float(o["loss"]) - g["loss"]) < 1e-6 * g["loss"]
+    assert o["K_count"] == g["K_count"]
+    assert relerr(np.concatenate([q.reshape(-1).numpy() for q in o["grads"]]), g["grad"]) < 1e-6
+    net = man.Net("densenet", dims, g["theta"])
+    m = man.diffusion(man.Problem("heat", d), net, g["X0"].astype(np.float64), g["t0"].astype(np.float64),
+                      g["xis"].astype(np.float64), g["delta_t"], int(g["N"]), int(g["K_boundary"]), alpha, T=T,
+                      pde=man.ALLEN_CAHN)
+    assert abs(m["loss"] - g["loss"]) < 1e-5 * g["loss"]
+    assert m["K_count"] == g["K_count"]
+    assert relerr(m["grad"], g["grad"]) < 2e-5
+
+
 def test_diffusion_c4_shape_seeded():
     """C4 / G4 shape (d=50, DenseNet[256,256]); inputs regenerated from the seed (same torch build on every box)."""
     g = load_golden("diff_heat_d50_w256")
