@@ -220,6 +220,7 @@ int pspde_diffusion_bwd(const pspde_cfg* cfg, float T_end, const float* theta, c
  *         X += (b(X) dt + sigma xi_n sqrt(dt)) act;   stopped |= !inside                         (:741-742, :772-779)
  *   PSPDE_DOMAIN_SPHERE  inside = |X_n| < radius, tested on the point BEFORE the step (:750-751)
  *   PSPDE_DOMAIN_BOX     inside = all_j (x_l <= proposal_j <= x_r); one_boundary: only proposal_j <= x_r (:755-758)
+ *   PSPDE_DOMAIN_ANNULUS inside = radius_in < |X_n| < radius ('two_spheres', :752-753)
  * h functors (h_param[0..2]; r2 = |x|^2):
  *   PSPDE_H_ZERO                  h = 0
  *   PSPDE_H_EXP_LINEAR            ExponentialOnSphere (problems.py:985-986): -a y (4 a r2 + 2 d),                a = h_param[0]
@@ -227,16 +228,18 @@ int pspde_diffusion_bwd(const pspde_cfg* cfg, float T_end, const float* theta, c
  *   PSPDE_H_EXP_NONLINEAR_SIN     ExponentialOnBallNonlinearSin (:1057-1058): ... + sin(exp(2 a r2) - y^2)
  *   PSPDE_H_HELMHOLTZ             Helmholtz (:1645-1648), d = 2: k^2 y + ((a_1 pi)^2 + (a_2 pi)^2 - k^2) sin(a_1 pi x_0) sin(a_2 pi x_1),
  *                                 (k, a_1, a_2) = h_param
- * The exact solution used by the V_L2 diagnostic (:733) is exp(a r2) (sin sin for Helmholtz).
+ *   PSPDE_H_COMMITTOR             Committor (:1546-1580): h = 0; (a, c) = h_param[0..1] only enter the exact solution
+ * The exact solution used by the V_L2 diagnostic (:733) is exp(a r2) (sin sin for Helmholtz, the harmonic profile
+ * (a^2 - r^(2-d) a^d) / (a^2 - c^(2-d) a^d) for the committor).
  *
  * pspde_elliptic_fwd -- per path: V0 = V(X_0), VE = V(X_end), Y_end, X_end (K_local x d), VL2 = sum over the steps
  * a path entered un-stopped of (V(X_n) - v_true(X_n))^2 dt (all nullable).  stats as in pspde_diffusion_fwd.
  * With N = 0 it evaluates V at X0 (the Dirichlet boundary term of :669-670 is this call on the boundary samples).
  * pspde_elliptic_bwd -- cotangents as in pspde_diffusion_bwd; the value row of step n additionally receives
  * cD act (-dh/dy(X_n, V(X_n)) dt).  INJECT strides as in pspde_diffusion_fwd. */
-enum { PSPDE_DOMAIN_SPHERE = 1, PSPDE_DOMAIN_BOX = 2 };
+enum { PSPDE_DOMAIN_SPHERE = 1, PSPDE_DOMAIN_BOX = 2, PSPDE_DOMAIN_ANNULUS = 3 };
 enum { PSPDE_H_ZERO = 0, PSPDE_H_EXP_LINEAR = 1, PSPDE_H_EXP_NONLINEAR = 2, PSPDE_H_EXP_NONLINEAR_SIN = 3,
-       PSPDE_H_HELMHOLTZ = 4 };
+       PSPDE_H_HELMHOLTZ = 4, PSPDE_H_COMMITTOR = 6 };
 typedef struct pspde_elliptic {
   int32_t domain;        /* PSPDE_DOMAIN_*                                   */
   float   radius;        /* sphere: problem.boundary_distance                */
@@ -244,6 +247,7 @@ typedef struct pspde_elliptic {
   int32_t one_boundary;  /* box: problem.one_boundary                        */
   int32_t h_id;          /* PSPDE_H_*                                        */
   float   h_param[3];
+  float   radius_in;     /* annulus: problem.boundary_distance_1 (radius = boundary_distance_2) */
 } pspde_elliptic;
 
 size_t pspde_elliptic_workspace_bytes(const pspde_cfg* cfg, const pspde_elliptic* ell);

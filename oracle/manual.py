@@ -372,6 +372,9 @@ class EllipticProblem:
         if kind == "helmholtz":
             self.boundary, self.one_boundary, self.X_l, self.X_r = "square", False, -1.0, 1.0
             self.a_1, self.a_2, self.k = 1.0, 4.0, 1.0
+        elif kind == "committor":
+            self.boundary, self.r_in, self.r_out = "two_spheres", 1.0, 2.0
+            self.B = np.eye(d, dtype=dtype)
         else:
             self.boundary, self.boundary_distance = "sphere", 1.0
 
@@ -379,9 +382,15 @@ class EllipticProblem:
         return np.sin(self.a_1 * np.pi * x[:, 0]) * np.sin(self.a_2 * np.pi * x[:, 1])
 
     def g(self, x):
+        if self.kind == "committor":
+            return (np.sqrt((x ** 2).sum(1)) > self.r_in).astype(x.dtype)
         return self._ss(x) if self.kind == "helmholtz" else np.exp(self.alpha * (x ** 2).sum(1))
 
-    v_true = g
+    def v_true(self, x):
+        if self.kind == "committor":
+            a, c, d = self.r_in, self.r_out, self.d
+            return (a ** 2 - np.sqrt((x ** 2).sum(1)) ** (2 - d) * a ** d) / (a ** 2 - c ** (2 - d) * a ** d)
+        return self.g(x)
 
     def h(self, x, y):
         a, d, r2 = self.alpha, self.d, (x ** 2).sum(1)
@@ -391,6 +400,8 @@ class EllipticProblem:
             return -2 * a * y * (2 * a * r2 + d) + np.exp(2 * a * r2) - y ** 2
         if self.kind == "expball_sin":
             return -2 * a * y * (2 * a * r2 + d) + np.sin(np.exp(2 * a * r2) - y ** 2)
+        if self.kind == "committor":
+            return np.zeros(x.shape[0], x.dtype)
         c = (self.a_1 * np.pi) ** 2 + (self.a_2 * np.pi) ** 2 - self.k ** 2
         return self.k ** 2 * y + c * self._ss(x)
 
@@ -402,17 +413,22 @@ class EllipticProblem:
             return -2 * a * (2 * a * r2 + d) - 2 * y
         if self.kind == "expball_sin":
             return -2 * a * (2 * a * r2 + d) - 2 * y * np.cos(np.exp(2 * a * r2) - y ** 2)
+        if self.kind == "committor":
+            return np.zeros(x.shape[0], x.dtype)
         return np.full(x.shape[0], self.k ** 2, dtype=x.dtype)
 
     def inside(self, X, X_prop):
         if self.boundary == "sphere":
             return np.sqrt((X ** 2).sum(1)) < self.boundary_distance          # solver.py:750-751: X, not the proposal
+        if self.boundary == "two_spheres":
+            r = np.sqrt((X ** 2).sum(1))
+            return (r > self.r_in) & (r < self.r_out)                         # :752-753
         if self.one_boundary:
             return (X_prop <= self.X_r).all(1)
         return ((X_prop >= self.X_l) & (X_prop <= self.X_r)).all(1)
 
 
-def elliptic(problem, net, Xb, X0, xis, dt, N, alpha=(1.0, 1.0)):
+def elliptic(problem, net, Xb, X0, xis, dt, N, alpha=(1.0, 1.0), gb=None):
     """Value and theta-gradient of the elliptic diffusion loss (non-adaptive, Dirichlet term); net input is X.
         Y = V(X_0) + sum_n act_n (-h(X_n, V(X_n)) dt + grad V(X_n) . B xi_n sqrt(dt)),  r = V(X_end) - Y
         dL = sum_k w_k [dV(X_end) - dV(X_0) + sum_n act_n (h_y dt dV(X_n) - d(grad V(X_n) . v_n))],  w = 2 alpha_0 r / K
@@ -423,7 +439,7 @@ def elliptic(problem, net, Xb, X0, xis, dt, N, alpha=(1.0, 1.0)):
     s = np.sqrt(dt)
     Bt = problem.B.T
     vb, tapeb = net.forward(Xb)
-    rb = vb[:, 0] - problem.g(Xb)
+    rb = vb[:, 0] - (problem.g(Xb) if gb is None else gb)      # gb: boundary data evaluated by the caller (fp32 indicator)
     loss_b = alpha[1] * (rb ** 2).mean()
     grad = net.vjp(tapeb, (alpha[1] * 2 * rb / Xb.shape[0])[:, None])
     X = X0.copy()

@@ -157,6 +157,16 @@ def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
             p.h = lambda x, y, z: -2 * a * y * (a * 2 * (x ** 2).sum(1) + d) + pt.exp(2 * a * (x ** 2).sum(1)) - y ** 2
         else:
             p.h = lambda x, y, z: -2 * a * y * (a * 2 * (x ** 2).sum(1) + d) + pt.sin(pt.exp(2 * a * (x ** 2).sum(1)) - y ** 2)
+    elif kind == "committor":
+        # problems.py:1546-1580: two concentric spheres a < |x| < c, sigma = I, h = 0, g = 1 on the outer sphere
+        a, c = 1.0, 2.0
+        p.a, p.c = a, c
+        p.B = pt.eye(d, dtype=dtype)
+        p.boundary, p.boundary_distance_1, p.boundary_distance_2 = "two_spheres", a, c
+        p.b = lambda x: pt.zeros_like(x)
+        p.g = lambda x: (pt.sqrt((x ** 2).sum(1)) > a).to(dtype)
+        p.h = lambda x, y, z: pt.zeros(x.shape[0], dtype=dtype)
+        p.v_true = lambda x: ((a ** 2 - pt.sqrt((x ** 2).sum(1)) ** (2 - d) * a ** d) / (a ** 2 - c ** (2 - d) * a ** d))
     elif kind == "helmholtz":
         # problems.py:1614-1654 (d = 2, square [-1, 1]^2, both sides absorbing)
         assert d == 2
@@ -320,6 +330,9 @@ def elliptic_exit_mask(problem, X, X_prop):
     proposal."""
     if problem.boundary == "sphere":
         return pt.sqrt((X ** 2).sum(1)) < problem.boundary_distance                  # :750-751
+    if problem.boundary == "two_spheres":
+        r = pt.sqrt((X ** 2).sum(1))
+        return (r > problem.boundary_distance_1) & (r < problem.boundary_distance_2)   # :752-753
     if problem.boundary == "square":
         if problem.one_boundary:
             return (X_prop <= problem.X_r).all(1)                                    # :755-756
@@ -402,10 +415,16 @@ def elliptic_draws(problem, K, K_boundary, N):
     if problem.boundary == "sphere":
         Xb = sample_sphere(K_boundary, d, problem.boundary_distance)
         X0 = sample_ball(K, d, problem.boundary_distance)
+    elif problem.boundary == "two_spheres":                                          # :650-654, :694-701: K shrinks
+        Xb = pt.randn(K_boundary, d)
+        radii = pt.tensor([problem.boundary_distance_1] * int(K_boundary / 2) + [problem.boundary_distance_2] * int(K_boundary / 2))
+        Xb = radii.unsqueeze(1) * Xb / pt.sqrt((Xb ** 2).sum(1)).unsqueeze(1)
+        X0 = sample_ball(K, d, problem.boundary_distance_2)
+        X0 = X0[pt.sqrt((X0 ** 2).sum(1)) > problem.boundary_distance_1, :]
     else:
         Xb = sample_square_boundary(K_boundary, d, problem.X_l, problem.X_r, problem.one_boundary)
         X0 = (problem.X_r - problem.X_l) * pt.rand(K, d) + problem.X_l
-    xis = pt.stack([pt.randn(K, d) for _ in range(N)]) if N > 0 else None
+    xis = pt.stack([pt.randn(X0.shape[0], d) for _ in range(N)]) if N > 0 else None
     return Xb, X0, xis
 
 

@@ -29,8 +29,9 @@ int validate_diffusion(const pspde_cfg* c, float T_end, const pspde_elliptic* el
     if (c->noise_mode != PSPDE_NOISE_INJECT && c->noise_mode != PSPDE_NOISE_PHILOX) return fail(-5, "unknown noise_mode");
     if (ell->domain == PSPDE_DOMAIN_SPHERE) { if (!(ell->radius > 0.f)) return fail(-2, "sphere radius must be > 0"); }
     else if (ell->domain == PSPDE_DOMAIN_BOX) { if (!(ell->x_r > ell->x_l)) return fail(-2, "box needs x_l < x_r"); }
-    else return fail(-4, "unknown domain %d (PSPDE_DOMAIN_SPHERE | PSPDE_DOMAIN_BOX)", ell->domain);
-    if (ell->h_id < PSPDE_H_ZERO || ell->h_id > PSPDE_H_HELMHOLTZ) return fail(-4, "unknown h_id %d", ell->h_id);
+    else if (ell->domain == PSPDE_DOMAIN_ANNULUS) { if (!(ell->radius > ell->radius_in) || !(ell->radius_in > 0.f)) return fail(-2, "annulus needs 0 < radius_in < radius"); }
+    else return fail(-4, "unknown domain %d (PSPDE_DOMAIN_SPHERE | PSPDE_DOMAIN_BOX | PSPDE_DOMAIN_ANNULUS)", ell->domain);
+    if (!(ell->h_id >= PSPDE_H_ZERO && ell->h_id <= PSPDE_H_HELMHOLTZ) && ell->h_id != PSPDE_H_COMMITTOR) return fail(-4, "unknown h_id %d", ell->h_id);
     if (ell->h_id == PSPDE_H_HELMHOLTZ && c->d < 2) return fail(-4, "the Helmholtz right-hand side needs d >= 2 (problems.py:1628)");
     return 0;
   }
@@ -73,8 +74,8 @@ void fill_diff_params(const pspde_cfg* c, float T_end, const DiffPlan& pl, Diffu
 }
 
 void fill_elliptic(const pspde_cfg* c, const pspde_elliptic* ell, DiffusionParams& p) {
-  p.domain = ell->domain == PSPDE_DOMAIN_SPHERE ? DOMAIN_SPHERE : DOMAIN_BOX;
-  p.radius = ell->radius; p.x_l = ell->x_l; p.x_r = ell->x_r; p.one_boundary = ell->one_boundary;
+  p.domain = ell->domain == PSPDE_DOMAIN_SPHERE ? DOMAIN_SPHERE : ell->domain == PSPDE_DOMAIN_BOX ? DOMAIN_BOX : DOMAIN_ANNULUS;
+  p.radius = ell->radius; p.x_l = ell->x_l; p.x_r = ell->x_r; p.one_boundary = ell->one_boundary; p.radius_in = ell->radius_in;
   p.hf.id = ell->h_id; p.hf.d = c->d; p.hf.p0 = ell->h_param[0]; p.hf.p1 = ell->h_param[1]; p.hf.p2 = ell->h_param[2];
 }
 

@@ -24,7 +24,8 @@
 // Elliptic variant (EllipticSolver.train, solver.py:628-790): the value network sees X only
 // (TIME_NONE), the path stops when it leaves the domain instead of at t = T, and h(x, y) need not vanish:
 //        act = !stopped & inside;   Y += (-h(X_n, V(X_n)) dt + grad V(X_n) . (B xi_n sqrt(dt))) act;   X += (...) act
-//   sphere: inside = |X_n| < R, tested on the point BEFORE the step (:750-751);  square: X_l <= proposal <= X_r (:755-758)
+//   sphere: inside = |X_n| < R, tested on the point BEFORE the step (:750-751);  square: X_l <= proposal <= X_r (:755-758);
+//   two spheres: R_in < |X_n| < R (:752-753)
 // V(X_n) is the value row of the pair the kernel carries anyway; in the reverse pass it receives the cotangent
 // cD act (-dh/dy(X_n, V(X_n)) dt).  The V_L2 diagnostic of :733 is accumulated from the same value row.
 #pragma once
@@ -32,12 +33,12 @@
 
 namespace pspde {
 
-enum { DOMAIN_TIME = 0, DOMAIN_SPHERE = 1, DOMAIN_BOX = 2 };
+enum { DOMAIN_TIME = 0, DOMAIN_SPHERE = 1, DOMAIN_BOX = 2, DOMAIN_ANNULUS = 3 };
 enum { HFUN_ZERO = 0, HFUN_EXP_LINEAR = 1, HFUN_EXP_NONLINEAR = 2, HFUN_EXP_NONLINEAR_SIN = 3, HFUN_HELMHOLTZ = 4,
-       HFUN_ALLEN_CAHN = 5 };
+       HFUN_ALLEN_CAHN = 5, HFUN_COMMITTOR = 6 };
 
 // h(x, y), dh/dy and the exact solution of the elliptic problems (problems.py:962-1064, :1614-1654); Allen-Cahn
-// (parabolic, problems.py:1203-1204): h = y - y^3.
+// (parabolic, problems.py:1203-1204): h = y - y^3; Committor (:1546-1580): h = 0, only the exact solution is used.
 //   r2 = |x|^2;  sx = sin(a_1 pi x_0) sin(a_2 pi x_1) (Helmholtz only);  hp = {alpha} or {k, a_1, a_2}
 struct HFun {
   int id, d;
@@ -67,7 +68,14 @@ struct HFun {
       default: return 0.f;
     }
   }
-  __host__ __device__ float v_true(float r2, float sx) const { return id == HFUN_HELMHOLTZ ? sx : expf(p0 * r2); }
+  __host__ __device__ float v_true(float r2, float sx) const {
+    if (id == HFUN_HELMHOLTZ) return sx;
+    if (id == HFUN_COMMITTOR) {      // problems.py:1578-1580 with a = p0, c = p1:  (a^2 - r^(2-d) a^d) / (a^2 - c^(2-d) a^d)
+      const float a = p0, c = p1, ad = powf(a, (float)d);
+      return (a * a - powf(sqrtf(r2), 2.0f - (float)d) * ad) / (a * a - powf(c, 2.0f - (float)d) * ad);
+    }
+    return expf(p0 * r2);
+  }
 };
 
 struct DiffusionParams {
@@ -88,7 +96,8 @@ struct DiffusionParams {
   double* stats_partial;           // [gridDim.x][4]: sum r^2, #active steps, sum r, #non-finite r
   // elliptic variant
   int domain;                      // DOMAIN_*
-  float radius, x_l, x_r;          // sphere radius / box bounds
+  float radius, x_l, x_r;          // sphere (outer) radius / box bounds
+  float radius_in;                 // annulus: inner radius
   int one_boundary;                // box: only the upper bound absorbs (solver.py:755-756)
   HFun hf;
   float* VL2;                      // forward output (per path, nullable): sum_n (V(X_n) - v_true(X_n))^2 dt over non-stopped steps
@@ -392,6 +401,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
             sSX[p] = sinf(hf.p1 * pi * xr[0]) * sinf(hf.p2 * pi * xr[1]);
           }
           if (domain == DOMAIN_SPHERE) sel = sqrtf(r2) < prm.radius;
+          else if (domain == DOMAIN_ANNULUS) sel = sqrtf(r2) > prm.radius_in && sqrtf(r2) < prm.radius;    // solver.py:752-753
           else {
             const float* vr = sAct + (P + p) * lda;
             sel = true;
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
         }
       } else {
         // ---- (e) reverse of the (value, tangent) pair; delta_l overwrites hidden segment l+1 in place
-        if (hf.id != HFUN_ZERO && step) {        // V(X_n) for dh/dy (value rows only)
+        if (hf.id != HFUN_ZERO && hf.id != HFUN_COMMITTOR && step) {        // V(X_n) for dh/dy (value rows only)
           for (int r = warp; r < P; r += NW) {
             const float* ar = sAct + r * lda + ylast.in_start;
             const float* w = prm.wpack + ylast.w_off;
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
         for (int p = tid; p < P; p += T) {
           float cv = (n == 0 ? sC0[p] : 0.f) + (step ? 0.f : sCE[p]);
           const float cd = step ? sCD[p] * sA[p] : 0.f;
-          if (hf.id != HFUN_ZERO && step) cv += cd * (-hf.h_y(sR2[p], sSX[p], sVn[p]) * dt);   // Y += -h(X_n, V(X_n)) dt
+          if (hf.id != HFUN_ZERO && hf.id != HFUN_COMMITTOR && step) cv += cd * (-hf.h_y(sR2[p], sSX[p], sVn[p]) * dt);   // Y += -h(X_n, V(X_n)) dt
           sOut[p * 4] = cv;
           sOut[(P + p) * 4] = cd;
         }

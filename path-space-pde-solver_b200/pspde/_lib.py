@@ -13,8 +13,8 @@ FLAG_DENSE_AB = 1
 NET_DENSENET, NET_MLP_TANH = 0, 1
 TIME_FIRST, TIME_NONE, TIME_LAST = 0, 1, 2
 NOISE_INJECT, NOISE_PHILOX = 0, 1
-DOMAIN_SPHERE, DOMAIN_BOX = 1, 2
-H_ZERO, H_EXP_LINEAR, H_EXP_NONLINEAR, H_EXP_NONLINEAR_SIN, H_HELMHOLTZ = 0, 1, 2, 3, 4
+DOMAIN_SPHERE, DOMAIN_BOX, DOMAIN_ANNULUS = 1, 2, 3
+H_ZERO, H_EXP_LINEAR, H_EXP_NONLINEAR, H_EXP_NONLINEAR_SIN, H_HELMHOLTZ, H_COMMITTOR = 0, 1, 2, 3, 4, 6
 ABI_VERSION = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,7 +43,7 @@ class pspde_udiag(ctypes.Structure):
 class pspde_elliptic(ctypes.Structure):
     _fields_ = [("domain", ctypes.c_int32), ("radius", ctypes.c_float), ("x_l", ctypes.c_float),
                 ("x_r", ctypes.c_float), ("one_boundary", ctypes.c_int32), ("h_id", ctypes.c_int32),
-                ("h_param", ctypes.c_float * 3)]
+                ("h_param", ctypes.c_float * 3), ("radius_in", ctypes.c_float)]
 
 
 _P = ctypes.c_void_p
@@ -135,10 +135,11 @@ def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=Tr
     return c
 
 
-def make_elliptic(domain, radius=1.0, x_l=-1.0, x_r=1.0, one_boundary=False, h_id=H_ZERO, h_param=(0.0, 0.0, 0.0)):
+def make_elliptic(domain, radius=1.0, x_l=-1.0, x_r=1.0, one_boundary=False, h_id=H_ZERO, h_param=(0.0, 0.0, 0.0),
+                  radius_in=0.0):
     e = pspde_elliptic()
     e.domain, e.radius, e.x_l, e.x_r = int(domain), float(radius), float(x_l), float(x_r)
-    e.one_boundary, e.h_id = int(bool(one_boundary)), int(h_id)
+    e.one_boundary, e.h_id, e.radius_in = int(bool(one_boundary)), int(h_id), float(radius_in)
     for i in range(3):
         e.h_param[i] = float(h_param[i]) if i < len(h_param) else 0.0
     return e

@@ -54,9 +54,15 @@ class EllipticEngine(DiffusionEngine):
         cfg = self.cfg(K, N, xis if N > 0 else None, offset)
         full = outs is None
         V0, VE, Y, X_end, _, stats = (self.V0, self.VE, self.Y, self.X_end, None, self.stats) if full else outs
+        VL2 = self.VL2 if full else None
+        if not full and N > 0:                       # a batch of another size ('two_spheres': K changes every iteration)
+            self.VL2_last = VL2 = pt.zeros(K, dtype=pt.float32, device=self.device)
+            self.stats_last = stats = pt.zeros(4, dtype=pt.float64, device=self.device)
+        elif full:
+            self.VL2_last, self.stats_last = self.VL2, self.stats
         rc = self.lib.pspde_elliptic_fwd(ctypes.byref(cfg), ctypes.byref(self.ell), self._p(theta), self._p(self.pack),
                                          self._p(X0), self._p(xis if N > 0 else None), self._p(V0), self._p(VE),
-                                         self._p(Y), self._p(X_end), self._p(self.VL2 if full else None),
+                                         self._p(Y), self._p(X_end), self._p(VL2),
                                          self._p(stats), self._p(self.workspace), self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
@@ -104,8 +110,10 @@ class EllipticSolver(GeneralSolver):
             off.append('approx_method=%r' % approx_method)
         if adaptive_forward_process or not detach_forward:
             off.append('adaptive / attached forward process')
-        if getattr(problem, 'boundary', None) not in ('sphere', 'square'):
+        if getattr(problem, 'boundary', None) not in ('sphere', 'square', 'two_spheres'):
             off.append('boundary=%r' % getattr(problem, 'boundary', None))
+        if getattr(problem, 'boundary', None) == 'two_spheres' and process_group is not None:
+            off.append("'two_spheres' (batch size changes every iteration) with a process group")
         if boundary_loss and boundary_type != 'Dirichlet':
             off.append('boundary_type=%r' % boundary_type)
         if sample_center or loss_with_stopped or uniform_square or variance_moment_split or full_hessian \
@@ -147,6 +155,10 @@ class EllipticSolver(GeneralSolver):
         if p.boundary == 'sphere':
             Xb = pt.randn(Kb, d)
             return p.boundary_distance * Xb / pt.sqrt(pt.sum(Xb ** 2, 1)).unsqueeze(1)
+        if p.boundary == 'two_spheres':                        # solver.py:650-654: half of the samples on each sphere
+            Xb = pt.randn(Kb, d)
+            radii = pt.tensor([p.boundary_distance_1] * int(Kb / 2) + [p.boundary_distance_2] * int(Kb / 2))
+            return radii.unsqueeze(1) * Xb / pt.sqrt(pt.sum(Xb ** 2, 1)).unsqueeze(1)
         h = int(Kb / 2)                                        # 'square': numpy shuffles, then one pt.rand draw
         s = np.concatenate([np.ones(h)[:, np.newaxis], np.zeros([h, d - 1])], 1)
         np.apply_along_axis(np.random.shuffle, 1, s)
@@ -165,9 +177,10 @@ class EllipticSolver(GeneralSolver):
         kernels never use (every path is stopped)."""
         p, dt = self.problem, pt.tensor(self.delta_t_np)
         sq, B = pt.sqrt(dt), p.B.cpu()
-        X, stopped, xis = X.clone(), pt.zeros(self.K, dtype=pt.bool), []
+        K = X.shape[0]
+        X, stopped, xis = X.clone(), pt.zeros(K, dtype=pt.bool), []
         for n in range(self.N):
-            xi = pt.randn(self.K, self.d)
+            xi = pt.randn(K, self.d)
             sel = ~stopped
             if int(sel.sum()) == 0:
                 break
@@ -175,6 +188,9 @@ class EllipticSolver(GeneralSolver):
             X_prop = X + (pt.mm(B, xi.t()).t() * sq) * sel.float().unsqueeze(1)
             if p.boundary == 'sphere':
                 new_sel = pt.sqrt(pt.sum(X ** 2, 1)) < p.boundary_distance
+            elif p.boundary == 'two_spheres':
+                r = pt.sqrt(pt.sum(X ** 2, 1))
+                new_sel = (r > p.boundary_distance_1) & (r < p.boundary_distance_2)
             elif p.one_boundary:
                 new_sel = pt.all(X_prop <= p.X_r, 1)
             else:
@@ -182,7 +198,7 @@ class EllipticSolver(GeneralSolver):
             act = (new_sel & ~stopped).float().unsqueeze(1)
             X = X * (1 - act) + X_prop * act
             stopped = stopped | (~new_sel & ~stopped)
-        xis += [pt.zeros(self.K, self.d)] * (self.N - len(xis))
+        xis += [pt.zeros(K, self.d)] * (self.N - len(xis))
         return pt.stack(xis)
 
     def initialize_training_data(self):
@@ -196,18 +212,34 @@ class EllipticSolver(GeneralSolver):
                 X = pt.randn(self.K, self.d)
                 X = p.boundary_distance * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * \
                     (pt.rand(self.K).unsqueeze(1) ** (1 / self.d))
+            elif p.boundary == 'two_spheres':                  # solver.py:694-701: the batch shrinks to the annulus
+                X = pt.randn(self.K_original, self.d)
+                X = p.boundary_distance_2 * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * \
+                    (pt.rand(self.K_original).unsqueeze(1) ** (1 / self.d))
+                X = X[pt.sqrt(pt.sum(X ** 2, 1)) > p.boundary_distance_1, :]
+                self.K = int(X.shape[0])
+                lo, hi = 0, self.K
             else:
                 X = (p.X_r - p.X_l) * pt.rand(self.K, self.d) + p.X_l
             xis = self._draw_increments_cpu(X)
             call = DiffusionCall(X[lo:hi].contiguous().to(self.device), None,
                                  xis[:, lo:hi].contiguous().to(self.device), self._iteration)
             call.Xb = Xb.to(self.device)
-            return call
+            call.gb = p.g(Xb).to(self.device)       # boundary data evaluated where the samples were drawn (the committor's
+            return call                             # indicator |x| > a sits exactly on the inner sphere: rounding decides)
         gen = pt.Generator(device=self.device).manual_seed((self.seed * 1000003 + self._iteration) % (2 ** 63))
         if p.boundary == 'sphere':
             X0, _ = eng.sample(float(p.boundary_distance), self._iteration)
             Xb = pt.randn(self.K_boundary, self.d, device=self.device, generator=gen)
             Xb = p.boundary_distance * Xb / pt.sqrt(pt.sum(Xb ** 2, 1)).unsqueeze(1)
+        elif p.boundary == 'two_spheres':
+            X0, _ = eng.sample(float(p.boundary_distance_2), self._iteration)
+            X0 = X0[pt.sqrt(pt.sum(X0 ** 2, 1)) > p.boundary_distance_1, :].contiguous()
+            self.K = int(X0.shape[0])
+            Xb = pt.randn(self.K_boundary, self.d, device=self.device, generator=gen)
+            radii = pt.tensor([p.boundary_distance_1] * int(self.K_boundary / 2) +
+                              [p.boundary_distance_2] * int(self.K_boundary / 2), device=self.device)
+            Xb = radii.unsqueeze(1) * Xb / pt.sqrt(pt.sum(Xb ** 2, 1)).unsqueeze(1)
         else:
             Xb = (p.X_r - p.X_l) * pt.rand(self.K_boundary, self.d, device=self.device, generator=gen) + p.X_l
             face = pt.randint(0, self.d, (self.K_boundary,), device=self.device, generator=gen)
@@ -229,14 +261,15 @@ class EllipticSolver(GeneralSolver):
         r = (VE - Y).double()
         ok = pt.isfinite(r)
         r = pt.where(ok, r, pt.zeros_like(r))
-        sums = pt.stack([(r * r).sum().detach(), call.stats[1], (~ok).sum().double(), eng.VL2.double().sum()])
+        sums = pt.stack([(r * r).sum().detach(), eng.stats_last[1], (~ok).sum().double(), eng.VL2_last.double().sum()])
         loss_local = self.alpha[0] * (r * r).sum() / self.K                                 # :790
         rank, _ = dist.world(self.process_group)
         lb = pt.zeros((), dtype=pt.float64, device=self.device)
         if self.boundary_loss and rank == 0:                                               # :669-670
             Xb = call.Xb.contiguous()
             Vb, _, _ = FusedDiffusion.apply(self._theta, eng, DiffusionCall(Xb, None, None, call.offset), 0)
-            lb = self.alpha[1] * ((Vb.double() - self.problem.g(Xb).double()) ** 2).mean()
+            gb = call.gb if getattr(call, 'gb', None) is not None else self.problem.g(Xb)
+            lb = self.alpha[1] * ((Vb.double() - gb.double()) ** 2).mean()
             loss_local = loss_local + lb
         loss_local.backward()
         self._ensure_grad_views()

@@ -551,3 +551,47 @@ class Helmholtz:
     def elliptic_spec(self):
         return L.make_elliptic(L.DOMAIN_BOX, x_l=self.X_l, x_r=self.X_r, one_boundary=self.one_boundary,
                                h_id=L.H_HELMHOLTZ, h_param=(self.k, self.a_1, self.a_2))
+
+
+class Committor:
+    """problems.py:1546-1580: committor function between two concentric spheres a < |x| < c (Brownian motion, sigma = I,
+    h = 0, boundary data 0 on the inner and 1 on the outer sphere); exact solution harmonic in r."""
+
+    def __init__(self, name="Committor", d=2, alpha=1.0, device=None):
+        self.device = default_device() if device is None else pt.device(device)
+        self.name, self.d = name, d
+        self.a, self.c = 1.0, 2.0
+        self.B = pt.eye(d).to(self.device)
+        self.X_0 = pt.zeros(d, device=self.device)
+        self.Y_0 = pt.zeros(1, device=self.device)
+        self.boundary, self.boundary_distance_1, self.boundary_distance_2 = "two_spheres", self.a, self.c
+
+    def b(self, x):
+        return pt.zeros_like(x)
+
+    def sigma(self, x):
+        return self.B
+
+    def f(self, x):
+        return pt.zeros(x.shape[0], device=x.device)
+
+    def g(self, x):
+        return (pt.sqrt((x ** 2).sum(1)) > self.a).float()
+
+    def h(self, x, y, z):
+        return pt.zeros(x.shape[0], device=x.device)
+
+    def u_true(self, x):
+        return pt.zeros(x.shape)
+
+    def v_true(self, x):
+        return ((self.a ** 2 - pt.sqrt((x ** 2).sum(1)) ** (2 - self.d) * self.a ** self.d)
+                / (self.a ** 2 - self.c ** (2 - self.d) * self.a ** self.d))
+
+    def functor_pack(self):
+        z = pt.zeros(self.d)
+        return L.PROBLEM_HEAT, 0, pt.cat([z, pt.diag(self.B).cpu(), z, z, z, z, z]).float().contiguous()
+
+    def elliptic_spec(self):
+        return L.make_elliptic(L.DOMAIN_ANNULUS, radius=self.boundary_distance_2, radius_in=self.boundary_distance_1,
+                               h_id=L.H_COMMITTOR, h_param=(self.a, self.c, 0.0))

@@ -198,6 +198,8 @@ def elliptic_spec(kind, alpha=1.0):
     if kind == "helmholtz":
         return L.make_elliptic(L.DOMAIN_BOX, x_l=-1.0, x_r=1.0, one_boundary=False, h_id=L.H_HELMHOLTZ,
                                h_param=(1.0, 1.0, 4.0))
+    if kind == "committor":
+        return L.make_elliptic(L.DOMAIN_ANNULUS, radius=2.0, radius_in=1.0, h_id=L.H_COMMITTOR, h_param=(1.0, 2.0, 0.0))
     return L.make_elliptic(L.DOMAIN_SPHERE, radius=1.0, h_id=ELLIPTIC_H[kind], h_param=(alpha, 0.0, 0.0))
 
 
@@ -246,7 +248,10 @@ class EllipticRunner:
         Xb = np.ascontiguousarray(g["Xb"], np.float32)
         xis = np.ascontiguousarray(g["xis"], np.float32)
         pack = heat_pack(d)
+        if str(g["kind"]) == "committor":              # sigma = I
+            pack[d:2 * d] = 1.0
         ell = elliptic_spec(str(g["kind"]))
+        K = X0.shape[0]                                # 'two_spheres': the start points outside the annulus were dropped
         cfg = elliptic_cfg(K, d, N, g["delta_t"], g["arch"])
         f = self.fwd(cfg, ell, theta, pack, X0, xis)
         r = f["VE"].astype(np.float64) - f["Y"]

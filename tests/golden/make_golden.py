@@ -167,7 +167,7 @@ def run_diffusion_case(tag, d, K, K_boundary, N, delta_t, arch, seed=42, full=Tr
 
 
 REF_ELLIPTIC = {"expsphere": "ExponentialOnSphere", "expball": "ExponentialOnBallNonlinear",
-                "expball_sin": "ExponentialOnBallNonlinearSin", "helmholtz": "Helmholtz"}
+                "expball_sin": "ExponentialOnBallNonlinearSin", "helmholtz": "Helmholtz", "committor": "Committor"}
 
 
 def run_elliptic_case(tag, kind, d, K, K_boundary, N, delta_t, arch, alpha, seed=42):
@@ -194,6 +194,8 @@ def run_elliptic_case(tag, kind, d, K, K_boundary, N, delta_t, arch, alpha, seed
     xis = pt.stack(o["xis"] + [pt.zeros(K, d)] * (N - len(o["xis"])))      # the reference stops drawing once all paths stopped
     errs = dict(loss=abs(float(o["loss"]) - loss) / abs(loss), grad=rel(flat(o["grads"]), flat(grads)),
                 kcount=abs(o["K_count"] - E.K_log[0]), vl2=abs(float(o["V_L2"].mean()) - E.V_L2_log[0]) / abs(E.V_L2_log[0]))
+    K = X0.shape[0]                                    # 'two_spheres' keeps only the start points in the annulus
+    assert K == E.K
     print("%-28s loss=%.7e |grad|=%.6e K_count=%d/%d V_L2=%.6e oracle-vs-ref: %s" % (
         tag, loss, np.linalg.norm(flat(grads)), E.K_log[0], K * N, E.V_L2_log[0],
         " ".join("%s=%.1e" % kv for kv in errs.items())))
@@ -223,6 +225,11 @@ def elliptic_cases():
     run_elliptic_case("ell_expball_d5", "expball", 5, 48, 10, 25, 4e-3, (16, 12), (1.0, 1.0))
     run_elliptic_case("ell_expsphere_d4", "expsphere", 4, 40, 10, 30, 1e-2, (12, 8, 8), (0.5, 2.0))  # all paths exit
     run_elliptic_case("ell_helmholtz_d2", "helmholtz", 2, 64, 20, 30, 5e-3, (20, 20), (1.0, 1.0))    # square domain
+    run_elliptic_case("ell_committor_d10", "committor", 10, 80, 20, 50, 1e-3, (30, 30), (1.0, 1.0))  # two spheres (K shrinks)
+
+    def g7():       # 'Committor function' notebook: d = 10, K = 200, N = 50, dt = 1e-3
+        return RS.EllipticSolver(RP.Committor(d=10), "G7", seed=42, delta_t=1e-3, N=50, lr=1e-3, L=3, K=200,
+                                 K_boundary=50, alpha=[1.0, 1.0], loss_method="diffusion", verbose=False)
 
     def g5():       # 'Nonlinear toy problem - elliptic with Dirichlet' notebook: d=50, K=200, N=20, dt=1e-3
         return RS.EllipticSolver(RP.ExponentialOnBallNonlinearSin(d=50), "G5", seed=42, delta_t=1e-3, N=20, lr=1e-3,
@@ -234,6 +241,7 @@ def elliptic_cases():
 
     run_loss_log_case("loop_G5", g5, 3)
     run_loss_log_case("loop_G5b", g5b, 3)
+    run_loss_log_case("loop_G7", g7, 3)
 
 
 def run_is_case(tag, kind, d, pkw, K, solver_dt, is_dt, net):

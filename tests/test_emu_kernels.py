@@ -329,14 +329,16 @@ def test_diffusion_ragged_and_stopping():
 
 
 # ---------------------------------------------------------------------------------------------- elliptic (row f4)
-@pytest.mark.parametrize("tag", ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2"])
+@pytest.mark.parametrize("tag", ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2", "ell_committor_d10"])
 def test_elliptic_golden_parity(tag):
     """EllipticSolver iteration (solver.py:646-670, :687-790) on the reference's own draws: loss, K_count, V_L2,
     end states, Y and the full gradient against golden vectors generated from the reference."""
     g = load_golden(tag)
     run = H.EllipticRunner(H.emu_lib())
-    mp = man.EllipticProblem(str(g["kind"]), int(g["d"]))
-    o = run.iteration(g, g["theta"].astype(np.float32), mp.g, alpha=tuple(g["alpha"]))
+    import torch as pt
+    from oracle import ref_port as orc
+    g_fun = lambda Xb: orc.make_problem(str(g["kind"]), int(g["d"])).g(pt.tensor(Xb, dtype=pt.float32)).numpy().astype(np.float64)
+    o = run.iteration(g, g["theta"].astype(np.float32), g_fun, alpha=tuple(g["alpha"]))
     assert o["K_count"] == g["K_count"]
     assert relerr(o["X"], g["X_end"]) < 1e-6
     assert relerr(o["Y"], g["Y_end"]) < 1e-5
@@ -438,3 +440,36 @@ def test_grad_from_checkpoint_rows(kind, d, hid):
                                   ws.nbytes, None)
     L.check(lib, rc)
     assert relerr(out, grad) < 1e-5
+
+
+def test_elliptic_annulus_variable_batch():
+    """'two_spheres' (Committor, solver.py:694-701, :752-753) in d = 3, where an eighth of the start points falls inside
+    the inner sphere and is dropped: exit through either sphere, h == 0, sigma = I, against the fp64 restatement."""
+    rng = np.random.default_rng(3)
+    d, N, dt, arch = 3, 12, 0.02, (9, 7)
+    X = rng.standard_normal((90, d))
+    X = 2.0 * X / np.linalg.norm(X, axis=1, keepdims=True) * rng.uniform(0, 1, (90, 1)) ** (1 / d)
+    X0 = np.ascontiguousarray(X[np.linalg.norm(X, axis=1) > 1.0], np.float32)
+    K = X0.shape[0]
+    assert 60 < K < 90
+    dims = [d] + list(arch) + [1]
+    n_theta = sum((sum(dims[:i + 1]) + 1) * dims[i + 1] for i in range(len(dims) - 1))
+    theta = (rng.standard_normal(n_theta) * 0.3).astype(np.float32)
+    xis = rng.standard_normal((N, K, d)).astype(np.float32)
+    lib = H.emu_lib()
+    run = H.EllipticRunner(lib)
+    pack = H.heat_pack(d)
+    pack[d:2 * d] = 1.0
+    ell = H.elliptic_spec("committor")
+    cfg = H.elliptic_cfg(K, d, N, dt, arch)
+    f = run.fwd(cfg, ell, theta, pack, X0, xis)
+    r = f["VE"].astype(np.float64) - f["Y"]
+    w = 2 * r / K
+    grad = run.bwd(cfg, ell, theta, pack, X0, xis, -w, w, -w)
+    net = man.Net("densenet", dims, theta.astype(np.float64))
+    m = man.elliptic(man.EllipticProblem("committor", d), net, X0[:1].astype(np.float64), X0.astype(np.float64),
+                     xis.astype(np.float64), dt, N, alpha=(1.0, 0.0))
+    assert 0 < int(f["stats"][1]) < K * N and int(f["stats"][1]) == m["K_count"]
+    assert relerr(f["X"], m["X"]) < 1e-6 and relerr(f["Y"], m["Y"]) < 1e-5
+    assert relerr(f["VL2"], m["V_L2"]) < 1e-4
+    assert relerr(grad, m["grad"]) < 2e-5

@@ -231,7 +231,7 @@ def test_analytic_llgc_value():
 
 
 # ---------------------------------------------------------------------------------------------- elliptic (row f4)
-ELL_TAGS = ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2"]
+ELL_TAGS = ["ell_expsin_d10", "ell_expball_d5", "ell_expsphere_d4", "ell_helmholtz_d2", "ell_committor_d10"]
 
 
 def ell_params(g):
@@ -262,8 +262,9 @@ def test_elliptic_port_and_manual(tag):
     assert relerr(np.concatenate([q.reshape(-1).numpy() for q in o["grads"]]), g["grad"]) < 2e-6
     assert 0 < int(o["stopped"].sum())                       # the exit logic is exercised
     net = man.Net("densenet", dims, g["theta"])
+    gb = orc.make_problem(kind, d).g(pt.tensor(g["Xb"])).numpy().astype(np.float64)   # fp32 like the reference (committor: indicator)
     m = man.elliptic(man.EllipticProblem(kind, d), net, g["Xb"].astype(np.float64), g["X0"].astype(np.float64),
-                     g["xis"].astype(np.float64), g["delta_t"], int(g["N"]), alpha)
+                     g["xis"].astype(np.float64), g["delta_t"], int(g["N"]), alpha, gb=gb)
     assert m["K_count"] == g["K_count"]
     assert abs(m["loss"] - g["loss"]) < 1e-5 * g["loss"]
     assert abs(m["V_L2"].mean() - g["V_L2"]) < 1e-5 * g["V_L2"]
@@ -271,11 +272,12 @@ def test_elliptic_port_and_manual(tag):
     assert relerr(m["X"], g["X_end"]) < 1e-6 and relerr(m["Y"], g["Y_end"]) < 1e-5
 
 
-@pytest.mark.parametrize("tag,kind,d", [("loop_G5", "expball_sin", 50), ("loop_G5b", "helmholtz", 2)])
-def test_elliptic_training_loop_pins(tag, kind, d):
+@pytest.mark.parametrize("tag,kind,d,N", [("loop_G5", "expball_sin", 50, 20), ("loop_G5b", "helmholtz", 2, 20),
+                                          ("loop_G7", "committor", 10, 50)])
+def test_elliptic_training_loop_pins(tag, kind, d, N):
     """Whole-loop pins: torch + numpy RNG order, rollout and Adam reproduce the reference's loss_log and K_log."""
     g = load_golden(tag)
     params = orc.densenet_init(d, 1, seed=42)
-    ll, kc = orc.elliptic_train_loop(orc.make_problem(kind, d), params, 200, 50, 20, 1e-3, 3, 1e-3, seed=42)
+    ll, kc = orc.elliptic_train_loop(orc.make_problem(kind, d), params, 200, 50, N, 1e-3, 3, 1e-3, seed=42)
     np.testing.assert_allclose(ll, g["loss_log"], rtol=2e-6)
     assert kc == [int(v) for v in g["K_log"]]
