@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
     tc::fence_after_sync();
     const uint32_t lbo = (variant & 1) ? 128u : (uint32_t)N * 16u;
     const uint32_t sbo = (variant & 1) ? (uint32_t)N * 16u : 128u;
-    tc::mma_3xtf32(d_col, a_hi, a_lo, tc::smem_u32(b_hi), tc::smem_u32(b_lo), N, K / 8, tc::idesc_tf32(128, N), false, lbo, sbo);
+    // variant bit 1: M = 64 (experiment: where do the 64 rows of D land in tensor memory?)
+    tc::mma_3xtf32(d_col, a_hi, a_lo, tc::smem_u32(b_hi), tc::smem_u32(b_lo), N, K / 8, tc::idesc_tf32((variant & 2) ? 64 : 128, N), false, lbo, sbo);
     tc::mma_commit(&bar);
   }
   if (warp < 4) {
