@@ -159,6 +159,32 @@ def test_problem_functors_match_oracle():
         assert pt.allclose(a.f(x, 0.1), b.f(x, 0.1), atol=1e-5)
 
 
+def test_elliptic_and_allen_cahn_functors_match_oracle_and_kernel_spec():
+    """Host problem classes of the diffusion-loss rows (problems.py:962-1064, :1175-1218, :1546-1580, :1614-1654) against the
+    oracle's closures, and the pspde_elliptic spec they hand to the kernels."""
+    import pspde
+    from oracle import ref_port as orc
+    from pspde import _lib as L
+    pt.manual_seed(0)
+    for kind, mine, d in (("expsphere", pspde.ExponentialOnSphere, 5), ("expball", pspde.ExponentialOnBallNonlinear, 5),
+                          ("expball_sin", pspde.ExponentialOnBallNonlinearSin, 5), ("helmholtz", pspde.Helmholtz, 2),
+                          ("committor", pspde.Committor, 4)):
+        x = pt.randn(7, d) * 0.6
+        y = pt.randn(7)
+        a, b = mine(d=d, device="cpu"), orc.make_problem(kind, d)
+        assert pt.allclose(a.h(x, y, None), b.h(x, y, None), rtol=1e-6, atol=1e-6)
+        assert pt.allclose(a.g(x), b.g(x)) and pt.allclose(a.v_true(x), b.v_true(x), rtol=1e-6)
+        assert pt.equal(a.sigma(x), b.B) and float(a.b(x).abs().max()) == 0.0
+        spec = a.elliptic_spec()
+        assert spec.domain == {"sphere": L.DOMAIN_SPHERE, "square": L.DOMAIN_BOX, "two_spheres": L.DOMAIN_ANNULUS}[a.boundary]
+        pid, flags, pack = a.functor_pack()
+        assert pid == L.PROBLEM_HEAT and flags == 0 and pt.equal(pack[d:2 * d], pt.diag(b.B))
+    a, b = pspde.AllenCahn(d=6, T=0.3, device="cpu"), orc.make_problem("allencahn", 6)
+    x, y = pt.randn(7, 6), pt.randn(7)
+    assert pt.allclose(a.h(0.1, x, y, None), b.h(0.1, x, y, None)) and pt.allclose(a.f(x), b.f(x))
+    assert a.functor_pack()[0] == L.PROBLEM_ALLEN_CAHN and a.T == b.T and pt.equal(a.B, b.B)
+
+
 GLOO_WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "path-space-pde-solver_b200"))
