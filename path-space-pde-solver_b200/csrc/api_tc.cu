@@ -21,12 +21,20 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
   // B tile: hi / lo copies in the K-major core-matrix layout
+  // variant bit 2 (experiment): B in the MN-major 128-byte-swizzled canonical layout (N == 32: one 128 B row of N per k,
+  // 8 k rows = one 1 KB atom, 16-byte chunk index xor-ed with the k row inside the atom); tiles 1 KB aligned
+  const uint32_t align_pad = (variant & 4) ? ((1024u - (tc::smem_u32(smem) & 1023u)) & 1023u) : 0u;
+  if (variant & 4) { b_hi = smem + align_pad; b_lo = b_hi + ((tile_bytes + 1023u) & ~1023u); }
   for (int q = tid; q < K * N; q += blockDim.x) {
     const int k = q / N, n = q - k * N;
     float hi, lo;
     tc::tf32_split(B[q], hi, lo);
-    *reinterpret_cast<float*>(b_hi + tc::b_tile_offset(n, k, N)) = hi;
-    *reinterpret_cast<float*>(b_lo + tc::b_tile_offset(n, k, N)) = lo;
+    // bit 5: the SWIZZLE_128B_BASE32B atom (4 k rows of 128 B, 32-byte chunk index xor-ed with the k row), atoms 512 B apart
+    const uint32_t off = (variant & 32) ? (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u + (uint32_t)((((n >> 3) & 3) ^ (k & 3)) * 32) + (uint32_t)(n & 7) * 4u
+                       : (variant & 4) ? (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + (uint32_t)(((n >> 2) ^ (k & 7)) * 16) + (uint32_t)(n & 3) * 4u
+                                       : tc::b_tile_offset(n, k, N);
+    *reinterpret_cast<float*>(b_hi + off) = hi;
+    *reinterpret_cast<float*>(b_lo + off) = lo;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -53,6 +61,20 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
     const uint32_t lbo = (variant & 1) ? 128u : (uint32_t)N * 16u;
     const uint32_t sbo = (variant & 1) ? (uint32_t)N * 16u : 128u;
     // variant bit 1: M = 64 (experiment: where do the 64 rows of D land in tensor memory?)
+    if (variant & 4) {      // MN-major B, SWIZZLE_128B: descriptor layout type 2, SBO = 1 KB between 8-k atoms; modes in bits 3..4
+      const uint32_t idesc = tc::idesc_tf32(128, N) | (1u << 16);
+      const int mode = (variant >> 3) & 3;
+      uint32_t lbo_s = (mode & 1) ? 1024u : 128u, sbo_s = (mode & 1) ? 128u : 1024u;
+      if (variant & 32) { lbo_s = (mode & 1) ? 512u : 1024u; sbo_s = (mode & 1) ? 1024u : 512u; }
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 0) ? a_lo : a_hi;
+        const uint32_t b = tc::smem_u32((pass == 1) ? b_lo : b_hi);
+        for (int s = 0; s < K / 8; ++s) {
+          const uint64_t bd = tc::smem_desc(b + (uint32_t)s * 1024u, lbo_s, sbo_s) | ((uint64_t)((mode & 2) ? 1 : 2) << 61);
+          tc::mma_tf32_ts(d_col, a + 8u * (uint32_t)s, bd, idesc, pass > 0 || s > 0);
+        }
+      }
+    } else
     tc::mma_3xtf32(d_col, a_hi, a_lo, tc::smem_u32(b_hi), tc::smem_u32(b_lo), N, K / 8, tc::idesc_tf32((variant & 2) ? 64 : 128, N), false, lbo, sbo);
     tc::mma_commit(&bar);
   }
@@ -82,7 +104,7 @@ extern "C" int pspde_tc_selftest(int K, int N, int variant, const float* A, cons
   return fail(-20, "the tensor-core path does not exist in the host emulator");
 #else
   if (K < 8 || (K & 7) || N < 16 || (N & 15) || N > 256 || 2 * K + N > 512 || !A || !B || !D) return fail(-2, "bad selftest shape");
-  const size_t smem = 2 * (size_t)tc::b_tile_bytes(K, N);
+  const size_t smem = 2 * (size_t)tc::b_tile_bytes(K, N) + 4096;
   if (smem > kMaxSmem) return fail(-6, "selftest tile too large");
   if (pspde_set_smem(tc_selftest_kernel, smem)) return fail(-11, "cudaFuncSetAttribute failed");
   PSPDE_LAUNCH(tc_selftest_kernel, 1, 160, smem, stream, K, N, variant, A, B, D);
