@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
     float hi, lo;
     tc::tf32_split(B[q], hi, lo);
     // bit 5: the SWIZZLE_128B_BASE32B atom (4 k rows of 128 B, 32-byte chunk index xor-ed with the k row), atoms 512 B apart
-    const uint32_t off = (variant & 32) ? (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u + (uint32_t)((((n >> 3) & 3) ^ (k & 3)) * 32) + (uint32_t)(n & 7) * 4u
+    // bit 6: the same physical atom read as a K-major operand (K == 32: one 128 B row of k per n, 8 n rows = 1 KB)
+    const uint32_t off = (variant & 64) ? (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)((((k >> 3) & 3) ^ (n & 3)) * 32) + (uint32_t)(k & 7) * 4u
+                       : (variant & 32) ? (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u + (uint32_t)((((n >> 3) & 3) ^ (k & 3)) * 32) + (uint32_t)(n & 7) * 4u
                        : (variant & 4) ? (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u + (uint32_t)(((n >> 2) ^ (k & 7)) * 16) + (uint32_t)(n & 3) * 4u
                                        : tc::b_tile_offset(n, k, N);
     *reinterpret_cast<float*>(b_hi + off) = hi;
@@ -62,15 +64,17 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
     const uint32_t sbo = (variant & 1) ? (uint32_t)N * 16u : 128u;
     // variant bit 1: M = 64 (experiment: where do the 64 rows of D land in tensor memory?)
     if (variant & 4) {      // MN-major B, SWIZZLE_128B: descriptor layout type 2, SBO = 1 KB between 8-k atoms; modes in bits 3..4
-      const uint32_t idesc = tc::idesc_tf32(128, N) | (1u << 16);
+      const uint32_t idesc = tc::idesc_tf32(128, N) | ((variant & 64) ? 0u : (1u << 16));
       const int mode = (variant >> 3) & 3;
       uint32_t lbo_s = (mode & 1) ? 1024u : 128u, sbo_s = (mode & 1) ? 128u : 1024u;
       if (variant & 32) { lbo_s = (mode & 1) ? 512u : 1024u; sbo_s = (mode & 1) ? 1024u : 512u; }
+      if (variant & 64) { lbo_s = (mode & 1) ? 1024u : 16u; sbo_s = (mode & 1) ? 16u : 1024u; }
+      const uint32_t k_adv = (variant & 64) ? 32u : 1024u;
       for (int pass = 0; pass < 3; ++pass) {
         const uint32_t a = (pass == 0) ? a_lo : a_hi;
         const uint32_t b = tc::smem_u32((pass == 1) ? b_lo : b_hi);
         for (int s = 0; s < K / 8; ++s) {
-          const uint64_t bd = tc::smem_desc(b + (uint32_t)s * 1024u, lbo_s, sbo_s) | ((uint64_t)((mode & 2) ? 1 : 2) << 61);
+          const uint64_t bd = tc::smem_desc(b + (uint32_t)s * k_adv, lbo_s, sbo_s) | ((uint64_t)((mode & 2) ? 1 : 2) << 61);
           tc::mma_tf32_ts(d_col, a + 8u * (uint32_t)s, bd, idesc, pass > 0 || s > 0);
         }
       }
