@@ -264,9 +264,15 @@ def run_ours(args, wl):
             c = Call(offset=1000 + i)
             flush.fill_(i & 1)
             e = [pt.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record(); eng.forward(theta, None, c); e[1].record()
+            single = eng.ckpt is not None          # the training step keeps the forward's operand rows (single rollout)
+            e[0].record(); eng.forward(theta, None, c, keep_rows=single); e[1].record()
             flush.fill_(1 - (i & 1))
-            e[2].record(); eng.backward_detached(theta, wY, None, c, grad); e[3].record()
+            e[2].record()
+            if single:
+                eng.grad_from_rows(theta, wY, c, grad)
+            else:
+                eng.backward_detached(theta, wY, None, c, grad)
+            e[3].record()
             pt.cuda.synchronize(dev)
             tf.append(e[0].elapsed_time(e[1])); tb.append(e[2].elapsed_time(e[3]))
         return tf, tb
@@ -338,7 +344,15 @@ def run_ours(args, wl):
         hid_max = 32 if eng.net_id == 0 else 31
         ckpt_path = os.environ.get("PSPDE_BWD_PATH", "") != "simt" and len(eng.dims) == 4 \
             and max(eng.dims[1:3]) <= hid_max and eng.time_mode == 0 and not (eng.flags & 1)
-        if ckpt_path:
+        single = eng.ckpt is not None
+        if ckpt_path and single:
+            s0 = (d + 2 + 7) // 8 * 8
+            ckpt_bytes = 2.0 * eng.K_local * N * (2 * (s0 // 4) + 16) * 16          # operand rows written once, read once
+            kernel = ("single-rollout step: the training forward (rollout_tc_fwd_kernel<CKPT>, timed as 'fwd') keeps the "
+                      "operand rows [a0|h1|h2|sqrt(dt) xi] of all tiles in HBM; backward = grad_tc_kernel over those rows "
+                      "(dL/dY_N applied at load, hidden cotangents in FP32 FMA, weight gradient on tcgen05 kind::tf32 3xTF32 "
+                      "with K = samples, accumulators resident in tensor memory) + reduce; no trajectory is recomputed")
+        elif ckpt_path:
             s0 = (d + 2 + 7) // 8 * 8
             ckpt_bytes = 2.0 * eng.K_local * N * (2 * (s0 // 4) + 16) * 16          # operand rows written once, read once
             kernel = ("checkpointed detached backward = rollout_tc_fwd_kernel<CKPT> (tensor-core rollout that leaves the "
@@ -353,7 +367,10 @@ def run_ours(args, wl):
                                "nominal 148 SM x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s" % (nominal or 0),
                 "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
-                "bwd_checkpoint": {"bytes_per_step": ckpt_bytes, "gbs_over_bwd": ckpt_bytes / (tb * 1e-3) / 1e9,
+                "single_rollout": bool(ckpt_path and single),
+                "bwd_checkpoint": {"bytes_per_step": ckpt_bytes,
+                                   "gbs_over_bwd": (ckpt_bytes / 2 if single else ckpt_bytes) / (tb * 1e-3) / 1e9,
+                                   "gbs_over_fwd": ckpt_bytes / 2 / (tf * 1e-3) / 1e9 if single else 0.0,
                                    "hbm_peak_gbs_measured": measured_peaks().get("hbm_gbs")} if ckpt_path else None,
                 "fwd": fwd_roofline(flops_fwd, tf, peak, eng),
                 "step": {"algorithmic_flops_per_path_step": 2.0 * (2 * M + Md),

@@ -11,7 +11,8 @@ unsigned long long* g_prof = nullptr;
 // Forward rollout launch: the tensor-core kernel (rollout_tc_kernels.cuh) for the shape class it covers, else the
 // FP32-FMA kernel.  PSPDE_FWD_PATH=simt forces the FMA kernel (A/B tests); PSPDE_FWD_PATH=tc makes an ineligible
 // configuration an error.  *grid_out = number of CTAs launched (rows of stats_partial that were written).
-static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, bool tc_allowed, void* stream, int* grid_out) {
+static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, bool tc_allowed, void* stream, int* grid_out,
+                          bool keep_ckpt = false) {
 #if !defined(PSPDE_EMULATE)
   TcGeom tg;
   const char* path = getenv("PSPDE_FWD_PATH");
@@ -22,7 +23,8 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
     const int sms = pspde_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     p.n_tiles = n_tiles;
-    const cudaError_t ce = tc_launch(p, tg, grid, (cudaStream_t)stream);
+    if (keep_ckpt) { p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; }
+    const cudaError_t ce = keep_ckpt ? tc_launch_fwd_ckpt(p, tg, grid, (cudaStream_t)stream) : tc_launch(p, tg, grid, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
     *grid_out = grid;
@@ -31,6 +33,7 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
 #else
   (void)cfg; (void)tc_allowed;
 #endif
+  if (keep_ckpt) return fail(-6, "configuration is outside the checkpointing forward's shape class");
   *grid_out = pl.grid;
   return launch_rollout<512, false, 1>(pl, p, stream);
 }
@@ -130,6 +133,25 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
 }
 #endif
 
+// Single-rollout training step: the forward pass itself leaves the operand rows of ALL tiles (unit cotangents) and the
+// gradient kernel applies dL/dY_N.  Needs the tensor-core shape class for both kernels and the adaptive (`-Z` drift)
+// process with no cotangent on Z_sum (zeta = wY sqrt(dt) xi does not involve Z).  Returns the buffer size, 0 if ineligible.
+static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl) {
+#if !defined(PSPDE_EMULATE)
+  TcGeom tg;
+  GradTcGeom gt;
+  for (const char* v : {"PSPDE_FWD_PATH", "PSPDE_BWD_PATH", "PSPDE_GRAD_PATH"})
+    if (const char* e = getenv(v)) if (!strcmp(e, "simt")) return 0;
+  if (cfg->N < 1 || !cfg->adaptive || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return 0;
+  if (!grad_tc_geom(pl.g, cfg->d, tg.s0, gt)) return 0;
+  const size_t n_tiles = (size_t)(cfg->K_local + kTcP - 1) / kTcP;
+  return align256(n_tiles * cfg->N * tc_ckpt_c4(tg) * kTcP * 16);
+#else
+  (void)cfg; (void)pl;
+  return 0;
+#endif
+}
+
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
@@ -187,9 +209,28 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
                            const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
                            double* stats, const pspde_udiag* diag, void* workspace, size_t workspace_bytes,
                            void* stream) {
+  return pspde_rollout_fwd_ckpt(cfg, theta, prob, x0, y0, xi, X_N, Y_N, gX, Zsum, stats, diag, nullptr, 0, workspace,
+                                workspace_bytes, stream);
+}
+
+size_t pspde_fwd_ckpt_bytes(const pspde_cfg* cfg) {
+  Plan pl;
+  if (make_plan(cfg, true, false, pl)) return 0;
+  return fwd_ckpt_bytes(cfg, pl);
+}
+
+int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                           const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
+                           double* stats, const pspde_udiag* diag, void* ckpt, size_t ckpt_bytes, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   Plan pl;
   int rc = make_plan(cfg, false, false, pl);
   if (rc) return rc;
+  if (ckpt) {
+    const size_t need = fwd_ckpt_bytes(cfg, pl);
+    if (!need) return fail(-6, "configuration is outside the checkpointing forward's shape class");
+    if (ckpt_bytes < need) return fail(-7, "checkpoint buffer too small (%zu < %zu)", ckpt_bytes, need);
+  }
   if (!theta || !prob || !x0) return fail(-1, "theta/prob/x0 must not be NULL");
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
   if (!workspace || workspace_bytes < pl.stats_bytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes);
@@ -205,8 +246,9 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
     p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
   }
   p.stats_partial = reinterpret_cast<double*>(workspace);
+  p.ckpt = reinterpret_cast<float*>(ckpt);
   int grid = pl.grid;
-  rc = launch_forward(cfg, pl, p, true, stream, &grid);
+  rc = launch_forward(cfg, pl, p, true, stream, &grid, ckpt != nullptr);
   if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, grid, stats);
@@ -303,6 +345,43 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
   if (rc) return rc;
   return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
+}
+
+int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const void* ckpt, size_t ckpt_bytes,
+                             const float* wY, float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+  Plan pl;
+  int rc = make_plan(cfg, true, false, pl);
+  if (rc) return rc;
+  if (!theta || !ckpt || !wY || !grad_theta) return fail(-1, "theta/ckpt/wY/grad_theta must not be NULL");
+#if !defined(PSPDE_EMULATE)
+  const size_t need = fwd_ckpt_bytes(cfg, pl);
+  if (!need) return fail(-6, "configuration is outside the checkpointing forward's shape class");
+  if (ckpt_bytes < need) return fail(-7, "checkpoint buffer too small (%zu < %zu)", ckpt_bytes, need);
+  TcGeom tg;
+  tc_geom(pl.g, cfg->d, tg);
+  const int sms = pspde_sm_count();
+  const long long n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
+  const long long items = n_tiles * cfg->N * (kTcP / kP);
+  if (items > 0x7fffffffLL) return fail(-6, "too many work items for one gradient launch");
+  const int grid = items < sms ? (int)items : sms;
+  const size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
+  if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
+  RolloutParams p;
+  fill_params(cfg, pl, p);
+  p.theta = theta; p.wY = wY;
+  p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
+  p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0;
+  p.tile0 = 0; p.ckpt_unit = 1;
+  if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
+  bool used_tc = false;
+  rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
+  if (rc) return rc;
+  if (!used_tc) return fail(-13, "internal: the forward checkpoint needs the tensor-core gradient kernel");
+  return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
+#else
+  (void)ckpt_bytes; (void)workspace; (void)workspace_bytes; (void)stream;
+  return fail(-20, "the tensor-core path does not exist in the host emulator");
+#endif
 }
 
 int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,

@@ -107,8 +107,9 @@ extern "C" int pspde_tc_selftest(int K, int N, int variant, const float* A, cons
   (void)K; (void)N; (void)variant; (void)A; (void)B; (void)D; (void)stream;
   return fail(-20, "the tensor-core path does not exist in the host emulator");
 #else
+  if ((variant & 4) && (N != 32 || K > 32)) return fail(-2, "the swizzled-operand probe is N = 32, K <= 32");
   if (K < 8 || (K & 7) || N < 16 || (N & 15) || N > 256 || 2 * K + N > 512 || !A || !B || !D) return fail(-2, "bad selftest shape");
-  const size_t smem = 2 * (size_t)tc::b_tile_bytes(K, N) + 4096;
+  const size_t smem = 2 * (size_t)tc::b_tile_bytes(K, N) + ((variant & 4) ? 4096 : 0);   // probe variants: 1 KB alignment + K-major atoms
   if (smem > kMaxSmem) return fail(-6, "selftest tile too large");
   if (pspde_set_smem(tc_selftest_kernel, smem)) return fail(-11, "cudaFuncSetAttribute failed");
   PSPDE_LAUNCH(tc_selftest_kernel, 1, 160, smem, stream, K, N, variant, A, B, D);

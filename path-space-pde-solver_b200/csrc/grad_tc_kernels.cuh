@@ -88,6 +88,13 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 // lo = x - trunc(x), rounded to TF32 so that the tensor core's own truncation of it is exact
 __device__ __forceinline__ float lo1(float x) { return tc::tf32_hi(x - trunc_tf32(x)); }
 __device__ __forceinline__ float4 lo4(const float4& v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
+// one checkpoint float4 of a sample whose cotangent w is applied here (RolloutParams::ckpt_unit): zeta columns are scaled,
+// activation columns kept; w == 0 drops the sample (selects, no branches)
+__device__ __forceinline__ float4 scale_row(const float4& v, float w, bool is_ze) {
+  const float f = is_ze ? w : 1.0f;
+  const bool keep = w != 0.f;
+  return make_float4(keep ? v.x * f : 0.f, keep ? v.y * f : 0.f, keep ? v.z * f : 0.f, keep ? v.w * f : 0.f);
+}
 
 __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutParams prm, const GradTcGeom tg, const int n_items,
                                                                 const int flush_items) {
@@ -134,6 +141,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
 
   const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
   const int src_groups = tg.act_groups + tg.ze_groups;       // the checkpoint row: [a0 | h1 | h2 | zeta]
+  const bool unit = prm.ckpt_unit != 0;
   // hidden-cotangent mapping: warp = 4 hidden columns hc0 .. hc0 + 3 of [h1 (32) | h2 (32)], lane = (sample quad, half of
   // the reduction range); the two halves are combined with one xor-shuffle
   const int hc0 = 4 * warp, hj = lane & 15, hk = lane >> 4;
@@ -186,12 +194,26 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
       constexpr int MAXI = 3;
       float4 v[MAXI][4];
       const int nq = src_groups * kGtQ;
+      // checkpoint written by the forward pass (unit cotangents): the per-path cotangent dL/dY_N of the thread's 4 samples
+      // (its sample quad is tid & 15 in every iteration below) scales the zeta rows; a path with zero cotangent is dropped
+      // entirely, so that a diverged trajectory (non-finite rows) with zero weight cannot poison the sums.
+      float wq[4] = {1.f, 1.f, 1.f, 1.f};
+      if (unit) {
+        const int k0 = (prm.tile0 + ts / prm.N) * kCkP + half * kGtS + 4 * (tid & (kGtQ - 1));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wq[i] = (k0 + i < prm.K_local) ? __ldg(prm.wY + k0 + i) : 0.f;
+      }
 #pragma unroll
       for (int it = 0; it < MAXI; ++it) {
         const int q = tid + it * kGtThreads;
         if (q < nq) {
           const float4* sp = src + (size_t)(q >> 4) * kCkP + 4 * (q & (kGtQ - 1));
           v[it][0] = __ldg(sp); v[it][1] = __ldg(sp + 1); v[it][2] = __ldg(sp + 2); v[it][3] = __ldg(sp + 3);
+          if (unit) {
+            const bool is_ze = (q >> 4) >= tg.act_groups;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[it][i] = scale_row(v[it][i], wq[i], is_ze);
+          }
         }
       }
       // the tensor core must be done with the tile of the previous item before it is overwritten (the loads above are
@@ -217,7 +239,11 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
       for (int q = tid + MAXI * kGtThreads; q < nq; q += kGtThreads) {                  // (wider inputs than the C2 shape)
         const int gi = q >> 4, j = q & (kGtQ - 1);
         const float4* sp = src + (size_t)gi * kCkP + 4 * j;
-        const float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
+        float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
+        if (unit) {
+          const bool is_ze = gi >= tg.act_groups;
+          v0 = scale_row(v0, wq[0], is_ze); v1 = scale_row(v1, wq[1], is_ze); v2 = scale_row(v2, wq[2], is_ze); v3 = scale_row(v3, wq[3], is_ze);
+        }
         const float4 c0 = make_float4(v0.x, v1.x, v2.x, v3.x), c1 = make_float4(v0.y, v1.y, v2.y, v3.y);
         const float4 c2 = make_float4(v0.z, v1.z, v2.z, v3.z), c3 = make_float4(v0.w, v1.w, v2.w, v3.w);
         quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;

@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
     const int k = (prm.tile0 + tile) * kTcP + p;
     const bool in = k < prm.K_local;
     float wy = 0.f, wz = 0.f;
-    if (CKPT && in) { wy = prm.wY ? __ldg(prm.wY + k) : 0.f; wz = prm.wZ ? __ldg(prm.wZ + k) : 0.f; }
+    if (CKPT && in) {
+      if (prm.ckpt_unit) wy = 1.0f;      // forward pass that keeps its operand rows: cotangents are applied by the gradient kernel
+      else { wy = prm.wY ? __ldg(prm.wY + k) : 0.f; wz = prm.wZ ? __ldg(prm.wZ + k) : 0.f; }
+    }
     const bool live = CKPT && (wy != 0.f || wz != 0.f);
     float4* ck = CKPT ? reinterpret_cast<float4*>(prm.ckpt) + (size_t)tile * N * prm.ckpt_c4 * kTcP + p : nullptr;
     const unsigned kglob = (unsigned)(prm.k_offset + k);
@@ -460,6 +463,10 @@ inline cudaError_t tc_launch_t(const RolloutParams& p, const TcGeom& tg, int gri
 }
 inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
   return p.u_mode != 0 ? tc_launch_t<false, true>(p, tg, grid, stream) : tc_launch_t<false, false>(p, tg, grid, stream);
+}
+// forward pass that also leaves the operand rows of ALL its tiles in prm.ckpt (unit cotangents, RolloutParams::ckpt_unit)
+inline cudaError_t tc_launch_fwd_ckpt(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  return p.u_mode != 0 ? tc_launch_t<true, true>(p, tg, grid, stream) : tc_launch_t<true, false>(p, tg, grid, stream);
 }
 // column groups (float4) per (tile slot, step) of the checkpoint buffer: a0 (s0) | h1 (hp) | h2 (hp) | zeta (s0)
 inline int tc_ckpt_c4(const TcGeom& tg) { return 2 * (tg.s0 >> 2) + 2 * (tg.hp >> 2); }

@@ -6,13 +6,16 @@ autograd Functions that replace the body of the reference's training iteration (
 :221 backward):
 
   detached forward (detach_forward=True)      Y_N, gX, Zsum = FusedRollout.apply(theta, y0, engine, call)
-      backward: one recompute rollout with per-path cotangents (dL/dY_N, dL/dZsum) -> dL/dtheta, dL/dy0
+      backward: per-path cotangents (dL/dY_N, dL/dZsum) -> dL/dtheta, dL/dy0.  When the forward pass could keep its
+      operand rows (tensor-core shape class, adaptive process, buffer affordable) and dL/dZsum is absent, one gradient
+      launch over those rows; else the checkpointed / recompute backward rollout.
   attached forward (relative entropy loss)     loss = FusedRolloutAttached.apply(theta, engine, call)
       forward and adjoint run in one kernel; backward hands the stored gradient back.
 
 There is no CPU fallback: constructing an engine without the CUDA library raises.
 """
 import ctypes
+import os
 
 import torch as pt
 
@@ -61,6 +64,28 @@ class RolloutEngine:
             raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
         self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
         self.udiag, self.uL2 = None, None
+        # Single-rollout step (pspde_rollout_fwd_ckpt): the training forward keeps the operand rows of all tiles for the
+        # gradient kernel.  The buffer is K_local * N * ~1 KB (C2: 7.1 GB); it is taken only while it stays below
+        # PSPDE_FWD_CKPT_MAX_GB (default 64) and below half of the free device memory, and dropped for good by the first
+        # backward that carries a cotangent on Z_sum (those losses need the rollout with the cotangents in hand).
+        self.ckpt, self.ckpt_ok = None, True
+
+    def _fwd_ckpt_buffer(self, cfg):
+        """The full forward checkpoint buffer, or None if this configuration / device cannot take it."""
+        if not self.ckpt_ok:
+            return None
+        need = int(self.lib.pspde_fwd_ckpt_bytes(ctypes.byref(cfg)))
+        if need == 0:
+            return None
+        if self.ckpt is None or self.ckpt.numel() < need:
+            self.ckpt = None
+            cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", "64")) * 2 ** 30
+            free, _ = pt.cuda.mem_get_info(self.device)
+            if need > cap or need > free // 2:
+                self.ckpt_ok = False
+                return None
+            self.ckpt = pt.empty(need, dtype=pt.uint8, device=self.device)
+        return self.ckpt
 
     def set_x0(self, x0):
         """(d,) broadcast start or (K_local, d) per-path starts (random_X_0, solver.py:366-367)."""
@@ -101,13 +126,25 @@ class RolloutEngine:
         u.table, u.uL2 = self._utab.data_ptr(), self.uL2.data_ptr()
         self.udiag = u
 
-    def forward(self, theta, y0, call):
+    def forward(self, theta, y0, call, keep_rows=False):
+        """keep_rows: training forward -- returns True if the operand rows were kept for `grad_from_rows`."""
         cfg = self.cfg(call)
         diag = None if self.udiag is None else ctypes.byref(self.udiag)
-        rc = self.lib.pspde_rollout_fwd_diag(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+        ck = self._fwd_ckpt_buffer(cfg) if keep_rows else None
+        rc = self.lib.pspde_rollout_fwd_ckpt(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
                                              self._p(y0), self._xi_ptr(call), self._p(self.X_N), self._p(self.Y_N),
                                              self._p(self.gX), self._p(self.Zsum), self._p(self.stats), diag,
+                                             self._p(ck), 0 if ck is None else ck.numel(),
                                              self._p(self.workspace), self.workspace.numel(), self._stream())
+        L.check(self.lib, rc)
+        return ck is not None
+
+    def grad_from_rows(self, theta, wY, call, grad_out):
+        """dL/dtheta from the rows the last training forward kept (pspde_grad_from_fwd_ckpt)."""
+        cfg = self.cfg(call)
+        rc = self.lib.pspde_grad_from_fwd_ckpt(ctypes.byref(cfg), self._p(theta), self._p(self.ckpt), self.ckpt.numel(),
+                                               self._p(wY), self._p(grad_out), self._p(self.workspace),
+                                               self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
     def backward_detached(self, theta, wY, wZ, call, grad_out):
@@ -146,10 +183,12 @@ class FusedRollout(pt.autograd.Function):
     def forward(ctx, theta, y0, engine, call):
         theta_c = theta.detach().contiguous()
         y0_c = None if y0 is None else y0.detach().contiguous()
-        engine.forward(theta_c, y0_c, call)
+        ctx.rows_kept = engine.forward(theta_c, y0_c, call, keep_rows=ctx.needs_input_grad[0])
+        ctx.rows_serial = engine.rows_serial = getattr(engine, "rows_serial", 0) + 1
         call.X_N, call.stats = engine.X_N, engine.stats
         ctx.engine, ctx.call, ctx.has_y0 = engine, call, y0 is not None
         ctx.save_for_backward(theta_c)
+        ctx.set_materialize_grads(False)      # an output the loss does not use arrives as None, not as zeros
         Y, gX, Zsum = engine.Y_N.clone(), engine.gX.clone(), engine.Zsum.clone()
         ctx.mark_non_differentiable(gX)
         return Y, gX, Zsum
@@ -161,7 +200,12 @@ class FusedRollout(pt.autograd.Function):
         wY = pt.zeros(engine.K_local, dtype=pt.float32, device=engine.device) if gY is None else gY.contiguous().float()
         wZ = None if gZsum is None else gZsum.contiguous().float()
         grad = pt.empty(engine.n_theta, dtype=pt.float32, device=engine.device)
-        engine.backward_detached(theta_c, wY, wZ, ctx.call, grad)
+        if wZ is not None:
+            engine.ckpt_ok, engine.ckpt = False, None       # this loss needs the rollout with the cotangents in hand
+        if ctx.rows_kept and wZ is None and engine.ckpt is not None and ctx.rows_serial == engine.rows_serial:
+            engine.grad_from_rows(theta_c, wY, ctx.call, grad)      # the rows are those of THIS forward
+        else:
+            engine.backward_detached(theta_c, wY, wZ, ctx.call, grad)
         gy0 = wY.sum().reshape(1) if ctx.has_y0 else None
         return grad, gy0, None, None
 

@@ -418,6 +418,26 @@ def test_tc_building_block_matches_fp64():
         assert float((D.double() - ref).norm() / ref.norm()) < 1e-6
 
 
+def test_tc_mn_major_operand_layout():
+    """The MN-major shared-memory operand form that kind::tf32 accepts on this part (DESIGN 4.3 item 0): layout type 1,
+    4-row x 128 B atoms with the 32-byte chunk index xor-ed with the k row (selftest variant 4 | 16 | 32)."""
+    import ctypes
+    from pspde import _lib
+    lib = _lib.load()
+    pt.manual_seed(1)
+    for K in (8, 32):
+        A = pt.randn(128, K, device="cuda")
+        B = pt.randn(K, 32, device="cuda")
+        D = pt.full((128, 32), float("nan"), device="cuda")
+        rc = lib.pspde_tc_selftest(K, 32, 4 | 16 | 32, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+                                   ctypes.c_void_p(D.data_ptr()), None)
+        assert rc == 0
+        pt.cuda.synchronize()
+        ref = A.double() @ B.double()
+        assert float((D.double() - ref).norm() / ref.norm()) < 1e-6
+    assert lib.pspde_tc_selftest(64, 32, 4 | 16 | 32, None, None, None, None) != 0     # probe shapes are bounded
+
+
 @pytest.mark.parametrize("kind,d,K", [("llgc", 100, 1000), ("lqgc", 10, 200), ("llgc", 3, 129), ("dwm", 50, 300),
                                       ("dwm", 7, 65)])
 def test_tc_forward_matches_fma_forward(monkeypatch, kind, d, K):
@@ -686,6 +706,93 @@ def test_checkpointed_backward_matches_recompute_backward(monkeypatch, kind, d, 
     g2 = pt.empty(eng.n_theta, device="cuda")
     eng.backward_detached(theta, wY, wZ, Call(offset=9, xi=xi), g2)
     assert np.array_equal(g2.cpu().numpy(), grads["ckpt"])
+
+
+@pytest.mark.parametrize("kind,d,K,opts", [("llgc", 100, 20000, {}), ("lqgc", 10, 333, {}), ("llgc", 3, 129, {}),
+                                           ("dwm", 50, 300, {}), ("dwm", 7, 65, {}),
+                                           ("llgc", 20, 260, dict(inject=True, dead=True))])
+def test_single_rollout_gradient_matches_recompute_backward(monkeypatch, kind, d, K, opts):
+    """The single-rollout step (the training forward keeps the operand rows of ALL tiles with unit cotangents, the
+    gradient kernel applies dL/dY_N: pspde_rollout_fwd_ckpt + pspde_grad_from_fwd_ckpt) against the FP32-FMA recompute
+    backward on identical noise and cotangents -- same cases as the wave-checkpointed backward above, plus: the
+    forward outputs do not change, dropped / diverged trajectories (zero weight) contribute nothing, fp64 check."""
+    import pspde
+    from pspde import _lib
+    from pspde.fused import Call, RolloutEngine
+    N = 50 if kind == "dwm" else 12
+    if kind == "dwm":
+        prob = pspde.DoubleWell_multidim(d=d, d_1=d // 3, d_2=d - d // 3, T=1.0, eta=3, kappa=5, device="cuda")
+        net, net_id = pspde.MySequential(d_in=d + 1, d_out=d, lr=1e-3, seed=123).cuda(), _lib.NET_MLP_TANH
+    else:
+        prob = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC}[kind](d=d, T=1.0, device="cuda")
+        net, net_id = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42).cuda(), _lib.NET_DENSENET
+    theta = pt.cat([q.detach().reshape(-1) for q in net.parameters()]).contiguous()
+    eng = RolloutEngine(prob, net_id, net.net_spec()[1], _lib.TIME_FIRST, K, N, 1.0 / N, seed=5)
+    gen = pt.Generator(device="cuda").manual_seed(K)
+    wY = pt.randn(K, device="cuda", generator=gen) / K
+    if opts.get("dead"):
+        wY[::7] = 0.0
+    xi = pt.randn(K, d, N + 1, device="cuda", generator=gen) if opts.get("inject") else None
+    eng.forward(theta, None, Call(offset=9, xi=xi))
+    plain = (eng.Y_N.clone(), eng.gX.clone(), eng.Zsum.clone(), eng.X_N.clone(), eng.stats.clone())
+    assert eng.forward(theta, None, Call(offset=9, xi=xi), keep_rows=True)          # eligible: the rows were kept
+    pt.cuda.synchronize()
+    for a, b in zip(plain, (eng.Y_N, eng.gX, eng.Zsum, eng.X_N, eng.stats)):        # same kernel arithmetic
+        assert pt.equal(pt.nan_to_num(a), pt.nan_to_num(b))
+    ok = pt.isfinite(eng.Y_N) & pt.isfinite(eng.gX)
+    wY = pt.where(ok, wY, pt.zeros_like(wY))
+    assert int(ok.sum()) > 0.9 * K
+    g1 = pt.full((eng.n_theta,), float("nan"), device="cuda")
+    eng.grad_from_rows(theta, wY, Call(offset=9, xi=xi), g1)
+    monkeypatch.setenv("PSPDE_BWD_PATH", "simt")
+    g0 = pt.full((eng.n_theta,), float("nan"), device="cuda")
+    eng.backward_detached(theta, wY, None, Call(offset=9, xi=xi), g0)
+    pt.cuda.synchronize()
+    g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
+    assert np.all(np.isfinite(g1))
+    assert relerr(g1, g0) < TOL
+    if kind != "dwm" and not opts:
+        from oracle import manual as man
+        xi_h = eng.philox_dump(offset=9).cpu().numpy().astype(np.float64)
+        mnet = man.Net("densenet", net.net_spec()[1], theta.cpu().numpy().astype(np.float64))
+        wY_h, ref = wY.cpu().numpy().astype(np.float64), 0.0
+        for lo in range(0, K, 1000):
+            hi = min(K, lo + 1000)
+            r, _ = man.grad_mode_a(man.Problem(kind, d), mnet, xi_h[lo:hi], np.float32(1.0 / N), N, np.zeros(d),
+                                   wY_h[lo:hi], np.zeros(hi - lo))
+            ref = ref + r
+        assert relerr(g1, ref) < 5e-6
+
+
+def test_single_rollout_training_matches_two_rollout_training(monkeypatch):
+    """Solver.train through the autograd bridge: the single-rollout step (default where eligible) and the
+    forward + checkpointed-backward step (PSPDE_FWD_CKPT_MAX_GB=0) give the same loss curve and parameters; a loss with a
+    cotangent on Z_sum or a non-adaptive process falls back by itself."""
+    import pspde
+
+    def run(loss_method="log-variance", adaptive=True, iters=4):
+        prob = pspde.LLGC(d=20, T=1.0, device="cuda")
+        S = pspde.Solver("s", prob, K=1000, L=iters, delta_t=0.05, time_approx="inner", detach_forward=True,
+                         loss_method=loss_method, adaptive_forward_process=adaptive, u_l2_error_flag=True,
+                         verbose=False, seed=7)
+        S.z_n = pspde.DenseNet(d_in=21, d_out=20, lr=1e-3, seed=42)
+        S.update_Phis()
+        S.train()
+        return S
+
+    A = run()
+    assert A._get_engine().ckpt is not None                       # the single-rollout path was taken
+    monkeypatch.setenv("PSPDE_FWD_CKPT_MAX_GB", "0")
+    B = run()
+    assert B._get_engine().ckpt is None
+    monkeypatch.delenv("PSPDE_FWD_CKPT_MAX_GB")
+    assert relerr(np.array(A.loss_log), np.array(B.loss_log)) < TOL
+    assert relerr(np.array(A.u_L2_loss), np.array(B.u_L2_loss)) < TOL
+    assert relerr(A._theta.detach().cpu().numpy(), B._theta.detach().cpu().numpy()) < 1e-4      # 4 Adam steps apart
+    C = run(adaptive=False)                                       # zeta needs Z: not eligible
+    assert C._get_engine().ckpt is None and np.all(np.isfinite(C.loss_log))
+    D = run(loss_method="relative_entropy")                       # cotangent on Z_sum: dropped by the first backward
+    assert D._get_engine().ckpt is None and not D._get_engine().ckpt_ok and np.all(np.isfinite(D.loss_log))
 
 
 def test_checkpointed_backward_rejects_ineligible_configuration(monkeypatch):
