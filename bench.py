@@ -351,7 +351,8 @@ def run_ours(args, wl):
             kernel = ("single-rollout step: the training forward (rollout_tc_fwd_kernel<CKPT>, timed as 'fwd') keeps the "
                       "operand rows [a0|h1|h2|sqrt(dt) xi] of all tiles in HBM; backward = grad_tc_kernel over those rows "
                       "(dL/dY_N applied at load, hidden cotangents in FP32 FMA, weight gradient on tcgen05 kind::tf32 3xTF32 "
-                      "with K = samples, accumulators resident in tensor memory) + reduce; no trajectory is recomputed")
+                      "with K = samples, accumulators resident in tensor memory) + reduce; tiles the buffer does not hold "
+                      "(rows_kept_fraction < 1) are recomputed by the wave-checkpointed backward inside 'bwd'")
         elif ckpt_path:
             s0 = (d + 2 + 7) // 8 * 8
             ckpt_bytes = 2.0 * eng.K_local * N * (2 * (s0 // 4) + 16) * 16          # operand rows written once, read once
@@ -368,6 +369,7 @@ def run_ours(args, wl):
                 "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
                 "single_rollout": bool(ckpt_path and single),
+                "rows_kept_fraction": (eng.ckpt.numel() / eng._ckpt_need) if (ckpt_path and single) else 0.0,
                 "bwd_checkpoint": {"bytes_per_step": ckpt_bytes,
                                    "gbs_over_bwd": (ckpt_bytes / 2 if single else ckpt_bytes) / (tb * 1e-3) / 1e9,
                                    "gbs_over_fwd": ckpt_bytes / 2 / (tf * 1e-3) / 1e9 if single else 0.0,

@@ -151,22 +151,27 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
 
 /* Single-rollout training step for detach_forward=True (solver.py:433-499 + :221 without recomputing the trajectories,
  * like the reference, whose autograd graph keeps every activation).  pspde_rollout_fwd_ckpt is pspde_rollout_fwd_diag
- * that additionally leaves the operand rows [a0 | h1 | h2 | zeta_unit] of ALL ceil(K_local / 128) tiles in `ckpt`
- * (layout as above, slot = tile; zeta_unit = sqrt(dt) xi_{n+1}); pspde_grad_from_fwd_ckpt then forms
+ * that additionally leaves the operand rows [a0 | h1 | h2 | zeta_unit] of its first ckpt_bytes / tile_bytes tiles of
+ * 128 paths in `ckpt` (layout as above, slot = tile; zeta_unit = sqrt(dt) xi_{n+1}; tile_bytes = N * C4 * 2048);
+ * pspde_grad_from_fwd_ckpt then forms
  *   dLoss/dtheta = sum_{k,n} J_theta Z' (wY_k zeta_unit)
- * with the tensor-core gradient kernel -- one forward and one gradient launch per iteration instead of forward +
- * checkpoint rollout + gradient.  Requirements (pspde_fwd_ckpt_bytes returns 0 otherwise and the caller uses
+ * with the tensor-core gradient kernel over those rows, and runs the wave-checkpointed backward of
+ * pspde_rollout_bwd_detached for the tiles the buffer did not hold (prob / x0 / xi are needed only then).  With the
+ * whole batch in the buffer an iteration is one forward and one gradient launch instead of forward + checkpoint
+ * rollout + gradient.  Requirements (pspde_fwd_ckpt_bytes returns 0 otherwise and the caller uses
  * pspde_rollout_fwd_diag + pspde_rollout_bwd_detached): tensor-core shape class, cfg->adaptive != 0, no cotangent on
- * Z_sum (dLoss/dZsum == 0: log-variance, moment, variance losses with the adaptive process).  The buffer is
- * K_local * N * 16 * C4 bytes (C2: 7.1 GB); the caller decides whether it affords it.  ckpt == NULL in
- * pspde_rollout_fwd_ckpt is the plain forward.  Paths with wY == 0 contribute nothing (even if they diverged). */
+ * Z_sum (dLoss/dZsum == 0: log-variance, moment, variance, cross-entropy losses with the adaptive process).
+ * pspde_fwd_ckpt_bytes = bytes for ALL ceil(K_local / 128) tiles (C2: 7.1 GB, C5: 228 GB -- the caller passes what it
+ * affords, the same buffer and size to both calls).  ckpt == NULL in pspde_rollout_fwd_ckpt is the plain forward.
+ * Paths with wY == 0 contribute nothing (even if they diverged). */
 size_t pspde_fwd_ckpt_bytes(const pspde_cfg* cfg);
 int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
                            const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
                            double* stats, const pspde_udiag* diag, void* ckpt, size_t ckpt_bytes, void* workspace,
                            size_t workspace_bytes, void* stream);
-int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const void* ckpt, size_t ckpt_bytes,
-                             const float* wY, float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                             const float* xi, const void* ckpt, size_t ckpt_bytes, const float* wY, float* grad_theta,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Forward + backward for detach_forward=False (solver.py:451-469 without the detach, :221): per tile of paths the
  * states X_n are checkpointed to the workspace and the discrete adjoint runs backwards in time in the same kernel.

@@ -12,7 +12,8 @@ unsigned long long* g_prof = nullptr;
 // FP32-FMA kernel.  PSPDE_FWD_PATH=simt forces the FMA kernel (A/B tests); PSPDE_FWD_PATH=tc makes an ineligible
 // configuration an error.  *grid_out = number of CTAs launched (rows of stats_partial that were written).
 static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, bool tc_allowed, void* stream, int* grid_out,
-                          bool keep_ckpt = false) {
+                          int keep_tiles = 0) {
+  const bool keep_ckpt = keep_tiles > 0;
 #if !defined(PSPDE_EMULATE)
   TcGeom tg;
   const char* path = getenv("PSPDE_FWD_PATH");
@@ -23,7 +24,7 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
     const int sms = pspde_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     p.n_tiles = n_tiles;
-    if (keep_ckpt) { p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; }
+    if (keep_ckpt) { p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles; }
     const cudaError_t ce = keep_ckpt ? tc_launch_fwd_ckpt(p, tg, grid, (cudaStream_t)stream) : tc_launch(p, tg, grid, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
@@ -136,7 +137,7 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
 // Single-rollout training step: the forward pass itself leaves the operand rows of ALL tiles (unit cotangents) and the
 // gradient kernel applies dL/dY_N.  Needs the tensor-core shape class for both kernels and the adaptive (`-Z` drift)
 // process with no cotangent on Z_sum (zeta = wY sqrt(dt) xi does not involve Z).  Returns the buffer size, 0 if ineligible.
-static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl) {
+static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_bytes = nullptr) {
 #if !defined(PSPDE_EMULATE)
   TcGeom tg;
   GradTcGeom gt;
@@ -145,12 +146,35 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl) {
   if (cfg->N < 1 || !cfg->adaptive || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return 0;
   if (!grad_tc_geom(pl.g, cfg->d, tg.s0, gt)) return 0;
   const size_t n_tiles = (size_t)(cfg->K_local + kTcP - 1) / kTcP;
-  return align256(n_tiles * cfg->N * tc_ckpt_c4(tg) * kTcP * 16);
+  const size_t tb = (size_t)cfg->N * tc_ckpt_c4(tg) * kTcP * 16;       // one 128-path tile; a multiple of 2 KB
+  if (tile_bytes) *tile_bytes = tb;
+  return n_tiles * tb;
 #else
-  (void)cfg; (void)pl;
+  (void)cfg; (void)pl; (void)tile_bytes;
   return 0;
 #endif
 }
+
+#if !defined(PSPDE_EMULATE)
+// tiles [t_begin, n_tiles128) of the checkpointed detached backward: per wave, the tensor-core rollout that writes the operand
+// rows (cotangents p.wY / p.wZ applied) into p.ckpt, then the gradient kernel; accumulates into p.grad_partial
+static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, const TcGeom& tg, const CkptPlan& cp, int t_begin,
+                     void* stream, bool* used_tc) {
+  p.ckpt_c4 = cp.c4; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0;
+  const int sms = pspde_sm_count();
+  for (int t0 = t_begin; t0 < cp.n_tiles128; t0 += cp.wave) {
+    const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
+    p.tile0 = t0; p.n_tiles = nt; p.ckpt_tiles = nt;
+    const cudaError_t ce = tc_launch_t<true>(p, tg, nt < sms ? nt : sms, (cudaStream_t)stream);
+    g_launches++;
+    if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
+    const long long items = (long long)nt * cfg->N * (kTcP / kP);
+    const int rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream, used_tc);
+    if (rc) return rc;
+  }
+  return 0;
+}
+#endif
 
 extern "C" {
 
@@ -226,10 +250,13 @@ int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float
   Plan pl;
   int rc = make_plan(cfg, false, false, pl);
   if (rc) return rc;
+  int keep_tiles = 0;
   if (ckpt) {
-    const size_t need = fwd_ckpt_bytes(cfg, pl);
+    size_t tb = 0;
+    const size_t need = fwd_ckpt_bytes(cfg, pl, &tb);
     if (!need) return fail(-6, "configuration is outside the checkpointing forward's shape class");
-    if (ckpt_bytes < need) return fail(-7, "checkpoint buffer too small (%zu < %zu)", ckpt_bytes, need);
+    if (ckpt_bytes < tb) return fail(-7, "checkpoint buffer too small for one tile (%zu < %zu)", ckpt_bytes, tb);
+    keep_tiles = (int)((ckpt_bytes < need ? ckpt_bytes : need) / tb);      // the first tiles that fit
   }
   if (!theta || !prob || !x0) return fail(-1, "theta/prob/x0 must not be NULL");
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
@@ -248,7 +275,7 @@ int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float
   p.stats_partial = reinterpret_cast<double*>(workspace);
   p.ckpt = reinterpret_cast<float*>(ckpt);
   int grid = pl.grid;
-  rc = launch_forward(cfg, pl, p, true, stream, &grid, ckpt != nullptr);
+  rc = launch_forward(cfg, pl, p, true, stream, &grid, keep_tiles);
   if (rc) return rc;
   if (stats) {
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, grid, stats);
@@ -292,19 +319,9 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
     if (eligible && !(path && !strcmp(path, "simt"))) {
       if (pspde_memset0(p.grad_partial, cp.grad_bytes, stream)) return fail(-12, "memset of the gradient partials failed");
       p.ckpt = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes + cp.grad_bytes);
-      p.ckpt_c4 = cp.c4; p.ckpt_s0 = cp.s0;
       bool used_tc = false;
-      for (int t0 = 0; t0 < cp.n_tiles128; t0 += cp.wave) {
-        const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
-        p.tile0 = t0; p.n_tiles = nt;
-        const int sms = pspde_sm_count();
-        const cudaError_t ce = tc_launch_t<true>(p, tg, nt < sms ? nt : sms, (cudaStream_t)stream);
-        g_launches++;
-        if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
-        const long long items = (long long)nt * cfg->N * (kTcP / kP);
-        rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream, &used_tc);
-        if (rc) return rc;
-      }
+      rc = run_waves(cfg, pl, p, tg, cp, 0, stream, &used_tc);
+      if (rc) return rc;
       return reduce_grad(cfg, pl, p, cp.grid_b, used_tc, grad_theta, stream);
     }
   }
@@ -347,28 +364,42 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
 }
 
-int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const void* ckpt, size_t ckpt_bytes,
-                             const float* wY, float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                             const float* xi, const void* ckpt, size_t ckpt_bytes, const float* wY, float* grad_theta,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   Plan pl;
   int rc = make_plan(cfg, true, false, pl);
   if (rc) return rc;
   if (!theta || !ckpt || !wY || !grad_theta) return fail(-1, "theta/ckpt/wY/grad_theta must not be NULL");
 #if !defined(PSPDE_EMULATE)
-  const size_t need = fwd_ckpt_bytes(cfg, pl);
+  size_t tb = 0;
+  const size_t need = fwd_ckpt_bytes(cfg, pl, &tb);
   if (!need) return fail(-6, "configuration is outside the checkpointing forward's shape class");
-  if (ckpt_bytes < need) return fail(-7, "checkpoint buffer too small (%zu < %zu)", ckpt_bytes, need);
+  if (ckpt_bytes < tb) return fail(-7, "checkpoint buffer too small for one tile (%zu < %zu)", ckpt_bytes, tb);
   TcGeom tg;
   tc_geom(pl.g, cfg->d, tg);
   const int sms = pspde_sm_count();
-  const long long n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
-  const long long items = n_tiles * cfg->N * (kTcP / kP);
+  const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
+  const int n_keep = (int)((ckpt_bytes < need ? ckpt_bytes : need) / tb);       // tiles whose rows the forward kept
+  const long long items = (long long)n_keep * cfg->N * (kTcP / kP);
   if (items > 0x7fffffffLL) return fail(-6, "too many work items for one gradient launch");
-  const int grid = items < sms ? (int)items : sms;
-  const size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
-  if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
+  int grid = items < sms ? (int)items : sms;
+  size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
+  size_t ws_need = pl.stats_bytes + gbytes;
+  CkptPlan cp;
+  if (n_keep < n_tiles) {        // the other tiles: rollout with the cotangents in hand, one wave at a time
+    if (!prob || !x0) return fail(-1, "prob/x0 must not be NULL when the buffer does not hold every tile");
+    if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
+    TcGeom tg2;
+    if (!ckpt_plan(cfg, pl, tg2, cp)) return fail(-6, "configuration is outside the checkpointed backward's shape class");
+    if (grid > cp.grid_b) grid = cp.grid_b;
+    gbytes = cp.grad_bytes;
+    ws_need = pl.stats_bytes + cp.grad_bytes + cp.ckpt_bytes;
+  }
+  if (!workspace || workspace_bytes < ws_need) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, ws_need);
   RolloutParams p;
   fill_params(cfg, pl, p);
-  p.theta = theta; p.wY = wY;
+  p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
   p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0;
   p.tile0 = 0; p.ckpt_unit = 1;
@@ -377,9 +408,16 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const voi
   rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
   if (rc) return rc;
   if (!used_tc) return fail(-13, "internal: the forward checkpoint needs the tensor-core gradient kernel");
-  return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
+  int nparts = grid;
+  if (n_keep < n_tiles) {
+    p.ckpt = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes + cp.grad_bytes);
+    rc = run_waves(cfg, pl, p, tg, cp, n_keep, stream, &used_tc);
+    if (rc) return rc;
+    nparts = cp.grid_b;
+  }
+  return reduce_grad(cfg, pl, p, nparts, used_tc, grad_theta, stream);
 #else
-  (void)ckpt_bytes; (void)workspace; (void)workspace_bytes; (void)stream;
+  (void)prob; (void)x0; (void)xi; (void)ckpt_bytes; (void)workspace; (void)workspace_bytes; (void)stream;
   return fail(-20, "the tensor-core path does not exist in the host emulator");
 #endif
 }

@@ -55,6 +55,7 @@ struct RolloutParams {
   int ckpt_c4;            // column groups per (slot, step): 2 * (s0 / 4) + 16
   int ckpt_s0;            // tensor-core width of the input segment (multiple of 8)
   int tile0;              // first 128-path tile of this wave (ckpt slot = tile - tile0)
+  int ckpt_tiles;         // rollout: only tiles < ckpt_tiles (launch-local index) write their rows
   int ckpt_unit;          // 1: the checkpoint was written by the FORWARD pass with unit cotangents (zeta = sqrt(dt) xi);
                           //    the gradient kernel scales the zeta rows by wY[path] (adaptive, wZ == 0 only)
   unsigned long long* prof;  // debug: per-phase clock64() totals of CTA 0 (16 slots) or nullptr

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       else { wy = prm.wY ? __ldg(prm.wY + k) : 0.f; wz = prm.wZ ? __ldg(prm.wZ + k) : 0.f; }
     }
     const bool live = CKPT && (wy != 0.f || wz != 0.f);
+    const bool keep = CKPT && tile < prm.ckpt_tiles;       // a forward pass may keep the rows of its first tiles only
     float4* ck = CKPT ? reinterpret_cast<float4*>(prm.ckpt) + (size_t)tile * N * prm.ckpt_c4 * kTcP + p : nullptr;
     const unsigned kglob = (unsigned)(prm.k_offset + k);
     // ---- tile init (solver.py:365-376) and the first a0
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + HC * part;
         tc::tmem_st8(th, hi);
         tc::tmem_st8(th + tg.hp, lo);
-        if (CKPT) {                          // h = hi + lo exactly
+        if (CKPT && keep) {                  // h = hi + lo exactly
           float4* o = ck + (size_t)(n * prm.ckpt_c4 + (tg.s0 >> 2) + (tg.hp >> 2) * hl + (HC >> 2) * part) * kTcP;
 #pragma unroll
           for (int u = 0; u < HC / 4; ++u)
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
               const float4 A4 = ld4(a_d + j0), B4 = ld4(b_d + j0), P4 = ld4(p_d + j0), K4 = ld4(kap + j0);
               const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
               const float pv[4] = {P4.x, P4.y, P4.z, P4.w}, kv[4] = {K4.x, K4.y, K4.z, K4.w};
-              if (CKPT) {                    // operand rows of this step: a0 = X_n (own columns) and zeta
+              if (CKPT && keep) {            // operand rows of this step: a0 = X_n (own columns) and zeta
                 const float kA = adaptive ? 0.f : dt;
                 float ze[4];
 #pragma unroll

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "pspde_fwd_ckpt_bytes": (ctypes.c_size_t, [_CFG]),
     "pspde_rollout_fwd_ckpt": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.POINTER(pspde_udiag),
                                               _P, ctypes.c_size_t, _P, ctypes.c_size_t, _P]),
-    "pspde_grad_from_fwd_ckpt": (ctypes.c_int, [_CFG, _P, _P, ctypes.c_size_t, _P, _P, _P, ctypes.c_size_t, _P]),
+    "pspde_grad_from_fwd_ckpt": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_size_t, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_rollout_attached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_importance_sampling": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P,

@@ -64,27 +64,30 @@ class RolloutEngine:
             raise RuntimeError("libpspde: %s" % self.lib.pspde_last_error().decode())
         self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
         self.udiag, self.uL2 = None, None
-        # Single-rollout step (pspde_rollout_fwd_ckpt): the training forward keeps the operand rows of all tiles for the
-        # gradient kernel.  The buffer is K_local * N * ~1 KB (C2: 7.1 GB); it is taken only while it stays below
-        # PSPDE_FWD_CKPT_MAX_GB (default 64) and below half of the free device memory, and dropped for good by the first
-        # backward that carries a cotangent on Z_sum (those losses need the rollout with the cotangents in hand).
+        # Single-rollout step (pspde_rollout_fwd_ckpt): the training forward keeps the operand rows of its tiles for the
+        # gradient kernel.  All tiles need K_local * N * ~1 KB (C2: 7.1 GB, C5: 228 GB); the buffer takes what fits below
+        # PSPDE_FWD_CKPT_MAX_GB (default 96) and 60 % of the free device memory -- the tiles it does not hold go through
+        # the wave-checkpointed backward -- and is dropped for good by the first backward that carries a cotangent on
+        # Z_sum (those losses need the rollout with the cotangents in hand).
         self.ckpt, self.ckpt_ok = None, True
 
     def _fwd_ckpt_buffer(self, cfg):
-        """The full forward checkpoint buffer, or None if this configuration / device cannot take it."""
+        """The forward checkpoint buffer (whole tiles), or None if this configuration / device cannot take it."""
         if not self.ckpt_ok:
             return None
         need = int(self.lib.pspde_fwd_ckpt_bytes(ctypes.byref(cfg)))
         if need == 0:
             return None
-        if self.ckpt is None or self.ckpt.numel() < need:
+        if self.ckpt is None or self._ckpt_need != need:
             self.ckpt = None
-            cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", "64")) * 2 ** 30
+            tile = need // ((self.K_local + 127) // 128)
+            cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", "96")) * 2 ** 30
             free, _ = pt.cuda.mem_get_info(self.device)
-            if need > cap or need > free // 2:
+            take = int(min(need, cap, 0.6 * free)) // tile * tile
+            if take < max(tile, need // 10):                  # less than a tenth of the batch: not worth a second code path
                 self.ckpt_ok = False
                 return None
-            self.ckpt = pt.empty(need, dtype=pt.uint8, device=self.device)
+            self.ckpt, self._ckpt_need = pt.empty(take, dtype=pt.uint8, device=self.device), need
         return self.ckpt
 
     def set_x0(self, x0):
@@ -142,7 +145,8 @@ class RolloutEngine:
     def grad_from_rows(self, theta, wY, call, grad_out):
         """dL/dtheta from the rows the last training forward kept (pspde_grad_from_fwd_ckpt)."""
         cfg = self.cfg(call)
-        rc = self.lib.pspde_grad_from_fwd_ckpt(ctypes.byref(cfg), self._p(theta), self._p(self.ckpt), self.ckpt.numel(),
+        rc = self.lib.pspde_grad_from_fwd_ckpt(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+                                               self._xi_ptr(call), self._p(self.ckpt), self.ckpt.numel(),
                                                self._p(wY), self._p(grad_out), self._p(self.workspace),
                                                self.workspace.numel(), self._stream())
         L.check(self.lib, rc)

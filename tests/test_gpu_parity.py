@@ -710,12 +710,14 @@ def test_checkpointed_backward_matches_recompute_backward(monkeypatch, kind, d, 
 
 @pytest.mark.parametrize("kind,d,K,opts", [("llgc", 100, 20000, {}), ("lqgc", 10, 333, {}), ("llgc", 3, 129, {}),
                                            ("dwm", 50, 300, {}), ("dwm", 7, 65, {}),
-                                           ("llgc", 20, 260, dict(inject=True, dead=True))])
+                                           ("llgc", 20, 260, dict(inject=True, dead=True)),
+                                           ("llgc", 100, 20000, dict(cap_gb=0.1)), ("lqgc", 10, 2000, dict(cap_gb=0.002, inject=True))])
 def test_single_rollout_gradient_matches_recompute_backward(monkeypatch, kind, d, K, opts):
     """The single-rollout step (the training forward keeps the operand rows of ALL tiles with unit cotangents, the
     gradient kernel applies dL/dY_N: pspde_rollout_fwd_ckpt + pspde_grad_from_fwd_ckpt) against the FP32-FMA recompute
     backward on identical noise and cotangents -- same cases as the wave-checkpointed backward above, plus: the
-    forward outputs do not change, dropped / diverged trajectories (zero weight) contribute nothing, fp64 check."""
+    forward outputs do not change, dropped / diverged trajectories (zero weight) contribute nothing, fp64 check, and a
+    buffer that holds only part of the tiles (cap_gb)."""
     import pspde
     from pspde import _lib
     from pspde.fused import Call, RolloutEngine
@@ -734,11 +736,17 @@ def test_single_rollout_gradient_matches_recompute_backward(monkeypatch, kind, d
         wY[::7] = 0.0
     xi = pt.randn(K, d, N + 1, device="cuda", generator=gen) if opts.get("inject") else None
     eng.forward(theta, None, Call(offset=9, xi=xi))
-    plain = (eng.Y_N.clone(), eng.gX.clone(), eng.Zsum.clone(), eng.X_N.clone(), eng.stats.clone())
+    plain = (eng.Y_N.clone(), eng.gX.clone(), eng.Zsum.clone(), eng.X_N.clone())
+    stats = eng.stats.clone()
+    if "cap_gb" in opts:          # the buffer holds only the first tiles: the others take the wave-checkpointed backward
+        monkeypatch.setenv("PSPDE_FWD_CKPT_MAX_GB", str(opts["cap_gb"]))
     assert eng.forward(theta, None, Call(offset=9, xi=xi), keep_rows=True)          # eligible: the rows were kept
+    if "cap_gb" in opts:
+        assert 0 < eng.ckpt.numel() < eng._ckpt_need
     pt.cuda.synchronize()
-    for a, b in zip(plain, (eng.Y_N, eng.gX, eng.Zsum, eng.X_N, eng.stats)):        # same kernel arithmetic
+    for a, b in zip(plain, (eng.Y_N, eng.gX, eng.Zsum, eng.X_N)):                   # same kernel arithmetic
         assert pt.equal(pt.nan_to_num(a), pt.nan_to_num(b))
+    assert pt.allclose(stats, eng.stats, rtol=1e-12, atol=0)                        # fp64 sums (atomic order varies)
     ok = pt.isfinite(eng.Y_N) & pt.isfinite(eng.gX)
     wY = pt.where(ok, wY, pt.zeros_like(wY))
     assert int(ok.sum()) > 0.9 * K
