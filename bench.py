@@ -362,17 +362,18 @@ def run_ours(args, wl):
                       "resident in tensor memory); timed together")
         else:
             ckpt_bytes, kernel = 0.0, "rollout_kernel<BWD> (detached backward, FP32-FMA recompute)"
+        kept = (eng.ckpt.numel() / eng._ckpt_need) if (ckpt_path and single) else 0.0
         roof = {"bound": "fp32_fma", "kernel": kernel,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "fp32 FMA probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure); "
                                "nominal 148 SM x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s" % (nominal or 0),
                 "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
-                "single_rollout": bool(ckpt_path and single),
-                "rows_kept_fraction": (eng.ckpt.numel() / eng._ckpt_need) if (ckpt_path and single) else 0.0,
+                "single_rollout": bool(ckpt_path and single), "rows_kept_fraction": kept,
                 "bwd_checkpoint": {"bytes_per_step": ckpt_bytes,
-                                   "gbs_over_bwd": (ckpt_bytes / 2 if single else ckpt_bytes) / (tb * 1e-3) / 1e9,
-                                   "gbs_over_fwd": ckpt_bytes / 2 / (tf * 1e-3) / 1e9 if single else 0.0,
+                                   # bwd reads every row once and writes those the forward did not keep
+                                   "gbs_over_bwd": ckpt_bytes / 2 * (2.0 - kept) / (tb * 1e-3) / 1e9,
+                                   "gbs_over_fwd": ckpt_bytes / 2 * kept / (tf * 1e-3) / 1e9,
                                    "hbm_peak_gbs_measured": measured_peaks().get("hbm_gbs")} if ckpt_path else None,
                 "fwd": fwd_roofline(flops_fwd, tf, peak, eng),
                 "step": {"algorithmic_flops_per_path_step": 2.0 * (2 * M + Md),
