@@ -367,7 +367,8 @@ def run_ours(args, wl):
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "fp32 FMA probe measured live in this run (MEASURED_PEAKS.json has no fp32 figure); "
                                "nominal 148 SM x 128 lanes x 2 x clocks.max.sm = %.1f TFLOP/s" % (nominal or 0),
-                "traffic": prof.get(args.workload, {}).get("bwd_dram_bytes_per_launch"),
+                "traffic": prof.get(args.workload if (single or not ckpt_path) else args.workload + "_two_rollout_step",
+                                    {}).get("bwd_dram_bytes_per_launch"),
                 "kernel_ms": {"fwd": tf, "bwd": tb},
                 "single_rollout": bool(ckpt_path and single), "rows_kept_fraction": kept,
                 "bwd_checkpoint": {"bytes_per_step": ckpt_bytes,
