@@ -30,6 +30,7 @@ class Call:
         self.xi = xi                 # injected increments, reference layout (K_local, d, N+1) on the device, or None
         self.X_N = None              # filled by the forward pass
         self.stats = None
+        self.grad_enabled = True     # set by FusedRollout.apply: was autograd recording when the rollout was called
 
 
 class RolloutEngine:
@@ -69,7 +70,8 @@ class RolloutEngine:
         # PSPDE_FWD_CKPT_MAX_GB (default 96) and 60 % of the free device memory -- the tiles it does not hold go through
         # the wave-checkpointed backward -- and is dropped for good by the first backward that carries a cotangent on
         # Z_sum (those losses need the rollout with the cotangents in hand).
-        self.ckpt, self.ckpt_ok = None, True
+        self.ckpt, self.ckpt_ok, self._ckpt_need = None, True, 0
+        self.rows_serial = 0         # row-keeping forwards so far: a backward may use the rows only if they are its own forward's
 
     def _fwd_ckpt_buffer(self, cfg):
         """The forward checkpoint buffer (whole tiles), or None if this configuration / device cannot take it."""
@@ -140,6 +142,8 @@ class RolloutEngine:
                                              self._p(ck), 0 if ck is None else ck.numel(),
                                              self._p(self.workspace), self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
+        if ck is not None:
+            self.rows_serial += 1       # the buffer now holds THIS forward's rows
         return ck is not None
 
     def grad_from_rows(self, theta, wY, call, grad_out):
@@ -183,12 +187,17 @@ class RolloutEngine:
 class FusedRollout(pt.autograd.Function):
     """(theta, y0) -> per-path (Y_N, g(X_N), Z_sum) for a theta-independent (detached) forward process."""
 
+    @classmethod
+    def apply(cls, theta, y0, engine, call):
+        call.grad_enabled = pt.is_grad_enabled()      # forward() below always runs with grad mode off
+        return super().apply(theta, y0, engine, call)
+
     @staticmethod
     def forward(ctx, theta, y0, engine, call):
         theta_c = theta.detach().contiguous()
         y0_c = None if y0 is None else y0.detach().contiguous()
-        ctx.rows_kept = engine.forward(theta_c, y0_c, call, keep_rows=ctx.needs_input_grad[0])
-        ctx.rows_serial = engine.rows_serial = getattr(engine, "rows_serial", 0) + 1
+        ctx.rows_kept = engine.forward(theta_c, y0_c, call, keep_rows=ctx.needs_input_grad[0] and call.grad_enabled)
+        ctx.rows_serial = engine.rows_serial
         call.X_N, call.stats = engine.X_N, engine.stats
         ctx.engine, ctx.call, ctx.has_y0 = engine, call, y0 is not None
         ctx.save_for_backward(theta_c)

@@ -803,6 +803,37 @@ def test_single_rollout_training_matches_two_rollout_training(monkeypatch):
     assert D._get_engine().ckpt is None and not D._get_engine().ckpt_ok and np.all(np.isfinite(D.loss_log))
 
 
+def test_single_rollout_rows_belong_to_their_forward():
+    """Two forwards through the autograd bridge before the first backward: the buffer holds the SECOND forward's rows, so
+    the first backward must not use them (it takes the rollout backward) -- both gradients equal a fresh evaluation."""
+    import pspde
+    from pspde import _lib
+    from pspde.fused import Call, FusedRollout, RolloutEngine
+    d, K, N = 12, 700, 10
+    prob = pspde.LLGC(d=d, T=1.0, device="cuda")
+    net = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42).cuda()
+    theta = pt.cat([q.detach().reshape(-1) for q in net.parameters()]).contiguous().requires_grad_(True)
+    eng = RolloutEngine(prob, _lib.NET_DENSENET, net.net_spec()[1], _lib.TIME_FIRST, K, N, 1.0 / N, seed=5)
+    w = pt.randn(K, device="cuda") / K
+
+    def grad_of(outs):
+        theta.grad = None
+        (outs[0] * w).sum().backward()
+        return theta.grad.clone()
+
+    o1 = FusedRollout.apply(theta, None, eng, Call(offset=1))
+    o2 = FusedRollout.apply(theta, None, eng, Call(offset=2))
+    assert eng.ckpt is not None and eng.rows_serial == 2
+    g1, g2 = grad_of(o1), grad_of(o2)                  # o1: rows overwritten -> rollout backward; o2: its own rows
+    f1 = grad_of(FusedRollout.apply(theta, None, eng, Call(offset=1)))
+    f2 = grad_of(FusedRollout.apply(theta, None, eng, Call(offset=2)))
+    assert relerr(g1.cpu().numpy(), f1.cpu().numpy()) < TOL and relerr(g2.cpu().numpy(), f2.cpu().numpy()) < TOL
+    assert relerr(g1.cpu().numpy(), g2.cpu().numpy()) > 1e-2                     # different noise, different gradients
+    with pt.no_grad():                                                           # no gradient wanted: plain forward
+        FusedRollout.apply(theta, None, eng, Call(offset=3))
+    assert eng.rows_serial == 4
+
+
 def test_checkpointed_backward_rejects_ineligible_configuration(monkeypatch):
     import pspde
     from pspde.fused import Call
