@@ -89,7 +89,11 @@ class RolloutEngine:
             if take < max(tile, need // 10):                  # less than a tenth of the batch: not worth a second code path
                 self.ckpt_ok = False
                 return None
-            self.ckpt, self._ckpt_need = pt.empty(take, dtype=pt.uint8, device=self.device), need
+            try:
+                self.ckpt, self._ckpt_need = pt.empty(take, dtype=pt.uint8, device=self.device), need
+            except pt.cuda.OutOfMemoryError:                  # fragmented pool: stay on the two-rollout step
+                self.ckpt_ok = False
+                return None
         return self.ckpt
 
     def set_x0(self, x0):
