@@ -33,6 +33,15 @@ class Call:
         self.grad_enabled = True     # set by FusedRollout.apply: was autograd recording when the rollout was called
 
 
+def rows_buffer_bytes(need, n_tiles, cap, free):
+    """Bytes of the single-rollout step's row buffer: whole 128-path tiles, at most `need` (all tiles), `cap`
+    (PSPDE_FWD_CKPT_MAX_GB) and 60 % of the free device memory; 0 when that is less than a tenth of the batch (not worth
+    keeping a second code path busy)."""
+    tile = need // n_tiles
+    take = int(min(need, cap, 0.6 * free)) // tile * tile
+    return take if take >= max(tile, need // 10) else 0
+
+
 class RolloutEngine:
     def __init__(self, problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive=True, k_offset=0,
                  K_global=None, seed=42, device=None, want_X_N=True):
@@ -82,11 +91,10 @@ class RolloutEngine:
             return None
         if self.ckpt is None or self._ckpt_need != need:
             self.ckpt = None
-            tile = need // ((self.K_local + 127) // 128)
             cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", "96")) * 2 ** 30
             free, _ = pt.cuda.mem_get_info(self.device)
-            take = int(min(need, cap, 0.6 * free)) // tile * tile
-            if take < max(tile, need // 10):                  # less than a tenth of the batch: not worth a second code path
+            take = rows_buffer_bytes(need, (self.K_local + 127) // 128, cap, free)
+            if take == 0:
                 self.ckpt_ok = False
                 return None
             try:

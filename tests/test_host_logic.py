@@ -77,6 +77,24 @@ def test_flat_parameter_buffer_and_module_adam():
         assert pt.equal(a.detach(), b)
 
 
+def test_rows_buffer_sizing():
+    """Single-rollout step: the row buffer is whole tiles, bounded by the cap and by 60 % of the free memory, and not
+    taken at all below a tenth of the batch (pspde/fused.py::rows_buffer_bytes)."""
+    from pspde.fused import rows_buffer_bytes
+    GB = 2 ** 30
+    tile = 100 * 68 * 2048                                   # C2: N = 100, C4 = 68 column groups
+    need = 512 * tile                                        # K = 2^16
+    assert rows_buffer_bytes(need, 512, 96 * GB, 170 * GB) == need                 # fits: every tile
+    part = rows_buffer_bytes(need, 512, 2 * GB, 170 * GB)                          # capped: whole tiles below 2 GB
+    assert 0 < part <= 2 * GB and part % tile == 0 and part + tile > 2 * GB
+    assert rows_buffer_bytes(need, 512, 96 * GB, 5 * GB) == int(0.6 * 5 * GB) // tile * tile
+    assert rows_buffer_bytes(need, 512, 0.5 * GB, 170 * GB) == 0                   # < 10 % of the batch
+    assert rows_buffer_bytes(need, 512, 0, 170 * GB) == 0                          # PSPDE_FWD_CKPT_MAX_GB=0
+    c5 = 8192 * 200 * 68 * 2048                                                    # C5: 228 GB do not fit 180 GB
+    kept = rows_buffer_bytes(c5, 8192, 96 * GB, 170 * GB)
+    assert kept % (200 * 68 * 2048) == 0 and 0.44 < kept / c5 < 0.46
+
+
 def test_shard_range_covers_everything():
     from pspde.dist import shard_range
     for K in (1, 7, 200, 65536, 65537):
