@@ -834,6 +834,26 @@ def test_single_rollout_rows_belong_to_their_forward():
     assert eng.rows_serial == 4
 
 
+def test_flat_adam_equals_per_module_adam_on_device():
+    """'outer' mode on the GPU: one Adam update over the flat buffer against N per-module torch Adams.  The op sequence is
+    torch's (bit-equal to its single-tensor implementation, CPU test in test_host_logic.py); torch's foreach CUDA kernels
+    round a few operations differently, hence a tolerance of a few ulp of the update here."""
+    import pspde
+    prob = pspde.LQGC(d=10, T=1.0, device="cuda")
+    mk = lambda: pspde.Solver("x", prob, K=64, delta_t=0.05, lr=1e-3, detach_forward=True, verbose=False,
+                              u_l2_error_flag=False)
+    A, B = mk(), mk()
+    B._flat_adam = False
+    gen = pt.Generator(device="cuda").manual_seed(0)
+    for it in range(4):
+        g = pt.randn(A._theta.numel(), device="cuda", generator=gen)
+        for S in (A, B):
+            S._theta.grad.copy_(g)
+            S.optimization_step()
+        assert relerr(A._theta.detach().cpu().numpy(), B._theta.detach().cpu().numpy()) < 1e-6
+    assert A._flat_adam and len(A.z_n) == 20
+
+
 def test_checkpointed_backward_rejects_ineligible_configuration(monkeypatch):
     import pspde
     from pspde.fused import Call

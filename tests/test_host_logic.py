@@ -77,6 +77,39 @@ def test_flat_parameter_buffer_and_module_adam():
         assert pt.equal(a.detach(), b)
 
 
+def test_flat_adam_equals_per_module_adam():
+    """'outer' mode: the single Adam update over the flat buffer is bit-equal to N per-module torch Adams, shares its
+    state with them (views), and hands over cleanly when a learning rate is changed or a module is stepped by hand."""
+    import pspde
+    prob = pspde.LQGC(d=3, T=0.25, device="cpu")
+    mk = lambda: pspde.Solver("x", prob, K=8, delta_t=0.05, lr=0.01, detach_forward=True, verbose=False, device="cpu")
+    A, B = mk(), mk()
+    B._flat_adam = False                                   # B: the per-module loop
+    gen = pt.Generator().manual_seed(0)
+    for it in range(5):
+        g = pt.randn(A._theta.numel(), generator=gen)
+        for S in (A, B):
+            S._theta.grad.copy_(g)
+            S.optimization_step()
+        if it == 2:                                        # from here on one module trains slower: both take the loop
+            for S in (A, B):
+                S.z_n[1].optim.param_groups[0]['lr'] = 0.003
+        assert pt.equal(A._theta.detach(), B._theta.detach())
+    assert A._flat_adam and not B._flat_adam
+    qa, qb = next(A.z_n[2].parameters()), next(B.z_n[2].parameters())
+    sa, sb = A.z_n[2].optim.state[qa], B.z_n[2].optim.state[qb]
+    assert float(sa['step']) == float(sb['step']) == 5
+    assert pt.equal(sa['exp_avg'], sb['exp_avg']) and pt.equal(sa['exp_avg_sq'], sb['exp_avg_sq'])
+    assert sa['exp_avg'].data_ptr() >= A._flat_adam['exp_avg'].data_ptr()          # a view of the flat state
+    A.z_n[0].optim = pt.optim.Adam(A.z_n[0].parameters(), lr=0.01)                 # replaced optimizer: state rebuilt
+    A._theta.grad.fill_(0.5)
+    A.optimization_step()
+    assert float(A.z_n[0].optim.state[next(A.z_n[0].parameters())]['step']) == 1
+    A.z_n[3].optim = pt.optim.SGD(A.z_n[3].parameters(), lr=0.01)                  # not Adam: per-module loop for all
+    A.optimization_step()
+    assert not A._flat_adam
+
+
 def test_rows_buffer_sizing():
     """Single-rollout step: the row buffer is whole tiles, bounded by the cap and by 60 % of the free memory, and not
     taken at all below a tenth of the batch (pspde/fused.py::rows_buffer_bytes)."""
