@@ -311,7 +311,7 @@ __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, con
   }
 }
 
-// acc -> grad_partial (this CTA's private slice; plain read-modify-write, one writer per element), then clear.
+// acc -> grad_partial (this CTA's private slice; fire-and-forget adds, one writer per element), then clear.
 // Must be called by all lanes of a warp (row-split warps combine their chunks with shuffles first).
 __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, const BwSlot& slot,
                                          float* __restrict__ gp, int lane) {
@@ -326,6 +326,11 @@ __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, con
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = 4 * (i < 4 ? kg : kg + y.kgh) + (i & 3);
+    // theta_index is affine in the column for a fixed row: two evaluations per row instead of one per element (its
+    // segment search dominated 'outer' mode, which flushes every step: ncu, C1)
+    const int ib0 = theta_index(g, l, row, 0);
+    const int ib1 = y.N > 1 ? theta_index(g, l, row, 1) : -1;
+    const int ics = ib1 >= 0 ? ib1 - ib0 : 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float v[2];
@@ -341,8 +346,11 @@ __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, con
       for (int h = 0; h < 2; ++h) {
         const int col = 4 * (q < 2 ? ng : ng + y.ngh) + 2 * (q & 1) + h;
         const bool ok = writer && (i < 4 || kg + y.kgh < y.nkg) && (q < 2 || ng + y.ngh < y.nng);
-        const int idx = ok ? theta_index(g, l, row, col) : -1;
-        if (idx >= 0) gp[idx] += v[h];
+        const int idx = (ok && ib0 >= 0 && col < y.N) ? ib0 + col * ics : -1;
+        // RED.ADD, not load-add-store: 64 dependent global round trips per thread cost ~100 k cycles per flush, which
+        // 'outer' mode pays every step (measured at C1).  Still one writer per element and program order per address,
+        // so the sums stay bitwise deterministic.
+        if (idx >= 0) atomicAdd(gp + idx, v[h]);
       }
     }
   }
