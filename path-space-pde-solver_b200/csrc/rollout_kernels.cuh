@@ -362,12 +362,17 @@ __device__ __forceinline__ void stage_weights(const NetGeom& g, const float* __r
                                               int nthr) {
   for (int l = 0; l < g.L; ++l) {
     const LayerGeom& y = g.layer[l];
-    const int tot = y.Kp * y.Np;
-    for (int q = tid; q < tot; q += nthr) {        // q = shared offset; decode (row, col) of the blocked layout
-      const int blk = q >> 4, in = q & 15;
-      const int r = 4 * (blk / y.nng) + (in >> 2), n = 4 * (blk % y.nng) + (in & 3);
-      const int idx = theta_index(g, l, r, n);
-      sW[y.w_off + q] = idx >= 0 ? __ldg(th + idx) : 0.f;
+    const int tot4 = (y.Kp * y.Np) >> 2;
+    for (int q4 = tid; q4 < tot4; q4 += nthr) {    // 4 q4 = shared offset of one row of a 4x4 block: 4 consecutive columns
+      const int blk = q4 >> 2;
+      const int r = 4 * (blk / y.nng) + (q4 & 3), n0 = 4 * (blk % y.nng);
+      // theta_index is affine in the column for a fixed row: two evaluations per 4 elements ('outer' mode stages every step)
+      const int b0 = theta_index(g, l, r, n0);
+      const int b1 = n0 + 1 < y.N ? theta_index(g, l, r, n0 + 1) : -1;
+      const int cs = b1 >= 0 ? b1 - b0 : 1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sW[y.w_off + 4 * q4 + c] = (b0 >= 0 && n0 + c < y.N) ? __ldg(th + b0 + c * cs) : 0.f;
     }
   }
 }
