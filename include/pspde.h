@@ -295,6 +295,13 @@ int pspde_philox_dump(const pspde_cfg* cfg, float* xi_out, void* stream);
  * K % 8 == 0, N % 16 == 0, N <= 256, 2K + N <= 512.  variant 0 is the production descriptor encoding. */
 int pspde_tc_selftest(int K, int N, int variant, const float* A, const float* B, float* D, void* stream);
 
+/* Self test of the TMA-fed operand path of the tensor-core gradient kernel (csrc/grad_tc_kernels.cuh): T is a device matrix
+ * [R][128] fp32 (one row of 128 samples per column: the checkpoint layout); D[128 x N] = T[0..127] . T[rB..rB+N)' over the 128
+ * samples, loaded 32 samples at a time by cp.async.bulk.tensor with CU_TENSOR_MAP_SWIZZLE_128B and multiplied by SS-mode
+ * tcgen05.mma kind::tf32 (3 passes).  raw (nullable, R * 32 floats) receives the shared-memory image of the first box.
+ * 128 <= R <= 256, R % 8 == 0, rB % 8 == 0, N % 16 == 0, rB + N <= R. */
+int pspde_tma_selftest(int R, int rB, int N, const float* T, float* D, float* raw, void* stream);
+
 /* Deterministic fp32 FMA throughput probe (roofline denominator measured live by bench.py):
  * runs `iters` dependent-chain FMA rounds on every SM; returns the FLOP count launched, or <0. */
 int64_t pspde_fma_probe(int iters, float* sink, void* stream);

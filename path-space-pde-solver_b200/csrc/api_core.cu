@@ -16,7 +16,7 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
   const bool keep_ckpt = keep_tiles > 0;
 #if !defined(PSPDE_EMULATE)
   TcGeom tg;
-  const char* path = getenv("PSPDE_FWD_PATH");
+  const char* path = getenv("PSPDE_FWD_PATH");     // per call on purpose: the A/B tests switch paths inside one process
   const bool eligible = tc_allowed && cfg->N >= 1 && !(cfg->problem_flags & PSPDE_FLAG_DENSE_AB) && tc_geom(pl.g, cfg->d, tg);
   if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core forward kernel's shape class");
   if (eligible && !(path && !strcmp(path, "simt"))) {
@@ -24,7 +24,7 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
     const int sms = pspde_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     p.n_tiles = n_tiles;
-    if (keep_ckpt) { p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles; }
+    if (keep_ckpt) { p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles; }
     const cudaError_t ce = keep_ckpt ? tc_launch_fwd_ckpt(p, tg, grid, (cudaStream_t)stream) : tc_launch(p, tg, grid, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
@@ -41,15 +41,17 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
 
 // ---- checkpointed detached backward: tensor-core forward (CKPT) + gradient accumulation, one wave of tiles at a time
 struct CkptPlan {
-  int n_tiles128, wave, c4, s0, grid_b;
+  int n_tiles128, wave, cols, s0, grid_b;
   size_t ckpt_bytes, grad_bytes;
 };
 
-// Gradient accumulation from the checkpoint rows: the tensor-core kernel (grad_tc_kernels.cuh) for the shape class it
-// covers, else the FP32-FMA kernel (grad_kernels.cuh).  PSPDE_GRAD_PATH=simt forces the FMA kernel (A/B tests),
-// PSPDE_GRAD_PATH=tc makes an ineligible configuration an error.
-static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, int n_items, void* stream, bool* used_tc) {
+// Gradient accumulation from the checkpoint rows of n_ts (tile, step) pairs: the tensor-core kernel (grad_tc_kernels.cuh)
+// for the shape class it covers, else the FP32-FMA kernel (grad_kernels.cuh).  PSPDE_GRAD_PATH=simt forces the FMA kernel
+// (A/B tests), PSPDE_GRAD_PATH=tc makes an ineligible configuration an error.  `grid` = CTAs (<= n_ts; every CTA writes
+// its own gradient partial).
+static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, long long n_ts, void* stream, bool* used_tc) {
   *used_tc = false;
+  if (n_ts < 1 || n_ts > 0x3fffffffLL) return fail(-6, "bad number of (tile, step) pairs for one gradient launch (%lld)", n_ts);
 #if !defined(PSPDE_EMULATE)
   GradTcGeom gt;
   const char* path = getenv("PSPDE_GRAD_PATH");
@@ -58,9 +60,11 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
   if (eligible && !(path && !strcmp(path, "simt"))) {
     if (cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt.total) != cudaSuccess)
       return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", gt.total);
-    int flush_items = kGtFlushItems;
-    if (const char* e = getenv("PSPDE_GRAD_FLUSH_ITEMS")) { const int v = atoi(e); if (v >= 1) flush_items = v; }
-    grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(p, gt, n_items, flush_items);
+    int flush_stages = kGtFlushStages;
+    if (const char* e = getenv("PSPDE_GRAD_FLUSH_STAGES")) { const int v = atoi(e); if (v >= 1) flush_stages = v; }
+    CUtensorMap tmap;
+    if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap)) return fail(-11, "cuTensorMapEncodeTiled failed for the checkpoint buffer");
+    grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(tmap, p, gt, (int)n_ts, flush_stages);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
     *used_tc = true;
@@ -69,6 +73,7 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
 #else
   (void)cfg;
 #endif
+  const int n_items = (int)(n_ts * (kCkP / kP));          // FMA kernel: work items of kP samples
   if (pl.T == 256) return pspde_launch_grad_256(pl, p, grid, n_items, stream);
   if (pl.T == 512) return pspde_launch_grad_512(pl, p, grid, n_items, stream);
   return fail(-13, "internal: no gradient kernel for T=%d", pl.T);
@@ -119,16 +124,16 @@ static bool ckpt_plan(const pspde_cfg* cfg, const Plan& pl, TcGeom& tg, CkptPlan
   // PSPDE_WAVE_TILES_PER_SM overrides the first choice.
   int per_sm = 2;
   if (const char* e = getenv("PSPDE_WAVE_TILES_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
-  const size_t tile_bytes = (size_t)cfg->N * tc_ckpt_c4(tg) * kTcP * 16;
+  const size_t tile_bytes = (size_t)cfg->N * tc_ckpt_cols(tg) * kTcP * 4;
   auto wave_of = [&](int ps) { return cp.n_tiles128 < ps * sms ? cp.n_tiles128 : ps * sms; };
   if ((size_t)wave_of(per_sm) * tile_bytes > ((size_t)12 << 30)) per_sm = 1;
   if ((size_t)wave_of(per_sm) * tile_bytes > ((size_t)24 << 30)) return false;
   cp.wave = wave_of(per_sm);
-  cp.c4 = tc_ckpt_c4(tg);
+  cp.cols = tc_ckpt_cols(tg);
   cp.s0 = tg.s0;
-  const long long items = (long long)cp.wave * cfg->N * (kTcP / kP);
-  cp.grid_b = items < sms ? (int)items : sms;
-  cp.ckpt_bytes = align256((size_t)cp.wave * cfg->N * cp.c4 * kTcP * 16);
+  const long long n_ts = (long long)cp.wave * cfg->N;
+  cp.grid_b = n_ts < sms ? (int)n_ts : sms;
+  cp.ckpt_bytes = align256((size_t)cp.wave * cfg->N * cp.cols * kTcP * 4);
   cp.grad_bytes = align256((size_t)cp.grid_b * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
   return true;
 }
@@ -146,7 +151,7 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
   if (cfg->N < 1 || !cfg->adaptive || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return 0;
   if (!grad_tc_geom(pl.g, cfg->d, tg.s0, gt)) return 0;
   const size_t n_tiles = (size_t)(cfg->K_local + kTcP - 1) / kTcP;
-  const size_t tb = (size_t)cfg->N * tc_ckpt_c4(tg) * kTcP * 16;       // one 128-path tile; a multiple of 2 KB
+  const size_t tb = (size_t)cfg->N * tc_ckpt_cols(tg) * kTcP * 4;      // one 128-path tile; a multiple of 512 B
   if (tile_bytes) *tile_bytes = tb;
   return n_tiles * tb;
 #else
@@ -160,7 +165,7 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
 // rows (cotangents p.wY / p.wZ applied) into p.ckpt, then the gradient kernel; accumulates into p.grad_partial
 static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, const TcGeom& tg, const CkptPlan& cp, int t_begin,
                      void* stream, bool* used_tc) {
-  p.ckpt_c4 = cp.c4; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0;
+  p.ckpt_cols = cp.cols; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0;
   const int sms = pspde_sm_count();
   for (int t0 = t_begin; t0 < cp.n_tiles128; t0 += cp.wave) {
     const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
@@ -168,8 +173,8 @@ static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, con
     const cudaError_t ce = tc_launch_t<true>(p, tg, nt < sms ? nt : sms, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core checkpoint rollout launch failed: %s", cudaGetErrorString(ce));
-    const long long items = (long long)nt * cfg->N * (kTcP / kP);
-    const int rc = launch_grad(cfg, pl, p, items < cp.grid_b ? (int)items : cp.grid_b, (int)items, stream, used_tc);
+    const long long n_ts = (long long)nt * cfg->N;
+    const int rc = launch_grad(cfg, pl, p, n_ts < cp.grid_b ? (int)n_ts : cp.grid_b, n_ts, stream, used_tc);
     if (rc) return rc;
   }
   return 0;
@@ -348,18 +353,18 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   if (pl.g.L != 3 || pl.g.time_mode == TIME_NONE || pl.g.seg_len[1] > 32 || pl.g.seg_len[2] > 32)
     return fail(-6, "configuration is outside the checkpointed backward's shape class");
   const int sms = pspde_sm_count();
-  const long long items = (long long)n_slots * cfg->N * (kCkP / kP);
-  const int grid = items < sms ? (int)items : sms;
+  const long long n_ts = (long long)n_slots * cfg->N;
+  const int grid = n_ts < sms ? (int)n_ts : sms;
   const size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, s0) * sizeof(float));
   if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
-  p.ckpt = const_cast<float*>(ckpt); p.ckpt_c4 = 2 * (s0 >> 2) + 16; p.ckpt_s0 = s0;
+  p.ckpt = const_cast<float*>(ckpt); p.ckpt_cols = 2 * s0 + 64; p.ckpt_s0 = s0;
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
   bool used_tc = false;
-  rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
+  rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);
   if (rc) return rc;
   return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
 }
@@ -381,9 +386,8 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
   const int sms = pspde_sm_count();
   const int n_tiles = (cfg->K_local + kTcP - 1) / kTcP;
   const int n_keep = (int)((ckpt_bytes < need ? ckpt_bytes : need) / tb);       // tiles whose rows the forward kept
-  const long long items = (long long)n_keep * cfg->N * (kTcP / kP);
-  if (items > 0x7fffffffLL) return fail(-6, "too many work items for one gradient launch");
-  int grid = items < sms ? (int)items : sms;
+  const long long n_ts = (long long)n_keep * cfg->N;
+  int grid = n_ts < sms ? (int)n_ts : sms;
   size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, tg.s0) * sizeof(float));
   size_t ws_need = pl.stats_bytes + gbytes;
   CkptPlan cp;
@@ -401,11 +405,11 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
-  p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_c4 = tc_ckpt_c4(tg); p.ckpt_s0 = tg.s0;
+  p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0;
   p.tile0 = 0; p.ckpt_unit = 1;
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
   bool used_tc = false;
-  rc = launch_grad(cfg, pl, p, grid, (int)items, stream, &used_tc);
+  rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);
   if (rc) return rc;
   if (!used_tc) return fail(-13, "internal: the forward checkpoint needs the tensor-core gradient kernel");
   int nparts = grid;

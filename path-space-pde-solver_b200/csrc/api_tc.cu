@@ -1,6 +1,7 @@
 // api_tc.cu -- tensor-core (tcgen05 / tensor memory) building block and its self test.
 #include "api_common.h"
 #include "tc_sm100.cuh"
+#include "grad_tc_kernels.cuh"
 
 #if !defined(PSPDE_EMULATE)
 namespace pspde {
@@ -99,8 +100,89 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// TMA + swizzled-operand building block of the gradient kernel: T is [R][128] fp32 (one 512-byte row of 128 samples per
+// column, the checkpoint layout).  For each of the 4 sample blocks a TMA box (32 samples x R rows, 128-byte swizzle)
+// lands in shared memory, a lo tile is formed element-wise and D[128 x N] += T[0..127][:] . T[rB..rB+N][:]' is accumulated
+// through SS-mode tcgen05.mma with SWIZZLE_128B K-major descriptors (3 passes).  `raw` (nullable) receives the shared-memory
+// image of the first block (R * 32 floats) so that the host can check the swizzle pattern.
+__global__ void __launch_bounds__(128, 1) tma_selftest_kernel(const __grid_constant__ CUtensorMap tmap, int R, int rB, int N,
+                                                              float* __restrict__ D, float* __restrict__ raw) {
+  extern __shared__ float4 smem4[];
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
+  smem += (1024u - (tc::smem_u32(smem) & 1023u)) & 1023u;
+  uint8_t* tH = smem;
+  uint8_t* tL = smem + (uint32_t)R * 128u;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { tc::mbar_init(&bar_full, 1); tc::mbar_init(&bar_mma, 1); tc::mbar_fence_init(); }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  for (int sub = 0; sub < 4; ++sub) {
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&bar_full, (uint32_t)R * 128u);
+      tc::tma_load_3d(tH, &tmap, &bar_full, sub * 32, 0, 0);
+    }
+    tc::mbar_wait(&bar_full, (uint32_t)sub & 1u);
+    if (sub == 0 && raw)
+      for (int q = tid; q < R * 32; q += 128) raw[q] = reinterpret_cast<const float*>(tH)[q];
+    for (int q = tid; q < R * 8; q += 128) reinterpret_cast<float4*>(tL)[q] = lo4(reinterpret_cast<const float4*>(tH)[q]);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL), id = tc::idesc_tf32(128, N);
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 0) ? sL : sH, b = ((pass == 1) ? sL : sH) + (uint32_t)rB * 128u;
+        for (int ks = 0; ks < 4; ++ks)
+          tc::mma_tf32_ss(tbase, tc::smem_desc_sw128(a + (uint32_t)ks * 32u), tc::smem_desc_sw128(b + (uint32_t)ks * 32u), id,
+                          sub > 0 || pass > 0 || ks > 0);
+      }
+      tc::mma_commit(&bar_mma);
+    }
+    tc::mbar_wait(&bar_mma, (uint32_t)sub & 1u);       // the tile is overwritten by the next block
+    tc::fence_after_sync();
+  }
+  const uint32_t lane_addr = ((uint32_t)(32 * warp)) << 16;
+  for (int n0 = 0; n0 < N; n0 += 8) {
+    float v[8];
+    tc::tmem_ld8(tbase + lane_addr + (uint32_t)n0, v);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[tid * N + n0 + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace pspde
 #endif
+
+extern "C" int pspde_tma_selftest(int R, int rB, int N, const float* T, float* D, float* raw, void* stream) {
+#if defined(PSPDE_EMULATE)
+  (void)R; (void)rB; (void)N; (void)T; (void)D; (void)raw; (void)stream;
+  return fail(-20, "the tensor-core path does not exist in the host emulator");
+#else
+  if (R < 128 || R > 256 || (R & 7) || (rB & 7) || rB < 0 || N < 16 || (N & 15) || N > 256 || rB + N > R || !T || !D)
+    return fail(-2, "bad selftest shape");
+  GradTcGeom tg;
+  memset(&tg, 0, sizeof(tg));
+  tg.cols = R; tg.box_rows = R;
+  CUtensorMap tmap;
+  if (grad_tc_tensor_map(tg, T, 1, &tmap)) return fail(-11, "cuTensorMapEncodeTiled failed");
+  const size_t smem = 2 * (size_t)R * 128 + 1024;
+  if (pspde_set_smem(tma_selftest_kernel, smem)) return fail(-11, "cudaFuncSetAttribute failed");
+  tma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmap, R, rB, N, D, raw);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "tma_selftest launch failed: %s", e);
+  return 0;
+#endif
+}
 
 extern "C" int pspde_tc_selftest(int K, int N, int variant, const float* A, const float* B, float* D, void* stream) {
 #if defined(PSPDE_EMULATE)

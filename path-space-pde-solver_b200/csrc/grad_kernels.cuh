@@ -7,7 +7,7 @@
 //     delta_2 = (zeta W2[h2 rows]') * act'(h2),  delta_1 = (zeta W2[h1 rows]' + delta_2 W1[h1 rows]') * act'(h1)
 // and dW_l += act_l' delta_l.  The tensor-core forward kernel (rollout_tc_fwd_kernel<.., CKPT = true>) regenerates the
 // trajectories of one WAVE of tiles (at most one 128-path tile per SM) and leaves those rows in the checkpoint
-// buffer; this kernel streams them back (L2 / HBM, 1 088 B per sample at the C2 shape), P = 64 samples at a time,
+// buffer; this kernel streams them back (L2 / HBM, 1 088 B per sample at the C2 shape; column-major rows of 128 paths), P = 64 samples at a time,
 // and accumulates the weight gradient in registers exactly like rollout_kernel<BWD = true> does (same routines:
 // net_backward_hidden, bw_accum, bw_flush).  The buffer is per wave, so its size does not depend on K.
 // The samples are independent: work items (slot, step, half tile) are dealt round-robin to the CTAs.
@@ -39,28 +39,27 @@ __global__ void __launch_bounds__(T, 1) grad_kernel(const RolloutParams prm, con
   const BwSlot slot = bw_slot(g, P, tid, T);
   float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
 
-  // checkpoint column groups -> tiles: segment s of the activation row, then zeta
-  const int s04 = prm.ckpt_s0 >> 2;
-  const int seg_src[3] = {0, s04, s04 + 8};
-  const int ze_src = s04 + 16, ze_n = ceil4(prm.d) >> 2;
-  const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
+  // checkpoint columns -> tiles: segment s of the activation row, then zeta (column-major rows of 128 paths)
+  const int s0 = prm.ckpt_s0;
+  const int seg_src[3] = {0, s0, s0 + 32};
+  const int ze_src = s0 + 64, ze_n = ceil4(prm.d);
+  const float* ck = prm.ckpt;
   int since_flush = 0;
   __syncthreads();
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int ts = item / HALVES, half = item - ts * HALVES;
-    const float4* src = ck + (size_t)ts * prm.ckpt_c4 * kCkP + half * P;
+    const float* src = ck + (size_t)ts * prm.ckpt_cols * kCkP + half * P;
     for (int s = 0; s < g.L; ++s) {
-      const int ng4 = g.seg_len[s] >> 2;
       float* dst = sAct + g.seg_off[s];
-      for (int q = tid; q < ng4 * P; q += T) {
-        const int c4 = q / P, p = q - c4 * P;
-        st4(dst + p * g.lda + 4 * c4, __ldg(src + (size_t)(seg_src[s] + c4) * kCkP + p));
+      for (int q = tid; q < g.seg_len[s] * P; q += T) {
+        const int c = q / P, p = q - c * P;
+        dst[p * g.lda + c] = __ldg(src + (size_t)(seg_src[s] + c) * kCkP + p);
       }
     }
     for (int q = tid; q < ze_n * P; q += T) {
-      const int c4 = q / P, p = q - c4 * P;
-      st4(sZe + p * g.ldz + 4 * c4, __ldg(src + (size_t)(ze_src + c4) * kCkP + p));
+      const int c = q / P, p = q - c * P;
+      sZe[p * g.ldz + c] = c < prm.ckpt_s0 ? __ldg(src + (size_t)(ze_src + c) * kCkP + p) : 0.f;
     }
     __syncthreads();
     net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);

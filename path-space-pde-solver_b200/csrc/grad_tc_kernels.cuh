@@ -1,121 +1,130 @@
-// grad_tc_kernels.cuh -- gradient accumulation from the checkpoint rows with the WEIGHT GRADIENT on the 5th-generation
-// tensor cores (tcgen05 + tensor memory).  Same contract as grad_kernel (grad_kernels.cuh): a pure streaming kernel
-// over (trajectory, step) samples, dtheta = sum_samples J_theta Z(a0)' zeta.
+// grad_tc_kernels.cuh -- gradient accumulation from the checkpoint rows: a TMA-fed, warp-specialised tcgen05 pipeline.
+// Same contract as grad_kernel (grad_kernels.cuh): a pure streaming kernel over (trajectory, step) samples,
+//     dtheta = sum_samples J_theta Z(a0)' zeta                                   (reference: loss.backward(), solver.py:221).
 //
 // The reduction dimension K of the weight gradient
 //     D[act col][cot col] += sum_samples act[sample][act col] * cot[sample][cot col]
-// is the SAMPLE index, M = activation column, N = cotangent column.  A half tile (64 samples) of checkpoint rows is
-// copied into shared memory with a 4 x 4 register transpose so that four consecutive samples of one column form a
-// float4: element (row r, sample 4 j + i) at j * LBO + r * 16 + i * 4 bytes, the canonical no-swizzle K-major operand
-// layout of tcgen05.mma (8-row x 16-byte core matrices, SBO = 128 B).  All columns -- [a0 | h1 | h2] and
-// [zeta | delta_2 | delta_1] -- are rows of ONE such matrix, so the A operand (two M tiles: rows 0..127, 128..255) and
-// the B operand (rows from zeta on: zeta padded to a multiple of 16 | delta_2 | delta_1, N = 176 at the C2 shape) are
-// windows of the same tile; the zeta columns are issued right after the copy (beside the hidden-cotangent FMA code),
-// the delta columns when they exist.  (MN-major descriptors,
-// which would accept the checkpoint layout without the transpose, returned zeros for kind::tf32 without swizzle.)
-// FP32 equivalence as in tc_sm100.cuh: the tile holds the raw FP32 values, which the tensor core truncates to TF32
-// (hi = trunc(x)), a second tile holds lo = x - trunc(x); three passes lo*hi + hi*lo + hi*hi into the FP32
-// accumulators in tensor memory (2 M tiles x N columns), which stay resident for the whole launch and are added to
-// the CTA's gradient partial once at the end.
+// is the SAMPLE index, M = activation column, N = cotangent column.  The checkpoint keeps, per (tile, step), one row of
+// 128 consecutive paths for every column of [a0 | h1 | h2 | zeta] (RolloutParams::ckpt: column-major, the path index
+// contiguous), i.e. exactly the K-major operand form of tcgen05.mma with K = sample.  A stage is 32 samples -- one 128-byte
+// row per column -- and arrives by TMA (cp.async.bulk.tensor, CU_TENSOR_MAP_SWIZZLE_128B) straight in the operand layout
+// (8 rows x 128 B atoms, 16-byte chunk index xor-ed with the row inside the atom): no transposing copy, no register staging.
+// All columns -- [a0 | h1 | h2] and [zeta | delta_2 | delta_1] -- are rows of ONE such tile, so the A operand (M tiles: rows
+// 0..127, 128..255) and the B operand (rows from zeta on, N = 176 at the C2 shape) are windows of the same tile.
+// FP32 equivalence as in tc_sm100.cuh: the tile holds raw FP32 values, which the tensor core truncates to TF32
+// (hi = trunc(x)); a second tile holds lo = rna_tf32(x - trunc(x)); three passes lo*hi + hi*lo + hi*hi into the FP32
+// accumulators in tensor memory (n_mt x nB columns), flushed to the CTA's partial every few stages (see below).
 //
-// The hidden cotangents delta_2, delta_1 (6 900 of the 29 960 MACs per sample at the C2 shape) are formed by FP32
-// FMA code on 4 samples x 4 hidden columns per thread that reads zeta / h straight from the operand tile (one
-// LDS.128 = one column of a sample quad) and appends the result to it.
+// Warp roles (384 threads, one CTA per SM, 2-stage ring of (hi, lo) tiles = 172 KB at the C2 shape):
+//   warps 0-7   hidden cotangents: delta_2 = (zeta W2[h2 rows]') act'(h2), delta_1 = (zeta W2[h1 rows]' + delta_2 W1[h1 rows]')
+//               act'(h1) in FP32 FMA (4 samples x 4 hidden columns per thread, operands read from the swizzled tile),
+//               appended to the tile as rows (hi and lo)
+//   warp  8     TMA producer (one lane): waits for a free stage, arms the mbarrier, issues the two box loads
+//   warp  9     MMA issuer (one lane): when the lo tile and the delta rows of a stage exist; tcgen05.commit frees the stage
+//   warps 10-11 lo tile of the loaded rows (element-wise, layout agnostic)
+//   warps 8-11  additionally flush the accumulators (one lane quarter of tensor memory each)
 #pragma once
 #if !defined(PSPDE_EMULATE)
+#include <cuda.h>
 #include "grad_kernels.cuh"
 #include "tc_sm100.cuh"
 
 namespace pspde {
 
-constexpr int kGtS = 64;                 // samples per work item (half a checkpoint tile) = K of one MMA group
-constexpr int kGtThreads = 512;
-constexpr int kGtQ = kGtS / 4;           // sample quads per item
-constexpr int kGtFlushItems = 4;         // accumulator flush period (items of 64 samples = 48 MMAs per accumulator)
+constexpr int kGtS = 32;                 // samples per stage = one 128-byte swizzle row of K = 4 MMA k steps
+constexpr int kGtStages = 2;
+constexpr int kGtWorkers = 256;          // hidden-cotangent threads (warps 0-7)
+constexpr int kGtThreads = 384;
+constexpr int kGtSub = kCkP / kGtS;      // stages per (tile, step)
+constexpr int kGtFlushStages = 16;       // accumulator flush period: 16 stages x 12 MMAs per accumulator
 
 struct GradTcGeom {
-  int s04;             // column groups of a0 in the checkpoint (s0 / 4)
-  int act_groups;      // s04 + 16: [a0 | h1 | h2]
-  int ze_groups;       // s04: zeta (d used, the rest zero)
-  int g_ze, g_d2, g_d1, n_groups;        // first group of zeta / delta_2 / delta_1 in the tile; total incl. zero pad
+  int s0;              // columns of a0 in the checkpoint (multiple of 8)
+  int cols;            // checkpoint columns per sample: [a0 (s0) | h1 (32) | h2 (32) | zeta (s0)]
+  int act_rows;        // s0 + 64: rows [a0 | h1 | h2] of the operand tile
+  int r_ze, r_d2, r_d1, rows;   // first row of zeta / delta_2 / delta_1; tile rows (multiple of 8, >= 128 n_mt)
+  int box_rows;        // rows per TMA box (cols / 2)
   int nB;              // N of the weight-gradient product: zeta (padded to nE) | delta_2 (32) | delta_1 (32)
   int nE;              // zeta columns padded to a multiple of 16: their MMAs are issued before the hidden cotangents exist
   int dense;
   int n_mt;            // M tiles of 128 activation columns (1 when [a0 | h1 | h2] has at most 128 columns)
-  uint32_t lbo;        // bytes between sample quads of the operand tile: (4 n_groups + 1) * 16
   // compact weights for the hidden cotangents, k4-blocked: W2c rows = [h1 (32) | h2 (32)] columns (zero rows where
   // the layer does not read the column), W1c rows = h1 (32) columns
   int w2_nng, w1_nng, o_w2, o_w1;
-  uint32_t o_hi, o_lo, o_w, total;       // shared-memory byte offsets
+  uint32_t tile_bytes;                   // rows * 128
+  uint32_t o_hi[kGtStages], o_lo[kGtStages], o_w, o_bar, total;   // shared-memory byte offsets from the 1 KB aligned base
 };
 
 inline bool grad_tc_geom(const NetGeom& g, int d, int s0, GradTcGeom& t) {
   if (g.L != 3 || g.time_mode == TIME_NONE || g.seg_len[1] > 32 || g.seg_len[2] > 32 || (s0 & 7) || s0 < g.seg_len[0]) return false;
-  t.dense = g.kind == NET_DENSENET ? 1 : 0;
-  t.s04 = s0 >> 2;
-  t.act_groups = t.s04 + 16;
-  t.ze_groups = t.s04;
-  t.nE = ((4 * t.ze_groups + 15) / 16) * 16;
-  t.nB = t.nE + 64;
-  t.g_ze = t.act_groups; t.g_d2 = t.g_ze + t.nE / 4; t.g_d1 = t.g_d2 + 8;
-  t.n_groups = t.g_ze + t.nB / 4;
-  t.n_mt = t.act_groups > 32 ? 2 : 1;
-  if (t.n_groups < 32 * t.n_mt) t.n_groups = 32 * t.n_mt;     // M tile mt reads rows [128 mt, 128 mt + 128)
-  if (t.act_groups > 64 || t.nB > 256 || 2 * t.nB > 512) return false;
   (void)d;
-  t.lbo = (uint32_t)(4 * t.n_groups + 1) * 16u;    // odd number of 16-byte rows: 8 consecutive quads hit 8 distinct bank groups
+  t.dense = g.kind == NET_DENSENET ? 1 : 0;
+  t.s0 = s0;
+  t.cols = 2 * s0 + 64;
+  t.act_rows = s0 + 64;
+  t.box_rows = t.cols / 2;               // s0 + 32: a multiple of 8, so the second box starts on an atom boundary
+  if (t.box_rows > 256) return false;
+  t.nE = ((s0 + 15) / 16) * 16;
+  t.nB = t.nE + 64;
+  t.r_ze = t.act_rows; t.r_d2 = t.r_ze + t.nE; t.r_d1 = t.r_d2 + 32;
+  t.n_mt = t.act_rows > 128 ? 2 : 1;
+  t.rows = t.r_d1 + 32;
+  if (t.rows < 128 * t.n_mt) t.rows = 128 * t.n_mt;          // M tile mt reads rows [128 mt, 128 mt + 128)
+  if (t.nB > 256 || t.n_mt * t.nB > 512) return false;
   t.w2_nng = g.layer[2].nng; t.w1_nng = g.layer[1].nng;
+  t.tile_bytes = (uint32_t)t.rows * 128u;                    // a multiple of 1 KB (rows % 8 == 0)
   uint32_t o = 0;
-  t.o_hi = o; o += (uint32_t)kGtQ * t.lbo;
-  t.o_lo = o; o += (uint32_t)kGtQ * t.lbo;
+  for (int s = 0; s < kGtStages; ++s) { t.o_hi[s] = o; o += t.tile_bytes; t.o_lo[s] = o; o += t.tile_bytes; }
   t.o_w = o;
   t.o_w2 = 0; t.o_w1 = 64 * t.w2_nng * 4;
   o += (uint32_t)(64 * t.w2_nng * 4 + 32 * t.w1_nng * 4) * 4u;
-  t.total = o;
+  t.o_bar = (o + 15u) & ~15u; o = t.o_bar + 16u * 8u;
+  t.total = o + 1024u;                                       // slack for the 1 KB alignment of the base
   return t.total <= 227u * 1024u;
-}
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // lo = x - trunc(x), rounded to TF32 so that the tensor core's own truncation of it is exact
 __device__ __forceinline__ float lo1(float x) { return tc::tf32_hi(x - trunc_tf32(x)); }
 __device__ __forceinline__ float4 lo4(const float4& v) { return make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w)); }
-// one checkpoint float4 of a sample whose cotangent w is applied here (RolloutParams::ckpt_unit): zeta columns are scaled,
-// activation columns kept; w == 0 drops the sample (selects, no branches)
-__device__ __forceinline__ float4 scale_row(const float4& v, float w, bool is_ze) {
-  const float f = is_ze ? w : 1.0f;
-  const bool keep = w != 0.f;
-  return make_float4(keep ? v.x * f : 0.f, keep ? v.y * f : 0.f, keep ? v.z * f : 0.f, keep ? v.w * f : 0.f);
-}
 
-__global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutParams prm, const GradTcGeom tg, const int n_items,
-                                                                const int flush_items) {
-  extern __shared__ float4 smem4[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
-  __shared__ uint64_t bar_mma;
+// byte offset of (row r, sample quad j) in a swizzled tile: 16-byte chunk index xor-ed with the row inside the 8-row atom
+__device__ __forceinline__ uint32_t gt_swz(int r, int j) { return (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void gt_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// n_ts = number of (tile, step) pairs in the checkpoint; CTA b streams pairs b, b + grid, ... (4 stages each).
+// flush_stages: accumulator flush period in stages.
+static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __grid_constant__ CUtensorMap tmap, const RolloutParams prm,
+                                                                const GradTcGeom tg, const int n_ts, const int flush_stages) {
+  extern __shared__ float4 smem4_gt[];
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>(smem4_gt);
   __shared__ uint32_t tmem_base_s;
   const NetGeom& g = prm.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* tH = smem + tg.o_hi;
-  uint8_t* tL = smem + tg.o_lo;
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* sW = reinterpret_cast<float*>(smem + tg.o_w);
-  const uint32_t lbo = tg.lbo;
-  // element (row r = column of [a0 | h1 | h2 | zeta | delta_2 | delta_1], sample 4 j + i) sits at j * lbo + r * 16 + i * 4:
-  // the canonical no-swizzle K-major operand layout with K = sample (8 rows x 16 B core matrices, SBO = 128 B, LBO = lbo)
-  auto quad = [&](uint8_t* t, int r, int j) -> float4& { return *reinterpret_cast<float4*>(t + (uint32_t)j * lbo + (uint32_t)r * 16u); };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tg.o_bar);
+  uint64_t* bar_full = bars;                  // [stage] TMA bytes landed
+  uint64_t* bar_empty = bars + 2;             // [stage] the tensor core is done with the stage
+  uint64_t* bar_lo = bars + 4;                // [stage] lo tile of the loaded rows written
+  uint64_t* bar_dl = bars + 6;                // [stage] delta rows (hi, lo) written
+  uint64_t* bar_acc_full = bars + 8;          // accumulators complete up to a flush point
+  uint64_t* bar_acc_empty = bars + 9;         // accumulators read out: the next MMA may overwrite them
 
   // ---- one-time setup
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-  if (tid == 0) { tc::mbar_init(&bar_mma, 1); tc::mbar_fence_init(); }
-  for (uint32_t q = tid; q < 2u * kGtQ * lbo / 16u; q += kGtThreads) reinterpret_cast<float4*>(tH)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 32) {
+    for (int s = 0; s < kGtStages; ++s) {
+      tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1);
+      tc::mbar_init(&bar_lo[s], 64); tc::mbar_init(&bar_dl[s], kGtWorkers);
+    }
+    tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
+    tc::mbar_fence_init();
+  }
+  if (tid == 8 * 32) tc::tma_prefetch_desc(&tmap);
+  for (uint32_t q = tid; q < (uint32_t)kGtStages * 2u * tg.tile_bytes / 16u; q += kGtThreads)
+    reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 1; l <= 2; ++l) {            // compact k4-blocked weights: row = hidden column slot (32 per segment)
     const LayerGeom& y = g.layer[l];
     const int rows = l == 2 ? 64 : 32;
@@ -137,208 +146,202 @@ __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const RolloutPar
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
-  const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL);
 
-  const float4* ck = reinterpret_cast<const float4*>(prm.ckpt);
-  const int src_groups = tg.act_groups + tg.ze_groups;       // the checkpoint row: [a0 | h1 | h2 | zeta]
+  const int my_ts = (n_ts - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // (tile, step) pairs of this CTA
+  const int n_stage_it = my_ts > 0 ? my_ts * kGtSub : 0;
   const bool unit = prm.ckpt_unit != 0;
-  // hidden-cotangent mapping: warp = 4 hidden columns hc0 .. hc0 + 3 of [h1 (32) | h2 (32)], lane = (sample quad, half of
-  // the reduction range); the two halves are combined with one xor-shuffle
-  const int hc0 = 4 * warp, hj = lane & 15, hk = lane >> 4;
-  const bool is_h2 = hc0 >= 32;
-  const int seg_n = g.dims[is_h2 ? 2 : 1];
-  const int h_row = 4 * tg.s04 + hc0;                         // tile row of the hidden activation h[hc0]
-  // D[m tile][:, n0 .. n0 + n) += act' . cot[:, n0 .. n0 + n) over the 64 samples of the tile, three passes (thread 0)
-  auto issue = [&](int n0, int n, bool overwrite) {
-    const uint32_t id = tc::idesc_tf32(128, n);
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t a = (pass == 0) ? sL : sH;
-      const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)(4 * tg.g_ze + n0) * 16u;
-      for (int mt = 0; mt < tg.n_mt; ++mt)
-        for (int ks = 0; ks < kGtS / 8; ++ks) {
-          const uint64_t ad = tc::smem_desc(a + (uint32_t)mt * 2048u + (uint32_t)ks * 2u * lbo, lbo, 128u);
-          const uint64_t bd = tc::smem_desc(b + (uint32_t)ks * 2u * lbo, lbo, 128u);
-          mma_tf32_ss(tbase + (uint32_t)(mt * tg.nB + n0), ad, bd, id, !overwrite || pass > 0 || ks > 0);
-        }
-    }
+  // per-path cotangents of the 4 samples of quad j of stage iteration `it` (forward-written checkpoint, unit cotangents)
+  auto unit_w = [&](int it, int j, float (&w)[4]) {
+    const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
+    const int k0 = (prm.tile0 + ts / prm.N) * kCkP + sub * kGtS + 4 * j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = (k0 + i < prm.K_local) ? __ldg(prm.wY + k0 + i) : 0.f;
   };
-  // raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
-  // reduce_grad_tc_kernel sums the partials in fp64 and scatters them to theta.  A warp reads the lane quarter 32 (warp % 4).
-  // Called every flush_items items (see the note at the call site).
-  auto flush = [&]() {
-    float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
-    const int qtr = warp & 3, cpart = warp >> 2;          // 4 warps per lane quarter split the columns
-    for (int mt = 0; mt < tg.n_mt; ++mt) {
-      if (128 * mt + 32 * qtr >= 4 * tg.act_groups) continue;      // lanes past the last activation column hold garbage rows
-      for (int c0 = 8 * cpart; c0 < tg.nB; c0 += 32) {
-        float v[8];
-        tc::tmem_ld8(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
-        tc::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(gp + (size_t)(mt * tg.nB + c0 + i) * 128 + 32 * qtr + lane, v[i]);   // RED: no round trip; one writer per address
-      }
+  // forward-written checkpoint: scale the zeta rows by the per-path cotangent and drop (zero) every row of a path whose
+  // cotangent is zero, so that a diverged trajectory the loss has discarded cannot poison the sums.  Threads 0..319
+  // (delta + lo warps); thread t owns chunk position t & 7 of rows (t >> 3) + 40 i: its sample quad is fixed.
+  auto fixup = [&](uint8_t* tH, int it, int t) {
+    const int pos = t & 7, r0 = t >> 3;
+    const int j = pos ^ (r0 & 7);
+    float w[4];
+    unit_w(it, j, w);
+    for (int r = r0; r < tg.cols; r += 40) {
+      float4* p = reinterpret_cast<float4*>(tH + (uint32_t)r * 128u + (uint32_t)(pos << 4));
+      float4 v = *p;
+      const bool ze = r >= tg.r_ze;
+      v.x = w[0] != 0.f ? (ze ? v.x * w[0] : v.x) : 0.f; v.y = w[1] != 0.f ? (ze ? v.y * w[1] : v.y) : 0.f;
+      v.z = w[2] != 0.f ? (ze ? v.z * w[2] : v.z) : 0.f; v.w = w[3] != 0.f ? (ze ? v.w * w[3] : v.w) : 0.f;
+      *p = v;
     }
-  };
-  uint32_t ph = 0;
-  bool first = true, pending = false;
-  int since_flush = 0;
-  PhaseTimer pt_;          // debug: [0] wait for the tensor core, [1] copy + transpose, [2] hidden cotangents, [3] MMA issue, [4] zeta . W2', [5] delta_2 + barrier, [6] delta_2 . W1' + delta_1, [2] fences + barrier
-  pt_.start(prm.prof, tid == 32 ? 0 : 1);
-
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int ts = item / 2, half = item - ts * 2;
-    const float4* src = ck + (size_t)ts * prm.ckpt_c4 * kCkP + half * kGtS;
-    // ---- (1) copy [a0 | h1 | h2 | zeta] with a 4 x 4 register transpose (sample-major float4 -> sample quads per column);
-    //      all global loads of the thread are in flight before the first one is used
-    {
-      constexpr int MAXI = 3;
-      float4 v[MAXI][4];
-      const int nq = src_groups * kGtQ;
-      // checkpoint written by the forward pass (unit cotangents): the per-path cotangent dL/dY_N of the thread's 4 samples
-      // (its sample quad is tid & 15 in every iteration below) scales the zeta rows; a path with zero cotangent is dropped
-      // entirely, so that a diverged trajectory (non-finite rows) with zero weight cannot poison the sums.
-      float wq[4] = {1.f, 1.f, 1.f, 1.f};
-      if (unit) {
-        const int k0 = (prm.tile0 + ts / prm.N) * kCkP + half * kGtS + 4 * (tid & (kGtQ - 1));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wq[i] = (k0 + i < prm.K_local) ? __ldg(prm.wY + k0 + i) : 0.f;
-      }
-#pragma unroll
-      for (int it = 0; it < MAXI; ++it) {
-        const int q = tid + it * kGtThreads;
-        if (q < nq) {
-          const float4* sp = src + (size_t)(q >> 4) * kCkP + 4 * (q & (kGtQ - 1));
-          v[it][0] = __ldg(sp); v[it][1] = __ldg(sp + 1); v[it][2] = __ldg(sp + 2); v[it][3] = __ldg(sp + 3);
-          if (unit) {
-            const bool is_ze = (q >> 4) >= tg.act_groups;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[it][i] = scale_row(v[it][i], wq[i], is_ze);
-          }
-        }
-      }
-      // the tensor core must be done with the tile of the previous item before it is overwritten (the loads above are
-      // in flight meanwhile)
-      if (pending) { tc::mbar_wait(&bar_mma, ph); ph ^= 1u; pending = false; tc::fence_after_sync(); }
-      // The tensor core does not round its FP32 accumulation to nearest: the error of a sum kept in tensor memory grows
-      // linearly with the number of MMAs that went into it (measured: 1.1e-5 relative after 25 items against 1.3e-6
-      // after one).  Every flush_items items the accumulators are therefore added to the CTA's partial (round-to-nearest
-      // FP32 adds, L2 resident) and started over -- here, where the pipeline has to wait for the tensor core anyway.
-      if (since_flush >= flush_items) { flush(); first = true; since_flush = 0; }
-      pt_.mark(0);
-#pragma unroll
-      for (int it = 0; it < MAXI; ++it) {
-        const int q = tid + it * kGtThreads;
-        if (q < nq) {
-          const int gi = q >> 4, j = q & (kGtQ - 1);
-          const float4 c0 = make_float4(v[it][0].x, v[it][1].x, v[it][2].x, v[it][3].x), c1 = make_float4(v[it][0].y, v[it][1].y, v[it][2].y, v[it][3].y);
-          const float4 c2 = make_float4(v[it][0].z, v[it][1].z, v[it][2].z, v[it][3].z), c3 = make_float4(v[it][0].w, v[it][1].w, v[it][2].w, v[it][3].w);
-          quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
-          quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
-        }
-      }
-      for (int q = tid + MAXI * kGtThreads; q < nq; q += kGtThreads) {                  // (wider inputs than the C2 shape)
-        const int gi = q >> 4, j = q & (kGtQ - 1);
-        const float4* sp = src + (size_t)gi * kCkP + 4 * j;
-        float4 v0 = __ldg(sp), v1 = __ldg(sp + 1), v2 = __ldg(sp + 2), v3 = __ldg(sp + 3);
-        if (unit) {
-          const bool is_ze = gi >= tg.act_groups;
-          v0 = scale_row(v0, wq[0], is_ze); v1 = scale_row(v1, wq[1], is_ze); v2 = scale_row(v2, wq[2], is_ze); v3 = scale_row(v3, wq[3], is_ze);
-        }
-        const float4 c0 = make_float4(v0.x, v1.x, v2.x, v3.x), c1 = make_float4(v0.y, v1.y, v2.y, v3.y);
-        const float4 c2 = make_float4(v0.z, v1.z, v2.z, v3.z), c3 = make_float4(v0.w, v1.w, v2.w, v3.w);
-        quad(tH, 4 * gi, j) = c0; quad(tH, 4 * gi + 1, j) = c1; quad(tH, 4 * gi + 2, j) = c2; quad(tH, 4 * gi + 3, j) = c3;
-        quad(tL, 4 * gi, j) = lo4(c0); quad(tL, 4 * gi + 1, j) = lo4(c1); quad(tL, 4 * gi + 2, j) = lo4(c2); quad(tL, 4 * gi + 3, j) = lo4(c3);
-      }
-    }
-    // the zeta part of the weight gradient does not need the hidden cotangents: its MMAs run beside them
     tc::fence_proxy_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    if (tid == 0) { tc::fence_after_sync(); issue(0, tg.nE, first); }
-    if (item + (int)gridDim.x < n_items) {                    // next item -> L2 while the hidden cotangents are formed
-      const int nitem = item + gridDim.x, nts = nitem / 2, nhalf = nitem - nts * 2;
-      for (int q = tid; q < src_groups * 8; q += kGtThreads) {                           // 8 lines of 128 B per column group
-        const char* np_ = reinterpret_cast<const char*>(ck + (size_t)nts * prm.ckpt_c4 * kCkP + nhalf * kGtS + (size_t)(q >> 3) * kCkP) + (q & 7) * 128;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
-      }
-    }
-    pt_.mark(1);
-    // ---- (2) hidden cotangents for 4 samples x 4 hidden columns per thread:
-    //      dh[s][c] = sum_n zeta[s][n] W2[c][n]   (+ sum_n delta_2[s][n] W1[c][n] for the h1 columns)
-    float acc[4][4];                      // [hidden column][sample]
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
-    auto accumulate = [&](const float* w, int nng, int row0, int nk4) {     // cotangent rows row0 + 4 k4 + e, weights W[hc0 + c][4 k4 + e]
-      for (int k4 = hk; k4 < nk4; k4 += 2) {
-        float4 z[4], wv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) z[e] = quad(tH, row0 + 4 * k4 + e, hj);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc[c][0] = fmaf(z[e].x, we[e], acc[c][0]); acc[c][1] = fmaf(z[e].y, we[e], acc[c][1]);
-            acc[c][2] = fmaf(z[e].z, we[e], acc[c][2]); acc[c][3] = fmaf(z[e].w, we[e], acc[c][3]);
-          }
-        }
-      }
-    };
-    auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
-      float sel[2][4];                     // half hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free selects)
+    gt_named_bar(1, 320);
+  };
+
+  if (warp < 8) {
+    // =============================================================== hidden cotangents (256 threads)
+    // thread = 4 samples (quad hj) x 4 hidden columns hc0..hc0+3 of [h1 (32) | h2 (32)] x half hk of the reduction range
+    const int hj = lane & 7, hk = (lane >> 3) & 1, hg = 2 * warp + (lane >> 4);
+    const int hc0 = 4 * hg;
+    const bool is_h2 = hc0 >= 32;
+    const int seg_n = g.dims[is_h2 ? 2 : 1];
+    const int h_row = tg.s0 + hc0;                              // tile row of the hidden activation h[hc0]
+    for (int it = 0; it < n_stage_it; ++it) {
+      const int s = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      uint8_t* tH = smem + tg.o_hi[s];
+      uint8_t* tL = smem + tg.o_lo[s];
+      tc::mbar_wait(&bar_full[s], par);
+      if (unit) fixup(tH, it, tid);
+      float acc[4][4];                      // [hidden column][sample]
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 16);
-          if ((c >> 1) == hk) sel[c & 1][i] = v;
+        for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+      // cotangent rows row0 + 4 k4 + e (row0 % 8 == 0), weights W[hc0 + c][4 k4 + e]; k4 = hk, hk + 2, ... keeps the parity
+      // of k4, so the swizzled chunk of the thread's quad is a per-thread constant for each e
+      auto accumulate = [&](const float* w, int nng, int row0, int nk4) {
+        const uint8_t* zb = tH + (uint32_t)row0 * 128u;
+        uint32_t ch[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ch[e] = (uint32_t)(4 * hk + e) * 128u + (uint32_t)((hj ^ (4 * hk + e)) << 4);
+        for (int k4 = hk; k4 < nk4; k4 += 2) {
+          float4 z[4], wv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[e] = *reinterpret_cast<const float4*>(zb + (uint32_t)(k4 - hk) * 512u + ch[e]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[c][0] = fmaf(z[e].x, we[e], acc[c][0]); acc[c][1] = fmaf(z[e].y, we[e], acc[c][1]);
+              acc[c][2] = fmaf(z[e].z, we[e], acc[c][2]); acc[c][3] = fmaf(z[e].w, we[e], acc[c][3]);
+            }
+          }
         }
+      };
+      auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
+        float sel[2][4];                     // half hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free selects)
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * hk + cc;
-        const float4 h = quad(tH, h_row + c, hj);
-        const float hv[4] = {h.x, h.y, h.z, h.w};
-        const bool live = (hc0 & 31) + c < seg_n;
-        float v[4];
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = live ? sel[cc][i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
-        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-        quad(tH, row_dst + (hc0 & 31) + c, hj) = o;
-        quad(tL, row_dst + (hc0 & 31) + c, hj) = lo4(o);
+          for (int i = 0; i < 4; ++i) {
+            const float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 8);
+            if ((c >> 1) == hk) sel[c & 1][i] = v;
+          }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * hk + cc;
+          const float4 h = *reinterpret_cast<const float4*>(tH + gt_swz(h_row + c, hj));
+          const float hv[4] = {h.x, h.y, h.z, h.w};
+          const bool live = (hc0 & 31) + c < seg_n;
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = live ? sel[cc][i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+          const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          const uint32_t off = gt_swz(row_dst + (hc0 & 31) + c, hj);
+          *reinterpret_cast<float4*>(tH + off) = o;
+          *reinterpret_cast<float4*>(tL + off) = lo4(o);
+        }
+      };
+      if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, tg.r_ze, g.layer[2].nng);
+      if (is_h2) finish(tg.r_d2);
+      gt_named_bar(2, kGtWorkers);
+      if (!is_h2) {
+        accumulate(sW + tg.o_w1, tg.w1_nng, tg.r_d2, g.layer[1].nng);
+        finish(tg.r_d1);
       }
-    };
-    if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, 4 * tg.g_ze, g.layer[2].nng);
-    pt_.mark(4);
-    if (is_h2) finish(4 * tg.g_d2);
-    __syncthreads();
-    pt_.mark(5);
-    if (!is_h2) {
-      accumulate(sW + tg.o_w1, tg.w1_nng, 4 * tg.g_d2, g.layer[1].nng);
-      finish(4 * tg.g_d1);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bar_dl[s]);
     }
-    pt_.mark(6);
-    // ---- (3) weight gradient: D[m tile][act col][cot col] += sum_samples, three passes, one thread issues
-    tc::fence_proxy_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    pt_.mark(2);
-    if (tid == 0) {
+  } else {
+    // =============================================================== utility warps 8..11
+    const int qtr = warp & 3;                                  // tensor-memory lane quarter of this warp (flush)
+    // raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
+    // reduce_grad_tc_kernel sums the partials in fp64 and scatters them to theta.  The tensor core does not round its
+    // FP32 accumulation to nearest: the error of a sum kept in tensor memory grows linearly with the number of MMAs that
+    // went into it (measured: 1.1e-5 relative after 1 200 against 1.3e-6 after 48), so the accumulators are added to the
+    // partial (round-to-nearest FP32 adds, L2 resident, one writer per address) every flush_stages stages and started over.
+    auto flush = [&](uint32_t fpar) {
+      tc::mbar_wait(bar_acc_full, fpar);
       tc::fence_after_sync();
-      issue(tg.nE, 64, first);
-      tc::mma_commit(&bar_mma);
+      float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nB);
+      for (int mt = 0; mt < tg.n_mt; ++mt) {
+        if (128 * mt + 32 * qtr >= tg.act_rows) continue;      // lanes past the last activation column hold garbage rows
+        for (int c0 = 0; c0 < tg.nB; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tbase + (((uint32_t)(32 * qtr)) << 16) + (uint32_t)(mt * tg.nB + c0), v);
+          tc::wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(gp + (size_t)(mt * tg.nB + c0 + i) * 128 + 32 * qtr + lane, v[i]);   // RED
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_acc_empty);
+    };
+    uint32_t n_flush = 0;
+    for (int it = 0; it < n_stage_it; ++it) {
+      const int s = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      uint8_t* tH = smem + tg.o_hi[s];
+      uint8_t* tL = smem + tg.o_lo[s];
+      const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_stage_it - 1;
+      if (warp == 8) {
+        // ----------------------------------------------------------- TMA producer
+        if (lane == 0) {
+          tc::mbar_wait(&bar_empty[s], par ^ 1u);                  // first use of a stage passes immediately
+          tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.cols * 128u);
+          const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
+          tc::tma_load_3d(tH, &tmap, &bar_full[s], sub * kGtS, 0, ts);
+          tc::tma_load_3d(tH + (uint32_t)tg.box_rows * 128u, &tmap, &bar_full[s], sub * kGtS, tg.box_rows, ts);
+        }
+        __syncwarp();
+      } else if (warp == 9) {
+        // ----------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+          const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL);
+          const bool first = (it % flush_stages) == 0;             // accumulators start over after a flush
+          // D[m tile][:, dcol .. dcol + n) (+)= act' . cot rows [row0, row0 + n) over the 32 samples of the stage, three passes
+          auto issue = [&](int row0, int n, int dcol) {
+            const uint32_t id = tc::idesc_tf32(128, n);
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a = (pass == 0) ? sL : sH;
+              const uint32_t b = ((pass == 1) ? sL : sH) + (uint32_t)row0 * 128u;
+              for (int mt = 0; mt < tg.n_mt; ++mt)
+                for (int ks = 0; ks < kGtS / 8; ++ks) {
+                  const uint64_t ad = tc::smem_desc_sw128(a + (uint32_t)mt * 16384u + (uint32_t)ks * 32u);
+                  const uint64_t bd = tc::smem_desc_sw128(b + (uint32_t)ks * 32u);
+                  tc::mma_tf32_ss(tbase + (uint32_t)(mt * tg.nB + dcol), ad, bd, id, !first || pass > 0 || ks > 0);
+                }
+            }
+          };
+          if (first && n_flush > 0) { tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u); }
+          tc::mbar_wait(&bar_lo[s], par);
+          tc::mbar_wait(&bar_dl[s], par);
+          tc::fence_after_sync();
+          issue(tg.r_ze, tg.nB, 0);          // one group of N = nB: a K = 8 MMA does not get cheaper in proportion to N
+          tc::mma_commit(&bar_empty[s]);
+          if (flush_now) tc::mma_commit(bar_acc_full);
+        }
+        __syncwarp();
+      } else {
+        // ----------------------------------------------------------- lo tile of the loaded rows (64 threads)
+        tc::mbar_wait(&bar_full[s], par);
+        if (unit) fixup(tH, it, tid - 64);                         // threads 320..383 -> 256..319
+        const int t = tid - 320;
+        const float4* src = reinterpret_cast<const float4*>(tH);
+        float4* dst = reinterpret_cast<float4*>(tL);
+        const int nq = tg.cols * 8;
+        for (int q = t; q < nq; q += 64) dst[q] = lo4(src[q]);
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&bar_lo[s]);
+      }
+      if (flush_now) { flush(n_flush & 1u); ++n_flush; }
     }
-    first = false;
-    pending = true;
-    pt_.mark(3);
-    ++since_flush;
   }
-  if (pending) { tc::mbar_wait(&bar_mma, ph); tc::fence_after_sync(); }
 
-  if (!first) flush();
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
@@ -355,12 +358,12 @@ static __global__ void reduce_grad_tc_kernel(const NetGeom g, const GradTcGeom t
     if (mt >= tg.n_mt) continue;
     const int m = 128 * mt + lane;
     int col = -1;
-    if (m < 4 * tg.s04) { if (m < g.seg_len[0]) col = m; }
-    else if (m < 4 * tg.s04 + 32) { if (m - 4 * tg.s04 < g.seg_len[1]) col = g.seg_off[1] + (m - 4 * tg.s04); }
-    else if (m < 4 * tg.s04 + 64) { if (m - 4 * tg.s04 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - 4 * tg.s04 - 32); }
+    if (m < tg.s0) { if (m < g.seg_len[0]) col = m; }
+    else if (m < tg.s0 + 32) { if (m - tg.s0 < g.seg_len[1]) col = g.seg_off[1] + (m - tg.s0); }
+    else if (m < tg.s0 + 64) { if (m - tg.s0 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - tg.s0 - 32); }
     if (col < 0) continue;
     int l, n;
-    if (c < 4 * tg.ze_groups) { l = 2; n = c; }
+    if (c < tg.s0) { l = 2; n = c; }
     else if (c < tg.nE) continue;
     else if (c < tg.nE + 32) { l = 1; n = c - tg.nE; }
     else { l = 0; n = c - tg.nE - 32; }
@@ -373,6 +376,35 @@ static __global__ void reduce_grad_tc_kernel(const NetGeom g, const GradTcGeom t
     for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * per + q];
     out[idx] = (float)s;
   }
+}
+
+// ---- host: tensor map of a checkpoint buffer [n_ts][cols][128 paths] fp32, box = 32 paths x box_rows columns x 1,
+//      128-byte swizzle.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_tmap_encode tmap_encode_fn() {
+  static PFN_tmap_encode fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmap_encode>(p);
+  }
+  return fn;
+}
+// returns 0 on success
+inline int grad_tc_tensor_map(const GradTcGeom& tg, const float* ckpt, long long n_ts, CUtensorMap* out) {
+  PFN_tmap_encode enc = tmap_encode_fn();
+  if (!enc) return -1;
+  const cuuint64_t gdim[3] = {(cuuint64_t)kCkP, (cuuint64_t)tg.cols, (cuuint64_t)n_ts};
+  const cuuint64_t gstr[2] = {(cuuint64_t)kCkP * 4u, (cuuint64_t)kCkP * 4u * (cuuint64_t)tg.cols};
+  const cuuint32_t box[3] = {(cuuint32_t)kGtS, (cuuint32_t)tg.box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ckpt), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
 }
 
 }  // namespace pspde

@@ -49,10 +49,11 @@ struct RolloutParams {
   float* grad_partial;    // [gridDim.x][n_theta_total]
   float* x_ckpt;          // attached mode: [gridDim.x][N][P][d] state checkpoints of the current tile
   // checkpointed detached backward (rollout_tc_kernels.cuh / grad_kernels.cuh): the tensor-core forward kernel writes,
-  // for every (tile slot, step), the operand rows of the gradient accumulation, [a0 | h1 | h2 | zeta], as float4
-  // column groups with the 128 paths of the tile contiguous:  ckpt[((slot * N + n) * ckpt_c4 + c4) * 128 + path] (float4)
+  // for every (tile slot, step), the operand rows of the gradient accumulation, [a0 | h1 | h2 | zeta], COLUMN-major with
+  // the 128 paths of the tile contiguous:  ckpt[((slot * N + n) * ckpt_cols + col) * 128 + path]  -- one 512-byte row per
+  // column, the K-major operand form (K = sample) that the tensor-core gradient kernel loads by TMA without a transposition
   float* ckpt;
-  int ckpt_c4;            // column groups per (slot, step): 2 * (s0 / 4) + 16
+  int ckpt_cols;          // columns per (slot, step): 2 * s0 + 64
   int ckpt_s0;            // tensor-core width of the input segment (multiple of 8)
   int tile0;              // first 128-path tile of this wave (ckpt slot = tile - tile0)
   int ckpt_tiles;         // rollout: only tiles < ckpt_tiles (launch-local index) write their rows

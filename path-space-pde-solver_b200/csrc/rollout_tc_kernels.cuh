@@ -98,7 +98,8 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
 // CKPT = true (detached backward, first half): the same rollout, but instead of the per-path outputs it writes the
 // operand rows of the gradient accumulation for every step -- the network input a0 = [X_n | t_n | 1], the hidden
 // activations h1, h2 and the cotangent on Z, zeta = wY (sqrt(dt) xi + [!adaptive] Z dt) + wZ Z dt -- to the
-// per-wave checkpoint buffer (RolloutParams::ckpt) that grad_kernel consumes.  Rows with zero cotangents (padding,
+// per-wave checkpoint buffer (RolloutParams::ckpt, column-major: one row of 128 paths per column) that the gradient
+// kernels consume.  Rows with zero cotangents (padding,
 // trajectories dropped by the host because their D was non-finite) are written as zeros: inert in the gradient.
 // DIAG = true: additionally the u_L2 diagnostic of solver.py:491-494 from the per-step device tables (include/pspde.h).
 template <int NG, bool CKPT, bool DIAG>
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
     }
     const bool live = CKPT && (wy != 0.f || wz != 0.f);
     const bool keep = CKPT && tile < prm.ckpt_tiles;       // a forward pass may keep the rows of its first tiles only
-    float4* ck = CKPT ? reinterpret_cast<float4*>(prm.ckpt) + (size_t)tile * N * prm.ckpt_c4 * kTcP + p : nullptr;
+    // checkpoint rows of this path: column col of step n at ck[(n * ckpt_cols + col) * 128] (a warp stores 128 contiguous bytes)
+    float* ck = CKPT ? prm.ckpt + (size_t)tile * N * prm.ckpt_cols * kTcP + p : nullptr;
     const unsigned kglob = (unsigned)(prm.k_offset + k);
     // ---- tile init (solver.py:365-376) and the first a0
 #pragma unroll
@@ -262,11 +264,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         tc::tmem_st8(th, hi);
         tc::tmem_st8(th + tg.hp, lo);
         if (CKPT && keep) {                  // h = hi + lo exactly
-          float4* o = ck + (size_t)(n * prm.ckpt_c4 + (tg.s0 >> 2) + (tg.hp >> 2) * hl + (HC >> 2) * part) * kTcP;
+          float* o = ck + (size_t)(n * prm.ckpt_cols + tg.s0 + tg.hp * hl + HC * part) * kTcP;
 #pragma unroll
-          for (int u = 0; u < HC / 4; ++u)
-            o[u * kTcP] = live ? make_float4(hi[4 * u] + lo[4 * u], hi[4 * u + 1] + lo[4 * u + 1], hi[4 * u + 2] + lo[4 * u + 2],
-                                             hi[4 * u + 3] + lo[4 * u + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < HC; ++u) o[u * kTcP] = live ? hi[u] + lo[u] : 0.f;
         }
         tc::wait_st();
         tc::fence_before_sync();
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       // network time of the next step: (n + 1) dt, or the caller's grid (importance sampling, Solver.Z_n :360-362)
       const float t_next = (prm.t_index && !last) ? (float)__ldg(prm.t_index + n + 1) * prm.dt_net : (float)(n + 1) * dt;
       const float cm = adaptive ? -1.0f : 0.f;
+      // checkpoint rows of this step: first own column of a0 / of zeta (one warp-wide store = 128 contiguous bytes)
+      float* ckx = CKPT ? ck + (size_t)(n * prm.ckpt_cols + 4 * g_lo) * kTcP : nullptr;
+      const int zoff = (tg.s0 + 2 * tg.hp) * kTcP;
 #pragma unroll
       for (int c0 = 0; c0 < NG; c0 += 2) {          // 2 column groups (8 columns) per tensor-memory access
         const bool full = (c0 + 1 < NG) && (c0 + 1 < ng);     // warp-uniform
@@ -316,10 +319,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                   const float z = Z[4 * u + i], ee = E[gi][i];
                   ze[i] = (j0 + i < d) ? wy * (sq * ee + kA * z) + wz * (dt * z) : 0.f;
                 }
-                float4* o = ck + (size_t)(n * prm.ckpt_c4 + (g_lo + gi)) * kTcP;
-                o[0] = live ? make_float4(X[gi][0], X[gi][1], X[gi][2], X[gi][3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                o[(size_t)((tg.s0 >> 2) + 2 * (tg.hp >> 2)) * kTcP] =
-                    live ? make_float4(ze[0], ze[1], ze[2], ze[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // group gi of this thread sits 4 gi columns (an immediate offset) behind its first one
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  ckx[(4 * gi + i) * kTcP] = live ? X[gi][i] : 0.f;
+                  ckx[zoff + (4 * gi + i) * kTcP] = live ? ze[i] : 0.f;
+                }
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -469,8 +474,8 @@ inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid,
 inline cudaError_t tc_launch_fwd_ckpt(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
   return p.u_mode != 0 ? tc_launch_t<true, true>(p, tg, grid, stream) : tc_launch_t<true, false>(p, tg, grid, stream);
 }
-// column groups (float4) per (tile slot, step) of the checkpoint buffer: a0 (s0) | h1 (hp) | h2 (hp) | zeta (s0)
-inline int tc_ckpt_c4(const TcGeom& tg) { return 2 * (tg.s0 >> 2) + 2 * (tg.hp >> 2); }
+// columns per (tile slot, step) of the checkpoint buffer: a0 (s0) | h1 (hp) | h2 (hp) | zeta (s0)
+inline int tc_ckpt_cols(const TcGeom& tg) { return 2 * tg.s0 + 2 * tg.hp; }
 
 }  // namespace pspde
 #endif  // !PSPDE_EMULATE

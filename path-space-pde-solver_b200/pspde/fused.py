@@ -33,12 +33,17 @@ class Call:
         self.grad_enabled = True     # set by FusedRollout.apply: was autograd recording when the rollout was called
 
 
+ROWS_BUFFER_DEFAULT_GB = 8.0        # PSPDE_FWD_CKPT_MAX_GB: opt in to more (the buffer scales with K * N)
+ROWS_BUFFER_FREE_FRACTION = 0.25    # never more than a quarter of what is free on the device right now
+
+
 def rows_buffer_bytes(need, n_tiles, cap, free):
     """Bytes of the single-rollout step's row buffer: whole 128-path tiles, at most `need` (all tiles), `cap`
-    (PSPDE_FWD_CKPT_MAX_GB) and 60 % of the free device memory; 0 when that is less than a tenth of the batch (not worth
-    keeping a second code path busy)."""
+    (PSPDE_FWD_CKPT_MAX_GB, default 8 GB -- C2's 7.1 GB fit, C3 / C5 take the K-independent wave-checkpointed backward
+    unless the user opts in) and a quarter of the free device memory (another solver on the same GPU keeps its room);
+    0 when that is less than a tenth of the batch (not worth keeping a second code path busy)."""
     tile = need // n_tiles
-    take = int(min(need, cap, 0.6 * free)) // tile * tile
+    take = int(min(need, cap, ROWS_BUFFER_FREE_FRACTION * free)) // tile * tile
     return take if take >= max(tile, need // 10) else 0
 
 
@@ -75,10 +80,11 @@ class RolloutEngine:
         self.workspace = pt.empty(nbytes, dtype=pt.uint8, device=self.device)
         self.udiag, self.uL2 = None, None
         # Single-rollout step (pspde_rollout_fwd_ckpt): the training forward keeps the operand rows of its tiles for the
-        # gradient kernel.  All tiles need K_local * N * ~1 KB (C2: 7.1 GB, C5: 228 GB); the buffer takes what fits below
-        # PSPDE_FWD_CKPT_MAX_GB (default 96) and 60 % of the free device memory -- the tiles it does not hold go through
-        # the wave-checkpointed backward -- and is dropped for good by the first backward that carries a cotangent on
-        # Z_sum (those losses need the rollout with the cotangents in hand).
+        # gradient kernel.  All tiles need K_local * N * ~1 KB (C2: 7.1 GB, C5: 228 GB), i.e. a K x N x d tape, so this is
+        # bounded: the buffer takes what fits below PSPDE_FWD_CKPT_MAX_GB (default 8) and a quarter of the free device
+        # memory, and nothing when that is less than a tenth of the batch -- the tiles it does not hold go through the
+        # K-independent wave-checkpointed backward -- and it is dropped for good by the first backward that carries a
+        # cotangent on Z_sum (those losses need the rollout with the cotangents in hand).
         self.ckpt, self.ckpt_ok, self._ckpt_need = None, True, 0
         self.rows_serial = 0         # row-keeping forwards so far: a backward may use the rows only if they are its own forward's
 
@@ -91,7 +97,7 @@ class RolloutEngine:
             return None
         if self.ckpt is None or self._ckpt_need != need:
             self.ckpt = None
-            cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", "96")) * 2 ** 30
+            cap = float(os.environ.get("PSPDE_FWD_CKPT_MAX_GB", str(ROWS_BUFFER_DEFAULT_GB))) * 2 ** 30
             free, _ = pt.cuda.mem_get_info(self.device)
             take = rows_buffer_bytes(need, (self.K_local + 127) // 128, cap, free)
             if take == 0:

@@ -111,21 +111,25 @@ def test_flat_adam_equals_per_module_adam():
 
 
 def test_rows_buffer_sizing():
-    """Single-rollout step: the row buffer is whole tiles, bounded by the cap and by 60 % of the free memory, and not
-    taken at all below a tenth of the batch (pspde/fused.py::rows_buffer_bytes)."""
-    from pspde.fused import rows_buffer_bytes
+    """Single-rollout step: the row buffer is whole tiles, bounded by the cap (default 8 GB) and by a quarter of the free
+    memory, and not taken at all below a tenth of the batch (pspde/fused.py::rows_buffer_bytes)."""
+    from pspde.fused import ROWS_BUFFER_DEFAULT_GB, rows_buffer_bytes
     GB = 2 ** 30
-    tile = 100 * 68 * 2048                                   # C2: N = 100, C4 = 68 column groups
-    need = 512 * tile                                        # K = 2^16
-    assert rows_buffer_bytes(need, 512, 96 * GB, 170 * GB) == need                 # fits: every tile
+    cap = ROWS_BUFFER_DEFAULT_GB * GB
+    tile = 100 * 272 * 512                                   # C2: N = 100, 272 columns x 128 paths x 4 B
+    need = 512 * tile                                        # K = 2^16: 7.1 GB
+    assert rows_buffer_bytes(need, 512, cap, 170 * GB) == need                     # fits the default cap: every tile
     part = rows_buffer_bytes(need, 512, 2 * GB, 170 * GB)                          # capped: whole tiles below 2 GB
     assert 0 < part <= 2 * GB and part % tile == 0 and part + tile > 2 * GB
-    assert rows_buffer_bytes(need, 512, 96 * GB, 5 * GB) == int(0.6 * 5 * GB) // tile * tile
+    assert rows_buffer_bytes(need, 512, cap, 8 * GB) == int(0.25 * 8 * GB) // tile * tile
     assert rows_buffer_bytes(need, 512, 0.5 * GB, 170 * GB) == 0                   # < 10 % of the batch
     assert rows_buffer_bytes(need, 512, 0, 170 * GB) == 0                          # PSPDE_FWD_CKPT_MAX_GB=0
-    c5 = 8192 * 200 * 68 * 2048                                                    # C5: 228 GB do not fit 180 GB
-    kept = rows_buffer_bytes(c5, 8192, 96 * GB, 170 * GB)
-    assert kept % (200 * 68 * 2048) == 0 and 0.44 < kept / c5 < 0.46
+    c5 = 8192 * 200 * 272 * 512                                                    # C5: a 228 GB tape
+    assert rows_buffer_bytes(c5, 8192, cap, 170 * GB) == 0                         # default: no K x N x d tape at C5
+    c3 = 2048 * 200 * 176 * 512                                                    # C3: 36.9 GB -> the 8 GB the cap allows
+    assert 0.2 < rows_buffer_bytes(c3, 2048, cap, 170 * GB) / c3 < 0.25 and rows_buffer_bytes(c3, 2048, cap, 170 * GB) <= cap
+    kept = rows_buffer_bytes(c5, 8192, 96 * GB, 170 * GB)                          # opt-in: what a quarter of the memory holds
+    assert kept % (200 * 272 * 512) == 0 and 0.19 < kept / c5 < 0.21
 
 
 def test_shard_range_covers_everything():

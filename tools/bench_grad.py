@@ -10,9 +10,9 @@ d, hid, N, slots = 100, (30, 30), int(sys.argv[1]) if len(sys.argv) > 1 else 25,
 dims = [d + 1, hid[0], hid[1], d]
 cfg = L.make_cfg(slots * 128, d, N, 0.01, L.PROBLEM_OU, L.NET_DENSENET, dims, L.TIME_FIRST)
 n_theta = lib.pspde_theta_size(ctypes.byref(cfg))
-s0 = (d + 2 + 7) // 8 * 8; C4 = 2 * (s0 // 4) + 16
+s0 = (d + 2 + 7) // 8 * 8; C = 2 * s0 + 64
 gen = pt.Generator(device="cuda").manual_seed(0)
-ck = pt.randn(slots, N, C4, 128, 4, device="cuda", generator=gen).abs_() * 0.3
+ck = pt.randn(slots, N, C, 128, device="cuda", generator=gen).abs_() * 0.3
 theta = pt.randn(n_theta, device="cuda", generator=gen) * 0.1
 ws = pt.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) + 4 * n_theta * 160, dtype=pt.uint8, device="cuda")
 out = pt.empty(n_theta, device="cuda")

@@ -16,8 +16,8 @@ def case(kind, d, hid, N=3, n_slots=2, K=200):
     theta = (rng.standard_normal(n_theta) * 0.3).astype(np.float32)
     net = man.Net(kind, dims, theta.astype(np.float64))
     s0 = (d + 2 + 7) // 8 * 8
-    C4 = 2 * (s0 // 4) + 16
-    ck = np.zeros((n_slots, N, C4, 128, 4), np.float32)
+    C = 2 * s0 + 64                                   # checkpoint columns [a0 | h1 | h2 | zeta], column-major rows of 128 paths
+    ck = np.zeros((n_slots, N, C, 128), np.float32)
     grad = np.zeros(n_theta)
     for slot in range(n_slots):
         live = min(128, K - 128 * slot)
@@ -27,14 +27,14 @@ def case(kind, d, hid, N=3, n_slots=2, K=200):
             zeta = (rng.standard_normal((live, d)) * 0.1).astype(np.float32)
             _, tape = net.forward(np.concatenate([t, X], 1).astype(np.float64))
             grad += net.vjp(tape, zeta.astype(np.float64))
-            row = np.zeros((live, 4 * C4), np.float32)
+            row = np.zeros((live, C), np.float32)
             row[:, :d], row[:, d:d + 1], row[:, d + 1] = X, t, 1.0
             for l in (0, 1):
                 row[:, s0 + 32 * l:s0 + 32 * l + hid[l]] = tape[l][2].astype(np.float32)
                 if kind == "mlp_tanh":
                     row[:, s0 + 32 * l + hid[l]] = 1.0
             row[:, s0 + 64:s0 + 64 + d] = zeta
-            ck[slot, n, :, :live, :] = row.reshape(live, C4, 4).transpose(1, 0, 2)
+            ck[slot, n, :, :live] = row.T
     th = pt.tensor(theta).cuda(); ckd = pt.tensor(ck).cuda()
     ws = pt.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) + 64 * n_theta * 148, dtype=pt.uint8, device="cuda")
     res = {}
