@@ -128,8 +128,9 @@ int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float
  * depend on theta, so dLoss/dtheta = sum_{k,n} J_theta Z(t_n, X_{k,n})' zeta_{k,n} with
  *   zeta = wY_k (sqrt(dt) xi_{n+1} + [adaptive == 0] Z dt) + wZ_k Z dt,
  * wY = dLoss/dY_N, wZ = dLoss/dZsum (nullable = 0), both of length K_local.  The rollout is recomputed
- * from (x0, xi | Philox); nothing of size K x N x d is kept in HBM.  grad_theta (pspde_theta_size floats)
- * is overwritten.
+ * from (x0, xi | Philox); this entry point keeps nothing of size K x N x d in HBM (its checkpoint buffer holds one wave
+ * of tiles, independent of K; the opt-in K-proportional row buffer belongs to pspde_rollout_fwd_ckpt below).
+ * grad_theta (pspde_theta_size floats) is overwritten.
  * Two kernel families implement it: for the tensor-core shape class the trajectories of one wave of
  * tiles (<= one 128-path tile per SM) are regenerated by the tensor-core forward kernel, which checkpoints the
  * per-step operand rows in the workspace, and a gradient kernel streams them back (pspde_grad_from_ckpt); any other
@@ -139,11 +140,12 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* Second half of the checkpointed detached backward, exposed for tests: accumulates dLoss/dtheta from the operand
- * rows [a0 | h1 | h2 | zeta] of n_slots tiles of 128 paths x cfg->N steps.  Layout of ckpt (device, fp32): float4
- * column groups with the 128 paths of a tile contiguous,
- *     ckpt[(((slot * N + n) * C4 + c4) * 128 + path) * 4 + i],   C4 = 2 * (s0 / 4) + 16,
- * groups [0, s0/4) = a0 = [X_n | t_n | 1 | 0..], then 8 groups h1, 8 groups h2 (hidden widths padded to 32, with the
- * constant-1 column of MySequential), then s0/4 groups zeta (d used); s0 = the input segment padded to a multiple
+ * rows [a0 | h1 | h2 | zeta] of n_slots tiles of 128 paths x cfg->N steps.  Layout of ckpt (device, fp32): COLUMN-major
+ * with the 128 paths of a tile contiguous (one 512-byte row per column: the K-major operand form, K = sample, that the
+ * tensor-core gradient kernel loads by TMA),
+ *     ckpt[((slot * N + n) * C + col) * 128 + path],   C = 2 * s0 + 64,
+ * columns [0, s0) = a0 = [X_n | t_n | 1 | 0..], then 32 columns h1, 32 columns h2 (hidden widths padded to 32, with the
+ * constant-1 column of MySequential), then s0 columns zeta (d used); s0 = the input segment padded to a multiple
  * of 8.  pspde_rollout_bwd_detached fills this buffer with the tensor-core forward kernel, one wave of tiles (at
  * most one per SM) at a time, so its size is independent of K.  Networks: 2 hidden layers of width <= 32 (31). */
 int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* ckpt, int n_slots, int s0,
@@ -152,7 +154,7 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
 /* Single-rollout training step for detach_forward=True (solver.py:433-499 + :221 without recomputing the trajectories,
  * like the reference, whose autograd graph keeps every activation).  pspde_rollout_fwd_ckpt is pspde_rollout_fwd_diag
  * that additionally leaves the operand rows [a0 | h1 | h2 | zeta_unit] of its first ckpt_bytes / tile_bytes tiles of
- * 128 paths in `ckpt` (layout as above, slot = tile; zeta_unit = sqrt(dt) xi_{n+1}; tile_bytes = N * C4 * 2048);
+ * 128 paths in `ckpt` (layout as above, slot = tile; zeta_unit = sqrt(dt) xi_{n+1}; tile_bytes = N * C * 512);
  * pspde_grad_from_fwd_ckpt then forms
  *   dLoss/dtheta = sum_{k,n} J_theta Z' (wY_k zeta_unit)
  * with the tensor-core gradient kernel over those rows, and runs the wave-checkpointed backward of
@@ -161,8 +163,8 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
  * rollout + gradient.  Requirements (pspde_fwd_ckpt_bytes returns 0 otherwise and the caller uses
  * pspde_rollout_fwd_diag + pspde_rollout_bwd_detached): tensor-core shape class, cfg->adaptive != 0, no cotangent on
  * Z_sum (dLoss/dZsum == 0: log-variance, moment, variance, cross-entropy losses with the adaptive process).
- * pspde_fwd_ckpt_bytes = bytes for ALL ceil(K_local / 128) tiles (C2: 7.1 GB, C5: 228 GB -- the caller passes what it
- * affords, the same buffer and size to both calls).  ckpt == NULL in pspde_rollout_fwd_ckpt is the plain forward.
+ * pspde_fwd_ckpt_bytes = bytes for ALL ceil(K_local / 128) tiles: a K x N tape (C2: 7.1 GB, C5: 228 GB), so the caller
+ * bounds it (pspde.fused: 8 GB by default) and passes what it affords, the same buffer and size to both calls.  ckpt == NULL in pspde_rollout_fwd_ckpt is the plain forward.
  * Paths with wY == 0 contribute nothing (even if they diverged). */
 size_t pspde_fwd_ckpt_bytes(const pspde_cfg* cfg);
 int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
@@ -184,6 +186,14 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
                            const float* y0, const float* xi, float w, const float* wY, const float* wZ,
                            const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                            float* grad_theta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* pspde_rollout_attached with the u_L2 diagnostic of pspde_rollout_fwd_diag evaluated in its forward sweep (the reference
+ * logs it in every iteration, also for the attached relative-entropy setup, solver.py:491-494, :515).  diag nullable. */
+int pspde_rollout_attached_diag(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                                const float* y0, const float* xi, float w, const float* wY, const float* wZ,
+                                const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
+                                const pspde_udiag* diag, float* grad_theta, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* Importance-sampling evaluation -- replaces the rollout of do_importance_sampling_me (utilities.py:287-359,
  * called from solver.py:521-528): forward-only simulation of the controlled process u = -Z on a time grid that

@@ -181,6 +181,16 @@ static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, con
 }
 #endif
 
+// u_L2 diagnostic descriptor (include/pspde.h) -> kernel parameters
+static int set_udiag(const pspde_cfg* cfg, const pspde_udiag* diag, RolloutParams& p) {
+  if (diag->mode < 0 || diag->mode > 2 || !diag->table || !diag->uL2) return fail(-8, "bad u_L2 diagnostic descriptor");
+  if (diag->mode == 2 && (diag->nx1 < 1 || !(diag->dx > 0.f))) return fail(-8, "bad lookup-table geometry");
+  if (diag->mode == 2 && (cfg->problem_flags & PSPDE_FLAG_DENSE_AB)) return fail(-8, "lookup diagnostic needs a diagonal problem");
+  p.u_mode = diag->mode; p.u_tab = diag->table; p.u_nx1 = diag->nx1; p.u_d1 = diag->d1;
+  p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
+  return 0;
+}
+
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
@@ -271,11 +281,8 @@ int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float
   p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi;
   p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Zsum = Zsum;
   if (diag && diag->mode != 0) {
-    if (diag->mode < 0 || diag->mode > 2 || !diag->table || !diag->uL2) return fail(-8, "bad u_L2 diagnostic descriptor");
-    if (diag->mode == 2 && (diag->nx1 < 1 || !(diag->dx > 0.f))) return fail(-8, "bad lookup-table geometry");
-    if (diag->mode == 2 && (cfg->problem_flags & PSPDE_FLAG_DENSE_AB)) return fail(-8, "lookup diagnostic needs a diagonal problem");
-    p.u_mode = diag->mode; p.u_tab = diag->table; p.u_nx1 = diag->nx1; p.u_d1 = diag->d1;
-    p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
+    rc = set_udiag(cfg, diag, p);
+    if (rc) return rc;
   }
   p.stats_partial = reinterpret_cast<double*>(workspace);
   p.ckpt = reinterpret_cast<float*>(ckpt);
@@ -430,6 +437,15 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
                            const float* y0, const float* xi, float w, const float* wY, const float* wZ,
                            const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
                            float* grad_theta, void* workspace, size_t workspace_bytes, void* stream) {
+  return pspde_rollout_attached_diag(cfg, theta, prob, x0, y0, xi, w, wY, wZ, wG, X_N, Y_N, gX, Zsum, stats, nullptr,
+                                     grad_theta, workspace, workspace_bytes, stream);
+}
+
+int pspde_rollout_attached_diag(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
+                                const float* y0, const float* xi, float w, const float* wY, const float* wZ,
+                                const float* wG, float* X_N, float* Y_N, float* gX, float* Zsum, double* stats,
+                                const pspde_udiag* diag, float* grad_theta, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   Plan pl;
   int rc = make_plan(cfg, true, true, pl);
   if (rc) return rc;
@@ -444,6 +460,10 @@ int pspde_rollout_attached(const pspde_cfg* cfg, const float* theta, const float
   p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi; p.w_attached = w;
   p.wY = wY; p.wZ = wZ; p.wG = wG;
   p.X_N = X_N; p.Y_N = Y_N; p.gX = gX; p.Zsum = Zsum;
+  if (diag && diag->mode != 0) {
+    const int rd = set_udiag(cfg, diag, p);
+    if (rd) return rd;
+  }
   char* ws = reinterpret_cast<char*>(workspace);
   p.stats_partial = reinterpret_cast<double*>(ws);
   p.grad_partial = reinterpret_cast<float*>(ws + pl.stats_bytes);

@@ -15,14 +15,14 @@
 // (hi = trunc(x)); a second tile holds lo = rna_tf32(x - trunc(x)); three passes lo*hi + hi*lo + hi*hi into the FP32
 // accumulators in tensor memory (n_mt x nB columns), flushed to the CTA's partial every few stages (see below).
 //
-// Warp roles (384 threads, one CTA per SM, 2-stage ring of (hi, lo) tiles = 172 KB at the C2 shape):
-//   warps 0-7   hidden cotangents: delta_2 = (zeta W2[h2 rows]') act'(h2), delta_1 = (zeta W2[h1 rows]' + delta_2 W1[h1 rows]')
-//               act'(h1) in FP32 FMA (4 samples x 4 hidden columns per thread, operands read from the swizzled tile),
-//               appended to the tile as rows (hi and lo)
-//   warp  8     TMA producer (one lane): waits for a free stage, arms the mbarrier, issues the two box loads
-//   warp  9     MMA issuer (one lane): when the lo tile and the delta rows of a stage exist; tcgen05.commit frees the stage
-//   warps 10-11 lo tile of the loaded rows (element-wise, layout agnostic)
-//   warps 8-11  additionally flush the accumulators (one lane quarter of tensor memory each)
+// Warp roles (640 threads, one CTA per SM, 2-stage ring of (hi, lo) tiles = 172 KB at the C2 shape):
+//   warps 0-15  hidden cotangents: delta_2 = (zeta W2[h2 rows]') act'(h2), delta_1 = (zeta W2[h1 rows]' + delta_2 W1[h1 rows]')
+//               act'(h1) in FP32 FMA (warp = 4 hidden columns; lane = 4 samples x a quarter of the reduction range, operands
+//               read from the swizzled tile), appended to the tile as rows (hi and lo)
+//   warp  16    TMA producer (one lane): waits for a free stage, arms the mbarrier, issues the two box loads
+//   warp  17    MMA issuer (one lane): when the lo tile and the delta rows of a stage exist; tcgen05.commit frees the stage
+//   warps 18-19 lo tile of the loaded rows (element-wise, layout agnostic)
+//   warps 16-19 additionally flush the accumulators (one lane quarter of tensor memory each)
 #pragma once
 #if !defined(PSPDE_EMULATE)
 #include <cuda.h>
@@ -33,8 +33,9 @@ namespace pspde {
 
 constexpr int kGtS = 32;                 // samples per stage = one 128-byte swizzle row of K = 4 MMA k steps
 constexpr int kGtStages = 2;
-constexpr int kGtWorkers = 256;          // hidden-cotangent threads (warps 0-7)
-constexpr int kGtThreads = 384;
+constexpr int kGtWorkers = 512;          // hidden-cotangent threads (warps 0-15)
+constexpr int kGtThreads = 640;
+constexpr int kGtUtil = kGtWorkers / 32; // first utility warp: TMA producer; +1 MMA issuer; +2, +3 lo tile
 constexpr int kGtSub = kCkP / kGtS;      // stages per (tile, step)
 constexpr int kGtFlushStages = 16;       // accumulator flush period: 16 stages x 12 MMAs per accumulator
 
@@ -91,6 +92,7 @@ __device__ __forceinline__ float4 lo4(const float4& v) { return make_float4(lo1(
 // byte offset of (row r, sample quad j) in a swizzled tile: 16-byte chunk index xor-ed with the row inside the 8-row atom
 __device__ __forceinline__ uint32_t gt_swz(int r, int j) { return (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4); }
 
+__device__ __forceinline__ float gt_sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void gt_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // n_ts = number of (tile, step) pairs in the checkpoint; CTA b streams pairs b, b + grid, ... (4 stages each).
@@ -122,7 +124,7 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
     tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
     tc::mbar_fence_init();
   }
-  if (tid == 8 * 32) tc::tma_prefetch_desc(&tmap);
+  if (tid == kGtUtil * 32) tc::tma_prefetch_desc(&tmap);
   for (uint32_t q = tid; q < (uint32_t)kGtStages * 2u * tg.tile_bytes / 16u; q += kGtThreads)
     reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 1; l <= 2; ++l) {            // compact k4-blocked weights: row = hidden column slot (32 per segment)
@@ -158,14 +160,15 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
     for (int i = 0; i < 4; ++i) w[i] = (k0 + i < prm.K_local) ? __ldg(prm.wY + k0 + i) : 0.f;
   };
   // forward-written checkpoint: scale the zeta rows by the per-path cotangent and drop (zero) every row of a path whose
-  // cotangent is zero, so that a diverged trajectory the loss has discarded cannot poison the sums.  Threads 0..319
-  // (delta + lo warps); thread t owns chunk position t & 7 of rows (t >> 3) + 40 i: its sample quad is fixed.
+  // cotangent is zero, so that a diverged trajectory the loss has discarded cannot poison the sums.  Threads 0..575
+  // (delta + lo warps); thread t owns chunk position t & 7 of rows (t >> 3) + 72 i: its sample quad is fixed.
+  constexpr int kFix = kGtWorkers + 64;
   auto fixup = [&](uint8_t* tH, int it, int t) {
     const int pos = t & 7, r0 = t >> 3;
     const int j = pos ^ (r0 & 7);
     float w[4];
     unit_w(it, j, w);
-    for (int r = r0; r < tg.cols; r += 40) {
+    for (int r = r0; r < tg.cols; r += kFix / 8) {
       float4* p = reinterpret_cast<float4*>(tH + (uint32_t)r * 128u + (uint32_t)(pos << 4));
       float4 v = *p;
       const bool ze = r >= tg.r_ze;
@@ -174,42 +177,48 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
       *p = v;
     }
     tc::fence_proxy_async();
-    gt_named_bar(1, 320);
+    gt_named_bar(1, kFix);
   };
 
-  if (warp < 8) {
-    // =============================================================== hidden cotangents (256 threads)
-    // thread = 4 samples (quad hj) x 4 hidden columns hc0..hc0+3 of [h1 (32) | h2 (32)] x half hk of the reduction range
-    const int hj = lane & 7, hk = (lane >> 3) & 1, hg = 2 * warp + (lane >> 4);
-    const int hc0 = 4 * hg;
+  if (warp < kGtUtil) {
+    // =============================================================== hidden cotangents (512 threads)
+    // warp = 4 hidden columns hc0..hc0+3 of [h1 (32) | h2 (32)]; lane = 4 samples (quad hj) x quarter hk of the reduction range
+    const int hj = lane & 7, hk = lane >> 3;
+    const int hc0 = 4 * warp;
     const bool is_h2 = hc0 >= 32;
     const int seg_n = g.dims[is_h2 ? 2 : 1];
     const int h_row = tg.s0 + hc0;                              // tile row of the hidden activation h[hc0]
+    // k4 = hk, hk + 4, ...: the cotangent rows row0 + 4 k4 + e of this lane keep (row & 7) = 4 (hk & 1) + e (row0 % 8 == 0),
+    // so the swizzled chunk of the lane's sample quad is a per-lane constant for each e
+    uint32_t ch[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ch[e] = (uint32_t)(4 * hk + e) * 128u + (uint32_t)((hj ^ (4 * (hk & 1) + e)) << 4);
+    PhaseTimer pt_;      // debug (CTA 0, thread 0): [0] wait for the TMA, [1] zeta . W2' (+ delta_2), [2] barrier + delta_2 . W1' + delta_1, [3] fence + arrive
+    pt_.start(prm.prof, tid);
     for (int it = 0; it < n_stage_it; ++it) {
       const int s = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       uint8_t* tH = smem + tg.o_hi[s];
       uint8_t* tL = smem + tg.o_lo[s];
       tc::mbar_wait(&bar_full[s], par);
+      pt_.mark(0);
       if (unit) fixup(tH, it, tid);
       float acc[4][4];                      // [hidden column][sample]
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
-      // cotangent rows row0 + 4 k4 + e (row0 % 8 == 0), weights W[hc0 + c][4 k4 + e]; k4 = hk, hk + 2, ... keeps the parity
-      // of k4, so the swizzled chunk of the thread's quad is a per-thread constant for each e
+      // cotangent rows row0 + 4 k4 + e, weights W[hc0 + c][4 k4 + e]
       auto accumulate = [&](const float* w, int nng, int row0, int nk4) {
         const uint8_t* zb = tH + (uint32_t)row0 * 128u;
-        uint32_t ch[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) ch[e] = (uint32_t)(4 * hk + e) * 128u + (uint32_t)((hj ^ (4 * hk + e)) << 4);
-        for (int k4 = hk; k4 < nk4; k4 += 2) {
+        const float* wb = w + (size_t)warp * nng * 16;
+#pragma unroll 2
+        for (int k4 = hk; k4 < nk4; k4 += 4) {
           float4 z[4], wv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) z[e] = *reinterpret_cast<const float4*>(zb + (uint32_t)(k4 - hk) * 512u + ch[e]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(w + ((hc0 >> 2) * nng + k4) * 16 + c * 4);
+          for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const float4*>(wb + k4 * 16 + c * 4);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float we[4] = {wv[c].x, wv[c].y, wv[c].z, wv[c].w};
@@ -221,42 +230,45 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
           }
         }
       };
-      auto finish = [&](int row_dst) {       // combine the halves, act', zero the pads, raw -> tH, lo -> tL
-        float sel[2][4];                     // half hk of the reduction lanes finishes columns 2 hk, 2 hk + 1 (branch-free selects)
+      auto finish = [&](int row_dst) {       // combine the four quarters; lane hk finishes column hk: act', zero the pads, raw -> tH, lo -> tL
+        float sel[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float v = acc[c][i] + __shfl_xor_sync(0xffffffffu, acc[c][i], 8);
-            if ((c >> 1) == hk) sel[c & 1][i] = v;
+            float v = acc[c][i];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (c == hk) sel[i] = v;
           }
+        const int c = hk;
+        const float4 h = *reinterpret_cast<const float4*>(tH + gt_swz(h_row + c, hj));
+        const float hv[4] = {h.x, h.y, h.z, h.w};
+        const bool live = (hc0 & 31) + c < seg_n;
+        float v[4];
+        // act': relu(.)^2 -> 2 relu(pre) = 2 sqrt(h) (sqrt.approx: 1 ulp, far inside the 1e-5 parity bar); tanh -> 1 - h^2
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = 2 * hk + cc;
-          const float4 h = *reinterpret_cast<const float4*>(tH + gt_swz(h_row + c, hj));
-          const float hv[4] = {h.x, h.y, h.z, h.w};
-          const bool live = (hc0 & 31) + c < seg_n;
-          float v[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = live ? sel[cc][i] * (tg.dense ? 2.0f * sqrtf(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
-          const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-          const uint32_t off = gt_swz(row_dst + (hc0 & 31) + c, hj);
-          *reinterpret_cast<float4*>(tH + off) = o;
-          *reinterpret_cast<float4*>(tL + off) = lo4(o);
-        }
+        for (int i = 0; i < 4; ++i) v[i] = live ? sel[i] * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        const uint32_t off = gt_swz(row_dst + (hc0 & 31) + c, hj);
+        *reinterpret_cast<float4*>(tH + off) = o;
+        *reinterpret_cast<float4*>(tL + off) = lo4(o);
       };
       if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, tg.r_ze, g.layer[2].nng);
       if (is_h2) finish(tg.r_d2);
+      pt_.mark(1);
       gt_named_bar(2, kGtWorkers);
       if (!is_h2) {
         accumulate(sW + tg.o_w1, tg.w1_nng, tg.r_d2, g.layer[1].nng);
         finish(tg.r_d1);
       }
+      pt_.mark(2);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_dl[s]);
+      pt_.mark(3);
     }
   } else {
-    // =============================================================== utility warps 8..11
+    // =============================================================== utility warps 16..19
     const int qtr = warp & 3;                                  // tensor-memory lane quarter of this warp (flush)
     // raw accumulators -> this CTA's partial, [m tile][cotangent column][lane = checkpoint column] (coalesced);
     // reduce_grad_tc_kernel sums the partials in fp64 and scatters them to theta.  The tensor core does not round its
@@ -281,6 +293,11 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(bar_acc_empty);
     };
+    // debug (CTA 0): MMA lane [4] wait accumulators free + lo tile, [5] wait delta rows, [6] issue + commit, [7] flush;
+    // lo thread [8] wait for the TMA, [9] lo pass, [10] flush; TMA lane [11] wait for a free stage, [12] issue, [13] flush
+    PhaseTimer pt_;
+    pt_.start(prm.prof, (lane == 0 && warp <= kGtUtil + 2) ? 0 : 1);
+    const int pb = warp == kGtUtil + 1 ? 4 : warp == kGtUtil + 2 ? 8 : 11;
     uint32_t n_flush = 0;
     for (int it = 0; it < n_stage_it; ++it) {
       const int s = it & 1;
@@ -288,17 +305,19 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
       uint8_t* tH = smem + tg.o_hi[s];
       uint8_t* tL = smem + tg.o_lo[s];
       const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_stage_it - 1;
-      if (warp == 8) {
+      if (warp == kGtUtil) {
         // ----------------------------------------------------------- TMA producer
         if (lane == 0) {
           tc::mbar_wait(&bar_empty[s], par ^ 1u);                  // first use of a stage passes immediately
+          pt_.mark(11);
           tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.cols * 128u);
           const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
           tc::tma_load_3d(tH, &tmap, &bar_full[s], sub * kGtS, 0, ts);
           tc::tma_load_3d(tH + (uint32_t)tg.box_rows * 128u, &tmap, &bar_full[s], sub * kGtS, tg.box_rows, ts);
+          pt_.mark(12);
         }
         __syncwarp();
-      } else if (warp == 9) {
+      } else if (warp == kGtUtil + 1) {
         // ----------------------------------------------------------- MMA issuer
         if (lane == 0) {
           const uint32_t sH = tc::smem_u32(tH), sL = tc::smem_u32(tL);
@@ -319,26 +338,39 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
           };
           if (first && n_flush > 0) { tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u); }
           tc::mbar_wait(&bar_lo[s], par);
+          pt_.mark(4);
           tc::mbar_wait(&bar_dl[s], par);
+          pt_.mark(5);
           tc::fence_after_sync();
           issue(tg.r_ze, tg.nB, 0);          // one group of N = nB: a K = 8 MMA does not get cheaper in proportion to N
           tc::mma_commit(&bar_empty[s]);
           if (flush_now) tc::mma_commit(bar_acc_full);
+          pt_.mark(6);
         }
         __syncwarp();
       } else {
         // ----------------------------------------------------------- lo tile of the loaded rows (64 threads)
         tc::mbar_wait(&bar_full[s], par);
-        if (unit) fixup(tH, it, tid - 64);                         // threads 320..383 -> 256..319
-        const int t = tid - 320;
+        pt_.mark(8);
+        if (unit) fixup(tH, it, tid - 64);                         // threads 576..639 -> 512..575
+        const int t = tid - (kGtUtil + 2) * 32;
         const float4* src = reinterpret_cast<const float4*>(tH);
         float4* dst = reinterpret_cast<float4*>(tL);
         const int nq = tg.cols * 8;
-        for (int q = t; q < nq; q += 64) dst[q] = lo4(src[q]);
+        int q = t;
+        for (; q + 7 * 64 < nq; q += 8 * 64) {                     // 8 loads in flight per thread: the shared-memory latency
+          float4 v[8];                                             // under the tensor core's operand traffic is > 100 cycles
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = src[q + 64 * u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dst[q + 64 * u] = lo4(v[u]);
+        }
+        for (; q < nq; q += 64) dst[q] = lo4(src[q]);
         tc::fence_proxy_async();
         tc::mbar_arrive(&bar_lo[s]);
+        pt_.mark(9);
       }
-      if (flush_now) { flush(n_flush & 1u); ++n_flush; }
+      if (flush_now) { flush(n_flush & 1u); ++n_flush; pt_.mark(pb + (warp == kGtUtil + 1 ? 3 : 2)); }
     }
   }
 

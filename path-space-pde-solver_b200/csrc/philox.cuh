@@ -22,16 +22,27 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
 // u = ((r >> 8) + 0.5) * 2^-24 lies strictly inside (0, 1): no log(0), |z| <= 5.9
 __device__ __forceinline__ float u01(unsigned r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-8f; }
 
+// sqrt.approx (one MUFU, ~1 ulp) -- the argument comes from __logf (2 ulp) anyway; sqrtf's Newton step costs ~10 instructions
+__device__ __forceinline__ float sqrt_fast(float x) {
+#if defined(PSPDE_EMULATE)
+  return sqrtf(x);
+#else
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
 __device__ __forceinline__ float4 philox_normal4(unsigned k_global, unsigned n, unsigned jb, unsigned offset,
                                                  unsigned long long seed) {
   unsigned r[4];
   philox4x32_10(k_global, n, jb, offset, (unsigned)(seed & 0xffffffffull), (unsigned)(seed >> 32), r);
   float4 z;
   float s, c;
-  const float rad0 = sqrtf(-2.0f * __logf(u01(r[0])));
+  const float rad0 = sqrt_fast(-2.0f * __logf(u01(r[0])));
   __sincosf(6.283185307179586f * u01(r[1]), &s, &c);
   z.x = rad0 * c; z.y = rad0 * s;
-  const float rad1 = sqrtf(-2.0f * __logf(u01(r[2])));
+  const float rad1 = sqrt_fast(-2.0f * __logf(u01(r[2])));
   __sincosf(6.283185307179586f * u01(r[3]), &s, &c);
   z.z = rad1 * c; z.w = rad1 * s;
   return z;

@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
     tile_init_state(prm, sAct, tile, P, false, tid, T);
     for (int p = tid; p < P; p += T) {
       const int k = tile * P + p;
-      sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f; sZs[p] = 0.f; sG[p] = 0.f; sY[6 * P + p] = 0.f;
+      sY[p] = prm.y0 ? __ldg(prm.y0) : 0.f; sZs[p] = 0.f; sG[p] = 0.f; sY[6 * P + p] = 0.f; sY[7 * P + p] = 0.f;
       const bool in = k < prm.K_local;
       if (per_path) {
         swY[p] = (in && prm.wY) ? __ldg(prm.wY + k) : 0.f;
@@ -889,6 +889,7 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
           if (prm.Y_N) prm.Y_N[k] = sY[tid];
+          if (prm.uL2) prm.uL2[k] = sY[7 * P + tid];          // u_L2 diagnostic of the forward sweep (solver.py:491-494)
           const double v = (double)ZS + (double)G, D = (double)sY[tid] - (double)G;
           if (isfinite(v) && isfinite(D)) s2 = v;
           else { s3 = 1.0; swY[tid] = 0.f; swZ[tid] = 0.f; swG[tid] = 0.f; }   // dropped from the batch and counted

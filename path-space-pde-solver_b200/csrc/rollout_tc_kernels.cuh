@@ -4,7 +4,7 @@
 //   DenseNet (function_space.py:116-140) or MySequential (:177-195) with two hidden layers of at most 32 (31) units,
 //   'inner' time input, diagonal problem functors (LLGC / LQGC with off_diag = 0, DoubleWell_multidim),
 // which covers the BASELINE configs C1-inner, C2, C3 (detached) and C5.  A tile is 128 trajectories = the 128 lanes of tensor
-// memory; every trajectory is owned by four threads (one per quarter of the state columns) for the whole rollout:
+// memory; every trajectory is owned by three threads (one per third of the state columns) for the whole rollout:
 //
 //   tensor memory (512 columns x 128 lanes, all allocated):
 //     A operands, hi and lo TF32 halves: a0 = [X | t | 1 | 0] (s0 columns), h1 (32), h2 (32)       2 (s0 + 64) columns
@@ -28,11 +28,15 @@
 namespace pspde {
 
 constexpr int kTcP = 128;        // trajectories per tile = tensor-memory lanes
-constexpr int kTcTPP = 4;        // threads per trajectory (column parts); 16 warps per CTA
+// Threads per trajectory (column parts).  THREE, i.e. 12 warps per CTA: one CTA per SM (213 KB of weights), so the register
+// file allows 65536 / 384 = 170 registers per thread -- room for the state, the step's Brownian increments (4 NG registers
+// each) and the transients of the update without spills.  With four threads per trajectory (128 registers) the kernel
+// spilled ~100 values per thread, and local memory is an L2 round trip here (L1 is what shared memory leaves: ~14 KB).
+constexpr int kTcTPP = 3;
 constexpr int kTcThreads = kTcP * kTcTPP;
-constexpr int kTcIssuer = 15 * 32; // the thread that issues the MMAs: a lane of the last warp, whose column part is one of the
-                                   // short ones (the state columns do not divide evenly), so the issue work does not delay the slowest warp
-constexpr int kTcMaxG = 8;       // float4 column groups per thread; the kernel is instantiated for NG <= this
+constexpr int kTcIssuer = (kTcThreads / 32 - 1) * 32; // the thread that issues the MMAs: a lane of the last warp, whose column part is
+                                   // the short one (the state columns do not divide evenly), so the issue work does not delay the slowest warp
+constexpr int kTcMaxG = 12;      // float4 column groups per thread; the kernel is instantiated for NG <= this
 
 struct TcGeom {
   int s0, hp, np3, n0, n1, n2, ng, dense;   // ng = column groups per thread (max over the parts)
@@ -92,6 +96,9 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
   }
 }
 
+// streaming store of one checkpoint element (written once, read once by another kernel)
+__device__ __forceinline__ void st_ckpt(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
 // One trajectory = one tensor-memory lane, owned by kTcTPP threads (one per part of the state columns).  Thread kTcIssuer
 // additionally issues the MMAs: after the last arrival on an "operands ready" barrier it launches the group and
 // commits it to the matching "group done" barrier; everybody (the issuer included) then waits for that one.
@@ -102,7 +109,9 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
 // kernels consume.  Rows with zero cotangents (padding,
 // trajectories dropped by the host because their D was non-finite) are written as zeros: inert in the gradient.
 // DIAG = true: additionally the u_L2 diagnostic of solver.py:491-494 from the per-step device tables (include/pspde.h).
-template <int NG, bool CKPT, bool DIAG>
+// PHILOX is a template parameter on purpose: with the noise source a run-time flag the 4 NG 64-bit addresses of the injected
+// increments are step-loop invariants, get hoisted, and push the Philox instantiation over the register limit.
+template <int NG, bool CKPT, bool DIAG, bool PHILOX>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const RolloutParams prm, const TcGeom tg) {
   extern __shared__ float4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
@@ -163,10 +172,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   const int G = tg.s0 / 4, gbase = G / kTcTPP, grem = G % kTcTPP;
   const int g_lo = part * gbase + (part < grem ? part : grem);
   const int ng = gbase + (part < grem ? 1 : 0);
-  constexpr int HC = 32 / kTcTPP;          // hidden columns per thread in the activation epilogues
+  // hidden columns per thread in the activation epilogues: the 8 column quads of a hidden segment go 3 / 3 / 2 to the parts
+  constexpr int HQ = (8 + kTcTPP - 1) / kTcTPP, HC = 4 * HQ;
+  const int hq0 = HQ * part, hnq = (8 - hq0) < HQ ? (8 - hq0) : HQ;
   const float *a_d = sProb, *b_d = sProb + tg.s0, *p_d = sProb + 2 * tg.s0, *r_d = sProb + 3 * tg.s0,
               *al = sProb + 4 * tg.s0, *kap = sProb + 5 * tg.s0, *eta = sProb + 6 * tg.s0;
-  const bool adaptive = prm.adaptive != 0, philox = prm.noise_mode == NOISE_PHILOX, dw = prm.problem_id == PROBLEM_DW;
+  const bool adaptive = prm.adaptive != 0, dw = prm.problem_id == PROBLEM_DW;
   uint32_t ph = 0;
   float X[NG][4];
 
@@ -218,12 +229,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       float E[NG][4];
       constexpr int NA = (NG + 1) / 2, NB = NA + (NG - NA + 1) / 2;
       auto draw = [&](int g0, int g1) {
-        if (philox) {
+        if (PHILOX) {
+          // The chains are independent, and the scheduler would interleave all of them (about 14 live registers each).  Two
+          // at a time hide the multiply latency just as well: `dep` (always 0, but only at run time -- a normal is never that
+          // NaN pattern) makes every chain wait for the one two places before it.
+          unsigned dep[2] = {0u, 0u};
 #pragma unroll
           for (int gi = 0; gi < NG; ++gi) {
             if (gi >= g0 && gi < g1) {
-              const float4 e4 = philox_normal4(kglob, (unsigned)n, (unsigned)(g_lo + gi), prm.offset, prm.seed);
+              const float4 e4 = philox_normal4(kglob, (unsigned)n, (unsigned)(g_lo + gi), prm.offset + dep[gi & 1], prm.seed);
               E[gi][0] = e4.x; E[gi][1] = e4.y; E[gi][2] = e4.z; E[gi][3] = e4.w;
+              dep[gi & 1] = (__float_as_uint(e4.w) == 0x7fffffffu) ? 1u : 0u;
             }
           }
         } else {
@@ -247,7 +263,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
         tc::fence_after_sync();
         pt_.mark(2 * hl);
         float v[HC], hi[HC], lo[HC];
-        tc::tmem_ld8(tD + hl * tg.hp + HC * part, v);
+#pragma unroll
+        for (int u = 0; u < HQ; ++u) {
+          float v4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (u < hnq) tc::tmem_ld4(tD + hl * tg.hp + 4 * (hq0 + u), v4);
+          v[4 * u] = v4[0]; v[4 * u + 1] = v4[1]; v[4 * u + 2] = v4[2]; v[4 * u + 3] = v4[3];
+        }
         tc::wait_ld();
         if (tg.dense) {
 #pragma unroll
@@ -256,17 +277,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
           const int one_col = g.dims[1 + hl];
 #pragma unroll
           for (int i = 0; i < HC; ++i) {
-            const float h = (HC * part + i == one_col) ? 1.0f : tanhf(v[i]);
+            const float h = (4 * hq0 + i == one_col) ? 1.0f : tanhf(v[i]);
             tc::tf32_split(h, hi[i], lo[i]);
           }
         }
-        const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + HC * part;
-        tc::tmem_st8(th, hi);
-        tc::tmem_st8(th + tg.hp, lo);
-        if (CKPT && keep) {                  // h = hi + lo exactly
-          float* o = ck + (size_t)(n * prm.ckpt_cols + tg.s0 + tg.hp * hl + HC * part) * kTcP;
+        const uint32_t th = tbase + lane_addr + (hl ? tg.c_h2h : tg.c_h1h) + 4 * hq0;
 #pragma unroll
-          for (int u = 0; u < HC; ++u) o[u * kTcP] = live ? hi[u] + lo[u] : 0.f;
+        for (int u = 0; u < HQ; ++u) {
+          if (u < hnq) {
+            const float h4[4] = {hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]};
+            const float l4[4] = {lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]};
+            tc::tmem_st4(th + 4 * u, h4);
+            tc::tmem_st4(th + tg.hp + 4 * u, l4);
+          }
+        }
+        if (CKPT && keep) {                  // h = hi + lo exactly
+          float* o = ck + (size_t)(n * prm.ckpt_cols + tg.s0 + tg.hp * hl + 4 * hq0) * kTcP;
+#pragma unroll
+          for (int u = 0; u < HC; ++u)
+            if (u < 4 * hnq) st_ckpt(o + u * kTcP, live ? hi[u] + lo[u] : 0.f);
         }
         tc::wait_st();
         tc::fence_before_sync();
@@ -322,8 +351,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                 // group gi of this thread sits 4 gi columns (an immediate offset) behind its first one
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  ckx[(4 * gi + i) * kTcP] = live ? X[gi][i] : 0.f;
-                  ckx[zoff + (4 * gi + i) * kTcP] = live ? ze[i] : 0.f;
+                  st_ckpt(ckx + (4 * gi + i) * kTcP, live ? X[gi][i] : 0.f);
+                  st_ckpt(ckx + zoff + (4 * gi + i) * kTcP, live ? ze[i] : 0.f);
                 }
               }
 #pragma unroll
@@ -452,19 +481,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
 }
 
 // NG instantiations: the smallest one that holds tg.ng column groups per thread
+template <int NG, bool CKPT, bool DIAG, bool PHILOX>
+inline cudaError_t tc_launch_k(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT, DIAG, PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
+  if (e != cudaSuccess) return e;
+  rollout_tc_fwd_kernel<NG, CKPT, DIAG, PHILOX><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
+  return cudaGetLastError();
+}
 template <int NG, bool CKPT, bool DIAG>
 inline cudaError_t tc_launch_one(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
-  if (e != cudaSuccess) return e;
-  rollout_tc_fwd_kernel<NG, CKPT, DIAG><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
-  return cudaGetLastError();
+  return p.noise_mode == NOISE_PHILOX ? tc_launch_k<NG, CKPT, DIAG, true>(p, tg, grid, stream)
+                                      : tc_launch_k<NG, CKPT, DIAG, false>(p, tg, grid, stream);
 }
 template <bool CKPT, bool DIAG = false>
 inline cudaError_t tc_launch_t(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
-  if (tg.ng <= 1) return tc_launch_one<1, CKPT, DIAG>(p, tg, grid, stream);
   if (tg.ng <= 2) return tc_launch_one<2, CKPT, DIAG>(p, tg, grid, stream);
-  if (tg.ng <= 4) return tc_launch_one<4, CKPT, DIAG>(p, tg, grid, stream);
-  if (tg.ng <= 7) return tc_launch_one<7, CKPT, DIAG>(p, tg, grid, stream);
+  if (tg.ng <= 5) return tc_launch_one<5, CKPT, DIAG>(p, tg, grid, stream);      // d <= 58 (C3: d = 50)
+  if (tg.ng <= 9) return tc_launch_one<9, CKPT, DIAG>(p, tg, grid, stream);      // d <= 106 (C2 / C5: d = 100)
   return tc_launch_one<kTcMaxG, CKPT, DIAG>(p, tg, grid, stream);
 }
 inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "pspde_grad_from_fwd_ckpt": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_size_t, _P, _P, _P, ctypes.c_size_t, _P]),
     "pspde_rollout_attached": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, ctypes.c_size_t, _P]),
+    "pspde_rollout_attached_diag": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, _P, _P,
+                                                   _P, ctypes.POINTER(pspde_udiag), _P, _P, ctypes.c_size_t, _P]),
     "pspde_importance_sampling": (ctypes.c_int, [_CFG, _P, _P, _P, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P,
                                                  ctypes.c_size_t, _P]),
     "pspde_philox_dump": (ctypes.c_int, [_CFG, _P, _P]),

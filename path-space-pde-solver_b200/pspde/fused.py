@@ -184,12 +184,15 @@ class RolloutEngine:
     def attached(self, theta, call, grad_out, y0=None, wY=None, wZ=None, wG=None):
         """wY = wZ = wG = None: relative entropy in one launch (constant cotangents 1 / K_global)."""
         cfg = self.cfg(call)
-        rc = self.lib.pspde_rollout_attached(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
-                                             self._p(y0), self._xi_ptr(call), ctypes.c_float(1.0 / self.K_global),
-                                             self._p(wY), self._p(wZ), self._p(wG), self._p(self.X_N),
-                                             self._p(self.Y_N), self._p(self.gX), self._p(self.Zsum),
-                                             self._p(self.stats), self._p(grad_out), self._p(self.workspace),
-                                             self.workspace.numel(), self._stream())
+        # the u_L2 diagnostic belongs to the forward sweep; the two-phase form (per-path cotangents) already got it from
+        # its forward launch
+        diag = None if (self.udiag is None or wY is not None or wZ is not None or wG is not None) else ctypes.byref(self.udiag)
+        rc = self.lib.pspde_rollout_attached_diag(ctypes.byref(cfg), self._p(theta), self._p(self.pack), self._p(self.x0),
+                                                  self._p(y0), self._xi_ptr(call), ctypes.c_float(1.0 / self.K_global),
+                                                  self._p(wY), self._p(wZ), self._p(wG), self._p(self.X_N),
+                                                  self._p(self.Y_N), self._p(self.gX), self._p(self.Zsum),
+                                                  self._p(self.stats), diag, self._p(grad_out), self._p(self.workspace),
+                                                  self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
     def philox_dump(self, offset=0):

@@ -303,7 +303,7 @@ class Solver:
             dist.all_reduce_sum_(self.y_0.Y_0.grad, self.process_group)
         self.optimization_step()
         u_l2 = pt.full((), float('nan'), dtype=pt.float64, device=self.device)
-        if self._u_l2_on and not (attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0):
+        if self._u_l2_on:
             u = eng.uL2.double()                               # filled by the forward launch of this iteration
             u_l2 = dist.all_reduce_sum_(pt.where(pt.isfinite(u), u, pt.zeros_like(u)).sum().reshape(1),
                                         self.process_group)[0] / self.K

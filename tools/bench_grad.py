@@ -1,4 +1,4 @@
-"""Microbenchmark + phase profile of the gradient kernels on a synthetic checkpoint buffer (C2 shape by default):
+"""Microbenchmark + per-role phase profile of the gradient kernels on a synthetic checkpoint buffer (C2 shape by default):
 148 tile slots x N steps of operand rows, timed through pspde_grad_from_ckpt."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,10 +16,12 @@ ck = pt.randn(slots, N, C, 128, device="cuda", generator=gen).abs_() * 0.3
 theta = pt.randn(n_theta, device="cuda", generator=gen) * 0.1
 ws = pt.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) + 4 * n_theta * 160, dtype=pt.uint8, device="cuda")
 out = pt.empty(n_theta, device="cuda")
-names = ["wait tensor core", "copy + transpose", "fences + barrier", "MMA issue", "zeta . W2'", "delta_2 + barrier", "delta_2 . W1' + delta_1"]
-for path in ("tc", "tc64", "simt"):
-    os.environ["PSPDE_GRAD_PATH"] = path[:2] if path != "simt" else path
-    os.environ["PSPDE_GRAD_FLUSH_ITEMS"] = path[2:] if path[:2] == "tc" and path[2:] else "4"
+names = ["delta: wait TMA", "delta: zeta.W2' (+delta_2)", "delta: barrier + delta_2.W1' + delta_1", "delta: fence + arrive",
+         "mma: wait acc free + lo tile", "mma: wait delta rows", "mma: issue + commit", "mma: flush",
+         "lo: wait TMA", "lo: lo pass", "lo: flush", "tma: wait free stage", "tma: issue", "tma: flush"]
+for path, flush in (("tc", "16"), ("tc", "100000"), ("tc", "4"), ("simt", "16")):
+    os.environ["PSPDE_GRAD_PATH"] = path
+    os.environ["PSPDE_GRAD_FLUSH_STAGES"] = flush
     call = lambda: lib.pspde_grad_from_ckpt(ctypes.byref(cfg), theta.data_ptr(), ck.data_ptr(), slots, s0, out.data_ptr(), ws.data_ptr(), ws.numel(), None)
     assert call() == 0, lib.pspde_last_error()
     pt.cuda.synchronize()
@@ -28,11 +30,11 @@ for path in ("tc", "tc64", "simt"):
         e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
         e0.record(); call(); e1.record(); pt.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[2]
-    items = slots * N * 2 / 148
-    print("%s (flush every %s items): %.3f ms for %d samples -> %.0f cycles per 64-sample item per SM, %.1f TFLOP/s algorithmic (29 960 MAC/sample)"
-          % (path, os.environ["PSPDE_GRAD_FLUSH_ITEMS"], ms, slots * 128 * N, ms * 1e-3 * 1.965e9 / items, 2 * 29960 * slots * 128 * N / ms / 1e9))
+    stages = slots * N * 4 / 148
+    print("%s (flush every %s stages): %.3f ms for %d samples -> %.0f cycles per 32-sample stage per SM, %.1f TFLOP/s algorithmic (29 960 MAC/sample)"
+          % (path, flush, ms, slots * 128 * N, ms * 1e-3 * 1.965e9 / stages, 2 * 29960 * slots * 128 * N / ms / 1e9))
     if path == "tc":
         buf = pt.zeros(16, dtype=pt.int64, device="cuda")
         lib.pspde_set_profile_buffer(ctypes.c_void_p(buf.data_ptr())); call(); pt.cuda.synchronize(); lib.pspde_set_profile_buffer(None)
         for n, v in zip(names, buf.tolist()):
-            print("    %-26s %8.0f cycles/item" % (n, v / items))
+            print("    %-40s %8.0f cycles/stage" % (n, v / stages))
