@@ -8,6 +8,14 @@ thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 unsigned long long* g_prof = nullptr;
 
+// Must the zeta columns be written to the checkpoint?  Not when zeta = wY sqrt(dt) xi with in-kernel noise (adaptive process,
+// no cotangent on Z_sum): the gradient kernel regenerates it from the Philox key (RolloutParams::ckpt_zeta).
+// PSPDE_CKPT_ZETA=1 forces the columns into the checkpoint (A/B tests).
+static int zeta_in_ckpt(const pspde_cfg* cfg, const float* wZ) {
+  if (const char* e = getenv("PSPDE_CKPT_ZETA")) if (e[0] == '1') return 1;
+  return (cfg->noise_mode == PSPDE_NOISE_PHILOX && cfg->adaptive && !wZ) ? 0 : 1;
+}
+
 // Forward rollout launch: the tensor-core kernel (rollout_tc_kernels.cuh) for the shape class it covers, else the
 // FP32-FMA kernel.  PSPDE_FWD_PATH=simt forces the FMA kernel (A/B tests); PSPDE_FWD_PATH=tc makes an ineligible
 // configuration an error.  *grid_out = number of CTAs launched (rows of stats_partial that were written).
@@ -24,7 +32,8 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
     const int sms = pspde_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     p.n_tiles = n_tiles;
-    if (keep_ckpt) { p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles; }
+    if (keep_ckpt) { p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles;
+                     p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr); }
     const cudaError_t ce = keep_ckpt ? tc_launch_fwd_ckpt(p, tg, grid, (cudaStream_t)stream) : tc_launch(p, tg, grid, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
@@ -63,7 +72,10 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
     int flush_stages = kGtFlushStages;
     if (const char* e = getenv("PSPDE_GRAD_FLUSH_STAGES")) { const int v = atoi(e); if (v >= 1) flush_stages = v; }
     CUtensorMap tmap;
-    if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap)) return fail(-11, "cuTensorMapEncodeTiled failed for the checkpoint buffer");
+    // zeta regenerated in the kernel: one box of the activation rows per stage; else two boxes of cols / 2 rows
+    if (!p.ckpt_zeta && gt.act_rows > 256) return fail(-6, "activation rows exceed one TMA box");
+    if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap, p.ckpt_zeta ? 0 : gt.act_rows))
+      return fail(-11, "cuTensorMapEncodeTiled failed for the checkpoint buffer");
     grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(tmap, p, gt, (int)n_ts, flush_stages);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
@@ -165,7 +177,7 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
 // rows (cotangents p.wY / p.wZ applied) into p.ckpt, then the gradient kernel; accumulates into p.grad_partial
 static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, const TcGeom& tg, const CkptPlan& cp, int t_begin,
                      void* stream, bool* used_tc) {
-  p.ckpt_cols = cp.cols; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0;
+  p.ckpt_cols = cp.cols; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0; p.ckpt_zeta = zeta_in_ckpt(cfg, p.wZ);
   const int sms = pspde_sm_count();
   for (int t0 = t_begin; t0 < cp.n_tiles128; t0 += cp.wave) {
     const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
@@ -368,7 +380,7 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   fill_params(cfg, pl, p);
   p.theta = theta;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
-  p.ckpt = const_cast<float*>(ckpt); p.ckpt_cols = 2 * s0 + 64; p.ckpt_s0 = s0;
+  p.ckpt = const_cast<float*>(ckpt); p.ckpt_cols = 2 * s0 + 64; p.ckpt_s0 = s0; p.ckpt_zeta = 1;
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
   bool used_tc = false;
   rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);
@@ -413,7 +425,7 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
   p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0;
-  p.tile0 = 0; p.ckpt_unit = 1;
+  p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr);
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
   bool used_tc = false;
   rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);

@@ -152,6 +152,7 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
   const int my_ts = (n_ts - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // (tile, step) pairs of this CTA
   const int n_stage_it = my_ts > 0 ? my_ts * kGtSub : 0;
   const bool unit = prm.ckpt_unit != 0;
+  const bool gen_ze = prm.ckpt_zeta == 0;      // zeta is not in the checkpoint: regenerate it from Philox (see RolloutParams)
   // per-path cotangents of the 4 samples of quad j of stage iteration `it` (forward-written checkpoint, unit cotangents)
   auto unit_w = [&](int it, int j, float (&w)[4]) {
     const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
@@ -168,7 +169,8 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
     const int j = pos ^ (r0 & 7);
     float w[4];
     unit_w(it, j, w);
-    for (int r = r0; r < tg.cols; r += kFix / 8) {
+    const int r_end = gen_ze ? tg.act_rows : tg.cols;          // regenerated zeta rows already carry the cotangent
+    for (int r = r0; r < r_end; r += kFix / 8) {
       float4* p = reinterpret_cast<float4*>(tH + (uint32_t)r * 128u + (uint32_t)(pos << 4));
       float4 v = *p;
       const bool ze = r >= tg.r_ze;
@@ -200,9 +202,35 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
       uint8_t* tH = smem + tg.o_hi[s];
       uint8_t* tL = smem + tg.o_lo[s];
-      tc::mbar_wait(&bar_full[s], par);
+      if (gen_ze) {
+        // zeta rows of this stage from Philox, exactly as the rollout drew them: thread = (sample, column group); value
+        // wY[path] * (sqrt(dt) xi), zero for padding paths and dropped trajectories.  The stage buffer must be free (the
+        // tensor core is done with its previous use); the TMA load of the activation rows is in flight meanwhile.
+        tc::mbar_wait(&bar_empty[s], par ^ 1u);
+        const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
+        const int kl = (prm.tile0 + ts / prm.N) * kCkP + sub * kGtS + lane;          // local path index of this lane's sample
+        const unsigned nstep = (unsigned)(ts % prm.N);
+        const float wk = (kl < prm.K_local) ? __ldg(prm.wY + kl) : 0.f;
+        const float sqdt = sqrtf(prm.dt);
+        const int ngroups = (prm.d + 3) >> 2;
+        for (int jb = warp; jb < ngroups; jb += kGtWorkers / 32) {
+          const float4 e4 = philox_normal4((unsigned)(prm.k_offset + kl), nstep, (unsigned)jb, prm.offset, prm.seed);
+          const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = 4 * jb + i;
+            const float v = (c < prm.d && wk != 0.f) ? wk * (sqdt * ev[i]) : 0.f;
+            const uint32_t off = (uint32_t)(tg.r_ze + c) * 128u + (uint32_t)((((lane >> 2) ^ ((tg.r_ze + c) & 7)) << 4) + ((lane & 3) << 2));
+            *reinterpret_cast<float*>(tH + off) = v;
+            *reinterpret_cast<float*>(tL + off) = lo1(v);
+          }
+        }
+        gt_named_bar(3, kGtWorkers);
+      } else {
+        tc::mbar_wait(&bar_full[s], par);
+      }
       pt_.mark(0);
-      if (unit) fixup(tH, it, tid);
+      if (unit && !gen_ze) fixup(tH, it, tid);
       float acc[4][4];                      // [hidden column][sample]
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -255,6 +283,10 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
         *reinterpret_cast<float4*>(tL + off) = lo4(o);
       };
       if (is_h2 || tg.dense) accumulate(sW + tg.o_w2, tg.w2_nng, tg.r_ze, g.layer[2].nng);
+      if (gen_ze) {                           // the hidden activations (act') arrive by TMA: needed from here on
+        tc::mbar_wait(&bar_full[s], par);
+        if (unit) fixup(tH, it, tid);
+      }
       if (is_h2) finish(tg.r_d2);
       pt_.mark(1);
       gt_named_bar(2, kGtWorkers);
@@ -310,10 +342,15 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
         if (lane == 0) {
           tc::mbar_wait(&bar_empty[s], par ^ 1u);                  // first use of a stage passes immediately
           pt_.mark(11);
-          tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.cols * 128u);
           const int ts = (int)blockIdx.x + (it / kGtSub) * (int)gridDim.x, sub = it % kGtSub;
-          tc::tma_load_3d(tH, &tmap, &bar_full[s], sub * kGtS, 0, ts);
-          tc::tma_load_3d(tH + (uint32_t)tg.box_rows * 128u, &tmap, &bar_full[s], sub * kGtS, tg.box_rows, ts);
+          if (gen_ze) {                       // activation rows only: one box of act_rows rows (the map's box)
+            tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.act_rows * 128u);
+            tc::tma_load_3d(tH, &tmap, &bar_full[s], sub * kGtS, 0, ts);
+          } else {
+            tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.cols * 128u);
+            tc::tma_load_3d(tH, &tmap, &bar_full[s], sub * kGtS, 0, ts);
+            tc::tma_load_3d(tH + (uint32_t)tg.box_rows * 128u, &tmap, &bar_full[s], sub * kGtS, tg.box_rows, ts);
+          }
           pt_.mark(12);
         }
         __syncwarp();
@@ -356,7 +393,7 @@ static __global__ void __launch_bounds__(kGtThreads, 1) grad_tc_kernel(const __g
         const int t = tid - (kGtUtil + 2) * 32;
         const float4* src = reinterpret_cast<const float4*>(tH);
         float4* dst = reinterpret_cast<float4*>(tL);
-        const int nq = tg.cols * 8;
+        const int nq = (gen_ze ? tg.act_rows : tg.cols) * 8;       // regenerated zeta rows come with their lo values
         int q = t;
         for (; q + 7 * 64 < nq; q += 8 * 64) {                     // 8 loads in flight per thread: the shared-memory latency
           float4 v[8];                                             // under the tensor core's operand traffic is > 100 cycles
@@ -426,12 +463,13 @@ inline PFN_tmap_encode tmap_encode_fn() {
   return fn;
 }
 // returns 0 on success
-inline int grad_tc_tensor_map(const GradTcGeom& tg, const float* ckpt, long long n_ts, CUtensorMap* out) {
+inline int grad_tc_tensor_map(const GradTcGeom& tg, const float* ckpt, long long n_ts, CUtensorMap* out, int box_rows = 0) {
+  if (box_rows <= 0) box_rows = tg.box_rows;
   PFN_tmap_encode enc = tmap_encode_fn();
   if (!enc) return -1;
   const cuuint64_t gdim[3] = {(cuuint64_t)kCkP, (cuuint64_t)tg.cols, (cuuint64_t)n_ts};
   const cuuint64_t gstr[2] = {(cuuint64_t)kCkP * 4u, (cuuint64_t)kCkP * 4u * (cuuint64_t)tg.cols};
-  const cuuint32_t box[3] = {(cuuint32_t)kGtS, (cuuint32_t)tg.box_rows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)kGtS, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ckpt), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

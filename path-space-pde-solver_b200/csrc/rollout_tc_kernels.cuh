@@ -13,7 +13,8 @@
 //     B0 = [W0 | W1[a0 rows] | W2[a0 rows]]   (s0 x (64 + np3))    the dense-concat layers all read a0: ONE MMA group
 //     B1 = [W1[h1 rows] | W2[h1 rows]]        (32 x (32 + np3))
 //     B2 =  W2[h2 rows]                       (32 x np3)
-//   registers: the state X (own columns), the per-path partial sums of Y, Z_sum, g.
+//   registers: the step's Brownian increments (own columns), the per-path partial sums of Y, Z_sum, g; the state X lives in
+//     the a0 operand columns of tensor memory (hi + lo is exact) and is read back for the Euler-Maruyama update.
 //
 // Per step: G0 = a0.B0 -> h1 = relu(pre1)^2 -> G1 += h1.B1 -> h2 = relu(pre2)^2 -> G2 += h2.B2 -> Z; the
 // Euler-Maruyama update then runs on the registers of the thread that owns the column and writes the next a0
@@ -179,7 +180,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
               *al = sProb + 4 * tg.s0, *kap = sProb + 5 * tg.s0, *eta = sProb + 6 * tg.s0;
   const bool adaptive = prm.adaptive != 0, dw = prm.problem_id == PROBLEM_DW;
   uint32_t ph = 0;
-  float X[NG][4];
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
     const int k = (prm.tile0 + tile) * kTcP + p;
@@ -206,7 +206,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
           if (j < d) { if (in) x = prm.x0_per_path ? __ldg(prm.x0 + (size_t)k * d + j) : __ldg(prm.x0 + j); }
           else if (j == d) x = prm.t_index ? (float)__ldg(prm.t_index) * prm.dt_net : 0.f;    // network time of step 0
           else if (j == d + 1) x = 1.0f;
-          X[gi][i] = x;
           tc::tf32_split(x, hi[i], lo[i]);
         }
         tc::tmem_st4(tA0h + 4 * (g_lo + gi), hi);
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       pt_.mark(4);
       // Branch-free per element: the problem vectors are zero on the [t | 1 | pad] columns (so x stays put there) and Z
       // is exactly zero on them (zero weight columns); only the time column is patched afterwards.
-      float zz = 0.f, zxi = 0.f, ff = 0.f, ul = 0.f;
+      float zz = 0.f, zxi = 0.f, ff = 0.f, ul = 0.f, gg = 0.f;
       // network time of the next step: (n + 1) dt, or the caller's grid (importance sampling, Solver.Z_n :360-362)
       const float t_next = (prm.t_index && !last) ? (float)__ldg(prm.t_index + n + 1) * prm.dt_net : (float)(n + 1) * dt;
       const float cm = adaptive ? -1.0f : 0.f;
@@ -320,14 +319,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
 #pragma unroll
       for (int c0 = 0; c0 < NG; c0 += 2) {          // 2 column groups (8 columns) per tensor-memory access
         const bool full = (c0 + 1 < NG) && (c0 + 1 < ng);     // warp-uniform
+        // The state X_n is NOT kept in registers across the step: it is read back from the a0 operand columns of tensor
+        // memory (hi + lo == x exactly, tc::tf32_split) together with Z.
         float Z[8], H[8], Lo[8];
-        if (full) tc::tmem_ld8(tD + 2 * tg.hp + 4 * (g_lo + c0), Z);
-        else {
+        if (full) {
+          tc::tmem_ld8(tD + 2 * tg.hp + 4 * (g_lo + c0), Z);
+          tc::tmem_ld8(tA0h + 4 * (g_lo + c0), H);
+          tc::tmem_ld8(tA0l + 4 * (g_lo + c0), Lo);
+        } else {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            float z4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (c0 + u < NG && c0 + u < ng) tc::tmem_ld4(tD + 2 * tg.hp + 4 * (g_lo + c0 + u), z4);
-            Z[4 * u] = z4[0]; Z[4 * u + 1] = z4[1]; Z[4 * u + 2] = z4[2]; Z[4 * u + 3] = z4[3];
+            float z4[4] = {0.f, 0.f, 0.f, 0.f}, h4[4] = {0.f, 0.f, 0.f, 0.f}, l4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c0 + u < NG && c0 + u < ng) {
+              tc::tmem_ld4(tD + 2 * tg.hp + 4 * (g_lo + c0 + u), z4);
+              tc::tmem_ld4(tA0h + 4 * (g_lo + c0 + u), h4);
+              tc::tmem_ld4(tA0l + 4 * (g_lo + c0 + u), l4);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { Z[4 * u + i] = z4[i]; H[4 * u + i] = h4[i]; Lo[4 * u + i] = l4[i]; }
           }
         }
         tc::wait_ld();
@@ -340,24 +349,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
               const float4 A4 = ld4(a_d + j0), B4 = ld4(b_d + j0), P4 = ld4(p_d + j0), K4 = ld4(kap + j0);
               const float av[4] = {A4.x, A4.y, A4.z, A4.w}, bv[4] = {B4.x, B4.y, B4.z, B4.w};
               const float pv[4] = {P4.x, P4.y, P4.z, P4.w}, kv[4] = {K4.x, K4.y, K4.z, K4.w};
-              if (CKPT && keep) {            // operand rows of this step: a0 = X_n (own columns) and zeta
-                const float kA = adaptive ? 0.f : dt;
-                float ze[4];
+              if (CKPT && keep) {            // operand rows of this step: a0 = X_n (own columns) and, unless the gradient
+                // kernel regenerates it, zeta; group gi of this thread sits 4 gi columns (an immediate offset) behind its first one
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float z = Z[4 * u + i], ee = E[gi][i];
-                  ze[i] = (j0 + i < d) ? wy * (sq * ee + kA * z) + wz * (dt * z) : 0.f;
-                }
-                // group gi of this thread sits 4 gi columns (an immediate offset) behind its first one
+                for (int i = 0; i < 4; ++i) st_ckpt(ckx + (4 * gi + i) * kTcP, live ? H[4 * u + i] + Lo[4 * u + i] : 0.f);
+                if (prm.ckpt_zeta) {
+                  const float kA = adaptive ? 0.f : dt;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  st_ckpt(ckx + (4 * gi + i) * kTcP, live ? X[gi][i] : 0.f);
-                  st_ckpt(ckx + zoff + (4 * gi + i) * kTcP, live ? ze[i] : 0.f);
+                  for (int i = 0; i < 4; ++i) {
+                    const float z = Z[4 * u + i], ee = E[gi][i];
+                    const float ze = (j0 + i < d) ? wy * (sq * ee + kA * z) + wz * (dt * z) : 0.f;
+                    st_ckpt(ckx + zoff + (4 * gi + i) * kTcP, live ? ze : 0.f);
+                  }
                 }
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float z = Z[4 * u + i], x = X[gi][i], ee = E[gi][i];
+                const float z = Z[4 * u + i], x = H[4 * u + i] + Lo[4 * u + i], ee = E[gi][i];
                 zz = fmaf(z, z, zz);
                 zxi = fmaf(z, ee, zxi);
                 const float drift = fmaf(av[i], x, -(4.0f * kv[i] * (x * (x * x - 1.0f))));   // OU: kappa = 0; double well: a = 0
@@ -377,7 +385,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                   ul = fmaf(du, du, ul);
                 }
                 xn = (j0 + i == d) ? t_next : xn;                                          // the time column
-                X[gi][i] = xn;
+                if (last) {                                                                // terminal cost g(X_N), X_N itself
+                  if (j0 + i < d) {
+                    gg += al[j0 + i] * xn + r_d[j0 + i] * xn * xn + eta[j0 + i] * (xn - 1.0f) * (xn - 1.0f);
+                    if (prm.X_N && in) prm.X_N[(size_t)k * d + j0 + i] = xn;
+                  }
+                }
                 tc::tf32_split(xn, H[4 * u + i], Lo[4 * u + i]);
               }
             }
@@ -396,20 +409,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                 tc::tmem_st4(tA0h + 4 * (g_lo + c0 + u), h4);
                 tc::tmem_st4(tA0l + 4 * (g_lo + c0 + u), l4);
               }
-            }
-          }
-        }
-      }
-      float gg = 0.f;
-      if (last) {                                   // terminal cost g(X_N) on the own columns
-#pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-          if (gi < ng) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = 4 * (g_lo + gi) + i;
-              const float xn = X[gi][i];
-              if (j < d) gg += al[j] * xn + r_d[j] * xn * xn + eta[j] * (xn - 1.0f) * (xn - 1.0f);
             }
           }
         }
@@ -458,18 +457,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
       }
       s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); s3 = warp_sum_d(s3);
       if (lane == 0) { atomicAdd(sRed + 0, s0); atomicAdd(sRed + 1, s1); atomicAdd(sRed + 2, s2); atomicAdd(sRed + 3, s3); }
-    }
-    if (prm.X_N && in) {
-#pragma unroll
-      for (int gi = 0; gi < NG; ++gi) {
-        if (gi < ng) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * (g_lo + gi) + i;
-            if (j < d) prm.X_N[(size_t)k * d + j] = X[gi][i];
-          }
-        }
-      }
     }
     __syncthreads();      // sExch is rewritten by the next tile
   }

@@ -1,4 +1,6 @@
-"""Per-phase cycle counts of the rollout kernels (CTA 0) via the pspde_set_profile_buffer debug hook."""
+"""Per-phase cycle counts (CTA 0) of the kernels of one training iteration via pspde_set_profile_buffer, on a bench.py
+workload (default c2):  forward rollout (plain and row-keeping), gradient kernel over the rows the forward kept
+(single-rollout step, zeta regenerated in the kernel), and their CUDA-event times."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "path-space-pde-solver_b200"))
@@ -10,22 +12,38 @@ wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 dev = pt.device("cuda", 0); pt.cuda.set_device(0)
 lib = _lib.load()
 S = bench.build_solver(wl, wl["K"], dev); eng = S._get_engine(); theta = S._theta.detach()
+wY = pt.randn(eng.K_local, device=dev) / eng.K_local
+grad = pt.empty(eng.n_theta, device=dev)
 buf = pt.zeros(16, dtype=pt.int64, device=dev)
-names = ["prologue", "net_forward(rest)", "sde_step", "backward_hidden", "weight_grad(+copy wait)", "L0 work", "L1 work", "L2 work", "L0 barrier wait", "L1 barrier wait", "L2 barrier wait"]
-tiles_cta0 = (eng.K_local + 63) // 64 // 148 + (1 if ((eng.K_local + 63) // 64) % 148 > 0 else 0)
-for which in ("fwd", "bwd"):
-    eng.forward(theta, None, Call(offset=0)); pt.cuda.synchronize()
+ntiles = (eng.K_local + 127) // 128
+tiles_cta0 = ntiles // 148 + (1 if ntiles % 148 > 0 else 0)
+
+
+def profiled(fn, warm=True):
+    if warm:
+        fn(); pt.cuda.synchronize()
     buf.zero_(); lib.pspde_set_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
     e0, e1 = pt.cuda.Event(enable_timing=True), pt.cuda.Event(enable_timing=True)
-    e0.record()
-    if which == "fwd":
-        eng.forward(theta, None, Call(offset=0))
-    else:
-        w = (pt.randn(eng.K_local, device=dev) / eng.K_local) * pt.isfinite(eng.Y_N - eng.gX)
-        g = pt.empty(eng.n_theta, device=dev); eng.backward_detached(theta, w.contiguous(), None, Call(offset=0), g)
-    e1.record(); pt.cuda.synchronize()
+    e0.record(); fn(); e1.record(); pt.cuda.synchronize()
     lib.pspde_set_profile_buffer(None)
-    c = buf.tolist(); tot = sum(c); steps = tiles_cta0 * eng.N
-    print("%s: %.2f ms, CTA0 %d tile-steps, %.0f cycles/tile-step" % (which, e0.elapsed_time(e1), steps, tot / steps))
-    for n, v in zip(names, c):
-        if v: print("    %-26s %8.0f cycles/tile-step  %5.1f%%" % (n, v / steps, 100 * v / tot))
+    return e0.elapsed_time(e1), buf.tolist()
+
+
+fwd_names = ["wait G0 (a0 . B0)", "h1 epilogue", "wait G1", "h2 epilogue", "wait G2", "SDE step (+Z ld, a0 st)", "noise (Philox + Box-Muller)"]
+for keep in (False, True):
+    ms, c = profiled(lambda: eng.forward(theta, None, Call(offset=0), keep_rows=keep))
+    steps = tiles_cta0 * eng.N; tot = sum(c[:7])
+    print("forward%s: %.2f ms, CTA0 %d tile-steps (128 paths), %.0f cycles/tile-step" % (" (keeps its rows)" if keep else "", ms, steps, tot / steps))
+    for n, v in zip(fwd_names, c):
+        print("    %-30s %8.0f cycles/tile-step  %5.1f%%" % (n, v / steps, 100 * v / max(tot, 1)))
+if eng.ckpt is not None:
+    grad_names = ["delta: zeta gen / wait TMA", "delta: zeta.W2' (+delta_2)", "delta: barrier + delta_2.W1' + delta_1", "delta: fence + arrive",
+                  "mma: wait acc free + lo tile", "mma: wait delta rows", "mma: issue + commit", "mma: flush",
+                  "lo: wait TMA", "lo: lo pass", "lo: flush", "tma: wait free stage", "tma: issue", "tma: flush"]
+    ms, c = profiled(lambda: eng.grad_from_rows(theta, wY, Call(offset=0), grad))
+    stages = tiles_cta0 * eng.N * 4
+    print("gradient kernel over the kept rows: %.2f ms, %.0f cycles per 32-sample stage" % (ms, ms * 1e-3 * 1.965e9 / stages))
+    for n, v in zip(grad_names, c):
+        print("    %-40s %8.0f cycles/stage" % (n, v / stages))
+ms, _ = profiled(lambda: eng.backward_detached(theta, wY, None, Call(offset=0), grad))
+print("two-rollout backward (checkpoint rollout + gradient kernel per wave): %.2f ms" % ms)
