@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PSPDE_ABI_VERSION 1
+#define PSPDE_ABI_VERSION 2
 #define PSPDE_MAX_LAYERS 4          /* linear layers per network (<= 3 hidden) */
 
 /* problem functors (problems.py): drift b(x), diffusion sigma = B, running cost f, terminal cost g.
@@ -110,13 +110,17 @@ int pspde_rollout_fwd(const pspde_cfg* cfg, const float* theta, const float* pro
  *   mode 1  u*_j = U0[n][j] + U1[n][j] * x_j          table fp32 [N][2][d]   (LLGC problems.py:51-53: U1 = 0;
  *                                                      LQGC :169-171 with diagonal Q^-1 B' F_n: U0 = 0)
  *   mode 2  u*_j = tab[n][j < d1 ? 0 : 1][cell(x_j)]  table fp32 [N][2][nx1], cell = floor((clip(x, -xb, xb - 2dx) + xb) / dx)
- *                                                      (DoubleWell(_multidim) finite-difference tables, :398-404, :463-476) */
+ *                                                      (DoubleWell(_multidim) finite-difference tables, :398-404, :463-476)
+ *           quirk_path >= 0: the path with that GLOBAL index reads its cell two to the left, a negative cell wrapping to the
+ *           table's end -- the reference's `i[-1] -= 2` on the last batch element (problems.py:279, :401, :464) followed by
+ *           numpy's negative indexing; -1 switches it off */
 typedef struct pspde_udiag {
   int32_t mode;          /* 0 off */
   int32_t nx1, d1;       /* mode 2 */
   float   xb, dx;        /* mode 2 */
   const float* table;    /* device */
   float*  uL2;           /* device, K_local per-path results */
+  int32_t quirk_path;    /* mode 2: global path index of the `i[-1] -= 2` element, or -1 */
 } pspde_udiag;
 
 int pspde_rollout_fwd_diag(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,

@@ -532,7 +532,17 @@ def diffusion_train_loop(problem, params, K, K_boundary, N, delta_t, L, lr, seed
         t0 = time.time()
         X0 = sample_ball(K, problem.d, problem.boundary_distance)                   # :1045-1046
         t0_ = pt.rand(K, 1) * problem.T                                             # :1078
-        xis = pt.stack([pt.randn(K, problem.d) for _ in range(N)])                  # :1106 (no early break here)
+        # :1106 -- one draw per step, none once every path is stopped (break at :1093-1094; unbounded domain: the time test
+        # of :1131 alone, replayed in fp32); the steps after the break get zeros, which diffusion_iteration never uses
+        dt_, t_, stopped_, xl = pt.as_tensor(delta_t, dtype=pt.float32), t0_.squeeze(1).clone(), pt.zeros(K, dtype=pt.bool), []
+        for _n in range(N):
+            if int((~stopped_).sum()) == 0:
+                break
+            xl.append(pt.randn(K, problem.d))
+            ns_ = (t_ + dt_) <= problem.T
+            t_ = t_ + dt_ * (ns_ & ~stopped_).float()
+            stopped_ = stopped_ | (~ns_ & ~stopped_)
+        xis = pt.stack(xl + [pt.zeros(K, problem.d)] * (N - len(xl)))
         opt.zero_grad()
         out = diffusion_iteration(problem, params, X0, t0_, xis, delta_t, N, K_boundary)
         for q, g in zip(params, out["grads"]):

@@ -150,6 +150,7 @@ static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams
   for (int l = 0; l < PSPDE_MAXL; ++l) p.r_fwd[l] = pl.r_fwd[l];
   p.prof = g_prof;
   p.n_sets = pl.n_sets;
+  p.u_quirk = -1;
 }
 
 template <int T, bool BWD, int NB>

@@ -199,7 +199,7 @@ static int set_udiag(const pspde_cfg* cfg, const pspde_udiag* diag, RolloutParam
   if (diag->mode == 2 && (diag->nx1 < 1 || !(diag->dx > 0.f))) return fail(-8, "bad lookup-table geometry");
   if (diag->mode == 2 && (cfg->problem_flags & PSPDE_FLAG_DENSE_AB)) return fail(-8, "lookup diagnostic needs a diagonal problem");
   p.u_mode = diag->mode; p.u_tab = diag->table; p.u_nx1 = diag->nx1; p.u_d1 = diag->d1;
-  p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2;
+  p.u_xb = diag->xb; p.u_dx = diag->dx; p.uL2 = diag->uL2; p.u_quirk = diag->mode == 2 ? diag->quirk_path : -1;
   return 0;
 }
 

@@ -44,6 +44,7 @@ struct RolloutParams {
   const float* u_tab;
   int u_nx1, u_d1;
   float u_xb, u_dx;
+  int u_quirk;         // mode 2: global index of the path whose cell is shifted by -2 (problems.py:279), or -1
   float* uL2;          // per-path output
   double* stats_partial;  // [gridDim.x][4]
   float* grad_partial;    // [gridDim.x][n_theta_total]
@@ -468,6 +469,7 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
               const float xc = fminf(fmaxf(xn[i], -prm.u_xb), prm.u_xb - 2.0f * prm.u_dx);
               int cell = (int)floorf((xc + prm.u_xb) / prm.u_dx);
               cell = cell < 0 ? 0 : (cell >= prm.u_nx1 ? prm.u_nx1 - 1 : cell);
+              if ((int)kglob == prm.u_quirk) { cell -= 2; if (cell < 0) cell += prm.u_nx1; }    // `i[-1] -= 2`, problems.py:279
               us = __ldg(prm.u_tab + ((size_t)(2 * n) + (j < prm.u_d1 ? 0 : 1)) * prm.u_nx1 + cell);
             }
             const float du = -z - us;

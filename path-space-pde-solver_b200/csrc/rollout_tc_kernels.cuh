@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
                     const float xc = fminf(fmaxf(xn, -prm.u_xb), prm.u_xb - 2.0f * prm.u_dx);
                     int cell = (int)floorf((xc + prm.u_xb) / prm.u_dx);
                     cell = cell < 0 ? 0 : (cell >= prm.u_nx1 ? prm.u_nx1 - 1 : cell);
+                    if (prm.k_offset + k == prm.u_quirk) { cell -= 2; if (cell < 0) cell += prm.u_nx1; }   // `i[-1] -= 2`, problems.py:279
                     us = __ldg(prm.u_tab + ((size_t)(2 * n) + (j < prm.u_d1 ? 0 : 1)) * prm.u_nx1 + cell);
                   }
                   const float du = -z - us;

@@ -15,7 +15,7 @@ TIME_FIRST, TIME_NONE, TIME_LAST = 0, 1, 2
 NOISE_INJECT, NOISE_PHILOX = 0, 1
 DOMAIN_SPHERE, DOMAIN_BOX, DOMAIN_ANNULUS = 1, 2, 3
 H_ZERO, H_EXP_LINEAR, H_EXP_NONLINEAR, H_EXP_NONLINEAR_SIN, H_HELMHOLTZ, H_COMMITTOR = 0, 1, 2, 3, 4, 6
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpspde.so")
@@ -37,7 +37,7 @@ class pspde_cfg(ctypes.Structure):
 
 class pspde_udiag(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int32), ("nx1", ctypes.c_int32), ("d1", ctypes.c_int32), ("xb", ctypes.c_float),
-                ("dx", ctypes.c_float), ("table", ctypes.c_void_p), ("uL2", ctypes.c_void_p)]
+                ("dx", ctypes.c_float), ("table", ctypes.c_void_p), ("uL2", ctypes.c_void_p), ("quirk_path", ctypes.c_int32)]
 
 
 class pspde_elliptic(ctypes.Structure):

@@ -24,6 +24,7 @@ import torch as pt
 from . import _lib as L
 from . import dist
 from .function_space import DenseNet
+from .fused import on_own_device
 from .general_solver import DiffusionCall, DiffusionEngine, FusedDiffusion, GeneralSolver
 
 
@@ -48,6 +49,7 @@ class EllipticEngine(DiffusionEngine):
     def workspace_bytes(self, cfg):
         return int(self.lib.pspde_elliptic_workspace_bytes(ctypes.byref(cfg), ctypes.byref(self.ell)))
 
+    @on_own_device
     def forward(self, theta, X0, t0, xis, offset, N=None, outs=None):
         K = X0.shape[0]
         N = self.N if N is None else N
@@ -66,6 +68,7 @@ class EllipticEngine(DiffusionEngine):
                                          self._p(stats), self._p(self.workspace), self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
+    @on_own_device
     def backward(self, theta, X0, t0, xis, offset, c0, cE, cD, grad_out, N=None):
         K = X0.shape[0]
         N = self.N if N is None else N

@@ -15,6 +15,7 @@ autograd Functions that replace the body of the reference's training iteration (
 There is no CPU fallback: constructing an engine without the CUDA library raises.
 """
 import ctypes
+import functools
 import os
 
 import torch as pt
@@ -47,6 +48,16 @@ def rows_buffer_bytes(need, n_tiles, cap, free):
     return take if take >= max(tile, need // 10) else 0
 
 
+def on_own_device(method):
+    """libpspde launches on the CURRENT CUDA device and sizes its grids from it (api_common.h): make the engine's device
+    current for the duration of the call, so that device='cuda:1' works while another device is current."""
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with pt.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
+
+
 class RolloutEngine:
     def __init__(self, problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive=True, k_offset=0,
                  K_global=None, seed=42, device=None, want_X_N=True):
@@ -54,6 +65,12 @@ class RolloutEngine:
         self.device = pt.device("cuda", pt.cuda.current_device()) if device is None else pt.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("the fused rollout runs on CUDA devices only (got %s)" % self.device)
+        if self.device.index is None:
+            self.device = pt.device("cuda", pt.cuda.current_device())
+        self._setup(problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive, k_offset, K_global, seed, want_X_N)
+
+    @on_own_device
+    def _setup(self, problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive, k_offset, K_global, seed, want_X_N):
         self.d, self.N, self.K_local, self.k_offset = int(problem.d), int(N), int(K_local), int(k_offset)
         self.K_global = int(K_global if K_global is not None else K_local)
         self.net_id, self.dims, self.time_mode = net_id, list(dims), time_mode
@@ -147,8 +164,10 @@ class RolloutEngine:
         u.mode, u.nx1, u.d1 = int(desc["mode"]), int(desc.get("nx1", 0)), int(desc.get("d1", 0))
         u.xb, u.dx = float(desc.get("xb", 0.0)), float(desc.get("dx", 0.0))
         u.table, u.uL2 = self._utab.data_ptr(), self.uL2.data_ptr()
+        u.quirk_path = self.K_global - 1 if desc.get("quirk_last") else -1
         self.udiag = u
 
+    @on_own_device
     def forward(self, theta, y0, call, keep_rows=False):
         """keep_rows: training forward -- returns True if the operand rows were kept for `grad_from_rows`."""
         cfg = self.cfg(call)
@@ -164,6 +183,7 @@ class RolloutEngine:
             self.rows_serial += 1       # the buffer now holds THIS forward's rows
         return ck is not None
 
+    @on_own_device
     def grad_from_rows(self, theta, wY, call, grad_out):
         """dL/dtheta from the rows the last training forward kept (pspde_grad_from_fwd_ckpt)."""
         cfg = self.cfg(call)
@@ -173,6 +193,7 @@ class RolloutEngine:
                                                self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
+    @on_own_device
     def backward_detached(self, theta, wY, wZ, call, grad_out):
         cfg = self.cfg(call)
         rc = self.lib.pspde_rollout_bwd_detached(ctypes.byref(cfg), self._p(theta), self._p(self.pack),
@@ -181,6 +202,7 @@ class RolloutEngine:
                                                  self._stream())
         L.check(self.lib, rc)
 
+    @on_own_device
     def attached(self, theta, call, grad_out, y0=None, wY=None, wZ=None, wG=None):
         """wY = wZ = wG = None: relative entropy in one launch (constant cotangents 1 / K_global)."""
         cfg = self.cfg(call)
@@ -195,6 +217,7 @@ class RolloutEngine:
                                                   self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
+    @on_own_device
     def philox_dump(self, offset=0):
         """Increments the kernels generate for iteration `offset`, in the reference layout (K_local, d, N+1)."""
         out = pt.empty(self.N, self.K_local, self.d, dtype=pt.float32, device=self.device)

@@ -22,6 +22,7 @@ import torch as pt
 from . import _lib as L
 from . import dist
 from .function_space import DenseNet
+from .fused import on_own_device
 
 
 class DiffusionCall:
@@ -40,6 +41,12 @@ class DiffusionEngine:
         self.device = pt.device("cuda", pt.cuda.current_device()) if device is None else pt.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("the fused rollout runs on CUDA devices only (got %s)" % self.device)
+        if self.device.index is None:
+            self.device = pt.device("cuda", pt.cuda.current_device())
+        self._setup(problem, dims, K_local, N, delta_t, k_offset, seed)
+
+    @on_own_device
+    def _setup(self, problem, dims, K_local, N, delta_t, k_offset, seed):
         self.d, self.N, self.K_local, self.k_offset = int(problem.d), int(N), int(K_local), int(k_offset)
         self.dims, self.seed, self.T = list(dims), int(seed), float(getattr(problem, 'T', 1.0))
         self.dt = float(pt.tensor(delta_t, dtype=pt.float32))
@@ -78,6 +85,7 @@ class DiffusionEngine:
     def _stream(self):
         return ctypes.c_void_p(pt.cuda.current_stream(self.device).cuda_stream)
 
+    @on_own_device
     def sample(self, radius, offset):
         """X_0 uniform in the ball, t_0 uniform in [0, T) from Philox (solver.py:1045-1046, :1078)."""
         X0 = pt.empty(self.K_local, self.d, dtype=pt.float32, device=self.device)
@@ -88,6 +96,7 @@ class DiffusionEngine:
                                                           self._stream()))
         return X0, t0
 
+    @on_own_device
     def forward(self, theta, X0, t0, xis, offset, N=None, outs=None):
         K = X0.shape[0]
         N = self.N if N is None else N
@@ -100,6 +109,7 @@ class DiffusionEngine:
                                           self._p(self.workspace), self.workspace.numel(), self._stream())
         L.check(self.lib, rc)
 
+    @on_own_device
     def backward(self, theta, X0, t0, xis, offset, c0, cE, cD, grad_out, N=None):
         K = X0.shape[0]
         N = self.N if N is None else N
@@ -255,7 +265,7 @@ class GeneralSolver:
                 X = pt.randn(self.K, self.d)
                 X = R * X / pt.sqrt(pt.sum(X ** 2, 1)).unsqueeze(1) * (pt.rand(self.K).unsqueeze(1) ** (1 / self.d))
             t0 = pt.rand(self.K, 1) * self.problem.T
-            xis = pt.stack([pt.randn(self.K, self.d) for _ in range(self.N)])
+            xis = self._draw_increments_cpu(t0)
             return DiffusionCall(X[lo:hi].contiguous().to(self.device), t0[lo:hi, 0].contiguous().to(self.device),
                                  xis[:, lo:hi].contiguous().to(self.device), self._iteration)
         X0, t0 = eng.sample(float(self.problem.boundary_distance), self._iteration)
@@ -266,6 +276,24 @@ class GeneralSolver:
                 pt.rand(self.K, 1, device=self.device, generator=gen)
             X0 = X[lo:hi].contiguous()
         return DiffusionCall(X0, t0, None, self._iteration)
+
+    def _draw_increments_cpu(self, t0):
+        """'inject' only: one randn(K, d) per step AFTER the all-stopped check (solver.py:1093-1094 break before :1106), so
+        that a whole training loop consumes the CPU RNG stream exactly like the reference also when N * delta_t > T (every
+        path stops early).  On the unbounded domain the stop mask is the time test of :1131 alone; it is replayed here in
+        fp32 like the reference's (K, 1) tensor t_n.  Steps after the break get zeros, which the kernels never use."""
+        dt, T = pt.tensor(self.delta_t_np), self.problem.T
+        t = t0.squeeze(1).clone()
+        stopped, xis = pt.zeros(self.K, dtype=pt.bool), []
+        for n in range(self.N):
+            if int((~stopped).sum()) == 0:
+                break
+            xis.append(pt.randn(self.K, self.d))
+            new_sel = (t + dt) <= T
+            t = t + dt * (new_sel & ~stopped).float()
+            stopped = stopped | (~new_sel & ~stopped)
+        xis += [pt.zeros(self.K, self.d)] * (self.N - len(xis))
+        return pt.stack(xis)
 
     def gradient_descent(self, call):
         """fused rollout -> loss (solver.py:1063-1064, :1163) -> fused backward -> Adam (:1187-1188)."""
@@ -278,13 +306,15 @@ class GeneralSolver:
         r = pt.where(ok, r, pt.zeros_like(r))
         sums = pt.stack([(r * r).sum().detach(), call.stats[1], (~ok).sum().double()])
         loss_local = self.alpha[0] * (r * r).sum() / self.K                                 # :1163
-        rank, _ = dist.world(self.process_group)
-        if self.boundary_loss and rank == 0:                                               # :1063-1064
-            Kb = min(self.K_boundary, call.X0.shape[0])
-            Xb = call.X0[:Kb].contiguous()
-            tb = pt.full((Kb,), float(self.problem.T), dtype=pt.float32, device=self.device)
+        # terminal-condition term on the first K_boundary points of the GLOBAL batch (:1063-1064): every rank takes its
+        # slice of that prefix and contributes sum / K_boundary, so loss and gradient do not depend on the number of ranks
+        Kb = min(self.K_boundary, self.K)
+        nb = max(0, min(Kb, self._k_hi) - self._k_lo)
+        if self.boundary_loss and nb > 0:
+            Xb = call.X0[:nb].contiguous()
+            tb = pt.full((nb,), float(self.problem.T), dtype=pt.float32, device=self.device)
             Vb, _, _ = FusedDiffusion.apply(self._theta, eng, DiffusionCall(Xb, tb, None, call.offset), 0)
-            lb = self.alpha[1] * ((Vb.double() - self.problem.f(Xb).double()) ** 2).mean()
+            lb = self.alpha[1] * ((Vb.double() - self.problem.f(Xb).double()) ** 2).sum() / Kb
             loss_local = loss_local + lb
         loss_local.backward()
         self._ensure_grad_views()

@@ -22,13 +22,17 @@ def value_and_cotangents(method, Y, gX, Zsum, K_global, adaptive=True, group=Non
     with no such trajectory the formulas below are exactly solver.py:164-192."""
     D = (Y - gX).double()
     ok = pt.isfinite(D) & pt.isfinite(Zsum)
-    n_bad = all_reduce_sum_((~ok).sum().double().reshape(1), group)[0]
-    K = float(K_global) - n_bad
+    nb = (~ok).sum().double().reshape(1)
     D = pt.where(ok, D, pt.zeros_like(D))
     zero = pt.zeros_like(D)
+
+    def reduce(*sums):
+        """ONE all-reduce per iteration: the method's fp64 sums and the count of dropped trajectories together."""
+        s = all_reduce_sum_(pt.cat([pt.stack(list(sums)) if len(sums) > 1 else sums[0].reshape(-1), nb]), group)
+        return s[:-1], s[-1], float(K_global) - s[-1]
+
     if method in ("log-variance", "moment"):
-        s = stats[:2].clone() if stats is not None else pt.stack([D.sum(), (D * D).sum()])
-        all_reduce_sum_(s, group)
+        s, n_bad, K = reduce(stats[:2].clone() if stats is not None else pt.stack([D.sum(), (D * D).sum()]))
         mean = s[0] / K
         if method == "moment":                                       # :165-166
             w = pt.where(ok, D * (2.0 / K), zero).float()
@@ -37,17 +41,17 @@ def value_and_cotangents(method, Y, gX, Zsum, K_global, adaptive=True, group=Non
         return s[1] / K - mean * mean, w, None, -w, n_bad               # :167-168 (biased variance)
     if method == "variance":                                         # :171-172  pt.var (unbiased) of exp(-g + Y)
         E = pt.where(ok, pt.exp(D), zero)
-        s = all_reduce_sum_(pt.stack([E.sum(), (E * E).sum()]), group)
+        s, n_bad, K = reduce(E.sum(), (E * E).sum())
         mean = s[0] / K
         w = pt.where(ok, 2.0 * (E - mean) * E / (K - 1.0), zero).float()
         return (s[1] - K * mean * mean) / (K - 1.0), w, None, -w, n_bad
     if method == "cross_entropy":                                    # :183-186
         E = pt.where(ok, pt.exp(D) if adaptive else pt.exp(-gX.double()), zero)
-        s = all_reduce_sum_((pt.where(ok, Y.double(), zero) * E).sum().reshape(1), group)
+        s, n_bad, K = reduce((pt.where(ok, Y.double(), zero) * E).sum())
         return s[0] / K, (E / K).float(), None, (-pt.where(ok, Y.double(), zero) * E / K).float(), n_bad
     if method == "relative_entropy":                                 # :179-180 with a detached forward process
-        s = stats[2:3].clone() if stats is not None else pt.where(ok, Zsum.double() + gX.double(), zero).sum().reshape(1)
-        all_reduce_sum_(s, group)
+        s, n_bad, K = reduce(stats[2:3].clone() if stats is not None
+                             else pt.where(ok, Zsum.double() + gX.double(), zero).sum())
         w = pt.where(ok, pt.ones_like(D) / K, zero).float()
         return s[0] / K, None, w, w, n_bad
     raise NotImplementedError("loss_method %r is not implemented by the fused solver (supported: %s)"

@@ -262,12 +262,13 @@ class DoubleWell:
 
     def u_true_table(self, N, delta_t):
         """pspde_udiag mode 2 from the finite-difference reference (compute_reference_solution must have run).
-        The reference's `i[-1] -= 2` quirk on the last batch element (:279) is not reproduced."""
+        quirk_last: the reference shifts the table cell of the LAST batch element by -2 (`i[-1] -= 2`, :279); the kernels
+        reproduce it for the path with global index K - 1 (pspde_udiag.quirk_path)."""
         if not hasattr(self, "u"):
             return None
         rows = [min(int(np.ceil(n * delta_t / self.delta_t)), self.u.shape[0] - 1) for n in range(N)]
         tab = np.stack([np.stack([self.u[r], self.u[r]]) for r in rows]).astype(np.float32)
-        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d, xb=self.xb, dx=self.dx)
+        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d, xb=self.xb, dx=self.dx, quirk_last=True)
 
 
 class DoubleWell_multidim:
@@ -357,7 +358,8 @@ class DoubleWell_multidim:
         u2 = self.u_2 if self.d_2 > 0 else self.u
         rows = [min(int(np.ceil(n * delta_t / self.delta_t)), self.u.shape[0] - 1) for n in range(N)]
         tab = np.stack([np.stack([self.u[r], u2[r]]) for r in rows]).astype(np.float32)
-        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d_1, xb=self.xb, dx=self.dx)
+        return dict(mode=2, table=pt.from_numpy(tab), nx1=self.u.shape[1], d1=self.d_1, xb=self.xb, dx=self.dx,
+                    quirk_last=True)                       # `i[-1] -= 2` in u_true_1 / u_true_2 (:401, :464)
 
 
 class HeatEquation:

@@ -13,6 +13,8 @@ Kept from the reference: the constructor signature (solver.py:20-25), the mutabl
     process_group               torch.distributed group; K is the GLOBAL batch, sharded over its ranks
 There is no CPU fallback; options of the reference that are off the fused path raise NotImplementedError.
 """
+import json
+import os
 import time
 from datetime import date
 
@@ -284,8 +286,8 @@ class Solver:
         if attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0:
             loss_local = FusedRolloutAttached.apply(self._theta, eng, call)       # constant cotangents: one launch
             loss_local.backward()
-            loss = dist.all_reduce_sum_(loss_local.detach().double().reshape(1), self.process_group)[0]
-            n_bad = dist.all_reduce_sum_(call.stats[3:4].clone(), self.process_group)[0]
+            loss, n_bad = dist.all_reduce_sum_(pt.cat([loss_local.detach().double().reshape(1), call.stats[3:4]]),
+                                               self.process_group)
         else:
             fn = FusedRolloutAttachedGeneral if attached else FusedRollout
             Y, gX, Zsum = fn.apply(self._theta, y0, eng, call)
@@ -358,6 +360,26 @@ class Solver:
             if self.early_stopping_time is not None and l > self.early_stopping_time:
                 if np.std(self.u_L2_loss[-self.early_stopping_time:]) / self.u_L2_loss[-1] < 0.02:
                     break
+        if self.save_results is True:                             # solver.py:556-557
+            self.save_logs()
+
+    def save_logs(self, model_name='model'):
+        """Run parameters, logs and the parameters of every trainable module as JSON under logs/ (solver.py:295-311: same
+        keys and file naming; the modules stay on the device -- their flat-buffer views must not be re-homed)."""
+        logs = dict(name=self.name, date=self.date, d=self.d, T=self.T, seed=self.seed, delta_t=self.delta_t_np, N=self.N,
+                    lr=self.lr, K=self.K, loss_method=self.loss_method, learn_Y_0=self.learn_Y_0,
+                    adaptive_forward_process=self.adaptive_forward_process, Y_0_log=self.Y_0_log, loss_log=self.loss_log,
+                    u_L2_loss=self.u_L2_loss,
+                    Phis_state_dict=[{k: v.detach().cpu().tolist() for k, v in z.state_dict().items()} for z in self.Phis])
+        os.makedirs('logs', exist_ok=True)
+        stem = 'logs/%s_%s_%s' % (model_name, self.name, self.date)
+        path_name, i = stem + '.json', 1
+        while os.path.isfile(path_name):
+            i += 1
+            path_name = '%s_%d.json' % (stem, i)
+        with open(path_name, 'w') as f:
+            json.dump(logs, f, indent=2)
+        return path_name
 
     # ------------------------------------------------------------------ host-side evaluation of the control
     def Z_n_(self, X, n):

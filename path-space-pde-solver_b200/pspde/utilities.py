@@ -44,7 +44,9 @@ def do_importance_sampling_me(problem, model, K, control='approx', simulate_naiv
     Y, gX, F, X = pt.empty(Kl, **f32), pt.empty(Kl, **f32), pt.empty(Kl, **f32), pt.empty(Kl, d, **f32)
     ws = pt.empty(max(int(lib.pspde_workspace_bytes_fwd(ctypes.byref(cfg))), 4096), dtype=pt.uint8, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = lib.pspde_importance_sampling(ctypes.byref(cfg), p(model._theta.detach()), p(eng.pack), p(eng.x0), xi_ptr,
+    # every path starts from problem.X_0 (utilities.py:302), also when training uses random_X_0 (eng.x0 is then per path)
+    x0 = problem.X_0.detach().to(dev, pt.float32).contiguous()
+    rc = lib.pspde_importance_sampling(ctypes.byref(cfg), p(model._theta.detach()), p(eng.pack), p(x0), xi_ptr,
                                        p(t_index), ctypes.c_float(float(model.delta_t)), p(X), p(Y), p(gX), p(F), p(ws),
                                        ws.numel(), ctypes.c_void_p(pt.cuda.current_stream(dev).cuda_stream))
     L.check(lib, rc)

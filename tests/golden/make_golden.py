@@ -48,12 +48,17 @@ def make_ref_problem(kind, d, **kw):
 
 
 def run_hjb_case(tag, kind, d, pkw, K, delta_t, net, time_approx, loss_method, detach_forward,
-                 adaptive=True, learn_Y_0=False, y0_init=None, xi_seed=7, store_xi=True, lr=1e-3):
-    """One iteration (L=1) of the reference Solver with injected xi; capture everything."""
+                 adaptive=True, learn_Y_0=False, y0_init=None, xi_seed=7, store_xi=True, lr=1e-3, u_l2=None):
+    """One iteration (L=1) of the reference Solver with injected xi; capture everything.
+    u_l2: None, or a dict (possibly empty) of keyword arguments for the problem's compute_reference_solution[_2] -- the
+    Solver then runs with u_l2_error_flag=True and its u_L2_loss entry (solver.py:491-494, :515) is stored."""
     problem = make_ref_problem(kind, d, **pkw)
+    if u_l2 is not None and kind == "dwm":
+        problem.compute_reference_solution(**u_l2)
+        problem.compute_reference_solution_2(**u_l2)
     S = RS.Solver(tag, problem, lr=lr, L=1, K=K, delta_t=delta_t, loss_method=loss_method,
                   time_approx=time_approx, learn_Y_0=learn_Y_0, adaptive_forward_process=adaptive,
-                  detach_forward=detach_forward, early_stopping_time=None, u_l2_error_flag=False,
+                  detach_forward=detach_forward, early_stopping_time=None, u_l2_error_flag=u_l2 is not None,
                   verbose=False, seed=42)
     if net == "densenet" and time_approx == "inner":
         S.z_n = RF.DenseNet(d_in=d + 1, d_out=d, lr=lr, seed=42)
@@ -123,6 +128,11 @@ def run_hjb_case(tag, kind, d, pkw, K, delta_t, net, time_approx, loss_method, d
         out["B"] = problem.B.numpy()
     if store_xi:
         out["xi"] = xi.numpy()
+    if u_l2 is not None:
+        out["u_L2_loss"] = np.float64(S.u_L2_loss[0])
+        out["ref_kw_keys"] = np.array(list(u_l2.keys()))
+        out["ref_kw_vals"] = np.array([float(v) for v in u_l2.values()])
+        print("%-28s u_L2_loss=%.7e" % (tag, S.u_L2_loss[0]))
     np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
 
 
@@ -329,6 +339,17 @@ def main():
                  "inner", "moment", False)
     run_hjb_case("hjb_lqgc_d10_outer_ce_att", "lqgc", 10, dict(T=0.5), 32, 0.05, "densenet", "outer",
                  "cross_entropy", False)
+    # u_L2 diagnostic (u_l2_error_flag=True, the reference default): solver.py:491-494 with problems.py:51-53 (LLGC),
+    # :169-171 (LQGC on its OWN Riccati grid delta_t = 0.025 under a solver step of 0.05), :398-404 / :463-476 (double-well
+    # finite-difference tables, including the `i[-1] -= 2` element)
+    run_hjb_case("hjb_llgc_d10_dense_lv_ul2", "llgc", 10, dict(T=0.5), 32, 0.05, "densenet", "inner",
+                 "log-variance", True, u_l2={})
+    run_hjb_case("hjb_lqgc_d10_dense_lv_ul2", "lqgc", 10, dict(T=1, delta_t=0.025), 32, 0.05, "densenet", "inner",
+                 "log-variance", True, u_l2={})
+    run_hjb_case("hjb_dwm_d4_mlp_lv_ul2", "dwm", 4, dict(d_1=2, d_2=2, T=0.3, eta=3, kappa=5), 32, 0.005,
+                 "mlp_tanh", "inner", "log-variance", True, lr=0.05, u_l2=dict(delta_t=0.005, nx=400))
+    run_hjb_case("hjb_dwm_d4_mlp_re_ul2", "dwm", 4, dict(d_1=2, d_2=2, T=0.3, eta=3, kappa=5), 32, 0.005,
+                 "mlp_tanh", "inner", "relative_entropy", False, lr=0.05, u_l2=dict(delta_t=0.005, nx=400))
     if only:
         return
     run_diffusion_case("diff_heat_d10_small", 10, 64, 50, 25, 1e-3, (24, 24), full=True)

@@ -252,6 +252,7 @@ def test_u_l2_diagnostic(run, kind):
     u.mode, u.nx1, u.d1 = desc["mode"], desc.get("nx1", 0), desc.get("d1", 0)
     u.xb, u.dx = desc.get("xb", 0.0), desc.get("dx", 0.0)
     u.table, u.uL2 = tab.ctypes.data, uL2.ctypes.data
+    u.quirk_path = K - 1 if desc.get("quirk_last") else -1
     Y = np.zeros(K, np.float32)
     ws = np.zeros(1 << 14, np.float64)
     x0 = prob.X_0.numpy().astype(np.float32)
@@ -271,8 +272,8 @@ def test_u_l2_diagnostic(run, kind):
             ut = pt.tensor(np.asarray(prob.u_true(X, n * dt))).t().float()
             ref += ((-Z - ut) ** 2).sum(1) * dt
     r = ref.numpy()
-    if kind == "dwm":      # the reference's `i[-1] -= 2` quirk moves the LAST batch element's cell; compare the others
-        assert relerr(uL2[:-1], r[:-1]) < 2e-3
+    if kind == "dwm":      # including the LAST batch element, whose cell the reference moves by `i[-1] -= 2` (quirk_path)
+        assert relerr(uL2, r) < 2e-3
     else:
         assert relerr(uL2, r) < 1e-4
 

@@ -901,3 +901,43 @@ def test_tc_forward_u_l2_diagnostic_matches_fma_forward(monkeypatch, kind, d, K)
     assert float(outs["simt"][0].min()) > 0
     assert relerr(outs["tc"][0].cpu().numpy(), outs["simt"][0].cpu().numpy()) < TOL
     assert relerr(outs["tc"][1].cpu().numpy(), outs["simt"][1].cpu().numpy()) < TOL
+
+
+UL2_TAGS = ["hjb_llgc_d10_dense_lv_ul2", "hjb_lqgc_d10_dense_lv_ul2", "hjb_dwm_d4_mlp_lv_ul2", "hjb_dwm_d4_mlp_re_ul2"]
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("tag", UL2_TAGS)
+def test_u_l2_diagnostic_matches_reference(tag, path, monkeypatch):
+    """u_l2_error_flag=True (the reference default): Solver.u_L2_loss of one iteration on the reference's own (theta, xi)
+    against the value the UNMODIFIED reference logged (solver.py:491-494, :515; tests/golden/make_golden.py) -- LLGC
+    (problems.py:51-53), LQGC on its own Riccati grid (:169-171), double-well finite-difference tables including the
+    `i[-1] -= 2` element (:398-404, :463-476) -- through the tcgen05 forward kernel's DIAG instantiation and through the FMA
+    kernel; the relative-entropy case goes through the attached kernel's forward sweep (one launch)."""
+    import pspde
+    from pspde.fused import Call
+    g = load_golden(tag)
+    monkeypatch.setenv("PSPDE_FWD_PATH", path)
+    d = g["d"]
+    cls = {"llgc": pspde.LLGC, "lqgc": pspde.LQGC, "dwm": pspde.DoubleWell_multidim}[g["kind"]]
+    prob = cls(d=d, device="cuda", **g["pkw"])
+    if g["kind"] == "dwm":
+        kw = {str(k): (int(v) if float(v).is_integer() else float(v)) for k, v in zip(g["ref_kw_keys"], g["ref_kw_vals"])}
+        prob.compute_reference_solution(**kw)
+        prob.compute_reference_solution_2(**kw)
+    S = pspde.Solver(tag, prob, lr=0.0, L=1, K=g["K"], delta_t=g["delta_t"], loss_method=g["loss_method"],
+                     time_approx=g["time_approx"], detach_forward=g["detach_forward"], early_stopping_time=None,
+                     u_l2_error_flag=True, verbose=False, noise="inject")
+    if g["net"] == "densenet":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=0.0, seed=42)
+        S.update_Phis()
+    with pt.no_grad():
+        S._theta.copy_(pt.tensor(g["theta"]))
+    res = S.gradient_descent(Call(offset=0, xi=pt.tensor(g["xi"]).cuda()))
+    pt.cuda.synchronize()
+    assert S._u_l2_on
+    loss, n_bad, u_l2 = res.tolist()
+    assert n_bad == 0 and abs(loss - g["loss"]) <= 2e-5 * abs(g["loss"]) + 4 * 6e-8 * float(((g["Y_N"] - g["gX"]) ** 2).mean())
+    # table lookups: a state within rounding of a cell face may land in the neighbouring cell (dwm): 1e-4; closed forms: 1e-5
+    tol = 1e-4 if g["kind"] == "dwm" else TOL
+    assert abs(u_l2 - g["u_L2_loss"]) < tol * g["u_L2_loss"], (u_l2, g["u_L2_loss"])
