@@ -79,6 +79,11 @@ typedef struct pspde_cfg {
    * being the increment that drives step n.  Reference layout (K, d, N+1) with slice n+1 driving step n
    * (solver.py:472): pass xi + 1 and strides (d*(N+1), N+1, 1). */
   int64_t xi_stride_k, xi_stride_j, xi_stride_n;
+  /* Blow-up bound: a trajectory whose |D| = |Y_N - g(X_N)| reaches d_abs_max is dropped from the batch exactly like one
+   * with a non-finite D (counted in stats[3], Y_N written as NaN, zero cotangent).  The untrained relu(.)^2 feedback
+   * control drives about one path in 10^5 to |D| ~ 10^20 .. 10^30 -- finite, but one such value makes the log-variance
+   * loss 10^34 and its gradient inf (the reference returns NaN for the whole batch from then on).  0 = off. */
+  float   d_abs_max;
 } pspde_cfg;
 
 int          pspde_abi_version(void);

@@ -42,7 +42,7 @@ static inline const char* pspde_peek_error() {
 
 using namespace pspde;
 
-static_assert(sizeof(pspde_cfg) == 112, "pspde_cfg layout is part of the ABI (mirrored by pspde/_lib.py)");
+static_assert(sizeof(pspde_cfg) == 120, "pspde_cfg layout is part of the ABI (mirrored by pspde/_lib.py)");
 
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
@@ -151,6 +151,7 @@ static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams
   p.prof = g_prof;
   p.n_sets = pl.n_sets;
   p.u_quirk = -1;
+  p.d_abs_max = c->d_abs_max > 0.f ? c->d_abs_max : INFINITY;
 }
 
 template <int T, bool BWD, int NB>

@@ -45,6 +45,8 @@ struct RolloutParams {
   int u_nx1, u_d1;
   float u_xb, u_dx;
   int u_quirk;         // mode 2: global index of the path whose cell is shifted by -2 (problems.py:279), or -1
+  float d_abs_max;     // a trajectory with |D| = |Y_N - g(X_N)| >= d_abs_max counts as blown up: dropped like a non-finite one
+                       // (pspde_cfg::d_abs_max; +inf when the caller leaves it off)
   float* uL2;          // per-path output
   double* stats_partial;  // [gridDim.x][4]
   float* grad_partial;    // [gridDim.x][n_theta_total]
@@ -65,6 +67,14 @@ struct RolloutParams {
                           //    noise), so the gradient kernel regenerates it: 38 % less checkpoint traffic at the C2 shape
   unsigned long long* prof;  // debug: per-phase clock64() totals of CTA 0 (16 slots) or nullptr
 };
+
+// A trajectory stays in the batch if its D = Y_N - g(X_N) and Z_sum are finite and |D| is below the caller's blow-up bound.
+// A dropped trajectory's Y_N is written as NaN so that the host-side mask (isfinite(Y_N - gX), pspde/losses.py) agrees with
+// the statistics the kernel accumulated.
+__device__ __forceinline__ bool path_kept(double D, float ZS, float d_abs_max) {
+  return isfinite(D) && isfinite((double)ZS) && fabs(D) < (double)d_abs_max;
+}
+__device__ __forceinline__ float dropped_mark(float Y) { return isfinite(Y) ? NAN : Y; }
 
 struct SmemLayout { int w, act, z, xi, delta, lam, scal, prob, red, zero, total; };
 
@@ -772,13 +782,14 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
         const int k = tile * P + tid;
         if (k < prm.K_local) {
           const float Y = sY[tid], G = sG[tid], ZS = sZs[tid];
-          if (prm.Y_N) prm.Y_N[k] = Y;
+          const double D = (double)Y - (double)G;
+          const bool keep = path_kept(D, ZS, prm.d_abs_max);
+          if (prm.Y_N) prm.Y_N[k] = keep ? Y : dropped_mark(Y);
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
           if (prm.Fint) prm.Fint[k] = sY[6 * P + tid];
           if (prm.uL2) prm.uL2[k] = sY[7 * P + tid];
-          const double D = (double)Y - (double)G;
-          if (isfinite(D) && isfinite((double)ZS)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)G; }
+          if (keep) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)G; }
           else s3 = 1.0;
         }
       }
@@ -893,10 +904,11 @@ __global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutPar
           const float G = sG[tid], ZS = sZs[tid];
           if (prm.gX) prm.gX[k] = G;
           if (prm.Zsum) prm.Zsum[k] = ZS;
-          if (prm.Y_N) prm.Y_N[k] = sY[tid];
-          if (prm.uL2) prm.uL2[k] = sY[7 * P + tid];          // u_L2 diagnostic of the forward sweep (solver.py:491-494)
           const double v = (double)ZS + (double)G, D = (double)sY[tid] - (double)G;
-          if (isfinite(v) && isfinite(D)) s2 = v;
+          const bool keep = isfinite(v) && path_kept(D, ZS, prm.d_abs_max);
+          if (prm.Y_N) prm.Y_N[k] = keep ? sY[tid] : dropped_mark(sY[tid]);
+          if (prm.uL2) prm.uL2[k] = sY[7 * P + tid];          // u_L2 diagnostic of the forward sweep (solver.py:491-494)
+          if (keep) s2 = v;
           else { s3 = 1.0; swY[tid] = 0.f; swZ[tid] = 0.f; swG[tid] = 0.f; }   // dropped from the batch and counted
         }
       }

@@ -448,12 +448,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
           if (DIAG) UL += sExch[4 * kTcP * (kTcTPP - 1) + kTcP * (r - 1) + p];
         }
         if (DIAG && prm.uL2) prm.uL2[k] = UL;
-        if (prm.Y_N) prm.Y_N[k] = Y;
+        const double D = (double)Y - (double)Gv;
+        const bool keep = path_kept(D, ZS, prm.d_abs_max);
+        if (prm.Y_N) prm.Y_N[k] = keep ? Y : dropped_mark(Y);
         if (prm.gX) prm.gX[k] = Gv;
         if (prm.Zsum) prm.Zsum[k] = ZS;
         if (prm.Fint) prm.Fint[k] = FI;
-        const double D = (double)Y - (double)Gv;
-        if (isfinite(D) && isfinite((double)ZS)) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)Gv; }
+        if (keep) { s0 = D; s1 = D * D; s2 = (double)ZS + (double)Gv; }
         else s3 = 1.0;
       }
       s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); s3 = warp_sum_d(s3);

@@ -32,6 +32,7 @@ class pspde_cfg(ctypes.Structure):
         ("x0_per_path", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint32), ("n_sets", ctypes.c_int32),
         ("xi_stride_k", ctypes.c_int64), ("xi_stride_j", ctypes.c_int64), ("xi_stride_n", ctypes.c_int64),
+        ("d_abs_max", ctypes.c_float),
     ]
 
 
@@ -124,7 +125,8 @@ def check(lib, rc):
 
 
 def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=True, k_offset=0, problem_flags=0,
-             noise_mode=NOISE_PHILOX, seed=0, offset=0, x0_per_path=False, xi_strides=(0, 0, 0), n_sets=0):
+             noise_mode=NOISE_PHILOX, seed=0, offset=0, x0_per_path=False, xi_strides=(0, 0, 0), n_sets=0,
+             d_abs_max=0.0):
     c = pspde_cfg()
     c.K_local, c.k_offset, c.d, c.N = int(K_local), int(k_offset), int(d), int(N)
     c.dt = float(dt)
@@ -139,6 +141,7 @@ def make_cfg(K_local, d, N, dt, problem_id, net_id, dims, time_mode, adaptive=Tr
     c.seed, c.offset = int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 32 - 1)
     c.n_sets = int(n_sets)
     c.xi_stride_k, c.xi_stride_j, c.xi_stride_n = (int(s) for s in xi_strides)
+    c.d_abs_max = float(d_abs_max)
     return c
 
 

@@ -60,8 +60,9 @@ def on_own_device(method):
 
 class RolloutEngine:
     def __init__(self, problem, net_id, dims, time_mode, K_local, N, delta_t, adaptive=True, k_offset=0,
-                 K_global=None, seed=42, device=None, want_X_N=True):
+                 K_global=None, seed=42, device=None, want_X_N=True, blowup_bound=0.0):
         self.lib = L.load()
+        self.blowup_bound = float(blowup_bound)     # pspde_cfg::d_abs_max of the training rollouts (0: off)
         self.device = pt.device("cuda", pt.cuda.current_device()) if device is None else pt.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("the fused rollout runs on CUDA devices only (got %s)" % self.device)
@@ -143,7 +144,7 @@ class RolloutEngine:
         return L.make_cfg(self.K_local, self.d, self.N, self.dt, self.problem_id, self.net_id, self.dims,
                           self.time_mode, adaptive=self.adaptive, k_offset=self.k_offset, problem_flags=self.flags,
                           noise_mode=noise, seed=self.seed, offset=call.offset, x0_per_path=self.x0_per_path,
-                          xi_strides=strides)
+                          xi_strides=strides, d_abs_max=self.blowup_bound)
 
     @staticmethod
     def _p(t):

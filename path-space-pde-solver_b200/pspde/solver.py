@@ -9,6 +9,10 @@ Kept from the reference: the constructor signature (solver.py:20-25), the mutabl
     noise='philox' | 'inject'   in-kernel counter-based noise (default) or the reference's CPU draw
                                 xi = randn(K, d, N+1) (:381) pushed to the device (parity mode: identical
                                 torch RNG stream, hence identical trajectories to the reference)
+    blowup_bound=1e6            trajectories with |Y_N - g(X_N)| >= blowup_bound are dropped from the batch like non-finite
+                                ones (zero cotangent, counted in nonfinite_log); None / 0 switches it off.  At large K
+                                the untrained control sends a few paths to |D| ~ 1e20: finite, but the loss becomes
+                                1e34 and the gradient inf (the reference then trains on NaN)
     device                      CUDA device (default: current)
     process_group               torch.distributed group; K is the GLOBAL batch, sharded over its ranks
 There is no CPU fallback; options of the reference that are off the fused path raise NotImplementedError.
@@ -35,7 +39,8 @@ class Solver:
                  early_stopping_time=10000, random_X_0=False, compute_gradient_variance=0,
                  IS_variance_K=0, IS_variance_iter=1, metastability_logs=None, print_every=100,
                  plot_trajectories=None, seed=42, save_results=False, u_l2_error_flag=True, log_gradient=False,
-                 burgers_drift=False, verbose=True, noise='philox', device=None, process_group=None):
+                 burgers_drift=False, verbose=True, noise='philox', device=None, process_group=None,
+                 blowup_bound=1e6):
         self.problem, self.name = problem, name
         self.date = date.today().strftime('%Y-%m-%d')
         self.d, self.T, self.X_0 = problem.d, problem.T, problem.X_0
@@ -65,6 +70,7 @@ class Solver:
         self.metastability_logs, self.plot_trajectories, self.log_gradient = (
             metastability_logs, plot_trajectories, log_gradient)
         self.noise, self.process_group = noise, process_group
+        self.blowup_bound = blowup_bound
         if noise not in ('philox', 'inject'):
             raise ValueError("noise must be 'philox' or 'inject'")
 
@@ -250,7 +256,7 @@ class Solver:
             tm = L.TIME_NONE if self.time_approx == 'outer' else L.TIME_FIRST
             self._engine = RolloutEngine(self.problem, self._net_id, self._dims, tm, hi - lo, self.N, self.delta_t_np,
                                          adaptive=self.adaptive_forward_process, k_offset=lo, K_global=self.K,
-                                         seed=self.seed, device=self.device)
+                                         seed=self.seed, device=self.device, blowup_bound=self.blowup_bound or 0.0)
             self._u_l2_on = False
             if self.u_l2_error_flag and hasattr(self.problem, 'u_true_table'):
                 desc = self.problem.u_true_table(self.N, self.delta_t_np)
@@ -307,7 +313,8 @@ class Solver:
         u_l2 = pt.full((), float('nan'), dtype=pt.float64, device=self.device)
         if self._u_l2_on:
             u = eng.uL2.double()                               # filled by the forward launch of this iteration
-            u_l2 = dist.all_reduce_sum_(pt.where(pt.isfinite(u), u, pt.zeros_like(u)).sum().reshape(1),
+            kept = pt.isfinite(u) & pt.isfinite(eng.Y_N)       # trajectories dropped from the batch carry Y_N = NaN
+            u_l2 = dist.all_reduce_sum_(pt.where(kept, u, pt.zeros_like(u)).sum().reshape(1),
                                         self.process_group)[0] / self.K
         return pt.stack([loss.double(), n_bad.double(), u_l2])
 

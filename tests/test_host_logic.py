@@ -27,7 +27,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     bound = _lib.bind(_lib.LIB_PATH)                     # no compute calls without a GPU
     assert bound.pspde_abi_version() == _lib.ABI_VERSION
-    assert ctypes.sizeof(_lib.pspde_cfg) == 112      # static_assert-ed in csrc/api_common.h
+    assert ctypes.sizeof(_lib.pspde_cfg) == 120      # static_assert-ed in csrc/api_common.h
 
 
 def test_product_path_fails_loudly_without_cuda():
