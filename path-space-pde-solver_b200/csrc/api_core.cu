@@ -2,6 +2,7 @@
 #include "api_common.h"
 #include "rollout_tc_kernels.cuh"
 #include "grad_kernels.cuh"
+#include "grad_tc2_kernels.cuh"
 #include "grad_tc_kernels.cuh"
 
 thread_local char g_err[512] = "";
@@ -58,8 +59,8 @@ struct CkptPlan {
 // for the shape class it covers, else the FP32-FMA kernel (grad_kernels.cuh).  PSPDE_GRAD_PATH=simt forces the FMA kernel
 // (A/B tests), PSPDE_GRAD_PATH=tc makes an ineligible configuration an error.  `grid` = CTAs (<= n_ts; every CTA writes
 // its own gradient partial).
-static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, long long n_ts, void* stream, bool* used_tc) {
-  *used_tc = false;
+static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int grid, long long n_ts, void* stream, int* used_tc) {
+  *used_tc = 0;
   if (n_ts < 1 || n_ts > 0x3fffffffLL) return fail(-6, "bad number of (tile, step) pairs for one gradient launch (%lld)", n_ts);
 #if !defined(PSPDE_EMULATE)
   GradTcGeom gt;
@@ -67,8 +68,6 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
   const bool eligible = grad_tc_geom(pl.g, cfg->d, p.ckpt_s0, gt);
   if (path && !strcmp(path, "tc") && !eligible) return fail(-6, "configuration is outside the tensor-core gradient kernel's shape class");
   if (eligible && !(path && !strcmp(path, "simt"))) {
-    if (cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt.total) != cudaSuccess)
-      return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", gt.total);
     int flush_stages = kGtFlushStages;
     if (const char* e = getenv("PSPDE_GRAD_FLUSH_STAGES")) { const int v = atoi(e); if (v >= 1) flush_stages = v; }
     CUtensorMap tmap;
@@ -76,10 +75,23 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
     if (!p.ckpt_zeta && gt.act_rows > 256) return fail(-6, "activation rows exceed one TMA box");
     if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap, p.ckpt_zeta ? 0 : gt.act_rows))
       return fail(-11, "cuTensorMapEncodeTiled failed for the checkpoint buffer");
+    GradTc2Geom g2;
+    // zeta from the Philox key: the kernel with the hidden cotangents on the tensor cores (PSPDE_GRAD_PATH=tc1: the older one)
+    if (!p.ckpt_zeta && !(path && !strcmp(path, "tc1")) && grad_tc2_geom(pl.g, p.ckpt_s0, g2)) {
+      if (cudaFuncSetAttribute(grad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2.total) != cudaSuccess)
+        return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", g2.total);
+      grad_tc2_kernel<<<grid, kG2Threads, g2.total, (cudaStream_t)stream>>>(tmap, p, g2, (int)n_ts, flush_stages);
+      g_launches++;
+      if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel (tc2) launch failed: %s", e);
+      *used_tc = 2;
+      return 0;
+    }
+    if (cudaFuncSetAttribute(grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt.total) != cudaSuccess)
+      return fail(-11, "cudaFuncSetAttribute(%u B smem) failed", gt.total);
     grad_tc_kernel<<<grid, kGtThreads, gt.total, (cudaStream_t)stream>>>(tmap, p, gt, (int)n_ts, flush_stages);
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "tensor-core gradient kernel launch failed: %s", e);
-    *used_tc = true;
+    *used_tc = 1;
     return 0;
   }
 #else
@@ -103,7 +115,7 @@ static size_t grad_part_floats(const pspde_cfg* cfg, const Plan& pl, int s0) {
   return n;
 }
 
-static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int nparts, bool used_tc, float* grad_theta, void* stream) {
+static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int nparts, int used_tc, float* grad_theta, void* stream) {
   const int n = pl.n_theta_total;
 #if !defined(PSPDE_EMULATE)
   if (used_tc) {
@@ -111,7 +123,13 @@ static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
     grad_tc_geom(pl.g, cfg->d, p.ckpt_s0, gt);
     if (pspde_memset0(grad_theta, (size_t)n * sizeof(float), stream)) return fail(-12, "memset of grad_theta failed");
     const int per = 2 * 128 * gt.nB;
-    reduce_grad_tc_kernel<<<(per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pl.g, gt, p.grad_partial, nparts, grad_theta);
+    if (used_tc == 2) {
+      GradTc2Geom g2;
+      grad_tc2_geom(pl.g, p.ckpt_s0, g2);
+      reduce_grad_tc2_kernel<<<(per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pl.g, g2, p.grad_partial, nparts, grad_theta);
+    } else {
+      reduce_grad_tc_kernel<<<(per + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pl.g, gt, p.grad_partial, nparts, grad_theta);
+    }
     g_launches++;
     if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad_tc launch failed: %s", e);
     return 0;
@@ -176,7 +194,7 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
 // tiles [t_begin, n_tiles128) of the checkpointed detached backward: per wave, the tensor-core rollout that writes the operand
 // rows (cotangents p.wY / p.wZ applied) into p.ckpt, then the gradient kernel; accumulates into p.grad_partial
 static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, const TcGeom& tg, const CkptPlan& cp, int t_begin,
-                     void* stream, bool* used_tc) {
+                     void* stream, int* used_tc) {
   p.ckpt_cols = cp.cols; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0; p.ckpt_zeta = zeta_in_ckpt(cfg, p.wZ);
   const int sms = pspde_sm_count();
   for (int t0 = t_begin; t0 < cp.n_tiles128; t0 += cp.wave) {
@@ -343,7 +361,7 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
     if (eligible && !(path && !strcmp(path, "simt"))) {
       if (pspde_memset0(p.grad_partial, cp.grad_bytes, stream)) return fail(-12, "memset of the gradient partials failed");
       p.ckpt = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes + cp.grad_bytes);
-      bool used_tc = false;
+      int used_tc = false;
       rc = run_waves(cfg, pl, p, tg, cp, 0, stream, &used_tc);
       if (rc) return rc;
       return reduce_grad(cfg, pl, p, cp.grid_b, used_tc, grad_theta, stream);
@@ -382,7 +400,7 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
   p.ckpt = const_cast<float*>(ckpt); p.ckpt_cols = 2 * s0 + 64; p.ckpt_s0 = s0; p.ckpt_zeta = 1;
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
-  bool used_tc = false;
+  int used_tc = false;
   rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);
   if (rc) return rc;
   return reduce_grad(cfg, pl, p, grid, used_tc, grad_theta, stream);
@@ -427,7 +445,7 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
   p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0;
   p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr);
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
-  bool used_tc = false;
+  int used_tc = false;
   rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);
   if (rc) return rc;
   if (!used_tc) return fail(-13, "internal: the forward checkpoint needs the tensor-core gradient kernel");

@@ -1,0 +1,459 @@
+// grad_tc2_kernels.cuh -- gradient accumulation from the checkpoint rows with EVERYTHING on the tensor cores: the weight
+// gradient and the hidden cotangents (reference: loss.backward(), solver.py:221, for detach_forward=True).
+//
+// Contract (same as grad_tc_kernel): a streaming kernel over (trajectory, step) samples,
+//     dtheta = sum_samples J_theta Z(a0)' zeta,      zeta = wY[path] sqrt(dt) xi[path, step]   (adaptive process, no dL/dZ_sum)
+// The checkpoint holds, per (tile, step), one row of 128 paths for every column of [a0 | h1 | h2] (RolloutParams::ckpt with
+// ckpt_zeta == 0); zeta is regenerated from the Philox key.  A stage is 32 samples.  Per stage:
+//     delta_pre' [64 x 32]  = W2h [64 x s0] . zeta' [s0 x 32]            tcgen05 SS, M = 64 (hidden slot), N = 32 (sample), K = zeta column
+//     delta_2 = delta_pre[h2 rows] * act'(h2)                            4 epilogue warps (TMEM -> registers -> TMEM + shared)
+//     delta_pre'[h1 rows] += W1h [32 x 32] . delta_2' [32 x 32]          tcgen05 SS
+//     delta_1 = delta_pre[h1 rows] * act'(h1)
+//     D0 [zeta col x act col]  += zeta'  . act      M = 128, N = s0 + 64, K = sample:  A = zeta' in TENSOR MEMORY, B = act rows (TMA, SW128)
+//     D1 [delta row x act col] += delta' . act      M = 64,  N = s0 + 32, K = sample:  A = [delta_2 | delta_1]' in tensor memory
+// Every product is 3xTF32 (tc_sm100.cuh).  Compared with grad_tc_kernel (FP32-FMA hidden cotangents, SS-mode weight gradient with
+// all operands in shared memory) the FMA pipe carries only Philox and the epilogues, and the weight-gradient MMAs read ONE operand
+// from shared memory instead of two.
+//
+// Where the operands live:
+//   zeta    Philox -> registers ->  (a) shared, sample-major K-major tile  zk[(col >> 2) * LBO + sample * 16 + (col & 3) * 4]  (hi, lo):
+//                                       B operand of the delta_pre MMA; one float4 per (sample, Philox call)
+//                                   (b) tensor memory, lane = zeta column, column = sample (hi, lo) after a 4 x 4 shuffle transpose:
+//                                       A operand of the weight-gradient MMA.  Lane <-> column: lane 32 q + l <-> zeta group
+//                                       4 (l >> 2) + q, component l & 3 (groups dealt round-robin to the four lane quarters,
+//                                       so that every quarter draws the same number of Philox blocks)
+//   act     TMA (CU_TENSOR_MAP_SWIZZLE_128B) -> shared [column][32 samples]; dead paths zeroed and the lo tile formed by 4 warps
+//   delta   D_delta (tensor memory, M = 64: hidden slot r at lane 32 (r >> 4) + (r & 15)) -> registers -> A1 (tensor memory, same
+//           lanes) and, delta_2 only, the sample-major shared tile dk (B operand of the second hidden MMA)
+//   weights W2h = [W2[h2 rows]; W2[h1 rows]] (64 x s0), W1h = [0; W1[h1 rows -> h2]] (64 x 32): shared, K-major, hi and lo, once per CTA
+//
+// Warp roles (576 threads, one CTA per SM):
+//   warps 0-3   epilogues of the hidden MMAs (lane quarter = warp): warps 0, 1 delta_2, warps 2, 3 delta_1
+//   warps 4-11  zeta: Philox + Box-Muller, the two copies (quarter = warp & 3, sample half = (warp - 4) >> 2)
+//   warps 12-15 activation rows: dead-path fix-up + lo tile; accumulator flush (quarter = warp & 3)
+//   warp  16    TMA producer (one lane)
+//   warp  17    MMA issuer (one lane), software-pipelined: dW0(i) | delta MMA 2 (i) | delta MMA 1 (i + 1) | dW1(i)
+#pragma once
+#if !defined(PSPDE_EMULATE)
+#include "grad_tc_kernels.cuh"
+
+namespace pspde {
+
+constexpr int kG2S = 32;                  // samples per stage
+constexpr int kG2Sub = kCkP / kG2S;       // stages per (tile, step)
+constexpr int kG2Threads = 18 * 32;
+constexpr int kG2FlushStages = 16;        // accumulator flush period (the tensor core's FP32 accumulation is not round-to-nearest)
+constexpr int kG2WGen = 4, kG2WLo = 12, kG2WTma = 16, kG2WMma = 17;
+constexpr int kG2GenThreads = 256, kG2LoThreads = 128;
+constexpr uint32_t kG2LboZ = 528;         // bytes between 4-column groups of the sample-major tiles: 32 samples x 16 B + 16
+                                          // (4 LBO = 64 mod 128: the float4 stores of a quarter-warp hit distinct banks)
+constexpr uint32_t kG2LboW = 1024;        // weights: 64 rows x 16 B per 4-column group
+
+struct GradTc2Geom {
+  int s0, act_rows, nA, nA1, dense, kz;
+  uint32_t act_bytes;
+  uint32_t o_act[2], o_lo[2], o_zk[2], o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // [hi, lo]; bytes from the 1 KB aligned base
+  int c_d0, c_d1, c_a0[2], c_a1[2], c_dd[2];                                      // tensor-memory columns
+};
+
+inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
+  if (g.L != 3 || g.time_mode == TIME_NONE || g.seg_len[1] > 32 || g.seg_len[2] > 32 || (s0 & 7) || s0 < g.seg_len[0] || s0 > 128)
+    return false;
+  t.dense = g.kind == NET_DENSENET ? 1 : 0;
+  t.s0 = s0; t.act_rows = s0 + 64; t.kz = s0 / 4;
+  t.nA = (t.act_rows + 15) / 16 * 16;     // N of an M = 128 MMA is a multiple of 16
+  t.nA1 = s0 + 32;                        // M = 64: a multiple of 8
+  if (t.nA > 256 || t.act_rows > 256) return false;
+  int c = 0;
+  t.c_d0 = c; c += t.nA;
+  t.c_d1 = c; c += t.nA1;
+  t.c_a0[0] = c; c += kG2S; t.c_a0[1] = c; c += kG2S;
+  t.c_a1[0] = c; c += kG2S; t.c_a1[1] = c; c += kG2S;
+  t.c_dd[0] = c; c += kG2S; t.c_dd[1] = c; c += kG2S;
+  if (c > 512) return false;
+  t.act_bytes = (uint32_t)t.nA * 128u;    // a multiple of 2 KB
+  uint32_t o = 0;
+  for (int s = 0; s < 2; ++s) { t.o_act[s] = o; o += t.act_bytes; t.o_lo[s] = o; o += t.act_bytes; }
+  for (int h = 0; h < 2; ++h) { t.o_zk[h] = o; o += (uint32_t)t.kz * kG2LboZ; }
+  for (int h = 0; h < 2; ++h) { t.o_dk[h] = o; o += 8u * kG2LboZ; }
+  for (int h = 0; h < 2; ++h) { t.o_w2[h] = o; o += (uint32_t)t.kz * kG2LboW; }
+  for (int h = 0; h < 2; ++h) { t.o_w1[h] = o; o += 8u * kG2LboW; }
+  t.o_bar = (o + 15u) & ~15u; o = t.o_bar + 32u * 8u;
+  t.total = o + 1024u;
+  return t.total <= 227u * 1024u;
+}
+
+// lane 32 q + l of the zeta tile in tensor memory <-> zeta column (see the header)
+__host__ __device__ inline int g2_ze_col(int lane128) { return 4 * (4 * ((lane128 & 31) >> 2) + (lane128 >> 5)) + (lane128 & 3); }
+
+static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const RolloutParams prm,
+                                                                        const GradTc2Geom tg, const int n_ts, const int flush_stages) {
+  extern __shared__ float4 smem4_g2[];
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>(smem4_g2);
+  __shared__ uint32_t tmem_base_s;
+  const NetGeom& g = prm.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tg.o_bar);
+  uint64_t* bar_full = bars;            // [2] TMA bytes of the activation rows landed
+  uint64_t* bar_lo = bars + 2;          // [2] dead paths zeroed, lo tile written
+  uint64_t* bar_free = bars + 4;        // [2] dW1 of the stage done: activation buffers, A1 and D_delta are free
+  uint64_t* bar_zk = bars + 6;          // sample-major zeta tile written
+  uint64_t* bar_a0 = bars + 7;          // zeta' in tensor memory written
+  uint64_t* bar_d1 = bars + 8;          // first hidden MMA done (also: the sample-major zeta tile is free)
+  uint64_t* bar_w0 = bars + 9;          // dW0 done: zeta' in tensor memory is free
+  uint64_t* bar_e1 = bars + 10;         // delta_2 written (tensor memory + sample-major tile)
+  uint64_t* bar_d2 = bars + 11;         // second hidden MMA done
+  uint64_t* bar_e2 = bars + 12;         // delta_1 written
+  uint64_t* bar_acc_full = bars + 13;   // accumulators complete up to a flush point
+  uint64_t* bar_acc_empty = bars + 14;  // accumulators read out
+
+  // ---- one-time setup
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) {
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_lo[s], kG2LoThreads); tc::mbar_init(&bar_free[s], 1); }
+    tc::mbar_init(bar_zk, kG2GenThreads); tc::mbar_init(bar_a0, kG2GenThreads);
+    tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, 64); tc::mbar_init(bar_d2, 1); tc::mbar_init(bar_e2, 64);
+    tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
+    tc::mbar_fence_init();
+  }
+  if (tid == kG2WTma * 32) tc::tma_prefetch_desc(&tmap);
+  for (uint32_t q = tid; q < tg.o_w2[0] / 16u; q += kG2Threads) reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // weights of the hidden MMAs, K-major (hidden slot m, column k) at (k >> 2) * 1 KB + m * 16 + (k & 3) * 4, hi and lo.
+  // slot m < 32: h2 column m (delta_2), else h1 column m - 32 (delta_1)
+  {
+    const LayerGeom& y2 = g.layer[2];
+    const LayerGeom& y1 = g.layer[1];
+    for (int q = tid; q < 64 * tg.s0; q += kG2Threads) {
+      const int m = q & 63, k = q >> 6;
+      const int sg = m < 32 ? 2 : 1, c = m & 31;
+      float w = 0.f;
+      if (c < g.seg_len[sg]) {
+        const int lr = g.seg_off[sg] + c - y2.in_start;
+        if (lr >= 0 && lr < y2.Kp) { const int idx = theta_index(g, 2, lr, k); if (idx >= 0) w = __ldg(prm.theta + idx); }
+      }
+      float hi, lo;
+      tc::tf32_split(w, hi, lo);
+      const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
+      *reinterpret_cast<float*>(smem + tg.o_w2[0] + off) = hi;
+      *reinterpret_cast<float*>(smem + tg.o_w2[1] + off) = lo;
+    }
+    for (int q = tid; q < 64 * 32; q += kG2Threads) {
+      const int m = q & 63, k = q >> 6;           // k = h2 column (delta_2 slot)
+      float w = 0.f;
+      if (m >= 32 && (m & 31) < g.seg_len[1]) {
+        const int lr = g.seg_off[1] + (m & 31) - y1.in_start;
+        if (lr >= 0 && lr < y1.Kp) { const int idx = theta_index(g, 1, lr, k); if (idx >= 0) w = __ldg(prm.theta + idx); }
+      }
+      float hi, lo;
+      tc::tf32_split(w, hi, lo);
+      const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
+      *reinterpret_cast<float*>(smem + tg.o_w1[0] + off) = hi;
+      *reinterpret_cast<float*>(smem + tg.o_w1[1] + off) = lo;
+    }
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+
+  const int my_ts = (n_ts - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // (tile, step) pairs of this CTA
+  const int n_it = my_ts > 0 ? my_ts * kG2Sub : 0;
+  const bool unit = prm.ckpt_unit != 0;
+  // first local path index and step of stage iteration `it`
+  auto stage_path0 = [&](int it) {
+    const int ts = (int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x;
+    return (prm.tile0 + ts / prm.N) * kCkP + (it % kG2Sub) * kG2S;
+  };
+  auto stage_step = [&](int it) { return (unsigned)(((int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x) % prm.N); };
+
+  if (warp < kG2WGen) {
+    // =============================================================== epilogues of the hidden MMAs
+    const int q = warp;                              // lane quarter; hidden slot r = 16 q + lane (lane < 16)
+    const bool is_d2 = q < 2;
+    const int c = (16 * q + (lane & 15)) & 31;       // column inside the hidden segment
+    const int sg = is_d2 ? 2 : 1;
+    const bool live = lane < 16 && c < g.dims[sg];
+    const int h_row = tg.s0 + (is_d2 ? 32 : 0) + c;  // tile row of the hidden activation
+    const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
+      tc::mbar_wait(is_d2 ? bar_d1 : bar_d2, p1);
+      tc::mbar_wait(&bar_lo[s], p2);                 // the hidden activations of dead paths are zero from here on
+      if (it > 0) tc::mbar_wait(&bar_free[s ^ 1], (uint32_t)((it - 1) >> 1) & 1u);     // dW1 of the previous stage read A1
+      tc::fence_after_sync();
+      const uint8_t* tH = smem + tg.o_act[s];
+      uint8_t* dh = smem + tg.o_dk[0] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u;
+      uint8_t* dl = smem + tg.o_dk[1] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {         // 16 samples at a time (registers)
+        float v[16], hi[16], lo[16];
+        tc::tmem_ld16(tbase + lane_addr + (uint32_t)tg.c_dd[s] + 16u * half, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 h = *reinterpret_cast<const float4*>(tH + gt_swz(h_row, 4 * half + j));
+          const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // act': relu(.)^2 -> 2 relu(pre) = 2 sqrt(h) (sqrt.approx: 1 ulp); tanh -> 1 - h^2
+            const float dv = live ? v[4 * j + i] * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+            tc::tf32_split(dv, hi[4 * j + i], lo[4 * j + i]);
+          }
+        }
+        if (is_d2 && lane < 16) {                    // sample-major copy: B operand of the second hidden MMA
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            *reinterpret_cast<float*>(dh + 16 * (16 * half + n)) = hi[n];
+            *reinterpret_cast<float*>(dl + 16 * (16 * half + n)) = lo[n];
+          }
+        }
+        tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a1[0] + 16u * half, hi);
+        tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a1[1] + 16u * half, lo);
+      }
+      if (is_d2) tc::fence_proxy_async();
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(is_d2 ? bar_e1 : bar_e2);
+    }
+  } else if (warp < kG2WLo) {
+    // =============================================================== zeta: Philox -> the two operand copies
+    const int q = warp & 3, half = (warp - kG2WGen) >> 2;
+    const int gq = 4 * (lane >> 2) + q;              // this lane's zeta group (4 columns)
+    const int r = lane & 3;
+    const bool real = 4 * gq < prm.d;                // the group has at least one state column
+    const bool in_tile = gq < tg.kz;
+    const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
+    const float sqdt = sqrtf(prm.dt);
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t p1 = (uint32_t)it & 1u;
+      const int k0 = stage_path0(it) + 16 * half;
+      const unsigned nstep = stage_step(it);
+      float e[4][4];                                 // [i][column of the group]: sample 16 half + 4 i + r
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kl = k0 + 4 * i + r;
+        const float wk = (kl < prm.K_local) ? __ldg(prm.wY + kl) : 0.f;
+        if (real && wk != 0.f) {
+          const float4 e4 = philox_normal4((unsigned)(prm.k_offset + kl), nstep, (unsigned)gq, prm.offset, prm.seed);
+          e[i][0] = wk * (sqdt * e4.x);
+          e[i][1] = (4 * gq + 1 < prm.d) ? wk * (sqdt * e4.y) : 0.f;
+          e[i][2] = (4 * gq + 2 < prm.d) ? wk * (sqdt * e4.z) : 0.f;
+          e[i][3] = (4 * gq + 3 < prm.d) ? wk * (sqdt * e4.w) : 0.f;
+        } else {
+          e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
+        }
+      }
+      // (a) sample-major tile: free once the first hidden MMA of the previous stage is done
+      tc::mbar_wait(bar_d1, p1 ^ 1u);
+      if (in_tile) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 h, l;
+          tc::tf32_split(e[i][0], h.x, l.x); tc::tf32_split(e[i][1], h.y, l.y);
+          tc::tf32_split(e[i][2], h.z, l.z); tc::tf32_split(e[i][3], h.w, l.w);
+          const uint32_t off = (uint32_t)gq * kG2LboZ + (uint32_t)(16 * half + 4 * i + r) * 16u;
+          *reinterpret_cast<float4*>(smem + tg.o_zk[0] + off) = h;
+          *reinterpret_cast<float4*>(smem + tg.o_zk[1] + off) = l;
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(bar_zk);
+      // (b) 4 x 4 transpose inside each group of 4 lanes: lane r ends up with column r of samples 4 i + 0..3
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cs = r ^ j;                      // the column lane (r ^ j) wants from me = its own index; I get my column from it
+          const float send = cs == 0 ? e[i][0] : cs == 1 ? e[i][1] : cs == 2 ? e[i][2] : e[i][3];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, j);
+          // recv = column r of sample 4 i + (r ^ j)
+          if (cs == 0) o[0] = recv; else if (cs == 1) o[1] = recv; else if (cs == 2) o[2] = recv; else o[3] = recv;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tc::tf32_split(o[j], hi[4 * i + j], lo[4 * i + j]);
+      }
+      tc::mbar_wait(bar_w0, p1 ^ 1u);                // dW0 of the previous stage read zeta' from tensor memory
+      tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a0[0] + 16u * half, hi);
+      tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a0[1] + 16u * half, lo);
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(bar_a0);
+    }
+  } else if (warp < kG2WTma) {
+    // =============================================================== activation rows: fix-up + lo tile; accumulator flush
+    const int t = tid - kG2WLo * 32;                 // 0..127
+    const int qtr = warp & 3;
+    const int pos = t & 7, r0 = t >> 3;              // chunk position; rows r0 + 16 i keep (row & 7), hence the sample quad
+    const int j = pos ^ (r0 & 7);
+    uint32_t n_flush = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const uint32_t p2 = (uint32_t)(it >> 1) & 1u;
+      uint8_t* tH = smem + tg.o_act[s];
+      uint8_t* tL = smem + tg.o_lo[s];
+      bool keep[4] = {true, true, true, true};
+      if (unit) {                                    // forward-written rows: drop every row of a path whose cotangent is zero
+        const int kq = stage_path0(it) + 4 * j;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) keep[i] = (kq + i < prm.K_local) && __ldg(prm.wY + kq + i) != 0.f;
+      }
+      tc::mbar_wait(&bar_full[s], p2);
+      for (int r = r0; r < tg.act_rows; r += 16) {
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)(pos << 4);
+        float4 v = *reinterpret_cast<const float4*>(tH + off);
+        if (unit) {
+          v.x = keep[0] ? v.x : 0.f; v.y = keep[1] ? v.y : 0.f; v.z = keep[2] ? v.z : 0.f; v.w = keep[3] ? v.w : 0.f;
+          *reinterpret_cast<float4*>(tH + off) = v;
+        }
+        *reinterpret_cast<float4*>(tL + off) = lo4(v);
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bar_lo[s]);
+      const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_it - 1;
+      if (flush_now) {
+        // raw accumulators -> this CTA's partial [tile][activation column][lane] (RED.ADD, one writer per address, L2 resident)
+        tc::mbar_wait(bar_acc_full, n_flush & 1u);
+        tc::fence_after_sync();
+        float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nA);
+        const uint32_t la = ((uint32_t)(32 * qtr)) << 16;
+        for (int c0 = 0; c0 < tg.nA; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tbase + la + (uint32_t)(tg.c_d0 + c0), v);
+          tc::wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(gp + (size_t)(c0 + i) * 128 + 32 * qtr + lane, v[i]);
+        }
+        for (int c0 = 0; c0 < tg.nA1; c0 += 8) {
+          float v[8];
+          tc::tmem_ld8(tbase + la + (uint32_t)(tg.c_d1 + c0), v);
+          tc::wait_ld();
+          if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(gp + (size_t)(tg.nA + c0 + i) * 128 + 32 * qtr + lane, v[i]);
+          }
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_acc_empty);
+        ++n_flush;
+      }
+    }
+  } else if (warp == kG2WTma) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        tc::mbar_wait(&bar_free[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);      // first use of a buffer passes immediately
+        const int ts = (int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x, sub = it % kG2Sub;
+        tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.act_rows * 128u);
+        tc::tma_load_3d(smem + tg.o_act[s], &tmap, &bar_full[s], sub * kG2S, 0, ts);
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t sb = tc::smem_u32(smem);
+      const uint32_t id_d = tc::idesc_tf32(64, kG2S), id_w0 = tc::idesc_tf32(128, tg.nA), id_w1 = tc::idesc_tf32(64, tg.nA1);
+      // delta_pre' (+)= W (64 x 4 nk) . X' (4 nk x 32): three passes, small terms first
+      auto hidden_mma = [&](const uint32_t (&ow)[2], const uint32_t (&ox)[2], int nk4, uint32_t dcol, bool acc0) {
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = sb + ow[pass == 0 ? 1 : 0], b = sb + ox[pass == 1 ? 1 : 0];
+          for (int ks = 0; ks < nk4 / 2; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, tc::smem_desc(a + (uint32_t)ks * 2u * kG2LboW, kG2LboW, 128u),
+                            tc::smem_desc(b + (uint32_t)ks * 2u * kG2LboZ, kG2LboZ, 128u), id_d, acc0 || pass > 0 || ks > 0);
+        }
+      };
+      // D (+)= A' (tensor memory, [hi, lo] column bases) . act rows [0, n) of buffer s over the 32 samples of the stage
+      auto wgrad_mma = [&](const int (&ca)[2], int s, uint32_t dcol, uint32_t idesc, bool acc0) {
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = tbase + (uint32_t)ca[pass == 0 ? 1 : 0];
+          const uint32_t b = sb + (pass == 1 ? tg.o_lo[s] : tg.o_act[s]);
+          for (int ks = 0; ks < kG2S / 8; ++ks)
+            tc::mma_tf32_ts(tbase + dcol, a + 8u * (uint32_t)ks, tc::smem_desc_sw128(b + (uint32_t)ks * 32u), idesc, acc0 || pass > 0 || ks > 0);
+        }
+      };
+      uint32_t n_flush = 0;
+      if (n_it > 0) {                                 // prologue: first hidden MMA of stage 0
+        tc::mbar_wait(bar_zk, 0u);
+        tc::fence_after_sync();
+        hidden_mma(tg.o_w2, tg.o_zk, tg.kz, (uint32_t)tg.c_dd[0], false);
+        tc::mma_commit(bar_d1);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
+        const bool first = (it % flush_stages) == 0;                       // accumulators start over after a flush
+        const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_it - 1;
+        if (first && n_flush > 0) tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u);
+        // dW0(it): zeta' . act
+        tc::mbar_wait(bar_a0, p1);
+        tc::mbar_wait(&bar_lo[s], p2);
+        tc::fence_after_sync();
+        wgrad_mma(tg.c_a0, s, (uint32_t)tg.c_d0, id_w0, !first);
+        tc::mma_commit(bar_w0);
+        // second hidden MMA (it): delta_pre[h1 rows] += W1h . delta_2'
+        tc::mbar_wait(bar_e1, p1);
+        tc::fence_after_sync();
+        hidden_mma(tg.o_w1, tg.o_dk, 8, (uint32_t)tg.c_dd[s], true);
+        tc::mma_commit(bar_d2);
+        // first hidden MMA (it + 1): fills the tensor pipe while the delta_1 epilogue of stage it runs
+        if (it + 1 < n_it) {
+          tc::mbar_wait(bar_zk, p1 ^ 1u);
+          tc::fence_after_sync();
+          hidden_mma(tg.o_w2, tg.o_zk, tg.kz, (uint32_t)tg.c_dd[s ^ 1], false);
+          tc::mma_commit(bar_d1);
+        }
+        // dW1(it): [delta_2 | delta_1]' . act
+        tc::mbar_wait(bar_e2, p1);
+        tc::fence_after_sync();
+        wgrad_mma(tg.c_a1, s, (uint32_t)tg.c_d1, id_w1, !first);
+        tc::mma_commit(&bar_free[s]);
+        if (flush_now) { tc::mma_commit(bar_acc_full); ++n_flush; }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
+}
+
+// partial[cta][tile][activation column m][lane] -> grad_theta.
+//   tile 0: lane <-> zeta column n = g2_ze_col(lane): W2[activation column m][n]
+//   tile 1: lane 32 q + l (l < 16) <-> hidden slot r = 16 q + l: r < 32 -> W1[m][r] (delta_2), else W0[m][r - 32] (delta_1)
+// activation column m: checkpoint columns [a0 (s0) | h1 (32) | h2 (32)].  Fixed summation order, fp64.
+static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom tg, const float* __restrict__ partial, int nparts,
+                                              float* __restrict__ out) {
+  const int per = 2 * 128 * tg.nA;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
+    const int lane = q & 127, mc = q >> 7, tile = mc / tg.nA, m = mc - tile * tg.nA;
+    int col = -1;
+    if (m < tg.s0) { if (m < g.seg_len[0]) col = m; }
+    else if (m < tg.s0 + 32) { if (m - tg.s0 < g.seg_len[1]) col = g.seg_off[1] + (m - tg.s0); }
+    else if (m < tg.s0 + 64) { if (m - tg.s0 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - tg.s0 - 32); }
+    if (col < 0) continue;
+    int l, n;
+    if (tile == 0) { l = 2; n = g2_ze_col(lane); }
+    else {
+      if ((lane & 31) >= 16 || m >= tg.nA1) continue;
+      const int r = 16 * (lane >> 5) + (lane & 15);
+      if (r < 32) { l = 1; n = r; } else { l = 0; n = r - 32; }
+    }
+    const LayerGeom& y = g.layer[l];
+    const int r = col - y.in_start;
+    if (r < 0 || r >= y.Kp || n >= y.N) continue;
+    const int idx = theta_index(g, l, r, n);
+    if (idx < 0) continue;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)partial[(size_t)p * per + q];
+    out[idx] = (float)s;
+  }
+}
+
+}  // namespace pspde
+#endif  // !PSPDE_EMULATE

@@ -118,7 +118,9 @@ def test_philox_dump_and_rollout_vs_oracle():
     g2 = pt.empty(eng.n_theta, device="cuda")
     eng.backward_detached(theta, wY, None, Call(offset=5, xi=xi), g2)
     assert pt.equal(Y1, eng.Y_N) and pt.equal(X1, eng.X_N)
-    assert pt.equal(g1, g2)
+    # the Philox backward regenerates zeta inside grad_tc2_kernel, the injected one reads it from the checkpoint
+    # (grad_tc_kernel): same sums, different kernels
+    assert relerr(g1.cpu().numpy(), g2.cpu().numpy()) < TOL
     z = xi[:, :, 1:]
     assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
 
