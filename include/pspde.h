@@ -90,7 +90,7 @@ int          pspde_abi_version(void);
 const char*  pspde_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 uint64_t     pspde_launch_count(void);
-/* Debug hook: when set to a device buffer of 16 uint64 (zeroed by the caller), CTA 0 of the detached rollout
+/* Debug hook: when set to a device buffer of 32 uint64 (zeroed by the caller), CTA 0 of the detached rollout
  * kernels adds clock64() cycles per phase: [0] step prologue, [1] network forward, [2] SDE step, [3] hidden
  * cotangents, [4] weight gradient.  NULL (default) disables it. */
 void         pspde_set_profile_buffer(unsigned long long* dev_buf16);
@@ -320,6 +320,11 @@ int pspde_tc_selftest(int K, int N, int variant, const float* A, const float* B,
  * tcgen05.mma kind::tf32 (3 passes).  raw (nullable, R * 32 floats) receives the shared-memory image of the first box.
  * 128 <= R <= 256, R % 8 == 0, rB % 8 == 0, N % 16 == 0, rB + N <= R. */
 int pspde_tma_selftest(int R, int rB, int N, const float* T, float* D, float* raw, void* stream);
+
+/* Diagnostic: issue-to-completion cycles of chains of n tcgen05.mma kind::tf32 instructions over zeroed operands, for a fixed
+ * list of (operand source, M, N) cases; out = device buffer of 4 x 32 uint64: per case {cycles to completion, cycles to issue,
+ * n, mode << 32 | M << 16 | N}, terminated by a zero.  The numbers behind the gradient kernel's MMA shapes. */
+int pspde_mma_probe(int n, unsigned long long* out, void* stream);
 
 /* Deterministic fp32 FMA throughput probe (roofline denominator measured live by bench.py):
  * runs `iters` dependent-chain FMA rounds on every SM; returns the FLOP count launched, or <0. */

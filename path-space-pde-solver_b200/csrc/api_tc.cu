@@ -200,3 +200,150 @@ extern "C" int pspde_tc_selftest(int K, int N, int variant, const float* A, cons
   return 0;
 #endif
 }
+
+// ---- tcgen05 issue / completion cost probe (tools/probe_mma_cost.py): chains of n kind::tf32 MMAs on zeroed operands, timed
+// with clock64 from the first issue to the arrival of the commit.  out[3 c + 0..2] = cycles, n, (M << 16 | N) for case c.
+#if !defined(PSPDE_EMULATE)
+namespace pspde {
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, unsigned long long* __restrict__ out) {
+  extern __shared__ float4 smem4[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
+  smem += (1024u - (tc::smem_u32(smem) & 1023u)) & 1023u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int q = tid; q < 96 * 1024 / 16; q += 128) reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tb = tmem_base_s, sb = tc::smem_u32(smem);
+  if (tid == 0) {
+    uint32_t ph = 0;
+    int c = 0;
+    // mode 0: SS K-major no-swizzle, one accumulator; 1: SS, two accumulators alternating; 2: TS (A in tensor memory), one
+    // accumulator; 3: SS, four accumulators round-robin
+    auto run = [&](int mode, int M, int N) {
+      const uint32_t id = tc::idesc_tf32(M, N);
+      const uint32_t lboA = (uint32_t)M * 16u, lboB = (uint32_t)N * 16u;
+      const long long t0 = clock64();
+      for (int i = 0; i < n; ++i) {
+        const uint32_t d = tb + (mode == 1 ? (uint32_t)(i & 1) * 256u : mode == 3 ? (uint32_t)(i & 3) * 128u : 0u);
+        const uint64_t bd = tc::smem_desc(sb + 49152u + (uint32_t)(i % 6) * 2u * lboB, lboB, 128u);
+        if (mode == 2) tc::mma_tf32_ts(d, tb + 256u + 8u * (uint32_t)(i & 7), bd, id, i > 0);
+        else tc::mma_tf32_ss(d, tc::smem_desc(sb + (uint32_t)(i % 6) * 2u * lboA, lboA, 128u), bd, id, i > 0);
+      }
+      const long long t1 = clock64();
+      tc::mma_commit(&bar);
+      tc::mbar_wait(&bar, ph); ph ^= 1u;
+      const long long t2 = clock64();
+      out[4 * c + 0] = (unsigned long long)(t2 - t0); out[4 * c + 1] = (unsigned long long)(t1 - t0);
+      out[4 * c + 2] = (unsigned long long)n; out[4 * c + 3] = ((unsigned long long)mode << 32) | ((unsigned long long)M << 16) | (unsigned long long)N;
+      ++c;
+    };
+    // modes 4 (TS) / 5 (SS): the 8 descriptors of a k loop are built BEFORE the timed region, the issue loop is 8 MMAs unrolled
+    auto run_pre = [&](int mode, int M, int N) {
+      const uint32_t id = tc::idesc_tf32(M, N);
+      const uint32_t lboA = (uint32_t)M * 16u, lboB = (uint32_t)N * 16u;
+      uint64_t bd[8], ad[8];
+      uint32_t aa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bd[j] = tc::smem_desc(sb + 49152u + (uint32_t)(j % 6) * 2u * lboB, lboB, 128u);
+        ad[j] = tc::smem_desc(sb + (uint32_t)(j % 6) * 2u * lboA, lboA, 128u);
+        aa[j] = tb + 256u + 8u * (uint32_t)j;
+      }
+      const long long t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (mode == 4) tc::mma_tf32_ts(tb, aa[j], bd[j], id, (i + j) > 0);
+          else tc::mma_tf32_ss(tb, ad[j], bd[j], id, (i + j) > 0);
+        }
+      }
+      const long long t1 = clock64();
+      tc::mma_commit(&bar);
+      tc::mbar_wait(&bar, ph); ph ^= 1u;
+      const long long t2 = clock64();
+      out[4 * c + 0] = (unsigned long long)(t2 - t0); out[4 * c + 1] = (unsigned long long)(t1 - t0);
+      out[4 * c + 2] = (unsigned long long)((n + 7) / 8 * 8); out[4 * c + 3] = ((unsigned long long)mode << 32) | ((unsigned long long)M << 16) | (unsigned long long)N;
+      ++c;
+    };
+    for (int rep = 0; rep < 2; ++rep) {
+      c = 0;
+      run(0, 64, 32); run(2, 64, 32); run(2, 128, 176); run(0, 128, 176);
+      run_pre(4, 64, 32); run_pre(4, 128, 64); run_pre(4, 128, 176); run_pre(4, 64, 136); run_pre(4, 128, 256);
+      run_pre(5, 64, 32); run_pre(5, 64, 64); run_pre(5, 128, 64); run_pre(5, 128, 176); run_pre(5, 128, 256);
+    }
+    out[4 * c] = 0ull;
+    out[4 * 31] = (unsigned long long)c;
+  }
+  __syncthreads();
+  if (warp == 1) {     // modes 6 (TS) / 7 (SS): the WHOLE warp runs the issue loop, one elected lane issues (no divergence)
+    int c = (int)out[4 * 31];
+    uint32_t ph = 0;   // bar has completed an even number of phases per rep pair? recomputed below
+    ph = (uint32_t)(2 * c) & 1u;
+    auto run_w = [&](int mode, int M, int N) {
+      const uint32_t id = tc::idesc_tf32(M, N);
+      const uint32_t lboA = (uint32_t)M * 16u, lboB = (uint32_t)N * 16u;
+      uint64_t bd[8], ad[8];
+      uint32_t aa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bd[j] = tc::smem_desc(sb + 49152u + (uint32_t)(j % 6) * 2u * lboB, lboB, 128u);
+        ad[j] = tc::smem_desc(sb + (uint32_t)(j % 6) * 2u * lboA, lboA, 128u);
+        aa[j] = tb + 256u + 8u * (uint32_t)j;
+      }
+      __syncwarp();
+      const long long t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t acc = (i + j) > 0 ? 1u : 0u;
+          if (mode == 6)
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                         ::"r"(tb), "r"(aa[j]), "l"(bd[j]), "r"(id), "r"(acc) : "memory");
+          else
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+                         "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tb), "l"(ad[j]), "l"(bd[j]), "r"(id), "r"(acc) : "memory");
+        }
+      }
+      const long long t1 = clock64();
+      asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(tc::smem_u32(&bar)) : "memory");
+      tc::mbar_wait(&bar, ph); ph ^= 1u;
+      const long long t2 = clock64();
+      if ((tid & 31) == 0) {
+        out[4 * c + 0] = (unsigned long long)(t2 - t0); out[4 * c + 1] = (unsigned long long)(t1 - t0);
+        out[4 * c + 2] = (unsigned long long)((n + 7) / 8 * 8); out[4 * c + 3] = ((unsigned long long)mode << 32) | ((unsigned long long)M << 16) | (unsigned long long)N;
+      }
+      ++c;
+    };
+    run_w(6, 64, 32); run_w(6, 128, 176); run_w(6, 64, 136); run_w(7, 64, 32); run_w(7, 128, 176);
+    if ((tid & 31) == 0) out[4 * c] = 0ull;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tb, 512);
+}
+}  // namespace pspde
+#endif
+
+extern "C" int pspde_mma_probe(int n, unsigned long long* out, void* stream) {
+#if defined(PSPDE_EMULATE)
+  (void)n; (void)out; (void)stream;
+  return fail(-20, "the tensor-core path does not exist in the host emulator");
+#else
+  if (n < 1 || n > 4096 || !out) return fail(-2, "bad probe arguments");
+  const size_t smem = 97 * 1024 + 1024;
+  if (pspde_set_smem(mma_probe_kernel, smem)) return fail(-11, "cudaFuncSetAttribute failed");
+  mma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n, out);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "mma_probe launch failed: %s", e);
+  return 0;
+#endif
+}

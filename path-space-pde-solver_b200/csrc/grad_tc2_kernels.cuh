@@ -177,12 +177,19 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     const bool live = lane < 16 && c < g.dims[sg];
     const int h_row = tg.s0 + (is_d2 ? 32 : 0) + c;  // tile row of the hidden activation
     const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
+    // debug (CTA 0): warp 0 [0] wait hidden MMA 1, [1] wait lo, [2] wait A1 free, [3] delta_2; warp 2 [4] waits, [5] delta_1
+    PhaseTimer pt_;
+    pt_.start(prm.prof, (lane == 0 && (warp == 0 || warp == 2)) ? 0 : 1);
+    const int pb = warp == 0 ? 0 : 4;
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
       tc::mbar_wait(is_d2 ? bar_d1 : bar_d2, p1);
+      pt_.mark(pb);
       tc::mbar_wait(&bar_lo[s], p2);                 // the hidden activations of dead paths are zero from here on
+      pt_.mark(warp == 0 ? 1 : 4);
       if (it > 0) tc::mbar_wait(&bar_free[s ^ 1], (uint32_t)((it - 1) >> 1) & 1u);     // dW1 of the previous stage read A1
+      pt_.mark(warp == 0 ? 2 : 4);
       tc::fence_after_sync();
       const uint8_t* tH = smem + tg.o_act[s];
       uint8_t* dh = smem + tg.o_dk[0] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u;
@@ -217,6 +224,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       tc::wait_st();
       tc::fence_before_sync();
       tc::mbar_arrive(is_d2 ? bar_e1 : bar_e2);
+      pt_.mark(warp == 0 ? 3 : 5);
     }
   } else if (warp < kG2WLo) {
     // =============================================================== zeta: Philox -> the two operand copies
@@ -227,6 +235,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     const bool in_tile = gq < tg.kz;
     const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
     const float sqdt = sqrtf(prm.dt);
+    // debug (CTA 0, warp 4): [6] Philox, [7] wait sample-major tile free, [8] its stores, [9] transposes, [10] wait A0 free + st
+    PhaseTimer pt_;
+    pt_.start(prm.prof, (lane == 0 && warp == kG2WGen) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t p1 = (uint32_t)it & 1u;
       const int k0 = stage_path0(it) + 16 * half;
@@ -246,8 +257,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
           e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
         }
       }
+      pt_.mark(6);
       // (a) sample-major tile: free once the first hidden MMA of the previous stage is done
       tc::mbar_wait(bar_d1, p1 ^ 1u);
+      pt_.mark(7);
       if (in_tile) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -261,6 +274,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(bar_zk);
+      pt_.mark(8);
       // (b) 4 x 4 transpose inside each group of 4 lanes: lane r ends up with column r of samples 4 i + 0..3
       float hi[16], lo[16];
 #pragma unroll
@@ -277,12 +291,14 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 #pragma unroll
         for (int j = 0; j < 4; ++j) tc::tf32_split(o[j], hi[4 * i + j], lo[4 * i + j]);
       }
+      pt_.mark(9);
       tc::mbar_wait(bar_w0, p1 ^ 1u);                // dW0 of the previous stage read zeta' from tensor memory
       tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a0[0] + 16u * half, hi);
       tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a0[1] + 16u * half, lo);
       tc::wait_st();
       tc::fence_before_sync();
       tc::mbar_arrive(bar_a0);
+      pt_.mark(10);
     }
   } else if (warp < kG2WTma) {
     // =============================================================== activation rows: fix-up + lo tile; accumulator flush
@@ -291,6 +307,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     const int pos = t & 7, r0 = t >> 3;              // chunk position; rows r0 + 16 i keep (row & 7), hence the sample quad
     const int j = pos ^ (r0 & 7);
     uint32_t n_flush = 0;
+    PhaseTimer pt_;      // debug (CTA 0, warp 12): [11] wait TMA, [12] fix-up + lo pass, [13] flush
+    pt_.start(prm.prof, (lane == 0 && warp == kG2WLo) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const uint32_t p2 = (uint32_t)(it >> 1) & 1u;
@@ -303,6 +321,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         for (int i = 0; i < 4; ++i) keep[i] = (kq + i < prm.K_local) && __ldg(prm.wY + kq + i) != 0.f;
       }
       tc::mbar_wait(&bar_full[s], p2);
+      pt_.mark(11);
       for (int r = r0; r < tg.act_rows; r += 16) {
         const uint32_t off = (uint32_t)r * 128u + (uint32_t)(pos << 4);
         float4 v = *reinterpret_cast<const float4*>(tH + off);
@@ -314,6 +333,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_lo[s]);
+      pt_.mark(12);
       const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_it - 1;
       if (flush_now) {
         // raw accumulators -> this CTA's partial [tile][activation column][lane] (RED.ADD, one writer per address, L2 resident)
@@ -341,14 +361,19 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(bar_acc_empty);
         ++n_flush;
+        pt_.mark(13);
       }
     }
   } else if (warp == kG2WTma) {
     // =============================================================== TMA producer
     if (lane == 0) {
+      PhaseTimer pt_;    // debug (CTA 0): [14] wait for a free buffer
+      pt_.start(prm.prof, 0);
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
+        pt_.mark(15);
         tc::mbar_wait(&bar_free[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);      // first use of a buffer passes immediately
+        pt_.mark(14);
         const int ts = (int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x, sub = it % kG2Sub;
         tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.act_rows * 128u);
         tc::tma_load_3d(smem + tg.o_act[s], &tmap, &bar_full[s], sub * kG2S, 0, ts);
@@ -378,6 +403,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         }
       };
       uint32_t n_flush = 0;
+      // debug (CTA 0): [16] wait zeta' + lo (+ flush), [17] dW0, [18] wait delta_2, [19] hidden MMA 2, [20] wait zeta tile,
+      // [21] hidden MMA 1, [22] wait delta_1, [23] dW1 + commits
+      PhaseTimer pt_;
+      pt_.start(prm.prof, 0);
       if (n_it > 0) {                                 // prologue: first hidden MMA of stage 0
         tc::mbar_wait(bar_zk, 0u);
         tc::fence_after_sync();
@@ -393,27 +422,35 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         // dW0(it): zeta' . act
         tc::mbar_wait(bar_a0, p1);
         tc::mbar_wait(&bar_lo[s], p2);
+        pt_.mark(16);
         tc::fence_after_sync();
         wgrad_mma(tg.c_a0, s, (uint32_t)tg.c_d0, id_w0, !first);
         tc::mma_commit(bar_w0);
+        pt_.mark(17);
         // second hidden MMA (it): delta_pre[h1 rows] += W1h . delta_2'
         tc::mbar_wait(bar_e1, p1);
+        pt_.mark(18);
         tc::fence_after_sync();
         hidden_mma(tg.o_w1, tg.o_dk, 8, (uint32_t)tg.c_dd[s], true);
         tc::mma_commit(bar_d2);
+        pt_.mark(19);
         // first hidden MMA (it + 1): fills the tensor pipe while the delta_1 epilogue of stage it runs
         if (it + 1 < n_it) {
           tc::mbar_wait(bar_zk, p1 ^ 1u);
+          pt_.mark(20);
           tc::fence_after_sync();
           hidden_mma(tg.o_w2, tg.o_zk, tg.kz, (uint32_t)tg.c_dd[s ^ 1], false);
           tc::mma_commit(bar_d1);
+          pt_.mark(21);
         }
         // dW1(it): [delta_2 | delta_1]' . act
         tc::mbar_wait(bar_e2, p1);
+        pt_.mark(22);
         tc::fence_after_sync();
         wgrad_mma(tg.c_a1, s, (uint32_t)tg.c_d1, id_w1, !first);
         tc::mma_commit(&bar_free[s]);
         if (flush_now) { tc::mma_commit(bar_acc_full); ++n_flush; }
+        pt_.mark(23);
       }
     }
   }

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "pspde_diffusion_sample": (ctypes.c_int, [_CFG, ctypes.c_float, ctypes.c_float, _P, _P, _P]),
     "pspde_tc_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P]),
     "pspde_tma_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P]),
+    "pspde_mma_probe": (ctypes.c_int, [ctypes.c_int, _P, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
     "pspde_fma_probe_ex": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, _P, _P]),
 }

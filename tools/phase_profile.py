@@ -14,7 +14,7 @@ lib = _lib.load()
 S = bench.build_solver(wl, wl["K"], dev); eng = S._get_engine(); theta = S._theta.detach()
 wY = pt.randn(eng.K_local, device=dev) / eng.K_local
 grad = pt.empty(eng.n_theta, device=dev)
-buf = pt.zeros(16, dtype=pt.int64, device=dev)
+buf = pt.zeros(32, dtype=pt.int64, device=dev)
 ntiles = (eng.K_local + 127) // 128
 tiles_cta0 = ntiles // 148 + (1 if ntiles % 148 > 0 else 0)
 
@@ -37,9 +37,11 @@ for keep in (False, True):
     for n, v in zip(fwd_names, c):
         print("    %-30s %8.0f cycles/tile-step  %5.1f%%" % (n, v / steps, 100 * v / max(tot, 1)))
 if eng.ckpt is not None:
-    grad_names = ["delta: zeta gen / wait TMA", "delta: zeta.W2' (+delta_2)", "delta: barrier + delta_2.W1' + delta_1", "delta: fence + arrive",
-                  "mma: wait acc free + lo tile", "mma: wait delta rows", "mma: issue + commit", "mma: flush",
-                  "lo: wait TMA", "lo: lo pass", "lo: flush", "tma: wait free stage", "tma: issue", "tma: flush"]
+    grad_names = ["epi d2: wait hidden MMA 1", "epi d2: wait lo", "epi d2: wait A1 free", "epi d2: delta_2 (ld, act', st)",
+                  "epi d1: waits", "epi d1: delta_1", "gen: Philox + Box-Muller", "gen: wait zeta tile free", "gen: zeta tile stores",
+                  "gen: transposes + split", "gen: wait A0 free + st", "lo: wait TMA", "lo: fix-up + lo pass", "lo: flush",
+                  "tma: wait free buffer", "tma: issue", "mma: wait zeta' + lo (+ flush)", "mma: dW0 issue", "mma: wait delta_2",
+                  "mma: hidden MMA 2 issue", "mma: wait zeta tile", "mma: hidden MMA 1 issue", "mma: wait delta_1", "mma: dW1 issue + commits"]
     ms, c = profiled(lambda: eng.grad_from_rows(theta, wY, Call(offset=0), grad))
     stages = tiles_cta0 * eng.N * 4
     print("gradient kernel over the kept rows: %.2f ms, %.0f cycles per 32-sample stage" % (ms, ms * 1e-3 * 1.965e9 / stages))
