@@ -5,34 +5,33 @@
 //     dtheta = sum_samples J_theta Z(a0)' zeta,      zeta = wY[path] sqrt(dt) xi[path, step]   (adaptive process, no dL/dZ_sum)
 // The checkpoint holds, per (tile, step), one row of 128 paths for every column of [a0 | h1 | h2] (RolloutParams::ckpt with
 // ckpt_zeta == 0); zeta is regenerated from the Philox key.  A stage is 32 samples.  Per stage:
-//     delta_pre' [64 x 32]  = W2h [64 x s0] . zeta' [s0 x 32]            tcgen05 SS, M = 64 (hidden slot), N = 32 (sample), K = zeta column
-//     delta_2 = delta_pre[h2 rows] * act'(h2)                            4 epilogue warps (TMEM -> registers -> TMEM + shared)
-//     delta_pre'[h1 rows] += W1h [32 x 32] . delta_2' [32 x 32]          tcgen05 SS
-//     delta_1 = delta_pre[h1 rows] * act'(h1)
+//     X [64 x 64]  = W2h [64 x s0] . [zeta_hi | zeta_lo]' [s0 x 64]     hidden MMA 1: tcgen05 SS, M = 64 (hidden slot), K = zeta column,
+//                  + W2h_lo . zeta_hi' (columns 0..31)                  N = (sample, hi | lo): the three 3xTF32 products in TWO passes
+//     delta_2 = (X[h2 rows, 0..31] + X[h2 rows, 32..63]) * act'(h2)     epilogue warps (TMEM -> registers -> TMEM in place + shared)
+//     X[h1 rows] += W1h [32 x 32] . [delta_2_hi | delta_2_lo]' ...      hidden MMA 2 (the delta_2 rows of W1h are zero: they add 0)
+//     delta_1 = (X[h1 rows, 0..31] + X[h1 rows, 32..63]) * act'(h1)
 //     D0 [zeta col x act col]  += zeta'  . act      M = 128, N = s0 + 64, K = sample:  A = zeta' in TENSOR MEMORY, B = act rows (TMA, SW128)
-//     D1 [delta row x act col] += delta' . act      M = 64,  N = s0 + 32, K = sample:  A = [delta_2 | delta_1]' in tensor memory
-// Every product is 3xTF32 (tc_sm100.cuh).  Compared with grad_tc_kernel (FP32-FMA hidden cotangents, SS-mode weight gradient with
-// all operands in shared memory) the FMA pipe carries only Philox and the epilogues, and the weight-gradient MMAs read ONE operand
-// from shared memory instead of two.
+//     D1 [delta row x act col] += delta' . act      M = 64,  N = s0 + 32, K = sample:  A = X itself: the epilogues leave hi(delta) in
+//                                                   columns 0..31 and lo(delta) in columns 32..63 of the rows they read
+// Measured on this part (pspde_mma_probe): ONE tcgen05.mma costs its issuing thread >= 52 cycles whatever its shape
+// (95 at N = 176), and a commit -> mbarrier round trip ~ 800 cycles.  Hence: as few MMA instructions as possible (hi | lo stacked
+// along N), and every buffer between two dependent MMAs double-buffered so that the round trips of neighbouring stages overlap.
 //
 // Where the operands live:
-//   zeta    Philox -> registers ->  (a) shared, sample-major K-major tile  zk[(col >> 2) * LBO + sample * 16 + (col & 3) * 4]  (hi, lo):
-//                                       B operand of the delta_pre MMA; one float4 per (sample, Philox call)
-//                                   (b) tensor memory, lane = zeta column, column = sample (hi, lo) after a 4 x 4 shuffle transpose:
-//                                       A operand of the weight-gradient MMA.  Lane <-> column: lane 32 q + l <-> zeta group
-//                                       4 (l >> 2) + q, component l & 3 (groups dealt round-robin to the four lane quarters,
-//                                       so that every quarter draws the same number of Philox blocks)
+//   zeta    Philox -> shared, sample-major K-major tile zk[(col >> 2) * LBO + (sample | 32 lo) * 16 + (col & 3) * 4]: the B operand of
+//           hidden MMA 1, one float4 per Philox call -> read back column-wise -> tensor memory (lane = zeta column, column = sample;
+//           hi, lo): the A operand of dW0
 //   act     TMA (CU_TENSOR_MAP_SWIZZLE_128B) -> shared [column][32 samples]; dead paths zeroed and the lo tile formed by 4 warps
-//   delta   D_delta (tensor memory, M = 64: hidden slot r at lane 32 (r >> 4) + (r & 15)) -> registers -> A1 (tensor memory, same
-//           lanes) and, delta_2 only, the sample-major shared tile dk (B operand of the second hidden MMA)
+//   delta   X (tensor memory, M = 64: hidden slot r at lane 32 (r >> 4) + (r & 15); two buffers) -> registers -> X in place and,
+//           delta_2 only, the sample-major shared tile dk (two buffers)
 //   weights W2h = [W2[h2 rows]; W2[h1 rows]] (64 x s0), W1h = [0; W1[h1 rows -> h2]] (64 x 32): shared, K-major, hi and lo, once per CTA
 //
-// Warp roles (576 threads, one CTA per SM):
-//   warps 0-3   epilogues of the hidden MMAs (lane quarter = warp): warps 0, 1 delta_2, warps 2, 3 delta_1
-//   warps 4-11  zeta: Philox + Box-Muller, the two copies (quarter = warp & 3, sample half = (warp - 4) >> 2)
-//   warps 12-15 activation rows: dead-path fix-up + lo tile; accumulator flush (quarter = warp & 3)
-//   warp  16    TMA producer (one lane)
-//   warp  17    MMA issuer (one lane), software-pipelined: dW0(i) | delta MMA 2 (i) | delta MMA 1 (i + 1) | dW1(i)
+// Warp roles (704 threads, one CTA per SM):
+//   warps 0-7   epilogues of the hidden MMAs (lane quarter = warp & 3, 16 samples each): quarters 0, 1 delta_2, quarters 2, 3 delta_1
+//   warps 8-15  zeta: Philox + Box-Muller (one warp = one 4-column group x 32 samples per call), then the tensor-memory copy
+//   warps 16-19 activation rows: dead-path fix-up + lo tile; accumulator flush (quarter = warp & 3)
+//   warp  20    TMA producer (one lane)
+//   warp  21    MMA issuer (one lane), software-pipelined: dW0(i) | hidden MMA 2 (i) | hidden MMA 1 (i + 1) | dW1(i)
 #pragma once
 #if !defined(PSPDE_EMULATE)
 #include "grad_tc_kernels.cuh"
@@ -41,19 +40,19 @@ namespace pspde {
 
 constexpr int kG2S = 32;                  // samples per stage
 constexpr int kG2Sub = kCkP / kG2S;       // stages per (tile, step)
-constexpr int kG2Threads = 18 * 32;
+constexpr int kG2Threads = 22 * 32;
 constexpr int kG2FlushStages = 16;        // accumulator flush period (the tensor core's FP32 accumulation is not round-to-nearest)
-constexpr int kG2WGen = 4, kG2WLo = 12, kG2WTma = 16, kG2WMma = 17;
-constexpr int kG2GenThreads = 256, kG2LoThreads = 128;
-constexpr uint32_t kG2LboZ = 528;         // bytes between 4-column groups of the sample-major tiles: 32 samples x 16 B + 16
-                                          // (4 LBO = 64 mod 128: the float4 stores of a quarter-warp hit distinct banks)
+constexpr int kG2WGen = 8, kG2WLo = 16, kG2WTma = 20, kG2WMma = 21;
+constexpr int kG2GenThreads = 256, kG2LoThreads = 128, kG2EpiThreads = 128;   // epilogue threads per hidden MMA
+constexpr uint32_t kG2LboZ = 1040;        // bytes between 4-column groups of the sample-major tiles: (32 hi + 32 lo samples) x 16 B + 16
+                                          // (LBO / 4 = 4 mod 32: the column-wise read-back and the scalar stores hit distinct banks)
 constexpr uint32_t kG2LboW = 1024;        // weights: 64 rows x 16 B per 4-column group
 
 struct GradTc2Geom {
   int s0, act_rows, nA, nA1, dense, kz;
   uint32_t act_bytes;
-  uint32_t o_act[2], o_lo[2], o_zk[2], o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // [hi, lo]; bytes from the 1 KB aligned base
-  int c_d0, c_d1, c_a0[2], c_a1[2], c_dd[2];                                      // tensor-memory columns
+  uint32_t o_act[2], o_lo[2], o_zk, o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // bytes from the 1 KB aligned base; w: [hi, lo]
+  int c_d0, c_d1, c_a0[2], c_x[2];                                             // tensor-memory columns
 };
 
 inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
@@ -68,23 +67,20 @@ inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
   t.c_d0 = c; c += t.nA;
   t.c_d1 = c; c += t.nA1;
   t.c_a0[0] = c; c += kG2S; t.c_a0[1] = c; c += kG2S;
-  t.c_a1[0] = c; c += kG2S; t.c_a1[1] = c; c += kG2S;
-  t.c_dd[0] = c; c += kG2S; t.c_dd[1] = c; c += kG2S;
+  t.c_x[0] = c; c += 2 * kG2S; t.c_x[1] = c; c += 2 * kG2S;
   if (c > 512) return false;
   t.act_bytes = (uint32_t)t.nA * 128u;    // a multiple of 2 KB
   uint32_t o = 0;
   for (int s = 0; s < 2; ++s) { t.o_act[s] = o; o += t.act_bytes; t.o_lo[s] = o; o += t.act_bytes; }
-  for (int h = 0; h < 2; ++h) { t.o_zk[h] = o; o += (uint32_t)t.kz * kG2LboZ; }
+  t.o_zk = o; o += (uint32_t)t.kz * kG2LboZ;
   for (int h = 0; h < 2; ++h) { t.o_dk[h] = o; o += 8u * kG2LboZ; }
+  o = (o + 127u) & ~127u;
   for (int h = 0; h < 2; ++h) { t.o_w2[h] = o; o += (uint32_t)t.kz * kG2LboW; }
   for (int h = 0; h < 2; ++h) { t.o_w1[h] = o; o += 8u * kG2LboW; }
   t.o_bar = (o + 15u) & ~15u; o = t.o_bar + 32u * 8u;
   t.total = o + 1024u;
   return t.total <= 227u * 1024u;
 }
-
-// lane 32 q + l of the zeta tile in tensor memory <-> zeta column (see the header)
-__host__ __device__ inline int g2_ze_col(int lane128) { return 4 * (4 * ((lane128 & 31) >> 2) + (lane128 >> 5)) + (lane128 & 3); }
 
 static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const RolloutParams prm,
                                                                         const GradTc2Geom tg, const int n_ts, const int flush_stages) {
@@ -97,13 +93,13 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tg.o_bar);
   uint64_t* bar_full = bars;            // [2] TMA bytes of the activation rows landed
   uint64_t* bar_lo = bars + 2;          // [2] dead paths zeroed, lo tile written
-  uint64_t* bar_free = bars + 4;        // [2] dW1 of the stage done: activation buffers, A1 and D_delta are free
+  uint64_t* bar_free = bars + 4;        // [2] dW1 of the stage done: the activation buffers are free
   uint64_t* bar_zk = bars + 6;          // sample-major zeta tile written
   uint64_t* bar_a0 = bars + 7;          // zeta' in tensor memory written
-  uint64_t* bar_d1 = bars + 8;          // first hidden MMA done (also: the sample-major zeta tile is free)
+  uint64_t* bar_d1 = bars + 8;          // hidden MMA 1 done (also: the sample-major zeta tile is free)
   uint64_t* bar_w0 = bars + 9;          // dW0 done: zeta' in tensor memory is free
-  uint64_t* bar_e1 = bars + 10;         // delta_2 written (tensor memory + sample-major tile)
-  uint64_t* bar_d2 = bars + 11;         // second hidden MMA done
+  uint64_t* bar_e1 = bars + 10;         // delta_2 written (X in place + sample-major tile)
+  uint64_t* bar_d2 = bars + 11;         // hidden MMA 2 done
   uint64_t* bar_e2 = bars + 12;         // delta_1 written
   uint64_t* bar_acc_full = bars + 13;   // accumulators complete up to a flush point
   uint64_t* bar_acc_empty = bars + 14;  // accumulators read out
@@ -113,7 +109,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   if (tid == 32) {
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_lo[s], kG2LoThreads); tc::mbar_init(&bar_free[s], 1); }
     tc::mbar_init(bar_zk, kG2GenThreads); tc::mbar_init(bar_a0, kG2GenThreads);
-    tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, 64); tc::mbar_init(bar_d2, 1); tc::mbar_init(bar_e2, 64);
+    tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, kG2EpiThreads); tc::mbar_init(bar_d2, 1);
+    tc::mbar_init(bar_e2, kG2EpiThreads);
     tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
     tc::mbar_fence_init();
   }
@@ -170,127 +167,114 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 
   if (warp < kG2WGen) {
     // =============================================================== epilogues of the hidden MMAs
-    const int q = warp;                              // lane quarter; hidden slot r = 16 q + lane (lane < 16)
+    const int q = warp & 3, sh = warp >> 2;          // lane quarter; 16-sample half.  Hidden slot r = 16 q + lane (lane < 16)
     const bool is_d2 = q < 2;
     const int c = (16 * q + (lane & 15)) & 31;       // column inside the hidden segment
     const int sg = is_d2 ? 2 : 1;
     const bool live = lane < 16 && c < g.dims[sg];
     const int h_row = tg.s0 + (is_d2 ? 32 : 0) + c;  // tile row of the hidden activation
     const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
-    // debug (CTA 0): warp 0 [0] wait hidden MMA 1, [1] wait lo, [2] wait A1 free, [3] delta_2; warp 2 [4] waits, [5] delta_1
+    // debug (CTA 0): warp 0 [0] wait hidden MMA 1, [1] wait lo, [3] delta_2; warp 2 [4] waits, [5] delta_1
     PhaseTimer pt_;
     pt_.start(prm.prof, (lane == 0 && (warp == 0 || warp == 2)) ? 0 : 1);
-    const int pb = warp == 0 ? 0 : 4;
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
       tc::mbar_wait(is_d2 ? bar_d1 : bar_d2, p1);
-      pt_.mark(pb);
+      pt_.mark(warp == 0 ? 0 : 4);
       tc::mbar_wait(&bar_lo[s], p2);                 // the hidden activations of dead paths are zero from here on
       pt_.mark(warp == 0 ? 1 : 4);
-      if (it > 0) tc::mbar_wait(&bar_free[s ^ 1], (uint32_t)((it - 1) >> 1) & 1u);     // dW1 of the previous stage read A1
-      pt_.mark(warp == 0 ? 2 : 4);
       tc::fence_after_sync();
       const uint8_t* tH = smem + tg.o_act[s];
-      uint8_t* dh = smem + tg.o_dk[0] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u;
-      uint8_t* dl = smem + tg.o_dk[1] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u;
+      const uint32_t xa = tbase + lane_addr + (uint32_t)tg.c_x[s] + 16u * (uint32_t)sh;
+      float P[16], Q[16];
+      tc::tmem_ld16(xa, P);                          // hi.hi + lo.hi partial sums
+      tc::tmem_ld16(xa + 32u, Q);                    // hi.lo partial sums
+      float4 h4[4];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {         // 16 samples at a time (registers)
-        float v[16], hi[16], lo[16];
-        tc::tmem_ld16(tbase + lane_addr + (uint32_t)tg.c_dd[s] + 16u * half, v);
-        tc::wait_ld();
+      for (int j = 0; j < 4; ++j) h4[j] = *reinterpret_cast<const float4*>(tH + gt_swz(h_row, 4 * sh + j));
+      tc::wait_ld();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 h = *reinterpret_cast<const float4*>(tH + gt_swz(h_row, 4 * half + j));
-          const float hv[4] = {h.x, h.y, h.z, h.w};
+      for (int j = 0; j < 4; ++j) {
+        const float hv[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // act': relu(.)^2 -> 2 relu(pre) = 2 sqrt(h) (sqrt.approx: 1 ulp); tanh -> 1 - h^2
-            const float dv = live ? v[4 * j + i] * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
-            tc::tf32_split(dv, hi[4 * j + i], lo[4 * j + i]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          // act': relu(.)^2 -> 2 relu(pre) = 2 sqrt(h) (sqrt.approx: 1 ulp); tanh -> 1 - h^2
+          const float dv = live ? (P[4 * j + i] + Q[4 * j + i]) * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+          tc::tf32_split(dv, P[4 * j + i], Q[4 * j + i]);       // P <- hi, Q <- lo
         }
-        if (is_d2 && lane < 16) {                    // sample-major copy: B operand of the second hidden MMA
-#pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            *reinterpret_cast<float*>(dh + 16 * (16 * half + n)) = hi[n];
-            *reinterpret_cast<float*>(dl + 16 * (16 * half + n)) = lo[n];
-          }
-        }
-        tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a1[0] + 16u * half, hi);
-        tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a1[1] + 16u * half, lo);
       }
-      if (is_d2) tc::fence_proxy_async();
+      tc::tmem_st16(xa, P);                          // in place: the A operand of dW1
+      tc::tmem_st16(xa + 32u, Q);
+      if (is_d2 && lane < 16) {                      // sample-major copy [hi | lo]: B operand of hidden MMA 2
+        uint8_t* dk = smem + tg.o_dk[s] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u + (uint32_t)(16 * sh) * 16u;
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          *reinterpret_cast<float*>(dk + 16 * n) = P[n];
+          *reinterpret_cast<float*>(dk + 512 + 16 * n) = Q[n];
+        }
+        tc::fence_proxy_async();
+      }
       tc::wait_st();
       tc::fence_before_sync();
       tc::mbar_arrive(is_d2 ? bar_e1 : bar_e2);
       pt_.mark(warp == 0 ? 3 : 5);
     }
   } else if (warp < kG2WLo) {
-    // =============================================================== zeta: Philox -> the two operand copies
-    const int q = warp & 3, half = (warp - kG2WGen) >> 2;
-    const int gq = 4 * (lane >> 2) + q;              // this lane's zeta group (4 columns)
-    const int r = lane & 3;
-    const bool real = 4 * gq < prm.d;                // the group has at least one state column
-    const bool in_tile = gq < tg.kz;
+    // =============================================================== zeta: Philox -> shared tile -> tensor memory
+    const int gw = warp - kG2WGen;                   // 0..7
+    const int q = warp & 3, half = gw >> 2;          // tensor-memory copy: lane quarter (zeta columns 32 q + lane), 16-sample half
     const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
     const float sqdt = sqrtf(prm.dt);
-    // debug (CTA 0, warp 4): [6] Philox, [7] wait sample-major tile free, [8] its stores, [9] transposes, [10] wait A0 free + st
+    const int zc = 32 * q + lane;                    // zeta column of this lane in the tensor-memory copy
+    const uint8_t* zrd = smem + tg.o_zk + (uint32_t)(zc >> 2) * kG2LboZ + (uint32_t)(zc & 3) * 4u + (uint32_t)(16 * half) * 16u;
+    const bool zin = zc < tg.s0;
+    // debug (CTA 0, warp 8): [6] Philox, [7] wait sample-major tile free, [8] its stores + barrier, [9] read-back, [10] wait A0 free + st
     PhaseTimer pt_;
     pt_.start(prm.prof, (lane == 0 && warp == kG2WGen) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
       const uint32_t p1 = (uint32_t)it & 1u;
-      const int k0 = stage_path0(it) + 16 * half;
+      const int kl = stage_path0(it) + lane;         // Philox: lane = sample, warp gw draws groups gw, gw + 8, ...
       const unsigned nstep = stage_step(it);
-      float e[4][4];                                 // [i][column of the group]: sample 16 half + 4 i + r
+      const float wk = (kl < prm.K_local) ? __ldg(prm.wY + kl) : 0.f;
+      const float sc = wk * sqdt;
+      float4 zh[4], zl[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int kl = k0 + 4 * i + r;
-        const float wk = (kl < prm.K_local) ? __ldg(prm.wY + kl) : 0.f;
-        if (real && wk != 0.f) {
-          const float4 e4 = philox_normal4((unsigned)(prm.k_offset + kl), nstep, (unsigned)gq, prm.offset, prm.seed);
-          e[i][0] = wk * (sqdt * e4.x);
-          e[i][1] = (4 * gq + 1 < prm.d) ? wk * (sqdt * e4.y) : 0.f;
-          e[i][2] = (4 * gq + 2 < prm.d) ? wk * (sqdt * e4.z) : 0.f;
-          e[i][3] = (4 * gq + 3 < prm.d) ? wk * (sqdt * e4.w) : 0.f;
-        } else {
-          e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
-        }
+        const int gq = gw + 8 * i;
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * gq < prm.d) e4 = philox_normal4((unsigned)(prm.k_offset + kl), nstep, (unsigned)gq, prm.offset, prm.seed);
+        // wk == 0 (padding, dropped trajectory): exact zeros whatever the draw
+        const float z0 = wk != 0.f ? sc * e4.x : 0.f;
+        const float z1 = (wk != 0.f && 4 * gq + 1 < prm.d) ? sc * e4.y : 0.f;
+        const float z2 = (wk != 0.f && 4 * gq + 2 < prm.d) ? sc * e4.z : 0.f;
+        const float z3 = (wk != 0.f && 4 * gq + 3 < prm.d) ? sc * e4.w : 0.f;
+        tc::tf32_split(z0, zh[i].x, zl[i].x); tc::tf32_split(z1, zh[i].y, zl[i].y);
+        tc::tf32_split(z2, zh[i].z, zl[i].z); tc::tf32_split(z3, zh[i].w, zl[i].w);
       }
       pt_.mark(6);
-      // (a) sample-major tile: free once the first hidden MMA of the previous stage is done
-      tc::mbar_wait(bar_d1, p1 ^ 1u);
+      tc::mbar_wait(bar_d1, p1 ^ 1u);                // hidden MMA 1 of the previous stage has read the tile
       pt_.mark(7);
-      if (in_tile) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 h, l;
-          tc::tf32_split(e[i][0], h.x, l.x); tc::tf32_split(e[i][1], h.y, l.y);
-          tc::tf32_split(e[i][2], h.z, l.z); tc::tf32_split(e[i][3], h.w, l.w);
-          const uint32_t off = (uint32_t)gq * kG2LboZ + (uint32_t)(16 * half + 4 * i + r) * 16u;
-          *reinterpret_cast<float4*>(smem + tg.o_zk[0] + off) = h;
-          *reinterpret_cast<float4*>(smem + tg.o_zk[1] + off) = l;
+      for (int i = 0; i < 4; ++i) {
+        const int gq = gw + 8 * i;
+        if (gq < tg.kz) {
+          uint8_t* dst = smem + tg.o_zk + (uint32_t)gq * kG2LboZ + (uint32_t)lane * 16u;
+          *reinterpret_cast<float4*>(dst) = zh[i];
+          *reinterpret_cast<float4*>(dst + 512) = zl[i];
         }
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(bar_zk);
+      gt_named_bar(4, kG2GenThreads);                // all 26 groups are in shared memory
       pt_.mark(8);
-      // (b) 4 x 4 transpose inside each group of 4 lanes: lane r ends up with column r of samples 4 i + 0..3
       float hi[16], lo[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cs = r ^ j;                      // the column lane (r ^ j) wants from me = its own index; I get my column from it
-          const float send = cs == 0 ? e[i][0] : cs == 1 ? e[i][1] : cs == 2 ? e[i][2] : e[i][3];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, j);
-          // recv = column r of sample 4 i + (r ^ j)
-          if (cs == 0) o[0] = recv; else if (cs == 1) o[1] = recv; else if (cs == 2) o[2] = recv; else o[3] = recv;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tc::tf32_split(o[j], hi[4 * i + j], lo[4 * i + j]);
+      for (int n = 0; n < 16; ++n) {
+        hi[n] = zin ? *reinterpret_cast<const float*>(zrd + 16 * n) : 0.f;
+        lo[n] = zin ? *reinterpret_cast<const float*>(zrd + 512 + 16 * n) : 0.f;
       }
+      gt_named_bar(5, kG2GenThreads);                // every warp has its columns: the tile may be overwritten by the next stage's draws
       pt_.mark(9);
       tc::mbar_wait(bar_w0, p1 ^ 1u);                // dW0 of the previous stage read zeta' from tensor memory
       tc::tmem_st16(tbase + lane_addr + (uint32_t)tg.c_a0[0] + 16u * half, hi);
@@ -307,7 +291,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     const int pos = t & 7, r0 = t >> 3;              // chunk position; rows r0 + 16 i keep (row & 7), hence the sample quad
     const int j = pos ^ (r0 & 7);
     uint32_t n_flush = 0;
-    PhaseTimer pt_;      // debug (CTA 0, warp 12): [11] wait TMA, [12] fix-up + lo pass, [13] flush
+    PhaseTimer pt_;      // debug (CTA 0, warp 16): [11] wait TMA, [12] fix-up + lo pass, [13] flush
     pt_.start(prm.prof, (lane == 0 && warp == kG2WLo) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
@@ -322,14 +306,28 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       }
       tc::mbar_wait(&bar_full[s], p2);
       pt_.mark(11);
-      for (int r = r0; r < tg.act_rows; r += 16) {
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)(pos << 4);
-        float4 v = *reinterpret_cast<const float4*>(tH + off);
-        if (unit) {
-          v.x = keep[0] ? v.x : 0.f; v.y = keep[1] ? v.y : 0.f; v.z = keep[2] ? v.z : 0.f; v.w = keep[3] ? v.w : 0.f;
-          *reinterpret_cast<float4*>(tH + off) = v;
+      // rows r0 + 16 i: four loads in flight at a time (the shared-memory latency under the tensor core's operand traffic is
+      // several hundred cycles)
+      for (int rb = r0; rb < tg.act_rows; rb += 64) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rb + 16 * i;
+          if (r < tg.act_rows) v[i] = *reinterpret_cast<const float4*>(tH + (uint32_t)r * 128u + (uint32_t)(pos << 4));
         }
-        *reinterpret_cast<float4*>(tL + off) = lo4(v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rb + 16 * i;
+          if (r < tg.act_rows) {
+            const uint32_t off = (uint32_t)r * 128u + (uint32_t)(pos << 4);
+            float4 w = v[i];
+            if (unit) {
+              w.x = keep[0] ? w.x : 0.f; w.y = keep[1] ? w.y : 0.f; w.z = keep[2] ? w.z : 0.f; w.w = keep[3] ? w.w : 0.f;
+              *reinterpret_cast<float4*>(tH + off) = w;
+            }
+            *reinterpret_cast<float4*>(tL + off) = lo4(w);
+          }
+        }
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_lo[s]);
@@ -383,23 +381,33 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t sb = tc::smem_u32(smem);
-      const uint32_t id_d = tc::idesc_tf32(64, kG2S), id_w0 = tc::idesc_tf32(128, tg.nA), id_w1 = tc::idesc_tf32(64, tg.nA1);
-      // delta_pre' (+)= W (64 x 4 nk) . X' (4 nk x 32): three passes, small terms first
-      auto hidden_mma = [&](const uint32_t (&ow)[2], const uint32_t (&ox)[2], int nk4, uint32_t dcol, bool acc0) {
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = sb + ow[pass == 0 ? 1 : 0], b = sb + ox[pass == 1 ? 1 : 0];
-          for (int ks = 0; ks < nk4 / 2; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, tc::smem_desc(a + (uint32_t)ks * 2u * kG2LboW, kG2LboW, 128u),
-                            tc::smem_desc(b + (uint32_t)ks * 2u * kG2LboZ, kG2LboZ, 128u), id_d, acc0 || pass > 0 || ks > 0);
-        }
+      const uint32_t id_h64 = tc::idesc_tf32(64, 2 * kG2S), id_h32 = tc::idesc_tf32(64, kG2S);
+      const uint32_t id_w0 = tc::idesc_tf32(128, tg.nA), id_w1 = tc::idesc_tf32(64, tg.nA1);
+      // descriptors: only the 14-bit start address (>> 4) changes from one MMA to the next -> add to the low word
+      const uint64_t dw_hi = tc::smem_desc(sb + tg.o_w2[0], kG2LboW, 128u), dw_lo = tc::smem_desc(sb + tg.o_w2[1], kG2LboW, 128u);
+      const uint64_t dv_hi = tc::smem_desc(sb + tg.o_w1[0], kG2LboW, 128u), dv_lo = tc::smem_desc(sb + tg.o_w1[1], kG2LboW, 128u);
+      const uint64_t dz = tc::smem_desc(sb + tg.o_zk, kG2LboZ, 128u);
+      const uint64_t dd0 = tc::smem_desc(sb + tg.o_dk[0], kG2LboZ, 128u), dd1 = tc::smem_desc(sb + tg.o_dk[1], kG2LboZ, 128u);
+      const uint64_t dah0 = tc::smem_desc_sw128(sb + tg.o_act[0]), dah1 = tc::smem_desc_sw128(sb + tg.o_act[1]);
+      const uint64_t dal0 = tc::smem_desc_sw128(sb + tg.o_lo[0]), dal1 = tc::smem_desc_sw128(sb + tg.o_lo[1]);
+      const uint32_t cx0 = (uint32_t)tg.c_x[0], cx1 = (uint32_t)tg.c_x[1];
+      constexpr uint64_t kStepW = (2u * kG2LboW) >> 4, kStepZ = (2u * kG2LboZ) >> 4, kStepA = 32u >> 4;
+      // X (+)= W . [x_hi | x_lo]'  (N = 64)  then  X[:, 0..31] += W_lo . x_hi'  (N = 32): the three 3xTF32 products in two passes
+      auto hidden_mma = [&](uint64_t w_hi, uint64_t w_lo, uint64_t x, int nk8, uint32_t dcol, bool acc0) {
+        for (int ks = 0; ks < nk8; ++ks)
+          tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
+        for (int ks = 0; ks < nk8; ++ks)
+          tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
       };
-      // D (+)= A' (tensor memory, [hi, lo] column bases) . act rows [0, n) of buffer s over the 32 samples of the stage
-      auto wgrad_mma = [&](const int (&ca)[2], int s, uint32_t dcol, uint32_t idesc, bool acc0) {
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = tbase + (uint32_t)ca[pass == 0 ? 1 : 0];
-          const uint32_t b = sb + (pass == 1 ? tg.o_lo[s] : tg.o_act[s]);
+      // D (+)= A' (tensor memory: hi at column ca, lo at ca + 32) . act rows of buffer s over the 32 samples of the stage
+      auto wgrad_mma = [&](uint32_t ca, int s, uint32_t dcol, uint32_t idesc, bool acc0) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {       // small terms first
+          const uint32_t a = tbase + ca + (pass == 0 ? 32u : 0u);
+          const uint64_t b = pass == 1 ? (s ? dal1 : dal0) : (s ? dah1 : dah0);
+#pragma unroll
           for (int ks = 0; ks < kG2S / 8; ++ks)
-            tc::mma_tf32_ts(tbase + dcol, a + 8u * (uint32_t)ks, tc::smem_desc_sw128(b + (uint32_t)ks * 32u), idesc, acc0 || pass > 0 || ks > 0);
+            tc::mma_tf32_ts(tbase + dcol, a + 8u * (uint32_t)ks, b + (uint64_t)ks * kStepA, idesc, acc0 || pass > 0 || ks > 0);
         }
       };
       uint32_t n_flush = 0;
@@ -407,10 +415,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       // [21] hidden MMA 1, [22] wait delta_1, [23] dW1 + commits
       PhaseTimer pt_;
       pt_.start(prm.prof, 0);
-      if (n_it > 0) {                                 // prologue: first hidden MMA of stage 0
+      if (n_it > 0) {                                 // prologue: hidden MMA 1 of stage 0
         tc::mbar_wait(bar_zk, 0u);
         tc::fence_after_sync();
-        hidden_mma(tg.o_w2, tg.o_zk, tg.kz, (uint32_t)tg.c_dd[0], false);
+        hidden_mma(dw_hi, dw_lo, dz, tg.kz / 2, cx0, false);
         tc::mma_commit(bar_d1);
       }
       for (int it = 0; it < n_it; ++it) {
@@ -424,22 +432,22 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         tc::mbar_wait(&bar_lo[s], p2);
         pt_.mark(16);
         tc::fence_after_sync();
-        wgrad_mma(tg.c_a0, s, (uint32_t)tg.c_d0, id_w0, !first);
+        wgrad_mma((uint32_t)tg.c_a0[0], s, (uint32_t)tg.c_d0, id_w0, !first);
         tc::mma_commit(bar_w0);
         pt_.mark(17);
-        // second hidden MMA (it): delta_pre[h1 rows] += W1h . delta_2'
+        // hidden MMA 2 (it): X[h1 rows] += W1h . delta_2'
         tc::mbar_wait(bar_e1, p1);
         pt_.mark(18);
         tc::fence_after_sync();
-        hidden_mma(tg.o_w1, tg.o_dk, 8, (uint32_t)tg.c_dd[s], true);
+        hidden_mma(dv_hi, dv_lo, s ? dd1 : dd0, 4, s ? cx1 : cx0, true);
         tc::mma_commit(bar_d2);
         pt_.mark(19);
-        // first hidden MMA (it + 1): fills the tensor pipe while the delta_1 epilogue of stage it runs
+        // hidden MMA 1 (it + 1): fills the tensor pipe while the delta_1 epilogue of stage it runs
         if (it + 1 < n_it) {
           tc::mbar_wait(bar_zk, p1 ^ 1u);
           pt_.mark(20);
           tc::fence_after_sync();
-          hidden_mma(tg.o_w2, tg.o_zk, tg.kz, (uint32_t)tg.c_dd[s ^ 1], false);
+          hidden_mma(dw_hi, dw_lo, dz, tg.kz / 2, s ? cx0 : cx1, false);
           tc::mma_commit(bar_d1);
           pt_.mark(21);
         }
@@ -447,7 +455,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         tc::mbar_wait(bar_e2, p1);
         pt_.mark(22);
         tc::fence_after_sync();
-        wgrad_mma(tg.c_a1, s, (uint32_t)tg.c_d1, id_w1, !first);
+        wgrad_mma(s ? cx1 : cx0, s, (uint32_t)tg.c_d1, id_w1, !first);
         tc::mma_commit(&bar_free[s]);
         if (flush_now) { tc::mma_commit(bar_acc_full); ++n_flush; }
         pt_.mark(23);
@@ -461,7 +469,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 }
 
 // partial[cta][tile][activation column m][lane] -> grad_theta.
-//   tile 0: lane <-> zeta column n = g2_ze_col(lane): W2[activation column m][n]
+//   tile 0: lane <-> zeta column n: W2[activation column m][n]
 //   tile 1: lane 32 q + l (l < 16) <-> hidden slot r = 16 q + l: r < 32 -> W1[m][r] (delta_2), else W0[m][r - 32] (delta_1)
 // activation column m: checkpoint columns [a0 (s0) | h1 (32) | h2 (32)].  Fixed summation order, fp64.
 static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom tg, const float* __restrict__ partial, int nparts,
@@ -475,7 +483,7 @@ static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom
     else if (m < tg.s0 + 64) { if (m - tg.s0 - 32 < g.seg_len[2]) col = g.seg_off[2] + (m - tg.s0 - 32); }
     if (col < 0) continue;
     int l, n;
-    if (tile == 0) { l = 2; n = g2_ze_col(lane); }
+    if (tile == 0) { l = 2; n = lane; }
     else {
       if ((lane & 31) >= 16 || m >= tg.nA1) continue;
       const int r = 16 * (lane >> 5) + (lane & 15);

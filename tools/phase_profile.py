@@ -37,9 +37,9 @@ for keep in (False, True):
     for n, v in zip(fwd_names, c):
         print("    %-30s %8.0f cycles/tile-step  %5.1f%%" % (n, v / steps, 100 * v / max(tot, 1)))
 if eng.ckpt is not None:
-    grad_names = ["epi d2: wait hidden MMA 1", "epi d2: wait lo", "epi d2: wait A1 free", "epi d2: delta_2 (ld, act', st)",
+    grad_names = ["epi d2: wait hidden MMA 1", "epi d2: wait lo", "epi d2: -", "epi d2: delta_2 (ld, act', st)",
                   "epi d1: waits", "epi d1: delta_1", "gen: Philox + Box-Muller", "gen: wait zeta tile free", "gen: zeta tile stores",
-                  "gen: transposes + split", "gen: wait A0 free + st", "lo: wait TMA", "lo: fix-up + lo pass", "lo: flush",
+                  "gen: read-back + barrier", "gen: wait A0 free + st", "lo: wait TMA", "lo: fix-up + lo pass", "lo: flush",
                   "tma: wait free buffer", "tma: issue", "mma: wait zeta' + lo (+ flush)", "mma: dW0 issue", "mma: wait delta_2",
                   "mma: hidden MMA 2 issue", "mma: wait zeta tile", "mma: hidden MMA 1 issue", "mma: wait delta_1", "mma: dW1 issue + commits"]
     ms, c = profiled(lambda: eng.grad_from_rows(theta, wY, Call(offset=0), grad))
