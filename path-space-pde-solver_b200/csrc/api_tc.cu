@@ -326,6 +326,48 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, unsigned long 
     run_w(6, 64, 32); run_w(6, 128, 176); run_w(6, 64, 136); run_w(7, 64, 32); run_w(7, 128, 176);
     if ((tid & 31) == 0) out[4 * c] = 0ull;
   }
+  // modes 8 / 9: TWO issuing threads (warps 2 and 3, lane 0) at the same time, each n MMAs into its own accumulator
+  // (8: both SS M = 64 N = 32; 9: warp 2 SS M = 64 N = 64, warp 3 TS M = 128 N = 176): is the ~50-cycle issue cost per thread?
+  __shared__ uint64_t bar2[2];
+  __shared__ int c_s;
+  if (tid == 0) { tc::mbar_init(&bar2[0], 1); tc::mbar_init(&bar2[1], 1); tc::mbar_fence_init(); }
+  __syncthreads();
+  if (tid == 32) c_s = 0;
+  for (int mode = 8; mode <= 9; ++mode) {
+    __syncthreads();
+    if ((warp == 2 || warp == 3) && (tid & 31) == 0) {
+      const int w = warp - 2;
+      const bool ts = mode == 9 && w == 1;
+      const int M = ts ? 128 : 64, N = ts ? 176 : (mode == 9 ? 64 : 32);
+      const uint32_t id = tc::idesc_tf32(M, N);
+      const uint32_t lboA = (uint32_t)M * 16u, lboB = (uint32_t)N * 16u;
+      uint64_t bd[8], ad[8];
+      uint32_t aa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bd[j] = tc::smem_desc(sb + 49152u + (uint32_t)(j % 6) * 2u * lboB, lboB, 128u);
+        ad[j] = tc::smem_desc(sb + (uint32_t)(j % 6) * 2u * lboA, lboA, 128u);
+        aa[j] = tb + 448u + 8u * (uint32_t)j;
+      }
+      const uint32_t d = tb + (uint32_t)w * 192u;
+      const long long t0 = clock64();
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (ts) tc::mma_tf32_ts(d, aa[j], bd[j], id, (i + j) > 0);
+          else tc::mma_tf32_ss(d, ad[j], bd[j], id, (i + j) > 0);
+        }
+      }
+      const long long t1 = clock64();
+      tc::mma_commit(&bar2[w]);
+      tc::mbar_wait(&bar2[w], (uint32_t)(mode - 8) & 1u);
+      const long long t2 = clock64();
+      const int c = (int)out[4 * 31] + 5 + 2 * (mode - 8) + w;
+      out[4 * c + 0] = (unsigned long long)(t2 - t0); out[4 * c + 1] = (unsigned long long)(t1 - t0);
+      out[4 * c + 2] = (unsigned long long)((n + 7) / 8 * 8); out[4 * c + 3] = ((unsigned long long)mode << 32) | ((unsigned long long)M << 16) | (unsigned long long)N;
+      if (mode == 9 && w == 1) out[4 * (c + 1)] = 0ull;
+    }
+  }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tb, 512);

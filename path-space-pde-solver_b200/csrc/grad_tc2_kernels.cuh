@@ -21,7 +21,8 @@
 //   zeta    Philox -> shared, sample-major K-major tile zk[(col >> 2) * LBO + (sample | 32 lo) * 16 + (col & 3) * 4]: the B operand of
 //           hidden MMA 1, one float4 per Philox call -> read back column-wise -> tensor memory (lane = zeta column, column = sample;
 //           hi, lo): the A operand of dW0
-//   act     TMA (CU_TENSOR_MAP_SWIZZLE_128B) -> shared [column][32 samples]; dead paths zeroed and the lo tile formed by 4 warps
+//   act     TMA (CU_TENSOR_MAP_SWIZZLE_128B) -> shared [column][32 samples], a ring of three landing buffers (= the hi operand);
+//           dead paths zeroed in place and the lo tile (two buffers) formed by 4 warps
 //   delta   X (tensor memory, M = 64: hidden slot r at lane 32 (r >> 4) + (r & 15); two buffers) -> registers -> X in place and,
 //           delta_2 only, the sample-major shared tile dk (two buffers)
 //   weights W2h = [W2[h2 rows]; W2[h1 rows]] (64 x s0), W1h = [0; W1[h1 rows -> h2]] (64 x 32): shared, K-major, hi and lo, once per CTA
@@ -51,7 +52,7 @@ constexpr uint32_t kG2LboW = 1024;        // weights: 64 rows x 16 B per 4-colum
 struct GradTc2Geom {
   int s0, act_rows, nA, nA1, dense, kz;
   uint32_t act_bytes;
-  uint32_t o_act[2], o_lo[2], o_zk, o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // bytes from the 1 KB aligned base; w: [hi, lo]
+  uint32_t o_act[3], o_lo[2], o_zk, o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // bytes from the 1 KB aligned base; w: [hi, lo]
   int c_d0, c_d1, c_a0[2], c_x[2];                                             // tensor-memory columns
 };
 
@@ -71,7 +72,8 @@ inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
   if (c > 512) return false;
   t.act_bytes = (uint32_t)t.nA * 128u;    // a multiple of 2 KB
   uint32_t o = 0;
-  for (int s = 0; s < 2; ++s) { t.o_act[s] = o; o += t.act_bytes; t.o_lo[s] = o; o += t.act_bytes; }
+  for (int s = 0; s < 3; ++s) { t.o_act[s] = o; o += t.act_bytes; }      // TMA landing ring = the hi operand
+  for (int s = 0; s < 2; ++s) { t.o_lo[s] = o; o += t.act_bytes; }
   t.o_zk = o; o += (uint32_t)t.kz * kG2LboZ;
   for (int h = 0; h < 2; ++h) { t.o_dk[h] = o; o += 8u * kG2LboZ; }
   o = (o + 127u) & ~127u;
@@ -91,9 +93,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tg.o_bar);
-  uint64_t* bar_full = bars;            // [2] TMA bytes of the activation rows landed
+  uint64_t* bar_full = bars + 16;       // [3] TMA bytes of the activation rows landed
+  uint64_t* bar_free = bars + 19;       // [3] dW1 of the stage done: the landing buffer is free
   uint64_t* bar_lo = bars + 2;          // [2] dead paths zeroed, lo tile written
-  uint64_t* bar_free = bars + 4;        // [2] dW1 of the stage done: the activation buffers are free
+  uint64_t* bar_lofree = bars + 4;      // [2] dW1 of the stage done: the lo tile is free
   uint64_t* bar_zk = bars + 6;          // sample-major zeta tile written
   uint64_t* bar_a0 = bars + 7;          // zeta' in tensor memory written
   uint64_t* bar_d1 = bars + 8;          // hidden MMA 1 done (also: the sample-major zeta tile is free)
@@ -107,7 +110,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   // ---- one-time setup
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 32) {
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_lo[s], kG2LoThreads); tc::mbar_init(&bar_free[s], 1); }
+    for (int s = 0; s < 3; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_free[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_lo[s], kG2LoThreads); tc::mbar_init(&bar_lofree[s], 1); }
     tc::mbar_init(bar_zk, kG2GenThreads); tc::mbar_init(bar_a0, kG2GenThreads);
     tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, kG2EpiThreads); tc::mbar_init(bar_d2, 1);
     tc::mbar_init(bar_e2, kG2EpiThreads);
@@ -185,7 +189,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       tc::mbar_wait(&bar_lo[s], p2);                 // the hidden activations of dead paths are zero from here on
       pt_.mark(warp == 0 ? 1 : 4);
       tc::fence_after_sync();
-      const uint8_t* tH = smem + tg.o_act[s];
+      const uint8_t* tH = smem + tg.o_act[it % 3];
       const uint32_t xa = tbase + lane_addr + (uint32_t)tg.c_x[s] + 16u * (uint32_t)sh;
       float P[16], Q[16];
       tc::tmem_ld16(xa, P);                          // hi.hi + lo.hi partial sums
@@ -296,7 +300,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const uint32_t p2 = (uint32_t)(it >> 1) & 1u;
-      uint8_t* tH = smem + tg.o_act[s];
+      const int s3 = it % 3;
+      const uint32_t p3 = (uint32_t)(it / 3) & 1u;
+      uint8_t* tH = smem + tg.o_act[s3];
       uint8_t* tL = smem + tg.o_lo[s];
       bool keep[4] = {true, true, true, true};
       if (unit) {                                    // forward-written rows: drop every row of a path whose cotangent is zero
@@ -304,7 +310,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 #pragma unroll
         for (int i = 0; i < 4; ++i) keep[i] = (kq + i < prm.K_local) && __ldg(prm.wY + kq + i) != 0.f;
       }
-      tc::mbar_wait(&bar_full[s], p2);
+      tc::mbar_wait(&bar_full[s3], p3);
+      tc::mbar_wait(&bar_lofree[s], p2 ^ 1u);        // dW1 of stage it - 2 has read this lo tile (first use passes)
       pt_.mark(11);
       // rows r0 + 16 i: four loads in flight at a time (the shared-memory latency under the tensor core's operand traffic is
       // several hundred cycles)
@@ -368,9 +375,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       PhaseTimer pt_;    // debug (CTA 0): [14] wait for a free buffer
       pt_.start(prm.prof, 0);
       for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
+        const int s = it % 3;
         pt_.mark(15);
-        tc::mbar_wait(&bar_free[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);      // first use of a buffer passes immediately
+        tc::mbar_wait(&bar_free[s], ((uint32_t)(it / 3) & 1u) ^ 1u);       // first use of a buffer passes immediately
         pt_.mark(14);
         const int ts = (int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x, sub = it % kG2Sub;
         tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)tg.act_rows * 128u);
@@ -389,22 +396,40 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       const uint64_t dz = tc::smem_desc(sb + tg.o_zk, kG2LboZ, 128u);
       const uint64_t dd0 = tc::smem_desc(sb + tg.o_dk[0], kG2LboZ, 128u), dd1 = tc::smem_desc(sb + tg.o_dk[1], kG2LboZ, 128u);
       const uint64_t dah0 = tc::smem_desc_sw128(sb + tg.o_act[0]), dah1 = tc::smem_desc_sw128(sb + tg.o_act[1]);
+      const uint64_t dah2 = tc::smem_desc_sw128(sb + tg.o_act[2]);
       const uint64_t dal0 = tc::smem_desc_sw128(sb + tg.o_lo[0]), dal1 = tc::smem_desc_sw128(sb + tg.o_lo[1]);
       const uint32_t cx0 = (uint32_t)tg.c_x[0], cx1 = (uint32_t)tg.c_x[1];
       constexpr uint64_t kStepW = (2u * kG2LboW) >> 4, kStepZ = (2u * kG2LboZ) >> 4, kStepA = 32u >> 4;
       // X (+)= W . [x_hi | x_lo]'  (N = 64)  then  X[:, 0..31] += W_lo . x_hi'  (N = 32): the three 3xTF32 products in two passes
       auto hidden_mma = [&](uint64_t w_hi, uint64_t w_lo, uint64_t x, int nk8, uint32_t dcol, bool acc0) {
-        for (int ks = 0; ks < nk8; ++ks)
-          tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
-        for (int ks = 0; ks < nk8; ++ks)
-          tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+        if (nk8 == 13) {                             // the C2 / C5 shape (s0 = 104): fully unrolled, descriptor offsets are immediates
+#pragma unroll
+          for (int ks = 0; ks < 13; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 13; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+        } else if (nk8 == 4) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+        } else {
+          for (int ks = 0; ks < nk8; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
+          for (int ks = 0; ks < nk8; ++ks)
+            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+        }
       };
       // D (+)= A' (tensor memory: hi at column ca, lo at ca + 32) . act rows of buffer s over the 32 samples of the stage
-      auto wgrad_mma = [&](uint32_t ca, int s, uint32_t dcol, uint32_t idesc, bool acc0) {
+      auto wgrad_mma = [&](uint32_t ca, int s, int s3, uint32_t dcol, uint32_t idesc, bool acc0) {
+        const uint64_t bh = s3 == 0 ? dah0 : s3 == 1 ? dah1 : dah2, bl = s ? dal1 : dal0;
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {       // small terms first
           const uint32_t a = tbase + ca + (pass == 0 ? 32u : 0u);
-          const uint64_t b = pass == 1 ? (s ? dal1 : dal0) : (s ? dah1 : dah0);
+          const uint64_t b = pass == 1 ? bl : bh;
 #pragma unroll
           for (int ks = 0; ks < kG2S / 8; ++ks)
             tc::mma_tf32_ts(tbase + dcol, a + 8u * (uint32_t)ks, b + (uint64_t)ks * kStepA, idesc, acc0 || pass > 0 || ks > 0);
@@ -432,7 +457,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         tc::mbar_wait(&bar_lo[s], p2);
         pt_.mark(16);
         tc::fence_after_sync();
-        wgrad_mma((uint32_t)tg.c_a0[0], s, (uint32_t)tg.c_d0, id_w0, !first);
+        wgrad_mma((uint32_t)tg.c_a0[0], s, it % 3, (uint32_t)tg.c_d0, id_w0, !first);
         tc::mma_commit(bar_w0);
         pt_.mark(17);
         // hidden MMA 2 (it): X[h1 rows] += W1h . delta_2'
@@ -455,8 +480,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         tc::mbar_wait(bar_e2, p1);
         pt_.mark(22);
         tc::fence_after_sync();
-        wgrad_mma(s ? cx1 : cx0, s, (uint32_t)tg.c_d1, id_w1, !first);
-        tc::mma_commit(&bar_free[s]);
+        wgrad_mma(s ? cx1 : cx0, s, it % 3, (uint32_t)tg.c_d1, id_w1, !first);
+        tc::mma_commit(&bar_free[it % 3]);
+        tc::mma_commit(&bar_lofree[s]);
         if (flush_now) { tc::mma_commit(bar_acc_full); ++n_flush; }
         pt_.mark(23);
       }

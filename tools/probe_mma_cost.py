@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "path-space-pde-
 import torch as pt
 from pspde import _lib
 lib = _lib.load()
-MODES = {0: "SS one acc", 1: "SS two acc", 2: "TS one acc", 3: "SS four acc", 4: "TS precomp", 5: "SS precomp", 6: "TS warp+elect", 7: "SS warp+elect"}
+MODES = {0: "SS one acc", 1: "SS two acc", 2: "TS one acc", 3: "SS four acc", 4: "TS precomp", 5: "SS precomp", 6: "TS warp+elect", 7: "SS warp+elect", 8: "2 thr SS|SS", 9: "2 thr SS|TS"}
 for n in (16, 96):
     out = pt.zeros(4 * 32, dtype=pt.int64, device="cuda")
     _lib.check(lib, lib.pspde_mma_probe(n, ctypes.c_void_p(out.data_ptr()), None))
