@@ -472,22 +472,29 @@ def accuracy_block(rig, iters):
     wl = dict(WORKLOADS["c2"])
     S = build_solver(wl, wl["K"], rig.dev, u_l2=True, name="accuracy")
     d, T = S.d, float(S.T)
+    V00 = -(d / 4.0) * (1.0 - np.exp(-2.0 * T))
+    u_norm2 = d * (1.0 - np.exp(-2.0 * T)) / 2.0                 # int_0^T |u*(t)|^2 dt, u* = -exp(-(T-t)) 1
+    eng = S._get_engine()
+    trace = []
     t0 = time.perf_counter()
     for l in range(iters):
         S.train_step(l)
+        if l + 1 in (100, 300, 1000, 3000) and l + 1 < iters:     # convergence trace (the last batch's statistics)
+            st = eng.stats.clone()
+            if rig.world > 1:
+                rig.td.all_reduce(st)
+            trace.append({"iteration": l + 1, "loss": S.loss_log[-1], "V00_rel_err": abs(-(st[0].item() / S.K) - V00) / abs(V00),
+                          "u_rel_L2_err": float(np.sqrt(max(S.u_L2_loss[-1], 0.0) / u_norm2))})
     pt.cuda.synchronize(rig.dev)
     train_s = time.perf_counter() - t0
-    eng = S._get_engine()
     stats = eng.stats.clone()
     if rig.world > 1:
         rig.td.all_reduce(stats)
-    V00 = -(d / 4.0) * (1.0 - np.exp(-2.0 * T))
     est = -(stats[0].item() / S.K)
-    u_norm2 = d * (1.0 - np.exp(-2.0 * T)) / 2.0                 # int_0^T |u*(t)|^2 dt, u* = -exp(-(T-t)) 1
     out = {"workload": wl["desc"], "iterations": iters, "train_seconds": train_s, "loss_first": S.loss_log[0],
            "loss_last": S.loss_log[-1], "V00": est, "V00_exact": V00, "V00_rel_err": abs(est - V00) / abs(V00),
            "u_rel_L2_err": float(np.sqrt(max(S.u_L2_loss[-1], 0.0) / u_norm2)), "u_L2_first": S.u_L2_loss[0],
-           "u_L2_last": S.u_L2_loss[-1]}
+           "u_L2_last": S.u_L2_loss[-1], "trace": trace}
     # V(.,0) on test points: per-path starts, one forward launch on this rank's shard of the 64 x 1024 paths
     n_pts, per = 64, 1024
     g = pt.Generator().manual_seed(7)
@@ -766,7 +773,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the c2 / strong / sharding / accuracy blocks")
-    ap.add_argument("--accuracy-iters", type=int, default=300)
+    ap.add_argument("--accuracy-iters", type=int, default=1000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     wl = WORKLOADS[args.workload]
