@@ -447,14 +447,45 @@ def cpu_port_baseline(wl, N, K_cpu, iters, threads):
     return K_cpu * N / (sum(tt) / len(tt)), len(tt)
 
 
-def cpu_baseline_block(wl, N):
+def eager_gpu_baseline(wl, N, K_gpu, iters, dev):
+    """The same eager procedure (oracle/ref_port.py) with its tensors on the B200 -- the reference's own device='cuda' mode
+    (solver.py:36): noise drawn on the host and copied (:381), one aten kernel per operation, autograd tape in HBM."""
+    from oracle import ref_port as orc
+    d = wl["pkw"]["d"]
+    pkw = {k: v for k, v in wl["pkw"].items() if k != "d"}
+    prob = orc.make_problem(wl["kind"], d, **pkw)
+    if wl["net"] == "mlp":
+        params, net = orc.mlp_init(d + 1, d, seed=123), "mlp_tanh"
+    elif wl["ta"] == "outer":
+        params, net = [orc.densenet_init(d, d, seed=42) for _ in range(N)], "densenet"
+    else:
+        params, net = orc.densenet_init(d + 1, d, seed=42), "densenet"
+    orc.to_device(prob, params, dev)
+    times = []
+    orc.hjb_train_loop(prob, net, params, K_gpu, wl["dt"], iters, wl["lr"], wl["loss"], wl["ta"], True, wl["detach"],
+                       seed=42, times=times, device=dev)
+    tt = times[1:] if len(times) > 1 else times
+    return K_gpu * N / (sum(tt) / len(tt)), len(tt)
+
+
+def cpu_baseline_block(wl, N, dev=None):
     cores = os.cpu_count() or 1
     K_cpu = min(wl["K"], CPU_SAMPLE_K)
     v, n = cpu_port_baseline(wl, N, K_cpu, 3, cores)
     K1 = min(wl["K"], 1024)
     v1, n1 = cpu_port_baseline(wl, N, K1, 2, 1)
     pt.set_num_threads(cores)
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+    eager = None
+    if dev is not None:
+        try:
+            vg, ng = eager_gpu_baseline(wl, N, K_cpu, 4, dev)
+            eager = {"value": vg, "unit": UNIT, "device": pt.cuda.get_device_name(dev),
+                     "sample": "K=%d, N=%d, %d timed iterations after 1 warm-up; PyTorch eager on the GPU (the reference's "
+                               "device='cuda' mode: host randn + H2D, aten kernels, autograd), context only" % (K_cpu, N, ng)}
+        except Exception as e:                     # context only: never fail the bench line over it
+            eager = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        pt.cuda.empty_cache()
+    return {"torch_eager_gpu": eager, "value": v, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "K=%d of %d trajectories, N=%d, %d timed iterations after 1 warm-up (torch CPU eager + autograd + CPU "
                       "randn, the reference's procedure)" % (K_cpu, wl["K"], N, n),
             "one_thread": {"value": v1, "unit": UNIT, "cores": 1,
@@ -615,7 +646,7 @@ def run_ours(args, wl):
         return
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores, bounded sample
-    cpu = cpu_baseline_block(wl, N) if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_block(wl, N, dev) if (world == 1 and not args.no_cpu_baseline) else None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -101,7 +101,7 @@ def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
         p.b = lambda x: (p.A @ x.t()).t()
         if kind == "llgc":
             p.alpha = pt.ones(d, 1, dtype=dtype)
-            p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype)
+            p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype, device=x.device)
             p.h = lambda t, x, y, z: -0.5 * (z ** 2).sum(1)            # problems.py:45-46
             p.g = lambda x: (x @ p.alpha)[:, 0]                         # :48-49
         else:
@@ -121,10 +121,10 @@ def make_problem(kind, d, T=None, dtype=pt.float32, **kw):
         p.kappa_ = pt.tensor([kw.get("kappa", 1)] * d_1 + [1.0] * d_2, dtype=dtype)
         p.B = pt.eye(d, dtype=dtype)
         p.X_0 = -pt.ones(d, dtype=dtype)
-        p.b = lambda x: -(4.0 * p.kappa_ * (x * (x ** 2 - one)))
-        p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype)
+        p.b = lambda x: -(4.0 * p.kappa_ * (x * (x ** 2 - 1.0)))
+        p.f = lambda x, t: pt.zeros(x.shape[0], dtype=dtype, device=x.device)
         p.h = lambda t, x, y, z: -0.5 * (z ** 2).sum(1)
-        p.g = lambda x: (p.eta_ * (x - one) ** 2).sum(1)
+        p.g = lambda x: (p.eta_ * (x - 1.0) ** 2).sum(1)
     elif kind == "heat":
         # problems.py:1734-1758 (f is the *terminal* condition here)
         p.T = 1 if T is None else T
@@ -190,7 +190,7 @@ def control_eval(net, params, X, n, delta_t, time_approx, N):
     if time_approx == "outer":
         n = max(0, min(n, N - 1))
         return NET_FORWARD[net](params[n], X)
-    t_col = pt.ones(X.shape[0], 1, dtype=X.dtype) * n * delta_t
+    t_col = pt.ones(X.shape[0], 1, dtype=X.dtype, device=X.device) * n * delta_t
     return NET_FORWARD[net](params, pt.cat([t_col, X], 1))
 
 
@@ -201,17 +201,17 @@ def hjb_rollout(problem, net, params, xi, delta_t, N, time_approx="inner", adapt
     xi has the reference layout (K, d, N+1); slice n+1 drives step n (:472).
     delta_t is a 0-dim tensor so that t_n, *dt and *sqrt(dt) round as in the reference (:39-40)."""
     K = xi.shape[0]
-    dtype = xi.dtype
-    dt = pt.as_tensor(delta_t, dtype=dtype)
+    dtype, dev = xi.dtype, xi.device
+    dt = pt.as_tensor(delta_t, dtype=dtype).to(dev)
     sq = pt.sqrt(dt)
     X = (problem.X_0 if X0 is None else X0).repeat(K, 1) if (X0 is None or X0.dim() == 1) else X0
-    Y = pt.zeros(K, dtype=dtype) if y0 is None else y0.expand(K) + pt.zeros(K, dtype=dtype)
-    Zsum = pt.zeros(K, dtype=dtype)
+    Y = pt.zeros(K, dtype=dtype, device=dev) if y0 is None else y0.expand(K) + pt.zeros(K, dtype=dtype, device=dev)
+    Zsum = pt.zeros(K, dtype=dtype, device=dev)
     path = [X] if store_path else None
     B = problem.B
     for n in range(N):
         Z = control_eval(net, params, X, n, dt, time_approx, N)                     # :449
-        c = -Z.t() if adaptive else pt.zeros(problem.d, K, dtype=dtype)             # :451-456
+        c = -Z.t() if adaptive else pt.zeros(problem.d, K, dtype=dtype, device=dev)             # :451-456
         if detach_forward:
             c = c.detach()                                                          # :468-469
         xin = xi[:, :, n + 1]
@@ -491,8 +491,21 @@ def importance_sampling(problem, net, params, xis, delta_t, solver_delta_t, time
 
 
 # --------------------------------------------------------------------------- whole training loops (CPU baseline)
+def to_device(problem, params, device):
+    """Move the tensors of a make_problem() namespace and a parameter list (or list of lists) to `device` in place: the
+    reference's own device='cuda' mode (solver.py:36) -- same eager procedure, noise still drawn on the host (:381)."""
+    for k, v in list(vars(problem).items()):
+        if isinstance(v, pt.Tensor):
+            setattr(problem, k, v.to(device))
+    nets = params if isinstance(params[0], (list, tuple)) else [params]
+    for net_ in nets:
+        for i, q in enumerate(net_):
+            net_[i] = q.detach().to(device)
+    return problem, params
+
+
 def hjb_train_loop(problem, net, params, K, delta_t, L, lr, loss_method="log-variance", time_approx="inner",
-                   adaptive=True, detach_forward=True, seed=42, times=None):
+                   adaptive=True, detach_forward=True, seed=42, times=None, device=None):
     """Solver.train (solver.py:420-531) without logging extras: per iteration draw xi = randn(K, d, N+1)
     on the CPU generator (:381), roll out, loss, backward, one Adam step per network (:198-200)."""
     import time
@@ -507,6 +520,8 @@ def hjb_train_loop(problem, net, params, K, delta_t, L, lr, loss_method="log-var
     for _ in range(L):
         t0 = time.time()
         xi = pt.randn(K, problem.d, N + 1)
+        if device is not None:
+            xi = xi.to(device)                                                      # :381 `.to(self.device)`
         for o in optims:
             o.zero_grad()
         ad = True if loss_method == "relative_entropy" else adaptive
@@ -518,6 +533,8 @@ def hjb_train_loop(problem, net, params, K, delta_t, L, lr, loss_method="log-var
             o.step()
         loss_log.append(loss.item())
         if times is not None:
+            if device is not None and pt.device(device).type == "cuda":
+                pt.cuda.synchronize()
             times.append(time.time() - t0)
     return loss_log
 

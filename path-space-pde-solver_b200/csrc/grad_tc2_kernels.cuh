@@ -84,6 +84,15 @@ inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
   return t.total <= 227u * 1024u;
 }
 
+// one RED.128 per lane: four consecutive floats (sm_90+); the SM retires ~1 RED warp instruction per 11 cycles whatever its width
+__device__ __forceinline__ void g2_red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// index of (tile, activation column c, lane) in a CTA's partial: 4-column groups, [group][lane][4]
+__host__ __device__ inline size_t g2_part_index(int nA, int tile, int c, int lane) {
+  return ((size_t)(tile * (nA >> 2) + (c >> 2)) * 128 + (size_t)lane) * 4 + (size_t)(c & 3);
+}
+
 static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const RolloutParams prm,
                                                                         const GradTc2Geom tg, const int n_ts, const int flush_stages) {
   extern __shared__ float4 smem4_g2[];
@@ -104,8 +113,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   uint64_t* bar_e1 = bars + 10;         // delta_2 written (X in place + sample-major tile)
   uint64_t* bar_d2 = bars + 11;         // hidden MMA 2 done
   uint64_t* bar_e2 = bars + 12;         // delta_1 written
-  uint64_t* bar_acc_full = bars + 13;   // accumulators complete up to a flush point
-  uint64_t* bar_acc_empty = bars + 14;  // accumulators read out
+  uint64_t* bar_acc_full = bars + 13;   // D0 complete up to a flush point (committed right after dW0 of the flush stage)
+  uint64_t* bar_acc_empty = bars + 14;  // D0 read out
+  uint64_t* bar_acc1_full = bars + 22;  // D1 complete up to a flush point (after dW1)
+  uint64_t* bar_acc1_empty = bars + 23; // D1 read out
 
   // ---- one-time setup
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -116,6 +127,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, kG2EpiThreads); tc::mbar_init(bar_d2, 1);
     tc::mbar_init(bar_e2, kG2EpiThreads);
     tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
+    tc::mbar_init(bar_acc1_full, 1); tc::mbar_init(bar_acc1_empty, 4);
     tc::mbar_fence_init();
   }
   if (tid == kG2WTma * 32) tc::tma_prefetch_desc(&tmap);
@@ -162,6 +174,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   const int my_ts = (n_ts - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // (tile, step) pairs of this CTA
   const int n_it = my_ts > 0 ? my_ts * kG2Sub : 0;
   const bool unit = prm.ckpt_unit != 0;
+  // The CTAs flush their accumulators at DIFFERENT stages (offset by the CTA index): 148 CTAs flushing in the same few
+  // microseconds saturate the L2's atomic units (measured: ~14 k cycles per flush when synchronous).
+  const int flush_off = (int)(blockIdx.x % (unsigned)flush_stages);
   // first local path index and step of stage iteration `it`
   auto stage_path0 = [&](int it) {
     const int ts = (int)blockIdx.x + (it / kG2Sub) * (int)gridDim.x;
@@ -339,32 +354,51 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_lo[s]);
       pt_.mark(12);
-      const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_it - 1;
+      const bool flush_now = ((it + 1 + flush_off) % flush_stages == 0) || it == n_it - 1;
       if (flush_now) {
-        // raw accumulators -> this CTA's partial [tile][activation column][lane] (RED.ADD, one writer per address, L2 resident)
-        tc::mbar_wait(bar_acc_full, n_flush & 1u);
-        tc::fence_after_sync();
+        // raw accumulators -> this CTA's partial [tile][activation column][lane] (RED.ADD, one writer per address, L2 resident).
+        // D0 first -- it is complete as soon as dW0 of this stage is, long before dW1 -- then D1; pad columns / lanes are skipped.
         float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nA);
         const uint32_t la = ((uint32_t)(32 * qtr)) << 16;
-        for (int c0 = 0; c0 < tg.nA; c0 += 16) {
-          float v[16];
-          tc::tmem_ld16(tbase + la + (uint32_t)(tg.c_d0 + c0), v);
-          tc::wait_ld();
+        tc::mbar_wait(bar_acc_full, n_flush & 1u);
+        tc::fence_after_sync();
+        const bool zlane = 32 * qtr + lane < tg.s0;
+        // 32 columns per tensor-memory round trip (the load latency, not the REDs, is what a flush costs)
+        auto flush_cols = [&](int tile, int ccol, int c_begin, int c_end, bool on) {
+          int c0 = c_begin;
+          for (; c0 + 32 <= c_end; c0 += 32) {
+            float v[4][8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(gp + (size_t)(c0 + i) * 128 + 32 * qtr + lane, v[i]);
-        }
-        for (int c0 = 0; c0 < tg.nA1; c0 += 8) {
-          float v[8];
-          tc::tmem_ld8(tbase + la + (uint32_t)(tg.c_d1 + c0), v);
-          tc::wait_ld();
-          if (lane < 16) {
+            for (int u = 0; u < 4; ++u) tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0 + 8 * u), v[u]);
+            tc::wait_ld();
+            if (on) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(gp + (size_t)(tg.nA + c0 + i) * 128 + 32 * qtr + lane, v[i]);
+              for (int u = 0; u < 4; ++u) {
+                g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u, 32 * qtr + lane), v[u][0], v[u][1], v[u][2], v[u][3]);
+                g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u + 4, 32 * qtr + lane), v[u][4], v[u][5], v[u][6], v[u][7]);
+              }
+            }
           }
-        }
+          for (; c0 < c_end; c0 += 8) {
+            float v[8];
+            tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0), v);
+            tc::wait_ld();
+            if (on) {
+              g2_red_add4(gp + g2_part_index(tg.nA, tile, c0, 32 * qtr + lane), v[0], v[1], v[2], v[3]);
+              g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 4, 32 * qtr + lane), v[4], v[5], v[6], v[7]);
+            }
+          }
+        };
+        flush_cols(0, tg.c_d0, 0, tg.act_rows, zlane);
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(bar_acc_empty);
+        tc::mbar_wait(bar_acc1_full, n_flush & 1u);
+        tc::fence_after_sync();
+        flush_cols(1, tg.c_d1, 0, tg.nA1, lane < 16);
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_acc1_empty);
         ++n_flush;
         pt_.mark(13);
       }
@@ -449,9 +483,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       for (int it = 0; it < n_it; ++it) {
         const int s = it & 1;
         const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
-        const bool first = (it % flush_stages) == 0;                       // accumulators start over after a flush
-        const bool flush_now = ((it + 1) % flush_stages == 0) || it == n_it - 1;
-        if (first && n_flush > 0) tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u);
+        const bool first = it == 0 || ((it + flush_off) % flush_stages) == 0;   // accumulators start over after a flush
+        const bool flush_now = ((it + 1 + flush_off) % flush_stages == 0) || it == n_it - 1;
+        if (first && n_flush > 0) tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u);      // D0 has been read out
         // dW0(it): zeta' . act
         tc::mbar_wait(bar_a0, p1);
         tc::mbar_wait(&bar_lo[s], p2);
@@ -459,6 +493,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         tc::fence_after_sync();
         wgrad_mma((uint32_t)tg.c_a0[0], s, it % 3, (uint32_t)tg.c_d0, id_w0, !first);
         tc::mma_commit(bar_w0);
+        if (flush_now) tc::mma_commit(bar_acc_full);
         pt_.mark(17);
         // hidden MMA 2 (it): X[h1 rows] += W1h . delta_2'
         tc::mbar_wait(bar_e1, p1);
@@ -478,12 +513,13 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         }
         // dW1(it): [delta_2 | delta_1]' . act
         tc::mbar_wait(bar_e2, p1);
+        if (first && n_flush > 0) tc::mbar_wait(bar_acc1_empty, (n_flush - 1u) & 1u);     // D1 has been read out
         pt_.mark(22);
         tc::fence_after_sync();
         wgrad_mma(s ? cx1 : cx0, s, it % 3, (uint32_t)tg.c_d1, id_w1, !first);
         tc::mma_commit(&bar_free[it % 3]);
         tc::mma_commit(&bar_lofree[s]);
-        if (flush_now) { tc::mma_commit(bar_acc_full); ++n_flush; }
+        if (flush_now) { tc::mma_commit(bar_acc1_full); ++n_flush; }
         pt_.mark(23);
       }
     }
@@ -494,7 +530,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
-// partial[cta][tile][activation column m][lane] -> grad_theta.
+// partial[cta][g2_part_index(tile, activation column m, lane)] -> grad_theta.
 //   tile 0: lane <-> zeta column n: W2[activation column m][n]
 //   tile 1: lane 32 q + l (l < 16) <-> hidden slot r = 16 q + l: r < 32 -> W1[m][r] (delta_2), else W0[m][r - 32] (delta_1)
 // activation column m: checkpoint columns [a0 (s0) | h1 (32) | h2 (32)].  Fixed summation order, fp64.
@@ -502,7 +538,8 @@ static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom
                                               float* __restrict__ out) {
   const int per = 2 * 128 * tg.nA;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < per; q += gridDim.x * blockDim.x) {
-    const int lane = q & 127, mc = q >> 7, tile = mc / tg.nA, m = mc - tile * tg.nA;
+    // q = g2_part_index(nA, tile, m, lane)
+    const int lane = (q >> 2) & 127, cg = q >> 9, tile = cg / (tg.nA >> 2), m = 4 * (cg - tile * (tg.nA >> 2)) + (q & 3);
     int col = -1;
     if (m < tg.s0) { if (m < g.seg_len[0]) col = m; }
     else if (m < tg.s0 + 32) { if (m - tg.s0 < g.seg_len[1]) col = g.seg_off[1] + (m - tg.s0); }
