@@ -943,3 +943,103 @@ def test_u_l2_diagnostic_matches_reference(tag, path, monkeypatch):
     # table lookups: a state within rounding of a cell face may land in the neighbouring cell (dwm): 1e-4; closed forms: 1e-5
     tol = 1e-4 if g["kind"] == "dwm" else TOL
     assert abs(u_l2 - g["u_L2_loss"]) < tol * g["u_L2_loss"], (u_l2, g["u_L2_loss"])
+
+
+# ---------------------------------------------------------------------------------------------- grad_tc2_kernel (round 2)
+TC2_CASES = [("llgc", 100, (30, 30), 128 * 3 + 17, 5, 0.02), ("llgc", 10, (30, 30), 300, 4, 0.02), ("llgc", 7, (12, 20), 200, 3, 0.02),
+             ("dwm", 50, None, 500, 6, 0.005), ("dwm", 6, None, 100, 3, 0.005), ("llgc", 100, (30, 30), 1 << 13, 20, 0.01)]
+
+
+@pytest.mark.parametrize("kind,d,arch,K,N,dt", TC2_CASES)
+def test_tc2_gradient_kernel_matches_fma_backward(kind, d, arch, K, N, dt, monkeypatch):
+    """grad_tc2_kernel -- hidden cotangents AND weight gradient on tcgen05, zeta regenerated from the Philox key, operand rows by
+    TMA -- against the FP32-FMA recompute backward (rollout_kernel<BWD>, emulator-covered and golden-checked) on the same Philox
+    noise: DenseNet and MySequential, odd hidden widths, ragged K, dead paths (zero cotangent), the wave-checkpointed form and the
+    single-rollout form (rows kept by the training forward).  The older tensor-core kernel (PSPDE_GRAD_PATH=tc1) must agree too."""
+    import pspde
+    from pspde.fused import Call
+    if kind == "dwm":
+        prob = pspde.DoubleWell_multidim(d=d, d_1=d // 2, d_2=d - d // 2, T=N * dt, eta=3, kappa=5, device="cuda")
+    else:
+        prob = pspde.LLGC(d=d, off_diag=0, T=N * dt, seed=42, device="cuda")
+    S = pspde.Solver("tc2", prob, K=K, L=1, delta_t=dt, time_approx="inner", detach_forward=True, u_l2_error_flag=False,
+                     early_stopping_time=None, verbose=False, seed=5)
+    if kind != "dwm":
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, arch=list(arch), seed=42)
+        S.update_Phis()
+    eng = S._get_engine()
+    theta = S._theta.detach()
+    gen = pt.Generator(device="cuda").manual_seed(1)
+    wY = pt.randn(K, device="cuda", generator=gen) / K
+    wY[::7] = 0.0
+    res = {}
+    lib = eng.lib
+    for mode, env in (("simt", dict(PSPDE_BWD_PATH="simt")), ("tc1", dict(PSPDE_GRAD_PATH="tc1")), ("tc2", {}), ("tc2_single", {})):
+        for k in ("PSPDE_BWD_PATH", "PSPDE_GRAD_PATH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = pt.full((eng.n_theta,), float("nan"), device="cuda")
+        c = Call(offset=3)
+        kept = eng.forward(theta, None, c, keep_rows=(mode == "tc2_single"))
+        n0 = lib.pspde_launch_count()
+        if mode == "tc2_single":
+            assert kept
+            eng.grad_from_rows(theta, wY, c, g)
+            assert lib.pspde_launch_count() - n0 == 2          # gradient kernel + reduce: no second rollout
+        else:
+            eng.backward_detached(theta, wY, None, c, g)
+        pt.cuda.synchronize()
+        res[mode] = g.double()
+    ref = res["simt"]
+    for mode in ("tc1", "tc2", "tc2_single"):
+        assert float((res[mode] - ref).norm() / ref.norm()) < 5e-6, mode
+    assert pt.equal(res["tc2"], res["tc2_single"]) or float((res["tc2"] - res["tc2_single"]).norm() / ref.norm()) < 1e-6
+
+
+def test_blowup_bound_drops_near_divergent_paths():
+    """pspde_cfg::d_abs_max (Solver(blowup_bound=...)): a trajectory with |Y_N - g(X_N)| >= bound is dropped exactly like a
+    non-finite one -- counted in stats[3], Y_N = NaN, zero cotangent -- and the batch statistics are those of the kept paths."""
+    import pspde
+    from pspde.fused import Call
+    d, K = 10, 4096
+    prob = pspde.LLGC(d=d, T=1.0, device="cuda")
+    outs = {}
+    for bound in (None, 3.0):
+        S = pspde.Solver("bb", prob, K=K, L=1, delta_t=0.02, time_approx="inner", detach_forward=True, u_l2_error_flag=False,
+                         early_stopping_time=None, verbose=False, blowup_bound=bound)
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+        S.update_Phis()
+        eng = S._get_engine()
+        eng.forward(S._theta.detach(), None, Call(offset=0))
+        pt.cuda.synchronize()
+        outs[bound] = (eng.Y_N.clone(), eng.gX.clone(), eng.stats.clone())
+    Y, gX, st = outs[None]
+    D = Y.double() - gX.double()
+    assert st[3].item() == 0 and bool(pt.isfinite(D).all())
+    big = D.abs() >= 3.0
+    assert 0 < int(big.sum()) < K                       # the bound actually splits this batch
+    Yb, gXb, stb = outs[3.0]
+    assert stb[3].item() == int(big.sum())
+    assert bool(pt.isnan(Yb[big]).all()) and pt.equal(Yb[~big], Y[~big]) and pt.equal(gXb, gX)
+    assert pt.allclose(stb[:2], pt.stack([D[~big].sum(), (D[~big] ** 2).sum()]), rtol=1e-10)
+    # a training step with the bound: finite loss, dropped paths counted in nonfinite_log
+    S.train_step(0)
+    assert np.isfinite(S.loss_log[-1]) and S.nonfinite_log[-1] > 0 and bool(pt.isfinite(S._theta).all())
+
+
+def test_save_logs_and_device_argument(tmp_path, monkeypatch):
+    """save_results=True writes the reference's JSON log (solver.py:295-311, :556-557); device='cuda:0' given explicitly."""
+    import json
+    import pspde
+    monkeypatch.chdir(tmp_path)
+    prob = pspde.LLGC(d=4, T=0.5, device="cuda:0")
+    S = pspde.Solver("sv", prob, K=64, L=3, delta_t=0.05, time_approx="inner", detach_forward=True, verbose=False,
+                     save_results=True, device="cuda:0")
+    S.train()
+    files = list((tmp_path / "logs").glob("model_sv_*.json"))
+    assert len(files) == 1
+    log = json.loads(files[0].read_text())
+    assert log["K"] == 64 and len(log["loss_log"]) == 3 and len(log["u_L2_loss"]) == 3
+    assert len(log["Phis_state_dict"]) == len(S.Phis) and log["loss_log"] == S.loss_log
+    assert S.save_logs() != str(files[0])               # a second log gets a numbered name

@@ -287,3 +287,66 @@ def test_world_size_2_gloo_sharded_statistics(tmp_path):
     outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GLOO_OK" in outs[0][0], outs
+
+
+def test_loss_statistics_match_direct_formulas():
+    """pspde.losses.value_and_cotangents (one fused all-reduce of the fp64 sums and the dropped-path count) against the
+    reference's formulas (solver.py:164-192) evaluated directly, with and without non-finite trajectories."""
+    import torch as pt
+    from pspde import losses
+    g = pt.Generator().manual_seed(0)
+    K = 257
+    Y, gX, Zs = pt.randn(K, generator=g), pt.randn(K, generator=g), pt.rand(K, generator=g)
+    for bad in ((), (3, 100)):
+        Yb = Y.clone()
+        for i in bad:
+            Yb[i] = float("nan")
+        ok = pt.isfinite(Yb)
+        D = (Yb - gX).double()[ok]
+        Ke = float(ok.sum())
+        loss, wY, wZ, wG, n_bad = losses.value_and_cotangents("log-variance", Yb, gX, Zs, K)
+        assert n_bad.item() == len(bad)
+        assert abs(loss.item() - ((D ** 2).mean() - D.mean() ** 2).item()) < 1e-12
+        assert pt.allclose(wY[ok].double(), (D - D.mean()) * 2.0 / Ke, atol=1e-7) and bool((wY[~ok] == 0).all()) and wZ is None
+        loss, wY, _, _, _ = losses.value_and_cotangents("moment", Yb, gX, Zs, K)
+        assert abs(loss.item() - (D ** 2).mean().item()) < 1e-12
+        loss, wY, _, _, _ = losses.value_and_cotangents("variance", Yb, gX, Zs, K)
+        assert abs(loss.item() - pt.var(pt.exp(D)).item()) < 1e-10
+        loss, _, wZ, wG, _ = losses.value_and_cotangents("relative_entropy", Yb, gX, Zs, K)
+        assert abs(loss.item() - (Zs.double() + gX.double())[ok].mean().item()) < 1e-12 and pt.allclose(wZ[ok].double().sum(), pt.tensor(1.0, dtype=pt.float64), atol=1e-5)
+        # kernel-provided statistics take the place of the local sums
+        st = pt.tensor([D.sum(), (D ** 2).sum(), (Zs.double() + gX.double())[ok].sum(), float(len(bad))], dtype=pt.float64)
+        loss2, _, _, _, _ = losses.value_and_cotangents("log-variance", Yb, gX, Zs, K, stats=st)
+        assert abs(loss2.item() - ((D ** 2).mean() - D.mean() ** 2).item()) < 1e-12
+
+
+def test_general_solver_inject_draws_follow_the_reference_break():
+    """GeneralSolver 'inject' noise: one randn(K, d) per step until every path has stopped (solver.py:1093-1094 before :1106);
+    with N * delta_t > T the reference stops drawing early -- the CPU RNG stream must be consumed identically."""
+    import torch as pt
+    from pspde.general_solver import GeneralSolver
+
+    class Stub:
+        pass
+    G = Stub()
+    G.K, G.d, G.N, G.delta_t_np = 6, 3, 50, 0.01
+    G.problem = Stub()
+    G.problem.T = 0.3
+    pt.manual_seed(11)
+    t0 = pt.rand(G.K, 1) * G.problem.T
+    xis = GeneralSolver._draw_increments_cpu(G, t0)
+    after = pt.rand(1)
+    # replay: the reference's loop
+    pt.manual_seed(11)
+    t = pt.rand(G.K, 1) * G.problem.T
+    dt = pt.tensor(G.delta_t_np)
+    stopped, n_draws, ref = pt.zeros(G.K, dtype=pt.bool), 0, []
+    for n in range(G.N):
+        if int((~stopped).sum()) == 0:
+            break
+        ref.append(pt.randn(G.K, G.d)); n_draws += 1
+        ns = (t.squeeze() + dt) <= G.problem.T
+        t = t + dt * (ns & ~stopped).float().unsqueeze(1)
+        stopped = stopped | (~ns & ~stopped)
+    assert n_draws < G.N and pt.equal(after, pt.rand(1))           # same position in the RNG stream afterwards
+    assert pt.equal(xis[:n_draws], pt.stack(ref)) and bool((xis[n_draws:] == 0).all()) and xis.shape == (G.N, G.K, G.d)
