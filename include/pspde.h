@@ -174,7 +174,12 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
  * Z_sum (dLoss/dZsum == 0: log-variance, moment, variance, cross-entropy losses with the adaptive process).
  * pspde_fwd_ckpt_bytes = bytes for ALL ceil(K_local / 128) tiles: a K x N tape (C2: 7.1 GB, C5: 228 GB), so the caller
  * bounds it (pspde.fused: 8 GB by default) and passes what it affords, the same buffer and size to both calls.  ckpt == NULL in pspde_rollout_fwd_ckpt is the plain forward.
- * Paths with wY == 0 contribute nothing (even if they diverged). */
+ * Paths with wY == 0 contribute nothing (even if they diverged).
+ * With in-kernel Philox noise the s0 zeta columns of a row are NOT written (the row layout and C stay as above): zeta_unit
+ * is a function of (path, step, Philox key) alone and pspde_grad_from_fwd_ckpt -- like the wave-checkpointed backward when
+ * dLoss/dZsum == 0 and cfg->adaptive != 0 -- regenerates wY_k zeta_unit inside the gradient kernel (grad_tc2_kernel: hidden
+ * cotangents and weight gradient on tcgen05, operand rows [a0 | h1 | h2] by TMA): 672 instead of 1 088 bytes per sample
+ * at the C2 shape.  With injected noise the zeta columns are written and the older gradient kernel reads them. */
 size_t pspde_fwd_ckpt_bytes(const pspde_cfg* cfg);
 int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,
                            const float* y0, const float* xi, float* X_N, float* Y_N, float* gX, float* Zsum,
