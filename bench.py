@@ -250,6 +250,8 @@ class Rig:
         pt.cuda.set_device(self.local)
         self.dev = pt.device("cuda", self.local)
         if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner to stdout,
+                os.environ["NCCL_DEBUG"] = "WARN"                           # in front of the one JSON line
             td.init_process_group("nccl", device_id=self.dev)
         self.flush = pt.empty(256 << 20, dtype=pt.uint8, device=self.dev)     # > 126 MB L2
 

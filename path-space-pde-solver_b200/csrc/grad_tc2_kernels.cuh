@@ -5,17 +5,23 @@
 //     dtheta = sum_samples J_theta Z(a0)' zeta,      zeta = wY[path] sqrt(dt) xi[path, step]   (adaptive process, no dL/dZ_sum)
 // The checkpoint holds, per (tile, step), one row of 128 paths for every column of [a0 | h1 | h2] (RolloutParams::ckpt with
 // ckpt_zeta == 0); zeta is regenerated from the Philox key.  A stage is 32 samples.  Per stage:
-//     X [64 x 64]  = W2h [64 x s0] . [zeta_hi | zeta_lo]' [s0 x 64]     hidden MMA 1: tcgen05 SS, M = 64 (hidden slot), K = zeta column,
-//                  + W2h_lo . zeta_hi' (columns 0..31)                  N = (sample, hi | lo): the three 3xTF32 products in TWO passes
-//     delta_2 = (X[h2 rows, 0..31] + X[h2 rows, 32..63]) * act'(h2)     epilogue warps (TMEM -> registers -> TMEM in place + shared)
-//     X[h1 rows] += W1h [32 x 32] . [delta_2_hi | delta_2_lo]' ...      hidden MMA 2 (the delta_2 rows of W1h are zero: they add 0)
-//     delta_1 = (X[h1 rows, 0..31] + X[h1 rows, 32..63]) * act'(h1)
+//     X [128 x 64] = [W2h_hi ; W2h_lo] [128 x s0] . [zeta_hi | zeta_lo]' [s0 x 64]   hidden MMA 1: tcgen05 SS, M = 128 = (hi | lo weights,
+//                                                                    hidden slot), K = zeta column, N = (hi | lo, sample): all four
+//                                                                    hi / lo products of 3xTF32 (+ lo.lo) in ONE pass of s0 / 8 MMAs
+//     delta_2 = (X[r, 0..31] + X[r, 32..63] + X[64 + r, 0..31] + X[64 + r, 32..63]) * act'(h2)     r = h2 slot; epilogue warps:
+//                                                                    TMEM -> registers (the W_lo rows through shared memory)
+//                                                                    -> TMEM in place + a sample-major shared copy
+//     X[h1 rows] += [W1h_hi ; W1h_lo] [128 x 32] . [delta_2_hi | delta_2_lo]'           hidden MMA 2 (the delta_2 rows of W1h are zero:
+//                                                                    the MMA adds exact zeros to rows that already hold operands)
+//     delta_1 = (the same four-term sum over the h1 slots) * act'(h1)
 //     D0 [zeta col x act col]  += zeta'  . act      M = 128, N = s0 + 64, K = sample:  A = zeta' in TENSOR MEMORY, B = act rows (TMA, SW128)
-//     D1 [delta row x act col] += delta' . act      M = 64,  N = s0 + 32, K = sample:  A = X itself: the epilogues leave hi(delta) in
-//                                                   columns 0..31 and lo(delta) in columns 32..63 of the rows they read
+//     D1 [delta row x act col] += delta' . act      M = 128 (64 used), N = s0 + 32, K = sample:  A = X itself: the epilogues leave
+//                                                   hi(delta) in columns 0..31 and lo(delta) in columns 32..63 of rows 0..63
+// Every product is FP32-equivalent (tc_sm100.cuh); hi = trunc_tf32(x) (what the tensor core keeps of a raw FP32 operand), lo = x - hi.
 // Measured on this part (pspde_mma_probe): ONE tcgen05.mma costs its issuing thread >= 52 cycles whatever its shape
-// (95 at N = 176), and a commit -> mbarrier round trip ~ 800 cycles.  Hence: as few MMA instructions as possible (hi | lo stacked
-// along N), and every buffer between two dependent MMAs double-buffered so that the round trips of neighbouring stages overlap.
+// (95 at N = 176), a commit -> mbarrier round trip ~ 800 cycles, and two issuing threads are slower than one.  Hence: as few MMA
+// instructions as possible -- 41 per 32-sample stage: 13 + 4 hidden (hi | lo stacked along M and N), 24 weight-gradient -- and every
+// buffer between two dependent MMAs double-buffered so that the round trips of neighbouring stages overlap.
 //
 // Where the operands live:
 //   zeta    Philox -> shared, sample-major K-major tile zk[(col >> 2) * LBO + (sample | 32 lo) * 16 + (col & 3) * 4]: the B operand of
@@ -23,16 +29,18 @@
 //           hi, lo): the A operand of dW0
 //   act     TMA (CU_TENSOR_MAP_SWIZZLE_128B) -> shared [column][32 samples], a ring of three landing buffers (= the hi operand);
 //           dead paths zeroed in place and the lo tile (two buffers) formed by 4 warps
-//   delta   X (tensor memory, M = 64: hidden slot r at lane 32 (r >> 4) + (r & 15); two buffers) -> registers -> X in place and,
-//           delta_2 only, the sample-major shared tile dk (two buffers)
-//   weights W2h = [W2[h2 rows]; W2[h1 rows]] (64 x s0), W1h = [0; W1[h1 rows -> h2]] (64 x 32): shared, K-major, hi and lo, once per CTA
+//   delta   X (tensor memory, lane = row, two buffers) -> registers -> X in place and, delta_2 only, the sample-major shared tile dk
+//           (two buffers)
+//   weights [W2h_hi ; W2h_lo] (128 x s0), W2h = [W2[h2 rows]; W2[h1 rows]]; [W1h_hi ; W1h_lo] (128 x 32), W1h = [0; W1[h1 rows -> h2]]:
+//           shared, K-major, once per CTA
 //
 // Warp roles (704 threads, one CTA per SM):
-//   warps 0-7   epilogues of the hidden MMAs (lane quarter = warp & 3, 16 samples each): quarters 0, 1 delta_2, quarters 2, 3 delta_1
+//   warps 0-7   epilogues of the hidden MMAs (lane quarter = warp & 3: q & 1 = delta_2 | delta_1 rows, q >= 2 = the W_lo partner rows;
+//               16 samples each)
 //   warps 8-15  zeta: Philox + Box-Muller (one warp = one 4-column group x 32 samples per call), then the tensor-memory copy
 //   warps 16-19 activation rows: dead-path fix-up + lo tile; accumulator flush (quarter = warp & 3)
 //   warp  20    TMA producer (one lane)
-//   warp  21    MMA issuer (one lane), software-pipelined: dW0(i) | hidden MMA 2 (i) | hidden MMA 1 (i + 1) | dW1(i)
+//   warp  21    MMA issuer (one lane), software-pipelined: hidden 2 (i) | hidden 1 (i + 1) | dW0(i + 1) | dW1(i)
 #pragma once
 #if !defined(PSPDE_EMULATE)
 #include "grad_tc_kernels.cuh"
@@ -44,15 +52,16 @@ constexpr int kG2Sub = kCkP / kG2S;       // stages per (tile, step)
 constexpr int kG2Threads = 22 * 32;
 constexpr int kG2FlushStages = 16;        // accumulator flush period (the tensor core's FP32 accumulation is not round-to-nearest)
 constexpr int kG2WGen = 8, kG2WLo = 16, kG2WTma = 20, kG2WMma = 21;
-constexpr int kG2GenThreads = 256, kG2LoThreads = 128, kG2EpiThreads = 128;   // epilogue threads per hidden MMA
+constexpr int kG2GenThreads = 256, kG2LoThreads = 128, kG2EpiThreads = 128, kG2EpiMain = 64;   // epilogue threads per hidden MMA (main + partner rows); those that finish a row
 constexpr uint32_t kG2LboZ = 1040;        // bytes between 4-column groups of the sample-major tiles: (32 hi + 32 lo samples) x 16 B + 16
                                           // (LBO / 4 = 4 mod 32: the column-wise read-back and the scalar stores hit distinct banks)
-constexpr uint32_t kG2LboW = 1024;        // weights: 64 rows x 16 B per 4-column group
+constexpr uint32_t kG2LboW = 2048;        // weights: 128 rows ([hi (64) ; lo (64)] stacked along M) x 16 B per 4-column group
 
 struct GradTc2Geom {
   int s0, act_rows, nA, nA1, dense, kz;
   uint32_t act_bytes;
-  uint32_t o_act[3], o_lo[2], o_zk, o_dk[2], o_w2[2], o_w1[2], o_bar, total;   // bytes from the 1 KB aligned base; w: [hi, lo]
+  int nA1p;                                 // N of the dW1 MMA (M = 128: a multiple of 16 >= nA1)
+  uint32_t o_act[3], o_lo[2], o_zk, o_dk[2], o_w2, o_w1, o_xb[2], o_bar, total;  // bytes from the 1 KB aligned base
   int c_d0, c_d1, c_a0[2], c_x[2];                                             // tensor-memory columns
 };
 
@@ -62,23 +71,28 @@ inline bool grad_tc2_geom(const NetGeom& g, int s0, GradTc2Geom& t) {
   t.dense = g.kind == NET_DENSENET ? 1 : 0;
   t.s0 = s0; t.act_rows = s0 + 64; t.kz = s0 / 4;
   t.nA = (t.act_rows + 15) / 16 * 16;     // N of an M = 128 MMA is a multiple of 16
-  t.nA1 = s0 + 32;                        // M = 64: a multiple of 8
+  t.nA1 = s0 + 32;                        // activation columns the hidden cotangents meet: [a0 | h1]
+  t.nA1p = (t.nA1 + 15) / 16 * 16;
   if (t.nA > 256 || t.act_rows > 256) return false;
   int c = 0;
   t.c_d0 = c; c += t.nA;
-  t.c_d1 = c; c += t.nA1;
+  t.c_d1 = c; c += t.nA1p;
   t.c_a0[0] = c; c += kG2S; t.c_a0[1] = c; c += kG2S;
   t.c_x[0] = c; c += 2 * kG2S; t.c_x[1] = c; c += 2 * kG2S;
   if (c > 512) return false;
-  t.act_bytes = (uint32_t)t.nA * 128u;    // a multiple of 2 KB
+  // An MMA of N = nA reads nA - act_rows (< 16) rows past the data of a buffer: they alias the head of the next buffer (finite
+  // values; those accumulator columns are never read), so the buffers are act_rows rows apart and only the last one is padded.
+  t.act_bytes = (uint32_t)t.act_rows * 128u;    // a multiple of 1 KB (act_rows % 8 == 0)
   uint32_t o = 0;
   for (int s = 0; s < 3; ++s) { t.o_act[s] = o; o += t.act_bytes; }      // TMA landing ring = the hi operand
   for (int s = 0; s < 2; ++s) { t.o_lo[s] = o; o += t.act_bytes; }
+  o += (uint32_t)(t.nA - t.act_rows) * 128u;
   t.o_zk = o; o += (uint32_t)t.kz * kG2LboZ;
   for (int h = 0; h < 2; ++h) { t.o_dk[h] = o; o += 8u * kG2LboZ; }
+  for (int h = 0; h < 2; ++h) { t.o_xb[h] = o; o += 32u * 32u * 4u; }    // partner-row exchange of the two epilogue groups
   o = (o + 127u) & ~127u;
-  for (int h = 0; h < 2; ++h) { t.o_w2[h] = o; o += (uint32_t)t.kz * kG2LboW; }
-  for (int h = 0; h < 2; ++h) { t.o_w1[h] = o; o += 8u * kG2LboW; }
+  t.o_w2 = o; o += (uint32_t)t.kz * kG2LboW;
+  t.o_w1 = o; o += 8u * kG2LboW;
   t.o_bar = (o + 15u) & ~15u; o = t.o_bar + 32u * 8u;
   t.total = o + 1024u;
   return t.total <= 227u * 1024u;
@@ -124,14 +138,14 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     for (int s = 0; s < 3; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_free[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&bar_lo[s], kG2LoThreads); tc::mbar_init(&bar_lofree[s], 1); }
     tc::mbar_init(bar_zk, kG2GenThreads); tc::mbar_init(bar_a0, kG2GenThreads);
-    tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, kG2EpiThreads); tc::mbar_init(bar_d2, 1);
-    tc::mbar_init(bar_e2, kG2EpiThreads);
+    tc::mbar_init(bar_d1, 1); tc::mbar_init(bar_w0, 1); tc::mbar_init(bar_e1, kG2EpiMain); tc::mbar_init(bar_d2, 1);
+    tc::mbar_init(bar_e2, kG2EpiMain);
     tc::mbar_init(bar_acc_full, 1); tc::mbar_init(bar_acc_empty, 4);
     tc::mbar_init(bar_acc1_full, 1); tc::mbar_init(bar_acc1_empty, 4);
     tc::mbar_fence_init();
   }
   if (tid == kG2WTma * 32) tc::tma_prefetch_desc(&tmap);
-  for (uint32_t q = tid; q < tg.o_w2[0] / 16u; q += kG2Threads) reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t q = tid; q < tg.o_w2 / 16u; q += kG2Threads) reinterpret_cast<float4*>(smem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   // weights of the hidden MMAs, K-major (hidden slot m, column k) at (k >> 2) * 1 KB + m * 16 + (k & 3) * 4, hi and lo.
   // slot m < 32: h2 column m (delta_2), else h1 column m - 32 (delta_1)
   {
@@ -148,8 +162,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       float hi, lo;
       tc::tf32_split(w, hi, lo);
       const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
-      *reinterpret_cast<float*>(smem + tg.o_w2[0] + off) = hi;
-      *reinterpret_cast<float*>(smem + tg.o_w2[1] + off) = lo;
+      *reinterpret_cast<float*>(smem + tg.o_w2 + off) = hi;                  // rows 0..63: hi, rows 64..127: lo
+      *reinterpret_cast<float*>(smem + tg.o_w2 + off + 64u * 16u) = lo;
     }
     for (int q = tid; q < 64 * 32; q += kG2Threads) {
       const int m = q & 63, k = q >> 6;           // k = h2 column (delta_2 slot)
@@ -161,8 +175,8 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       float hi, lo;
       tc::tf32_split(w, hi, lo);
       const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
-      *reinterpret_cast<float*>(smem + tg.o_w1[0] + off) = hi;
-      *reinterpret_cast<float*>(smem + tg.o_w1[1] + off) = lo;
+      *reinterpret_cast<float*>(smem + tg.o_w1 + off) = hi;
+      *reinterpret_cast<float*>(smem + tg.o_w1 + off + 64u * 16u) = lo;
     }
   }
   tc::fence_proxy_async();
@@ -186,52 +200,70 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 
   if (warp < kG2WGen) {
     // =============================================================== epilogues of the hidden MMAs
-    const int q = warp & 3, sh = warp >> 2;          // lane quarter; 16-sample half.  Hidden slot r = 16 q + lane (lane < 16)
-    const bool is_d2 = q < 2;
-    const int c = (16 * q + (lane & 15)) & 31;       // column inside the hidden segment
+    // X rows (= tensor-memory lanes, M = 128): 0..31 delta_2 slots, 32..63 delta_1 slots -- products with W_hi -- and
+    // 64..127 the same slots' products with W_lo (the "partner" rows).  Quarter q of the lanes: q & 1 = which delta,
+    // q >= 2 = partner.  A partner warp only adds its hi | lo partial sums and hands them over through shared memory.
+    const int q = warp & 3, sh = warp >> 2;          // lane quarter; 16-sample half
+    const bool is_d2 = (q & 1) == 0, partner = q >= 2;
+    const int c = lane;                              // column inside the hidden segment
     const int sg = is_d2 ? 2 : 1;
-    const bool live = lane < 16 && c < g.dims[sg];
+    const bool live = c < g.dims[sg];
     const int h_row = tg.s0 + (is_d2 ? 32 : 0) + c;  // tile row of the hidden activation
     const uint32_t lane_addr = ((uint32_t)(32 * q)) << 16;
-    // debug (CTA 0): warp 0 [0] wait hidden MMA 1, [1] wait lo, [3] delta_2; warp 2 [4] waits, [5] delta_1
+    float* xb = reinterpret_cast<float*>(smem + tg.o_xb[is_d2 ? 0 : 1]) + (16 * sh) * 32 + lane;     // [sample][slot]
+    // debug (CTA 0): warp 0 [0] wait hidden MMA 1, [1] wait lo, [3] delta_2; warp 1 [4] waits, [5] delta_1
     PhaseTimer pt_;
-    pt_.start(prm.prof, (lane == 0 && (warp == 0 || warp == 2)) ? 0 : 1);
+    pt_.start(prm.prof, (lane == 0 && (warp == 0 || warp == 1)) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
       const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
       tc::mbar_wait(is_d2 ? bar_d1 : bar_d2, p1);
       pt_.mark(warp == 0 ? 0 : 4);
-      tc::mbar_wait(&bar_lo[s], p2);                 // the hidden activations of dead paths are zero from here on
+      if (!partner) tc::mbar_wait(&bar_lo[s], p2);   // the hidden activations of dead paths are zero from here on
       pt_.mark(warp == 0 ? 1 : 4);
       tc::fence_after_sync();
-      const uint8_t* tH = smem + tg.o_act[it % 3];
       const uint32_t xa = tbase + lane_addr + (uint32_t)tg.c_x[s] + 16u * (uint32_t)sh;
       float P[16], Q[16];
-      tc::tmem_ld16(xa, P);                          // hi.hi + lo.hi partial sums
-      tc::tmem_ld16(xa + 32u, Q);                    // hi.lo partial sums
+      tc::tmem_ld16(xa, P);                          // . x_hi partial sums
+      tc::tmem_ld16(xa + 32u, Q);                    // . x_lo partial sums
+      if (partner) {
+        tc::wait_ld();
+#pragma unroll
+        for (int n = 0; n < 16; ++n) xb[32 * n] = P[n] + Q[n];
+        tc::fence_before_sync();
+        gt_named_bar(is_d2 ? 6 : 7, kG2EpiThreads);
+        continue;
+      }
+      const uint8_t* tH = smem + tg.o_act[it % 3];
       float4 h4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) h4[j] = *reinterpret_cast<const float4*>(tH + gt_swz(h_row, 4 * sh + j));
       tc::wait_ld();
+      gt_named_bar(is_d2 ? 6 : 7, kG2EpiThreads);    // the partner rows' sums are in shared memory
+      if (warp == 0) pt_.mark(24);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float hv[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           // act': relu(.)^2 -> 2 relu(pre) = 2 sqrt(h) (sqrt.approx: 1 ulp); tanh -> 1 - h^2
-          const float dv = live ? (P[4 * j + i] + Q[4 * j + i]) * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
-          tc::tf32_split(dv, P[4 * j + i], Q[4 * j + i]);       // P <- hi, Q <- lo
+          const float pre = (P[4 * j + i] + Q[4 * j + i]) + xb[32 * (4 * j + i)];
+          const float dv = live ? pre * (tg.dense ? 2.0f * gt_sqrt_approx(hv[i]) : (1.0f - hv[i] * hv[i])) : 0.f;
+          P[4 * j + i] = trunc_tf32(dv);                        // P <- hi (what the tensor core would keep of dv anyway),
+          Q[4 * j + i] = dv - P[4 * j + i];                     // Q <- lo (exact; its own truncation loses < 2^-21 |dv|)
         }
       }
+      if (warp == 0) pt_.mark(25);
       tc::tmem_st16(xa, P);                          // in place: the A operand of dW1
       tc::tmem_st16(xa + 32u, Q);
-      if (is_d2 && lane < 16) {                      // sample-major copy [hi | lo]: B operand of hidden MMA 2
+      if (is_d2) {                                   // sample-major copy [hi | lo]: B operand of hidden MMA 2
         uint8_t* dk = smem + tg.o_dk[s] + (uint32_t)(c >> 2) * kG2LboZ + (uint32_t)(c & 3) * 4u + (uint32_t)(16 * sh) * 16u;
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
           *reinterpret_cast<float*>(dk + 16 * n) = P[n];
           *reinterpret_cast<float*>(dk + 512 + 16 * n) = Q[n];
         }
+        if (warp == 0) pt_.mark(26);
         tc::fence_proxy_async();
       }
       tc::wait_st();
@@ -268,8 +300,9 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         const float z1 = (wk != 0.f && 4 * gq + 1 < prm.d) ? sc * e4.y : 0.f;
         const float z2 = (wk != 0.f && 4 * gq + 2 < prm.d) ? sc * e4.z : 0.f;
         const float z3 = (wk != 0.f && 4 * gq + 3 < prm.d) ? sc * e4.w : 0.f;
-        tc::tf32_split(z0, zh[i].x, zl[i].x); tc::tf32_split(z1, zh[i].y, zl[i].y);
-        tc::tf32_split(z2, zh[i].z, zl[i].z); tc::tf32_split(z3, zh[i].w, zl[i].w);
+        // hi = what the tensor core keeps of z (truncation), lo = z - hi exactly (its own truncation loses < 2^-21 |z|)
+        zh[i].x = trunc_tf32(z0); zl[i].x = z0 - zh[i].x; zh[i].y = trunc_tf32(z1); zl[i].y = z1 - zh[i].y;
+        zh[i].z = trunc_tf32(z2); zl[i].z = z2 - zh[i].z; zh[i].w = trunc_tf32(z3); zl[i].w = z3 - zh[i].w;
       }
       pt_.mark(6);
       tc::mbar_wait(bar_d1, p1 ^ 1u);                // hidden MMA 1 of the previous stage has read the tile
@@ -309,7 +342,45 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     const int qtr = warp & 3;
     const int pos = t & 7, r0 = t >> 3;              // chunk position; rows r0 + 16 i keep (row & 7), hence the sample quad
     const int j = pos ^ (r0 & 7);
-    uint32_t n_flush = 0;
+    uint32_t n_flush = 0, n_flush1 = 0;
+    bool d1_pending = false;
+    float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nA);
+    const uint32_t la = ((uint32_t)(32 * qtr)) << 16;
+    // 32 columns per tensor-memory round trip (the load latency, not the REDs, is what a flush costs); pad columns / lanes skipped
+    auto flush_cols = [&](int tile, int ccol, int c_begin, int c_end, bool on) {
+      int c0 = c_begin;
+      for (; c0 + 32 <= c_end; c0 += 32) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0 + 8 * u), v[u]);
+        tc::wait_ld();
+        if (on) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u, 32 * qtr + lane), v[u][0], v[u][1], v[u][2], v[u][3]);
+            g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u + 4, 32 * qtr + lane), v[u][4], v[u][5], v[u][6], v[u][7]);
+          }
+        }
+      }
+      for (; c0 < c_end; c0 += 8) {
+        float v[8];
+        tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0), v);
+        tc::wait_ld();
+        if (on) {
+          g2_red_add4(gp + g2_part_index(tg.nA, tile, c0, 32 * qtr + lane), v[0], v[1], v[2], v[3]);
+          g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 4, 32 * qtr + lane), v[4], v[5], v[6], v[7]);
+        }
+      }
+    };
+    auto flush_d1 = [&]() {
+      tc::mbar_wait(bar_acc1_full, n_flush1 & 1u);
+      tc::fence_after_sync();
+      flush_cols(1, tg.c_d1, 0, tg.nA1, qtr < 2);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_acc1_empty);
+      ++n_flush1;
+    };
     PhaseTimer pt_;      // debug (CTA 0, warp 16): [11] wait TMA, [12] fix-up + lo pass, [13] flush
     pt_.start(prm.prof, (lane == 0 && warp == kG2WLo) ? 0 : 1);
     for (int it = 0; it < n_it; ++it) {
@@ -354,55 +425,25 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       tc::fence_proxy_async();
       tc::mbar_arrive(&bar_lo[s]);
       pt_.mark(12);
+      // Accumulator flush: raw accumulators -> this CTA's partial (RED.128, one writer per address, L2 resident).  D0 is complete
+      // as soon as dW0 of the flush stage is; D1 only after dW1, which the issuer places AFTER dW0 of the next stage -- and that
+      // one needs the next lo tile from these warps.  So: D0 right after the lo pass of the flush stage, D1 after the lo pass
+      // of the stage that follows (or after the loop).
+      if (d1_pending) { flush_d1(); d1_pending = false; pt_.mark(13); }
       const bool flush_now = ((it + 1 + flush_off) % flush_stages == 0) || it == n_it - 1;
       if (flush_now) {
-        // raw accumulators -> this CTA's partial [tile][activation column][lane] (RED.ADD, one writer per address, L2 resident).
-        // D0 first -- it is complete as soon as dW0 of this stage is, long before dW1 -- then D1; pad columns / lanes are skipped.
-        float* gp = prm.grad_partial + (size_t)blockIdx.x * (2 * 128 * tg.nA);
-        const uint32_t la = ((uint32_t)(32 * qtr)) << 16;
         tc::mbar_wait(bar_acc_full, n_flush & 1u);
         tc::fence_after_sync();
-        const bool zlane = 32 * qtr + lane < tg.s0;
-        // 32 columns per tensor-memory round trip (the load latency, not the REDs, is what a flush costs)
-        auto flush_cols = [&](int tile, int ccol, int c_begin, int c_end, bool on) {
-          int c0 = c_begin;
-          for (; c0 + 32 <= c_end; c0 += 32) {
-            float v[4][8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0 + 8 * u), v[u]);
-            tc::wait_ld();
-            if (on) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u, 32 * qtr + lane), v[u][0], v[u][1], v[u][2], v[u][3]);
-                g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 8 * u + 4, 32 * qtr + lane), v[u][4], v[u][5], v[u][6], v[u][7]);
-              }
-            }
-          }
-          for (; c0 < c_end; c0 += 8) {
-            float v[8];
-            tc::tmem_ld8(tbase + la + (uint32_t)(ccol + c0), v);
-            tc::wait_ld();
-            if (on) {
-              g2_red_add4(gp + g2_part_index(tg.nA, tile, c0, 32 * qtr + lane), v[0], v[1], v[2], v[3]);
-              g2_red_add4(gp + g2_part_index(tg.nA, tile, c0 + 4, 32 * qtr + lane), v[4], v[5], v[6], v[7]);
-            }
-          }
-        };
-        flush_cols(0, tg.c_d0, 0, tg.act_rows, zlane);
+        flush_cols(0, tg.c_d0, 0, tg.act_rows, 32 * qtr + lane < tg.s0);
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(bar_acc_empty);
-        tc::mbar_wait(bar_acc1_full, n_flush & 1u);
-        tc::fence_after_sync();
-        flush_cols(1, tg.c_d1, 0, tg.nA1, lane < 16);
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(bar_acc1_empty);
         ++n_flush;
+        d1_pending = true;
         pt_.mark(13);
       }
     }
+    if (d1_pending) flush_d1();
   } else if (warp == kG2WTma) {
     // =============================================================== TMA producer
     if (lane == 0) {
@@ -422,11 +463,10 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
     // =============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t sb = tc::smem_u32(smem);
-      const uint32_t id_h64 = tc::idesc_tf32(64, 2 * kG2S), id_h32 = tc::idesc_tf32(64, kG2S);
-      const uint32_t id_w0 = tc::idesc_tf32(128, tg.nA), id_w1 = tc::idesc_tf32(64, tg.nA1);
+      const uint32_t id_h = tc::idesc_tf32(128, 2 * kG2S);
+      const uint32_t id_w0 = tc::idesc_tf32(128, tg.nA), id_w1 = tc::idesc_tf32(128, tg.nA1p);
       // descriptors: only the 14-bit start address (>> 4) changes from one MMA to the next -> add to the low word
-      const uint64_t dw_hi = tc::smem_desc(sb + tg.o_w2[0], kG2LboW, 128u), dw_lo = tc::smem_desc(sb + tg.o_w2[1], kG2LboW, 128u);
-      const uint64_t dv_hi = tc::smem_desc(sb + tg.o_w1[0], kG2LboW, 128u), dv_lo = tc::smem_desc(sb + tg.o_w1[1], kG2LboW, 128u);
+      const uint64_t dw = tc::smem_desc(sb + tg.o_w2, kG2LboW, 128u), dv = tc::smem_desc(sb + tg.o_w1, kG2LboW, 128u);
       const uint64_t dz = tc::smem_desc(sb + tg.o_zk, kG2LboZ, 128u);
       const uint64_t dd0 = tc::smem_desc(sb + tg.o_dk[0], kG2LboZ, 128u), dd1 = tc::smem_desc(sb + tg.o_dk[1], kG2LboZ, 128u);
       const uint64_t dah0 = tc::smem_desc_sw128(sb + tg.o_act[0]), dah1 = tc::smem_desc_sw128(sb + tg.o_act[1]);
@@ -434,27 +474,20 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
       const uint64_t dal0 = tc::smem_desc_sw128(sb + tg.o_lo[0]), dal1 = tc::smem_desc_sw128(sb + tg.o_lo[1]);
       const uint32_t cx0 = (uint32_t)tg.c_x[0], cx1 = (uint32_t)tg.c_x[1];
       constexpr uint64_t kStepW = (2u * kG2LboW) >> 4, kStepZ = (2u * kG2LboZ) >> 4, kStepA = 32u >> 4;
-      // X (+)= W . [x_hi | x_lo]'  (N = 64)  then  X[:, 0..31] += W_lo . x_hi'  (N = 32): the three 3xTF32 products in two passes
-      auto hidden_mma = [&](uint64_t w_hi, uint64_t w_lo, uint64_t x, int nk8, uint32_t dcol, bool acc0) {
+      // X (+)= [W_hi ; W_lo] . [x_hi | x_lo]'  (M = 128, N = 64): all four hi / lo products in ONE pass; the epilogue adds
+      // X[r, 0..31] + X[r, 32..63] + X[64 + r, 0..31] + X[64 + r, 32..63] (lo . lo, 2^-22 relative, comes along for free)
+      auto hidden_mma = [&](uint64_t w, uint64_t x, int nk8, uint32_t dcol, bool acc0) {
         if (nk8 == 13) {                             // the C2 / C5 shape (s0 = 104): fully unrolled, descriptor offsets are immediates
 #pragma unroll
           for (int ks = 0; ks < 13; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
-#pragma unroll
-          for (int ks = 0; ks < 13; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+            tc::mma_tf32_ss(tbase + dcol, w + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h, acc0 || ks > 0);
         } else if (nk8 == 4) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+            tc::mma_tf32_ss(tbase + dcol, w + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h, acc0 || ks > 0);
         } else {
           for (int ks = 0; ks < nk8; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_hi + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h64, acc0 || ks > 0);
-          for (int ks = 0; ks < nk8; ++ks)
-            tc::mma_tf32_ss(tbase + dcol, w_lo + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h32, true);
+            tc::mma_tf32_ss(tbase + dcol, w + (uint64_t)ks * kStepW, x + (uint64_t)ks * kStepZ, id_h, acc0 || ks > 0);
         }
       };
       // D (+)= A' (tensor memory: hi at column ca, lo at ca + 32) . act rows of buffer s over the 32 samples of the stage
@@ -469,58 +502,67 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
             tc::mma_tf32_ts(tbase + dcol, a + 8u * (uint32_t)ks, b + (uint64_t)ks * kStepA, idesc, acc0 || pass > 0 || ks > 0);
         }
       };
-      uint32_t n_flush = 0;
+      uint32_t nf0 = 0, nf1 = 0;                      // flushes of D0 / D1 committed so far
       // debug (CTA 0): [16] wait zeta' + lo (+ flush), [17] dW0, [18] wait delta_2, [19] hidden MMA 2, [20] wait zeta tile,
       // [21] hidden MMA 1, [22] wait delta_1, [23] dW1 + commits
       PhaseTimer pt_;
       pt_.start(prm.prof, 0);
-      if (n_it > 0) {                                 // prologue: hidden MMA 1 of stage 0
-        tc::mbar_wait(bar_zk, 0u);
-        tc::fence_after_sync();
-        hidden_mma(dw_hi, dw_lo, dz, tg.kz / 2, cx0, false);
-        tc::mma_commit(bar_d1);
-      }
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
-        const uint32_t p1 = (uint32_t)it & 1u, p2 = (uint32_t)(it >> 1) & 1u;
-        const bool first = it == 0 || ((it + flush_off) % flush_stages) == 0;   // accumulators start over after a flush
-        const bool flush_now = ((it + 1 + flush_off) % flush_stages == 0) || it == n_it - 1;
-        if (first && n_flush > 0) tc::mbar_wait(bar_acc_empty, (n_flush - 1u) & 1u);      // D0 has been read out
-        // dW0(it): zeta' . act
-        tc::mbar_wait(bar_a0, p1);
-        tc::mbar_wait(&bar_lo[s], p2);
+      auto is_first = [&](int j) { return j == 0 || ((j + flush_off) % flush_stages) == 0; };   // accumulators start over after a flush
+      auto is_flush = [&](int j) { return ((j + 1 + flush_off) % flush_stages == 0) || j == n_it - 1; };
+      // dW0(j): zeta' . act
+      auto issue_dw0 = [&](int j) {
+        const bool first = is_first(j);
+        if (first && nf0 > 0) tc::mbar_wait(bar_acc_empty, (nf0 - 1u) & 1u);          // D0 has been read out
+        tc::mbar_wait(bar_a0, (uint32_t)j & 1u);
+        tc::mbar_wait(&bar_lo[j & 1], (uint32_t)(j >> 1) & 1u);
         pt_.mark(16);
         tc::fence_after_sync();
-        wgrad_mma((uint32_t)tg.c_a0[0], s, it % 3, (uint32_t)tg.c_d0, id_w0, !first);
+        wgrad_mma((uint32_t)tg.c_a0[0], j & 1, j % 3, (uint32_t)tg.c_d0, id_w0, !first);
         tc::mma_commit(bar_w0);
-        if (flush_now) tc::mma_commit(bar_acc_full);
+        if (is_flush(j)) { tc::mma_commit(bar_acc_full); ++nf0; }
         pt_.mark(17);
-        // hidden MMA 2 (it): X[h1 rows] += W1h . delta_2'
+      };
+      // dW1(j): [delta_2 | delta_1]' . act
+      auto issue_dw1 = [&](int j) {
+        const bool first = is_first(j);
+        tc::mbar_wait(bar_e2, (uint32_t)j & 1u);
+        if (first && nf1 > 0) tc::mbar_wait(bar_acc1_empty, (nf1 - 1u) & 1u);         // D1 has been read out
+        pt_.mark(22);
+        tc::fence_after_sync();
+        wgrad_mma((j & 1) ? cx1 : cx0, j & 1, j % 3, (uint32_t)tg.c_d1, id_w1, !first);
+        tc::mma_commit(&bar_free[j % 3]);
+        tc::mma_commit(&bar_lofree[j & 1]);
+        if (is_flush(j)) { tc::mma_commit(bar_acc1_full); ++nf1; }
+        pt_.mark(23);
+      };
+      if (n_it > 0) {                                 // prologue: hidden MMA 1 and dW0 of stage 0
+        tc::mbar_wait(bar_zk, 0u);
+        tc::fence_after_sync();
+        hidden_mma(dw, dz, tg.kz / 2, cx0, false);
+        tc::mma_commit(bar_d1);
+        issue_dw0(0);
+      }
+      // steady state: hidden 2 (it) | hidden 1 (it + 1) | dW0(it + 1) | dW1(it) -- the delta_1 epilogue of stage it (the longest
+      // dependent hop) runs under hidden 1 and dW0 of the next stage
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it & 1;
+        const uint32_t p1 = (uint32_t)it & 1u;
         tc::mbar_wait(bar_e1, p1);
         pt_.mark(18);
         tc::fence_after_sync();
-        hidden_mma(dv_hi, dv_lo, s ? dd1 : dd0, 4, s ? cx1 : cx0, true);
+        hidden_mma(dv, s ? dd1 : dd0, 4, s ? cx1 : cx0, true);
         tc::mma_commit(bar_d2);
         pt_.mark(19);
-        // hidden MMA 1 (it + 1): fills the tensor pipe while the delta_1 epilogue of stage it runs
         if (it + 1 < n_it) {
           tc::mbar_wait(bar_zk, p1 ^ 1u);
           pt_.mark(20);
           tc::fence_after_sync();
-          hidden_mma(dw_hi, dw_lo, dz, tg.kz / 2, s ? cx0 : cx1, false);
+          hidden_mma(dw, dz, tg.kz / 2, s ? cx0 : cx1, false);
           tc::mma_commit(bar_d1);
           pt_.mark(21);
+          issue_dw0(it + 1);
         }
-        // dW1(it): [delta_2 | delta_1]' . act
-        tc::mbar_wait(bar_e2, p1);
-        if (first && n_flush > 0) tc::mbar_wait(bar_acc1_empty, (n_flush - 1u) & 1u);     // D1 has been read out
-        pt_.mark(22);
-        tc::fence_after_sync();
-        wgrad_mma(s ? cx1 : cx0, s, it % 3, (uint32_t)tg.c_d1, id_w1, !first);
-        tc::mma_commit(&bar_free[it % 3]);
-        tc::mma_commit(&bar_lofree[s]);
-        if (flush_now) { tc::mma_commit(bar_acc1_full); ++n_flush; }
-        pt_.mark(23);
+        issue_dw1(it);
       }
     }
   }
@@ -532,7 +574,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
 
 // partial[cta][g2_part_index(tile, activation column m, lane)] -> grad_theta.
 //   tile 0: lane <-> zeta column n: W2[activation column m][n]
-//   tile 1: lane 32 q + l (l < 16) <-> hidden slot r = 16 q + l: r < 32 -> W1[m][r] (delta_2), else W0[m][r - 32] (delta_1)
+//   tile 1: lane r < 64 <-> hidden slot r: r < 32 -> W1[m][r] (delta_2), else W0[m][r - 32] (delta_1)
 // activation column m: checkpoint columns [a0 (s0) | h1 (32) | h2 (32)].  Fixed summation order, fp64.
 static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom tg, const float* __restrict__ partial, int nparts,
                                               float* __restrict__ out) {
@@ -548,8 +590,8 @@ static __global__ void reduce_grad_tc2_kernel(const NetGeom g, const GradTc2Geom
     int l, n;
     if (tile == 0) { l = 2; n = lane; }
     else {
-      if ((lane & 31) >= 16 || m >= tg.nA1) continue;
-      const int r = 16 * (lane >> 5) + (lane & 15);
+      if (lane >= 64 || m >= tg.nA1) continue;
+      const int r = lane;
       if (r < 32) { l = 1; n = r; } else { l = 0; n = r - 32; }
     }
     const LayerGeom& y = g.layer[l];

@@ -41,7 +41,9 @@ if eng.ckpt is not None:
                   "epi d1: waits", "epi d1: delta_1", "gen: Philox + Box-Muller", "gen: wait zeta tile free", "gen: zeta tile stores",
                   "gen: read-back + barrier", "gen: wait A0 free + st", "lo: wait TMA", "lo: fix-up + lo pass", "lo: flush",
                   "tma: wait free buffer", "tma: issue", "mma: wait zeta' + lo (+ flush)", "mma: dW0 issue", "mma: wait delta_2",
-                  "mma: hidden MMA 2 issue", "mma: wait zeta tile", "mma: hidden MMA 1 issue", "mma: wait delta_1", "mma: dW1 issue + commits"]
+                  "mma: hidden MMA 2 issue", "mma: wait zeta tile", "mma: hidden MMA 1 issue", "mma: wait delta_1", "mma: dW1 issue + commits",
+                  "epi d2 detail: ld + h LDS + wait_ld + group barrier", "epi d2 detail: sum + act' + split", "epi d2 detail: tmem st issue + 32 STS",
+                  "(unused)"]
     ms, c = profiled(lambda: eng.grad_from_rows(theta, wY, Call(offset=0), grad))
     stages = tiles_cta0 * eng.N * 4
     print("gradient kernel over the kept rows: %.2f ms, %.0f cycles per 32-sample stage" % (ms, ms * 1e-3 * 1.965e9 / stages))
