@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(int K, int N, int v
   for (int q = tid; q < K * N; q += blockDim.x) {
     const int k = q / N, n = q - k * N;
     float hi, lo;
-    tc::tf32_split(B[q], hi, lo);
+    tc::tf32_split_rn(B[q], hi, lo);
     // bit 5: the SWIZZLE_128B_BASE32B atom (4 k rows of 128 B, 32-byte chunk index xor-ed with the k row), atoms 512 B apart
     // bit 6: the same physical atom read as a K-major operand (K == 32: one 128 B row of k per n, 8 n rows = 1 KB)
     const uint32_t off = (variant & 64) ? (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)((((k >> 3) & 3) ^ (n & 3)) * 32) + (uint32_t)(k & 7) * 4u

@@ -160,7 +160,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         if (lr >= 0 && lr < y2.Kp) { const int idx = theta_index(g, 2, lr, k); if (idx >= 0) w = __ldg(prm.theta + idx); }
       }
       float hi, lo;
-      tc::tf32_split(w, hi, lo);
+      tc::tf32_split_rn(w, hi, lo);
       const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
       *reinterpret_cast<float*>(smem + tg.o_w2 + off) = hi;                  // rows 0..63: hi, rows 64..127: lo
       *reinterpret_cast<float*>(smem + tg.o_w2 + off + 64u * 16u) = lo;
@@ -173,7 +173,7 @@ static __global__ void __launch_bounds__(kG2Threads, 1) grad_tc2_kernel(const __
         if (lr >= 0 && lr < y1.Kp) { const int idx = theta_index(g, 1, lr, k); if (idx >= 0) w = __ldg(prm.theta + idx); }
       }
       float hi, lo;
-      tc::tf32_split(w, hi, lo);
+      tc::tf32_split_rn(w, hi, lo);
       const uint32_t off = (uint32_t)(k >> 2) * kG2LboW + (uint32_t)m * 16u + (uint32_t)(k & 3) * 4u;
       *reinterpret_cast<float*>(smem + tg.o_w1 + off) = hi;
       *reinterpret_cast<float*>(smem + tg.o_w1 + off + 64u * 16u) = lo;

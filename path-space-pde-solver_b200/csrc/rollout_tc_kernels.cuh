@@ -91,7 +91,7 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
       if (idx >= 0) w = __ldg(th + idx);
     }
     float h, r;
-    tc::tf32_split(w, h, r);
+    tc::tf32_split_rn(w, h, r);
     *reinterpret_cast<float*>(hi + tc::b_tile_offset(n, k, Np)) = h;
     *reinterpret_cast<float*>(lo + tc::b_tile_offset(n, k, Np)) = r;
   }

@@ -192,7 +192,15 @@ __device__ __forceinline__ float tf32_hi(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) { hi = tf32_hi(x); lo = x - hi; }
+// hi = x truncated to TF32 -- exactly what the tensor core keeps of a raw FP32 operand -- and lo = x - hi (exact; x == hi + lo).
+// (cvt.rna.tf32 would halve |lo|, but costs ~15 cycles of a worker's time per value where AND + FADD cost two; the dropped
+// lo.lo term is 2^-21 instead of 2^-22 relative, the truncation of lo itself < 2^-21 |x|.)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+// round-to-nearest split (|lo| <= 2^-11 |x|): for operands that are split once per kernel (the weights)
+__device__ __forceinline__ void tf32_split_rn(float x, float& hi, float& lo) { hi = tf32_hi(x); lo = x - hi; }
 
 // byte offset of element (n, k) inside a B tile of padded width Np (see the header comment)
 __host__ __device__ constexpr uint32_t b_tile_offset(int n, int k, int Np) {
@@ -205,13 +213,15 @@ __host__ __device__ constexpr uint32_t b_tile_bytes(int Kp, int Np) { return (ui
 __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                            int Np, int ksteps, uint32_t idesc, bool accumulate, uint32_t lbo, uint32_t sbo) {
   // small terms first: they are added while the accumulator is still small
+  // one descriptor per pass; only its 14-bit start address (>> 4) moves from one k step to the next (a tcgen05.mma costs its
+  // issuing thread 50 - 100 cycles, most of the excess being descriptor arithmetic in the loop: pspde_mma_probe)
+  const uint64_t step = (uint64_t)((2u * (uint32_t)Np * 16u) >> 4);
+  const uint64_t d_hi = smem_desc(b_hi, lbo, sbo), d_lo = smem_desc(b_lo, lbo, sbo);
   for (int pass = 0; pass < 3; ++pass) {
     const uint32_t a = (pass == 0) ? a_lo : a_hi;
-    const uint32_t b = (pass == 1) ? b_lo : b_hi;
-    for (int s = 0; s < ksteps; ++s) {
-      const uint64_t bd = smem_desc(b + (uint32_t)s * 2u * (uint32_t)Np * 16u, lbo, sbo);
+    uint64_t bd = (pass == 1) ? d_lo : d_hi;
+    for (int s = 0; s < ksteps; ++s, bd += step)
       mma_tf32_ts(d_tmem, a + 8u * (uint32_t)s, bd, idesc, accumulate || pass > 0 || s > 0);
-    }
   }
 }
 
