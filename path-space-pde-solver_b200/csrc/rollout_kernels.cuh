@@ -65,6 +65,8 @@ struct RolloutParams {
   int ckpt_zeta;          // 1: the zeta columns are in the checkpoint; 0: they are NOT written -- zeta = wY sqrt(dt) xi is a
                           //    function of (path, step, Philox key) alone (adaptive process, no cotangent on Z_sum, in-kernel
                           //    noise), so the gradient kernel regenerates it: 38 % less checkpoint traffic at the C2 shape
+  const uint8_t* wpack;   // tensor-core rollout: shared-memory image of the six weight tiles in global memory (one bulk copy per
+                          // CTA), or nullptr = every CTA stages its tiles from theta
   unsigned long long* prof;  // debug: per-phase clock64() totals of CTA 0 (16 slots) or nullptr
 };
 

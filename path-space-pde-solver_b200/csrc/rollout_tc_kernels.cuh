@@ -23,6 +23,7 @@
 // mbarriers (operands ready: every thread arrives; group done: tcgen05.commit).
 #pragma once
 #if !defined(PSPDE_EMULATE)
+#include <mutex>
 #include "rollout_kernels.cuh"
 #include "tc_sm100.cuh"
 
@@ -97,6 +98,16 @@ __device__ __forceinline__ void tc_stage_tile(const NetGeom& g, const float* __r
   }
 }
 
+// The six B tiles exactly as they sit in shared memory ([o_b0h, o_prob): hi / lo of B0, B1, B2), built ONCE per launch in
+// global memory; every CTA of the rollout then fetches the image with one bulk copy (cp.async.bulk -> mbarrier) instead of
+// evaluating theta_index for its own 53 k elements.
+static __global__ void tc_pack_weights_kernel(const NetGeom g, const float* __restrict__ theta, const TcGeom tg, uint8_t* __restrict__ out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  tc_stage_tile(g, theta, out + tg.o_b0h, out + tg.o_b0l, tg.s0, tg.n0, 0, g.seg_len[0], 0, tg.hp, tid, nthr);
+  tc_stage_tile(g, theta, out + tg.o_b1h, out + tg.o_b1l, tg.hp, tg.n1, g.seg_off[1], g.seg_len[1], 1, tg.hp, tid, nthr);
+  tc_stage_tile(g, theta, out + tg.o_b2h, out + tg.o_b2l, tg.hp, tg.n2, g.seg_off[2], g.seg_len[2], 2, tg.hp, tid, nthr);
+}
+
 // streaming store of one checkpoint element (written once, read once by another kernel)
 __device__ __forceinline__ void st_ckpt(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
@@ -116,7 +127,8 @@ template <int NG, bool CKPT, bool DIAG, bool PHILOX>
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const RolloutParams prm, const TcGeom tg) {
   extern __shared__ float4 smem4[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(smem4);
-  __shared__ uint64_t bars[6];          // [0..2] operands of group g ready (all threads arrive), [3..5] group g done (commit)
+  __shared__ uint64_t bars[7];          // [0..2] operands of group g ready (all threads arrive), [3..5] group g done (commit),
+                                        // [6] the weight image has landed (bulk copy)
   __shared__ uint32_t tmem_base_s;
   const NetGeom& g = prm.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -130,12 +142,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars[i], kTcThreads); tc::mbar_init(&bars[3 + i], 1); }
+    tc::mbar_init(&bars[6], 1);
     tc::mbar_fence_init();
+    if (prm.wpack) {      // weights: ONE bulk copy (TMA engine) of the packed image, completion on bars[6]
+      tc::mbar_arrive_expect_tx(&bars[6], tg.o_prob);
+      tc::bulk_load(smem + tg.o_b0h, prm.wpack, tg.o_prob, &bars[6]);
+    }
   }
   if (tid < 4) sRed[tid] = 0.0;
-  tc_stage_tile(g, prm.theta, smem + tg.o_b0h, smem + tg.o_b0l, tg.s0, tg.n0, 0, g.seg_len[0], 0, tg.hp, tid, kTcThreads);
-  tc_stage_tile(g, prm.theta, smem + tg.o_b1h, smem + tg.o_b1l, tg.hp, tg.n1, g.seg_off[1], g.seg_len[1], 1, tg.hp, tid, kTcThreads);
-  tc_stage_tile(g, prm.theta, smem + tg.o_b2h, smem + tg.o_b2l, tg.hp, tg.n2, g.seg_off[2], g.seg_len[2], 2, tg.hp, tid, kTcThreads);
+  if (!prm.wpack) {       // no packed image (allocation failed): every CTA builds its tiles from theta
+    tc_stage_tile(g, prm.theta, smem + tg.o_b0h, smem + tg.o_b0l, tg.s0, tg.n0, 0, g.seg_len[0], 0, tg.hp, tid, kTcThreads);
+    tc_stage_tile(g, prm.theta, smem + tg.o_b1h, smem + tg.o_b1l, tg.hp, tg.n1, g.seg_off[1], g.seg_len[1], 1, tg.hp, tid, kTcThreads);
+    tc_stage_tile(g, prm.theta, smem + tg.o_b2h, smem + tg.o_b2l, tg.hp, tg.n2, g.seg_off[2], g.seg_len[2], 2, tg.hp, tid, kTcThreads);
+  }
   for (int q = tid; q < 7 * tg.s0; q += kTcThreads) {
     const int v = q / tg.s0, j = q - v * tg.s0;
     sProb[q] = j < d ? __ldg(prm.prob + v * d + j) : 0.f;
@@ -144,6 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  if (prm.wpack) tc::mbar_wait(&bars[6], 0u);
   const uint32_t tbase = tmem_base_s;
 
   // ---- MMA groups (thread kTcIssuer)
@@ -469,12 +489,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_fwd_kernel(const Rol
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// Scratch for the packed weight image, one per (device, stream) that ever launched a rollout (at most 16, 256 KB each, kept for
+// the life of the process): stream order alone then keeps a pack kernel from overwriting an image a rollout is still loading.
+// nullptr (table full or allocation failure) = the rollout stages its tiles itself.
+inline void* tc_wpack_buffer(size_t bytes, cudaStream_t stream) {
+  struct Slot { int dev; cudaStream_t stream; void* buf; size_t bytes; };
+  static Slot slots[16];
+  static int n_slots = 0;
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_slots; ++i)
+    if (slots[i].dev == dev && slots[i].stream == stream) {
+      if (slots[i].bytes >= bytes) return slots[i].buf;
+      cudaFree(slots[i].buf);                       // a larger network on this stream: grow (cudaFree synchronises)
+      if (cudaMalloc(&slots[i].buf, bytes) != cudaSuccess) { (void)cudaGetLastError(); slots[i].buf = nullptr; slots[i].bytes = 0; return nullptr; }
+      slots[i].bytes = bytes;
+      return slots[i].buf;
+    }
+  if (n_slots == 16) return nullptr;
+  void* buf = nullptr;
+  if (cudaMalloc(&buf, bytes) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  slots[n_slots++] = Slot{dev, stream, buf, bytes};
+  return buf;
+}
+
 // NG instantiations: the smallest one that holds tg.ng column groups per thread
 template <int NG, bool CKPT, bool DIAG, bool PHILOX>
 inline cudaError_t tc_launch_k(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(rollout_tc_fwd_kernel<NG, CKPT, DIAG, PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tg.total);
   if (e != cudaSuccess) return e;
-  rollout_tc_fwd_kernel<NG, CKPT, DIAG, PHILOX><<<grid, kTcThreads, tg.total, stream>>>(p, tg);
+  RolloutParams q = p;
+  q.wpack = nullptr;
+  if (void* wp = tc_wpack_buffer(tg.o_prob, stream)) {               // scratch for the packed weight image (per device and stream)
+    tc_pack_weights_kernel<<<64, 256, 0, stream>>>(p.g, p.theta, tg, reinterpret_cast<uint8_t*>(wp));
+    g_launches++;
+    q.wpack = reinterpret_cast<const uint8_t*>(wp);
+  }
+  rollout_tc_fwd_kernel<NG, CKPT, DIAG, PHILOX><<<grid, kTcThreads, tg.total, stream>>>(q, tg);
   return cudaGetLastError();
 }
 template <int NG, bool CKPT, bool DIAG>
