@@ -273,8 +273,16 @@ class Solver:
         then H2D); 'philox' draws nothing here -- the kernels generate the increments from (seed, iteration)."""
         eng = self._get_engine()
         if self.random_X_0:
-            X0 = pt.randn(self.K, self.d)[self._k_lo:self._k_hi]  # solver.py:366-367
-            eng.set_x0(X0.to(self.device))
+            if self.noise == 'inject':                            # the reference's CPU draw, solver.py:366-367
+                X0 = pt.randn(self.K, self.d)[self._k_lo:self._k_hi].to(self.device)
+            else:
+                # Philox mode: drawn on the device, one generator per (seed, iteration, shard start); K * d floats on the
+                # host every iteration would be 400 MB at K = 2^20.  (Per-path starts therefore depend on the sharding,
+                # unlike the in-kernel increments; the distribution does not.)
+                gen = pt.Generator(device=self.device)
+                gen.manual_seed((self.seed * 1000003 + self._iteration * 8191 + self._k_lo) % (2 ** 63))
+                X0 = pt.randn(self._k_hi - self._k_lo, self.d, device=self.device, generator=gen)
+            eng.set_x0(X0)
         xi = None
         if self.noise == 'inject':
             xi = pt.randn(self.K, self.d, self.N + 1)[self._k_lo:self._k_hi].to(self.device)

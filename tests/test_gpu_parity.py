@@ -1043,3 +1043,28 @@ def test_save_logs_and_device_argument(tmp_path, monkeypatch):
     assert log["K"] == 64 and len(log["loss_log"]) == 3 and len(log["u_L2_loss"]) == 3
     assert len(log["Phis_state_dict"]) == len(S.Phis) and log["loss_log"] == S.loss_log
     assert S.save_logs() != str(files[0])               # a second log gets a numbered name
+
+
+def test_random_x0_philox_and_importance_sampling_start():
+    """random_X_0=True with in-kernel noise draws the per-path starts on the device (no K x d host tensor per iteration), and
+    do_importance_sampling_me still starts every path from problem.X_0 (utilities.py:302) although the engine now holds
+    per-path starts (advisor finding, round 1)."""
+    import pspde
+    d = 6
+    prob = pspde.LLGC(d=d, T=0.5, device="cuda")
+    mk = lambda rx0: pspde.Solver("rx", prob, K=512, L=1, delta_t=0.05, time_approx="inner", detach_forward=True,
+                                  u_l2_error_flag=False, early_stopping_time=None, verbose=False, random_X_0=rx0, seed=3)
+    A, B = mk(True), mk(False)
+    for S in (A, B):
+        S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=0.0, seed=42)
+        S.update_Phis()
+    A.train_step(0)
+    eng = A._get_engine()
+    assert eng.x0_per_path and tuple(eng.x0.shape) == (512, d) and eng.x0.is_cuda and np.isfinite(A.loss_log[-1])
+    x0_first = eng.x0.clone()
+    A.train_step(1)
+    assert not pt.equal(x0_first, eng.x0)                 # a new draw every iteration
+    B._get_engine()
+    ra = pspde.do_importance_sampling_me(prob, A, 4096, delta_t=0.05)
+    rb = pspde.do_importance_sampling_me(prob, B, 4096, delta_t=0.05)
+    assert ra == rb                                       # lr = 0: same theta, same Philox stream, same start X_0
