@@ -14,8 +14,13 @@ unsigned long long* g_prof = nullptr;
 // PSPDE_CKPT_ZETA=1 forces the columns into the checkpoint (A/B tests).
 static int zeta_in_ckpt(const pspde_cfg* cfg, const float* wZ) {
   if (const char* e = getenv("PSPDE_CKPT_ZETA")) if (e[0] == '1') return 1;
+  if (const char* e = getenv("PSPDE_GRAD_PATH")) if (!strcmp(e, "simt")) return 1;     // the FMA gradient kernel reads zeta
   return (cfg->noise_mode == PSPDE_NOISE_PHILOX && cfg->adaptive && !wZ) ? 0 : 1;
 }
+#if !defined(PSPDE_EMULATE)
+// columns per (tile slot, step) of a checkpoint: [a0 (s0) | h1 | h2] and, only when it is written, zeta (s0)
+static int ckpt_cols_of(const TcGeom& tg, int ckpt_zeta) { return ckpt_zeta ? tc_ckpt_cols(tg) : tg.s0 + 2 * tg.hp; }
+#endif
 
 // Forward rollout launch: the tensor-core kernel (rollout_tc_kernels.cuh) for the shape class it covers, else the
 // FP32-FMA kernel.  PSPDE_FWD_PATH=simt forces the FMA kernel (A/B tests); PSPDE_FWD_PATH=tc makes an ineligible
@@ -33,8 +38,8 @@ static int launch_forward(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p
     const int sms = pspde_sm_count();
     const int grid = n_tiles < sms ? n_tiles : sms;
     p.n_tiles = n_tiles;
-    if (keep_ckpt) { p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0; p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles;
-                     p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr); }
+    if (keep_ckpt) { p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr); p.ckpt_cols = ckpt_cols_of(tg, p.ckpt_zeta); p.ckpt_s0 = tg.s0;
+                     p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_tiles = keep_tiles; }
     const cudaError_t ce = keep_ckpt ? tc_launch_fwd_ckpt(p, tg, grid, (cudaStream_t)stream) : tc_launch(p, tg, grid, (cudaStream_t)stream);
     g_launches++;
     if (ce != cudaSuccess) return fail(-12, "tensor-core rollout launch failed: %s", cudaGetErrorString(ce));
@@ -73,7 +78,7 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
     CUtensorMap tmap;
     // zeta regenerated in the kernel: one box of the activation rows per stage; else two boxes of cols / 2 rows
     if (!p.ckpt_zeta && gt.act_rows > 256) return fail(-6, "activation rows exceed one TMA box");
-    if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap, p.ckpt_zeta ? 0 : gt.act_rows))
+    if (grad_tc_tensor_map(gt, p.ckpt, n_ts, &tmap, p.ckpt_zeta ? 0 : gt.act_rows, p.ckpt_cols))
       return fail(-11, "cuTensorMapEncodeTiled failed for the checkpoint buffer");
     GradTc2Geom g2;
     // zeta from the Philox key: the kernel with the hidden cotangents on the tensor cores (PSPDE_GRAD_PATH=tc1: the older one)
@@ -181,7 +186,7 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
   if (cfg->N < 1 || !cfg->adaptive || (cfg->problem_flags & PSPDE_FLAG_DENSE_AB) || !tc_geom(pl.g, cfg->d, tg)) return 0;
   if (!grad_tc_geom(pl.g, cfg->d, tg.s0, gt)) return 0;
   const size_t n_tiles = (size_t)(cfg->K_local + kTcP - 1) / kTcP;
-  const size_t tb = (size_t)cfg->N * tc_ckpt_cols(tg) * kTcP * 4;      // one 128-path tile; a multiple of 512 B
+  const size_t tb = (size_t)cfg->N * ckpt_cols_of(tg, zeta_in_ckpt(cfg, nullptr)) * kTcP * 4;      // one 128-path tile; a multiple of 512 B
   if (tile_bytes) *tile_bytes = tb;
   return n_tiles * tb;
 #else
@@ -195,7 +200,8 @@ static size_t fwd_ckpt_bytes(const pspde_cfg* cfg, const Plan& pl, size_t* tile_
 // rows (cotangents p.wY / p.wZ applied) into p.ckpt, then the gradient kernel; accumulates into p.grad_partial
 static int run_waves(const pspde_cfg* cfg, const Plan& pl, RolloutParams& p, const TcGeom& tg, const CkptPlan& cp, int t_begin,
                      void* stream, int* used_tc) {
-  p.ckpt_cols = cp.cols; p.ckpt_s0 = cp.s0; p.ckpt_unit = 0; p.ckpt_zeta = zeta_in_ckpt(cfg, p.wZ);
+  // (the wave buffer is sized for rows WITH zeta columns; rows without them are simply shorter)
+  p.ckpt_zeta = zeta_in_ckpt(cfg, p.wZ); p.ckpt_cols = ckpt_cols_of(tg, p.ckpt_zeta); p.ckpt_s0 = cp.s0; p.ckpt_unit = 0;
   const int sms = pspde_sm_count();
   for (int t0 = t_begin; t0 < cp.n_tiles128; t0 += cp.wave) {
     const int nt = cp.n_tiles128 - t0 < cp.wave ? cp.n_tiles128 - t0 : cp.wave;
@@ -442,8 +448,9 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY;
   p.grad_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + pl.stats_bytes);
-  p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_cols = tc_ckpt_cols(tg); p.ckpt_s0 = tg.s0;
-  p.tile0 = 0; p.ckpt_unit = 1; p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr);
+  p.ckpt = reinterpret_cast<float*>(const_cast<void*>(ckpt)); p.ckpt_zeta = zeta_in_ckpt(cfg, nullptr);
+  p.ckpt_cols = ckpt_cols_of(tg, p.ckpt_zeta); p.ckpt_s0 = tg.s0;
+  p.tile0 = 0; p.ckpt_unit = 1;
   if (pspde_memset0(p.grad_partial, gbytes, stream)) return fail(-12, "memset of the gradient partials failed");
   int used_tc = false;
   rc = launch_grad(cfg, pl, p, grid, n_ts, stream, &used_tc);

@@ -463,12 +463,13 @@ inline PFN_tmap_encode tmap_encode_fn() {
   return fn;
 }
 // returns 0 on success
-inline int grad_tc_tensor_map(const GradTcGeom& tg, const float* ckpt, long long n_ts, CUtensorMap* out, int box_rows = 0) {
+inline int grad_tc_tensor_map(const GradTcGeom& tg, const float* ckpt, long long n_ts, CUtensorMap* out, int box_rows = 0, int cols = 0) {
   if (box_rows <= 0) box_rows = tg.box_rows;
+  if (cols <= 0) cols = tg.cols;              // columns per (slot, step) in memory (RolloutParams::ckpt_cols)
   PFN_tmap_encode enc = tmap_encode_fn();
   if (!enc) return -1;
-  const cuuint64_t gdim[3] = {(cuuint64_t)kCkP, (cuuint64_t)tg.cols, (cuuint64_t)n_ts};
-  const cuuint64_t gstr[2] = {(cuuint64_t)kCkP * 4u, (cuuint64_t)kCkP * 4u * (cuuint64_t)tg.cols};
+  const cuuint64_t gdim[3] = {(cuuint64_t)kCkP, (cuuint64_t)cols, (cuuint64_t)n_ts};
+  const cuuint64_t gstr[2] = {(cuuint64_t)kCkP * 4u, (cuuint64_t)kCkP * 4u * (cuuint64_t)cols};
   const cuuint32_t box[3] = {(cuuint32_t)kGtS, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ckpt), gdim, gstr, box, estr,

@@ -56,7 +56,7 @@ struct RolloutParams {
   // the 128 paths of the tile contiguous:  ckpt[((slot * N + n) * ckpt_cols + col) * 128 + path]  -- one 512-byte row per
   // column, the K-major operand form (K = sample) that the tensor-core gradient kernel loads by TMA without a transposition
   float* ckpt;
-  int ckpt_cols;          // columns per (slot, step): 2 * s0 + 64
+  int ckpt_cols;          // columns per (slot, step): 2 * s0 + 64, or s0 + 64 when the zeta columns are not written (ckpt_zeta == 0)
   int ckpt_s0;            // tensor-core width of the input segment (multiple of 8)
   int tile0;              // first 128-path tile of this wave (ckpt slot = tile - tile0)
   int ckpt_tiles;         // rollout: only tiles < ckpt_tiles (launch-local index) write their rows
