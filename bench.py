@@ -120,7 +120,8 @@ def _print_reference(args, wl, times, K_cpu, N, cores):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "K_global": wl["K"] * args.gpus, "K_per_gpu": wl["K"], "N": N, "d": wl["pkw"]["d"],
-                       "device": "cpu", "sample": sample},
+                       "noise": "torch CPU randn(K, d, N+1) per iteration (the reference's own, solver.py:381)",
+                       "parallelism": "host threads: %d" % cores, "device": "cpu", "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -379,7 +380,7 @@ def detached_roofline(rig, lib, S, eng, N, clocks, workload):
                   "regenerated from Philox, hidden cotangents and weight gradient on tcgen05 kind::tf32 3xTF32); timed together")
     else:
         kernel = "rollout_kernel<BWD> (detached backward, FP32-FMA recompute)"
-    key = workload if (single or not ckpt_path) else workload + "_two_rollout_step"
+    key = workload if (single or not ckpt_path) else workload + "_two_rollout_step"      # profiles/roofline_traffic.json
     roof = {"bound": "tensor" if ckpt_path else "fp32_fma", "kernel": kernel, "achieved": ach,
             "peak": tpeak if ckpt_path else fma_peak, "unit": "TFLOP/s", "frac": ach / (tpeak if ckpt_path else fma_peak),
             "peak_source": tsrc if ckpt_path else "fp32 FMA probe measured live in this run",
