@@ -1068,3 +1068,44 @@ def test_random_x0_philox_and_importance_sampling_start():
     ra = pspde.do_importance_sampling_me(prob, A, 4096, delta_t=0.05)
     rb = pspde.do_importance_sampling_me(prob, B, 4096, delta_t=0.05)
     assert ra == rb                                       # lr = 0: same theta, same Philox stream, same start X_0
+
+
+def test_full_size_properties_c5():
+    """north_star size (BASELINE configs[4], K = 2^20, d = 100, N = 200), wave-checkpointed backward through grad_tc2_kernel:
+    deterministic forward, kernel statistics == host recomputation over the kept paths, the blow-up bound drops the
+    near-divergent trajectories the untrained control produces at this K (finite loss and parameters after training steps --
+    round 1 trained on NaN here), gradient linear in the cotangent and bit-reproducible."""
+    import pspde
+    from pspde.fused import Call
+    d, K = 100, 1 << 20
+    prob = pspde.LLGC(d=d, off_diag=0, T=1, seed=42, device="cuda")
+    S = pspde.Solver("c5", prob, K=K, L=1, delta_t=0.005, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, early_stopping_time=None, verbose=False)
+    S.z_n = pspde.DenseNet(d_in=d + 1, d_out=d, lr=1e-3, seed=42)
+    S.update_Phis()
+    eng = S._get_engine()
+    theta = S._theta.detach()
+    eng.forward(theta, None, Call(offset=0))
+    Y, gX, st = eng.Y_N.clone(), eng.gX.clone(), eng.stats.clone()
+    eng.forward(theta, None, Call(offset=0))
+    nn_ = lambda t: pt.nan_to_num(t, nan=0.0, posinf=1e30, neginf=-1e30)
+    assert pt.equal(nn_(Y), nn_(eng.Y_N)) and pt.allclose(st, eng.stats, rtol=1e-13)
+    D = Y.double() - gX.double()
+    ok = pt.isfinite(D)
+    assert pt.allclose(st[:2], pt.stack([D[ok].sum(), (D[ok] ** 2).sum()]), rtol=1e-10)
+    assert 0 < st[3].item() == (~ok).sum().item() <= 64            # a few dropped paths (non-finite or |D| >= 1e6) out of 2^20
+    assert float(D[ok].abs().max()) < 1e6
+    w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    w1[~ok] = 0.0
+    w2[~ok] = 0.0
+    gs = []
+    for w in (w1, w2, (w1 + 2 * w2).contiguous(), w1):
+        gr = pt.empty(eng.n_theta, device="cuda")
+        eng.backward_detached(theta, w, None, Call(offset=0), gr)
+        gs.append(gr)
+    assert relerr((gs[0] + 2 * gs[1]).cpu().numpy(), gs[2].cpu().numpy()) < 2e-5
+    assert pt.equal(gs[3], gs[0])
+    S.L = 3
+    S.train()
+    # kept paths have |D| < 1e6, so the variance is bounded by 1e12 (a few paths near the bound dominate the first iterations)
+    assert all(np.isfinite(S.loss_log)) and max(S.loss_log) < 1e12 and bool(pt.isfinite(S._theta).all())
