@@ -947,7 +947,8 @@ def test_u_l2_diagnostic_matches_reference(tag, path, monkeypatch):
 
 # ---------------------------------------------------------------------------------------------- grad_tc2_kernel (round 2)
 TC2_CASES = [("llgc", 100, (30, 30), 128 * 3 + 17, 5, 0.02), ("llgc", 10, (30, 30), 300, 4, 0.02), ("llgc", 7, (12, 20), 200, 3, 0.02),
-             ("dwm", 50, None, 500, 6, 0.005), ("dwm", 6, None, 100, 3, 0.005), ("llgc", 100, (30, 30), 1 << 13, 20, 0.01)]
+             ("dwm", 50, None, 500, 6, 0.005), ("dwm", 6, None, 100, 3, 0.005), ("llgc", 100, (30, 30), 1 << 13, 20, 0.01),
+             ("llgc", 1, (30, 30), 40, 2, 0.02), ("llgc", 3, (5, 7), 20, 1, 0.02), ("llgc", 102, (32, 32), 130, 2, 0.02)]
 
 
 @pytest.mark.parametrize("kind,d,arch,K,N,dt", TC2_CASES)
