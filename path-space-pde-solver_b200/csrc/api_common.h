@@ -61,7 +61,7 @@ constexpr size_t kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per
 
 struct Plan {
   NetGeom g;
-  int T, NB, n_tiles, grid, n_sets, n_theta_total;
+  int T, NB, n_tiles, grid, n_sets, n_theta_total, ctas_per_sm;
   int r_fwd[PSPDE_MAXL];
   size_t smem_bytes, stats_bytes, grad_bytes;
 };
@@ -133,6 +133,15 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
   pl.smem_bytes = (size_t)sl.total * sizeof(float);
   if (pl.smem_bytes > kMaxSmem)
     return fail(-6, "network + tile need %zu B of shared memory (> %zu)", pl.smem_bytes, kMaxSmem);
+  // Attached kernel, 256 threads: alone on an SM it runs at 208 registers with 8 warps (ncu: FMA pipe 24 %, warps stalled on
+  // fixed latencies, profiles/r02_attached_ncu_full_summary.json).  Two CTAs per SM at <= 128 registers (75 spilled floats)
+  // are 31 % faster at the C3 shape (205 -> 156 ms), so that is the default whenever two tiles' shared memory fits;
+  // PSPDE_ATT_CTAS=1 restores one CTA per SM.
+  pl.ctas_per_sm = 1;
+  if (attached && pl.T == 256 && 2 * (pl.smem_bytes + 1024) <= kMaxSmem + 1024) {
+    const char* e = getenv("PSPDE_ATT_CTAS");
+    if (!(e && e[0] == '1')) { pl.ctas_per_sm = 2; pl.grid = pl.n_tiles < 2 * sms ? pl.n_tiles : 2 * sms; }
+  }
   pl.stats_bytes = align256((size_t)pl.grid * 4 * sizeof(double));
   pl.grad_bytes = bwd ? align256((size_t)pl.grid * pl.n_theta_total * sizeof(float)) : 0;
   return 0;

@@ -826,8 +826,8 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
 // Per tile: the forward sweep checkpoints X_n (P x d floats per step) to a per-CTA scratch slice, the backward
 // sweep reloads them in reverse and recomputes the network; forward and backward of a tile run in the same
 // kernel, so the scratch is bounded by gridDim.x * N * P * d floats whatever K is.
-template <int P, int T, int NB>
-__global__ void __launch_bounds__(T, 1) rollout_attached_kernel(const RolloutParams prm) {
+template <int P, int T, int NB, int MINB = 1>
+__global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const RolloutParams prm) {
   PSPDE_DYN_SMEM(smem4);
   float* smem = reinterpret_cast<float*>(smem4);
   const NetGeom& g = prm.g;
