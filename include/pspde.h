@@ -189,6 +189,18 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
                              const float* xi, const void* ckpt, size_t ckpt_bytes, const float* wY, float* grad_theta,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Iteration glue in one launch each (the reference does these with a dozen element-wise torch kernels per iteration):
+ *   pspde_lv_cotangents  loss value and per-path cotangent dLoss/dY_N of the log-variance (moment = 0, solver.py:167-168) or
+ *                        moment (moment = 1, :165-166) loss from the statistics of pspde_rollout_fwd* (stats: 4 doubles, already
+ *                        summed over the ranks; K_global = global batch).  A dropped trajectory (Y_N = NaN) gets zero weight.
+ *                        wY: K_local floats; out3 = [loss, #dropped, K_eff] (device doubles).
+ *   pspde_adam_flat      one torch.optim.Adam step (no weight decay / amsgrad) over a flat fp32 parameter buffer and its state
+ *                        (solver.py:198-200 for every module at once); step = the 1-based step count AFTER this update. */
+int pspde_lv_cotangents(int K_local, double K_global, int moment, const float* Y_N, const float* gX, const double* stats,
+                        float* wY, double* out3, void* stream);
+int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                    float beta2, float eps, int64_t step, void* stream);
+
 /* Forward + backward for detach_forward=False (solver.py:451-469 without the detach, :221): per tile of paths the
  * states X_n are checkpointed to the workspace and the discrete adjoint runs backwards in time in the same kernel.
  *   - relative entropy, loss = mean(Zsum + g(X_N)) (solver.py:180): pass wY = wZ = wG = NULL and w = 1 / K_global;

@@ -230,6 +230,26 @@ static int set_udiag(const pspde_cfg* cfg, const pspde_udiag* diag, RolloutParam
 extern "C" {
 
 int pspde_abi_version(void) { return PSPDE_ABI_VERSION; }
+
+int pspde_lv_cotangents(int K_local, double K_global, int moment, const float* Y_N, const float* gX, const double* stats,
+                        float* wY, double* out3, void* stream) {
+  if (K_local < 1 || !(K_global >= 1.0) || !Y_N || !gX || !stats || !wY || !out3) return fail(-1, "bad arguments");
+  PSPDE_LAUNCH(lv_cotangents_kernel, (K_local + 255) / 256, 256, 0, stream, K_local, K_global, moment, Y_N, gX, stats, wY, out3);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "lv_cotangents launch failed: %s", e);
+  return 0;
+}
+
+int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                    float beta2, float eps, int64_t step, void* stream) {
+  if (n < 1 || n > 0x7fffffffLL || !theta || !grad || !exp_avg || !exp_avg_sq || step < 1) return fail(-1, "bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  PSPDE_LAUNCH(adam_flat_kernel, (int)((n + 255) / 256), 256, 0, stream, (int)n, theta, grad, exp_avg, exp_avg_sq,
+               (float)((double)lr / bc1), (float)sqrt(bc2), beta1, beta2, eps);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "adam_flat launch failed: %s", e);
+  return 0;
+}
 const char* pspde_last_error(void) { return g_err; }
 uint64_t pspde_launch_count(void) { return g_launches.load(); }
 void pspde_set_profile_buffer(unsigned long long* dev_buf16) { g_prof = dev_buf16; }

@@ -1052,6 +1052,52 @@ static __global__ void reduce_stats_kernel(const double* __restrict__ partial, i
   }
 }
 
+// Loss value and per-path cotangents of the log-variance / moment losses (solver.py:165-168) from the batch statistics the
+// forward kernel accumulated (summed over the ranks by the caller): the dozen element-wise launches of the host formulation
+// in one.  stats = [sum D, sum D^2, -, #dropped] over the kept trajectories, D = Y_N - g(X_N); a dropped trajectory carries
+// Y_N = NaN (path_kept) and gets zero weight.  out = [loss, #dropped, K_eff].
+static __global__ void lv_cotangents_kernel(int K_local, double K_global, int moment, const float* __restrict__ Y,
+                                            const float* __restrict__ gX, const double* __restrict__ stats,
+                                            float* __restrict__ wY, double* __restrict__ out) {
+  const double Ke = K_global - stats[3];
+  const double mean = stats[0] / Ke;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K_local) {
+    const double D = (double)(Y[k] - gX[k]);                   // fp32 subtraction, then widened: the host formulation's order
+    wY[k] = isfinite(D) ? (float)((moment ? D : D - mean) * (2.0 / Ke)) : 0.f;
+  }
+  if (k == 0) { out[0] = moment ? stats[1] / Ke : stats[1] / Ke - mean * mean; out[1] = stats[3]; out[2] = Ke; }
+}
+
+// single-rounding fp32 operations (no FMA contraction): the update must follow torch's op sequence
+#if defined(PSPDE_EMULATE)
+static inline float rn_add(float a, float b) { volatile float r = a + b; return r; }
+static inline float rn_sub(float a, float b) { volatile float r = a - b; return r; }
+static inline float rn_mul(float a, float b) { volatile float r = a * b; return r; }
+static inline float rn_div(float a, float b) { volatile float r = a / b; return r; }
+static inline float rn_sqrt(float a) { return sqrtf(a); }
+#else
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float rn_sqrt(float a) { return __fsqrt_rn(a); }
+#endif
+// One Adam step over a flat parameter buffer: the op sequence of torch.optim.Adam's single-tensor form (no weight decay,
+// no amsgrad): m = lerp(m, g, 1 - b1); v = v b2 + (1 - b2) g g; theta -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps).
+static __global__ void adam_flat_kernel(int n, float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+                                        float* __restrict__ v, float lr_over_bc1, float sqrt_bc2, float b1, float b2, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float gi = g[i];
+    const float mi = rn_add(m[i], rn_mul(rn_sub(gi, m[i]), 1.0f - b1));
+    const float vi = rn_add(rn_mul(v[i], b2), rn_mul(rn_mul(gi, gi), 1.0f - b2));
+    m[i] = mi; v[i] = vi;
+    const float denom = rn_add(rn_div(rn_sqrt(vi), sqrt_bc2), eps);
+    theta[i] = rn_sub(theta[i], rn_mul(lr_over_bc1, rn_div(mi, denom)));
+  }
+}
+
 static __global__ void reduce_grad_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

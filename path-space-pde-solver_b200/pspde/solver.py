@@ -180,11 +180,20 @@ class Solver:
                 steps += 1
                 t = float(steps[0])
                 g, m1, m2 = self._theta.grad, fa['exp_avg'], fa['exp_avg_sq']
-                m1.lerp_(g, 1 - beta1)
-                m2.mul_(beta2).addcmul_(g, g, value=1 - beta2)
-                bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
-                denom = m2.sqrt().div_(bc2 ** 0.5).add_(eps)
-                self._theta.data.addcdiv_(m1, denom, value=(lr / bc1) * -1)
+                if self._theta.is_cuda:                          # the same update in ONE launch (pspde_adam_flat)
+                    import ctypes
+                    lib = L.load()
+                    vp = lambda x: ctypes.c_void_p(x.data_ptr())
+                    with pt.cuda.device(self.device):
+                        L.check(lib, lib.pspde_adam_flat(self._theta.numel(), vp(self._theta.data), vp(g), vp(m1), vp(m2), lr,
+                                                         beta1, beta2, eps, int(t),
+                                                         ctypes.c_void_p(pt.cuda.current_stream(self.device).cuda_stream)))
+                else:
+                    m1.lerp_(g, 1 - beta1)
+                    m2.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+                    bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
+                    denom = m2.sqrt().div_(bc2 ** 0.5).add_(eps)
+                    self._theta.data.addcdiv_(m1, denom, value=(lr / bc1) * -1)
                 rest = [phi for phi in self.Phis if all(phi is not m for m in fa['nets'])]
         for phi in rest:
             phi.optim.step()
@@ -202,13 +211,14 @@ class Solver:
 
     def _flat_adam_state(self):
         """Flat Adam state shared with the per-module optimizers of the networks (built on first use after update_Phis);
-        None when there is only one network or an optimizer is not a plain Adam over exactly its module's parameters."""
+        None when an optimizer is not a plain Adam over exactly its module's parameters (or, on the CPU, when there is only one
+        network: torch's own step is then just as good)."""
         nets = self._nets()
         if self._flat_adam and self._flat_adam['opts'] != [id(m.optim) for m in nets]:
             self._flat_adam = None                                             # an optimizer was replaced: start over
         if self._flat_adam is None:
             self._flat_adam = False
-            ok = len(nets) > 1 and all(hasattr(m, 'optim') and self._adam_hyper(m.optim) is not None and
+            ok = (len(nets) > 1 or self._theta.is_cuda) and all(hasattr(m, 'optim') and self._adam_hyper(m.optim) is not None and
                                        [id(q) for q in m.optim.param_groups[0]['params']] == [id(q) for q in m.parameters()]
                                        for m in nets)
             if ok:
@@ -297,7 +307,34 @@ class Solver:
         # X depends on theta only through an attached adaptive control (solver.py:451-469)
         attached = (not self.detach_forward) and self.adaptive_forward_process
         y0 = self.y_0.Y_0 if self.learn_Y_0 else None
-        if attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0:
+        if (not attached) and self.loss_method in ('log-variance', 'moment'):
+            # Detached forward, log-variance / moment loss (every log-variance notebook): forward launch -> statistics (one
+            # all-reduce) -> ONE launch for the loss value and the per-path cotangents -> gradient launch(es), without going
+            # through autograd and the dozen element-wise kernels of losses.value_and_cotangents (same arithmetic).
+            import ctypes
+            theta = self._theta.detach()
+            y0c = None if y0 is None else y0.detach().contiguous()
+            kept = eng.forward(theta, y0c, call, keep_rows=True)
+            call.X_N, call.stats = eng.X_N, eng.stats
+            stats = eng.stats
+            if dist.world(self.process_group)[1] > 1:
+                stats = dist.all_reduce_sum_(eng.stats.clone(), self.process_group)
+            if getattr(self, '_wY', None) is None or self._wY.numel() != eng.K_local:
+                self._wY = pt.empty(eng.K_local, dtype=pt.float32, device=self.device)
+                self._lv_out = pt.empty(3, dtype=pt.float64, device=self.device)
+            vp = lambda x: ctypes.c_void_p(x.data_ptr())
+            with pt.cuda.device(self.device):
+                L.check(eng.lib, eng.lib.pspde_lv_cotangents(eng.K_local, float(self.K), 1 if self.loss_method == 'moment' else 0,
+                                                             vp(eng.Y_N), vp(eng.gX), vp(stats), vp(self._wY), vp(self._lv_out),
+                                                             ctypes.c_void_p(pt.cuda.current_stream(self.device).cuda_stream)))
+            if kept and eng.ckpt is not None:
+                eng.grad_from_rows(theta, self._wY, call, self._theta.grad)
+            else:
+                eng.backward_detached(theta, self._wY, None, call, self._theta.grad)
+            if self.learn_Y_0:
+                self.y_0.Y_0.grad = self._wY.sum().reshape(1)
+            loss, n_bad = self._lv_out[0].clone(), self._lv_out[1].clone()
+        elif attached and self.loss_method == 'relative_entropy' and not self.learn_Y_0:
             loss_local = FusedRolloutAttached.apply(self._theta, eng, call)       # constant cotangents: one launch
             loss_local.backward()
             loss, n_bad = dist.all_reduce_sum_(pt.cat([loss_local.detach().double().reshape(1), call.stats[3:4]]),

@@ -1110,3 +1110,39 @@ def test_full_size_properties_c5():
     S.train()
     # kept paths have |D| < 1e6, so the variance is bounded by 1e12 (a few paths near the bound dominate the first iterations)
     assert all(np.isfinite(S.loss_log)) and max(S.loss_log) < 1e12 and bool(pt.isfinite(S._theta).all())
+
+
+def test_fused_iteration_glue_kernels():
+    """pspde_lv_cotangents (loss value + per-path cotangents in one launch) against pspde/losses.py, and pspde_adam_flat against
+    torch.optim.Adam over three steps."""
+    import ctypes
+    from pspde import _lib, losses
+    lib = _lib.load()
+    vp = lambda x: ctypes.c_void_p(x.data_ptr())
+    g = pt.Generator(device="cuda").manual_seed(0)
+    K = 10007
+    Y, gX = pt.randn(K, device="cuda", generator=g), pt.randn(K, device="cuda", generator=g)
+    Y[5], Y[777] = float("nan"), float("nan")                     # dropped trajectories carry Y_N = NaN
+    D = (Y - gX).double()
+    ok = pt.isfinite(D)
+    stats = pt.stack([D[ok].sum(), (D[ok] ** 2).sum(), pt.zeros((), dtype=pt.float64, device="cuda"), (~ok).sum().double()])
+    for moment, name in ((0, "log-variance"), (1, "moment")):
+        wY, out = pt.empty(K, device="cuda"), pt.empty(3, dtype=pt.float64, device="cuda")
+        _lib.check(lib, lib.pspde_lv_cotangents(K, float(K), moment, vp(Y), vp(gX), vp(stats), vp(wY), vp(out), None))
+        loss, w_ref, _, _, n_bad = losses.value_and_cotangents(name, Y, gX, pt.zeros_like(Y), K, stats=stats)
+        assert pt.equal(wY, w_ref) and out[1].item() == n_bad.item() == 2 and out[2].item() == K - 2
+        assert abs(out[0].item() - loss.item()) <= 1e-14 * abs(loss.item())
+    n = 5000
+    p0 = pt.randn(n, device="cuda", generator=g)
+    a, b = p0.clone(), pt.nn.Parameter(p0.clone())
+    m, v = pt.zeros(n, device="cuda"), pt.zeros(n, device="cuda")
+    opt = pt.optim.Adam([b], lr=1e-2)
+    for t in range(1, 4):
+        gr = pt.randn(n, device="cuda", generator=g)
+        b.grad = gr.clone()
+        opt.step()
+        _lib.check(lib, lib.pspde_adam_flat(n, vp(a), vp(gr), vp(m), vp(v), 1e-2, 0.9, 0.999, 1e-8, t, None))
+    pt.cuda.synchronize()
+    assert relerr(a.cpu().numpy(), b.detach().cpu().numpy()) < 1e-6
+    assert relerr(m.cpu().numpy(), opt.state[b]["exp_avg"].cpu().numpy()) < 1e-6
+    assert relerr(v.cpu().numpy(), opt.state[b]["exp_avg_sq"].cpu().numpy()) < 1e-6
