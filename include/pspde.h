@@ -198,8 +198,8 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
  *                        (solver.py:198-200 for every module at once); step = the 1-based step count AFTER this update. */
 int pspde_lv_cotangents(int K_local, double K_global, int moment, const float* Y_N, const float* gX, const double* stats,
                         float* wY, double* out3, void* stream);
-int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                    float beta2, float eps, int64_t step, void* stream);
+int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                    double beta2, double eps, int64_t step, void* stream);
 
 /* Forward + backward for detach_forward=False (solver.py:451-469 without the detach, :221): per tile of paths the
  * states X_n are checkpointed to the workspace and the discrete adjoint runs backwards in time in the same kernel.

@@ -240,12 +240,13 @@ int pspde_lv_cotangents(int K_local, double K_global, int moment, const float* Y
   return 0;
 }
 
-int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
-                    float beta2, float eps, int64_t step, void* stream) {
+int pspde_adam_flat(int64_t n, float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                    double beta2, double eps, int64_t step, void* stream) {
   if (n < 1 || n > 0x7fffffffLL || !theta || !grad || !exp_avg || !exp_avg_sq || step < 1) return fail(-1, "bad arguments");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  // every scalar is formed in double and rounded once, like the Python floats torch hands to its kernels
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   PSPDE_LAUNCH(adam_flat_kernel, (int)((n + 255) / 256), 256, 0, stream, (int)n, theta, grad, exp_avg, exp_avg_sq,
-               (float)((double)lr / bc1), (float)sqrt(bc2), beta1, beta2, eps);
+               (float)(lr / bc1), (float)sqrt(bc2), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
   g_launches++;
   if (const char* e = pspde_peek_error()) return fail(-12, "adam_flat launch failed: %s", e);
   return 0;

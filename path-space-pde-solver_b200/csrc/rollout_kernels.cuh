@@ -1086,12 +1086,13 @@ __device__ __forceinline__ float rn_sqrt(float a) { return __fsqrt_rn(a); }
 // One Adam step over a flat parameter buffer: the op sequence of torch.optim.Adam's single-tensor form (no weight decay,
 // no amsgrad): m = lerp(m, g, 1 - b1); v = v b2 + (1 - b2) g g; theta -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps).
 static __global__ void adam_flat_kernel(int n, float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
-                                        float* __restrict__ v, float lr_over_bc1, float sqrt_bc2, float b1, float b2, float eps) {
+                                        float* __restrict__ v, float lr_over_bc1, float sqrt_bc2, float omb1, float b2, float omb2,
+                                        float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const float gi = g[i];
-    const float mi = rn_add(m[i], rn_mul(rn_sub(gi, m[i]), 1.0f - b1));
-    const float vi = rn_add(rn_mul(v[i], b2), rn_mul(rn_mul(gi, gi), 1.0f - b2));
+    const float mi = rn_add(m[i], rn_mul(rn_sub(gi, m[i]), omb1));
+    const float vi = rn_add(rn_mul(v[i], b2), rn_mul(rn_mul(gi, gi), omb2));
     m[i] = mi; v[i] = vi;
     const float denom = rn_add(rn_div(rn_sqrt(vi), sqrt_bc2), eps);
     theta[i] = rn_sub(theta[i], rn_mul(lr_over_bc1, rn_div(mi, denom)));

@@ -88,8 +88,8 @@ PROTOTYPES = {
     "pspde_tma_selftest": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, _P, _P, _P]),
     "pspde_mma_probe": (ctypes.c_int, [ctypes.c_int, _P, _P]),
     "pspde_lv_cotangents": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, _P, _P, _P, _P, _P, _P]),
-    "pspde_adam_flat": (ctypes.c_int, [ctypes.c_int64, _P, _P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                       ctypes.c_float, ctypes.c_int64, _P]),
+    "pspde_adam_flat": (ctypes.c_int, [ctypes.c_int64, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_int64, _P]),
     "pspde_fma_probe": (ctypes.c_int64, [ctypes.c_int, _P, _P]),
     "pspde_fma_probe_ex": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int, _P, _P]),
 }
