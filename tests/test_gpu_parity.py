@@ -1146,3 +1146,43 @@ def test_fused_iteration_glue_kernels():
     assert relerr(a.cpu().numpy(), b.detach().cpu().numpy()) < 1e-6
     assert relerr(m.cpu().numpy(), opt.state[b]["exp_avg"].cpu().numpy()) < 1e-6
     assert relerr(v.cpu().numpy(), opt.state[b]["exp_avg_sq"].cpu().numpy()) < 1e-6
+
+
+def test_full_size_properties_c3(monkeypatch):
+    """BASELINE configs[2] size (DoubleWell_multidim d = 50, K = 2^18, N = 200, MySequential): the log-variance step through the
+    tensor-core kernels (deterministic forward, statistics == host recomputation, gradient linear in the cotangent) and the
+    attached relative-entropy kernel, whose default of two CTAs per SM (<= 128 registers) must reproduce one CTA per SM
+    (PSPDE_ATT_CTAS=1, 208 registers): same loss, same gradient up to the order of the per-CTA partial sums."""
+    import pspde
+    from pspde.fused import Call
+    d, K = 50, 1 << 18
+    prob = pspde.DoubleWell_multidim(d=d, d_1=15, d_2=35, T=1, eta=3, kappa=5, device="cuda")
+    S = pspde.Solver("c3", prob, K=K, L=1, lr=0.05, delta_t=0.005, time_approx="inner", detach_forward=True,
+                     u_l2_error_flag=False, early_stopping_time=None, verbose=False)
+    eng = S._get_engine()
+    theta = S._theta.detach()
+    eng.forward(theta, None, Call(offset=0))
+    Y, gX, st = eng.Y_N.clone(), eng.gX.clone(), eng.stats.clone()
+    eng.forward(theta, None, Call(offset=0))
+    assert pt.equal(Y, eng.Y_N) and pt.allclose(st, eng.stats, rtol=1e-13) and st[3].item() == 0
+    D = Y.double() - gX.double()
+    assert pt.allclose(st[:2], pt.stack([D.sum(), (D ** 2).sum()]), rtol=1e-10)
+    w1, w2 = pt.randn(K, device="cuda") / K, pt.randn(K, device="cuda") / K
+    gs = []
+    for w in (w1, w2, (w1 + 2 * w2).contiguous()):
+        gr = pt.empty(eng.n_theta, device="cuda")
+        eng.backward_detached(theta, w, None, Call(offset=0), gr)
+        gs.append(gr)
+    assert relerr((gs[0] + 2 * gs[1]).cpu().numpy(), gs[2].cpu().numpy()) < 2e-5
+    # attached relative entropy: 2 CTAs per SM (default) against 1
+    out = {}
+    for mode in ("2", "1"):
+        monkeypatch.setenv("PSPDE_ATT_CTAS", mode)
+        A = pspde.Solver("c3re", prob, K=K, L=1, lr=0.0, delta_t=0.005, time_approx="inner", loss_method="relative_entropy",
+                         detach_forward=False, u_l2_error_flag=False, early_stopping_time=None, verbose=False)
+        res = A.gradient_descent(Call(offset=0))
+        pt.cuda.synchronize()
+        out[mode] = (res[0].item(), A._theta.grad.clone(), A._get_engine().Zsum.clone())
+    assert pt.equal(out["1"][2], out["2"][2])                          # per-path results do not depend on the CTA layout
+    assert abs(out["1"][0] - out["2"][0]) <= 1e-9 * abs(out["1"][0])
+    assert relerr(out["2"][1].cpu().numpy(), out["1"][1].cpu().numpy()) < 2e-6
