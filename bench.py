@@ -51,6 +51,13 @@ WORKLOADS = {
     "c5": dict(kind="llgc", pkw=dict(d=100, off_diag=0, T=1, seed=42), net="densenet", ta="inner", K=1 << 20,
                dt=0.005, loss="log-variance", detach=True, lr=1e-3,
                desc="C5: LLGC d=100, DenseNet inner, K=2^20/GPU, N=200, log-variance"),
+    # the rest of BASELINE configs[4]'s sweep K = 2^20 .. 2^24: 2^22 on one GPU; 2^21 per GPU = 2^24 over 8 GPUs
+    "c5_k22": dict(kind="llgc", pkw=dict(d=100, off_diag=0, T=1, seed=42), net="densenet", ta="inner", K=1 << 22,
+                   dt=0.005, loss="log-variance", detach=True, lr=1e-3,
+                   desc="C5 sweep: LLGC d=100, DenseNet inner, K=2^22/GPU, N=200, log-variance"),
+    "c5_k21": dict(kind="llgc", pkw=dict(d=100, off_diag=0, T=1, seed=42), net="densenet", ta="inner", K=1 << 21,
+                   dt=0.005, loss="log-variance", detach=True, lr=1e-3,
+                   desc="C5 sweep: LLGC d=100, DenseNet inner, K=2^21/GPU (2^24 over 8 GPUs), N=200, log-variance"),
     "c1": dict(kind="lqgc", pkw=dict(d=10), net="densenet", ta="outer", K=200, dt=0.05, loss="log-variance",
                detach=True, lr=1e-3, desc="C1: LQGC d=10, 100 x DenseNet[10,30,30,10] outer, K=200, N=100"),
     "c3": dict(kind="dwm", pkw=dict(d=50, d_1=15, d_2=35, T=1, eta=3, kappa=5), net="mlp", ta="inner", K=1 << 18,
