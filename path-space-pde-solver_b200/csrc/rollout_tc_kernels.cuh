@@ -4,7 +4,7 @@
 //   DenseNet (function_space.py:116-140) or MySequential (:177-195) with two hidden layers of at most 32 (31) units,
 //   'inner' time input, diagonal problem functors (LLGC / LQGC with off_diag = 0, DoubleWell_multidim),
 // which covers the BASELINE configs C1-inner, C2, C3 (detached) and C5.  A tile is 128 trajectories = the 128 lanes of tensor
-// memory; every trajectory is owned by three threads (one per third of the state columns) for the whole rollout:
+// memory; every trajectory is owned by kTcTPP = 4 threads (one per quarter of the state columns) for the whole rollout:
 //
 //   tensor memory (512 columns x 128 lanes, all allocated):
 //     A operands, hi and lo TF32 halves: a0 = [X | t | 1 | 0] (s0 columns), h1 (32), h2 (32)       2 (s0 + 64) columns
@@ -30,11 +30,13 @@
 namespace pspde {
 
 constexpr int kTcP = 128;        // trajectories per tile = tensor-memory lanes
-// Threads per trajectory (column parts).  THREE, i.e. 12 warps per CTA: one CTA per SM (213 KB of weights), so the register
-// file allows 65536 / 384 = 170 registers per thread -- room for the state, the step's Brownian increments (4 NG registers
-// each) and the transients of the update without spills.  With four threads per trajectory (128 registers) the kernel
-// spilled ~100 values per thread, and local memory is an L2 round trip here (L1 is what shared memory leaves: ~14 KB).
-constexpr int kTcTPP = 3;
+// Threads per trajectory (column parts).  FOUR, i.e. 16 warps per CTA at 128 registers (one CTA per SM: 213 KB of weights).
+// History: while the state X lived in registers, four threads per trajectory spilled ~100 values per thread (local memory is an
+// L2 round trip here: L1 is what shared memory leaves, ~14 KB) and THREE (170 registers) was faster.  Since X is read back from
+// its tensor-memory operand columns the kernel spills ~40 - 50 values either way, and the fourth warp per scheduler hides more
+// of the tensor-memory / mbarrier latency than the spills cost: row-keeping forward 4.60 -> 4.39 ms at C2, C3 step 70.0 ->
+// 66.1 ms, C5 step 372 -> 368 ms (the plain forward is a wash: 105 -> 108 ms at C5).
+constexpr int kTcTPP = 4;
 constexpr int kTcThreads = kTcP * kTcTPP;
 constexpr int kTcIssuer = (kTcThreads / 32 - 1) * 32; // the thread that issues the MMAs: a lane of the last warp, whose column part is
                                    // the short one (the state columns do not divide evenly), so the issue work does not delay the slowest warp
@@ -538,8 +540,8 @@ inline cudaError_t tc_launch_one(const RolloutParams& p, const TcGeom& tg, int g
 template <bool CKPT, bool DIAG = false>
 inline cudaError_t tc_launch_t(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
   if (tg.ng <= 2) return tc_launch_one<2, CKPT, DIAG>(p, tg, grid, stream);
-  if (tg.ng <= 5) return tc_launch_one<5, CKPT, DIAG>(p, tg, grid, stream);      // d <= 58 (C3: d = 50)
-  if (tg.ng <= 9) return tc_launch_one<9, CKPT, DIAG>(p, tg, grid, stream);      // d <= 106 (C2 / C5: d = 100)
+  if (tg.ng <= 4) return tc_launch_one<4, CKPT, DIAG>(p, tg, grid, stream);      // (C3: d = 50)
+  if (tg.ng <= 7) return tc_launch_one<7, CKPT, DIAG>(p, tg, grid, stream);      // (C2 / C5: d = 100)
   return tc_launch_one<kTcMaxG, CKPT, DIAG>(p, tg, grid, stream);
 }
 inline cudaError_t tc_launch(const RolloutParams& p, const TcGeom& tg, int grid, cudaStream_t stream) {
