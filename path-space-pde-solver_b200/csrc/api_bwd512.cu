@@ -7,6 +7,7 @@ int pspde_launch_bwd_512(const Plan& pl, const pspde::RolloutParams& p, void* st
 }
 
 int pspde_launch_grad_512(const Plan& pl, const pspde::RolloutParams& p, int grid, int n_items, void* stream) {
+  if (!p.th_tbl) return fail(-13, "could not allocate the weight-image index table");
   auto kern = pspde::grad_kernel<kP, 512>;
   if (pspde_set_smem(kern, pl.smem_bytes)) return fail(-11, "cudaFuncSetAttribute(%zu B smem) failed", pl.smem_bytes);
   PSPDE_LAUNCH(kern, grid, 512, pl.smem_bytes, stream, p, n_items);

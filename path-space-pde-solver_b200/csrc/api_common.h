@@ -61,7 +61,7 @@ constexpr size_t kMaxSmem = 227 * 1024;      // opt-in dynamic shared memory per
 
 struct Plan {
   NetGeom g;
-  int T, NB, n_tiles, grid, n_sets, n_theta_total, ctas_per_sm;
+  int T, NB, n_tiles, grid, n_sets, n_theta_total, n_img_total, ctas_per_sm;
   int r_fwd[PSPDE_MAXL];
   size_t smem_bytes, stats_bytes, grad_bytes;
 };
@@ -113,6 +113,7 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
   if (rc) return fail(-3, "network geometry rejected (code %d): dims[0] must be d%s", rc, c->time_mode == PSPDE_TIME_NONE ? "" : "+1");
   pl.n_sets = (c->time_mode == PSPDE_TIME_NONE) ? (c->n_sets > 0 ? c->n_sets : c->N) : 1;
   pl.n_theta_total = pl.g.n_params * pl.n_sets;
+  pl.n_img_total = pl.g.w_floats * pl.n_sets;     // one CTA's weight-gradient partial (weight-image layout)
   pl.n_tiles = (c->K_local + kP - 1) / kP;
   const int sms = pspde_sm_count();
   if (sms <= 0) return fail(-10, "no CUDA device");
@@ -143,9 +144,11 @@ static inline int make_plan(const pspde_cfg* c, bool bwd, bool attached, Plan& p
     if (!(e && e[0] == '1')) { pl.ctas_per_sm = 2; pl.grid = pl.n_tiles < 2 * sms ? pl.n_tiles : 2 * sms; }
   }
   pl.stats_bytes = align256((size_t)pl.grid * 4 * sizeof(double));
-  pl.grad_bytes = bwd ? align256((size_t)pl.grid * pl.n_theta_total * sizeof(float)) : 0;
+  pl.grad_bytes = bwd ? align256((size_t)pl.grid * pl.n_img_total * sizeof(float)) : 0;
   return 0;
 }
+
+const int* pspde_theta_table(const pspde::NetGeom& g);   // api_core.cu
 
 static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams& p) {
   memset(&p, 0, sizeof(p));
@@ -155,16 +158,18 @@ static inline void fill_params(const pspde_cfg* c, const Plan& pl, RolloutParams
   p.noise_mode = c->noise_mode; p.x0_per_path = c->x0_per_path;
   p.seed = c->seed; p.offset = c->offset;
   p.xs_k = c->xi_stride_k; p.xs_j = c->xi_stride_j; p.xs_n = c->xi_stride_n;
-  p.n_tiles = pl.n_tiles; p.n_theta_total = pl.n_theta_total;
+  p.n_tiles = pl.n_tiles; p.n_theta_total = pl.n_theta_total; p.n_img_total = pl.n_img_total;
   for (int l = 0; l < PSPDE_MAXL; ++l) p.r_fwd[l] = pl.r_fwd[l];
   p.prof = g_prof;
   p.n_sets = pl.n_sets;
   p.u_quirk = -1;
   p.d_abs_max = c->d_abs_max > 0.f ? c->d_abs_max : INFINITY;
+  p.th_tbl = pspde_theta_table(pl.g);   // nullptr = allocation failure: the launchers of the gradient kernels report it
 }
 
 template <int T, bool BWD, int NB>
 static inline int launch_rollout(const Plan& pl, const RolloutParams& p, void* stream) {
+  if (BWD && !p.th_tbl) return fail(-13, "could not allocate the weight-image index table");
   auto kern = rollout_kernel<kP, T, BWD, NB>;
   if (pspde_set_smem(kern, pl.smem_bytes)) return fail(-11, "cudaFuncSetAttribute(%zu B smem) failed", pl.smem_bytes);
   PSPDE_LAUNCH(kern, pl.grid, T, pl.smem_bytes, stream, p);

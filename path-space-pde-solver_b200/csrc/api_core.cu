@@ -1,5 +1,6 @@
 // api_core.cu -- extern "C" entry points declared in include/pspde.h.
 #include "api_common.h"
+#include <mutex>
 #include "rollout_tc_kernels.cuh"
 #include "grad_kernels.cuh"
 #include "grad_tc2_kernels.cuh"
@@ -8,6 +9,48 @@
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 unsigned long long* g_prof = nullptr;
+
+// Index table of the shared weight image for the FP32-FMA kernels in 'outer' mode (RolloutParams::th_tbl): built on the host
+// once per (device, network geometry), kept for the life of the process (at most 32 geometries; nullptr beyond that or on an
+// allocation failure = the kernels fall back to theta_index()).
+const int* pspde_theta_table(const NetGeom& g) {
+  struct Entry { int dev, kind, L, time_mode, d, dims[PSPDE_MAXL + 1]; int* tbl; };
+  static Entry cache[32];
+  static int n_cache = 0;
+  static std::mutex mu;
+  int dev = 0;
+#if !defined(PSPDE_EMULATE)
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+#endif
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_cache; ++i) {
+    const Entry& e = cache[i];
+    bool same = e.dev == dev && e.kind == g.kind && e.L == g.L && e.time_mode == g.time_mode && e.d == g.d;
+    for (int l = 0; same && l <= g.L; ++l) same = e.dims[l] == g.dims[l];
+    if (same) return e.tbl;
+  }
+  if (n_cache == 32) return nullptr;
+  const size_t n = 2 * (size_t)(g.w_floats >> 2);
+  int* host = static_cast<int*>(malloc(n * sizeof(int)));
+  if (!host) return nullptr;
+  theta_table_fill(g, host);
+  int* tbl = host;
+#if !defined(PSPDE_EMULATE)
+  tbl = nullptr;
+  if (cudaMalloc(&tbl, n * sizeof(int)) != cudaSuccess || cudaMemcpy(tbl, host, n * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (tbl) cudaFree(tbl);
+    free(host);
+    return nullptr;
+  }
+  free(host);
+#endif
+  Entry e;
+  e.dev = dev; e.kind = g.kind; e.L = g.L; e.time_mode = g.time_mode; e.d = g.d; e.tbl = tbl;
+  for (int l = 0; l <= PSPDE_MAXL; ++l) e.dims[l] = l <= g.L ? g.dims[l] : 0;
+  cache[n_cache++] = e;
+  return tbl;
+}
 
 // Must the zeta columns be written to the checkpoint?  Not when zeta = wY sqrt(dt) xi with in-kernel noise (adaptive process,
 // no cotangent on Z_sum): the gradient kernel regenerates it from the Philox key (RolloutParams::ckpt_zeta).
@@ -108,9 +151,9 @@ static int launch_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
   return fail(-13, "internal: no gradient kernel for T=%d", pl.T);
 }
 
-// floats of one CTA's gradient partial: theta layout (FMA kernel) or raw accumulator layout (tensor-core kernel)
+// floats of one CTA's gradient partial: weight-image layout (FMA kernel) or raw accumulator layout (tensor-core kernel)
 static size_t grad_part_floats(const pspde_cfg* cfg, const Plan& pl, int s0) {
-  size_t n = (size_t)pl.n_theta_total;
+  size_t n = (size_t)pl.n_img_total;
 #if !defined(PSPDE_EMULATE)
   GradTcGeom gt;
   if (grad_tc_geom(pl.g, cfg->d, s0, gt) && (size_t)(2 * 128 * gt.nB) > n) n = (size_t)(2 * 128 * gt.nB);
@@ -118,6 +161,17 @@ static size_t grad_part_floats(const pspde_cfg* cfg, const Plan& pl, int s0) {
   (void)cfg; (void)s0;
 #endif
   return n;
+}
+
+// FP32-FMA kernels: weight-image partials of nparts CTAs -> grad_theta (reduce_grad_image_kernel)
+static int reduce_grad_image(const Plan& pl, const RolloutParams& p, int nparts, float* grad_theta, void* stream) {
+  if (!p.th_tbl) return fail(-13, "could not allocate the weight-image index table");
+  const int w4 = pl.g.w_floats >> 2, tot = pl.n_sets * w4;
+  PSPDE_LAUNCH(reduce_grad_image_kernel, (tot + 255) / 256, 256, 0, stream, p.grad_partial, nparts, pl.n_sets, w4, p.th_tbl,
+               pl.g.n_params, grad_theta);
+  g_launches++;
+  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
+  return 0;
 }
 
 static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams& p, int nparts, int used_tc, float* grad_theta, void* stream) {
@@ -142,10 +196,8 @@ static int reduce_grad(const pspde_cfg* cfg, const Plan& pl, const RolloutParams
 #else
   (void)cfg; (void)used_tc;
 #endif
-  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, nparts, n, grad_theta);
-  g_launches++;
-  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
-  return 0;
+  (void)n;
+  return reduce_grad_image(pl, p, nparts, grad_theta, stream);
 }
 
 #if !defined(PSPDE_EMULATE)
@@ -395,17 +447,13 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
     }
   }
 #endif
-  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
+  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_img_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
   if (pl.T == 256) rc = pspde_launch_bwd_256(pl, p, stream);
   else if (pl.T == 512) rc = pspde_launch_bwd_512(pl, p, stream);
   else rc = fail(-13, "internal: no kernel for T=%d NB=%d", pl.T, pl.NB);
   if (rc) return rc;
-  const int n = pl.n_theta_total;
-  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, pl.grid, n, grad_theta);
-  g_launches++;
-  if (const char* e = pspde_peek_error()) return fail(-12, "reduce_grad launch failed: %s", e);
-  return 0;
+  return reduce_grad_image(pl, p, pl.grid, grad_theta, stream);
 }
 
 int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* ckpt, int n_slots, int s0,
@@ -526,7 +574,7 @@ int pspde_rollout_attached_diag(const pspde_cfg* cfg, const float* theta, const 
   p.stats_partial = reinterpret_cast<double*>(ws);
   p.grad_partial = reinterpret_cast<float*>(ws + pl.stats_bytes);
   p.x_ckpt = reinterpret_cast<float*>(ws + pl.stats_bytes + pl.grad_bytes);
-  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_theta_total * sizeof(float), stream))
+  if (pspde_memset0(p.grad_partial, (size_t)pl.grid * pl.n_img_total * sizeof(float), stream))
     return fail(-12, "memset of the gradient partials failed");
   rc = (pl.T == 256) ? pspde_launch_att_256(pl, p, stream) : pspde_launch_att_512(pl, p, stream);
   if (rc) return rc;
@@ -534,11 +582,7 @@ int pspde_rollout_attached_diag(const pspde_cfg* cfg, const float* theta, const 
     PSPDE_LAUNCH(reduce_stats_kernel, 1, 32, 0, stream, p.stats_partial, pl.grid, stats);
     g_launches++;
   }
-  const int n = pl.n_theta_total;
-  PSPDE_LAUNCH(reduce_grad_kernel, (n + 255) / 256, 256, 0, stream, p.grad_partial, pl.grid, n, grad_theta);
-  g_launches++;
-  if (const char* e = pspde_peek_error()) return fail(-12, "reduce launch failed: %s", e);
-  return 0;
+  return reduce_grad_image(pl, p, pl.grid, grad_theta, stream);
 }
 
 int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const float* prob, const float* x0,

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(T, 1) grad_kernel(const RolloutParams prm, con
 #pragma unroll
   for (int q = 0; q < 32; ++q) acc[q] = f2_zero();
   const BwSlot slot = bw_slot(g, P, tid, T);
-  float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
+  float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_img_total;
 
   // checkpoint columns -> tiles: segment s of the activation row, then zeta (column-major rows of 128 paths)
   const int s0 = prm.ckpt_s0;

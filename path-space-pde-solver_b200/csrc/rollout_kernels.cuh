@@ -32,6 +32,7 @@ struct RolloutParams {
   long long xs_k, xs_j, xs_n;
   int n_tiles;         // ceil(K_local / P)
   int n_theta_total;   // n_params * (TIME_NONE ? N : 1)
+  int n_img_total;     // w_floats * (TIME_NONE ? N : 1): floats of one CTA's weight-gradient partial (weight-IMAGE layout)
   int r_fwd[PSPDE_MAXL];  // paths per thread tile in gemm_nn, per layer (1, 2, 4 or 8)
   float w_attached;    // attached mode without per-path cotangents: wZ = wG = w_attached, wY = 0 (relative entropy)
   const float *theta, *prob, *x0, *y0, *xi, *wY, *wZ, *wG;
@@ -49,7 +50,9 @@ struct RolloutParams {
                        // (pspde_cfg::d_abs_max; +inf when the caller leaves it off)
   float* uL2;          // per-path output
   double* stats_partial;  // [gridDim.x][4]
-  float* grad_partial;    // [gridDim.x][n_theta_total]
+  float* grad_partial;    // FP32-FMA kernels: [gridDim.x][n_sets][w_floats], the k4-blocked layout of the shared weight image
+                          // (pspde_geom.h) -- a thread's 8x8 block is then 16 aligned float4s; reduce_grad_image_kernel maps it
+                          // to theta.  (The tensor-core gradient kernels keep their own accumulator layout here.)
   float* x_ckpt;          // attached mode: [gridDim.x][N][P][d] state checkpoints of the current tile
   // checkpointed detached backward (rollout_tc_kernels.cuh / grad_kernels.cuh): the tensor-core forward kernel writes,
   // for every (tile slot, step), the operand rows of the gradient accumulation, [a0 | h1 | h2 | zeta], COLUMN-major with
@@ -65,6 +68,10 @@ struct RolloutParams {
   int ckpt_zeta;          // 1: the zeta columns are in the checkpoint; 0: they are NOT written -- zeta = wY sqrt(dt) xi is a
                           //    function of (path, step, Philox key) alone (adaptive process, no cotangent on Z_sum, in-kernel
                           //    noise), so the gradient kernel regenerates it: 38 % less checkpoint traffic at the C2 shape
+  const int* th_tbl;      // FP32-FMA kernels, nullable: (theta index, column stride | valid columns << 28) of every float4 of the
+                          // shared k4-blocked weight image (theta_table_fill() below); 'outer' mode restages the weights and flushes
+                          // the weight gradient EVERY step, and evaluating theta_index() there cost more than the network itself
+                          // (C1: 28 k of 78 k cycles per step in the flush alone)
   const uint8_t* wpack;   // tensor-core rollout: shared-memory image of the six weight tiles in global memory (one bulk copy per
                           // CTA), or nullptr = every CTA stages its tiles from theta
   unsigned long long* prof;  // debug: per-phase clock64() totals of CTA 0 (16 slots) or nullptr
@@ -103,6 +110,11 @@ __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_ca
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over aligned groups of G lanes (G a power of two); every lane of the warp must call it
+__device__ __forceinline__ float group_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -276,22 +288,32 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, c
 // an extra full-length warp for a handful of blocks (SMSP loads 3/3/3/3 + a sliver instead of 4/3/3/3 at C2).
 // A leftover block is split into cpb = 2^k row chunks held by cpb ADJACENT lanes of one warp; the flush combines
 // them with a fixed xor-shuffle butterfly, so the result stays bitwise deterministic.
-struct BwSlot { int b, p_lo, p_hi, cpb; };   // cpb > 1: this WARP holds row-split blocks (uniform per warp)
+// cpb > 1: this WARP holds row-split blocks (uniform per warp); a lane then owns the rows p_lo, p_lo + cpb, ... of its block.
+// (Interleaved, not contiguous chunks: neighbouring lanes then read neighbouring rows of the activation and cotangent tiles,
+// like the quarter-warps of gemm_nn; with contiguous chunks they sat P / cpb rows = a multiple of 32 banks apart and every
+// LDS.128 replayed cpb times -- 420 cycles per row at C1.)
+struct BwSlot { int b, p_lo, p_hi, cpb; };
 
 __device__ __forceinline__ BwSlot bw_slot(const NetGeom& g, int P, int tid, int nthr) {
   BwSlot s; s.b = -1; s.p_lo = 0; s.p_hi = P; s.cpb = 1;
-  const int nb = g.n_blocks, full = nb & ~31, rem = nb - full, lrem = nthr - full;
+  const int nb = g.n_blocks;
+  // small networks (fewer blocks than half the threads): split EVERY block's rows over cpb lanes, so that no warp walks
+  // all P rows alone while the others idle (C1: 52 blocks, 256 threads -> 4 lanes x 16 rows per block)
+  if (2 * nb <= nthr) {
+    int cpb = 2;
+    while (cpb * 2 <= 32 && cpb * 2 <= P && cpb * 2 * nb <= nthr) cpb *= 2;
+    if ((tid & ~31) < nb * cpb) s.cpb = cpb;         // (a warp without any block stays out of the flush shuffles)
+    if (tid < nb * cpb) { s.b = tid / cpb; s.p_lo = tid % cpb; }
+    return s;
+  }
+  const int full = nb & ~31, rem = nb - full, lrem = nthr - full;
   if (tid < full) { s.b = tid; return s; }
   if (rem == 0 || lrem <= 0) return s;
   int cpb = 1;
   while (cpb * 2 <= 32 && cpb * 2 <= P && cpb * 2 * rem <= lrem) cpb *= 2;
-  const int l = tid - full, chunk = P / cpb;     // P and cpb are powers of two
+  const int l = tid - full;                      // P and cpb are powers of two
   s.cpb = cpb;
-  if (l < rem * cpb) {
-    s.b = full + l / cpb;
-    s.p_lo = (l % cpb) * chunk;
-    s.p_hi = s.p_lo + chunk;
-  }
+  if (l < rem * cpb) { s.b = full + l / cpb; s.p_lo = l % cpb; }
   return s;
 }
 
@@ -314,11 +336,12 @@ __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, con
   const bool ha = kg + y.kgh < y.nkg, hd = ng + y.ngh < y.nng;
   const float* a1p = ha ? a0p + 4 * y.kgh : smem + sl.zero;
   const float* d1p = hd ? d0p + 4 * y.ngh : smem + sl.zero;
-  const int sa1 = ha ? lda : 0, sd1 = hd ? ldd : 0;
+  const int step = slot.cpb, sa0 = step * lda, sd0 = step * ldd;
+  const int sa1 = ha ? sa0 : 0, sd1 = hd ? sd0 : 0;
 #pragma unroll 2
-  for (int p = slot.p_lo; p < slot.p_hi; ++p) {
+  for (int p = slot.p_lo; p < slot.p_hi; p += step) {
     const float4 a0 = ld4(a0p), v0 = ld4(d0p), a1 = ld4(a1p), v1 = ld4(d1p);
-    a0p += lda; a1p += sa1; d0p += ldd; d1p += sd1;
+    a0p += sa0; a1p += sa1; d0p += sd0; d1p += sd1;
     const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -328,10 +351,39 @@ __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, con
   }
 }
 
-// acc -> grad_partial (this CTA's private slice; fire-and-forget adds, one writer per element), then clear.
-// Must be called by all lanes of a warp (row-split warps combine their chunks with shuffles first).
+#if defined(PSPDE_EMULATE)
+#define PSPDE_NOINLINE
+#else
+#define PSPDE_NOINLINE __noinline__
+#endif
+
+// One float4 (4 neighbouring columns of one row) of a weight-gradient block: combine the row-split lanes (fixed order), then
+// add it into the CTA's private slice with ONE 16-byte RED (one writer per element and program order per address, so the
+// sums stay bitwise deterministic).  The slice is in weight-image layout, so the float4 is aligned; in theta layout the same
+// flush took 64 scalar REDs per thread, which in 'outer' mode (a flush every step into a 9 KB slice) queued up in a few L2
+// slices: 16 k cycles per flush at C1.
+// NOT inlined on purpose: unrolled per flush (and the flush twice per kernel) this tail was 5 k instructions, and 'outer'
+// mode, which runs every phase of the kernel once per step, then spends its time in instruction fetch.
+static __device__ PSPDE_NOINLINE void bw_flush_quad(float v0, float v1, float v2, float v3, int cpb, float* p, bool write) {
+  for (int o = 1; o < cpb; o <<= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+  }
+  if (write) {
+#if defined(PSPDE_EMULATE)
+    p[0] += v0; p[1] += v1; p[2] += v2; p[3] += v3;
+#else
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+#endif
+  }
+}
+
+// acc -> grad_partial (this CTA's private slice, weight-image layout), then clear.  Must be called by all lanes of a warp
+// (row-split warps combine their chunks with shuffles first).
 __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, const BwSlot& slot,
-                                         float* __restrict__ gp, int lane) {
+                                         float* __restrict__ gimg, int lane) {
   if (slot.cpb == 1 && slot.b < 0) return;      // whole warp idle or plain lane without a block
   const int b = slot.b < 0 ? 0 : slot.b;
   int l = 0;
@@ -340,35 +392,61 @@ __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, con
   int kg, ng;
   bw_block_coords(y, b - y.blk_begin, kg, ng);
   const bool writer = slot.b >= 0 && (slot.cpb == 1 || (lane & (slot.cpb - 1)) == 0);
+  const int nng = y.nng;
+  const bool okn[2] = {writer, writer && ng + y.ngh < nng};
+  const bool okk[2] = {true, kg + y.kgh < y.nkg};
+  // image offset of (row 4 kgx + r, columns 4 ngx ..): w_off + ((kgx * nng + ngx) * 4 + r) * 4
+  float* base = gimg + y.w_off;
+  const int o_k[2] = {kg * nng, (kg + y.kgh) * nng}, o_n[2] = {ng, ng + y.ngh};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int row = 4 * (i < 4 ? kg : kg + y.kgh) + (i & 3);
-    // theta_index is affine in the column for a fixed row: two evaluations per row instead of one per element (its
-    // segment search dominated 'outer' mode, which flushes every step: ncu, C1)
-    const int ib0 = theta_index(g, l, row, 0);
-    const int ib1 = y.N > 1 ? theta_index(g, l, row, 1) : -1;
-    const int ics = ib1 >= 0 ? ib1 - ib0 : 1;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v[2];
-      f2_unpack(acc[4 * i + q], v[0], v[1]);
-      acc[4 * i + q] = f2_zero();
-      if (slot.cpb > 1) {                        // warp-uniform: sum the row chunks of each block, fixed order
-        for (int o = 1; o < slot.cpb; o <<= 1) {
-          v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-          v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = 4 * (q < 2 ? ng : ng + y.ngh) + 2 * (q & 1) + h;
-        const bool ok = writer && (i < 4 || kg + y.kgh < y.nkg) && (q < 2 || ng + y.ngh < y.nng);
-        const int idx = (ok && ib0 >= 0 && col < y.N) ? ib0 + col * ics : -1;
-        // RED.ADD, not load-add-store: 64 dependent global round trips per thread cost ~100 k cycles per flush, which
-        // 'outer' mode pays every step (measured at C1).  Still one writer per element and program order per address,
-        // so the sums stay bitwise deterministic.
-        if (idx >= 0) atomicAdd(gp + idx, v[h]);
-      }
+    for (int hq = 0; hq < 2; ++hq) {
+      float v0, v1, v2, v3;
+      f2_unpack(acc[4 * i + 2 * hq], v0, v1);
+      f2_unpack(acc[4 * i + 2 * hq + 1], v2, v3);
+      acc[4 * i + 2 * hq] = f2_zero();
+      acc[4 * i + 2 * hq + 1] = f2_zero();
+      bw_flush_quad(v0, v1, v2, v3, slot.cpb, base + ((o_k[i >> 2] + o_n[hq]) * 4 + (i & 3)) * 4, okk[i >> 2] && okn[hq]);
+    }
+  }
+}
+
+// weight-image partials of all CTAs -> theta layout: one thread per (parameter set, float4 of the image); the CTAs are summed
+// in index order (deterministic).  tbl = RolloutParams::th_tbl.  Every parameter is the image of exactly one entry.
+static __global__ void reduce_grad_image_kernel(const float* __restrict__ partial, int nparts, int n_sets, int w4,
+                                                const int* __restrict__ tbl, int n_params, float* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_sets * w4) return;
+  const int set = q / w4, q4 = q - set * w4;
+  const int b0 = tbl[2 * q4], cs = tbl[2 * q4 + 1];
+  if (b0 < 0) return;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < nparts; ++c) {
+    const float* v = partial + (((size_t)c * n_sets + set) * w4 + q4) * 4;
+    s[0] += v[0]; s[1] += v[1]; s[2] += v[2]; s[3] += v[3];
+  }
+  const int nv = cs >> 28, st = cs & 0x0fffffff;
+  float* o = out + (size_t)set * n_params + b0;
+  for (int c = 0; c < nv; ++c) o[c * st] = s[c];
+}
+
+// (theta index, column stride | valid columns << 28) for every float4 of the shared weight image: what stage_weights and
+// bw_flush otherwise derive per element with theta_index().  tbl holds 2 * (g.w_floats / 4) ints; built once per network
+// geometry on the host (api_core.cu: pspde_theta_table).
+inline void theta_table_fill(const NetGeom& g, int* tbl) {
+  for (int l = 0; l < g.L; ++l) {
+    const LayerGeom& y = g.layer[l];
+    const int tot4 = (y.Kp * y.Np) >> 2;
+    for (int q4 = 0; q4 < tot4; ++q4) {
+      const int blk = q4 >> 2;
+      const int r = 4 * (blk / y.nng) + (q4 & 3), n0 = 4 * (blk % y.nng);
+      const int b0 = theta_index(g, l, r, n0);
+      const int b1 = n0 + 1 < y.N ? theta_index(g, l, r, n0 + 1) : -1;
+      const int cs = b1 >= 0 ? b1 - b0 : 1;
+      const int nv = b0 >= 0 ? (y.N - n0 < 4 ? y.N - n0 : 4) : 0;
+      int* e = tbl + 2 * ((y.w_off >> 2) + q4);
+      e[0] = b0; e[1] = cs | (nv << 28);
     }
   }
 }
@@ -376,7 +454,23 @@ __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, con
 // ------------------------------------------------------------------------------------------------ staging
 // theta (one parameter set, reference layout) -> shared k4-blocked W_l with zero pads.
 __device__ __forceinline__ void stage_weights(const NetGeom& g, const float* __restrict__ th, float* sW, int tid,
-                                              int nthr) {
+                                              int nthr, const int* __restrict__ tbl = nullptr) {
+  if (tbl) {       // one (index, stride) pair per float4 of the image; the image is contiguous over the layers
+    const int tot4 = g.w_floats >> 2;
+    for (int q4 = tid; q4 < tot4; q4 += nthr) {
+      const int b0 = __ldg(tbl + 2 * q4), cs = __ldg(tbl + 2 * q4 + 1);
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 >= 0) {
+        const int nv = cs >> 28, st = cs & 0x0fffffff;  // valid columns of this float4 (1..4), column stride
+        w.x = __ldg(th + b0);
+        if (nv > 1) w.y = __ldg(th + b0 + st);
+        if (nv > 2) w.z = __ldg(th + b0 + 2 * st);
+        if (nv > 3) w.w = __ldg(th + b0 + 3 * st);
+      }
+      st4(sW + 4 * q4, w);
+    }
+    return;
+  }
   for (int l = 0; l < g.L; ++l) {
     const LayerGeom& y = g.layer[l];
     const int tot4 = (y.Kp * y.Np) >> 2;
@@ -436,7 +530,14 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
   const bool philox = prm.noise_mode == NOISE_PHILOX;
   const bool dw = prm.problem_id == PROBLEM_DW;
   const float kA = adaptive ? 0.f : 1.f;
-  for (int p = warp; p < P; p += nwarps) {
+  // G lanes per trajectory: a whole warp when the state needs it (or for the dense matvecs), else the smallest power of
+  // two that covers the d/4 groups, so that a warp advances 32/G trajectories at once (d = 10: 8 per warp instead of 1 with
+  // 3 live lanes).  The group sums below run over the same xor offsets as a full-warp sum whose other lanes hold zeros,
+  // so the results do not depend on G.
+  int G = 32;
+  if (!dense) while (G > 1 && (G >> 1) >= ngrp) G >>= 1;
+  const int ppw = 32 / G, gl = lane & (G - 1);
+  for (int p = warp * ppw + lane / G; p < P; p += nwarps * ppw) {
     float* zr = smem + sl.z + p * g.ldz;
     float* xr = smem + sl.act + p * g.lda;          // X starts at column 0
     float* er = smem + sl.xi + p * g.ldz;
@@ -448,7 +549,7 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
     const unsigned kglob = (unsigned)(prm.k_offset + tile * P + p);
     float zz = 0.f, zxi = 0.f, ff = 0.f, gg = 0.f, ul = 0.f;
     if (!dense) {
-      for (int jb = lane; jb < ngrp; jb += 32) {
+      for (int jb = gl; jb < ngrp; jb += G) {
         const int j0 = 4 * jb;
         const float4 z4 = ld4(zr + j0), x4 = ld4(xr + j0);
         float4 e4 = philox ? philox_normal4(kglob, (unsigned)n, (unsigned)jb, prm.offset, prm.seed) : ld4(er + j0);
@@ -556,10 +657,10 @@ __device__ __forceinline__ void sde_step(const RolloutParams& prm, const SmemLay
       // the float4 copy-back of the parked state covers whole groups: carry the t / 1 / pad columns along
       if (BWD) for (int i = d + lane; i < d4; i += 32) { zr[i] = xr[i]; er[i] = 0.f; }
     }
-    zz = warp_sum(zz); zxi = warp_sum(zxi); ff = warp_sum(ff);
-    if (last) gg = warp_sum(gg);
-    if (!BWD && prm.u_mode != 0) { ul = warp_sum(ul); if (lane == 0) sY[7 * P + p] += ul * dt; }
-    if (lane == 0) {
+    zz = group_sum(zz, G); zxi = group_sum(zxi, G); ff = group_sum(ff, G);
+    if (last) gg = group_sum(gg, G);
+    if (!BWD && prm.u_mode != 0) { ul = group_sum(ul, G); if (gl == 0) sY[7 * P + p] += ul * dt; }
+    if (gl == 0) {
       const float run = 0.5f * zz + ff;
       sY[p] += (run + (adaptive ? -zz : 0.f)) * dt + zxi * sq;
       sZs[p] += run * dt;
@@ -723,7 +824,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
 #pragma unroll
     for (int q = 0; q < 32; ++q) acc[q] = f2_zero();
   }
-  float* gp = BWD ? prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total : nullptr;
+  float* gp = BWD ? prm.grad_partial + (size_t)blockIdx.x * prm.n_img_total : nullptr;
   __syncthreads();
 
   for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
@@ -751,7 +852,7 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
       if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
       if (outer) {
         const int set = n_net < 0 ? 0 : (n_net >= prm.n_sets ? prm.n_sets - 1 : n_net);   // clamp like :352
-        stage_weights(g, prm.theta + (size_t)set * g.n_params, smem + sl.w, tid, T);
+        stage_weights(g, prm.theta + (size_t)set * g.n_params, smem + sl.w, tid, T, prm.th_tbl);
       }
       __syncthreads();
       pt_.mark(0);
@@ -764,7 +865,9 @@ __global__ void __launch_bounds__(T, 1) rollout_kernel(const RolloutParams prm) 
         net_backward_hidden<P>(prm, sl, smem, warp, lane, NW);
         pt_.mark(3);
         bw_accum<P>(acc, g, sl, smem, slot);
-        if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.n_params, lane);
+        pt_.mark(11);
+        if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.w_floats, lane);
+        pt_.mark(12);
         __syncthreads();
         pt_.mark(4);
         for (int q = tid; q < P * (d4 >> 2); q += T) {  // X_{n+1}: parked in sZ -> activation tile
@@ -866,7 +969,7 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
   const BwSlot slot = bw_slot(g, P, tid, T);
 #pragma unroll
   for (int q = 0; q < 32; ++q) acc[q] = f2_zero();
-  float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_theta_total;
+  float* gp = prm.grad_partial + (size_t)blockIdx.x * prm.n_img_total;
   float* ck = prm.x_ckpt + (size_t)blockIdx.x * N * P * d;
   __syncthreads();
 
@@ -891,7 +994,7 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
       if (inject) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);
-      if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
+      if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T, prm.th_tbl);
       __syncthreads();
       net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
       sde_step<P, false>(prm, sl, smem, tile, n, n == N - 1, warp, lane, NW);
@@ -953,7 +1056,7 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
       if (inject && per_path) stage_noise<P>(prm, tile, n, smem + sl.xi, tid, T);   // xi_{n+1} enters zeta through wY
-      if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T);
+      if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T, prm.th_tbl);
       __syncthreads();
       net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
       for (int p = warp; p < P; p += NW) {                          // zeta -> sXi
@@ -1005,7 +1108,7 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
         }
       }
       bw_accum<P>(acc, g, sl, smem, slot);
-      if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.n_params, lane);
+      if (outer) bw_flush(acc, g, slot, gp + (size_t)n * g.w_floats, lane);
       __syncthreads();
       for (int p = warp; p < P; p += NW) {                          // lambda_n
         const float* xr = sAct + p * g.lda;
@@ -1096,15 +1199,6 @@ static __global__ void adam_flat_kernel(int n, float* __restrict__ theta, const 
     m[i] = mi; v[i] = vi;
     const float denom = rn_add(rn_div(rn_sqrt(vi), sqrt_bc2), eps);
     theta[i] = rn_sub(theta[i], rn_mul(lr_over_bc1, rn_div(mi, denom)));
-  }
-}
-
-static __global__ void reduce_grad_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += (double)partial[(size_t)c * n + i];
-    out[i] = (float)s;
   }
 }
 
