@@ -292,10 +292,10 @@ __device__ __forceinline__ void gemm_nt(const float* __restrict__ dl, int ldl, c
 // (Interleaved, not contiguous chunks: neighbouring lanes then read neighbouring rows of the activation and cotangent tiles,
 // like the quarter-warps of gemm_nn; with contiguous chunks they sat P / cpb rows = a multiple of 32 banks apart and every
 // LDS.128 replayed cpb times -- 420 cycles per row at C1.)
-struct BwSlot { int b, p_lo, p_hi, cpb; };
+struct BwSlot { int b, p_lo, p_hi, cpb, l, kg, ng; };   // (l, kg, ng): layer and block coordinates of block b, found once
 
-__device__ __forceinline__ BwSlot bw_slot(const NetGeom& g, int P, int tid, int nthr) {
-  BwSlot s; s.b = -1; s.p_lo = 0; s.p_hi = P; s.cpb = 1;
+__device__ __forceinline__ BwSlot bw_slot_rows(const NetGeom& g, int P, int tid, int nthr) {
+  BwSlot s; s.b = -1; s.p_lo = 0; s.p_hi = P; s.cpb = 1; s.l = 0; s.kg = 0; s.ng = 0;
   const int nb = g.n_blocks;
   // small networks (fewer blocks than half the threads): split EVERY block's rows over cpb lanes, so that no warp walks
   // all P rows alone while the others idle (C1: 52 blocks, 256 threads -> 4 lanes x 16 rows per block)
@@ -317,16 +317,22 @@ __device__ __forceinline__ BwSlot bw_slot(const NetGeom& g, int P, int tid, int 
   return s;
 }
 
+__device__ __forceinline__ BwSlot bw_slot(const NetGeom& g, int P, int tid, int nthr) {
+  BwSlot s = bw_slot_rows(g, P, tid, nthr);
+  const int b = s.b < 0 ? 0 : s.b;      // (lanes without a block still walk through the flush shuffles of a row-split warp)
+  int l = 0;
+  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
+  s.l = l;
+  bw_block_coords(g.layer[l], b - g.layer[l].blk_begin, s.kg, s.ng);
+  return s;
+}
+
 template <int P>
 __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, const SmemLayout& sl,
                                          const float* smem, const BwSlot& slot) {
   if (slot.b < 0) return;
-  const int b = slot.b;
-  int l = 0;
-  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
+  const int l = slot.l, kg = slot.kg, ng = slot.ng;
   const LayerGeom& y = g.layer[l];
-  int kg, ng;
-  bw_block_coords(y, b - y.blk_begin, kg, ng);
   const bool last = (l == g.L - 1);
   const int ldd = last ? g.ldz : g.ldd;
   const int lda = g.lda;
@@ -385,12 +391,8 @@ static __device__ PSPDE_NOINLINE void bw_flush_quad(float v0, float v1, float v2
 __device__ __forceinline__ void bw_flush(f32x2 (&acc)[32], const NetGeom& g, const BwSlot& slot,
                                          float* __restrict__ gimg, int lane) {
   if (slot.cpb == 1 && slot.b < 0) return;      // whole warp idle or plain lane without a block
-  const int b = slot.b < 0 ? 0 : slot.b;
-  int l = 0;
-  while (l + 1 < g.L && b >= g.layer[l + 1].blk_begin) ++l;
-  const LayerGeom& y = g.layer[l];
-  int kg, ng;
-  bw_block_coords(y, b - y.blk_begin, kg, ng);
+  const LayerGeom& y = g.layer[slot.l];
+  const int kg = slot.kg, ng = slot.ng;
   const bool writer = slot.b >= 0 && (slot.cpb == 1 || (lane & (slot.cpb - 1)) == 0);
   const int nng = y.nng;
   const bool okn[2] = {writer, writer && ng + y.ngh < nng};
@@ -759,7 +761,7 @@ __device__ __forceinline__ void net_backward_hidden(const RolloutParams& prm, co
         const int i = col - seg_lo;
         if (i < seg_n) {
           const float h = sAct[p * lda + col];
-          v *= (kind == NET_DENSENET) ? 2.0f * sqrtf(h) : (1.0f - h * h);
+          v *= (kind == NET_DENSENET) ? 2.0f * sqrt_fast(h) : (1.0f - h * h);
         } else v = 0.f;
       }
       *o = v;
