@@ -112,6 +112,33 @@ def test_philox_multi_tile_vs_oracle(run):
                                rtol=1e-12)
 
 
+def test_outer_multi_tile_vs_oracle(run):
+    """'outer' mode (one parameter set per step) over several tiles per CTA: the per-step weight staging through the index
+    table, the weight-image gradient partials that a CTA revisits for every one of its tiles, the row-split gradient
+    blocks of a small network and the several-trajectories-per-warp SDE step (d = 10 -> 4 lanes per trajectory)."""
+    g = load_golden("hjb_lqgc_d10_outer_lv")
+    d, N, dt = g["d"], 5, 0.05
+    K = 64 * 4 * 2 + 17           # 9 tiles over the emulator's 4 "SMs", last tile ragged
+    n_par = g["theta"].size // g["N"]
+    g = dict(g, N=N)
+    theta = g["theta"][:N * n_par].astype(np.float32)
+    cfg, pack, x0 = H.cfg_from_golden(g, noise=L.NOISE_PHILOX, K=K, seed=4242, offset=1)
+    o = run.fwd(cfg, theta, pack, x0)
+    rng = np.random.default_rng(11)
+    wY, wZ = rng.standard_normal(K), rng.standard_normal(K)
+    grad = run.bwd(cfg, theta, pack, x0, wY, wZ)
+    assert grad.shape == (N * n_par,) and np.isfinite(grad).all()
+    xi = ph.xi_tensor(4242, 1, 0, K, d, N).astype(np.float64)
+    nets = [man.Net("densenet", [d, 30, 30, d], theta[n * n_par:(n + 1) * n_par]) for n in range(N)]
+    prob = man.Problem("lqgc", d)
+    gm, ro = man.grad_mode_a(prob, nets, xi, dt, N, np.zeros(d), wY, wZ, True, "none")
+    assert relerr(o["X"], ro["X"]) < 1e-5 and relerr(o["Y"], ro["Y"]) < 1e-5 and relerr(o["Zsum"], ro["Zsum"]) < 1e-5
+    assert relerr(grad, gm) < 2e-5
+    # every step's block of the gradient is populated (a flush into the wrong slice would leave zeros / double counts)
+    per_step = np.abs(grad.reshape(N, n_par)).sum(axis=1)
+    assert (per_step > 0).all()
+
+
 def test_philox_dump_matches_oracle_and_kernel(run):
     lib = run.lib
     K, d, N = 70, 10, 4

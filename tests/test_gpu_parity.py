@@ -125,6 +125,37 @@ def test_philox_dump_and_rollout_vs_oracle():
     assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
 
 
+def test_outer_mode_more_tiles_than_sms_vs_oracle():
+    """'outer' mode (one network per time step, the reference's default) with more 64-path tiles than SMs, so that every
+    CTA revisits its weight-image gradient slices: states and the per-step gradient blocks against the numpy oracle on the
+    same Philox increments."""
+    from oracle import manual as man, philox as ph
+    from pspde.fused import Call
+    g = load_golden("hjb_lqgc_d10_outer_lv")
+    d, N, dt = g["d"], g["N"], g["delta_t"]
+    K = 64 * 148 * 2 + 64 * 5 + 17
+    S = make_solver(dict(g, tag="outer"), K=K, noise="philox", seed=99)
+    eng = S._get_engine()
+    theta = S._theta.detach()
+    eng.forward(theta, None, Call(offset=2))
+    rng = np.random.default_rng(3)
+    wY, wZ = rng.standard_normal(K) / K, rng.standard_normal(K) / K
+    grad = pt.full((eng.n_theta,), float("nan"), device="cuda")
+    eng.backward_detached(theta, pt.tensor(wY, device="cuda", dtype=pt.float32), pt.tensor(wZ, device="cuda", dtype=pt.float32),
+                          Call(offset=2), grad)
+    n_par = eng.n_theta // N
+    th = theta.cpu().numpy()
+    nets = [man.Net("densenet", [d, 30, 30, d], th[n * n_par:(n + 1) * n_par]) for n in range(N)]
+    xi = ph.xi_tensor(99, 2, 0, K, d, N).astype(np.float64)
+    gm, ro = man.grad_mode_a(man.Problem("lqgc", d), nets, xi, dt, N, np.zeros(d), wY.astype(np.float32).astype(np.float64),
+                             wZ.astype(np.float32).astype(np.float64), True, "none")
+    assert relerr(eng.X_N.cpu().numpy(), ro["X"]) < TOL and relerr(eng.Y_N.cpu().numpy(), ro["Y"]) < TOL
+    gk = grad.cpu().numpy()
+    assert np.isfinite(gk).all()
+    for n in range(N):       # per step: a flush into the wrong slice would show as one bad block, not as a small global error
+        assert relerr(gk[n * n_par:(n + 1) * n_par], gm[n * n_par:(n + 1) * n_par]) < 5 * TOL, n
+
+
 def test_sharding_invariance_single_gpu():
     """Splitting K into two shards (k_offset) gives the same per-path results and the same summed gradient."""
     import pspde
