@@ -1044,16 +1044,54 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
     // ---------------- backward sweep (same warp-per-row mapping for every lambda update: no barrier needed
     //                  between the end of one iteration and the start of the next)
     for (int n = N - 1; n >= 0; --n) {
-      for (int p = warp; p < P; p += NW) {
-        const float wf = swY[p] + swZ[p];
-        const bool live = swY[p] != 0.f || swZ[p] != 0.f || swG[p] != 0.f;
-        float* xr = sAct + p * g.lda;
-        float* lr = sLam + p * g.ldz;
-        for (int j = lane; j < d; j += 32) {
-          if (live) {
-            lr[j] += wf * dt * 2.0f * p_d[j] * xr[j];              // grad f at X_{n+1} (f = x'Px, P diagonal)
-            xr[j] = ck[(size_t)n * P * d + p * d + j];             // reload X_n
-          } else { lr[j] = 0.f; xr[j] = 0.f; }                     // inert row: finite state, zero adjoint
+      // reload X_n: the checkpoint loads of four of the warp's rows are issued together (one exposed global-memory latency
+      // per batch instead of one per row: the row-by-row form was 10 % of the kernel's stall samples at the C3 shape)
+      if (d <= 128) {
+        const float* ckn = ck + (size_t)n * P * d;
+        for (int p0 = warp; p0 < P; p0 += 4 * NW) {
+          float xv[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * NW;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int j = lane + 32 * c;
+              xv[u][c] = (p < P && j < d) ? ckn[p * d + j] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int p = p0 + u * NW;
+            if (p < P) {
+              const float wf = swY[p] + swZ[p];
+              const bool live = swY[p] != 0.f || swZ[p] != 0.f || swG[p] != 0.f;
+              float* xr = sAct + p * g.lda;
+              float* lr = sLam + p * g.ldz;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int j = lane + 32 * c;
+                if (j < d) {
+                  if (live) {
+                    lr[j] += wf * dt * 2.0f * p_d[j] * xr[j];      // grad f at X_{n+1} (f = x'Px, P diagonal)
+                    xr[j] = xv[u][c];                              // X_n
+                  } else { lr[j] = 0.f; xr[j] = 0.f; }             // inert row: finite state, zero adjoint
+                }
+              }
+            }
+          }
+        }
+      } else {
+        for (int p = warp; p < P; p += NW) {
+          const float wf = swY[p] + swZ[p];
+          const bool live = swY[p] != 0.f || swZ[p] != 0.f || swG[p] != 0.f;
+          float* xr = sAct + p * g.lda;
+          float* lr = sLam + p * g.ldz;
+          for (int j = lane; j < d; j += 32) {
+            if (live) {
+              lr[j] += wf * dt * 2.0f * p_d[j] * xr[j];
+              xr[j] = ck[(size_t)n * P * d + p * d + j];
+            } else { lr[j] = 0.f; xr[j] = 0.f; }
+          }
         }
       }
       if (g.t_col >= 0) for (int p = tid; p < P; p += T) sAct[p * g.lda + g.t_col] = (float)n * dt;
