@@ -363,6 +363,15 @@ __device__ __forceinline__ void bw_accum(f32x2 (&acc)[32], const NetGeom& g, con
 #define PSPDE_NOINLINE __noinline__
 #endif
 
+// p[0..3] += v (16-byte aligned global address), fire-and-forget: one RED.128 instead of a load-add-store round trip
+__device__ __forceinline__ void red_add4(float* p, float v0, float v1, float v2, float v3) {
+#if defined(PSPDE_EMULATE)
+  p[0] += v0; p[1] += v1; p[2] += v2; p[3] += v3;
+#else
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+#endif
+}
+
 // One float4 (4 neighbouring columns of one row) of a weight-gradient block: combine the row-split lanes (fixed order), then
 // add it into the CTA's private slice with ONE 16-byte RED (one writer per element and program order per address, so the
 // sums stay bitwise deterministic).  The slice is in weight-image layout, so the float4 is aligned; in theta layout the same
@@ -377,13 +386,7 @@ static __device__ PSPDE_NOINLINE void bw_flush_quad(float v0, float v1, float v2
     v2 += __shfl_xor_sync(0xffffffffu, v2, o);
     v3 += __shfl_xor_sync(0xffffffffu, v3, o);
   }
-  if (write) {
-#if defined(PSPDE_EMULATE)
-    p[0] += v0; p[1] += v1; p[2] += v2; p[3] += v3;
-#else
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-#endif
-  }
+  if (write) red_add4(p, v0, v1, v2, v3);
 }
 
 // acc -> grad_partial (this CTA's private slice, weight-image layout), then clear.  Must be called by all lanes of a warp
