@@ -124,6 +124,13 @@ PSPDE_HD inline int dw_partial_floats(const NetGeom& g) { return ((g.n_blocks + 
 PSPDE_HD inline int dw_partial_index(int b, int e4) { return (((b >> 5) * 16 + e4) * 32 + (b & 31)) * 4; }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float div_fast(float a, float b) {
+#if defined(PSPDE_EMULATE)
+  return a / b;
+#else
+  return __fdividef(a, b);
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------ forward GEMM
 // pre[r][4ni..4ni+3] = sum_k act[r][k] W[k][4ni..]; thread tile = R strided rows x 4 columns; rows r and r + R/2 of
@@ -493,8 +500,8 @@ __global__ void __launch_bounds__(T, 1) diffusion_kernel(const DiffusionParams p
           auto epi = [&](int rv, int col, float gv, float gt) {
             float* hv = sAct + rv * lda + col;
             float* ht = hv + P * lda;
-            const float s = sqrtf(*hv);                        // relu(p); h'' p' = 2 [p > 0] p' = h' / relu(p)
-            const float dv = gv * (2.0f * s) + (s > 0.f ? gt * (*ht / s) : 0.f);
+            const float s = sqrt_fast(*hv);                    // relu(p); h'' p' = 2 [p > 0] p' = h' / relu(p)
+            const float dv = gv * (2.0f * s) + (s > 0.f ? gt * div_fast(*ht, s) : 0.f);   // (approx sqrt / div: ~2 ulp, no slow paths)
             const float dd = gt * (2.0f * s);
             *hv = dv;
             *ht = dd;
