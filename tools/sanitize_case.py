@@ -1,6 +1,8 @@
 """Small workload for compute-sanitizer (memcheck / racecheck): the tcgen05 kernels that have no emulator coverage --
 rollout_tc_fwd_kernel (plain, DIAG and row-keeping instantiations) and grad_tc_kernel (single-rollout and wave-checkpointed
-launches) -- on the C2 network shape at a few tiles, checked against the FMA kernels in the same run."""
+launches) -- on the C2 network shape at a few tiles, checked against the FMA kernels in the same run; then the FMA kernels in
+the forms that use the index table and the RED.128 flushes: 'outer' mode (C1 shape, several tiles), the attached kernel
+(relative entropy) and the diffusion kernels (small C4-like case)."""
 import os
 import sys
 
@@ -39,3 +41,24 @@ for mode in ("single", "waves"):
     assert err < 1e-5
 S.train_step(0)
 print("train_step ok, loss %.6e u_L2 %.6e" % (S.loss_log[-1], S.u_L2_loss[-1]))
+
+# ---- FP32-FMA kernels: 'outer' mode over several tiles, attached kernel, diffusion kernels (bench.py workloads, small K)
+import bench  # noqa: E402
+for name, K2 in (("c1", 64 * 5 + 9), ("c3re", 64 * 3 + 5)):
+    wl = dict(bench.WORKLOADS[name])
+    if name == "c3re":
+        wl["dt"] = 0.02          # N = 50 (explicit Euler on the double well is unstable at 0.1)
+    S2 = bench.build_solver(wl, K2, pt.device("cuda", 0), name="san_" + name)
+    for it in range(2):
+        S2.train_step(it)
+    pt.cuda.synchronize()
+    print(name, "train_step ok, loss %.6e" % S2.loss_log[-1])
+wl = dict(bench.WORKLOADS["c4"])
+dev = pt.device("cuda", 0)
+G = pspde.GeneralSolver(pspde.HeatEquation(device=dev, **wl["pkw"]), "san_c4", seed=42, delta_t=wl["dt"], N=4, lr=wl["lr"], L=1,
+                        K=300, K_boundary=wl["K_boundary"], verbose=False, device=dev)
+G.V = pspde.DenseNet(d_in=wl["pkw"]["d"] + 1, d_out=1, lr=wl["lr"], arch=wl["arch"], seed=42)
+for it in range(2):
+    G.train_step(it)
+pt.cuda.synchronize()
+print("c4 train_step ok, loss %.6e" % G.loss_log[-1])
