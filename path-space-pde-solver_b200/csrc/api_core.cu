@@ -11,8 +11,8 @@ std::atomic<unsigned long long> g_launches{0};
 unsigned long long* g_prof = nullptr;
 
 // Index table of the shared weight image for the FP32-FMA kernels in 'outer' mode (RolloutParams::th_tbl): built on the host
-// once per (device, network geometry), kept for the life of the process (at most 32 geometries; nullptr beyond that or on an
-// allocation failure = the kernels fall back to theta_index()).
+// once per (device, network geometry) and cached (32 entries; a 33rd geometry evicts the oldest one -- cudaFree waits for the
+// kernels that may still read it).  nullptr = allocation failure, reported by the launchers of the gradient kernels.
 const int* pspde_theta_table(const NetGeom& g) {
   struct Entry { int dev, kind, L, time_mode, d, dims[PSPDE_MAXL + 1]; int* tbl; };
   static Entry cache[32];
@@ -29,7 +29,17 @@ const int* pspde_theta_table(const NetGeom& g) {
     for (int l = 0; same && l <= g.L; ++l) same = e.dims[l] == g.dims[l];
     if (same) return e.tbl;
   }
-  if (n_cache == 32) return nullptr;
+  static int n_evict = 0;
+  int slot = n_cache;
+  if (n_cache == 32) {
+    slot = n_evict++ % 32;
+#if defined(PSPDE_EMULATE)
+    free(cache[slot].tbl);
+#else
+    cudaFree(cache[slot].tbl);
+#endif
+    cache[slot].tbl = nullptr; cache[slot].dev = -1;
+  }
   const size_t n = 2 * (size_t)(g.w_floats >> 2);
   int* host = static_cast<int*>(malloc(n * sizeof(int)));
   if (!host) return nullptr;
@@ -48,7 +58,8 @@ const int* pspde_theta_table(const NetGeom& g) {
   Entry e;
   e.dev = dev; e.kind = g.kind; e.L = g.L; e.time_mode = g.time_mode; e.d = g.d; e.tbl = tbl;
   for (int l = 0; l <= PSPDE_MAXL; ++l) e.dims[l] = l <= g.L ? g.dims[l] : 0;
-  cache[n_cache++] = e;
+  cache[slot] = e;
+  if (slot == n_cache) ++n_cache;
   return tbl;
 }
 

@@ -139,6 +139,27 @@ def test_outer_multi_tile_vs_oracle(run):
     assert (per_step > 0).all()
 
 
+def test_index_table_cache_survives_many_geometries(run):
+    """The weight-image index table is cached per network geometry (32 entries, oldest evicted): 40 different networks in one
+    process, then the first one again, all against the numpy oracle."""
+    d, K, N, dt = 4, 21, 2, 0.1
+    pid, flags, pack = H.problem_pack("lqgc", d, {})
+    x0 = np.zeros(d, np.float32)
+    rng = np.random.default_rng(0)
+    wY = rng.standard_normal(K)
+    for h in list(range(3, 43)) + [3]:
+        dims = [d + 1, h, h + 1, d]
+        cfg = L.make_cfg(K, d, N, np.float32(dt), pid, L.NET_DENSENET, dims, L.TIME_FIRST, problem_flags=flags,
+                         noise_mode=L.NOISE_PHILOX, seed=5, offset=0)
+        n_theta = run.lib.pspde_theta_size(ctypes.byref(cfg))
+        theta = (0.3 * np.random.default_rng(h).standard_normal(n_theta)).astype(np.float32)
+        grad = run.bwd(cfg, theta, pack, x0, wY, None)
+        net = man.Net("densenet", dims, theta)
+        xi = ph.xi_tensor(5, 0, 0, K, d, N).astype(np.float64)
+        gm, _ = man.grad_mode_a(man.Problem("lqgc", d), net, xi, dt, N, np.zeros(d), wY, np.zeros(K), True, "first")
+        assert relerr(grad, gm) < 2e-5, h
+
+
 def test_philox_dump_matches_oracle_and_kernel(run):
     lib = run.lib
     K, d, N = 70, 10, 4
