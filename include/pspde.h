@@ -7,7 +7,10 @@
  *
  * Conventions
  *   - plain C, plain pointers and sizes; no torch types.  All buffer arguments of the device entry points
- *     are DEVICE pointers owned by the caller; the library allocates nothing persistent.
+ *     are DEVICE pointers owned by the caller.  `workspace` and `ckpt` buffers must be at least 16-byte aligned (checked; cudaMalloc
+ *     and the torch allocator return 256 / 512): the kernels address them with 16-byte vector accesses and TMA.  The library keeps only
+ *     two small caches of its own on the device (a packed weight image per stream that launched a tensor-core rollout, an
+ *     index table per network geometry; INTEGRATION.md, "Ownership").
  *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no host synchronisation,
  *     re-entrant per device, one process per GPU.  The *_host entry point is the exception (documented there).
  *   - return value 0 = ok; negative = error, message via pspde_last_error() (thread local).  Never throws.

@@ -2,6 +2,7 @@
 #pragma once
 #include <atomic>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,6 +68,7 @@ struct Plan {
 };
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+static inline bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }   // float4 / RED.128 accesses
 
 static inline int validate(const pspde_cfg* c) {
   if (!c) return fail(-1, "cfg is NULL");

@@ -396,6 +396,7 @@ int pspde_rollout_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const float
   if (!theta || !prob || !x0) return fail(-1, "theta/prob/x0 must not be NULL");
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
   if (!workspace || workspace_bytes < pl.stats_bytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi;
@@ -427,6 +428,7 @@ int pspde_rollout_bwd_detached(const pspde_cfg* cfg, const float* theta, const f
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
   if (!workspace || workspace_bytes < pl.stats_bytes + pl.grad_bytes)
     return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.grad_bytes);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY; p.wZ = wZ;
@@ -480,6 +482,7 @@ int pspde_grad_from_ckpt(const pspde_cfg* cfg, const float* theta, const float* 
   const int grid = n_ts < sms ? (int)n_ts : sms;
   const size_t gbytes = align256((size_t)grid * grad_part_floats(cfg, pl, s0) * sizeof(float));
   if (!workspace || workspace_bytes < pl.stats_bytes + gbytes) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + gbytes);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta;
@@ -524,6 +527,7 @@ int pspde_grad_from_fwd_ckpt(const pspde_cfg* cfg, const float* theta, const flo
     ws_need = pl.stats_bytes + cp.grad_bytes + cp.ckpt_bytes;
   }
   if (!workspace || workspace_bytes < ws_need) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, ws_need);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi; p.wY = wY;
@@ -572,6 +576,7 @@ int pspde_rollout_attached_diag(const pspde_cfg* cfg, const float* theta, const 
   const size_t ckpt_bytes = align256((size_t)pl.grid * cfg->N * kP * cfg->d * sizeof(float));
   if (!workspace || workspace_bytes < pl.stats_bytes + pl.grad_bytes + ckpt_bytes)
     return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.grad_bytes + ckpt_bytes);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.y0 = y0; p.xi = xi; p.w_attached = w;
@@ -607,6 +612,7 @@ int pspde_importance_sampling(const pspde_cfg* cfg, const float* theta, const fl
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && !xi) return fail(-1, "noise_mode INJECT needs xi");
   if (t_index && !(dt_net > 0.f)) return fail(-2, "dt_net must be > 0 when t_index is given");
   if (!workspace || workspace_bytes < pl.stats_bytes) return fail(-7, "workspace too small");
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   RolloutParams p;
   fill_params(cfg, pl, p);
   p.theta = theta; p.prob = prob; p.x0 = x0; p.xi = xi;

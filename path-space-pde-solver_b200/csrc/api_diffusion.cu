@@ -117,6 +117,7 @@ static int diffusion_fwd_impl(const pspde_cfg* cfg, float T_end, const pspde_ell
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && cfg->N > 0 && !xi) return fail(-1, "noise_mode INJECT needs xi");
   if (!workspace || workspace_bytes < pl.stats_bytes + pl.wpack_bytes)
     return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, pl.stats_bytes + pl.wpack_bytes);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   char* ws = reinterpret_cast<char*>(workspace);
   float* wpack = reinterpret_cast<float*>(ws + pl.stats_bytes);
   rc = pack_weights(pl, theta, wpack, stream);
@@ -148,6 +149,7 @@ static int diffusion_bwd_impl(const pspde_cfg* cfg, float T_end, const pspde_ell
   if (cfg->noise_mode == PSPDE_NOISE_INJECT && cfg->N > 0 && !xi) return fail(-1, "noise_mode INJECT needs xi");
   const size_t need = pl.stats_bytes + pl.wpack_bytes + pl.grad_bytes;
   if (!workspace || workspace_bytes < need) return fail(-7, "workspace too small (%zu < %zu)", workspace_bytes, need);
+  if (misaligned16(workspace)) return fail(-7, "workspace must be 16-byte aligned");
   char* ws = reinterpret_cast<char*>(workspace);
   float* wpack = reinterpret_cast<float*>(ws + pl.stats_bytes);
   rc = pack_weights(pl, theta, wpack, stream);

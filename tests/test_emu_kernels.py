@@ -160,6 +160,24 @@ def test_index_table_cache_survives_many_geometries(run):
         assert relerr(grad, gm) < 2e-5, h
 
 
+def test_misaligned_workspace_is_rejected(run):
+    """The kernels address the workspace with 16-byte vector accesses: a misaligned pointer is an error, not a fault."""
+    g = load_golden("hjb_lqgc_d10_dense_lv")
+    cfg, pack, x0 = H.cfg_from_golden(dict(g, N=2), noise=L.NOISE_PHILOX, K=9, seed=1)
+    theta = g["theta"].astype(np.float32)
+    lib = run.lib
+    ws = np.zeros(lib.pspde_workspace_bytes(ctypes.byref(cfg)) // 8 + 4, np.float64)
+    grad = np.zeros(lib.pspde_theta_size(ctypes.byref(cfg)), np.float32)
+    wY = np.ones(9, np.float32)
+    base = ws.ctypes.data + (-ws.ctypes.data) % 16
+    rc = lib.pspde_rollout_bwd_detached(ctypes.byref(cfg), H.ptr(theta), H.ptr(pack), H.ptr(x0), None, H.ptr(wY), None,
+                                        H.ptr(grad), ctypes.c_void_p(base + 4), ws.nbytes - 24, None)
+    assert rc == -7 and b"aligned" in lib.pspde_last_error()
+    rc = lib.pspde_rollout_bwd_detached(ctypes.byref(cfg), H.ptr(theta), H.ptr(pack), H.ptr(x0), None, H.ptr(wY), None,
+                                        H.ptr(grad), ctypes.c_void_p(base), ws.nbytes - 24, None)
+    assert rc == 0, lib.pspde_last_error()
+
+
 def test_philox_dump_matches_oracle_and_kernel(run):
     lib = run.lib
     K, d, N = 70, 10, 4
