@@ -1102,13 +1102,17 @@ __global__ void __launch_bounds__(T, MINB) rollout_attached_kernel(const Rollout
       if (outer) stage_weights(g, prm.theta + (size_t)n * g.n_params, smem + sl.w, tid, T, prm.th_tbl);
       __syncthreads();
       net_forward<P, 4>(prm, sl, smem, warp, lane, NW);
-      for (int p = warp; p < P; p += NW) {                          // zeta -> sXi
+      // zeta -> sXi: no cross-lane sums here, so the (row, 4-column group) pairs are simply dealt out to all threads (a warp
+      // per row left 19 of 32 lanes idle at d = 50 and walked its 8 rows one after the other)
+      const int ngrp_z = (d + 3) >> 2;
+      for (int q = tid; q < P * ngrp_z; q += T) {
+        const int p = q / ngrp_z, jb = q - p * ngrp_z;
         const float wy = swY[p], wz = swZ[p];
         const float* zr = smem + sl.z + p * g.ldz;
         const float* lr = sLam + p * g.ldz;
         float* er = smem + sl.xi + p * g.ldz;
         const unsigned kglob = (unsigned)(prm.k_offset + tile * P + p);
-        for (int jb = lane; 4 * jb < d; jb += 32) {
+        {
           float e4[4] = {0.f, 0.f, 0.f, 0.f};
           if (wy != 0.f) {
             if (inject) { const float4 t4 = ld4(er + 4 * jb); e4[0] = t4.x; e4[1] = t4.y; e4[2] = t4.z; e4[3] = t4.w; }
