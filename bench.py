@@ -132,7 +132,7 @@ def _print_reference(args, wl, times, K_cpu, N, cores):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -258,8 +258,6 @@ class Rig:
         pt.cuda.set_device(self.local)
         self.dev = pt.device("cuda", self.local)
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner to stdout,
-                os.environ["NCCL_DEBUG"] = "WARN"                           # in front of the one JSON line
             td.init_process_group("nccl", device_id=self.dev)
         self.flush = pt.empty(256 << 20, dtype=pt.uint8, device=self.dev)     # > 126 MB L2
 
@@ -671,7 +669,7 @@ def run_ours(args, wl):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "final_loss": final_loss}
     line.update(extra)
-    print(json.dumps(line))
+    emit(line)
     rig.close()
 
 
@@ -800,12 +798,33 @@ def run_ours_c4(args, wl):
                            "pinned host memory and (loss, K_count) read back every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "final_loss": G.loss_log[-1]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         td.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner comes out of a plain printf
+    whenever NCCL_DEBUG is VERSION or WARN, whatever NCCL_DEBUG_FILE says): keep a private handle on the real stdout for the
+    JSON line and point file descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
