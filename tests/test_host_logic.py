@@ -350,3 +350,22 @@ def test_general_solver_inject_draws_follow_the_reference_break():
         stopped = stopped | (~ns & ~stopped)
     assert n_draws < G.N and pt.equal(after, pt.rand(1))           # same position in the RNG stream afterwards
     assert pt.equal(xis[:n_draws], pt.stack(ref)) and bool((xis[n_draws:] == 0).all()) and xis.shape == (G.N, G.K, G.d)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (everything else goes to stderr); the reference arm runs on the CPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1, out.stdout[:500]
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
