@@ -178,6 +178,25 @@ def test_misaligned_workspace_is_rejected(run):
     assert rc == 0, lib.pspde_last_error()
 
 
+@pytest.mark.parametrize("d", [20, 132])
+def test_attached_kernel_wide_state_vs_oracle(run, d):
+    """Attached (relative-entropy) kernel against the numpy discrete adjoint at a state wider than 128 columns -- the backward
+    sweep reloads its checkpointed rows four at a time only up to d = 128 and row by row beyond -- and at a narrow one."""
+    K, N, dt = 70, 3, 0.05          # two tiles, the second ragged
+    pid, flags, pack = H.problem_pack("lqgc", d, {})
+    dims = [d + 1, 6, 5, d]         # (tanh MLP: a DenseNet's last layer alone would not fit shared memory at d = 132)
+    cfg = L.make_cfg(K, d, N, np.float32(dt), pid, L.NET_MLP_TANH, dims, L.TIME_FIRST, problem_flags=flags,
+                     noise_mode=L.NOISE_PHILOX, seed=21, offset=4)
+    n_theta = run.lib.pspde_theta_size(ctypes.byref(cfg))
+    theta = (0.1 * np.random.default_rng(d).standard_normal(n_theta)).astype(np.float32)
+    x0 = np.zeros(d, np.float32)
+    o = run.attached(cfg, theta, pack, x0, 1.0 / K)
+    xi = ph.xi_tensor(21, 4, 0, K, d, N).astype(np.float64)
+    gm, ro = man.grad_mode_b(man.Problem("lqgc", d), man.Net("mlp_tanh", dims, theta), xi, dt, N, np.zeros(d), "first")
+    assert relerr(o["X"], ro["X"]) < 1e-5 and relerr(o["Zsum"], ro["Zsum"]) < 1e-5
+    assert relerr(o["grad"], gm) < 2e-5
+
+
 def test_philox_dump_matches_oracle_and_kernel(run):
     lib = run.lib
     K, d, N = 70, 10, 4
