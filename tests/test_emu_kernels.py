@@ -197,6 +197,28 @@ def test_attached_kernel_wide_state_vs_oracle(run, d):
     assert relerr(o["grad"], gm) < 2e-5
 
 
+@pytest.mark.parametrize("d", [1, 2, 5, 9, 17, 33, 65])
+def test_sde_step_lane_groups_vs_oracle(run, d):
+    """The SDE step gives each trajectory G = 1, 2, 4, ... 32 lanes depending on d (several trajectories per warp for small
+    d): forward states and the detached gradient against the numpy oracle for one d per group size, ragged last tile."""
+    K, N, dt = 64 + 37, 3, 0.05
+    pid, flags, pack = H.problem_pack("lqgc", d, {})
+    dims = [d + 1, 7, 6, d]
+    cfg = L.make_cfg(K, d, N, np.float32(dt), pid, L.NET_DENSENET, dims, L.TIME_FIRST, problem_flags=flags,
+                     noise_mode=L.NOISE_PHILOX, seed=8, offset=2)
+    n_theta = run.lib.pspde_theta_size(ctypes.byref(cfg))
+    theta = (0.2 * np.random.default_rng(100 + d).standard_normal(n_theta)).astype(np.float32)
+    x0 = np.zeros(d, np.float32)
+    o = run.fwd(cfg, theta, pack, x0)
+    rng = np.random.default_rng(d)
+    wY, wZ = rng.standard_normal(K), rng.standard_normal(K)
+    grad = run.bwd(cfg, theta, pack, x0, wY, wZ)
+    xi = ph.xi_tensor(8, 2, 0, K, d, N).astype(np.float64)
+    gm, ro = man.grad_mode_a(man.Problem("lqgc", d), man.Net("densenet", dims, theta), xi, dt, N, np.zeros(d), wY, wZ, True, "first")
+    assert relerr(o["X"], ro["X"]) < 1e-5 and relerr(o["Y"], ro["Y"]) < 1e-5 and relerr(o["Zsum"], ro["Zsum"]) < 1e-5
+    assert relerr(grad, gm) < 2e-5
+
+
 def test_philox_dump_matches_oracle_and_kernel(run):
     lib = run.lib
     K, d, N = 70, 10, 4
